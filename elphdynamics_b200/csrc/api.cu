@@ -1,0 +1,749 @@
+// extern "C" entry points of libelph_b200.so (see include/elph_b200.h).
+// Host-buffer entry points copy in, convert between the reference host layout
+// (tau fastest) and the engine layout ([tau][site]) on the device, run the
+// device path and copy out.  There is no CPU implementation of any operator here.
+#include "elph_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+std::string& elph_global_error() {
+    static thread_local std::string e;
+    return e;
+}
+
+void elph_lincomb(elph_handle* h, double* out, double a, const double* X, double b, const double* Y, double c, const double* Z,
+                  int64_t n);
+void elph_langevin_step_dev(elph_handle* h, int method, double dt, const double* eta_dev, const double* g1_dev,
+                            const double* g2_dev, const double* arn1, const double* arn2, bool use_precond, int64_t* iters,
+                            elph_solve_info* info1, elph_solve_info* info2);
+std::vector<std::complex<double>> elph_debug_hess_eig(const std::vector<double>& h, int n);
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (dev != prev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != prev && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+void up(T*& dst, const std::vector<T>& src) {
+    dst = elph_dalloc<T>(src.size());
+    if (!src.empty()) ELPH_CUDA(cudaMemcpy(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+
+double* zeros(size_t n) {
+    double* p = elph_dalloc<double>(n);
+    ELPH_CUDA(cudaMemset(p, 0, (n ? n : 1) * sizeof(double)));
+    return p;
+}
+
+// grow-only staging area (device, host layout) for the host-buffer entry points
+double* stage(elph_handle* h, int slot, size_t ndoubles) {
+    if (h->stage_cap[slot] < ndoubles) {
+        if (h->d_stage[slot]) ELPH_CUDA(cudaFree(h->d_stage[slot]));
+        h->d_stage[slot] = elph_dalloc<double>(ndoubles);
+        h->stage_cap[slot] = ndoubles;
+    }
+    return h->d_stage[slot];
+}
+
+// host vector (host layout, ncols columns of length L) -> engine buffer
+void upload_vec(elph_handle* h, const double* host, double* engine_dev, int ncols, int64_t nbatch = 1) {
+    ELPH_REQUIRE(host != nullptr, ELPH_ERR_INVALID, "null host input pointer");
+    const size_t n = (size_t)ncols * h->L * nbatch;
+    double* st = stage(h, 0, n);
+    ELPH_CUDA(cudaMemcpyAsync(st, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    elph_to_engine(h, st, engine_dev, ncols, nbatch);
+}
+
+void download_vec(elph_handle* h, const double* engine_dev, double* host, int ncols, int64_t nbatch = 1) {
+    ELPH_REQUIRE(host != nullptr, ELPH_ERR_INVALID, "null host output pointer");
+    const size_t n = (size_t)ncols * h->L * nbatch;
+    double* st = stage(h, 1, n);
+    elph_from_engine(h, engine_dev, st, ncols, nbatch);
+    ELPH_CUDA(cudaMemcpyAsync(host, st, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ELPH_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void build(elph_handle* h, const elph_config* c) {
+    ELPH_REQUIRE(c->model == ELPH_MODEL_HOLSTEIN || c->model == ELPH_MODEL_SSH, ELPH_ERR_INVALID, "unknown model kind");
+    ELPH_REQUIRE(c->index_base == 0 || c->index_base == 1, ELPH_ERR_INVALID, "index_base must be 0 or 1");
+    ELPH_REQUIRE(c->Ltau >= 1 && c->Nsites >= 1 && c->Nbonds >= 0 && c->Nph >= 0, ELPH_ERR_INVALID, "bad dimensions");
+    ELPH_REQUIRE(c->Ltau < (1 << 24) && c->Nsites < (1 << 24) && c->Nbonds < (1LL << 30), ELPH_ERR_INVALID, "dimensions too large");
+    ELPH_REQUIRE(c->dtau > 0.0, ELPH_ERR_INVALID, "dtau must be positive");
+    ELPH_REQUIRE(c->Nbonds == 0 || c->neighbor_table, ELPH_ERR_INVALID, "neighbor_table is NULL");
+    ELPH_REQUIRE(c->mu, ELPH_ERR_INVALID, "mu is NULL");
+    h->model = c->model;
+    h->L = (int)c->Ltau;
+    h->N = (int)c->Nsites;
+    h->Nb = (int)c->Nbonds;
+    h->Nph = (int)c->Nph;
+    if (h->model == ELPH_MODEL_HOLSTEIN) ELPH_REQUIRE(c->Nph == c->Nsites, ELPH_ERR_INVALID, "Holstein: Nph must equal Nsites");
+    h->Ndim = (int64_t)h->N * h->L;
+    h->Ndof = (int64_t)h->Nph * h->L;
+    h->dtau = c->dtau;
+    h->cg_tol = c->cg_tol > 0 ? c->cg_tol : 1e-4;
+    h->cg_maxiter = c->cg_maxiter >= 1 ? c->cg_maxiter : h->Ndim;  // ConjugateGradient(): maxiter<1 -> N (:47-49)
+    h->cg_kappa_max = c->cg_kappa_max > 0 ? c->cg_kappa_max : 1e12;
+
+    int dev = c->device;
+    if (dev < 0) ELPH_CUDA(cudaGetDevice(&dev));
+    ELPH_CUDA(cudaSetDevice(dev));
+    h->device = dev;
+    cudaDeviceProp prop;
+    ELPH_CUDA(cudaGetDeviceProperties(&prop, dev));
+    ELPH_REQUIRE(prop.major >= 10, ELPH_ERR_UNSUPPORTED, "libelph_b200 requires a Blackwell (sm_100a) GPU");
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+
+    // ---- bonds: 0-based pairs in checkerboard order; colour groups recovered from the order:
+    // a new group starts at the first bond that touches a site already used in the current group
+    // (identical to the reference's greedy groups; any disjoint split gives the same numbers)
+    const int64_t base = c->index_base;
+    h->bonds_host.resize(h->Nb);
+    for (int b = 0; b < h->Nb; ++b) {
+        const int64_t i = c->neighbor_table[2 * (size_t)b] - base, j = c->neighbor_table[2 * (size_t)b + 1] - base;
+        ELPH_REQUIRE(i >= 0 && i < h->N && j >= 0 && j < h->N && i != j, ELPH_ERR_INVALID, "neighbor_table entry out of range");
+        h->bonds_host[b] = make_int2((int)i, (int)j);
+    }
+    {
+        std::vector<int> stamp(h->N, -1);
+        h->goff_host.clear();
+        h->goff_host.push_back(0);
+        int g = 0;
+        for (int b = 0; b < h->Nb; ++b) {
+            const int2 ij = h->bonds_host[b];
+            if (stamp[ij.x] == g || stamp[ij.y] == g) {
+                h->goff_host.push_back(b);
+                ++g;
+            }
+            stamp[ij.x] = g;
+            stamp[ij.y] = g;
+        }
+        if (h->Nb > 0) h->goff_host.push_back(h->Nb);
+        h->ngroups = (int)h->goff_host.size() - 1;
+        h->max_group = 0;
+        for (int k = 0; k < h->ngroups; ++k) h->max_group = std::max(h->max_group, h->goff_host[k + 1] - h->goff_host[k]);
+    }
+    up(h->d_bonds, h->bonds_host);
+    up(h->d_goff, h->goff_host);
+
+    auto vec = [&](const double* p, size_t n, double fill) {
+        std::vector<double> v(n, fill);
+        if (p) std::copy(p, p + n, v.begin());
+        return v;
+    };
+    up(h->d_mu, vec(c->mu, h->N, 0.0));
+    up(h->d_omega, vec(c->omega, h->Nph, 0.0));
+    up(h->d_omega4, vec(c->omega4, h->Nph, 0.0));
+    h->d_x = zeros(h->Ndof);
+
+    if (h->model == ELPH_MODEL_HOLSTEIN) {
+        ELPH_REQUIRE(h->Nb == 0 || (c->cosht && c->sinht), ELPH_ERR_INVALID, "cosht/sinht are NULL");
+        std::vector<double2> cs(h->Nb);
+        for (int b = 0; b < h->Nb; ++b) cs[b] = make_double2(c->cosht[b], c->sinht[b]);
+        up(h->d_cs, cs);
+        up(h->d_lam, vec(c->lambda, h->N, 0.0));
+        up(h->d_lam2, vec(c->lambda2, h->N, 0.0));
+        h->d_D = zeros(h->Ndim);
+    } else {
+        ELPH_REQUIRE(h->Nb == 0 || (c->t && c->checkerboard_perm && c->inv_checkerboard_perm && c->bond_to_phonon),
+                     ELPH_ERR_INVALID, "SSH tables (t, checkerboard_perm, inv_checkerboard_perm, bond_to_phonon) are NULL");
+        ELPH_REQUIRE(h->Nph == 0 || (c->alpha && c->phonon_to_bond), ELPH_ERR_INVALID, "SSH phonon tables are NULL");
+        up(h->d_t, vec(c->t, h->Nb, 0.0));
+        up(h->d_alpha, vec(c->alpha, h->Nph, 0.0));
+        up(h->d_alpha2, vec(c->alpha2, h->Nph, 0.0));
+        std::vector<int> col_bond(h->Nb), col_ph(h->Nb, -1), ph_col(h->Nph, -1);
+        for (int col = 0; col < h->Nb; ++col) {
+            const int64_t bond = c->inv_checkerboard_perm[col] - base;
+            ELPH_REQUIRE(bond >= 0 && bond < h->Nb, ELPH_ERR_INVALID, "inv_checkerboard_perm out of range");
+            ELPH_REQUIRE(c->checkerboard_perm[bond] - base == col, ELPH_ERR_INVALID,
+                         "checkerboard_perm and inv_checkerboard_perm are not inverse permutations");
+            col_bond[col] = (int)bond;
+            const int64_t ph = c->bond_to_phonon[bond] - base;  // 0 (1-based) / -1 (0-based) = no phonon
+            if (ph >= 0) {
+                ELPH_REQUIRE(ph < h->Nph, ELPH_ERR_INVALID, "bond_to_phonon out of range");
+                ELPH_REQUIRE(c->phonon_to_bond[ph] - base == bond, ELPH_ERR_INVALID, "phonon_to_bond/bond_to_phonon mismatch");
+                col_ph[col] = (int)ph;
+                ph_col[ph] = col;
+            }
+        }
+        for (int ph = 0; ph < h->Nph; ++ph) ELPH_REQUIRE(ph_col[ph] >= 0, ELPH_ERR_INVALID, "phonon without a bond");
+        up(h->d_col_bond, col_bond);
+        up(h->d_col_ph, col_ph);
+        up(h->d_ph_col, ph_col);
+        // primary_field (host layout field = ph*L + tau) must be tau-diagonal: field (ph,tau) -> (ph',tau)
+        h->primary_ph_host.resize(h->Nph);
+        for (int ph = 0; ph < h->Nph; ++ph) {
+            int pr = ph;
+            if (c->primary_field) {
+                for (int tau = 0; tau < h->L; ++tau) {
+                    const int64_t f = c->primary_field[(size_t)ph * h->L + tau] - base;
+                    ELPH_REQUIRE(f >= 0 && f < h->Ndof && f % h->L == tau, ELPH_ERR_INVALID, "primary_field is not tau-diagonal");
+                    if (tau == 0) pr = (int)(f / h->L);
+                    ELPH_REQUIRE(f / h->L == pr, ELPH_ERR_INVALID, "primary_field differs between time slices");
+                }
+            }
+            h->primary_ph_host[ph] = pr;
+        }
+        for (int ph = 0; ph < h->Nph; ++ph)
+            ELPH_REQUIRE(h->primary_ph_host[h->primary_ph_host[ph]] == h->primary_ph_host[ph], ELPH_ERR_INVALID,
+                         "primary_field does not map onto primary fields");
+        up(h->d_primary_ph, h->primary_ph_host);
+        // CSR of equivalent phonons per primary, members in neighbour-table column order
+        std::vector<int> start(h->Nph + 1, 0), members(h->Nph);
+        for (int ph = 0; ph < h->Nph; ++ph) start[h->primary_ph_host[ph] + 1]++;
+        for (int k = 0; k < h->Nph; ++k) start[k + 1] += start[k];
+        std::vector<int> order(h->Nph);
+        for (int k = 0; k < h->Nph; ++k) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ph_col[a] < ph_col[b]; });
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int k : order) members[fill[h->primary_ph_host[k]]++] = k;
+        up(h->d_grp_start, start);
+        up(h->d_grp_members, members);
+        h->d_cs = elph_dalloc<double2>((size_t)h->L * h->Nb);
+        h->d_tprime = elph_dalloc<double>((size_t)h->L * h->Nb);
+        h->d_D = zeros(h->N);
+        h->d_lam = zeros(h->N);
+        h->d_lam2 = zeros(h->N);
+    }
+
+    // scratch
+    const size_t nd = (size_t)std::max(h->Ndim, h->Ndof);
+    h->d_va = zeros(nd);
+    h->d_vb = zeros(nd);
+    h->d_vc = zeros(nd);
+    h->d_b = zeros(h->Ndim);
+    h->d_res = zeros(h->Ndim);
+    h->d_r = zeros(h->Ndim);
+    h->d_p[0] = zeros(h->Ndim);
+    h->d_p[1] = zeros(h->Ndim);
+    h->d_z = zeros(h->Ndim);
+    h->partial_cap = std::max(4 * h->sm_count, 2 * h->L + 8);
+    h->d_partial = zeros(h->partial_cap);
+    h->d_ticket = elph_dalloc<unsigned int>(1);
+    ELPH_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+    h->d_cg = elph_dalloc<CgScalars>(1);
+    ELPH_CUDA(cudaMemset(h->d_cg, 0, sizeof(CgScalars)));
+    ELPH_CUDA(cudaMallocHost(&h->h_cg, sizeof(CgScalars)));
+    ELPH_CUDA(cudaMallocHost(&h->h_scal, 8 * sizeof(double)));
+    h->d_scal = zeros(8);
+    h->d_dSdx = zeros(h->Ndof);
+    h->d_dSdx2 = zeros(h->Ndof);
+    h->d_eta = zeros(h->Ndof);
+    h->d_dx = zeros(h->Ndof);
+    h->d_tmp = zeros(h->Ndof);
+    h->d_g = zeros(h->Ndim);
+    h->d_g2 = zeros(h->Ndim);
+    h->d_Minv = zeros(h->Ndim);
+    h->d_nu2 = elph_dalloc<cplx>((size_t)h->L * h->N);
+
+    elph_fft_init(h);
+    if (c->kpm_n > 0) elph_kpm_init(h, (int)c->kpm_n, c->kpm_buf, c->kpm_c1, c->kpm_c2);
+
+    // Fourier-acceleration diagonals -> engine layout [k][phonon]
+    auto load_diag = [&](const double* src, double*& dst, bool& have) {
+        if (!src) return;
+        dst = elph_dalloc<double>(h->Ndof);
+        double* st = stage(h, 0, h->Ndof);
+        ELPH_CUDA(cudaMemcpy(st, src, h->Ndof * sizeof(double), cudaMemcpyHostToDevice));
+        elph_to_engine(h, st, dst, h->Nph);
+        have = true;
+    };
+    load_diag(c->fa_Q, h->d_Q, h->have_Q);
+    load_diag(c->fa_M, h->d_Mass, h->have_M);
+    elph_launch_update_model(h);
+    ELPH_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void destroy(elph_handle* h) {
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    elph_kpm_free(h);
+    void* ptrs[] = {h->d_bonds, h->d_goff, h->d_cs, h->d_lam, h->d_lam2, h->d_mu, h->d_omega, h->d_omega4, h->d_x, h->d_D,
+                    h->d_Q, h->d_Mass, h->d_t, h->d_alpha, h->d_alpha2, h->d_ph_col, h->d_col_ph, h->d_col_bond,
+                    h->d_primary_ph, h->d_grp_start, h->d_grp_members, h->d_tprime, h->d_va, h->d_vb, h->d_vc, h->d_b,
+                    h->d_res, h->d_r, h->d_p[0], h->d_p[1], h->d_z, h->d_partial, h->d_ticket, h->d_cg, h->d_scal,
+                    h->d_dSdx, h->d_dSdx2, h->d_eta, h->d_dx, h->d_tmp, h->d_g, h->d_g2, h->d_Minv, h->d_nu2,
+                    h->d_twiddle, h->d_theta, h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stage[3]};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_cg) cudaFreeHost(h->h_cg);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    delete h;
+}
+
+}  // namespace
+
+#define ENTER(h)                                                      \
+    if (!(h)) {                                                       \
+        elph_global_error() = "null handle";                          \
+        return ELPH_ERR_INVALID;                                      \
+    }                                                                 \
+    DeviceGuard guard__((h)->device);                                 \
+    ELPH_TRY
+
+extern "C" {
+
+const char* elph_version(void) { return "elph_b200 0.1.0 (sm_100a)"; }
+
+const char* elph_last_error(const elph_handle* h) { return h ? h->err.c_str() : elph_global_error().c_str(); }
+
+int32_t elph_create(const elph_config* cfg, elph_handle** out) {
+    elph_handle* h = nullptr;
+    elph_handle* none = nullptr;
+    ELPH_TRY {
+        ELPH_REQUIRE(cfg && out, ELPH_ERR_INVALID, "elph_create: null argument");
+        *out = nullptr;
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        ELPH_REQUIRE(e == cudaSuccess && ndev > 0, ELPH_ERR_CUDA,
+                     std::string("no CUDA device available (libelph_b200 has no CPU fallback): ") + cudaGetErrorString(e));
+        h = new elph_handle();
+        try {
+            build(h, cfg);
+        } catch (...) {
+            std::string keep;
+            try { throw; } catch (const elph_error& er) { keep = er.msg; } catch (...) { keep = "elph_create failed"; }
+            destroy(h);
+            h = nullptr;
+            throw elph_error{ELPH_ERR_INVALID, keep};
+        }
+        *out = h;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(none)
+}
+
+int32_t elph_destroy(elph_handle* h) {
+    if (!h) return ELPH_OK;
+    destroy(h);
+    return ELPH_OK;
+}
+
+int32_t elph_set_stream(elph_handle* h, void* cuda_stream) {
+    ENTER(h) {
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        h->stream = (cudaStream_t)cuda_stream;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_synchronize(elph_handle* h) {
+    ENTER(h) {
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_set_solver(elph_handle* h, double tol, int64_t maxiter, double kappa_max) {
+    ENTER(h) {
+        if (tol > 0.0) h->cg_tol = tol;
+        if (maxiter > 0) h->cg_maxiter = maxiter;
+        if (kappa_max > 0.0) h->cg_kappa_max = kappa_max;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_configure(elph_handle* h, int64_t n, double buf, double c1, double c2) {
+    ENTER(h) {
+        ELPH_REQUIRE(n >= 1, ELPH_ERR_INVALID, "KPM Krylov dimension n must be >= 1");
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        elph_kpm_free(h);
+        elph_kpm_init(h, (int)n, buf, c1, c2);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_set_fourier_acceleration(elph_handle* h, const double* Q, const double* M) {
+    ENTER(h) {
+        auto load = [&](const double* src, double*& dst, bool& have) {
+            if (!src) return;
+            if (!dst) dst = elph_dalloc<double>(h->Ndof);
+            double* st = stage(h, 0, h->Ndof);
+            ELPH_CUDA(cudaMemcpyAsync(st, src, h->Ndof * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            elph_to_engine(h, st, dst, h->Nph);
+            have = true;
+        };
+        load(Q, h->d_Q, h->have_Q);
+        load(M, h->d_Mass, h->have_M);
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_set_x(elph_handle* h, const double* x) {
+    ENTER(h) {
+        upload_vec(h, x, h->d_x, h->Nph);
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_get_x(elph_handle* h, double* x) {
+    ENTER(h) {
+        download_vec(h, h->d_x, x, h->Nph);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_set_mu(elph_handle* h, const double* mu) {
+    ENTER(h) {
+        ELPH_REQUIRE(mu, ELPH_ERR_INVALID, "mu is NULL");
+        ELPH_CUDA(cudaMemcpyAsync(h->d_mu, mu, h->N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_update_model(elph_handle* h) {
+    ENTER(h) {
+        elph_launch_update_model(h);
+        if (h->model == ELPH_MODEL_SSH) {
+            // "make sure equivalent fields are equal" (src/SSHModels.jl:547-559): isapprox with default rtol = sqrt(eps)
+            std::vector<double> x(h->Ndof);
+            ELPH_CUDA(cudaMemcpyAsync(x.data(), h->d_x, h->Ndof * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            ELPH_CUDA(cudaStreamSynchronize(h->stream));
+            const double rtol = std::sqrt(2.220446049250313e-16);
+            for (int ph = 0; ph < h->Nph; ++ph) {
+                const int pr = h->primary_ph_host[ph];
+                if (pr == ph) continue;
+                for (int tau = 0; tau < h->L; ++tau) {
+                    const double a = x[(size_t)tau * h->Nph + ph], b = x[(size_t)tau * h->Nph + pr];
+                    if (!(a == b || std::fabs(a - b) <= rtol * std::max(std::fabs(a), std::fabs(b))))
+                        throw elph_error{ELPH_ERR_STATE, "equivalent phonon fields differ (update_model!)"};
+                }
+            }
+        }
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_get_expnV(elph_handle* h, double* out) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_INVALID, "expnV exists only for the Holstein model");
+        download_vec(h, h->d_D, out, h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_get_cosh_sinh(elph_handle* h, double* cosht, double* sinht) {
+    ENTER(h) {
+        ELPH_REQUIRE(cosht && sinht, ELPH_ERR_INVALID, "null output");
+        if (h->model == ELPH_MODEL_HOLSTEIN) {
+            std::vector<double2> cs(h->Nb);
+            ELPH_CUDA(cudaMemcpyAsync(cs.data(), h->d_cs, h->Nb * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+            ELPH_CUDA(cudaStreamSynchronize(h->stream));
+            for (int b = 0; b < h->Nb; ++b) { cosht[b] = cs[b].x; sinht[b] = cs[b].y; }
+        } else {
+            std::vector<double2> cs((size_t)h->L * h->Nb);
+            ELPH_CUDA(cudaMemcpyAsync(cs.data(), h->d_cs, cs.size() * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+            ELPH_CUDA(cudaStreamSynchronize(h->stream));
+            // reference layout: (Ltau, Nbonds) column-major -> index tau + Ltau*col
+            for (int tau = 0; tau < h->L; ++tau)
+                for (int b = 0; b < h->Nb; ++b) {
+                    cosht[(size_t)b * h->L + tau] = cs[(size_t)tau * h->Nb + b].x;
+                    sinht[(size_t)b * h->L + tau] = cs[(size_t)tau * h->Nb + b].y;
+                }
+        }
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+static int32_t host_matvec(elph_handle* h, MatvecMode mode, const double* v, double* y, int64_t nrhs) {
+    ENTER(h) {
+        ELPH_REQUIRE(nrhs >= 1, ELPH_ERR_INVALID, "nrhs must be >= 1");
+        double* vin = (nrhs == 1) ? h->d_va : stage(h, 2, (size_t)h->Ndim * nrhs);
+        double* vout = (nrhs == 1) ? h->d_vb : stage(h, 3, (size_t)h->Ndim * nrhs);
+        upload_vec(h, v, vin, h->N, nrhs);
+        MatvecArgs a;
+        a.v = vin;
+        a.y = vout;
+        a.nbatch = nrhs;
+        a.v_stride = h->Ndim;
+        a.y_stride = h->Ndim;
+        elph_launch_matvec(h, mode, a);
+        download_vec(h, vout, y, h->N, nrhs);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_mulM(elph_handle* h, const double* v, double* y) { return host_matvec(h, MODE_M, v, y, 1); }
+int32_t elph_mulMT(elph_handle* h, const double* v, double* y) { return host_matvec(h, MODE_MT, v, y, 1); }
+int32_t elph_mulMTM(elph_handle* h, const double* v, double* y) { return host_matvec(h, MODE_MTM, v, y, 1); }
+int32_t elph_mulMTM_batch(elph_handle* h, int64_t nrhs, const double* v, double* y) { return host_matvec(h, MODE_MTM, v, y, nrhs); }
+
+int32_t elph_muldMdx(elph_handle* h, const double* u, const double* v, double* dMdx) {
+    ENTER(h) {
+        upload_vec(h, u, h->d_va, h->N);
+        upload_vec(h, v, h->d_vb, h->N);
+        elph_muldMdx_dev(h, h->d_va, h->d_vb, h->d_vc, 1.0, false, false);
+        download_vec(h, h->d_vc, dMdx, h->Nph);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_setup(elph_handle* h, const double* arnoldi_noise, elph_kpm_info* info) {
+    ENTER(h) {
+        elph_kpm_setup_impl(h, arnoldi_noise, info);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_apply(elph_handle* h, const double* vin, double* vout) {
+    ENTER(h) {
+        upload_vec(h, vin, h->d_va, h->N);
+        elph_kpm_apply_dev(h, h->d_va, h->d_vb);
+        download_vec(h, h->d_vb, vout, h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_get_orders(elph_handle* h, int64_t* orders) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->kpm.configured && orders, ELPH_ERR_STATE, "KPM not configured");
+        for (int w = 0; w < h->kpm.Lo2; ++w) orders[w] = h->kpm.order[w];
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_get_coeff(elph_handle* h, int64_t w, double* out) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->kpm.configured && out && w >= 0 && w < h->kpm.Lo2, ELPH_ERR_INVALID, "bad frequency index");
+        for (int m = 0; m < h->kpm.order[w]; ++m) {
+            out[2 * m] = h->kpm.coeff[h->kpm.coeff_off[w] + m].real();
+            out[2 * m + 1] = h->kpm.coeff[h->kpm.coeff_off[w] + m].imag();
+        }
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_cg_solve(elph_handle* h, const double* b, double* x, int32_t use_precond, double tol, int64_t maxiter, int64_t* iters,
+                      double* eps) {
+    ENTER(h) {
+        upload_vec(h, b, h->d_va, h->N);
+        upload_vec(h, x, h->d_vb, h->N);
+        elph_cg_device(h, h->d_va, h->d_vb, use_precond != 0, tol, maxiter, iters, eps);
+        download_vec(h, h->d_vb, x, h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_solve(elph_handle* h, const double* b, double* x, int32_t use_precond, double tol_power, elph_solve_info* info) {
+    ENTER(h) {
+        upload_vec(h, b, h->d_va, h->N);
+        upload_vec(h, x, h->d_vb, h->N);
+        elph_solve_device(h, h->d_va, h->d_vb, use_precond != 0, tol_power, info);
+        download_vec(h, h->d_vb, x, h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_tau_to_omega(elph_handle* h, const double* vin, double* vout_complex) {
+    ENTER(h) {
+        ELPH_REQUIRE(vout_complex, ELPH_ERR_INVALID, "null output");
+        upload_vec(h, vin, h->d_va, h->N);
+        elph_tau_to_omega_dev(h, h->d_va, h->d_nu2);
+        // [omega][site] complex -> host layout (site-major, omega fastest)
+        cplx* st = reinterpret_cast<cplx*>(stage(h, 1, 2 * (size_t)h->Ndim));
+        elph_launch_transpose_c(h, h->d_nu2, st, h->L, h->N);
+        ELPH_CUDA(cudaMemcpyAsync(vout_complex, st, h->Ndim * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_omega_to_tau(elph_handle* h, const double* vin_complex, double* vout) {
+    ENTER(h) {
+        ELPH_REQUIRE(vin_complex, ELPH_ERR_INVALID, "null input");
+        cplx* st = reinterpret_cast<cplx*>(stage(h, 0, 2 * (size_t)h->Ndim));
+        ELPH_CUDA(cudaMemcpyAsync(st, vin_complex, h->Ndim * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+        elph_launch_transpose_c(h, st, h->d_nu2, h->N, h->L);
+        elph_omega_to_tau_dev(h, h->d_nu2, h->d_vb);
+        download_vec(h, h->d_vb, vout, h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_fourier_accelerate(elph_handle* h, const double* v, double* vout, double power, int32_t use_mass) {
+    ENTER(h) {
+        upload_vec(h, v, h->d_va, h->Nph);
+        elph_fourier_accelerate_dev(h, h->d_va, h->d_vb, power, use_mass != 0);
+        download_vec(h, h->d_vb, vout, h->Nph);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_Sb(elph_handle* h, int32_t shifted, double* Sb) {
+    ENTER(h) {
+        ELPH_REQUIRE(Sb, ELPH_ERR_INVALID, "null output");
+        elph_Sb_dev(h, shifted != 0, Sb);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dSbdx(elph_handle* h, int32_t shifted, double* dSbdx) {
+    ENTER(h) {
+        upload_vec(h, dSbdx, h->d_va, h->Nph);
+        elph_dSbdx_dev(h, h->d_va, shifted != 0);
+        download_vec(h, h->d_va, dSbdx, h->Nph);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_calc_dSdx(elph_handle* h, const double* g, const double* arnoldi_noise, int32_t use_precond, double* dSdx,
+                       double* Minv_g, elph_solve_info* info) {
+    ENTER(h) {
+        upload_vec(h, g, h->d_g, h->N);
+        elph_calc_dSdx_dev(h, h->d_g, arnoldi_noise, use_precond != 0, h->d_dSdx, h->d_Minv, info);
+        download_vec(h, h->d_dSdx, dSdx, h->Nph);
+        if (Minv_g) download_vec(h, h->d_Minv, Minv_g, h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_langevin_step(elph_handle* h, int32_t method, double dt, const double* eta, const double* g1, const double* g2,
+                           const double* arnoldi1, const double* arnoldi2, int32_t use_precond, int64_t* iters,
+                           elph_solve_info* info1, elph_solve_info* info2) {
+    ENTER(h) {
+        ELPH_REQUIRE(method == ELPH_LANGEVIN_EULER || g2, ELPH_ERR_INVALID, "g2 is required for the two-stage updates");
+        upload_vec(h, eta, h->d_vc, h->Nph);
+        upload_vec(h, g1, h->d_g, h->N);
+        if (g2) upload_vec(h, g2, h->d_g2, h->N);
+        elph_langevin_step_dev(h, method, dt, h->d_vc, h->d_g, h->d_g2, arnoldi1, arnoldi2, use_precond != 0, iters, info1, info2);
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// ------------------------------------------------------------------------------- device-resident API
+static int32_t dev_matvec(elph_handle* h, MatvecMode mode, const double* v, double* y) {
+    ENTER(h) {
+        ELPH_REQUIRE(v && y, ELPH_ERR_INVALID, "null device pointer");
+        MatvecArgs a;
+        a.v = v;
+        a.y = y;
+        elph_launch_matvec(h, mode, a);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_mulMTM(elph_handle* h, const double* v, double* y) { return dev_matvec(h, MODE_MTM, v, y); }
+int32_t elph_dev_mulM(elph_handle* h, const double* v, double* y) { return dev_matvec(h, MODE_M, v, y); }
+int32_t elph_dev_mulMT(elph_handle* h, const double* v, double* y) { return dev_matvec(h, MODE_MT, v, y); }
+
+int32_t elph_dev_mulMTM_replicas(elph_handle* h, int64_t nrep, const double* expnV_dev, int64_t expnV_stride, const double* v_dev,
+                                 double* y_dev, int64_t vec_stride) {
+    ENTER(h) {
+        ELPH_REQUIRE(v_dev && y_dev && nrep >= 1, ELPH_ERR_INVALID, "bad replica arguments");
+        ELPH_REQUIRE(h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED, "replica batches are implemented for the Holstein model");
+        MatvecArgs a;
+        a.v = v_dev;
+        a.y = y_dev;
+        a.D = expnV_dev;
+        a.nbatch = nrep;
+        a.v_stride = vec_stride;
+        a.y_stride = vec_stride;
+        a.D_stride = expnV_dev ? expnV_stride : 0;
+        elph_launch_matvec(h, MODE_MTM, a);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_to_engine_layout(elph_handle* h, const double* host_layout_dev, double* engine_dev, int64_t ncols) {
+    ENTER(h) {
+        elph_to_engine(h, host_layout_dev, engine_dev, (int)ncols);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_from_engine_layout(elph_handle* h, const double* engine_dev, double* host_layout_dev, int64_t ncols) {
+    ENTER(h) {
+        elph_from_engine(h, engine_dev, host_layout_dev, (int)ncols);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_ptr_x(elph_handle* h, double** x_dev) {
+    ENTER(h) {
+        *x_dev = h->d_x;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_ptr_expnV(elph_handle* h, double** p) {
+    ENTER(h) {
+        *p = h->d_D;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_cg_solve(elph_handle* h, const double* b_dev, double* x_dev, int32_t use_precond, double tol, int64_t maxiter,
+                          int64_t* iters, double* eps) {
+    ENTER(h) {
+        elph_cg_device(h, b_dev, x_dev, use_precond != 0, tol, maxiter, iters, eps);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int64_t elph_launch_count(const elph_handle* h) { return h ? h->launches : 0; }
+int32_t elph_set_chunk(elph_handle* h, int32_t c) {
+    ENTER(h) {
+        ELPH_REQUIRE(c >= 0 && c <= 64, ELPH_ERR_INVALID, "slices_per_cta out of range");
+        h->chunk_override = c;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// test hook (not in the public header): eigenvalues of a real upper-Hessenberg matrix, row-major n x n
+int32_t elph_debug_hessenberg_eigvals(int32_t n, const double* hmat, double* re, double* im) {
+    elph_handle* none = nullptr;
+    ELPH_TRY {
+        std::vector<double> hv(hmat, hmat + (size_t)n * n);
+        auto ev = elph_debug_hess_eig(hv, n);
+        for (int i = 0; i < n; ++i) { re[i] = ev[i].real(); im[i] = ev[i].imag(); }
+        return ELPH_OK;
+    }
+    ELPH_CATCH(none)
+}
+
+}  // extern "C"

