@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 engine for the ElPhDynamics hot path.
+
+Metric (BASELINE.json): M^T M matvecs/s on Holstein square 32x32, Ltau=200 (config B), plus
+Langevin steps/s and CG iterations/s as extra keys, with the kernel's fraction of the HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the fused M^T M kernel over one batch of
+synthetic input: R independent replicas of the 32x32x200 lattice (own phonon field / expnV table and own
+vector each -- the reference's only scale-out is independent runs, src/ElPhDynamics.jl:90-95), sized so
+that the inputs (v + expnV + y = R * 4.9 MB) exceed the 126 MB L2.  `value` times the kernel with inputs
+resident in HBM; `e2e` times the reference-facing C-ABI call (elph_mulMTM_batch) with pinned HOST buffers,
+H2D + layout change + kernel + D2H inside the timed region.  N > 1: replicas are sharded across ranks
+(no data-path collective; weak scaling), max-over-ranks timing.
+
+--impl reference: the reference's CPU implementation cannot run here (pure Julia, no julia in the image),
+so the arm times the C restatement of its loops (oracle/c/elph_ref.c) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "MTM matvecs/s (Holstein 32x32xL200)"
+UNIT = "matvecs/s"
+LSIDE, BETA, DTAU = 32, 20.0, 0.1
+BYTES_PER_POINT = 24.0  # read v + read expnV + write y
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_models():
+    from helpers import engine_holstein_like, oracle_holstein
+    om, rng = oracle_holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=1234, eps=0.3)  # only to generate inputs
+    em = engine_holstein_like(om)
+    return om, em, rng
+
+
+def cpu_baseline(om, target_seconds=12.0, nthreads=0):
+    """C restatement of the reference loops on the host cores; bounded sample of the same workload."""
+    from oracle.cref import CRef
+    c = CRef(om, native=True)
+    ncpu = os.cpu_count() or 1
+    nthreads = nthreads or ncpu
+    nrep = nthreads
+    secs, used = c.mulMTM_throughput(nrep=nrep, reps=2, nthreads=nthreads)
+    per = secs / 2
+    reps = max(2, int(target_seconds / max(per, 1e-6)))
+    secs, used = c.mulMTM_throughput(nrep=nrep, reps=reps, nthreads=nthreads)
+    return {"value": nrep * reps / secs, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": f"{nrep} independent 32x32xL200 replicas x {reps} M^T M products each, one thread per replica "
+                      f"(C restatement of the Julia loops, gcc -O3 -march=native -ffast-math); the Julia reference itself "
+                      f"cannot run here", "seconds": secs}, (nrep, reps, secs, used)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from helpers import oracle_holstein
+    om, _ = oracle_holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=1234, eps=0.3)
+    from oracle.cref import CRef
+    c = CRef(om, native=True)
+    nthreads = os.cpu_count() or 1
+    nrep = nthreads
+    secs, used = c.mulMTM_throughput(nrep=nrep, reps=2, nthreads=nthreads)
+    reps = max(1, int(1.0 / max(secs / 2, 1e-6)))     # ~1 s of CPU work per step
+    for _ in range(args.warmup):
+        c.mulMTM_throughput(nrep=nrep, reps=reps, nthreads=nthreads)
+    t = 0.0
+    for _ in range(args.steps):
+        s, used = c.mulMTM_throughput(nrep=nrep, reps=reps, nthreads=nthreads)
+        t += s
+    value = nrep * reps * args.steps / t
+    sample = (f"each step = {nrep} independent 32x32xL200 replicas x {reps} M^T M products, one thread per replica; "
+              f"C restatement of the reference's Julia loops (Julia itself is not installed in this image)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "holstein_square_32x32_L200", "replicas_per_step": nrep, "products_per_replica": reps},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--replicas", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the CG / Langevin extra measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import elphdynamics_b200 as E
+    from elphdynamics_b200._lib import ptr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    om, em, rng = build_models()
+    lib = em._lib
+    stream = torch.cuda.current_stream()
+    em.set_stream(stream.cuda_stream)
+    n = om.Ndim
+    R = args.replicas
+    hbm_peak, peak_src, _ = peaks()
+
+    # ---------------- device-resident inputs: R replicas, each with its own expnV table and vector ------------
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    V = torch.randn(R, n, dtype=torch.float64, device="cuda", generator=g)
+    Y = torch.empty_like(V)
+    # expnV of the synthetic field in the engine layout [tau][site], perturbed per replica (independent chains)
+    base = torch.from_numpy(np.ascontiguousarray(em.expnV.reshape(om.N, om.L).T)).reshape(-1).cuda()
+    D = base.unsqueeze(0).repeat(R, 1) * (1.0 + 0.01 * torch.rand(R, n, dtype=torch.float64, device="cuda", generator=g))
+
+    def step_device():
+        st = lib.elph_dev_mulMTM_replicas(em.handle, R, D.data_ptr(), n, V.data_ptr(), Y.data_ptr(), n)
+        if st != 0:
+            raise RuntimeError(lib.elph_last_error(em.handle))
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = em.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = em.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * R * args.steps / (ms * 1e-3)
+    kernel_us = ms * 1e3 / args.steps
+    achieved = BYTES_PER_POINT * n * R / (kernel_us * 1e-6) / 1e9   # GB/s per GPU
+
+    # ---------------- e2e: host buffers through the C ABI ------------------------------------------------------
+    Vh = torch.randn(R, n, dtype=torch.float64).pin_memory()
+    Yh = torch.empty(R, n, dtype=torch.float64).pin_memory()
+    vp = C.cast(Vh.data_ptr(), C.POINTER(C.c_double))
+    yp = C.cast(Yh.data_ptr(), C.POINTER(C.c_double))
+
+    def step_e2e():
+        st = lib.elph_mulMTM_batch(em.handle, R, vp, yp)
+        if st != 0:
+            raise RuntimeError(lib.elph_last_error(em.handle))
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    ksteps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(ksteps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * R * ksteps / e2e_s
+
+    extra = {}
+    if not args.no_extra and rank == 0:
+        # single lattice, L2-resident: latency-bound regime of the real simulation
+        v1 = V[0].contiguous()
+        y1 = torch.empty_like(v1)
+        for _ in range(20):
+            lib.elph_dev_mulMTM(em.handle, v1.data_ptr(), y1.data_ptr())
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(200):
+            lib.elph_dev_mulMTM(em.handle, v1.data_ptr(), y1.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        us1 = e0.elapsed_time(e1) * 1e3 / 200
+        extra["single_lattice"] = {"us_per_matvec": us1, "matvecs_per_s": 1e6 / us1,
+                                   "algorithmic_GBps": BYTES_PER_POINT * n / us1 / 1e3, "note": "L2-resident, launch/latency bound"}
+        # CG and one Langevin RK step with injected noise (KPM-preconditioned), through the C ABI
+        gvec = rng.normal(size=n)
+        b = np.zeros(n)
+        E.mulMT_(b, em, gvec)
+        xs = np.zeros(n)
+        t0 = time.perf_counter()
+        it, res, flag = E.ldiv_(xs, em, b)
+        dt_cg = time.perf_counter() - t0
+        extra["cg"] = {"iters": it, "residual": res, "flag": flag, "seconds": dt_cg, "iters_per_s": it / dt_cg}
+        P = E.SymmetricKPMPreconditioner(em)
+        fa = E.FourierAccelerator(em)
+        E.update_Q_(fa, em, 0.0, 10.0, 1.0)
+        dyn = E.RungeKuttaDynamics(em, 1e-3)
+        nsteps = 3
+        its = []
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            its.append(E.evolve_(em, dyn, fa, P, eta=rng.normal(size=n), g1=rng.normal(size=n), g2=rng.normal(size=n),
+                                 arnoldi1=rng.normal(size=2 * om.N), arnoldi2=rng.normal(size=2 * om.N)))
+        dt_l = time.perf_counter() - t0
+        extra["langevin_rk_kpm"] = {"steps_per_s": nsteps / dt_l, "pcg_iters_second_solve": its,
+                                    "note": "elph_langevin_step through the C ABI with host noise buffers"}
+
+    if rank == 0:
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("mtm_replicas_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "holstein_square_32x32_L200", "replicas_per_gpu": R,
+                           "l2_policy": f"inputs larger than L2: {3 * R * n * 8 / 1e6:.0f} MB per step vs 126 MB L2",
+                           "parallelism": f"replicas x{world}" if world > 1 else "single GPU"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "matvec_kernel<MTM> (fused M^T M)",
+                             "algorithmic_bytes_per_launch": BYTES_PER_POINT * n * R, "kernel_us": kernel_us},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * n * 8, "d2h_bytes_per_step": R * n * 8,
+                        "api": "elph_mulMTM_batch (host pointers, pinned)"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        line.update(extra)
+        if not args.no_cpu:
+            cb, _ = cpu_baseline(om)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    em.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -104,7 +104,9 @@ void build(elph_handle* h, const elph_config* c) {
     ELPH_CUDA(cudaGetDeviceProperties(&prop, dev));
     ELPH_REQUIRE(prop.major >= 10, ELPH_ERR_UNSUPPORTED, "libelph_b200 requires a Blackwell (sm_100a) GPU");
     h->sm_count = prop.multiProcessorCount;
-    h->smem_optin = prop.sharedMemPerBlockOptin;
+    // dynamic shared memory available to the slice kernels: the opt-in maximum minus 1 KB kept for their
+    // (small) static shared arrays -- cudaFuncAttributeMaxDynamicSharedMemorySize counts static + dynamic
+    h->smem_optin = prop.sharedMemPerBlockOptin - 1024;
 
     // ---- bonds: 0-based pairs in checkerboard order; colour groups recovered from the order:
     // a new group starts at the first bond that touches a site already used in the current group

@@ -1,0 +1,149 @@
+/*
+ * CPU restatement (plain C) of the reference's hot loops -- TEST INFRASTRUCTURE / CPU BASELINE ONLY.
+ *
+ * Mirrors, loop for loop, the Julia code of cohensbw/ElPhDynamics v1.1.3 (which cannot run here: no
+ * Julia in the image).  Host layout: index = site*Ltau + tau (src/Utilities.jl:12-15), 0-based.
+ *   checkerboard_mul!            src/Checkerboard.jl:57-83     (bond-major, inner @simd loop over tau)
+ *   checkerboard_transpose_mul!  src/Checkerboard.jl:149-175
+ *   mulM!, mulMT!                src/HolsteinModels.jl:569-626, 631-684
+ *   mulMTM!                      src/Models.jl:215-224
+ *   solve! (plain CG)            src/IterativeSolvers.jl:239-314
+ * Compiled with -O3 -ffast-math to match the reference's @fastmath @inbounds @simd loops.
+ * Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() may use it.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    int64_t N, L, Nb;
+    const int64_t* nt;   /* 2*Nb, (i,j) pairs, 0-based, checkerboard order */
+    const double* cosht; /* Nb */
+    const double* sinht; /* Nb */
+} ref_model;
+
+static void checkerboard_mul(double* y, const ref_model* m) {
+    const int64_t L = m->L;
+    for (int64_t n = 0; n < m->Nb; ++n) {
+        const double c = m->cosht[n], s = m->sinht[n];
+        double* yi = y + m->nt[2 * n] * L;
+        double* yj = y + m->nt[2 * n + 1] * L;
+        for (int64_t t = 0; t < L; ++t) {
+            const double t1 = yi[t], t2 = yj[t];
+            yi[t] = c * t1 + s * t2;
+            yj[t] = c * t2 + s * t1;
+        }
+    }
+}
+
+static void checkerboard_transpose_mul(double* y, const ref_model* m) {
+    const int64_t L = m->L;
+    for (int64_t n = m->Nb - 1; n >= 0; --n) {
+        const double c = m->cosht[n], s = m->sinht[n];
+        double* yi = y + m->nt[2 * n] * L;
+        double* yj = y + m->nt[2 * n + 1] * L;
+        for (int64_t t = 0; t < L; ++t) {
+            const double t1 = yi[t], t2 = yj[t];
+            yi[t] = c * t1 + s * t2;
+            yj[t] = c * t2 + s * t1;
+        }
+    }
+}
+
+void ref_mulM(double* y, const ref_model* m, const double* expnV, const double* v) {
+    const int64_t N = m->N, L = m->L;
+    for (int64_t i = 0; i < N; ++i)
+        for (int64_t t = 0; t < L; ++t) {
+            const int64_t tm1 = (t == 0) ? L - 1 : t - 1;
+            y[i * L + t] = expnV[i * L + t] * v[i * L + tm1];
+        }
+    checkerboard_mul(y, m);
+    for (int64_t i = 0; i < N; ++i) {
+        y[i * L] = v[i * L] + y[i * L];
+        for (int64_t t = 1; t < L; ++t) y[i * L + t] = v[i * L + t] - y[i * L + t];
+    }
+}
+
+void ref_mulMT(double* y, const ref_model* m, const double* expnV, const double* v) {
+    const int64_t N = m->N, L = m->L;
+    memcpy(y, v, (size_t)(N * L) * sizeof(double));
+    checkerboard_transpose_mul(y, m);
+    for (int64_t i = 0; i < N; ++i) {
+        const double yL = v[i * L + L - 1] + expnV[i * L] * y[i * L];
+        for (int64_t t = 0; t < L - 1; ++t) y[i * L + t] = v[i * L + t] - expnV[i * L + t + 1] * y[i * L + t + 1];
+        y[i * L + L - 1] = yL;
+    }
+}
+
+void ref_mulMTM(double* y, const ref_model* m, const double* expnV, const double* v, double* scratch) {
+    ref_mulM(scratch, m, expnV, v);
+    ref_mulMT(y, m, expnV, scratch);
+}
+
+static double dot(const double* a, const double* b, int64_t n) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+    return s;
+}
+
+/* plain CG on A = M^T M; x in/out; work = 4*N*L doubles.  Returns the iteration count. */
+int64_t ref_cg(double* x, const ref_model* m, const double* expnV, const double* b, double tol, int64_t maxiter,
+               double kappa_max, double* work, double* eps_out) {
+    const int64_t n = m->N * m->L;
+    double *r = work, *p = work + n, *z = work + 2 * n, *scr = work + 3 * n;
+    const double normb = sqrt(dot(b, b, n));
+    ref_mulMTM(r, m, expnV, x, scr);
+    for (int64_t i = 0; i < n; ++i) r[i] = b[i] - r[i];
+    memcpy(p, r, (size_t)n * sizeof(double));
+    double rdotr = dot(r, r, n);
+    const double eps0 = sqrt(rdotr) / normb;
+    double eps = eps0, kmin = 0.0;
+    for (int64_t j = 1; j <= maxiter; ++j) {
+        ref_mulMTM(z, m, expnV, p, scr);
+        const double alpha = rdotr / dot(p, z, n);
+        for (int64_t i = 0; i < n; ++i) x[i] += alpha * p[i];
+        for (int64_t i = 0; i < n; ++i) r[i] -= alpha * z[i];
+        const double nr = dot(r, r, n);
+        eps = sqrt(nr) / normb;
+        const double q = 2.0 * (double)j / log(2.0 * eps0 / eps);
+        if (q * q > kmin) kmin = q * q;
+        if (eps < tol || kmin > kappa_max) {
+            if (eps_out) *eps_out = eps;
+            return j;
+        }
+        const double beta = nr / rdotr;
+        rdotr = nr;
+        for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * p[i];
+    }
+    if (eps_out) *eps_out = eps;
+    return maxiter;
+}
+
+/* Throughput driver: `nrep` independent replicas (the reference's own scale-out: independent runs, one
+ * thread each -- BLAS/FFTW are pinned to 1 thread, src/ElPhDynamics.jl:74-75), `reps` M^T M products each.
+ * v, y, expnV, scratch: nrep contiguous blocks of N*L doubles.  Returns the number of threads used. */
+int ref_mulMTM_replicas(const ref_model* m, int64_t nrep, int64_t reps, const double* expnV, double* v, double* y,
+                        double* scratch, int nthreads) {
+    const int64_t n = m->N * m->L;
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+    {
+#pragma omp single
+        used = omp_get_num_threads();
+#pragma omp for schedule(static)
+        for (int64_t r = 0; r < nrep; ++r)
+            for (int64_t k = 0; k < reps; ++k) ref_mulMTM(y + r * n, m, expnV + r * n, v + r * n, scratch + r * n);
+    }
+#else
+    (void)nthreads;
+    for (int64_t r = 0; r < nrep; ++r)
+        for (int64_t k = 0; k < reps; ++k) ref_mulMTM(y + r * n, m, expnV + r * n, v + r * n, scratch + r * n);
+#endif
+    return used;
+}

@@ -109,6 +109,8 @@ def sorted_neighbor_table_perm(nt: np.ndarray) -> np.ndarray:
     ``maximum(nt)*nt[1,:] + nt[2,:]`` on 1-based indices; the 0-based key
     ``(max+1)*(a+1) + (b+1)`` orders identically."""
     assert nt.shape[0] == 2
+    if nt.shape[1] == 0:
+        return np.zeros(0, dtype=np.int64)
     swap = nt[0] > nt[1]
     nt[:, swap] = nt[::-1, swap]
     m = int(nt.max()) + 1  # = maximum of the 1-based table

@@ -40,7 +40,7 @@ def timeit(fn, iters=200, warm=20):
 for chunk in (1, 2, 4, 0):
     lib.elph_set_chunk(em.handle, chunk)
     us = timeit(lambda: lib.elph_dev_mulMTM(em.handle, v.data_ptr(), y.data_ptr()))
-    print(f"MTM single  chunk={chunk}: {us:8.2f} us  -> {24*n/us/1e6:8.1f} GB/s algorithmic")
+    print(f"MTM single  chunk={chunk}: {us:8.2f} us  -> {24*n/us/1e3:8.1f} GB/s algorithmic")
 for nrep in (16, 64, 128):
     V = torch.randn(nrep, n, dtype=torch.float64, device="cuda")
     Y = torch.empty_like(V)
@@ -48,7 +48,7 @@ for nrep in (16, 64, 128):
     for chunk in (1, 2, 4, 8):
         lib.elph_set_chunk(em.handle, chunk)
         us = timeit(lambda: lib.elph_dev_mulMTM_replicas(em.handle, nrep, D.data_ptr(), n, V.data_ptr(), Y.data_ptr(), n), iters=50, warm=5)
-        print(f"MTM replicas={nrep} chunk={chunk}: {us:8.2f} us -> {24*n*nrep/us/1e6:8.1f} GB/s, {nrep/us*1e6:10.0f} matvecs/s")
+        print(f"MTM replicas={nrep} chunk={chunk}: {us:8.2f} us -> {24*n*nrep/us/1e3:8.1f} GB/s, {nrep/us*1e6:10.0f} matvecs/s")
 lib.elph_set_chunk(em.handle, 0)
 # CG
 g = rng.normal(size=n)

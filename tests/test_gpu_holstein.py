@@ -192,19 +192,28 @@ def test_kpm_setup_apply_and_pcg(pair):
     Po.setup(noise)
     info = E.setup_(Pe, noise)
     assert bool(info.active) == Po.active
-    assert abs(info.e_min - Po.e_min) <= 1e-9 * abs(Po.e_min)
-    assert abs(info.e_max - Po.e_max) <= 1e-9 * abs(Po.e_max)
+    # the 20-step Arnoldi estimate is not converged, so rounding differences (summation order of the
+    # Gram-Schmidt dots) are amplified; it only feeds lambda_lo/hi through a 5% buffer and a hysteresis
+    assert abs(info.e_min - Po.e_min) <= 1e-6 * abs(Po.e_min)
+    assert abs(info.e_max - Po.e_max) <= 1e-6 * abs(Po.e_max)
     if not Po.active:
         return
     assert np.array_equal(Pe.orders(), Po.order)
     for w in (0, len(Po.order) - 1):
-        assert relerr(Pe.coeff(w), Po.coeff[w]) <= 1e-9
+        assert relerr(Pe.coeff(w), Po.coeff[w]) <= 1e-6
+    # apply parity at identical coefficients: feed the oracle the engine's spectral window
+    Po.lam_lo, Po.lam_hi = info.lambda_lo, info.lambda_hi
+    Po.lam_avg, Po.lam_mag = (Po.lam_hi + Po.lam_lo) / 2, (Po.lam_hi - Po.lam_lo) / 2
+    from oracle.kpm import kpm_coefficients
+    Po.coeff = [kpm_coefficients(int(Po.order[w]), Po.lam_lo, Po.lam_hi, Po.phis[w]) for w in range(Po.Lo2)]
+    for w in (0, len(Po.order) - 1):
+        assert relerr(Pe.coeff(w), Po.coeff[w]) <= 1e-12
     r = rng.normal(size=om.Ndim)
     zo = np.zeros(om.Ndim)
     ze = np.zeros(om.Ndim)
     Po.ldiv(zo, r)
     E.kpm_ldiv_(ze, Pe, r)
-    assert relerr(ze, zo) <= 1e-9
+    assert relerr(ze, zo) <= 1e-11
     # preconditioned solve: iterations within +-2
     g = rng.normal(size=om.Ndim)
     b = np.zeros(om.Ndim)
