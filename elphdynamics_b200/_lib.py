@@ -128,6 +128,8 @@ def load() -> C.CDLL:
         "elph_dev_cg_solve": (i32, [H, C.c_void_p, C.c_void_p, i32, dbl, i64, ip, dp]),
         "elph_launch_count": (i64, [H]),
         "elph_set_chunk": (i32, [H, i32]),
+        "elph_set_tuning": (i32, [H, i32, i32]),
+        "elph_get_kernel_info": (i32, [H, C.POINTER(i32), C.POINTER(i32)]),
         "elph_debug_hessenberg_eigvals": (i32, [i32, dp, dp, dp]),
     }
     for name, (res, args) in sig.items():

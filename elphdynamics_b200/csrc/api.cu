@@ -155,6 +155,7 @@ void build(elph_handle* h, const elph_config* c) {
         std::vector<double2> cs(h->Nb);
         for (int b = 0; b < h->Nb; ++b) cs[b] = make_double2(c->cosht[b], c->sinht[b]);
         up(h->d_cs, cs);
+        elph_detect_square(h, cs);
         up(h->d_lam, vec(c->lambda, h->N, 0.0));
         up(h->d_lam2, vec(c->lambda2, h->N, 0.0));
         h->d_D = zeros(h->Ndim);
@@ -731,6 +732,27 @@ int32_t elph_set_chunk(elph_handle* h, int32_t c) {
     ENTER(h) {
         ELPH_REQUIRE(c >= 0 && c <= 64, ELPH_ERR_INVALID, "slices_per_cta out of range");
         h->chunk_override = c;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
+    ENTER(h) {
+        switch (key) {
+            case 0: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "chunk out of range"); h->chunk_override = value; break;
+            case 1: h->sq_disable = (value != 0); break;
+            case 2: h->sq_py = value; break;
+            default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
+        }
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_get_kernel_info(elph_handle* h, int32_t* square_kernel, int32_t* ngroups) {
+    ENTER(h) {
+        if (square_kernel) *square_kernel = (h->sq.enabled && !h->sq_disable) ? 1 : 0;
+        if (ngroups) *ngroups = h->ngroups;
         return ELPH_OK;
     }
     ELPH_CATCH(h)

@@ -187,6 +187,14 @@ struct elph_handle {
     cplx* d_nu2 = nullptr;          // second frequency-space work vector [L][N]
     bool kpm_skip_enabled = false;  // inside the CG loop the KPM kernels honour the convergence latch
 
+    // register/shuffle kernel for periodic square lattices (mtm_square.cu)
+    struct {
+        bool enabled = false;
+        int Lx = 0, Ly = 0;
+        double c[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
+    } sq;
+    bool sq_disable = false;
+    int sq_py = 0;
     int chunk_override = 0;
     unsigned smem_attr_mask = 0;  // which matvec kernel instances already have the opt-in smem attribute
     int threads = 256;
@@ -215,6 +223,8 @@ struct MatvecArgs {
 
 void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a);
 void elph_launch_update_model(elph_handle* h);
+void elph_detect_square(elph_handle* h, const std::vector<double2>& cs);
+bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a);
 void elph_launch_transpose(elph_handle* h, const double* in, double* out, int rows, int cols, int64_t nbatch);
 void elph_launch_transpose_c(elph_handle* h, const cplx* in, cplx* out, int rows, int cols);
 // host layout (ncols rows of length L) -> engine layout [L][ncols]

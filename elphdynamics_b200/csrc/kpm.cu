@@ -305,7 +305,7 @@ __device__ __forceinline__ void poly(cplx (&acc)[SPT], const cplx (&vin)[SPT], c
 }
 
 template <int SPT>
-__global__ void kpm_apply_kernel(KpmParams P) {
+__global__ void __launch_bounds__(512) kpm_apply_kernel(KpmParams P) {
     extern __shared__ double smem_raw[];
     cplx* sw = reinterpret_cast<cplx*>(smem_raw);
     if (P.skip && *P.skip) return;
@@ -509,7 +509,7 @@ void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) {
     P.inv_mag = 1.0 / K.lam_mag;
     P.avg_over_mag = K.lam_avg / K.lam_mag;
     int threads = 256;
-    while (threads < 1024 && threads * 4 < h->N) threads *= 2;
+    while (threads < 512 && threads * 4 < h->N) threads *= 2;   // <= 512 threads: __launch_bounds__(512) on the kernel
     const int spt = (h->N + threads - 1) / threads;
     if (spt <= 1) launch_apply<1>(h, P, threads);
     else if (spt <= 2) launch_apply<2>(h, P, threads);

@@ -313,6 +313,7 @@ static int pick_chunk(elph_handle* h, MatvecMode mode, int64_t nbatch) {
 }
 
 void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a) {
+    if (mode == MODE_MTM && elph_launch_mtm_square(h, a)) return;
     ELPH_REQUIRE(a.v != a.y || a.cg_S, ELPH_ERR_INVALID, "matvec output must not alias its input");
     KParams P;
     P.v = a.v;

@@ -1,0 +1,457 @@
+// Register-resident fused M^T M kernel for periodic square lattices (Holstein, uniform hopping per colour).
+//
+// Same operator as matvec.cu (reference: src/HolsteinModels.jl:569-684, src/Checkerboard.jl:57-175,
+// src/Models.jl:215-224); this is the roofline path for configs B (32x32xL200) and E (64x64xL400).
+//
+// Mapping.  site = x + Lx*y.  A warp owns PY consecutive rows of one tau-slice; lane = x mod 32, and for
+// Lx = 32*NSEG each lane carries NSEG x-segments, so the warp's tile (PY x Lx sites) lives in registers
+// (R = PY*NSEG doubles per array).  The four colour groups of the square lattice
+//     g0: (x,x+1) x even     g1: (x,x+1) x odd (incl. the periodic wrap)
+//     g2: (y,y+1) y even     g3: (y,y+1) y odd (incl. the periodic wrap)
+// become:  g0 = one butterfly shuffle (lane^1), g1 = one rotate shuffle (lane+-1, wrap lanes forward the
+// neighbouring x-segment), g2 = register-to-register, g3 = register-to-register except the two tile-edge rows,
+// which are exchanged with the neighbouring warps of the CTA through a double-buffered shared-memory strip
+// (one __syncthreads per sweep).  No shared-memory traffic for the sweeps themselves.
+//
+// Streaming.  A CTA (all warps of a slice) walks a chunk of C+1 consecutive slices:
+//     t = D(tau) .* v(tau-1);  t = K t;  w(tau) = v(tau) -/+ t;  u = K^T w(tau);
+//     y(tau-1) = w(tau-1) -/+ D(tau) .* u
+// keeping v(tau-1), w(tau-1) in registers, so each slice of v and D is read once per chunk (+1 halo slice)
+// and y written once: 24 B/pt compulsory traffic.  The v/D tiles of the next slices are prefetched by TMA
+// bulk copies (cp.async.bulk + mbarrier, one private pipeline per warp: a tile is contiguous in the
+// [tau][y][x] layout), so HBM latency overlaps the sweeps.
+//
+// CG fusion (FUSEP): v := pr + beta*pold is formed on the fly and written to pnew; p.Ap = |M p|^2 is
+// accumulated as sum w^2 (identical in exact arithmetic to dot(p, M^T M p)); the last CTA folds the per-CTA
+// partials in index order and publishes alpha (see cg.cu).
+#include "elph_internal.cuh"
+
+namespace {
+
+constexpr int kStages = 2;
+
+struct SqParams {
+    const double* __restrict__ v;
+    double* __restrict__ y;
+    const double* __restrict__ D;
+    const double* __restrict__ pr;
+    const double* __restrict__ pold;
+    double* __restrict__ pnew;
+    double* __restrict__ partial;
+    CgScalars* S;
+    unsigned int* ticket;
+    long long v_stride, y_stride, D_stride;
+    int L, Ly, C;
+    double c0, s0, c1, s1, c2, s2, c3, s3;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int NSEG, int PY>
+struct Tile {
+    double a[PY][NSEG];
+};
+
+// ---- colour groups on a register tile ---------------------------------------------------------------------
+template <int NSEG, int PY>
+__device__ __forceinline__ void g0_x_even(Tile<NSEG, PY>& t, double c, double s) {
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double o = __shfl_xor_sync(0xffffffffu, t.a[r][q], 1);
+            t.a[r][q] = c * t.a[r][q] + s * o;
+        }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g1_x_odd(Tile<NSEG, PY>& t, double c, double s, int lane) {
+    const int partner = (lane & 1) ? ((lane + 1) & 31) : ((lane + 31) & 31);
+#pragma unroll
+    for (int r = 0; r < PY; ++r) {
+        double o[NSEG];
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            // lane 0 is read only by lane 31 (whose partner sits in the NEXT x-segment), lane 31 only by lane 0
+            double send = t.a[r][q];
+            if (NSEG > 1) {
+                const double nxt = t.a[r][(q + 1) % NSEG], prv = t.a[r][(q + NSEG - 1) % NSEG];
+                send = (lane == 0) ? nxt : ((lane == 31) ? prv : send);
+            }
+            o[q] = __shfl_sync(0xffffffffu, send, partner);
+        }
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) t.a[r][q] = c * t.a[r][q] + s * o[q];
+    }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g2_y_even(Tile<NSEG, PY>& t, double c, double s) {
+#pragma unroll
+    for (int r = 0; r < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = c * t1 + s * t2;
+            t.a[r + 1][q] = c * t2 + s * t1;
+        }
+}
+
+// interior odd pairs (1,2),(3,4),...,(PY-3,PY-2); the edge rows 0 and PY-1 pair with the neighbouring tiles
+template <int NSEG, int PY>
+__device__ __forceinline__ void g3_y_odd(Tile<NSEG, PY>& t, double c, double s, const double (&above)[NSEG],
+                                         const double (&below)[NSEG]) {
+#pragma unroll
+    for (int r = 1; r + 1 < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = c * t1 + s * t2;
+            t.a[r + 1][q] = c * t2 + s * t1;
+        }
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        t.a[0][q] = c * t.a[0][q] + s * above[q];
+        t.a[PY - 1][q] = c * t.a[PY - 1][q] + s * below[q];
+    }
+}
+
+// publish the tile-edge rows, barrier, fetch the neighbours' edge rows
+template <int NSEG, int PY>
+__device__ __forceinline__ void exchange_edges(const Tile<NSEG, PY>& t, double* strip, int warp, int nwarps, int lane,
+                                               double (&above)[NSEG], double (&below)[NSEG]) {
+    constexpr int LX = 32 * NSEG;
+    double* mine = strip + (size_t)warp * 2 * LX;
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        mine[32 * q + lane] = t.a[0][q];
+        mine[LX + 32 * q + lane] = t.a[PY - 1][q];
+    }
+    __syncthreads();
+    const int up = (warp == 0) ? nwarps - 1 : warp - 1;
+    const int dn = (warp + 1 == nwarps) ? 0 : warp + 1;
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        above[q] = strip[(size_t)up * 2 * LX + LX + 32 * q + lane];  // last row of the tile above
+        below[q] = strip[(size_t)dn * 2 * LX + 32 * q + lane];       // first row of the tile below
+    }
+}
+
+template <int NSEG, int PY, bool FUSEP, int MAXT>
+__global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
+    constexpr int LX = 32 * NSEG;
+    constexpr int TILE = PY * LX;                      // doubles per tile
+    constexpr int NT = FUSEP ? 3 : 2;                  // tiles per stage: v (or pr, pold) and D
+    constexpr uint32_t STAGE_BYTES = NT * TILE * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ bool is_last;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int L = P.L;
+    const int N = LX * P.Ly;
+    const int a = blockIdx.x * P.C;
+    const int nout = min(P.C, L - a);
+    const int nsteps = nout + 1;
+
+    double beta = 0.0;
+    if (FUSEP) {
+        if (P.S->done) return;
+        beta = P.S->beta;
+    }
+    const double* __restrict__ vin = FUSEP ? P.pr : P.v + (size_t)blockIdx.y * P.v_stride;
+    const double* __restrict__ D = P.D + (size_t)blockIdx.y * P.D_stride;
+    double* __restrict__ y = P.y + (size_t)blockIdx.y * P.y_stride;
+
+    double* stage_base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kStages * NT * TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * kStages * STAGE_BYTES) + warp * kStages;
+    double* strips = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * kStages * STAGE_BYTES + (size_t)nwarps * kStages * 8);
+    const size_t tile_off = (size_t)warp * TILE;  // offset of this warp's rows inside a slice
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kStages; ++k) mbar_init(&bars[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue = [&](int j) {
+        if (lane == 0) {
+            int tau = a + j;
+            if (tau >= L) tau -= L;
+            const int st = j % kStages;
+            double* dst = stage_base + (size_t)st * NT * TILE;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bars[st], STAGE_BYTES);
+            const size_t g = (size_t)tau * N + tile_off;
+            bulk_g2s(dst, vin + g, TILE * sizeof(double), &bars[st]);
+            if (FUSEP) bulk_g2s(dst + TILE, P.pold + g, TILE * sizeof(double), &bars[st]);
+            bulk_g2s(dst + (NT - 1) * TILE, D + g, TILE * sizeof(double), &bars[st]);
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < kStages; ++j)
+        if (j < nsteps) issue(j);
+
+    Tile<NSEG, PY> vprev, wprev, t, u;
+    {   // v(a-1), straight from global (coalesced, once per chunk)
+        const int taum = (a == 0) ? L - 1 : a - 1;
+        const size_t g = (size_t)taum * N + tile_off;
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const size_t e = g + r * LX + 32 * q + lane;
+                vprev.a[r][q] = FUSEP ? fma(beta, P.pold[e], P.pr[e]) : vin[e];
+                wprev.a[r][q] = 0.0;
+            }
+    }
+
+    double acc = 0.0;
+    int xbuf = 0;
+    double above[NSEG], below[NSEG];
+    for (int j = 0; j < nsteps; ++j) {
+        int tau = a + j;
+        if (tau >= L) tau -= L;
+        const int st = j % kStages;
+        const double* sv = stage_base + (size_t)st * NT * TILE;
+        const double* sD = sv + (NT - 1) * TILE;
+        mbar_wait(&bars[st], (uint32_t)((j / kStages) & 1));
+        // t = D(tau) .* v(tau-1)
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) t.a[r][q] = sD[r * LX + 32 * q + lane] * vprev.a[r][q];
+        // t = K t : g0, g1, g2, g3
+        g0_x_even(t, P.c0, P.s0);
+        g1_x_odd(t, P.c1, P.s1, lane);
+        g2_y_even(t, P.c2, P.s2);
+        exchange_edges(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+        xbuf ^= 1;
+        g3_y_odd(t, P.c3, P.s3, above, below);
+        // w(tau) = v(tau) -/+ t
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const int e = r * LX + 32 * q + lane;
+                const double vc = FUSEP ? fma(beta, sv[TILE + e], sv[e]) : sv[e];
+                if (FUSEP && j < nout) P.pnew[(size_t)tau * N + tile_off + e] = vc;
+                const double w = (tau == 0) ? (vc + t.a[r][q]) : (vc - t.a[r][q]);
+                t.a[r][q] = w;
+                vprev.a[r][q] = vc;
+                if (FUSEP && j < nout) acc = fma(w, w, acc);
+            }
+        if (j >= 1) {
+            // u = K^T w(tau) : g3, g2, g1, g0
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) u.a[r][q] = t.a[r][q];
+            exchange_edges(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+            xbuf ^= 1;
+            g3_y_odd(u, P.c3, P.s3, above, below);
+            g2_y_even(u, P.c2, P.s2);
+            g1_x_odd(u, P.c1, P.s1, lane);
+            g0_x_even(u, P.c0, P.s0);
+            // y(tau-1) = w(tau-1) -/+ D(tau) .* u     ('+' on the antiperiodic wrap tau = 0)
+            const int taum = (tau == 0) ? L - 1 : tau - 1;
+            const size_t g = (size_t)taum * N + tile_off;
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) {
+                    const int e = r * LX + 32 * q + lane;
+                    const double du = sD[e] * u.a[r][q];
+                    y[g + e] = (tau == 0) ? (wprev.a[r][q] + du) : (wprev.a[r][q] - du);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) wprev.a[r][q] = t.a[r][q];
+        __syncwarp();  // every lane is done reading this stage
+        if (j + kStages < nsteps) issue(j + kStages);
+    }
+
+    if (FUSEP) {
+        // per-CTA partial of p.Ap = |M p|^2 over the CTA's own slices, then last-CTA fold (index order)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int k = 0; k < nwarps; ++k) s += red[k];
+            P.partial[blockIdx.x] = s;
+            __threadfence();
+            const unsigned int n = atomicAdd(P.ticket, 1u);
+            is_last = (n == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            double s = 0.0;
+            for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += ((volatile double*)P.partial)[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            __syncthreads();
+            if (lane == 0) red[warp] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double pAp = 0.0;
+                for (int k = 0; k < nwarps; ++k) pAp += red[k];
+                P.S->pAp = pAp;
+                P.S->alpha = P.S->rdotz / pAp;
+                *P.ticket = 0u;
+            }
+        }
+    }
+}
+
+template <int NSEG, int PY, bool FUSEP, int MAXT>
+void launch_sq(elph_handle* h, const SqParams& P, dim3 grid, int nwarps) {
+    constexpr int LX = 32 * NSEG;
+    constexpr int NT = FUSEP ? 3 : 2;
+    const size_t smem = (size_t)nwarps * kStages * NT * PY * LX * sizeof(double) + (size_t)nwarps * kStages * 8 +
+                        2ull * nwarps * 2 * LX * sizeof(double);
+    ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "square kernel: tile pipeline does not fit in shared memory");
+    ELPH_CUDA(cudaFuncSetAttribute(mtm_square_kernel<NSEG, PY, FUSEP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)h->smem_optin));
+    mtm_square_kernel<NSEG, PY, FUSEP, MAXT><<<grid, nwarps * 32, smem, h->stream>>>(P);
+    ELPH_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+}  // namespace
+
+// Recognise the periodic square lattice with the reference's colouring and uniform (cosh, sinh) per colour.
+void elph_detect_square(elph_handle* h, const std::vector<double2>& cs) {
+    h->sq.enabled = false;
+    if (h->model != ELPH_MODEL_HOLSTEIN || h->ngroups != 4) return;
+    const int N = h->N;
+    for (int Lx = 32; Lx <= 128; Lx += 32) {
+        if (N % Lx) continue;
+        const int Ly = N / Lx;
+        if (Ly < 4 || (Ly & 1) || Lx > 128) continue;
+        if (h->Nb != 2 * N) continue;
+        bool ok = true;
+        for (int g = 0; g < 4 && ok; ++g) {
+            const int lo = h->goff_host[g], hi = h->goff_host[g + 1];
+            if (hi - lo != N / 2) { ok = false; break; }
+            std::vector<char> seen(N, 0);
+            for (int b = lo; b < hi && ok; ++b) {
+                int i = h->bonds_host[b].x, j = h->bonds_host[b].y;
+                if (cs[b].x != cs[lo].x || cs[b].y != cs[lo].y) { ok = false; break; }
+                // canonical "first" site of the bond in each group
+                int xi = i % Lx, yi = i / Lx, xj = j % Lx, yj = j / Lx;
+                bool match = false;
+                if (g < 2) {   // x-bond: same row, x' = x+1 mod Lx with x parity = g
+                    if (yi == yj) {
+                        if ((xi + 1) % Lx == xj && (xi & 1) == g) match = true;
+                        else if ((xj + 1) % Lx == xi && (xj & 1) == g) { match = true; std::swap(i, j); }
+                    }
+                } else {       // y-bond: same column, y' = y+1 mod Ly with y parity = g-2
+                    if (xi == xj) {
+                        if ((yi + 1) % Ly == yj && (yi & 1) == g - 2) match = true;
+                        else if ((yj + 1) % Ly == yi && (yj & 1) == g - 2) { match = true; std::swap(i, j); }
+                    }
+                }
+                if (!match || seen[i]) ok = false;
+                seen[i] = 1;
+            }
+        }
+        if (!ok) continue;
+        h->sq.enabled = true;
+        h->sq.Lx = Lx;
+        h->sq.Ly = Ly;
+        for (int g = 0; g < 4; ++g) {
+            h->sq.c[g] = cs[h->goff_host[g]].x;
+            h->sq.s[g] = cs[h->goff_host[g]].y;
+        }
+        return;
+    }
+}
+
+bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
+    if (!h->sq.enabled || h->sq_disable) return false;
+    if (a.partial_dot && !a.cg_S) return false;
+    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
+    const bool fusep = (a.cg_S != nullptr);
+    // tile shape: PY rows per warp
+    int PY;
+    if (Lx == 32) PY = (Ly % 16 == 0 && h->sq_py != 8) ? 16 : 8;
+    else if (Lx == 128) PY = 4;
+    else PY = 8;
+    if (h->sq_py == 4 && Lx == 64) PY = 4;
+    if (Ly % PY) return false;
+    const int nwarps = Ly / PY;
+    if (nwarps > 32 || nwarps < 2) return false;
+    SqParams P;
+    P.v = a.v; P.y = a.y; P.D = a.D ? a.D : h->d_D;
+    P.pr = a.cg_pr; P.pold = a.cg_pold; P.pnew = a.cg_pnew; P.partial = a.partial_dot; P.S = a.cg_S; P.ticket = a.cg_ticket;
+    P.v_stride = a.v_stride; P.y_stride = a.y_stride; P.D_stride = a.D_stride;
+    P.L = h->L; P.Ly = Ly;
+    int C = h->chunk_override;
+    if (C <= 0) {
+        // halo overhead is one extra K-sweep and one extra v slice per chunk: favour long chunks once the
+        // machine is covered ~4x, otherwise split finer
+        // measured on B200 (32x32xL200, 16..128 replicas): C = 4 is the optimum once the grid covers the
+        // machine several times (5.7-6.2 TB/s); longer chunks lose more to the tail than they save in halo
+        C = 1;
+        const int64_t want = 6LL * h->sm_count;
+        for (int c : {4, 2}) {
+            if (a.nbatch * ((h->L + c - 1) / c) >= want) { C = c; break; }
+        }
+    }
+    if (C > h->L) C = h->L;
+    P.C = C;
+    P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
+    P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
+    const int nchunks = (h->L + C - 1) / C;
+    dim3 grid(nchunks, (unsigned)a.nbatch);
+    if (fusep) ELPH_REQUIRE(nchunks <= h->partial_cap, ELPH_ERR_INVALID, "partial buffer too small");
+    if (a.npartial) *a.npartial = nchunks;
+#define SQ_CASE(NS, PYV, MAXT)                                               \
+    if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {                 \
+        if (fusep) launch_sq<NS, PYV, true, MAXT>(h, P, grid, nwarps);       \
+        else launch_sq<NS, PYV, false, MAXT>(h, P, grid, nwarps);            \
+        return true;                                                         \
+    }
+    SQ_CASE(1, 16, 256)
+    SQ_CASE(1, 8, 256)
+    SQ_CASE(2, 8, 256)
+    SQ_CASE(2, 4, 512)
+    SQ_CASE(3, 8, 256)
+    SQ_CASE(4, 4, 512)
+#undef SQ_CASE
+    return false;
+}

@@ -23,6 +23,9 @@ CASES = [
     ("triangular", 5, 1.0, 0.05),
     ("chain", 6, 1.0, 0.1),
     ("square", 12, 4.0, 0.1),
+    # Lx = 32, 64: served by the register/shuffle square-lattice kernel (mtm_square.cu)
+    ("square", 32, 0.7, 0.1),
+    ("square", 64, 0.3, 0.1),
 ]
 
 
@@ -62,6 +65,39 @@ def test_matvecs(pair, chunk):
         fe(ye, em, v)
         assert relerr(ye, yo) <= MATVEC_TOL, fe.__name__
     em._call("elph_set_chunk", 0)
+
+
+def test_square_kernel_selected_and_matches_generic(pair):
+    """Lx in {32, 64}: the register/shuffle kernel is used, for every tile shape / chunk length, and agrees
+    with the generic shared-memory kernel (and hence the oracle) to rounding."""
+    import ctypes as C
+    import elphdynamics_b200 as E
+    om, em, rng = pair
+    sq, ng = C.c_int32(), C.c_int32()
+    em._call("elph_get_kernel_info", C.byref(sq), C.byref(ng))
+    assert ng.value == len(om.group_offsets) - 1
+    side = om.lat.L1
+    assert bool(sq.value) == (om.geom_defs == __import__("oracle.lattice", fromlist=["x"]).SQUARE_BONDS and side in (32, 64))
+    if not sq.value:
+        return
+    v = rng.normal(size=om.Ndim)
+    yo = np.zeros(om.Ndim)
+    om.mulMTM(yo, v)
+    yg = np.zeros(om.Ndim)
+    em._call("elph_set_tuning", 1, 1)
+    E.mulMTM_(yg, em, v)
+    em._call("elph_set_tuning", 1, 0)
+    assert relerr(yg, yo) <= MATVEC_TOL
+    for py in (0, 8, 4):
+        em._call("elph_set_tuning", 2, py)
+        for chunk in (0, 1, 2, 5, om.L):
+            em._call("elph_set_tuning", 0, chunk)
+            ys = np.zeros(om.Ndim)
+            E.mulMTM_(ys, em, v)
+            assert relerr(ys, yo) <= MATVEC_TOL, (py, chunk)
+            assert relerr(ys, yg) <= 1e-14, (py, chunk)
+    em._call("elph_set_tuning", 2, 0)
+    em._call("elph_set_tuning", 0, 0)
 
 
 def test_mulMTM_batch(pair):
@@ -199,8 +235,9 @@ def test_kpm_setup_apply_and_pcg(pair):
     if not Po.active:
         return
     assert np.array_equal(Pe.orders(), Po.order)
-    for w in (0, len(Po.order) - 1):
-        assert relerr(Pe.coeff(w), Po.coeff[w]) <= 1e-6
+    assert abs(info.lambda_lo - Po.lam_lo) <= 1e-6 * Po.lam_lo and abs(info.lambda_hi - Po.lam_hi) <= 1e-6 * Po.lam_hi
+    # (high-order Chebyshev coefficients amplify the ~1e-8 window difference, so they are compared below
+    #  at identical windows, to 1e-12)
     # apply parity at identical coefficients: feed the oracle the engine's spectral window
     Po.lam_lo, Po.lam_hi = info.lambda_lo, info.lambda_hi
     Po.lam_avg, Po.lam_mag = (Po.lam_hi + Po.lam_lo) / 2, (Po.lam_hi - Po.lam_lo) / 2
