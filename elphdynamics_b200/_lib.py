@@ -117,6 +117,14 @@ def load() -> C.CDLL:
         "elph_dSbdx": (i32, [H, i32, dp]),
         "elph_calc_dSdx": (i32, [H, dp, dp, i32, dp, dp, C.POINTER(SolveInfo)]),
         "elph_langevin_step": (i32, [H, i32, dbl, dp, dp, dp, dp, dp, i32, ip, C.POINTER(SolveInfo), C.POINTER(SolveInfo)]),
+        "elph_hmc_set_v": (i32, [H, dp]),
+        "elph_hmc_get": (i32, [H, i32, dp]),
+        "elph_hmc_refresh_v": (i32, [H, dbl, dp]),
+        "elph_hmc_refresh_phi": (i32, [H, dp, dp, dp]),
+        "elph_hmc_calc_Oinv": (i32, [H, i32, dp, dbl, ip, C.POINTER(i32)]),
+        "elph_hmc_calc_H": (i32, [H, dp, dp, dp]),
+        "elph_hmc_calc_dSdx": (i32, [H, i32, dp]),
+        "elph_hmc_update": (i32, [H, dbl, i64, i64, dbl, dp, dp, dp, dp, i32, dbl, C.POINTER(i32), dp, dp, dp, C.POINTER(i32)]),
         "elph_dev_mulMTM": (i32, [H, C.c_void_p, C.c_void_p]),
         "elph_dev_mulM": (i32, [H, C.c_void_p, C.c_void_p]),
         "elph_dev_mulMT": (i32, [H, C.c_void_p, C.c_void_p]),

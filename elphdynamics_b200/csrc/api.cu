@@ -273,6 +273,7 @@ void destroy(elph_handle* h) {
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
     elph_kpm_free(h);
+    elph_hmc_free(h);
     void* ptrs[] = {h->d_bonds, h->d_goff, h->d_cs, h->d_lam, h->d_lam2, h->d_mu, h->d_omega, h->d_omega4, h->d_x, h->d_D,
                     h->d_Q, h->d_Mass, h->d_t, h->d_alpha, h->d_alpha2, h->d_ph_col, h->d_col_ph, h->d_col_bond,
                     h->d_primary_ph, h->d_grp_start, h->d_grp_members, h->d_tprime, h->d_va, h->d_vb, h->d_vc, h->d_b,
@@ -651,6 +652,116 @@ int32_t elph_langevin_step(elph_handle* h, int32_t method, double dt, const doub
         if (g2) upload_vec(h, g2, h->d_g2, h->N);
         elph_langevin_step_dev(h, method, dt, h->d_vc, h->d_g, h->d_g2, arnoldi1, arnoldi2, use_precond != 0, iters, info1, info2);
         ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// ------------------------------------------------------------------------------- HMC (src/HMC.jl)
+int32_t elph_hmc_set_v(elph_handle* h, const double* v) {
+    ENTER(h) {
+        elph_hmc_ensure(h);
+        upload_vec(h, v, h->hmc.v, h->Nph);
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_hmc_get(elph_handle* h, int32_t which, double* out) {
+    ENTER(h) {
+        elph_hmc_ensure(h);
+        HmcState& S = h->hmc;
+        const double* src[] = {S.v, S.phip, S.phim, S.Lphip, S.Lphim, S.Op, S.Om, S.Lam, S.dS};
+        ELPH_REQUIRE(which >= 0 && which <= 8, ELPH_ERR_INVALID, "unknown HMC vector id");
+        const bool dof = (which == 0 || which == 8);
+        download_vec(h, src[which], out, dof ? h->Nph : h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_hmc_refresh_v(elph_handle* h, double alpha, const double* R) {
+    ENTER(h) {
+        ELPH_REQUIRE(alpha >= 0.0 && alpha < 1.0, ELPH_ERR_INVALID, "alpha must be in [0,1)");
+        elph_hmc_ensure(h);
+        upload_vec(h, R, h->d_vc, h->Nph);
+        elph_hmc_refresh_v_dev(h, alpha, h->d_vc);
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_hmc_refresh_phi(elph_handle* h, const double* R_plus, const double* R_minus, double* S) {
+    ENTER(h) {
+        elph_hmc_ensure(h);
+        upload_vec(h, R_plus, h->hmc.Rp, h->N);
+        upload_vec(h, R_minus, h->hmc.Rm, h->N);
+        const double s = elph_hmc_refresh_phi_dev(h);
+        if (S) *S = s;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_hmc_calc_Oinv(elph_handle* h, int32_t use_precond, const double* arnoldi_noise, double power, int64_t* iters,
+                           int32_t* flag) {
+    ENTER(h) {
+        elph_hmc_ensure(h);
+        int64_t it = 0;
+        int fl = 0;
+        elph_hmc_calc_Oinv_dev(h, use_precond != 0, arnoldi_noise, power, &it, &fl);
+        if (iters) *iters = it;
+        if (flag) *flag = fl;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_hmc_calc_H(elph_handle* h, double* H, double* S, double* K) {
+    ENTER(h) {
+        elph_hmc_ensure(h);
+        double a, b, c;
+        elph_hmc_calc_H_dev(h, &a, &b, &c);
+        if (H) *H = a;
+        if (S) *S = b;
+        if (K) *K = c;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_hmc_calc_dSdx(elph_handle* h, int32_t fermion_only, double* dSdx) {
+    ENTER(h) {
+        elph_hmc_ensure(h);
+        ELPH_CUDA(cudaMemsetAsync(h->hmc.dS, 0, h->Ndof * sizeof(double), h->stream));
+        elph_hmc_calc_dSfdx_dev(h, h->hmc.dS);
+        if (!fermion_only) elph_dSbdx_dev(h, h->hmc.dS, false);
+        download_vec(h, h->hmc.dS, dSdx, h->Nph);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_hmc_update(elph_handle* h, double dt, int64_t Nt, int64_t Nb, double alpha, const double* R_v, const double* R_plus,
+                        const double* R_minus, const double* arnoldi_noise, int32_t use_precond, double uniform,
+                        int32_t* accepted, double* iters, double* H0, double* H1, int32_t* flag) {
+    ENTER(h) {
+        ELPH_REQUIRE(Nt >= 0 && Nb >= 1 && dt > 0.0, ELPH_ERR_INVALID, "bad HMC parameters");
+        ELPH_REQUIRE(alpha >= 0.0 && alpha < 1.0, ELPH_ERR_INVALID, "alpha must be in [0,1)");
+        ELPH_REQUIRE(!use_precond || arnoldi_noise, ELPH_ERR_INVALID, "arnoldi_noise needs (Nt+2)*2*Nsites values");
+        if (h->Ndof == 0) {  // update! returns (true, 0) when there is nothing to update (:313,:331-333)
+            if (accepted) *accepted = 1;
+            if (iters) *iters = 0.0;
+            return ELPH_OK;
+        }
+        elph_hmc_ensure(h);
+        upload_vec(h, R_v, h->d_vc, h->Nph);
+        upload_vec(h, R_plus, h->hmc.Rp, h->N);
+        upload_vec(h, R_minus, h->hmc.Rm, h->N);
+        elph_hmc_update_dev(h, dt, (int)Nt, (int)Nb, alpha, h->d_vc, use_precond != 0, arnoldi_noise, uniform, accepted, iters, H0,
+                            H1, flag);
         return ELPH_OK;
     }
     ELPH_CATCH(h)

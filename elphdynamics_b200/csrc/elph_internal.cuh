@@ -99,8 +99,17 @@ struct KpmState {
     cplx* d_nu = nullptr;         // [L][N] complex work vector (frequency space)
 };
 
+// HybridMonteCarlo work vectors (src/HMC.jl:20-279), engine layout, allocated on first use
+struct HmcState {
+    bool init = false;
+    double *v = nullptr, *v0 = nullptr, *x0 = nullptr, *dS = nullptr, *y = nullptr, *Q = nullptr;   // Ndof
+    double *Lam = nullptr, *Rp = nullptr, *Rm = nullptr, *phip = nullptr, *phim = nullptr;        // Ndim
+    double *Lphip = nullptr, *Lphim = nullptr, *Op = nullptr, *Om = nullptr, *u = nullptr;        // Ndim
+};
+
 struct elph_handle {
     std::string err;
+    HmcState hmc;
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -263,6 +272,18 @@ void elph_muldMdx_dev(elph_handle* h, const double* u, const double* v, double* 
                       bool shifted);
 void elph_dSbdx_dev(elph_handle* h, double* dSbdx, bool shifted);
 void elph_Sb_dev(elph_handle* h, bool shifted, double* host_out);
+
+// hmc.cu
+void elph_hmc_ensure(elph_handle* h);
+void elph_hmc_free(elph_handle* h);
+void elph_hmc_refresh_v_dev(elph_handle* h, double alpha, const double* R_dev);
+double elph_hmc_refresh_phi_dev(elph_handle* h);
+void elph_hmc_calc_Oinv_dev(elph_handle* h, bool use_precond, const double* arnoldi_host, double power, int64_t* iters, int* flag);
+void elph_hmc_calc_H_dev(elph_handle* h, double* H, double* S, double* K);
+void elph_hmc_calc_dSfdx_dev(elph_handle* h, double* dS);
+void elph_hmc_update_dev(elph_handle* h, double dt, int Nt, int Nb, double alpha, const double* Rv_dev, bool use_precond,
+                         const double* arnoldi_host, double uniform, int32_t* accepted, double* iters_out, double* H0out,
+                         double* H1out, int32_t* flag_out);
 
 // dynamics.cu
 void elph_calc_dSdx_dev(elph_handle* h, const double* g_dev, const double* arnoldi_host, bool use_precond, double* dSdx_dev,

@@ -1,0 +1,94 @@
+"""Host-side mirror of ``src/HMC.jl`` on top of libelph_b200.so.
+
+``update_(model, hmc, fa, P, ...)`` runs one whole HMC trajectory on the device (leapfrog or the
+multi-timestep integrator); the Metropolis decision uses the injected uniform exactly like
+``rand(model.rng) < P`` in the reference.  All noise is injected by the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import ptr
+from .models import AbstractModel, _f64
+
+_IDS = {"v": 0, "phi_plus": 1, "phi_minus": 2, "Lphi_plus": 3, "Lphi_minus": 4, "O_plus": 5, "O_minus": 6, "Lambda": 7, "dSdx": 8}
+
+
+class HybridMonteCarlo:
+    """``HybridMonteCarlo(model, dt, tr, alpha, Nb)`` (src/HMC.jl:188-233): Nt = round(tr/dt), dt' = dt/Nb."""
+
+    def __init__(self, model: AbstractModel, dt: float, tr: float, alpha: float = 0.0, Nb: int = 1):
+        if not 0.0 <= alpha < 1.0:
+            raise ValueError("alpha must be in [0, 1)")
+        self.model = model
+        self.Ndof, self.Ndim = model.Ndof, model.Ndim
+        self.dt, self.tr, self.alpha, self.Nb = float(dt), float(tr), float(alpha), int(Nb)
+        self.Nt = int(round(tr / dt))
+        self.dtp = self.dt / self.Nb
+        self.accepted = False
+        self.H0 = self.H1 = float("nan")
+        self.flag = 0
+
+    def get(self, name: str) -> np.ndarray:
+        n = self.Ndof if name in ("v", "dSdx") else self.Ndim
+        out = np.empty(n)
+        self.model._call("elph_hmc_get", _IDS[name], ptr(out))
+        return out
+
+    def set_v(self, v):
+        self.model._call("elph_hmc_set_v", ptr(_f64(v, self.Ndof, "v")))
+
+
+def _use_p(P):
+    return 0 if (P is None or getattr(P, "is_identity", False)) else 1
+
+
+def refresh_v_(hmc: HybridMonteCarlo, model, fa, R):
+    """``refresh_v!`` (src/HMC.jl:648-660); ``fa`` must have its mass matrix uploaded (update_M_)."""
+    model._call("elph_hmc_refresh_v", hmc.alpha, ptr(_f64(R, model.Ndof, "R")))
+
+
+def refresh_phi_(hmc: HybridMonteCarlo, model, R_plus, R_minus) -> float:
+    """``refresh_ϕ!`` (src/HMC.jl:666-692)."""
+    S = C.c_double()
+    model._call("elph_hmc_refresh_phi", ptr(_f64(R_plus, model.Ndim, "R_plus")), ptr(_f64(R_minus, model.Ndim, "R_minus")), C.byref(S))
+    return S.value
+
+
+def calc_Oinv_(hmc: HybridMonteCarlo, model, P=None, power: float = 1.0, arnoldi_noise=None):
+    """``calc_O⁻¹Λϕ!`` (src/HMC.jl:820-915) -> (iters, flag)."""
+    it, fl = C.c_int64(), C.c_int32()
+    an = None if arnoldi_noise is None else ptr(_f64(arnoldi_noise, 2 * model.Nsites, "arnoldi_noise"))
+    model._call("elph_hmc_calc_Oinv", _use_p(P), an, float(power), C.byref(it), C.byref(fl))
+    return int(it.value), int(fl.value)
+
+
+def calc_H(hmc: HybridMonteCarlo, model, fa):
+    """``calc_H`` (src/HMC.jl:698-705) -> (H, S, K)."""
+    H, S, K = C.c_double(), C.c_double(), C.c_double()
+    model._call("elph_hmc_calc_H", C.byref(H), C.byref(S), C.byref(K))
+    return H.value, S.value, K.value
+
+
+def calc_dSdx_(hmc: HybridMonteCarlo, model, fermion_only: bool = False) -> np.ndarray:
+    """``fill!(dSdx,0); calc_dSdx!`` / ``calc_dSfdx!`` (src/HMC.jl:749-814)."""
+    out = np.empty(model.Ndof)
+    model._call("elph_hmc_calc_dSdx", 1 if fermion_only else 0, ptr(out))
+    return out
+
+
+def update_(model, hmc: HybridMonteCarlo, fa, P=None, *, R_v, R_plus, R_minus, arnoldi_noises=None, uniform: float):
+    """``update!(model, hmc, fa, P)`` (src/HMC.jl:310-335) -> ``(accepted, iters)``."""
+    acc, fl = C.c_int32(), C.c_int32()
+    it, H0, H1 = C.c_double(), C.c_double(), C.c_double()
+    an = None
+    if _use_p(P):
+        an = ptr(_f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in arnoldi_noises]),
+                      (hmc.Nt + 2) * 2 * model.Nsites, "arnoldi_noises"))
+    model._call("elph_hmc_update", hmc.dt, hmc.Nt, hmc.Nb, hmc.alpha, ptr(_f64(R_v, model.Ndof, "R_v")),
+                ptr(_f64(R_plus, model.Ndim, "R_plus")), ptr(_f64(R_minus, model.Ndim, "R_minus")), an, _use_p(P), float(uniform),
+                C.byref(acc), C.byref(it), C.byref(H0), C.byref(H1), C.byref(fl))
+    hmc.accepted, hmc.H0, hmc.H1, hmc.flag = bool(acc.value), H0.value, H1.value, int(fl.value)
+    return hmc.accepted, it.value

@@ -316,3 +316,99 @@ def kpm_ldiv_(vout, P, vin):
         vout[:] = vin
         return
     P.model._call("elph_kpm_apply", ptr(_f64(vin, P.model.Ndim, "vin")), ptr(vout))
+
+
+class SSHModel(AbstractModel):
+    """``SSHModel(lattice, beta, dtau; ...)`` (src/SSHModels.jl:79-314): phonons live on bonds and modulate the
+    hopping, ``t' = t - (alpha x + sign(x) alpha2 x^2)``."""
+    kind = SSH
+
+    def __init__(self, lattice: Lattice, beta: float, dtau: float, tol: float = 1e-4, maxiter: int = 10000, device: int = -1):
+        super().__init__()
+        self.lattice = lattice
+        self.beta, self.dtau = float(beta), float(dtau)
+        self.Ltau = int(round(beta / dtau))
+        self.Nsites = lattice.nsites
+        self.Ndim = self.Nsites * self.Ltau
+        self.device = device
+        self.mu = np.zeros(self.Nsites)
+        self.bond_definitions = []
+        self.solver = ConjugateGradient(self.Ndim, tol=tol, maxiter=maxiter)
+        self.Nbonds = self.Nph = self.Ndof = 0
+
+    def assign_mu(self, value, orbit=None):
+        """``assign_μ!`` (src/SSHModels.jl:332-343)."""
+        v = np.asarray(value, dtype=np.float64)
+        sel = slice(None) if orbit is None else (self.lattice.site_to_orbit == orbit)
+        self.mu[sel] = v if v.ndim == 0 else v[sel]
+
+    def assign_hopping(self, t, omega, omega4, alpha, alpha2, o1: int, o2: int, v, name: str = ""):
+        """``assign_hopping!`` (src/SSHModels.jl:319-327); a phonon lives on the bond iff omega != 0."""
+        self.bond_definitions.append(dict(t=float(t), omega=float(omega), omega4=float(omega4), alpha=float(alpha),
+                                          alpha2=float(alpha2), o1=o1, o2=o2, v=tuple(v), name=name))
+
+    def initialize_model_(self):
+        """``initialize_model!`` (src/SSHModels.jl:348-505) + engine creation."""
+        tables, t, om, om4, al, al2, p2b, b2p, names = [], [], [], [], [], [], [], [], []
+        ntypes = 0
+        for i, bd in enumerate(self.bond_definitions):
+            nn = calc_neighbor_table(self.lattice, bd["o1"], bd["o2"], bd["v"])
+            n_new = nn.shape[1]
+            tables.append(nn)
+            t += [bd["t"]] * n_new
+            if bd["omega"] != 0.0:
+                ntypes += 1
+                names.append(bd["name"] if bd["name"] else f"__unnamed_{i}")
+                om += [bd["omega"]] * n_new
+                om4 += [bd["omega4"]] * n_new
+                al += [bd["alpha"]] * n_new
+                al2 += [bd["alpha2"]] * n_new
+                p2b += list(range(i * n_new, (i + 1) * n_new))
+                b2p += list(range((ntypes - 1) * n_new, ntypes * n_new))
+            else:
+                b2p += [-1] * n_new
+        nt = np.concatenate(tables, axis=1) if tables else np.zeros((2, 0), dtype=np.int64)
+        tabs = assemble_checkerboard(nt)
+        self.neighbor_table = tabs.neighbor_table
+        self.checkerboard_perm = np.ascontiguousarray(tabs.checkerboard_perm, dtype=np.int64)
+        self.inv_checkerboard_perm = np.ascontiguousarray(tabs.inv_checkerboard_perm, dtype=np.int64)
+        self.group_sizes = tabs.group_sizes
+        self.t = np.asarray(t, dtype=np.float64)
+        self.omega, self.omega4 = np.asarray(om, dtype=np.float64), np.asarray(om4, dtype=np.float64)
+        self.alpha, self.alpha2 = np.asarray(al, dtype=np.float64), np.asarray(al2, dtype=np.float64)
+        self.phonon_to_bond = np.asarray(p2b, dtype=np.int64)
+        self.bond_to_phonon = np.asarray(b2p, dtype=np.int64)
+        self.nph = ntypes
+        self.Nbonds, self.Nph = self.t.size, self.omega.size
+        self.Ndof = self.Nph * self.Ltau
+        primary = np.arange(self.Ndof, dtype=np.int64)
+        if ntypes > 0:
+            per = self.Ndof // ntypes
+            pf = primary.reshape(ntypes, per)
+            for a in range(ntypes):
+                for b in range(a + 1, ntypes):
+                    if names[a] == names[b] and pf[b, 0] > a * per:
+                        pf[b, :] = np.arange(a * per, (a + 1) * per)
+        self.primary_field = primary
+        ntp = np.ascontiguousarray(self.neighbor_table.T)
+        cfg = Config()
+        cfg.model, cfg.index_base, cfg.device = SSH, 0, self.device
+        cfg.Ltau, cfg.Nsites, cfg.Nbonds, cfg.Nph = self.Ltau, self.Nsites, self.Nbonds, self.Nph
+        cfg.dtau = self.dtau
+        cfg.neighbor_table = ptr(ntp, np.int64)
+        cfg.mu, cfg.omega, cfg.omega4 = ptr(self.mu), ptr(self.omega), ptr(self.omega4)
+        cfg.t, cfg.alpha, cfg.alpha2 = ptr(self.t), ptr(self.alpha), ptr(self.alpha2)
+        cfg.checkerboard_perm = ptr(self.checkerboard_perm, np.int64)
+        cfg.inv_checkerboard_perm = ptr(self.inv_checkerboard_perm, np.int64)
+        cfg.phonon_to_bond = ptr(self.phonon_to_bond, np.int64)
+        cfg.bond_to_phonon = ptr(self.bond_to_phonon, np.int64)
+        cfg.primary_field = ptr(self.primary_field, np.int64)
+        cfg.cg_tol, cfg.cg_maxiter, cfg.cg_kappa_max = self.solver.tol, self.solver.maxiter, self.solver.kappa_max
+        self._create(cfg, [ntp])
+
+    def cosh_sinh(self):
+        """(cosht, sinht) as (Nbonds, Ltau) arrays = C-order view of the reference's (Ltau, Nbonds) matrices."""
+        c = np.empty((self.Nbonds, self.Ltau))
+        s = np.empty((self.Nbonds, self.Ltau))
+        self._call("elph_get_cosh_sinh", ptr(c), ptr(s))
+        return c, s

@@ -230,6 +230,32 @@ int32_t elph_langevin_step(elph_handle* h, int32_t method, double dt, const doub
                            const double* g2, const double* arnoldi1, const double* arnoldi2, int32_t use_precond,
                            int64_t* iters, elph_solve_info* info1, elph_solve_info* info2);
 
+/* ------------------------------------------------------------------------- HMC */
+/* HybridMonteCarlo state (v, phi+-, Lambda phi+-, O^-1 Lambda phi+-, Lambda; src/HMC.jl:20-279) lives in the handle.
+ * elph_hmc_get ids: 0 v, 1 phi+, 2 phi-, 3 Lambda phi+, 4 Lambda phi-, 5 O^-1 Lambda phi+, 6 O^-1 Lambda phi-,
+ * 7 Lambda, 8 dSdx of the last elph_hmc_calc_dSdx.  (For SSH the Lambda operators are no-ops: Lambda phi = M^T R.) */
+int32_t elph_hmc_set_v(elph_handle* h, const double* v);
+int32_t elph_hmc_get(elph_handle* h, int32_t which, double* out);
+/* refresh_v!(hmc,model,fa) src/HMC.jl:648: v = alpha v + sqrt(1-alpha^2) sqrt(M^-1) R, R (Ndof) injected */
+int32_t elph_hmc_refresh_v(elph_handle* h, double alpha, const double* R);
+/* refresh_phi!(hmc,model) src/HMC.jl:666: phi+- = Lambda^-1 M^T R+-, returns S = (R+^2+R-^2)/2 + Sb */
+int32_t elph_hmc_refresh_phi(elph_handle* h, const double* R_plus, const double* R_minus, double* S);
+/* calc_O^-1 Lambda phi!(hmc,model,P,power) src/HMC.jl:820: setup!(P) (2*Nsites Arnoldi values or NULL), two solves
+ * with tol^power; iters = cld(sum,2) when both converge; flag as ldiv! */
+int32_t elph_hmc_calc_Oinv(elph_handle* h, int32_t use_precond, const double* arnoldi_noise, double power, int64_t* iters,
+                           int32_t* flag);
+/* calc_H(hmc,model,fa) src/HMC.jl:698: H = S + K, S = Sf + Sb, K = v.M.v/2 (SSH: primary fields only) */
+int32_t elph_hmc_calc_H(elph_handle* h, double* H, double* S, double* K);
+/* fill!(dSdx,0); calc_dSfdx!(hmc,model) [+ calc_dSbdx!(dSdx,model)] src/HMC.jl:749-814 */
+int32_t elph_hmc_calc_dSdx(elph_handle* h, int32_t fermion_only, double* dSdx);
+/* update!(model,hmc,fa,P) src/HMC.jl:310: one whole trajectory on the device (standard leapfrog for Nb == 1,
+ * multi-timestep otherwise).  Injected: R_v (Ndof), R_plus/R_minus (Ndim), arnoldi_noise ((Nt+2) x 2*Nsites values in
+ * call order, NULL without preconditioner), the Metropolis uniform.  On rejection x is restored and v = -v0.
+ * iters = cld(total, Nt+2) like the reference (which drops the first solve's count in the multi-timestep path, :515). */
+int32_t elph_hmc_update(elph_handle* h, double dt, int64_t Nt, int64_t Nb, double alpha, const double* R_v, const double* R_plus,
+                        const double* R_minus, const double* arnoldi_noise, int32_t use_precond, double uniform,
+                        int32_t* accepted, double* iters, double* H0, double* H1, int32_t* flag);
+
 /* --------------------------------------------------- device-resident (bench) API */
 /* Device pointers, engine layout [tau][site], asynchronous on the handle's stream. */
 int32_t elph_dev_mulMTM(elph_handle* h, const double* v_dev, double* y_dev);

@@ -1,0 +1,171 @@
+"""HMC: oracle invariants (CPU) and GPU parity of the pieces and of whole trajectories (src/HMC.jl)."""
+import numpy as np
+import pytest
+
+from helpers import engine_holstein_like, oracle_holstein, relerr
+from helpers_ssh import engine_ssh_like, oracle_ssh
+from oracle import hmc as ohmc
+from oracle.fourier import FourierAccelerator
+from oracle.kpm import KPMPreconditioner
+from oracle.solvers import ConjugateGradient
+
+
+def _fa(om, mass):
+    fa = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
+    fa.update_Q(0.0, 10.0, mass)
+    fa.update_M(0.0, 10.0, mass, 0.0)
+    return fa
+
+
+# ----------------------------------------------------------------------------- CPU: oracle invariants
+def test_lambda_operators_are_inverse_and_consistent():
+    om, rng = oracle_holstein("square", 3, 0.6, 0.1, lam2=0.05)
+    h = ohmc.HybridMonteCarlo(om, 0.01, 0.05, 0.0, 1)
+    ohmc.update_Lam(h, om)
+    v = rng.normal(size=om.Ndim)
+    a, b = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    ohmc.mulLam(a, v, h, om)
+    ohmc.mulLaminv(b, a, h, om)
+    assert np.abs(b - v).max() < 1e-14
+
+
+def test_hmc_force_is_the_gradient_of_the_action():
+    """dS/dx from calc_dSdx! equals the finite-difference gradient of S(x) = Sb + sum_s phi_s^T Lam (M^T M)^-1 Lam phi_s / 2
+    at fixed pseudofermion fields phi (src/HMC.jl:749-814)."""
+    om, rng = oracle_holstein("square", 2, 0.4, 0.1, lam2=0.03)
+    cg = ConjugateGradient(om.Ndim, tol=1e-7, maxiter=5000)   # tol^2 = 1e-14 for the energies
+    h = ohmc.HybridMonteCarlo(om, 0.01, 0.05, 0.0, 1)
+    ohmc.refresh_phi(h, om, rng.normal(size=om.Ndim), rng.normal(size=om.Ndim))
+
+    def S_of_x():
+        om.update_model()
+        it, flag = ohmc.calc_Oinv(h, om, cg, None, 2.0)
+        assert flag == 0
+        from oracle.action import calc_Sb
+        return ohmc.calc_Sf(h) + calc_Sb(om)
+
+    S_of_x()
+    h.dSdx[:] = 0.0
+    ohmc.calc_dSdx(h, om)
+    grad = h.dSdx.copy()
+    x0 = om.x.copy()
+    eps = 1e-5
+    for k in rng.choice(om.Ndof, size=6, replace=False):
+        om.x[:] = x0
+        om.x[k] += eps
+        sp = S_of_x()
+        om.x[k] -= 2 * eps
+        sm = S_of_x()
+        assert abs((sp - sm) / (2 * eps) - grad[k]) < 2e-5 * max(1.0, abs(grad[k])), k
+    om.x[:] = x0
+    om.update_model()
+
+
+def test_trajectory_conserves_energy_and_is_reversible_in_accept_reject():
+    om, rng = oracle_holstein("square", 2, 0.4, 0.1)
+    cg = ConjugateGradient(om.Ndim, tol=1e-8, maxiter=5000)
+    fa = _fa(om, 1.0)
+    for Nb in (1, 4):
+        x0 = om.x.copy()
+        h = ohmc.HybridMonteCarlo(om, 0.01, 0.1, 0.0, Nb)
+        acc, iters = ohmc.update(om, h, fa, cg, None, rng.normal(size=om.Ndof), rng.normal(size=om.Ndim), rng.normal(size=om.Ndim),
+                                 None, uniform=0.0)
+        assert acc and abs(h.H1 - h.H0) < 5e-3          # symplectic integrator: dH = O(dt^2)
+        h2 = ohmc.HybridMonteCarlo(om, 0.01, 0.1, 0.0, Nb)
+        x1 = om.x.copy()
+        acc, _ = ohmc.update(om, h2, fa, cg, None, rng.normal(size=om.Ndof), rng.normal(size=om.Ndim), rng.normal(size=om.Ndim),
+                             None, uniform=2.0)          # forced rejection
+        assert not acc and np.array_equal(om.x, x1)
+        om.x[:] = x0
+        om.update_model()
+
+
+# ----------------------------------------------------------------------------- GPU parity
+HOLSTEIN = [("square", 4, 1.0, 0.1), ("honeycomb", 3, 0.8, 0.1), ("triangular", 3, 0.6, 0.05)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", HOLSTEIN, ids=lambda c: f"{c[0]}{c[1]}")
+def test_gpu_hmc_pieces_holstein(case):
+    import elphdynamics_b200 as E
+    from elphdynamics_b200 import hmc as ehmc
+    geom, Ls, beta, dtau = case
+    om, rng = oracle_holstein(geom, Ls, beta, dtau, mu=-0.2, lam2=0.04)
+    em = engine_holstein_like(om)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    fo = _fa(om, 1.0)
+    fe = E.FourierAccelerator(em)
+    E.update_Q_(fe, em, 0.0, 10.0, 1.0)
+    E.update_M_(fe, em, 0.0, 10.0, 1.0, 0.0)
+    ho = ohmc.HybridMonteCarlo(om, 0.01, 0.05, 0.3, 1)
+    he = ehmc.HybridMonteCarlo(em, 0.01, 0.05, 0.3, 1)
+    v0 = rng.normal(size=om.Ndof)
+    ho.v[:] = v0
+    he.set_v(v0)
+    R = rng.normal(size=om.Ndof)
+    ohmc.refresh_v(ho, om, fo, R)
+    ehmc.refresh_v_(he, em, fe, R)
+    assert relerr(he.get("v"), ho.v) <= 1e-13
+    Rp, Rm = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    So = ohmc.refresh_phi(ho, om, Rp, Rm)
+    Se = ehmc.refresh_phi_(he, em, Rp, Rm)
+    assert abs(Se - So) <= 1e-12 * abs(So)
+    assert relerr(he.get("phi_plus"), ho.phip) <= 1e-12 and relerr(he.get("phi_minus"), ho.phim) <= 1e-12
+    Po, Pe = KPMPreconditioner(om), E.SymmetricKPMPreconditioner(em)
+    noise = rng.normal(size=2 * om.N)
+    it_o, fl_o = ohmc.calc_Oinv(ho, om, cg, Po, 2.0, noise)
+    it_e, fl_e = ehmc.calc_Oinv_(he, em, Pe, 2.0, noise)
+    assert fl_o == fl_e == 0 and abs(it_o - it_e) <= 2
+    assert relerr(he.get("Lphi_plus"), ho.Lphip) <= 1e-12
+    assert relerr(he.get("O_plus"), ho.Op) <= 1e-7 and relerr(he.get("O_minus"), ho.Om) <= 1e-7
+    Ho, So, Ko = ohmc.calc_H(ho, om, fo)
+    He, Se, Ke = ehmc.calc_H(he, em, fe)
+    assert abs(Ke - Ko) <= 1e-12 * abs(Ko) and abs(Se - So) <= 1e-8 * abs(So) and abs(He - Ho) <= 1e-8 * abs(Ho)
+    ho.dSdx[:] = 0.0
+    ohmc.calc_dSdx(ho, om)
+    assert relerr(ehmc.calc_dSdx_(he, em), ho.dSdx) <= 1e-6      # solves at tol^2 = 1e-10 on both sides
+    ho.dSdx[:] = 0.0
+    ohmc.calc_dSfdx(ho, om)
+    assert relerr(ehmc.calc_dSdx_(he, em, fermion_only=True), ho.dSdx) <= 1e-6
+    em.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Nb", [1, 3])
+@pytest.mark.parametrize("kind", ["holstein", "ssh", "ssh-equiv"])
+def test_gpu_hmc_trajectory(kind, Nb):
+    """Whole update! with identical injected noise: same accept decision, energies and final field."""
+    import elphdynamics_b200 as E
+    from elphdynamics_b200 import hmc as ehmc
+    if kind == "holstein":
+        om, rng = oracle_holstein("square", 4, 0.6, 0.1, mu=-0.3, tol=1e-7)
+        em = engine_holstein_like(om)
+        mass = 1.0
+    else:
+        om, rng = oracle_ssh(Lside=4, beta=0.4, dtau=0.05, tol=1e-7, names=(["a", "a"] if kind == "ssh-equiv" else None))
+        em = engine_ssh_like(om)
+        mass = 0.1
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    fo = _fa(om, mass)
+    fe = E.FourierAccelerator(em)
+    E.update_Q_(fe, em, 0.0, 10.0, mass)
+    E.update_M_(fe, em, 0.0, 10.0, mass, 0.0)
+    dt, tr = 0.01, 0.04
+    for uniform in (0.0, 2.0):       # forced accept, forced reject
+        x0 = om.x.copy()
+        ho = ohmc.HybridMonteCarlo(om, dt, tr, 0.0, Nb)
+        he = ehmc.HybridMonteCarlo(em, dt, tr, 0.0, Nb)
+        Po, Pe = KPMPreconditioner(om), E.SymmetricKPMPreconditioner(em)
+        Rv, Rp, Rm = rng.normal(size=om.Ndof), rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+        noises = [rng.normal(size=2 * om.N) for _ in range(ho.Nt + 2)]
+        acc_o, it_o = ohmc.update(om, ho, fo, cg, Po, Rv, Rp, Rm, noises, uniform)
+        acc_e, it_e = ehmc.update_(em, he, fe, Pe, R_v=Rv, R_plus=Rp, R_minus=Rm, arnoldi_noises=noises, uniform=uniform)
+        assert acc_o == acc_e == (uniform == 0.0)
+        assert abs(it_o - it_e) <= 2
+        assert abs(he.H0 - ho.H0) <= 1e-8 * abs(ho.H0) and abs(he.H1 - ho.H1) <= 1e-7 * abs(ho.H1)
+        if acc_o:
+            assert relerr(em.x - x0, om.x - x0) <= 1e-6
+        else:
+            assert np.array_equal(em.x, x0) and np.array_equal(om.x, x0)
+        assert relerr(he.get("v"), ho.v) <= 1e-6
+    em.close()
