@@ -284,12 +284,14 @@ def main():
         fa = E.FourierAccelerator(em)
         E.update_Q_(fa, em, 0.0, 10.0, 1.0)
         dyn = E.RungeKuttaDynamics(em, 1e-3)
-        nsteps = 3
+        nsteps = 5
         its = []
+        noise = [dict(eta=rng.normal(size=n), g1=rng.normal(size=n), g2=rng.normal(size=n),
+                      arnoldi1=rng.normal(size=2 * om.N), arnoldi2=rng.normal(size=2 * om.N)) for _ in range(nsteps + 1)]
+        E.evolve_(em, dyn, fa, P, **noise[nsteps])   # warm-up
         t0 = time.perf_counter()
-        for _ in range(nsteps):
-            its.append(E.evolve_(em, dyn, fa, P, eta=rng.normal(size=n), g1=rng.normal(size=n), g2=rng.normal(size=n),
-                                 arnoldi1=rng.normal(size=2 * om.N), arnoldi2=rng.normal(size=2 * om.N)))
+        for k in range(nsteps):
+            its.append(E.evolve_(em, dyn, fa, P, **noise[k]))   # noise drawn outside the timed region (stays in the driver)
         dt_l = time.perf_counter() - t0
         extra["langevin_rk_kpm"] = {"steps_per_s": nsteps / dt_l, "pcg_iters_second_solve": its,
                                     "note": "elph_langevin_step through the C ABI with host noise buffers"}

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <complex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -110,6 +111,7 @@ struct HmcState {
 struct elph_handle {
     std::string err;
     HmcState hmc;
+    std::set<const void*> smem_enabled;  // kernels that already have the opt-in shared-memory attribute
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -264,6 +266,7 @@ void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2);
 void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info);
 void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout);
 void elph_kpm_free(elph_handle* h);
+bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, const int* skip);
 void elph_tau_to_omega_dev_skip(elph_handle* h, const double* vin, cplx* vout, const int* skip);
 void elph_omega_to_tau_dev_skip(elph_handle* h, const cplx* vin, double* vout, const int* skip);
 
@@ -288,6 +291,14 @@ void elph_hmc_update_dev(elph_handle* h, double dt, int Nt, int Nb, double alpha
 // dynamics.cu
 void elph_calc_dSdx_dev(elph_handle* h, const double* g_dev, const double* arnoldi_host, bool use_precond, double* dSdx_dev,
                         double* Minv_dev, elph_solve_info* info);
+
+// opt a kernel in to the large dynamic shared-memory carve-out ONCE per handle (the driver call costs
+// microseconds of host time; doing it on every launch made the solver loop launch bound)
+template <typename K>
+static inline void elph_enable_smem(elph_handle* h, K kernel) {
+    if (h->smem_enabled.insert((const void*)kernel).second)
+        ELPH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+}
 
 template <typename T>
 static inline T* elph_dalloc(size_t n) {

@@ -10,9 +10,10 @@
 // Engine layout is [tau][site]; one CTA owns SB consecutive sites for ALL tau, so
 // global accesses are coalesced along the site index and the transform runs entirely
 // in shared memory ([tau][SB] complex, site fastest => conflict-free butterflies,
-// twiddles warp-uniform).  Lengths are arbitrary: a mixed-radix Stockham (autosort,
-// decimation in frequency) with one generic radix-r stage per prime factor
-// (4 preferred over 2x2).  Ltau = 20, 40, 200, 400 factor into {4, 2, 5}.
+// twiddles warp-uniform and staged in shared memory).  Lengths are arbitrary: a
+// mixed-radix Stockham autosort (decimation in frequency).  Radices 2, 3, 4, 5 are
+// register butterflies (one thread = one butterfly); any other prime factor uses a
+// generic O(r)-per-output stage.  Ltau = 20, 40, 200, 400 factor into {4, 2, 5}.
 #include "elph_internal.cuh"
 
 #include <cmath>
@@ -28,13 +29,102 @@ struct FftPlan {
     int rad[kMaxRad];
 };
 
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) {  // a*b + c
     return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
+// multiply by -i*sg (sg = +1 forward, -1 inverse): (x + iy)(-i sg) = sg*y - i sg*x
+__device__ __forceinline__ cplx mul_mi(cplx a, double sg) { return make_double2(sg * a.y, -sg * a.x); }
+__device__ __forceinline__ cplx twid(const cplx* tw, int idx, bool inverse) {
+    cplx w = tw[idx];
+    if (inverse) w.y = -w.y;
+    return w;
+}
 
-// In-place-on-two-buffers Stockham FFT of SB interleaved sequences of length L.
-// x, y: shared buffers [L][SB].  tw: exp(-2 pi i k/L) table in global memory.
+// One Stockham stage of radix R: butterfly (p, q) reads x[q + s(p + m k)], writes y[q + s(R p + j)] * W_L^{p j s}.
+template <int SB, int R>
+__device__ __forceinline__ void stage_radix(const cplx* __restrict__ x, cplx* __restrict__ y, int L, int n, int s,
+                                            const cplx* __restrict__ tw, bool inverse, int site, int slot, int nslots) {
+    const int m = n / R;
+    const int nb = L / R;  // butterflies per sequence
+    const double sg = inverse ? -1.0 : 1.0;
+    for (int bb = slot; bb < nb; bb += nslots) {
+        const int q = bb % s;
+        const int p = bb / s;
+        const int base = q + s * p;
+        cplx a[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) a[k] = x[(size_t)(base + s * m * k) * SB + site];
+        cplx b[R];
+        if (R == 2) {
+            b[0] = cadd(a[0], a[1]);
+            b[1] = csub(a[0], a[1]);
+        } else if (R == 3) {
+            const cplx t = cadd(a[1], a[2]);
+            b[0] = cadd(a[0], t);
+            const cplx mm = make_double2(a[0].x - 0.5 * t.x, a[0].y - 0.5 * t.y);
+            const double h = 0.86602540378443864676;  // sin(2 pi/3)
+            const cplx d = csub(a[1], a[2]);
+            const cplx nn = mul_mi(make_double2(h * d.x, h * d.y), sg);  // -i sg h (a1 - a2)
+            b[1] = cadd(mm, nn);
+            b[2] = csub(mm, nn);
+        } else if (R == 4) {
+            const cplx t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]), t2 = cadd(a[1], a[3]), t3 = mul_mi(csub(a[1], a[3]), sg);
+            b[0] = cadd(t0, t2);
+            b[2] = csub(t0, t2);
+            b[1] = cadd(t1, t3);
+            b[3] = csub(t1, t3);
+        } else {  // R == 5
+            const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;   // cos(2pi/5), cos(4pi/5)
+            const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;    // sin(2pi/5), sin(4pi/5)
+            const cplx t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+            b[0] = make_double2(a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y);
+            const cplx m1 = make_double2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
+            const cplx m2 = make_double2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
+            const cplx n1 = mul_mi(make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y), sg);
+            const cplx n2 = mul_mi(make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y), sg);
+            b[1] = cadd(m1, n1);
+            b[4] = csub(m1, n1);
+            b[2] = cadd(m2, n2);
+            b[3] = csub(m2, n2);
+        }
+        const int obase = q + s * R * p;
+        y[(size_t)obase * SB + site] = b[0];
+#pragma unroll
+        for (int j = 1; j < R; ++j) {
+            // twiddle W_L^{p j s}; p j s <= (m-1)(R-1)s < L, no reduction needed
+            y[(size_t)(obase + s * j) * SB + site] = cmul(b[j], twid(tw, p * j * s, inverse));
+        }
+    }
+}
+
+// generic prime radix r: one thread per output element, O(r) work each
+template <int SB>
+__device__ __forceinline__ void stage_generic(const cplx* __restrict__ x, cplx* __restrict__ y, int L, int n, int s, int r,
+                                              const cplx* __restrict__ tw, bool inverse, int site, int slot, int nslots) {
+    const int m = n / r;
+    const int wstep = L / r;
+    for (int e = slot; e < L; e += nslots) {
+        const int q = e % s;
+        const int pj = e / s;
+        const int j = pj % r;
+        const int p = pj / r;
+        cplx acc = make_double2(0.0, 0.0);
+        const int base = q + s * p;
+        int widx = 0;
+        const int winc = (int)(((long long)j * wstep) % L);
+        for (int k = 0; k < r; ++k) {
+            acc = cfma(x[(size_t)(base + s * m * k) * SB + site], twid(tw, widx, inverse), acc);
+            widx += winc;
+            if (widx >= L) widx -= L;
+        }
+        y[(size_t)e * SB + site] = cmul(acc, twid(tw, p * j * s, inverse));
+    }
+}
+
+// Stockham FFT of SB interleaved sequences of length L held in shared memory (x, y: [L][SB]).
 // Returns the buffer holding the result.  All threads of the CTA must call it.
 template <int SB>
 __device__ cplx* fft_smem(cplx* x, cplx* y, const FftPlan& plan, const cplx* __restrict__ tw, bool inverse) {
@@ -42,40 +132,21 @@ __device__ cplx* fft_smem(cplx* x, cplx* y, const FftPlan& plan, const cplx* __r
     const int site = threadIdx.x % SB;
     const int slot = threadIdx.x / SB;
     const int nslots = blockDim.x / SB;
-    int n = L;  // current sub-transform length
-    int s = 1;  // current stride
+    int n = L, s = 1;
     for (int st = 0; st < plan.nrad; ++st) {
         const int r = plan.rad[st];
-        const int m = n / r;
-        const int wstep = L / r;  // omega_r = W_L^{L/r}
-        // output element e = (p, j, q): index q + s*(r*p + j), inputs q + s*(p + m*k)
-        for (int e = slot; e < L; e += nslots) {
-            const int q = e % s;
-            const int pj = e / s;
-            const int j = pj % r;
-            const int p = pj / r;
-            cplx acc = make_double2(0.0, 0.0);
-            const int base = q + s * p;
-            int widx = 0;  // (j*k*wstep) mod L
-            const int winc = (int)(((long long)j * wstep) % L);
-            for (int k = 0; k < r; ++k) {
-                cplx w = tw[widx];
-                if (inverse) w.y = -w.y;
-                acc = cfma(x[(size_t)(base + s * m * k) * SB + site], w, acc);
-                widx += winc;
-                if (widx >= L) widx -= L;
-            }
-            // twiddle wp^j = exp(-2 pi i p j / n) = W_L^{p*j*s}
-            const int tidx = (int)(((long long)p * j * s) % L);
-            cplx t = tw[tidx];
-            if (inverse) t.y = -t.y;
-            y[(size_t)e * SB + site] = cmul(acc, t);
+        switch (r) {
+            case 2: stage_radix<SB, 2>(x, y, L, n, s, tw, inverse, site, slot, nslots); break;
+            case 3: stage_radix<SB, 3>(x, y, L, n, s, tw, inverse, site, slot, nslots); break;
+            case 4: stage_radix<SB, 4>(x, y, L, n, s, tw, inverse, site, slot, nslots); break;
+            case 5: stage_radix<SB, 5>(x, y, L, n, s, tw, inverse, site, slot, nslots); break;
+            default: stage_generic<SB>(x, y, L, n, s, r, tw, inverse, site, slot, nslots); break;
         }
         __syncthreads();
         cplx* tmp = x;
         x = y;
         y = tmp;
-        n = m;
+        n /= r;
         s *= r;
     }
     return x;
@@ -87,13 +158,14 @@ __device__ cplx* fft_smem(cplx* x, cplx* y, const FftPlan& plan, const cplx* __r
 template <int SB>
 __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* __restrict__ rin, const cplx* __restrict__ cin,
                                                  double* __restrict__ rout, cplx* __restrict__ cout, FftPlan plan, int N,
-                                                 const cplx* __restrict__ tw, const cplx* __restrict__ theta,
+                                                 const cplx* __restrict__ tw_g, const cplx* __restrict__ theta,
                                                  const double* __restrict__ diag, double power, const int* skip) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     if (skip && *skip) return;
     const int L = plan.L;
     cplx* b0 = reinterpret_cast<cplx*>(smem_raw);
     cplx* b1 = b0 + (size_t)L * SB;
+    cplx* tw = b1 + (size_t)L * SB;  // [L] twiddles staged once per CTA
     const int site = threadIdx.x % SB;
     const int slot = threadIdx.x / SB;
     const int nslots = blockDim.x / SB;
@@ -101,6 +173,7 @@ __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* __restr
     const bool ok = gsite < N;
     const double invL = 1.0 / (double)L;
 
+    for (int k = threadIdx.x; k < L; k += blockDim.x) tw[k] = tw_g[k];
     for (int t = slot; t < L; t += nslots) {
         cplx v = make_double2(0.0, 0.0);
         if (ok) {
@@ -161,12 +234,14 @@ FftPlan make_plan(const elph_handle* h) {
 }
 
 template <int SB>
+size_t fft_smem_bytes(int L) { return (2ull * L * SB + L) * sizeof(cplx); }
+
+template <int SB>
 void launch_fft(elph_handle* h, int mode, int ncols, const double* rin, const cplx* cin, double* rout, cplx* cout,
                 const double* diag, double power, const int* skip) {
-    const size_t smem = 2ull * h->L * SB * sizeof(cplx);
+    const size_t smem = fft_smem_bytes<SB>(h->L);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Ltau too large for the shared-memory FFT");
-    if (smem > 48 * 1024)
-        ELPH_CUDA(cudaFuncSetAttribute(fft_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    elph_enable_smem(h, fft_kernel<SB>);
     const int blocks = (ncols + SB - 1) / SB;
     fft_kernel<SB><<<blocks, kT, smem, h->stream>>>(mode, rin, cin, rout, cout, make_plan(h), ncols, h->d_twiddle, h->d_theta,
                                                      diag, power, skip);
@@ -176,14 +251,15 @@ void launch_fft(elph_handle* h, int mode, int ncols, const double* rin, const cp
 
 void dispatch_fft(elph_handle* h, int mode, int ncols, const double* rin, const cplx* cin, double* rout, cplx* cout,
                   const double* diag, double power, const int* skip = nullptr) {
-    // fewer sites per CTA -> more CTAs; keep at least ~one CTA per SM when possible, bounded by shared memory
+    // fewer sites per CTA -> more CTAs: aim at ~2 CTAs per SM, bounded below by 4 sites and above by shared memory
     int sb = 32;
-    while (sb > 8 && (ncols + sb - 1) / sb < h->sm_count) sb >>= 1;
-    while (sb > 8 && 2ull * h->L * sb * sizeof(cplx) > h->smem_optin) sb >>= 1;
+    while (sb > 4 && (ncols + sb - 1) / sb < 2 * h->sm_count) sb >>= 1;
+    while (sb > 4 && (2ull * h->L * sb + h->L) * sizeof(cplx) > h->smem_optin) sb >>= 1;
     switch (sb) {
         case 32: launch_fft<32>(h, mode, ncols, rin, cin, rout, cout, diag, power, skip); break;
         case 16: launch_fft<16>(h, mode, ncols, rin, cin, rout, cout, diag, power, skip); break;
-        default: launch_fft<8>(h, mode, ncols, rin, cin, rout, cout, diag, power, skip); break;
+        case 8: launch_fft<8>(h, mode, ncols, rin, cin, rout, cout, diag, power, skip); break;
+        default: launch_fft<4>(h, mode, ncols, rin, cin, rout, cout, diag, power, skip); break;
     }
 }
 
@@ -201,15 +277,13 @@ void elph_fft_init(elph_handle* h) {
     ELPH_REQUIRE((int)rad.size() <= kMaxRad, ELPH_ERR_UNSUPPORTED, "Ltau has too many prime factors");
     h->fft_radices = rad;
     std::vector<cplx> tw(L), th(L);
-    const double pi = 3.14159265358979323846;
+    const long double pi = 3.14159265358979323846264338327950288L;
     for (int k = 0; k < L; ++k) {
-        // exact-argument reduction: angle = -2 pi k / L
-        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)L;
+        const long double a = -2.0L * pi * (long double)k / (long double)L;
         tw[k] = make_double2((double)cosl(a), (double)sinl(a));
-        const long double b = -3.14159265358979323846264338327950288L * (long double)k / (long double)L;
+        const long double b = -pi * (long double)k / (long double)L;
         th[k] = make_double2((double)cosl(b), (double)sinl(b));
     }
-    (void)pi;
     h->d_twiddle = elph_dalloc<cplx>(L);
     h->d_theta = elph_dalloc<cplx>(L);
     ELPH_CUDA(cudaMemcpy(h->d_twiddle, tw.data(), L * sizeof(cplx), cudaMemcpyHostToDevice));

@@ -251,7 +251,7 @@ void elph_muldMdx_dev(elph_handle* h, const double* u, const double* v, double* 
         for (int c : {4, 2}) if ((h->L + c - 1) / c >= 2 * h->sm_count && c * slice <= 96 * 1024) { C = c; break; }
         ELPH_REQUIRE(C * slice <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Nsites too large for the shared-memory force kernel");
         P.C = C; P.dtau = h->dtau; P.scale = scale; P.add_dSb = add_dSb ? 1 : 0; P.shifted = shifted ? 1 : 0;
-        ELPH_CUDA(cudaFuncSetAttribute(holstein_force_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        elph_enable_smem(h, holstein_force_kernel);
         holstein_force_kernel<<<(h->L + C - 1) / C, kT, C * slice, h->stream>>>(P);
         ELPH_CUDA(cudaGetLastError());
         h->launches++;
@@ -264,7 +264,7 @@ void elph_muldMdx_dev(elph_handle* h, const double* u, const double* v, double* 
     P.ngroups = h->ngroups; P.N = h->N; P.L = h->L; P.Nb = h->Nb; P.Nph = h->Nph; P.C = 1; P.dtau = h->dtau;
     ELPH_REQUIRE(2 * slice <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Nsites too large for the shared-memory force kernel");
     ELPH_CUDA(cudaMemsetAsync(h->d_tmp, 0, h->Ndof * sizeof(double), h->stream));
-    ELPH_CUDA(cudaFuncSetAttribute(ssh_force_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    elph_enable_smem(h, ssh_force_kernel);
     ssh_force_kernel<<<h->L, kT, 2 * slice, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;

@@ -337,7 +337,7 @@ template <int SPT>
 void launch_apply(elph_handle* h, const KpmParams& P, int threads) {
     const size_t smem = (size_t)h->N * sizeof(cplx);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Nsites too large for the KPM shared-memory kernel");
-    ELPH_CUDA(cudaFuncSetAttribute(kpm_apply_kernel<SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    elph_enable_smem(h, kpm_apply_kernel<SPT>);
     kpm_apply_kernel<SPT><<<h->kpm.Lo2, threads, smem, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
@@ -508,6 +508,10 @@ void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) {
     P.L = h->L;
     P.inv_mag = 1.0 / K.lam_mag;
     P.avg_over_mag = K.lam_avg / K.lam_mag;
+    if (elph_launch_kpm_square(h, nu_in, nu_out, skip)) {   // register/shuffle kernel (kpm_square.cu)
+        elph_omega_to_tau_dev_skip(h, nu_out, vout, skip);
+        return;
+    }
     int threads = 256;
     while (threads < 512 && threads * 4 < h->N) threads *= 2;   // <= 512 threads: __launch_bounds__(512) on the kernel
     const int spt = (h->N + threads - 1) / threads;

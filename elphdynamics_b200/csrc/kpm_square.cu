@@ -1,0 +1,209 @@
+// Register-resident KPM apply for periodic square lattices (Holstein, uniform hopping per colour).
+//
+// Same arithmetic as kpm_apply_kernel in kpm.cu (reference: src/KPMPreconditioners.jl:606-693,758-778):
+// for every frequency w <= ceil(L/2):  u = sum_m conj(c_m) T_m(A'^T) v ;  out = sum_m c_m T_m(A') u,
+// A' = (A - lam_avg)/lam_mag,  A = K diag(eVbar),  mirror out[L-1-w] = conj(out[w]).
+// One CTA per frequency (longest polynomial first).  The complex N-vector lives in registers as a pair of
+// real tiles (lane = x, PY rows per warp); a sweep is shuffles + register rotations + ONE __syncthreads for the
+// tile-edge rows, instead of ngroups+1 barriers and a shared-memory round trip per bond.  The chain for the
+// lowest frequency (2*(order-1) sequential sweeps, order ~ 70 at config B) is latency bound; this kernel cuts
+// the latency per sweep by an order of magnitude.
+#include "square_tiles.cuh"
+
+namespace {
+
+using namespace sqt;
+
+struct KsqParams {
+    const cplx* __restrict__ in;
+    cplx* __restrict__ out;
+    const double* __restrict__ eVbar;
+    const cplx* __restrict__ coeff;
+    const int* __restrict__ order;
+    const int* __restrict__ coeff_off;
+    const int* __restrict__ schedule;
+    const int* skip;
+    int L, Ly;
+    double inv_mag, avg_over_mag;
+    double c0, s0, c1, s1, c2, s2, c3, s3;
+};
+
+template <int NSEG, int PY>
+struct CTile {
+    Tile<NSEG, PY> re, im;
+};
+
+template <int NSEG, int PY, bool TRANSPOSED>
+__device__ __forceinline__ void apply_A(CTile<NSEG, PY>& s, const Tile<NSEG, PY>& ev, const KsqParams& P, double* strips, int& xbuf,
+                                        int warp, int nwarps, int lane) {
+    constexpr int LX = 32 * NSEG;
+    double ar[NSEG], ai[NSEG], br[NSEG], bi[NSEG];
+    if (!TRANSPOSED) {
+        // A s = K (eVbar .* s): g0, g1, g2, g3
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                s.re.a[r][q] *= ev.a[r][q];
+                s.im.a[r][q] *= ev.a[r][q];
+            }
+        g0_x_even(s.re, P.c0, P.s0);
+        g0_x_even(s.im, P.c0, P.s0);
+        g1_x_odd(s.re, P.c1, P.s1, lane);
+        g1_x_odd(s.im, P.c1, P.s1, lane);
+        g2_y_even(s.re, P.c2, P.s2);
+        g2_y_even(s.im, P.c2, P.s2);
+        exchange_edges2(s.re, s.im, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, ar, ai, br, bi);
+        xbuf ^= 1;
+        g3_y_odd(s.re, P.c3, P.s3, ar, br);
+        g3_y_odd(s.im, P.c3, P.s3, ai, bi);
+    } else {
+        // A^T s = eVbar .* (K^T s): g3, g2, g1, g0
+        exchange_edges2(s.re, s.im, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, ar, ai, br, bi);
+        xbuf ^= 1;
+        g3_y_odd(s.re, P.c3, P.s3, ar, br);
+        g3_y_odd(s.im, P.c3, P.s3, ai, bi);
+        g2_y_even(s.re, P.c2, P.s2);
+        g2_y_even(s.im, P.c2, P.s2);
+        g1_x_odd(s.re, P.c1, P.s1, lane);
+        g1_x_odd(s.im, P.c1, P.s1, lane);
+        g0_x_even(s.re, P.c0, P.s0);
+        g0_x_even(s.im, P.c0, P.s0);
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                s.re.a[r][q] *= ev.a[r][q];
+                s.im.a[r][q] *= ev.a[r][q];
+            }
+    }
+}
+
+// acc = sum_m c_m T_m(A') vin   (TRANSPOSED: A'^T and conjugated coefficients), three-term recurrence (:625-676)
+template <int NSEG, int PY, bool TRANSPOSED>
+__device__ __forceinline__ void poly(CTile<NSEG, PY>& acc, const CTile<NSEG, PY>& vin, const Tile<NSEG, PY>& ev, const cplx* c_s,
+                                     int order, const KsqParams& P, double* strips, int& xbuf, int warp, int nwarps, int lane) {
+    CTile<NSEG, PY> un, uprev, s;
+    const double c0r = c_s[0].x, c0i = TRANSPOSED ? -c_s[0].y : c_s[0].y;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double vr = vin.re.a[r][q], vi = vin.im.a[r][q];
+            acc.re.a[r][q] = c0r * vr - c0i * vi;
+            acc.im.a[r][q] = c0r * vi + c0i * vr;
+            un.re.a[r][q] = vr;
+            un.im.a[r][q] = vi;
+            uprev.re.a[r][q] = 0.0;
+            uprev.im.a[r][q] = 0.0;
+        }
+    for (int n = 1; n < order; ++n) {
+        s = un;
+        apply_A<NSEG, PY, TRANSPOSED>(s, ev, P, strips, xbuf, warp, nwarps, lane);
+        const double cr = c_s[n].x, ci = TRANSPOSED ? -c_s[n].y : c_s[n].y;
+        const double two = (n > 1) ? 2.0 : 1.0, one = (n > 1) ? 1.0 : 0.0;
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                // A' u = (1/mag) A u - (avg/mag) u ; T_{n+1} = 2 A' T_n - T_{n-1} (first step: T_1 = A' T_0)
+                double ar_ = P.inv_mag * s.re.a[r][q] - P.avg_over_mag * un.re.a[r][q];
+                double ai_ = P.inv_mag * s.im.a[r][q] - P.avg_over_mag * un.im.a[r][q];
+                ar_ = two * ar_ - one * uprev.re.a[r][q];
+                ai_ = two * ai_ - one * uprev.im.a[r][q];
+                uprev.re.a[r][q] = un.re.a[r][q];
+                uprev.im.a[r][q] = un.im.a[r][q];
+                un.re.a[r][q] = ar_;
+                un.im.a[r][q] = ai_;
+                acc.re.a[r][q] += cr * ar_ - ci * ai_;
+                acc.im.a[r][q] += cr * ai_ + ci * ar_;
+            }
+    }
+}
+
+template <int NSEG, int PY, int MAXT>
+__global__ void __launch_bounds__(MAXT) kpm_square_kernel(KsqParams P, int max_order) {
+    constexpr int LX = 32 * NSEG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (P.skip && *P.skip) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int N = LX * P.Ly;
+    const int w = P.schedule[blockIdx.x];
+    const int order = P.order[w];
+    cplx* c_s = reinterpret_cast<cplx*>(smem_raw);                                  // [max_order]
+    double* strips = reinterpret_cast<double*>(smem_raw + (size_t)max_order * sizeof(cplx));  // 2 x [nwarps][4][LX]
+    for (int k = threadIdx.x; k < order; k += blockDim.x) c_s[k] = P.coeff[P.coeff_off[w] + k];
+    const size_t tile_off = (size_t)warp * PY * LX;
+    CTile<NSEG, PY> v, t1, t2;
+    Tile<NSEG, PY> ev;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const size_t e = tile_off + r * LX + 32 * q + lane;
+            const cplx z = P.in[(size_t)w * N + e];
+            v.re.a[r][q] = z.x;
+            v.im.a[r][q] = z.y;
+            ev.a[r][q] = P.eVbar[e];
+        }
+    __syncthreads();  // coefficients staged
+    int xbuf = 0;
+    poly<NSEG, PY, true>(t1, v, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);    // M^-T[w,w]
+    poly<NSEG, PY, false>(t2, t1, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);  // M^-1[w,w]
+    const int wm = P.L - 1 - w;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const size_t e = tile_off + r * LX + 32 * q + lane;
+            if (wm != w) P.out[(size_t)w * N + e] = make_double2(t2.re.a[r][q], t2.im.a[r][q]);
+            P.out[(size_t)wm * N + e] = make_double2(t2.re.a[r][q], -t2.im.a[r][q]);
+        }
+}
+
+template <int NSEG, int PY, int MAXT>
+void launch_ksq(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
+    constexpr int LX = 32 * NSEG;
+    const size_t smem = (size_t)max_order * sizeof(cplx) + 2ull * nwarps * 4 * LX * sizeof(double);
+    ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "KPM square kernel: polynomial order too large for shared memory");
+    elph_enable_smem(h, kpm_square_kernel<NSEG, PY, MAXT>);
+    kpm_square_kernel<NSEG, PY, MAXT><<<h->kpm.Lo2, nwarps * 32, smem, h->stream>>>(P, max_order);
+    ELPH_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+}  // namespace
+
+// Returns false when the model is not served by the square-lattice kernel (caller falls back to kpm_apply_kernel).
+bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, const int* skip) {
+    if (!h->sq.enabled || h->sq_disable || h->model != ELPH_MODEL_HOLSTEIN) return false;
+    const KpmState& K = h->kpm;
+    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
+    int PY = 4;
+    if (Lx == 32 && h->sq_py == 8 && Ly % 8 == 0) PY = 8;
+    if (Lx == 32 && h->sq_py == 2) PY = 2;
+    if (Ly % PY) return false;
+    const int nwarps = Ly / PY;
+    if (nwarps < 2 || nwarps > 32) return false;
+    int max_order = 1;
+    for (int w = 0; w < K.Lo2; ++w) max_order = std::max(max_order, K.order[w]);
+    KsqParams P;
+    P.in = nu_in; P.out = nu_out; P.eVbar = K.d_eVbar; P.coeff = K.d_coeff; P.order = K.d_order; P.coeff_off = K.d_coeff_off;
+    P.schedule = K.d_schedule; P.skip = skip; P.L = h->L; P.Ly = Ly;
+    P.inv_mag = 1.0 / K.lam_mag; P.avg_over_mag = K.lam_avg / K.lam_mag;
+    P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
+    P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
+#define KSQ_CASE(NS, PYV, MAXT)                                    \
+    if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {       \
+        launch_ksq<NS, PYV, MAXT>(h, P, nwarps, max_order);        \
+        return true;                                               \
+    }
+    KSQ_CASE(1, 4, 512)
+    KSQ_CASE(1, 8, 256)
+    KSQ_CASE(1, 2, 1024)
+    KSQ_CASE(2, 4, 512)
+    KSQ_CASE(3, 4, 1024)
+    KSQ_CASE(4, 4, 1024)
+#undef KSQ_CASE
+    return false;
+}

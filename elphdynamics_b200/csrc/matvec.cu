@@ -277,12 +277,7 @@ __global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, 
 
 template <int MODE, bool SSH, bool FUSEP = false>
 void launch_one(elph_handle* h, const KParams& P, dim3 grid, size_t smem) {
-    const unsigned bit = 1u << (MODE * 4 + (SSH ? 2 : 0) + (FUSEP ? 1 : 0));
-    if (!(h->smem_attr_mask & bit)) {
-        ELPH_CUDA(cudaFuncSetAttribute(matvec_kernel<MODE, SSH, FUSEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)h->smem_optin));
-        h->smem_attr_mask |= bit;
-    }
+    elph_enable_smem(h, matvec_kernel<MODE, SSH, FUSEP>);
     matvec_kernel<MODE, SSH, FUSEP><<<grid, kThreads, smem, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;

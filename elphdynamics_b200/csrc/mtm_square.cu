@@ -344,8 +344,7 @@ void launch_sq(elph_handle* h, const SqParams& P, dim3 grid, int nwarps) {
     const size_t smem = (size_t)nwarps * kStages * NT * PY * LX * sizeof(double) + (size_t)nwarps * kStages * 8 +
                         2ull * nwarps * 2 * LX * sizeof(double);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "square kernel: tile pipeline does not fit in shared memory");
-    ELPH_CUDA(cudaFuncSetAttribute(mtm_square_kernel<NSEG, PY, FUSEP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)h->smem_optin));
+    elph_enable_smem(h, mtm_square_kernel<NSEG, PY, FUSEP, MAXT>);
     mtm_square_kernel<NSEG, PY, FUSEP, MAXT><<<grid, nwarps * 32, smem, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;

@@ -1,0 +1,103 @@
+// Register tiles for periodic square lattices: the four checkerboard colours as warp shuffles and
+// register-to-register rotations (see the header comment of mtm_square.cu for the mapping).
+// Shared by kpm_square.cu (complex tiles = a pair of real tiles).
+#pragma once
+
+#include "elph_internal.cuh"
+
+namespace sqt {
+
+template <int NSEG, int PY>
+struct Tile {
+    double a[PY][NSEG];
+};
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g0_x_even(Tile<NSEG, PY>& t, double c, double s) {
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double o = __shfl_xor_sync(0xffffffffu, t.a[r][q], 1);
+            t.a[r][q] = c * t.a[r][q] + s * o;
+        }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g1_x_odd(Tile<NSEG, PY>& t, double c, double s, int lane) {
+    const int partner = (lane & 1) ? ((lane + 1) & 31) : ((lane + 31) & 31);
+#pragma unroll
+    for (int r = 0; r < PY; ++r) {
+        double o[NSEG];
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            double send = t.a[r][q];
+            if (NSEG > 1) {
+                const double nxt = t.a[r][(q + 1) % NSEG], prv = t.a[r][(q + NSEG - 1) % NSEG];
+                send = (lane == 0) ? nxt : ((lane == 31) ? prv : send);
+            }
+            o[q] = __shfl_sync(0xffffffffu, send, partner);
+        }
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) t.a[r][q] = c * t.a[r][q] + s * o[q];
+    }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g2_y_even(Tile<NSEG, PY>& t, double c, double s) {
+#pragma unroll
+    for (int r = 0; r < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = c * t1 + s * t2;
+            t.a[r + 1][q] = c * t2 + s * t1;
+        }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g3_y_odd(Tile<NSEG, PY>& t, double c, double s, const double (&above)[NSEG],
+                                         const double (&below)[NSEG]) {
+#pragma unroll
+    for (int r = 1; r + 1 < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = c * t1 + s * t2;
+            t.a[r + 1][q] = c * t2 + s * t1;
+        }
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        t.a[0][q] = c * t.a[0][q] + s * above[q];
+        t.a[PY - 1][q] = c * t.a[PY - 1][q] + s * below[q];
+    }
+}
+
+// publish the edge rows of a complex tile (re, im), one barrier, fetch the neighbours' edge rows.
+// strip: [nwarps][4][LX] doubles = (first row re, first row im, last row re, last row im) per warp.
+template <int NSEG, int PY>
+__device__ __forceinline__ void exchange_edges2(const Tile<NSEG, PY>& re, const Tile<NSEG, PY>& im, double* strip, int warp,
+                                                int nwarps, int lane, double (&ab_re)[NSEG], double (&ab_im)[NSEG],
+                                                double (&be_re)[NSEG], double (&be_im)[NSEG]) {
+    constexpr int LX = 32 * NSEG;
+    double* mine = strip + (size_t)warp * 4 * LX;
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        mine[0 * LX + 32 * q + lane] = re.a[0][q];
+        mine[1 * LX + 32 * q + lane] = im.a[0][q];
+        mine[2 * LX + 32 * q + lane] = re.a[PY - 1][q];
+        mine[3 * LX + 32 * q + lane] = im.a[PY - 1][q];
+    }
+    __syncthreads();
+    const int up = (warp == 0) ? nwarps - 1 : warp - 1;
+    const int dn = (warp + 1 == nwarps) ? 0 : warp + 1;
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        ab_re[q] = strip[(size_t)up * 4 * LX + 2 * LX + 32 * q + lane];
+        ab_im[q] = strip[(size_t)up * 4 * LX + 3 * LX + 32 * q + lane];
+        be_re[q] = strip[(size_t)dn * 4 * LX + 0 * LX + 32 * q + lane];
+        be_im[q] = strip[(size_t)dn * 4 * LX + 1 * LX + 32 * q + lane];
+    }
+}
+
+}  // namespace sqt
