@@ -274,6 +274,10 @@ void destroy(elph_handle* h) {
     cudaDeviceSynchronize();
     elph_kpm_free(h);
     elph_hmc_free(h);
+    if (h->d_D_alloc) {  // sharded: d_D points one slice into this allocation
+        cudaFree(h->d_D_alloc);
+        h->d_D = nullptr;
+    }
     void* ptrs[] = {h->d_bonds, h->d_goff, h->d_cs, h->d_lam, h->d_lam2, h->d_mu, h->d_omega, h->d_omega4, h->d_x, h->d_D,
                     h->d_Q, h->d_Mass, h->d_t, h->d_alpha, h->d_alpha2, h->d_ph_col, h->d_col_ph, h->d_col_bond,
                     h->d_primary_ph, h->d_grp_start, h->d_grp_members, h->d_tprime, h->d_va, h->d_vb, h->d_vc, h->d_b,
@@ -797,6 +801,79 @@ int32_t elph_dev_mulMTM_replicas(elph_handle* h, int64_t nrep, const double* exp
         a.y_stride = vec_stride;
         a.D_stride = expnV_dev ? expnV_stride : 0;
         elph_launch_matvec(h, MODE_MTM, a);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// ---- tau-sharding (multi-GPU): this handle owns global slices [tau0, tau0 + Ltau) of Lglob -------------------
+int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED, "tau-sharding is implemented for the Holstein model");
+        ELPH_REQUIRE(Lglob >= h->L && tau0 >= 0 && tau0 + h->L <= Lglob, ELPH_ERR_INVALID, "bad shard bounds");
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        if (!h->sharded) {
+            // re-home expnV with one halo slice on each side: [halo_lo][own ...][halo_hi]
+            double* alloc = elph_dalloc<double>((size_t)(h->L + 2) * h->N);
+            ELPH_CUDA(cudaMemset(alloc, 0, (size_t)(h->L + 2) * h->N * sizeof(double)));
+            ELPH_CUDA(cudaMemcpy(alloc + h->N, h->d_D, h->Ndim * sizeof(double), cudaMemcpyDeviceToDevice));
+            ELPH_CUDA(cudaFree(h->d_D));
+            h->d_D_alloc = alloc;
+            h->d_D = alloc + h->N;
+        }
+        h->sharded = true;
+        h->shard_tau0 = (int)tau0;
+        h->shard_Lglob = (int)Lglob;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_shard_matvec(elph_handle* h, int32_t mode, const double* v_own, double* y_own) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->sharded, ELPH_ERR_STATE, "elph_set_shard has not been called");
+        ELPH_REQUIRE(mode >= 0 && mode <= 2 && v_own && y_own, ELPH_ERR_INVALID, "bad arguments");
+        MatvecArgs a;
+        a.v = v_own;
+        a.y = y_own;
+        a.open = true;
+        elph_launch_matvec(h, (MatvecMode)mode, a);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_shard_muldMdx(elph_handle* h, const double* u_own, const double* v_own, double* out, double scale) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->sharded, ELPH_ERR_STATE, "elph_set_shard has not been called");
+        elph_muldMdx_dev(h, u_own, v_own, out, scale, false, false);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_update_model(elph_handle* h) {
+    ENTER(h) {
+        elph_launch_update_model(h);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_lincomb(elph_handle* h, double* out, double a, const double* X, double b, const double* Y, double c, const double* Z,
+                         int64_t n) {
+    ENTER(h) {
+        ELPH_REQUIRE(out && X && n >= 0, ELPH_ERR_INVALID, "bad arguments");
+        elph_lincomb(h, out, a, X, b, Y, c, Z, n);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_dot(elph_handle* h, const double* a, const double* b, int64_t n, double* out_dev) {
+    ENTER(h) {
+        ELPH_REQUIRE(a && b && out_dev, ELPH_ERR_INVALID, "bad arguments");
+        elph_dot_async(h, a, b, n, out_dev);   // out_dev[0] = a.b (out_dev needs room for 2 doubles)
         return ELPH_OK;
     }
     ELPH_CATCH(h)

@@ -204,6 +204,11 @@ struct elph_handle {
         int Lx = 0, Ly = 0;
         double c[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
     } sq;
+    // tau-sharding (multi-GPU): this handle owns global slices [shard_tau0, shard_tau0 + L) of shard_Lglob
+    bool sharded = false;
+    int shard_tau0 = 0, shard_Lglob = 0;
+    double* d_D_alloc = nullptr;   // sharded: d_D points one slice into this allocation (halo slices around it)
+    double* d_x_alloc = nullptr;   // sharded: same for the phonon field (the force needs no x halo; kept symmetric)
     bool sq_disable = false;
     int sq_py = 0;
     int chunk_override = 0;
@@ -222,6 +227,7 @@ struct MatvecArgs {
     const double* D = nullptr;   // nullptr -> handle's table
     int64_t nbatch = 1;
     int64_t v_stride = 0, y_stride = 0, D_stride = 0;
+    bool open = false;              // tau-sharded slab: v (and D) carry one halo slice before and after the own slices
     double* partial_dot = nullptr;  // if set: per-CTA partial sums of dot(v, y); returns count via *npartial
     int* npartial = nullptr;
     // CG fusion (see matvec.cu): v := cg_pr + S->beta * cg_pold on the fly, stored to cg_pnew

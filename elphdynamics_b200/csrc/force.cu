@@ -32,6 +32,7 @@ struct FParams {
     const int* __restrict__ goff;
     const double2* __restrict__ cs;
     int ngroups, N, L, Nb, C;
+    int open, tau0, Lglob;
     double dtau, scale;
     int add_dSb, shifted;
 };
@@ -73,12 +74,14 @@ __global__ void __launch_bounds__(kT) holstein_force_kernel(FParams P) {
     }
     for (int k = 0; k < nout; ++k) {
         const int tau = a + k;
-        const int taum = (tau == 0) ? L - 1 : tau - 1;
+        // tau-sharded slab: v(tau-1) of the first own slice is the left halo (index -1); '-' sign on GLOBAL slice 0
+        const long long taum = (tau == 0) ? (P.open ? -1 : L - 1) : tau - 1;
+        const bool flip = ((P.tau0 + tau) % P.Lglob) == 0;
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
             const size_t idx = (size_t)tau * N + i;
             const double xt = P.x[idx];
-            double d = P.dtau * (P.lam[i] + 2.0 * P.lam2[i] * xt) * P.D[idx] * P.v[(size_t)taum * N + i];
-            if (tau == 0) d = -d;
+            double d = P.dtau * (P.lam[i] + 2.0 * P.lam2[i] * xt) * P.D[idx] * P.v[taum * N + i];
+            if (flip) d = -d;
             double r = P.scale * (smem[(size_t)k * N + i] * d);
             if (P.add_dSb)
                 r += dSb_term(P.x, tau, i, N, L, P.dtau, P.omega[i], P.omega4[i], P.shifted ? P.dtau * P.lam[i] : 0.0);
@@ -247,6 +250,9 @@ void elph_muldMdx_dev(elph_handle* h, const double* u, const double* v, double* 
         P.u = u; P.v = v; P.out = out; P.x = h->d_x; P.D = h->d_D; P.lam = h->d_lam; P.lam2 = h->d_lam2;
         P.omega = h->d_omega; P.omega4 = h->d_omega4; P.bonds = h->d_bonds; P.goff = h->d_goff; P.cs = h->d_cs;
         P.ngroups = h->ngroups; P.N = h->N; P.L = h->L; P.Nb = h->Nb;
+        P.open = h->sharded ? 1 : 0; P.tau0 = h->sharded ? h->shard_tau0 : 0; P.Lglob = h->sharded ? h->shard_Lglob : h->L;
+        ELPH_REQUIRE(!(h->sharded && add_dSb), ELPH_ERR_UNSUPPORTED,
+                     "tau-sharded force: add the bosonic gradient separately (it needs x halos)");
         int C = 1;
         for (int c : {4, 2}) if ((h->L + c - 1) / c >= 2 * h->sm_count && c * slice <= 96 * 1024) { C = c; break; }
         ELPH_REQUIRE(C * slice <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Nsites too large for the shared-memory force kernel");

@@ -38,6 +38,7 @@ struct KParams {
     unsigned int* ticket;
     int ngroups;
     int N, L, Nb, C;
+    int open, tau0, Lglob;   // tau-sharded slab (halo slices at index -1 / L) instead of the periodic wrap
     long long v_stride, y_stride, D_stride;
 };
 
@@ -107,47 +108,55 @@ __global__ void __launch_bounds__(kThreads) matvec_kernel(KParams P) {
     double* __restrict__ y = P.y + (size_t)blockIdx.y * P.y_stride;
     const double* __restrict__ D = P.D + (size_t)blockIdx.y * P.D_stride;
     double acc = 0.0;
-    auto loadv = [&](size_t idx) -> double { return FUSEP ? fma(beta, P.pold[idx], P.pr[idx]) : v[idx]; };
+    auto loadv = [&](long long idx) -> double { return FUSEP ? fma(beta, P.pold[idx], P.pr[idx]) : v[idx]; };
+    // memory slice index of logical local slice t in [-1, L]: periodic wrap, or (tau-sharded slab) halo slices
+    auto midx = [&](int t) -> long long { return P.open ? (long long)t : (long long)(t < 0 ? t + L : (t >= L ? t - L : t)); };
+    // the antiperiodic '+' sign belongs to GLOBAL time slice 0
+    auto wrapsign = [&](int t) -> bool { return ((P.tau0 + t + P.Lglob) % P.Lglob) == 0; };
 
     if (MODE == MODE_M) {
         // A[k] = D(tau) .* v(tau-1), tau = a+k
         for (int k = 0; k < nout; ++k) {
             const int tau = a + k;
-            const int taum = (tau == 0) ? L - 1 : tau - 1;
+            const long long taum = midx(tau - 1);
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
                 const double d = SSH ? D[i] : D[(size_t)tau * N + i];
-                smem[(size_t)k * N + i] = d * v[(size_t)taum * N + i];
+                smem[(size_t)k * N + i] = d * v[taum * N + i];
             }
         }
         __syncthreads();
         sweep_smem<SSH, false>(smem, nout, a, P);
         for (int k = 0; k < nout; ++k) {
             const int tau = a + k;
+            const bool plus = wrapsign(tau);
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
                 const double vv = v[(size_t)tau * N + i];
                 const double bv = smem[(size_t)k * N + i];
-                const double r = (tau == 0) ? (vv + bv) : (vv - bv);
+                const double r = plus ? (vv + bv) : (vv - bv);
                 y[(size_t)tau * N + i] = r;
                 acc += vv * r;
             }
         }
     } else if (MODE == MODE_MT) {
-        // A[k] = v(tau'), tau' = a+k ; u = K^T A ; y(tau'-1) = v(tau'-1) -/+ D(tau') u
+        // A[k] = v(tau'), u = K^T A ; y(tau'-1) = v(tau'-1) -/+ D(tau') u.  Periodic: tau' = a+k covers 0..L-1 (output
+        // slice tau'-1 wraps); open slab: tau' = a+k+1 covers 1..L (slice L = right halo), outputs 0..L-1.
+        const int shift = P.open ? 1 : 0;
         for (int k = 0; k < nout; ++k) {
-            const int tau = a + k;
+            const int tau = a + k + shift;
             for (int i = threadIdx.x; i < N; i += blockDim.x) smem[(size_t)k * N + i] = v[(size_t)tau * N + i];
         }
         __syncthreads();
-        sweep_smem<SSH, true>(smem, nout, a, P);
+        sweep_smem<SSH, true>(smem, nout, a + shift, P);
         for (int k = 0; k < nout; ++k) {
-            const int tau = a + k;
-            const int taum = (tau == 0) ? L - 1 : tau - 1;
+            const int tau = a + k + shift;
+            const long long taum = midx(tau - 1);
+            const bool plus = wrapsign(tau);
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
                 const double d = SSH ? D[i] : D[(size_t)tau * N + i];
-                const double vv = v[(size_t)taum * N + i];
+                const double vv = v[taum * N + i];
                 const double bu = d * smem[(size_t)k * N + i];
-                const double r = (tau == 0) ? (vv + bu) : (vv - bu);
-                y[(size_t)taum * N + i] = r;
+                const double r = plus ? (vv + bu) : (vv - bu);
+                y[taum * N + i] = r;
                 acc += vv * r;
             }
         }
@@ -157,25 +166,24 @@ __global__ void __launch_bounds__(kThreads) matvec_kernel(KParams P) {
         double* A = smem;                        // nw slices
         double* W = smem + (size_t)(P.C + 1) * N;  // copies of w(a+1 .. a+nout-1)
         for (int k = 0; k < nw; ++k) {
-            int tau = a + k;
-            if (tau >= L) tau -= L;
-            const int taum = (tau == 0) ? L - 1 : tau - 1;
+            const long long tau = midx(a + k);
+            const long long taum = midx(a + k - 1);
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const double d = SSH ? D[i] : D[(size_t)tau * N + i];
-                A[(size_t)k * N + i] = d * loadv((size_t)taum * N + i);
+                const double d = SSH ? D[i] : D[tau * N + i];
+                A[(size_t)k * N + i] = d * loadv(taum * N + i);
             }
         }
         __syncthreads();
         sweep_smem<SSH, false>(A, nw, a, P);
         // w = v -/+ B v(tau-1); same thread reads and writes element (k,i): no barrier needed before
         for (int k = 0; k < nw; ++k) {
-            int tau = a + k;
-            if (tau >= L) tau -= L;
+            const long long tau = midx(a + k);
+            const bool plus = wrapsign(a + k);
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const double vv = loadv((size_t)tau * N + i);
-                if (FUSEP && k < nout) P.pnew[(size_t)tau * N + i] = vv;
+                const double vv = loadv(tau * N + i);
+                if (FUSEP && k < nout) P.pnew[tau * N + i] = vv;
                 const double bv = A[(size_t)k * N + i];
-                const double w = (tau == 0) ? (vv + bv) : (vv - bv);
+                const double w = plus ? (vv + bv) : (vv - bv);
                 A[(size_t)k * N + i] = w;
                 if (k >= 1 && k < nout) W[(size_t)(k - 1) * N + i] = w;
             }
@@ -184,13 +192,13 @@ __global__ void __launch_bounds__(kThreads) matvec_kernel(KParams P) {
         sweep_smem<SSH, true>(A + N, nout, a + 1, P);  // u(tau) = K^T(tau) w(tau), tau = a+1 .. a+nout
         for (int k = 0; k < nout; ++k) {
             const int tau = a + k;
-            int taup = tau + 1;
-            if (taup >= L) taup -= L;
+            const long long taup = midx(tau + 1);
+            const bool plus = wrapsign(tau + 1);
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const double d = SSH ? D[i] : D[(size_t)taup * N + i];
+                const double d = SSH ? D[i] : D[taup * N + i];
                 const double w = (k == 0) ? A[i] : W[(size_t)(k - 1) * N + i];
                 const double bu = d * A[(size_t)(k + 1) * N + i];
-                const double r = (tau == L - 1) ? (w + bu) : (w - bu);
+                const double r = plus ? (w + bu) : (w - bu);
                 y[(size_t)tau * N + i] = r;
                 if (P.partial) acc += loadv((size_t)tau * N + i) * r;
             }
@@ -327,6 +335,11 @@ void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a) {
     ELPH_REQUIRE(!fusep || (mode == MODE_MTM && a.nbatch == 1 && a.partial_dot), ELPH_ERR_INVALID,
                  "CG fusion is only available for the single-vector M^T M product");
     P.ngroups = h->ngroups;
+    P.open = a.open ? 1 : 0;
+    P.tau0 = a.open ? h->shard_tau0 : 0;
+    P.Lglob = a.open ? h->shard_Lglob : h->L;
+    ELPH_REQUIRE(!a.open || h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
+                 "tau-sharded slabs are implemented for the Holstein model");
     P.N = h->N;
     P.L = h->L;
     P.Nb = h->Nb;

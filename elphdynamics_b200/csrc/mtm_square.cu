@@ -42,6 +42,7 @@ struct SqParams {
     unsigned int* ticket;
     long long v_stride, y_stride, D_stride;
     int L, Ly, C;
+    int open, tau0, Lglob;   // tau-sharded slab: halo slices at index -1 / L instead of the periodic wrap
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
 
@@ -205,8 +206,8 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 
     auto issue = [&](int j) {
         if (lane == 0) {
-            int tau = a + j;
-            if (tau >= L) tau -= L;
+            int tau = a + j;                       // memory slice index; in an open slab index L is the right halo
+            if (!P.open && tau >= L) tau -= L;
             const int st = j % kStages;
             double* dst = stage_base + (size_t)st * NT * TILE;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -223,13 +224,13 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 
     Tile<NSEG, PY> vprev, wprev, t, u;
     {   // v(a-1), straight from global (coalesced, once per chunk)
-        const int taum = (a == 0) ? L - 1 : a - 1;
-        const size_t g = (size_t)taum * N + tile_off;
+        const int taum = (a == 0) ? (P.open ? -1 : L - 1) : a - 1;   // open slab: index -1 is the left halo slice
+        const long long g = (long long)taum * N + (long long)tile_off;
 #pragma unroll
         for (int r = 0; r < PY; ++r)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
-                const size_t e = g + r * LX + 32 * q + lane;
+                const long long e = g + r * LX + 32 * q + lane;
                 vprev.a[r][q] = FUSEP ? fma(beta, P.pold[e], P.pr[e]) : vin[e];
                 wprev.a[r][q] = 0.0;
             }
@@ -240,7 +241,9 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     double above[NSEG], below[NSEG];
     for (int j = 0; j < nsteps; ++j) {
         int tau = a + j;
-        if (tau >= L) tau -= L;
+        if (!P.open && tau >= L) tau -= L;
+        // antiperiodic boundary: the '+' sign belongs to GLOBAL time slice 0 (tau0 = global index of local slice 0)
+        const bool wrap = ((P.tau0 + a + j) % P.Lglob) == 0;
         const int st = j % kStages;
         const double* sv = stage_base + (size_t)st * NT * TILE;
         const double* sD = sv + (NT - 1) * TILE;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
                 const int e = r * LX + 32 * q + lane;
                 const double vc = FUSEP ? fma(beta, sv[TILE + e], sv[e]) : sv[e];
                 if (FUSEP && j < nout) P.pnew[(size_t)tau * N + tile_off + e] = vc;
-                const double w = (tau == 0) ? (vc + t.a[r][q]) : (vc - t.a[r][q]);
+                const double w = wrap ? (vc + t.a[r][q]) : (vc - t.a[r][q]);
                 t.a[r][q] = w;
                 vprev.a[r][q] = vc;
                 if (FUSEP && j < nout) acc = fma(w, w, acc);
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
             g1_x_odd(u, P.c1, P.s1, lane);
             g0_x_even(u, P.c0, P.s0);
             // y(tau-1) = w(tau-1) -/+ D(tau) .* u     ('+' on the antiperiodic wrap tau = 0)
-            const int taum = (tau == 0) ? L - 1 : tau - 1;
+            const int taum = a + j - 1;   // always one of the CTA's own output slices
             const size_t g = (size_t)taum * N + tile_off;
 #pragma unroll
             for (int r = 0; r < PY; ++r)
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
                 for (int q = 0; q < NSEG; ++q) {
                     const int e = r * LX + 32 * q + lane;
                     const double du = sD[e] * u.a[r][q];
-                    y[g + e] = (tau == 0) ? (wprev.a[r][q] + du) : (wprev.a[r][q] - du);
+                    y[g + e] = wrap ? (wprev.a[r][q] + du) : (wprev.a[r][q] - du);
                 }
         }
 #pragma unroll
@@ -419,6 +422,7 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
     P.pr = a.cg_pr; P.pold = a.cg_pold; P.pnew = a.cg_pnew; P.partial = a.partial_dot; P.S = a.cg_S; P.ticket = a.cg_ticket;
     P.v_stride = a.v_stride; P.y_stride = a.y_stride; P.D_stride = a.D_stride;
     P.L = h->L; P.Ly = Ly;
+    P.open = a.open ? 1 : 0; P.tau0 = a.open ? h->shard_tau0 : 0; P.Lglob = a.open ? h->shard_Lglob : h->L;
     int C = h->chunk_override;
     if (C <= 0) {
         // halo overhead is one extra K-sweep and one extra v slice per chunk: favour long chunks once the

@@ -265,6 +265,21 @@ int32_t elph_dev_mulMT(elph_handle* h, const double* v_dev, double* y_dev);
  * scale-out is independent runs distinguished by `id` (src/ElPhDynamics.jl:90-95). */
 int32_t elph_dev_mulMTM_replicas(elph_handle* h, int64_t nrep, const double* expnV_dev, int64_t expnV_stride,
                                  const double* v_dev, double* y_dev, int64_t vec_stride);
+/* ---- tau-sharding across GPUs: one handle per rank, created with Ltau = the rank's slab length.
+ * elph_set_shard tells it which global slices it owns (tau0 .. tau0+Ltau-1 of Lglob) so that the antiperiodic sign
+ * lands on GLOBAL slice 0; expnV is re-homed with one halo slice on each side ([halo_lo][own...][halo_hi], own start =
+ * elph_dev_ptr_expnV).  The shard entry points take pointers to the FIRST OWN slice of vectors laid out the same way:
+ * the caller (one process per GPU, torch.distributed/NCCL) fills v[-1] with the left neighbour's last slice and v[Ltau]
+ * (and expnV[Ltau]) with the right neighbour's first slice before the call -- one halo exchange per product.
+ * mode: 0 = M v, 1 = M^T v, 2 = M^T M v.  No reference counterpart (the reference is single-process). */
+int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob);
+int32_t elph_dev_shard_matvec(elph_handle* h, int32_t mode, const double* v_own, double* y_own);
+int32_t elph_dev_shard_muldMdx(elph_handle* h, const double* u_own, const double* v_own, double* out, double scale);
+int32_t elph_dev_update_model(elph_handle* h);
+/* BLAS-1 on device pointers for the sharded solver: out = a X + b Y + c Z (Y, Z may be NULL); out_dev[0] = a.b */
+int32_t elph_dev_lincomb(elph_handle* h, double* out, double a, const double* X, double b, const double* Y, double c,
+                         const double* Z, int64_t n);
+int32_t elph_dev_dot(elph_handle* h, const double* a, const double* b, int64_t n, double* out_dev);
 /* host layout (N x Ltau, tau fastest) <-> engine layout (Ltau x N) on the device */
 int32_t elph_dev_to_engine_layout(elph_handle* h, const double* host_layout_dev, double* engine_dev, int64_t ncols);
 int32_t elph_dev_from_engine_layout(elph_handle* h, const double* engine_dev, double* host_layout_dev, int64_t ncols);

@@ -1,0 +1,299 @@
+"""tau-sharded products and CG.
+
+CPU: the host-side logic (slab bounds, ring halo exchange incl. the antiperiodic closure, scalar all-reduces, CG
+control flow) runs over gloo with world_size 2 and 3, with a NumPy slab backend built from the oracle.
+GPU: the open-slab CUDA kernels are checked (a) on one GPU with several slabs driven in-process and (b) with real
+NCCL ranks when at least two GPUs are visible.
+"""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from helpers import oracle_holstein, relerr  # noqa: E402
+from oracle import checkerboard as cb  # noqa: E402
+from oracle.solvers import ConjugateGradient, solve_cg  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+class OracleSlabBackend:
+    """NumPy slab arithmetic from the oracle's checkerboard sweeps (TEST ONLY; the package has no CPU backend)."""
+
+    def __init__(self, om, tau0, lloc):
+        import torch
+        self.torch = torch
+        self.om, self.tau0, self.lloc, self.N, self.Lg = om, tau0, lloc, om.N, om.L
+        E = om.expnV.reshape(om.N, om.L).T          # [tau][site]
+        idx = [(tau0 + t - 1) % om.L for t in range(lloc + 2)]
+        self.D = torch.from_numpy(np.ascontiguousarray(E[idx])).clone()
+        self.D[0] = 0.0
+        self.D[lloc + 1] = 0.0                      # the halo is filled by the exchange, like on the GPU
+
+    def empty(self):
+        return self.torch.zeros(self.lloc + 2, self.N, dtype=self.torch.float64)
+
+    def D_tensor(self):
+        return self.D
+
+    def update_model(self):
+        pass
+
+    def _K(self, slices, transpose):
+        Y = np.ascontiguousarray(slices.T)           # (N, nsl)
+        f = cb.checkerboard_transpose_mul if transpose else cb.checkerboard_mul
+        f(Y, self.om.neighbor_table, self.om.cosht, self.om.sinht, self.om.group_offsets)
+        return Y.T
+
+    def _w(self, v, D, ts):
+        """w(t) = v(t) -/+ K D(t) v(t-1) for slab indices ts (1-based rows of the halo'd arrays)."""
+        ts = np.asarray(ts)
+        Bv = self._K(D[ts] * v[ts - 1], False)
+        sign = np.where((self.tau0 + ts - 1) % self.Lg == 0, 1.0, -1.0)[:, None]
+        return v[ts] + sign * Bv
+
+    def matvec(self, mode, v, y):
+        vn, Dn, L = v.numpy(), self.D.numpy(), self.lloc
+        own = np.arange(1, L + 1)
+        if mode == 0:
+            out = self._w(vn, Dn, own)
+        else:
+            w = vn if mode == 1 else np.zeros_like(vn)
+            if mode == 2:
+                w[1:L + 2] = self._w(vn, Dn, np.arange(1, L + 2))
+            u = self._K(w[own + 1], True)
+            sign = np.where((self.tau0 + own) % self.Lg == 0, 1.0, -1.0)[:, None]
+            out = w[own] + sign * Dn[own + 1] * u
+        y.numpy()[1:L + 1] = out
+
+    def lincomb(self, out, a, X, b=0.0, Y=None):
+        L = self.lloc
+        r = a * X[1:L + 1]
+        if Y is not None:
+            r = r + b * Y[1:L + 1]
+        out[1:L + 1] = r
+
+    def dot(self, a, b):
+        L = self.lloc
+        return (a[1:L + 1] * b[1:L + 1]).sum().reshape(1)
+
+
+def _global_reference(om, rng):
+    v = rng.normal(size=om.Ndim)
+    outs = {}
+    for name, fn in (("M", om.mulM), ("MT", om.mulMT), ("MTM", om.mulMTM)):
+        y = np.zeros(om.Ndim)
+        fn(y, v)
+        outs[name] = y.reshape(om.N, om.L).T.copy()
+    return v.reshape(om.N, om.L).T.copy(), outs
+
+
+def _check_rank(op, be, comm_rank, tau0, lloc, V, outs, om, b_glob, x_ref, it_ref):
+    import torch
+    v = be.empty()
+    v[1:lloc + 1] = torch.from_numpy(V[tau0:tau0 + lloc]).to(v.device)
+    y = be.empty()
+    op.update_model()
+    for name, fn in (("M", op.mulM), ("MT", op.mulMT), ("MTM", op.mulMTM)):
+        fn(y, v)
+        got = y[1:lloc + 1].cpu().numpy()
+        assert relerr(got, outs[name][tau0:tau0 + lloc]) <= 1e-12, (name, comm_rank)
+    b = be.empty()
+    b[1:lloc + 1] = torch.from_numpy(b_glob[tau0:tau0 + lloc]).to(b.device)
+    x = be.empty()
+    it, eps = op.solve_cg(x, b)
+    assert abs(it - it_ref) <= 2, (it, it_ref)
+    assert relerr(x[1:lloc + 1].cpu().numpy(), x_ref[tau0:tau0 + lloc]) <= 1e-3   # both stop at eps < 1e-5
+
+
+def _problem(seed=7, Ls=4, beta=1.1):
+    om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-0.5, seed=seed)
+    V, outs = _global_reference(om, rng)
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    x = np.zeros(om.Ndim)
+    it = solve_cg(x, om, b, ConjugateGradient(om.Ndim, tol=1e-5, maxiter=5000))
+    to_eng = lambda a: a.reshape(om.N, om.L).T.copy()
+    return om, V, outs, to_eng(b), to_eng(x), it
+
+
+def _cpu_worker(rank, world, port):
+    import torch.distributed as dist
+    from elphdynamics_b200.sharded import RingComm, ShardedOperator, slab_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        om, V, outs, b, x_ref, it_ref = _problem()
+        tau0, lloc = slab_bounds(om.L, world, rank)
+        be = OracleSlabBackend(om, tau0, lloc)
+        op = ShardedOperator(be, RingComm(rank, world), tol=1e-5, maxiter=5000)
+        _check_rank(op, be, rank, tau0, lloc, V, outs, om, b, x_ref, it_ref)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_host_logic_over_gloo(world):
+    import torch.multiprocessing as mp
+    mp.spawn(_cpu_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def test_slab_bounds_cover_the_time_axis():
+    from elphdynamics_b200.sharded import slab_bounds
+    for L in (11, 20, 200, 400):
+        for world in (1, 2, 3, 4, 8):
+            spans = [slab_bounds(L, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(s[1] for s in spans) == L
+            for (t0, l0), (t1, _) in zip(spans[:-1], spans[1:]):
+                assert t0 + l0 == t1
+            assert max(s[1] for s in spans) - min(s[1] for s in spans) <= 1
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def _engine_slab(om, tau0, lloc):
+    """Engine model for one slab: Ltau = lloc, field = the slab of the global field."""
+    import elphdynamics_b200 as E
+    lat = om.lat
+    elat = E.Lattice(E.UnitCell(lat.ndim, lat.norbits), lat.L1, lat.L2, lat.L3)
+    em = E.HolsteinModel(elat, lloc * om.dtau, om.dtau, tol=om.tol, maxiter=om.maxiter)
+    assert em.Ltau == lloc
+    em.assign_omega(om.omega); em.assign_mu(om.mu); em.assign_lambda(om.lam); em.assign_lambda2(om.lam2); em.assign_omega4(om.omega4)
+    off = 0
+    for (o1, o2, d), cnt in zip(om.geom_defs, om.geom.def_counts):
+        em.assign_t(om.t[off:off + cnt], o1, o2, d)
+        off += cnt
+    em.initialize_model_()
+    em.x = np.ascontiguousarray(om.x.reshape(om.N, om.L)[:, tau0:tau0 + lloc]).reshape(-1)
+    return em
+
+
+class _InProcessRing:
+    """All slabs live in one process on one GPU: the 'exchange' copies between the slabs' tensors."""
+
+    def __init__(self, world):
+        self.world = world
+        self.registry = {}      # id(tensor of rank r) -> list of the matching tensors of all ranks
+
+    def comm(self, rank):
+        ring = self
+
+        class _C:
+            def exchange(self, v, lloc, lo=True, hi=True):
+                group = ring.registry[id(v)]
+                w = ring.world
+                if lo:
+                    left = group[(rank - 1) % w]
+                    v[0].copy_(left[left.shape[0] - 2])
+                if hi:
+                    v[lloc + 1].copy_(group[(rank + 1) % w][1])
+
+            def allreduce_sum(self, t):
+                return t
+        return _C()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,world", [(4, 1), (4, 3), (32, 2), (32, 4)])
+def test_open_slab_kernels_single_gpu(Ls, world):
+    """Several slabs on ONE GPU, halos copied in-process: checks the open-slab kernels (generic and register/shuffle),
+    the global-tau sign and uneven slab lengths against the oracle's global products."""
+    import torch
+    from elphdynamics_b200.sharded import CudaSlabBackend, ShardedOperator, slab_bounds
+    om, V, outs, b, x_ref, it_ref = _problem(Ls=Ls, beta=1.1 if Ls == 4 else 0.9)
+    ring = _InProcessRing(world)
+    slabs = []
+    for r in range(world):
+        tau0, lloc = slab_bounds(om.L, world, r)
+        em = _engine_slab(om, tau0, lloc)
+        be = CudaSlabBackend(em, tau0, om.L)
+        slabs.append((em, be, tau0, lloc))
+    # expnV halos
+    for r, (em, be, tau0, lloc) in enumerate(slabs):
+        be.update_model()
+    Ds = [be.D_tensor() for (_, be, _, _) in slabs]
+    for r, (em, be, tau0, lloc) in enumerate(slabs):
+        Ds[r][lloc + 1].copy_(Ds[(r + 1) % world][1])
+    vs, ys = [], []
+    for (em, be, tau0, lloc) in slabs:
+        v = be.empty()
+        v[1:lloc + 1] = torch.from_numpy(V[tau0:tau0 + lloc]).cuda()
+        vs.append(v)
+        ys.append(be.empty())
+    for r in range(world):
+        ring.registry[id(vs[r])] = vs
+    for mode, name in ((0, "M"), (1, "MT"), (2, "MTM")):
+        for r, (em, be, tau0, lloc) in enumerate(slabs):
+            ring.comm(r).exchange(vs[r], lloc)
+            be.matvec(mode, vs[r], ys[r])
+            got = ys[r][1:lloc + 1].cpu().numpy()
+            assert relerr(got, outs[name][tau0:tau0 + lloc]) <= 1e-12, (name, r)
+    # force <dM/dx> = u^T dM/dx v on the slab (left halo of v)
+    rng = np.random.default_rng(3)
+    u_g = rng.normal(size=om.Ndim)
+    d_ref = np.zeros(om.Ndof)
+    om.muldMdx(d_ref, u_g, V.T.reshape(-1))
+    d_ref = d_ref.reshape(om.N, om.L).T
+    U = u_g.reshape(om.N, om.L).T
+    for r, (em, be, tau0, lloc) in enumerate(slabs):
+        u = be.empty()
+        u[1:lloc + 1] = torch.from_numpy(np.ascontiguousarray(U[tau0:tau0 + lloc])).cuda()
+        out = be.empty()
+        be.muldMdx(u, vs[r], out, 1.0)
+        assert relerr(out[1:lloc + 1].cpu().numpy(), d_ref[tau0:tau0 + lloc]) <= 1e-9, r
+    if world == 1:
+        em, be, tau0, lloc = slabs[0]
+        from elphdynamics_b200.sharded import RingComm
+        op = ShardedOperator(be, RingComm(0, 1), tol=1e-5, maxiter=5000)
+        bb = be.empty()
+        bb[1:lloc + 1] = torch.from_numpy(b).cuda()
+        x = be.empty()
+        it, eps = op.solve_cg(x, bb)
+        assert abs(it - it_ref) <= 2 and relerr(x[1:lloc + 1].cpu().numpy(), x_ref) <= 1e-3
+    for em, *_ in slabs:
+        em.close()
+
+
+def _gpu_worker(rank, world, port):
+    import torch
+    import torch.distributed as dist
+    from elphdynamics_b200.sharded import CudaSlabBackend, RingComm, ShardedOperator, slab_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        om, V, outs, b, x_ref, it_ref = _problem(Ls=32, beta=0.9)
+        tau0, lloc = slab_bounds(om.L, world, rank)
+        em = _engine_slab(om, tau0, lloc)
+        be = CudaSlabBackend(em, tau0, om.L)
+        op = ShardedOperator(be, RingComm(rank, world), tol=1e-5, maxiter=5000)
+        _check_rank(op, be, rank, tau0, lloc, V, outs, om, b, x_ref, it_ref)
+        em.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_over_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    mp.spawn(_gpu_worker, args=(world, _free_port()), nprocs=world, join=True)
