@@ -296,6 +296,45 @@ def main():
         extra["langevin_rk_kpm"] = {"steps_per_s": nsteps / dt_l, "pcg_iters_second_solve": its,
                                     "note": "elph_langevin_step through the C ABI with host noise buffers"}
 
+    # ---------------- tau-sharded single lattice (config E: Holstein 64x64, L=400), strong scaling over ranks -----
+    sharded = None
+    if not args.no_extra:
+        from elphdynamics_b200.sharded import CudaSlabBackend, RingComm, ShardedOperator, slab_bounds
+        LE, LtauE = 64, 400
+        tau0, lloc = slab_bounds(LtauE, world, rank)
+        latE = E.Lattice(E.UnitCell(2, 1), LE)
+        mE = E.HolsteinModel(latE, lloc * DTAU, DTAU, tol=1e-5, maxiter=10000)
+        mE.assign_omega(1.0); mE.assign_lambda(1.0); mE.assign_mu(-1.0)
+        mE.assign_t(1.0, 0, 0, (1, 0, 0)); mE.assign_t(1.0, 0, 0, (0, 1, 0))
+        mE.initialize_model_()
+        rs = np.random.default_rng(99 + rank)
+        mE.x = (rs.integers(-1, 2, size=(mE.Nsites, 1)) + 0.7 * rs.normal(size=(mE.Nsites, 1)) + 0.3 * rs.normal(size=(mE.Nsites, lloc))).reshape(-1)
+        beE = CudaSlabBackend(mE, tau0, LtauE)
+        opE = ShardedOperator(beE, RingComm(rank, world))
+        opE.update_model()
+        vE, yE = beE.empty(), beE.empty()
+        vE[1:lloc + 1].normal_()
+        for _ in range(5):
+            opE.mulMTM(yE, vE)
+        barrier()
+        nrep = 50
+        e0.record()
+        for _ in range(nrep):
+            opE.mulMTM(yE, vE)
+        e1.record()
+        barrier()
+        msE = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([msE], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            msE = float(t.item())
+        usE = msE * 1e3 / nrep
+        sharded = {"workload": "holstein_square_64x64_L400, one lattice tau-sharded over the ranks (strong scaling)",
+                   "us_per_matvec": usE, "matvecs_per_s": 1e6 / usE, "slab_slices_per_gpu": lloc,
+                   "algorithmic_GBps_per_gpu": BYTES_PER_POINT * mE.Nsites * lloc / usE / 1e3,
+                   "collective": "1 halo slice each way per product (NCCL send/recv), antiperiodic sign on global slice 0"}
+        mE.close()
+
     if rank == 0:
         traffic = None
         tp = ROOT / "profiles" / "traffic.json"
@@ -317,6 +356,8 @@ def main():
                         "api": "elph_mulMTM_batch (host pointers, pinned)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         line.update(extra)
+        if sharded is not None:
+            line["tau_sharded"] = sharded
         if not args.no_cpu:
             cb, _ = cpu_baseline(om)
             line["cpu_baseline"] = cb

@@ -1,0 +1,154 @@
+"""GPU parity at BASELINE.json's full sizes (configs B, C, E), through the C ABI.
+
+At these sizes the checks are (i) direct comparison with the fast oracles (the C restatement for products and CG,
+NumPy for the force / KPM / PCG, all of which finish in seconds) and (ii) size-independent properties of the
+operator: adjointness, fused-vs-composed M^T M, linearity, true-residual of the solves, agreement of the two kernel
+families.
+"""
+import numpy as np
+import pytest
+
+from helpers import engine_holstein_like, oracle_holstein, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def config_B():
+    """Holstein square 32x32, beta = 20, dtau = 0.1 -> Ltau = 200 (N*Ltau = 204,800), shipped parameters."""
+    om, rng = oracle_holstein("square", 32, 20.0, 0.1, mu=-1.0, seed=1234, eps=0.3)
+    em = engine_holstein_like(om)
+    yield om, em, rng
+    em.close()
+
+
+def test_B_products_against_c_restatement(config_B):
+    import elphdynamics_b200 as E
+    from oracle.cref import CRef
+    om, em, rng = config_B
+    c = CRef(om)
+    v = rng.normal(size=om.Ndim)
+    yc, ye = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    for fc, fe in ((c.mulM, E.mulM_), (c.mulMT, E.mulMT_), (c.mulMTM, E.mulMTM_)):
+        fc(yc, v)
+        fe(ye, em, v)
+        assert relerr(ye, yc) <= 1e-12, fe.__name__
+
+
+def test_B_operator_properties(config_B):
+    import elphdynamics_b200 as E
+    om, em, rng = config_B
+    u, v = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    Mv, Mtu, MtMv, comp = (np.zeros(om.Ndim) for _ in range(4))
+    E.mulM_(Mv, em, v)
+    E.mulMT_(Mtu, em, u)
+    assert abs(u @ Mv - Mtu @ v) <= 1e-12 * np.linalg.norm(u) * np.linalg.norm(Mv)        # adjointness
+    E.mulMTM_(MtMv, em, v)
+    E.mulMT_(comp, em, Mv)
+    assert relerr(MtMv, comp) <= 1e-13                                                        # fused == composed
+    a, b = 0.37, -1.9
+    lin = np.zeros(om.Ndim)
+    E.mulMTM_(lin, em, a * u + b * v)
+    MtMu = np.zeros(om.Ndim)
+    E.mulMTM_(MtMu, em, u)
+    assert relerr(lin, a * MtMu + b * MtMv) <= 1e-13                                          # linearity
+    assert v @ MtMv > 0                                                                       # positive definite
+    # both kernel families agree (register/shuffle vs generic shared-memory)
+    em._call("elph_set_tuning", 1, 1)
+    gen = np.zeros(om.Ndim)
+    E.mulMTM_(gen, em, v)
+    em._call("elph_set_tuning", 1, 0)
+    assert relerr(MtMv, gen) <= 1e-14
+
+
+def test_B_cg_iterations_and_residual(config_B):
+    """CG at the shipped tolerance: iteration count within +-2 of the reference algorithm (C restatement) and the
+    true residual below sqrt(tol) (src/Models.jl:94-126)."""
+    import elphdynamics_b200 as E
+    from oracle.cref import CRef
+    om, em, rng = config_B
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    xc = np.zeros(om.Ndim)
+    it_c, eps_c = CRef(om).cg(xc, b, tol=om.tol, maxiter=om.maxiter)
+    xe = np.zeros(om.Ndim)
+    it_e, res_e, flag_e = E.ldiv_(xe, em, b)
+    assert flag_e == 0 and abs(it_e - it_c) <= 2, (it_e, it_c)
+    chk = np.zeros(om.Ndim)
+    E.mulMTM_(chk, em, xe)
+    true_res = np.linalg.norm(chk - b) / np.linalg.norm(b)
+    assert true_res <= np.sqrt(om.tol) and abs(true_res - res_e) <= 1e-8
+    assert relerr(xe, xc) <= 1e-3
+
+
+def test_B_kpm_pcg_and_force(config_B):
+    import elphdynamics_b200 as E
+    from oracle.kpm import KPMPreconditioner
+    from oracle.solvers import ConjugateGradient, ldiv
+    om, em, rng = config_B
+    Po, Pe = KPMPreconditioner(om), E.SymmetricKPMPreconditioner(em)
+    noise = rng.normal(size=2 * om.N)
+    Po.setup(noise)
+    info = E.setup_(Pe, noise)
+    assert info.active == 1 and Po.active
+    assert np.array_equal(Pe.orders(), Po.order)
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    xo, xe = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    it_o, _, fo = ldiv(xo, om, b, cg, Po)
+    it_e, res_e, fe = E.ldiv_(xe, em, b, Pe)
+    assert fo == fe == 0 and abs(it_o - it_e) <= 2, (it_o, it_e)
+    # force kernel at full size (no solve involved): <dM/dx> with the oracle's vectors
+    do, de = np.zeros(om.Ndof), np.zeros(om.Ndof)
+    om.muldMdx(do, g, xo)
+    E.muldMdx_(de, g, em, xo)
+    assert relerr(de, do) <= 1e-9
+
+
+def test_E_products_64x64_L400():
+    """Config E: Holstein 64x64, Ltau = 400 (1,638,400 points)."""
+    import elphdynamics_b200 as E
+    from oracle.cref import CRef
+    om, rng = oracle_holstein("square", 64, 40.0, 0.1, mu=-1.0, seed=5, eps=0.3)
+    em = engine_holstein_like(om)
+    c = CRef(om)
+    u, v = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    yc, ye = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    c.mulMTM(yc, v)
+    E.mulMTM_(ye, em, v)
+    assert relerr(ye, yc) <= 1e-12
+    Mv, Mtu = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    E.mulM_(Mv, em, v)
+    E.mulMT_(Mtu, em, u)
+    assert abs(u @ Mv - Mtu @ v) <= 1e-12 * np.linalg.norm(u) * np.linalg.norm(Mv)
+    for py in (8, 4):
+        em._call("elph_set_tuning", 2, py)
+        y2 = np.zeros(om.Ndim)
+        E.mulMTM_(y2, em, v)
+        assert relerr(y2, yc) <= 1e-12
+    em.close()
+
+
+def test_C_ssh_32x32_L200_products():
+    """Config C: SSH 32x32, Ltau = 200 (phonon-modulated bonds, per-(tau,bond) tables)."""
+    import elphdynamics_b200 as E
+    from helpers_ssh import engine_ssh_like, oracle_ssh
+    om, rng = oracle_ssh(Lside=32, beta=10.0, dtau=0.05, seed=11)
+    em = engine_ssh_like(om)
+    u, v = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    yo, ye = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    om.mulMTM(yo, v)
+    E.mulMTM_(ye, em, v)
+    assert relerr(ye, yo) <= 1e-12
+    Mv, Mtu = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    E.mulM_(Mv, em, v)
+    E.mulMT_(Mtu, em, u)
+    assert abs(u @ Mv - Mtu @ v) <= 1e-12 * np.linalg.norm(u) * np.linalg.norm(Mv)
+    do, de = np.zeros(om.Ndof), np.zeros(om.Ndof)
+    om.muldMdx(do, u, v)
+    E.muldMdx_(de, u, em, v)
+    assert relerr(de, do) <= 1e-9
+    em.close()
