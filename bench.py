@@ -176,6 +176,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # work on a real (non-legacy) stream: CUDA events time it, and the engine can capture CUDA graphs on it
+    torch.cuda.set_stream(torch.cuda.Stream())
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

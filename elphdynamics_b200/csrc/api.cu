@@ -104,6 +104,10 @@ void build(elph_handle* h, const elph_config* c) {
     ELPH_CUDA(cudaGetDeviceProperties(&prop, dev));
     ELPH_REQUIRE(prop.major >= 10, ELPH_ERR_UNSUPPORTED, "libelph_b200 requires a Blackwell (sm_100a) GPU");
     h->sm_count = prop.multiProcessorCount;
+    // the handle works on its own non-blocking stream (CUDA graphs cannot be captured on the legacy default stream);
+    // elph_set_stream replaces it
+    ELPH_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
     // dynamic shared memory available to the slice kernels: the opt-in maximum minus 1 KB kept for their
     // (small) static shared arrays -- cudaFuncAttributeMaxDynamicSharedMemorySize counts static + dynamic
     h->smem_optin = prop.sharedMemPerBlockOptin - 1024;
@@ -263,6 +267,7 @@ void build(elph_handle* h, const elph_config* c) {
         elph_to_engine(h, st, dst, h->Nph);
         have = true;
     };
+    ELPH_CUDA(cudaDeviceSynchronize());   // cudaMemset on the legacy stream does not order with the handle's stream
     load_diag(c->fa_Q, h->d_Q, h->have_Q);
     load_diag(c->fa_M, h->d_Mass, h->have_M);
     elph_launch_update_model(h);
@@ -274,6 +279,20 @@ void destroy(elph_handle* h) {
     cudaDeviceSynchronize();
     elph_kpm_free(h);
     elph_hmc_free(h);
+    for (auto& g : h->cg_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->cg_graphs.clear();
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    if (h->pipe.init) {
+        for (int b = 0; b < 2; ++b) {
+            cudaEventDestroy(h->pipe.ev_in[b]);
+            cudaEventDestroy(h->pipe.ev_comp[b]);
+            cudaEventDestroy(h->pipe.ev_out[b]);
+            for (int k = 0; k < 4; ++k) cudaFree(h->pipe.buf[b][k]);
+        }
+        cudaStreamDestroy(h->pipe.s_in);
+        cudaStreamDestroy(h->pipe.s_out);
+    }
     if (h->d_D_alloc) {  // sharded: d_D points one slice into this allocation
         cudaFree(h->d_D_alloc);
         h->d_D = nullptr;
@@ -342,6 +361,8 @@ int32_t elph_destroy(elph_handle* h) {
 int32_t elph_set_stream(elph_handle* h, void* cuda_stream) {
     ENTER(h) {
         ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+        h->own_stream = false;
         h->stream = (cudaStream_t)cuda_stream;
         return ELPH_OK;
     }
@@ -480,9 +501,62 @@ int32_t elph_get_cosh_sinh(elph_handle* h, double* cosht, double* sinht) {
     ELPH_CATCH(h)
 }
 
+// Batched products from/to HOST buffers: chunks of the batch are pipelined over three streams (H2D copy | layout
+// change + kernel + layout change | D2H copy) with double-buffered staging, so that the two PCIe directions and
+// the kernel overlap.  The entry point is PCIe-bound: 16 B per point cross the bus for 24 B of HBM traffic.
+static void host_matvec_pipelined(elph_handle* h, MatvecMode mode, const double* v, double* y, int64_t nrhs) {
+    HostPipe& P = h->pipe;
+    const int64_t chunk = 8;
+    const size_t cdoubles = (size_t)chunk * h->Ndim;
+    if (!P.init) {
+        ELPH_CUDA(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
+        ELPH_CUDA(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            ELPH_CUDA(cudaEventCreateWithFlags(&P.ev_in[b], cudaEventDisableTiming));
+            ELPH_CUDA(cudaEventCreateWithFlags(&P.ev_comp[b], cudaEventDisableTiming));
+            ELPH_CUDA(cudaEventCreateWithFlags(&P.ev_out[b], cudaEventDisableTiming));
+            for (int k = 0; k < 4; ++k) P.buf[b][k] = elph_dalloc<double>(cdoubles);
+        }
+        P.init = true;
+    }
+    ELPH_CUDA(cudaStreamSynchronize(h->stream));
+    const int64_t nchunks = (nrhs + chunk - 1) / chunk;
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int b = (int)(k & 1);
+        const int64_t r0 = k * chunk, nr = std::min<int64_t>(chunk, nrhs - r0);
+        const size_t nd = (size_t)nr * h->Ndim;
+        double *in_host = P.buf[b][0], *in_eng = P.buf[b][1], *out_eng = P.buf[b][2], *out_host = P.buf[b][3];
+        if (k >= 2) ELPH_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_comp[b], 0));     // staging slot free again
+        ELPH_CUDA(cudaMemcpyAsync(in_host, v + (size_t)r0 * h->Ndim, nd * sizeof(double), cudaMemcpyHostToDevice, P.s_in));
+        ELPH_CUDA(cudaEventRecord(P.ev_in[b], P.s_in));
+        ELPH_CUDA(cudaStreamWaitEvent(h->stream, P.ev_in[b], 0));
+        if (k >= 2) ELPH_CUDA(cudaStreamWaitEvent(h->stream, P.ev_out[b], 0));   // previous D2H of this slot done
+        elph_to_engine(h, in_host, in_eng, h->N, nr);
+        MatvecArgs a;
+        a.v = in_eng;
+        a.y = out_eng;
+        a.nbatch = nr;
+        a.v_stride = h->Ndim;
+        a.y_stride = h->Ndim;
+        elph_launch_matvec(h, mode, a);
+        elph_from_engine(h, out_eng, out_host, h->N, nr);
+        ELPH_CUDA(cudaEventRecord(P.ev_comp[b], h->stream));
+        ELPH_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_comp[b], 0));
+        ELPH_CUDA(cudaMemcpyAsync(y + (size_t)r0 * h->Ndim, out_host, nd * sizeof(double), cudaMemcpyDeviceToHost, P.s_out));
+        ELPH_CUDA(cudaEventRecord(P.ev_out[b], P.s_out));
+    }
+    ELPH_CUDA(cudaStreamSynchronize(P.s_out));
+    ELPH_CUDA(cudaStreamSynchronize(h->stream));
+}
+
 static int32_t host_matvec(elph_handle* h, MatvecMode mode, const double* v, double* y, int64_t nrhs) {
     ENTER(h) {
         ELPH_REQUIRE(nrhs >= 1, ELPH_ERR_INVALID, "nrhs must be >= 1");
+        ELPH_REQUIRE(v && y, ELPH_ERR_INVALID, "null host pointer");
+        if (nrhs >= 16) {
+            host_matvec_pipelined(h, mode, v, y, nrhs);
+            return ELPH_OK;
+        }
         double* vin = (nrhs == 1) ? h->d_va : stage(h, 2, (size_t)h->Ndim * nrhs);
         double* vout = (nrhs == 1) ? h->d_vb : stage(h, 3, (size_t)h->Ndim * nrhs);
         upload_vec(h, v, vin, h->N, nrhs);
@@ -821,6 +895,7 @@ int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob) {
             h->d_D_alloc = alloc;
             h->d_D = alloc + h->N;
         }
+        ELPH_CUDA(cudaDeviceSynchronize());
         h->sharded = true;
         h->shard_tau0 = (int)tau0;
         h->shard_Lglob = (int)Lglob;
@@ -915,6 +990,20 @@ int32_t elph_dev_cg_solve(elph_handle* h, const double* b_dev, double* x_dev, in
     }
     ELPH_CATCH(h)
 }
+int32_t elph_dev_kpm_apply(elph_handle* h, const double* vin_dev, double* vout_dev) {
+    ENTER(h) {
+        elph_kpm_apply_dev(h, vin_dev, vout_dev);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_fourier_accelerate(elph_handle* h, const double* vin_dev, double* vout_dev, double power, int32_t use_mass) {
+    ENTER(h) {
+        elph_fourier_accelerate_dev(h, vin_dev, vout_dev, power, use_mass != 0);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
 int64_t elph_launch_count(const elph_handle* h) { return h ? h->launches : 0; }
 int32_t elph_set_chunk(elph_handle* h, int32_t c) {
     ENTER(h) {
@@ -930,7 +1019,8 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
         switch (key) {
             case 0: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "chunk out of range"); h->chunk_override = value; break;
             case 1: h->sq_disable = (value != 0); break;
-            case 2: h->sq_py = value; break;
+            case 2: h->sq_py = value; h->kpm_version++; break;
+            case 3: h->use_graphs = (value != 0); break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }
         return ELPH_OK;

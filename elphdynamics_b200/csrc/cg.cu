@@ -246,13 +246,15 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
     }
 
     ELPH_CUDA(cudaMemsetAsync(h->d_p[1], 0, n * sizeof(double), st));  // p_old of the first iteration (beta = 0)
-    const int check_every = precond ? 2 : 8;
+    // The host polls the convergence latch every `check_every` iterations (even, so the p double buffer is back at
+    // parity 0).  A block of check_every iterations is captured ONCE into a CUDA graph (per solution vector /
+    // preconditioner state) and replayed: one graph launch instead of 2-6 kernel launches per iteration.
+    const int check_every = precond ? 4 : 8;
     h->kpm_skip_enabled = true;
     int64_t launched = 0;
-    int parity = 0;
-    while (true) {
-        const int64_t todo = std::min<int64_t>(check_every, maxiter - launched);
-        for (int64_t k = 0; k < todo; ++k) {
+    auto body = [&](int64_t niter) {
+        int parity = 0;
+        for (int64_t k = 0; k < niter; ++k) {
             MatvecArgs m;
             m.v = nullptr;
             m.y = h->d_z;
@@ -274,6 +276,47 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
                 h->launches++;
             }
             parity ^= 1;
+        }
+    };
+    auto graph_for = [&]() -> CgGraph* {
+        for (auto& g : h->cg_graphs)
+            if (g.x == x_dev && g.precond == precond && g.kpm_version == h->kpm_version && g.chunk == h->chunk_override &&
+                g.sq_disable == h->sq_disable && g.stream == st)
+                return &g;
+        CgGraph g;
+        g.x = x_dev; g.precond = precond; g.kpm_version = h->kpm_version; g.chunk = h->chunk_override;
+        g.sq_disable = h->sq_disable; g.stream = st;
+        const int64_t before = h->launches;
+        cudaGraph_t graph = nullptr;
+        ELPH_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        try {
+            body(check_every);
+        } catch (...) {
+            cudaStreamEndCapture(st, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        ELPH_CUDA(cudaStreamEndCapture(st, &graph));
+        g.nlaunch = h->launches - before;
+        h->launches = before;
+        ELPH_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+        ELPH_CUDA(cudaGraphDestroy(graph));
+        if (h->cg_graphs.size() >= 16) {   // bounded cache
+            cudaGraphExecDestroy(h->cg_graphs.front().exec);
+            h->cg_graphs.erase(h->cg_graphs.begin());
+        }
+        h->cg_graphs.push_back(g);
+        return &h->cg_graphs.back();
+    };
+    while (true) {
+        const int64_t todo = std::min<int64_t>(check_every, maxiter - launched);
+        // the first block runs as plain launches (it also performs the one-time kernel attribute set-up)
+        if (h->use_graphs && todo == check_every && launched > 0 && st != nullptr) {
+            CgGraph* g = graph_for();
+            ELPH_CUDA(cudaGraphLaunch(g->exec, st));
+            h->launches += g->nlaunch;
+        } else {
+            body(todo);
         }
         launched += todo;
         ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));

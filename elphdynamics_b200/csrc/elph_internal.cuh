@@ -108,9 +108,34 @@ struct HmcState {
     double *Lphip = nullptr, *Lphim = nullptr, *Op = nullptr, *Om = nullptr, *u = nullptr;        // Ndim
 };
 
+// a block of CG iterations captured as a CUDA graph (cg.cu); the key fields decide whether it can be replayed
+struct CgGraph {
+    cudaGraphExec_t exec = nullptr;
+    const double* x = nullptr;
+    bool precond = false;
+    int64_t kpm_version = 0;
+    int chunk = 0;
+    bool sq_disable = false;
+    cudaStream_t stream = nullptr;
+    int64_t nlaunch = 0;
+};
+
+// copy/compute pipeline of the batched host-buffer entry points (api.cu: host_matvec_pipelined)
+struct HostPipe {
+    bool init = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    double* buf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+};
+
 struct elph_handle {
     std::string err;
     HmcState hmc;
+    HostPipe pipe;
+    std::vector<CgGraph> cg_graphs;
+    int64_t kpm_version = 0;   // bumped whenever the KPM kernels' launch parameters change
+    bool use_graphs = true;
+    bool own_stream = false;
     std::set<const void*> smem_enabled;  // kernels that already have the opt-in shared-memory attribute
     int device = 0;
     int sm_count = 148;

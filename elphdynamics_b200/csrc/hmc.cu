@@ -102,6 +102,7 @@ void elph_hmc_ensure(elph_handle* h) {
     S.v = z(h->Ndof); S.v0 = z(h->Ndof); S.x0 = z(h->Ndof); S.dS = z(h->Ndof); S.y = z(h->Ndof); S.Q = z(h->Ndof);
     S.Lam = z(h->Ndim); S.Rp = z(h->Ndim); S.Rm = z(h->Ndim); S.phip = z(h->Ndim); S.phim = z(h->Ndim);
     S.Lphip = z(h->Ndim); S.Lphim = z(h->Ndim); S.Op = z(h->Ndim); S.Om = z(h->Ndim); S.u = z(h->Ndim);
+    ELPH_CUDA(cudaDeviceSynchronize());
     S.init = true;
 }
 

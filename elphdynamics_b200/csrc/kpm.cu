@@ -372,6 +372,8 @@ void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2) {
     K.d_schedule = elph_dalloc<int>(K.Lo2);
     K.d_nu = elph_dalloc<cplx>((size_t)h->L * h->N);
     ELPH_CUDA(cudaMemset(K.d_nu, 0, (size_t)h->L * h->N * sizeof(cplx)));
+    ELPH_CUDA(cudaDeviceSynchronize());
+    h->kpm_version++;
 }
 
 void elph_kpm_free(elph_handle* h) {
@@ -457,6 +459,7 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
             ELPH_CUDA(cudaMemcpyAsync(K.d_schedule, K.schedule.data(), K.Lo2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
             ELPH_CUDA(cudaStreamSynchronize(h->stream));  // host vectors may be reallocated by the next setup
             recomputed = true;
+            h->kpm_version++;   // captured CG graphs carry the old polynomial orders / window
         }
         K.active = true;
     } else {

@@ -410,7 +410,10 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
     const bool fusep = (a.cg_S != nullptr);
     // tile shape: PY rows per warp
     int PY;
-    if (Lx == 32) PY = (Ly % 16 == 0 && h->sq_py != 8) ? 16 : 8;
+    // latency regime (one L2-resident lattice, fewer slices than the machine can hold): shorter per-warp chains win
+    // (measured at 32x32xL200: PY=8, C=2 -> 5.5 us; PY=16, C=1 -> 7.6 us); throughput regime: PY=16, C=4
+    const bool latency_regime = (a.nbatch * (int64_t)h->L < 6LL * h->sm_count);
+    if (Lx == 32) PY = (Ly % 16 == 0 && h->sq_py != 8 && !(latency_regime && h->sq_py == 0)) ? 16 : 8;
     else if (Lx == 128) PY = 4;
     else PY = 8;
     if (h->sq_py == 4 && Lx == 64) PY = 4;
@@ -429,7 +432,7 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
         // machine is covered ~4x, otherwise split finer
         // measured on B200 (32x32xL200, 16..128 replicas): C = 4 is the optimum once the grid covers the
         // machine several times (5.7-6.2 TB/s); longer chunks lose more to the tail than they save in halo
-        C = 1;
+        C = (latency_regime && Lx == 32) ? 2 : 1;
         const int64_t want = 6LL * h->sm_count;
         for (int c : {4, 2}) {
             if (a.nbatch * ((h->L + c - 1) / c) >= want) { C = c; break; }

@@ -289,6 +289,9 @@ int32_t elph_dev_ptr_expnV(elph_handle* h, double** expnV_dev);
 /* CG on device pointers; asynchronous until the result scalars are read (blocks). */
 int32_t elph_dev_cg_solve(elph_handle* h, const double* b_dev, double* x_dev, int32_t use_precond, double tol,
                           int64_t maxiter, int64_t* iters, double* eps);
+/* ldiv!(vout,P,vin) and fourier_accelerate! on device pointers (engine layout), asynchronous */
+int32_t elph_dev_kpm_apply(elph_handle* h, const double* vin_dev, double* vout_dev);
+int32_t elph_dev_fourier_accelerate(elph_handle* h, const double* vin_dev, double* vout_dev, double power, int32_t use_mass);
 /* number of kernels this handle has launched since creation (bench `gpu_launches`) */
 int64_t elph_launch_count(const elph_handle* h);
 /* tuning knob: tau-slices per CTA for the fused matvec kernels (0 = auto) */

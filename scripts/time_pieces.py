@@ -1,0 +1,47 @@
+"""Warm device-side timing (CUDA events) of the pieces of a PCG iteration on config B (development aid)."""
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+import elphdynamics_b200 as E
+from helpers import engine_holstein_like, oracle_holstein
+
+Ls = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+beta = float(sys.argv[2]) if len(sys.argv) > 2 else 20.0
+om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-1.0)
+em = engine_holstein_like(om)
+torch.cuda.set_stream(torch.cuda.Stream())
+em.set_stream(torch.cuda.current_stream().cuda_stream)
+lib, h, n = em._lib, em.handle, om.Ndim
+P = E.SymmetricKPMPreconditioner(em)
+info = E.setup_(P, rng.normal(size=2 * om.N))
+fa = E.FourierAccelerator(em)
+E.update_Q_(fa, em, 0.0, 10.0, 1.0)
+v = torch.randn(n, dtype=torch.float64, device="cuda")
+y = torch.empty_like(v)
+
+
+def timeit(fn, iters=200, warm=20):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+print("kpm orders: total", info.total_order, "max", info.max_order)
+print(f"MTM                : {timeit(lambda: lib.elph_dev_mulMTM(h, v.data_ptr(), y.data_ptr())):8.2f} us")
+print(f"KPM apply (2 FFT + poly): {timeit(lambda: lib.elph_dev_kpm_apply(h, v.data_ptr(), y.data_ptr())):8.2f} us")
+print(f"fourier_accelerate (2 FFT in one kernel): {timeit(lambda: lib.elph_dev_fourier_accelerate(h, v.data_ptr(), y.data_ptr(), 1.0, 0)):8.2f} us")
+for py in (2, 4, 8):
+    lib.elph_set_tuning(h, 2, py)
+    print(f"KPM apply py={py}: {timeit(lambda: lib.elph_dev_kpm_apply(h, v.data_ptr(), y.data_ptr())):8.2f} us")
+lib.elph_set_tuning(h, 2, 0)

@@ -1,0 +1,139 @@
+"""GPU edge cases: degenerate lattices and time extents, error behaviour of the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import engine_holstein_like, relerr, synthetic_field
+from oracle import lattice as olat
+from oracle.holstein import HolsteinModel as OracleHolstein
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(lat, bonds, t, beta, dtau, seed=0, **kw):
+    om = OracleHolstein(lat, bonds, t, beta, dtau, omega=1.0, lam=1.0, mu=-0.4, **kw)
+    rng = np.random.default_rng(seed)
+    om.x[:] = synthetic_field(rng, om.N, om.L, beta, 1.0, 1.0, 0.3)
+    om.update_model()
+    return om, engine_holstein_like(om), rng
+
+
+@pytest.mark.parametrize("beta,dtau", [(0.1, 0.1), (0.2, 0.1), (0.3, 0.1), (1.1, 0.1), (1.3, 0.1), (2.3, 0.1)],
+                         ids=["L1", "L2", "L3", "L11-prime", "L13-prime", "L23-prime"])
+def test_short_and_prime_time_extents(beta, dtau):
+    """Ltau = 1 (M = I + B), 2, 3 and prime lengths (generic-radix FFT stage, antiperiodic wrap on every slice pair)."""
+    import elphdynamics_b200 as E
+    from oracle.fourier import TimeFreqFFT
+    om, em, rng = _pair(olat.Lattice(2, 1, 4), olat.SQUARE_BONDS, 1.0, beta, dtau)
+    v = rng.normal(size=om.Ndim)
+    yo, ye = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    for fo, fe in ((om.mulM, E.mulM_), (om.mulMT, E.mulMT_), (om.mulMTM, E.mulMTM_)):
+        fo(yo, v)
+        fe(ye, em, v)
+        assert relerr(ye, yo) <= 1e-12, fe.__name__
+    nu = np.zeros(om.Ndim, dtype=np.complex128)
+    E.tau_to_omega_(nu, E.TimeFreqFFT(em), v)
+    assert relerr(nu, TimeFreqFFT(om.N, om.L).tau_to_omega(v)) <= 1e-13
+    do, de = np.zeros(om.Ndof), np.zeros(om.Ndof)
+    om.muldMdx(do, v, yo)
+    E.muldMdx_(de, v, em, yo)
+    assert relerr(de, do) <= 1e-9
+    em.close()
+
+
+def test_single_site_no_bonds():
+    """examples/holstein_hmc_single_site.toml: N = 1, Nbonds = 0 (empty neighbour table, zero colour groups)."""
+    import elphdynamics_b200 as E
+    from oracle.solvers import ConjugateGradient, ldiv
+    om, em, rng = _pair(olat.Lattice(1, 1, 1), [], np.zeros(0), 2.0, 0.1)
+    assert om.Nbonds == 0 and em.Nbonds == 0
+    v = rng.normal(size=om.Ndim)
+    yo, ye = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    for fo, fe in ((om.mulM, E.mulM_), (om.mulMT, E.mulMT_), (om.mulMTM, E.mulMTM_)):
+        fo(yo, v)
+        fe(ye, em, v)
+        assert relerr(ye, yo) <= 1e-13
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, v)
+    xo, xe = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    it_o, _, f_o = ldiv(xo, om, b, ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter))
+    it_e, _, f_e = E.ldiv_(xe, em, b)
+    assert f_o == f_e == 0 and abs(it_o - it_e) <= 2 and relerr(xe, xo) <= 1e-4
+    em.close()
+
+
+def test_disordered_hoppings_fall_back_to_the_generic_kernel():
+    """Per-bond hoppings (sigma_t != 0 in the reference) on a 32x32 lattice: the register/shuffle kernel requires a
+    uniform (cosh, sinh) per colour, so the generic kernel must be selected -- and must agree with the oracle."""
+    import elphdynamics_b200 as E
+    lat = olat.Lattice(2, 1, 32)
+    rng0 = np.random.default_rng(5)
+    t = 1.0 + 0.1 * rng0.normal(size=2 * lat.nsites)
+    om, em, rng = _pair(lat, olat.SQUARE_BONDS, t, 0.5, 0.1)
+    sq = C.c_int32()
+    em._call("elph_get_kernel_info", C.byref(sq), None)
+    assert sq.value == 0
+    v = rng.normal(size=om.Ndim)
+    yo, ye = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    om.mulMTM(yo, v)
+    E.mulMTM_(ye, em, v)
+    assert relerr(ye, yo) <= 1e-12
+    em.close()
+
+
+def test_maxiter_flag_and_fallback_semantics():
+    """ldiv!: hitting maxiter gives flag 1 and a zeroed x (src/Models.jl:156-166); with a preconditioner the failed
+    attempt is retried without it at 10*maxiter (:129-133)."""
+    import elphdynamics_b200 as E
+    from oracle.kpm import KPMPreconditioner
+    from oracle.solvers import ConjugateGradient, ldiv
+    om, em, rng = _pair(olat.Lattice(2, 1, 4), olat.SQUARE_BONDS, 1.0, 2.0, 0.1)
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    em._call("elph_set_solver", 1e-10, 3, 0.0)
+    cg = ConjugateGradient(om.Ndim, tol=1e-10, maxiter=3)
+    xo, xe = np.ones(om.Ndim) * 0, np.zeros(om.Ndim)
+    it_o, r_o, f_o = ldiv(xo, om, b, cg)
+    it_e, r_e, f_e = E.ldiv_(xe, em, b)
+    assert (it_o, f_o) == (3, 1) and (it_e, f_e) == (3, 1) and not xe.any() and abs(r_e - r_o) <= 1e-9 * r_o
+    Po, Pe = KPMPreconditioner(om), E.SymmetricKPMPreconditioner(em)
+    noise = rng.normal(size=2 * om.N)
+    Po.setup(noise)
+    E.setup_(Pe, noise)
+    xo[:] = 0
+    it_o, r_o, f_o = ldiv(xo, om, b, cg, Po)            # PCG fails at 3 iterations -> CG at 30
+    it_e, r_e, f_e = E.ldiv_(xe, em, b, Pe)
+    assert f_o == f_e and abs(it_o - it_e) <= 2
+    assert em.last_solve_info.used_fallback == 1
+    em.close()
+
+
+def test_error_reporting_through_the_abi():
+    import elphdynamics_b200 as E
+    from elphdynamics_b200._lib import Config, ElphError, check, load, ptr
+    lib = load()
+    cfg = Config()
+    cfg.model, cfg.Ltau, cfg.Nsites, cfg.Nbonds, cfg.Nph, cfg.dtau = 0, 4, 2, 1, 2, 0.1
+    h = C.c_void_p()
+    st = lib.elph_create(C.byref(cfg), C.byref(h))          # neighbor_table / mu are NULL
+    assert st != 0 and b"NULL" in lib.elph_last_error(None)
+    nt = np.array([[5, 9]], dtype=np.int64)                 # site index out of range
+    mu = np.zeros(2)
+    cs = np.ones(1)
+    cfg.neighbor_table, cfg.mu, cfg.cosht, cfg.sinht = ptr(nt, np.int64), ptr(mu), ptr(cs), ptr(cs)
+    st = lib.elph_create(C.byref(cfg), C.byref(h))
+    assert st != 0 and b"out of range" in lib.elph_last_error(None)
+    assert lib.elph_mulM(None, None, None) != 0             # null handle is an error, not a crash
+    lat = E.Lattice(E.UnitCell(2, 1), 4)
+    m = E.HolsteinModel(lat, 1.0, 0.1)
+    m.assign_t(1.0, 0, 0, (1, 0, 0))
+    m.initialize_model_()
+    with pytest.raises(ElphError):                          # preconditioned solve before setup!(P)
+        m._call("elph_cg_solve", ptr(np.ones(m.Ndim)), ptr(np.zeros(m.Ndim)), 1, 0.0, 0, None, None)
+    with pytest.raises(ElphError):                          # fourier acceleration without Q
+        m._call("elph_fourier_accelerate", ptr(np.ones(m.Ndof)), ptr(np.zeros(m.Ndof)), 1.0, 0)
+    with pytest.raises(ValueError):
+        E.mulM_(np.zeros(m.Ndim), m, np.zeros(3))
+    m.close()

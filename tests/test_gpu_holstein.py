@@ -104,14 +104,14 @@ def test_mulMTM_batch(pair):
     import ctypes as C
     from elphdynamics_b200._lib import ptr
     om, em, rng = pair
-    nrhs = 3
-    V = rng.normal(size=(nrhs, om.Ndim))
-    Y = np.zeros_like(V)
-    em._call("elph_mulMTM_batch", nrhs, ptr(V), ptr(Y))
-    yo = np.zeros(om.Ndim)
-    for k in range(nrhs):
-        om.mulMTM(yo, V[k])
-        assert relerr(Y[k], yo) <= MATVEC_TOL
+    for nrhs in (3, 19):      # 19 >= 16: the chunked copy/compute pipeline (3 chunks, ragged tail)
+        V = rng.normal(size=(nrhs, om.Ndim))
+        Y = np.zeros_like(V)
+        em._call("elph_mulMTM_batch", nrhs, ptr(V), ptr(Y))
+        yo = np.zeros(om.Ndim)
+        for k in range(nrhs):
+            om.mulMTM(yo, V[k])
+            assert relerr(Y[k], yo) <= MATVEC_TOL, (nrhs, k)
 
 
 def test_adjointness(pair):
