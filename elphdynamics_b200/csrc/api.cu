@@ -1021,6 +1021,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 1: h->sq_disable = (value != 0); break;
             case 2: h->sq_py = value; h->kpm_version++; break;
             case 3: h->use_graphs = (value != 0); break;
+            case 4: h->kpm_split = (value != 0); h->kpm_version++; break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }
         return ELPH_OK;

@@ -135,6 +135,7 @@ struct elph_handle {
     std::vector<CgGraph> cg_graphs;
     int64_t kpm_version = 0;   // bumped whenever the KPM kernels' launch parameters change
     bool use_graphs = true;
+    bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool own_stream = false;
     std::set<const void*> smem_enabled;  // kernels that already have the opt-in shared-memory attribute
     int device = 0;

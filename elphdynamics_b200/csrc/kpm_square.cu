@@ -161,6 +161,181 @@ __global__ void __launch_bounds__(MAXT) kpm_square_kernel(KsqParams P, int max_o
         }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Cluster-split variant.  A is real, so T_n(A') acts on the real and imaginary parts of the frequency-space vector
+// independently; only the coefficient sums mix them:
+//     sum_n c_n T_n (vr + i vi):   re = sum cr T vr - sum ci T vi ,   im = sum cr T vi + sum ci T vr .
+// A 2-CTA thread-block cluster handles one frequency: CTA 0 runs the chain on vr, CTA 1 on vi, each accumulating
+// A = sum cr T v and B = sum ci T v; the B tiles are swapped through distributed shared memory (DSMEM) ONCE per
+// polynomial (twice per apply).  The work per sweep on the critical chain (the lowest frequency, ~70 terms at
+// config B) is halved.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NSEG, int PY, bool TRANSPOSED>
+__device__ __forceinline__ void apply_A_real(Tile<NSEG, PY>& s, const Tile<NSEG, PY>& ev, const KsqParams& P, double* strips,
+                                             int& xbuf, int warp, int nwarps, int lane) {
+    constexpr int LX = 32 * NSEG;
+    double ab[NSEG], be[NSEG];
+    if (!TRANSPOSED) {
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+        g0_x_even(s, P.c0, P.s0);
+        g1_x_odd(s, P.c1, P.s1, lane);
+        g2_y_even(s, P.c2, P.s2);
+        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+        xbuf ^= 1;
+        g3_y_odd(s, P.c3, P.s3, ab, be);
+    } else {
+        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+        xbuf ^= 1;
+        g3_y_odd(s, P.c3, P.s3, ab, be);
+        g2_y_even(s, P.c2, P.s2);
+        g1_x_odd(s, P.c1, P.s1, lane);
+        g0_x_even(s, P.c0, P.s0);
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+    }
+}
+
+// A = sum_n cr_n T_n v ,  B = sum_n ci'_n T_n v   (ci' = -ci for the transposed/conjugated pass)
+template <int NSEG, int PY, bool TRANSPOSED>
+__device__ __forceinline__ void poly_real(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, const Tile<NSEG, PY>& vin, const Tile<NSEG, PY>& ev,
+                                          const cplx* c_s, int order, const KsqParams& P, double* strips, int& xbuf, int warp,
+                                          int nwarps, int lane) {
+    Tile<NSEG, PY> un, uprev, s;
+    const double sg = TRANSPOSED ? -1.0 : 1.0;
+    const double c0r = c_s[0].x, c0i = sg * c_s[0].y;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double v = vin.a[r][q];
+            A.a[r][q] = c0r * v;
+            B.a[r][q] = c0i * v;
+            un.a[r][q] = v;
+            uprev.a[r][q] = 0.0;
+        }
+    const double k1 = P.inv_mag, k2 = P.avg_over_mag;
+    for (int n = 1; n < order; ++n) {
+        s = un;
+        apply_A_real<NSEG, PY, TRANSPOSED>(s, ev, P, strips, xbuf, warp, nwarps, lane);
+        const double cr = c_s[n].x, ci = sg * c_s[n].y;
+        const double two = (n > 1) ? 2.0 : 1.0, one = (n > 1) ? 1.0 : 0.0;
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                double a = k1 * s.a[r][q] - k2 * un.a[r][q];
+                a = two * a - one * uprev.a[r][q];
+                uprev.a[r][q] = un.a[r][q];
+                un.a[r][q] = a;
+                A.a[r][q] += cr * a;
+                B.a[r][q] += ci * a;
+            }
+    }
+}
+
+template <int NSEG, int PY, int MAXT>
+__global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int max_order) {
+    constexpr int LX = 32 * NSEG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // NOTE: both CTAs of a cluster take the same early exit (the flag is written before this kernel starts)
+    if (P.skip && *P.skip) return;
+    unsigned int crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    // both CTAs of the pair must be running before either touches the other's shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int N = LX * P.Ly;
+    const int w = P.schedule[blockIdx.x >> 1];
+    const int order = P.order[w];
+    cplx* c_s = reinterpret_cast<cplx*>(smem_raw);                                            // [max_order]
+    double* strips = reinterpret_cast<double*>(smem_raw + (size_t)max_order * sizeof(cplx));  // 2 x [nwarps][2][LX]
+    double* xch = strips + 2ull * nwarps * 2 * LX;                                            // [N] written by the partner CTA
+    for (int k = threadIdx.x; k < order; k += blockDim.x) c_s[k] = P.coeff[P.coeff_off[w] + k];
+    const size_t tile_off = (size_t)warp * PY * LX;
+    Tile<NSEG, PY> v, A, B, ev;
+    const double* in_comp = reinterpret_cast<const double*>(P.in) + crank;   // re (CTA 0) or im (CTA 1) of the complex input
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const size_t e = tile_off + r * LX + 32 * q + lane;
+            v.a[r][q] = in_comp[2 * ((size_t)w * N + e)];
+            ev.a[r][q] = P.eVbar[e];
+        }
+    __syncthreads();
+    // DSMEM address of the partner's exchange buffer
+    const uint32_t my_xch = (uint32_t)__cvta_generic_to_shared(xch);
+    uint32_t remote_xch;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_xch) : "r"(my_xch), "r"(crank ^ 1u));
+    auto cluster_sync = []() {
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    };
+    // swap B tiles and combine:  CTA 0 (re): A - B_partner ;  CTA 1 (im): A + B_partner
+    auto swap_combine = [&](Tile<NSEG, PY>& out) {
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const uint32_t addr = remote_xch + (uint32_t)((tile_off + r * LX + 32 * q + lane) * sizeof(double));
+                asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(B.a[r][q]) : "memory");
+            }
+        cluster_sync();
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const double bp = xch[tile_off + r * LX + 32 * q + lane];
+                out.a[r][q] = (crank == 0) ? (A.a[r][q] - bp) : (A.a[r][q] + bp);
+            }
+        cluster_sync();   // the partner may overwrite xch again only after both have read
+    };
+    int xbuf = 0;
+    Tile<NSEG, PY> t1, t2;
+    poly_real<NSEG, PY, true>(A, B, v, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);    // M^-T[w,w]
+    swap_combine(t1);
+    poly_real<NSEG, PY, false>(A, B, t1, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);  // M^-1[w,w]
+    swap_combine(t2);
+    const int wm = P.L - 1 - w;
+    double* out_comp = reinterpret_cast<double*>(P.out) + crank;
+    const double msign = (crank == 0) ? 1.0 : -1.0;   // mirror frequency = complex conjugate
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const size_t e = tile_off + r * LX + 32 * q + lane;
+            if (wm != w) out_comp[2 * ((size_t)w * N + e)] = t2.a[r][q];
+            out_comp[2 * ((size_t)wm * N + e)] = msign * t2.a[r][q];
+        }
+}
+
+template <int NSEG, int PY, int MAXT>
+void launch_ksq_split(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
+    constexpr int LX = 32 * NSEG;
+    const size_t smem = (size_t)max_order * sizeof(cplx) + 2ull * nwarps * 2 * LX * sizeof(double) +
+                        (size_t)LX * P.Ly * sizeof(double);
+    ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "KPM split kernel does not fit in shared memory");
+    elph_enable_smem(h, kpm_square_split_kernel<NSEG, PY, MAXT>);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * h->kpm.Lo2);
+    cfg.blockDim = dim3(nwarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ELPH_CUDA(cudaLaunchKernelEx(&cfg, kpm_square_split_kernel<NSEG, PY, MAXT>, P, max_order));
+    h->launches++;
+}
+
 template <int NSEG, int PY, int MAXT>
 void launch_ksq(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
     constexpr int LX = 32 * NSEG;
@@ -195,7 +370,8 @@ bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, con
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
 #define KSQ_CASE(NS, PYV, MAXT)                                    \
     if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {       \
-        launch_ksq<NS, PYV, MAXT>(h, P, nwarps, max_order);        \
+        if (h->kpm_split) launch_ksq_split<NS, PYV, MAXT>(h, P, nwarps, max_order); \
+        else launch_ksq<NS, PYV, MAXT>(h, P, nwarps, max_order);   \
         return true;                                               \
     }
     KSQ_CASE(1, 4, 512)

@@ -73,6 +73,27 @@ __device__ __forceinline__ void g3_y_odd(Tile<NSEG, PY>& t, double c, double s, 
     }
 }
 
+// real tile: publish the edge rows, one barrier, fetch the neighbours' edge rows.  strip: [nwarps][2][LX].
+template <int NSEG, int PY>
+__device__ __forceinline__ void exchange_edges1(const Tile<NSEG, PY>& t, double* strip, int warp, int nwarps, int lane,
+                                                double (&above)[NSEG], double (&below)[NSEG]) {
+    constexpr int LX = 32 * NSEG;
+    double* mine = strip + (size_t)warp * 2 * LX;
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        mine[32 * q + lane] = t.a[0][q];
+        mine[LX + 32 * q + lane] = t.a[PY - 1][q];
+    }
+    __syncthreads();
+    const int up = (warp == 0) ? nwarps - 1 : warp - 1;
+    const int dn = (warp + 1 == nwarps) ? 0 : warp + 1;
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        above[q] = strip[(size_t)up * 2 * LX + LX + 32 * q + lane];
+        below[q] = strip[(size_t)dn * 2 * LX + 32 * q + lane];
+    }
+}
+
 // publish the edge rows of a complex tile (re, im), one barrier, fetch the neighbours' edge rows.
 // strip: [nwarps][4][LX] doubles = (first row re, first row im, last row re, last row im) per warp.
 template <int NSEG, int PY>

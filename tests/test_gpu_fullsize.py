@@ -93,6 +93,22 @@ def test_B_kpm_pcg_and_force(config_B):
     info = E.setup_(Pe, noise)
     assert info.active == 1 and Po.active
     assert np.array_equal(Pe.orders(), Po.order)
+    # preconditioner apply: all three kernel variants (2-CTA cluster split, single CTA, generic shared-memory)
+    # against the oracle at the engine's spectral window
+    from oracle.kpm import kpm_coefficients
+    Po.lam_lo, Po.lam_hi = info.lambda_lo, info.lambda_hi
+    Po.lam_avg, Po.lam_mag = (Po.lam_hi + Po.lam_lo) / 2, (Po.lam_hi - Po.lam_lo) / 2
+    Po.coeff = [kpm_coefficients(int(Po.order[w]), Po.lam_lo, Po.lam_hi, Po.phis[w]) for w in range(Po.Lo2)]
+    r = rng.normal(size=om.Ndim)
+    zo = np.zeros(om.Ndim)
+    Po.ldiv(zo, r)
+    for key, val in ((4, 1), (4, 0), (1, 1)):
+        em._call("elph_set_tuning", key, val)
+        ze = np.zeros(om.Ndim)
+        E.kpm_ldiv_(ze, Pe, r)
+        assert relerr(ze, zo) <= 1e-11, (key, val)
+    em._call("elph_set_tuning", 1, 0)
+    em._call("elph_set_tuning", 4, 1)
     g = rng.normal(size=om.Ndim)
     b = np.zeros(om.Ndim)
     om.mulMT(b, g)
