@@ -240,6 +240,8 @@ void build(elph_handle* h, const elph_config* c) {
     h->d_partial = zeros(h->partial_cap);
     h->d_ticket = elph_dalloc<unsigned int>(1);
     ELPH_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+    h->d_bar = elph_dalloc<unsigned int>(1);
+    ELPH_CUDA(cudaMemset(h->d_bar, 0, sizeof(unsigned int)));
     h->d_cg = elph_dalloc<CgScalars>(1);
     ELPH_CUDA(cudaMemset(h->d_cg, 0, sizeof(CgScalars)));
     ELPH_CUDA(cudaMallocHost(&h->h_cg, sizeof(CgScalars)));
@@ -300,7 +302,7 @@ void destroy(elph_handle* h) {
     void* ptrs[] = {h->d_bonds, h->d_goff, h->d_cs, h->d_lam, h->d_lam2, h->d_mu, h->d_omega, h->d_omega4, h->d_x, h->d_D,
                     h->d_Q, h->d_Mass, h->d_t, h->d_alpha, h->d_alpha2, h->d_ph_col, h->d_col_ph, h->d_col_bond,
                     h->d_primary_ph, h->d_grp_start, h->d_grp_members, h->d_tprime, h->d_va, h->d_vb, h->d_vc, h->d_b,
-                    h->d_res, h->d_r, h->d_p[0], h->d_p[1], h->d_z, h->d_partial, h->d_ticket, h->d_cg, h->d_scal,
+                    h->d_res, h->d_r, h->d_p[0], h->d_p[1], h->d_z, h->d_partial, h->d_ticket, h->d_bar, h->d_cg, h->d_scal,
                     h->d_dSdx, h->d_dSdx2, h->d_eta, h->d_dx, h->d_tmp, h->d_g, h->d_g2, h->d_Minv, h->d_nu2,
                     h->d_twiddle, h->d_theta, h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stage[3]};
     for (void* p : ptrs)
@@ -1022,6 +1024,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 2: h->sq_py = value; h->kpm_version++; break;
             case 3: h->use_graphs = (value != 0); break;
             case 4: h->kpm_split = (value != 0); h->kpm_version++; break;
+            case 5: h->use_persistent = (value != 0); break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }
         return ELPH_OK;

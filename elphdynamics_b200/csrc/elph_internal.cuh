@@ -136,6 +136,8 @@ struct elph_handle {
     int64_t kpm_version = 0;   // bumped whenever the KPM kernels' launch parameters change
     bool use_graphs = true;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
+    bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
+    unsigned int* d_bar = nullptr;  // grid-barrier arrival counter of the persistent CG
     bool own_stream = false;
     std::set<const void*> smem_enabled;  // kernels that already have the opt-in shared-memory attribute
     int device = 0;
@@ -283,6 +285,7 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
                     int64_t* iters, double* eps);
 void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool use_precond, double tol_power,
                        elph_solve_info* info);
+bool elph_cg_persistent(elph_handle* h, double* x_dev);   // cg_persistent.cu
 // reductions: out[0] = sum a*b  (deterministic two-stage); blocking read helpers
 void elph_dot_async(elph_handle* h, const double* a, const double* b, int64_t n, double* d_out);
 void elph_diffnorm2_async(elph_handle* h, const double* a, const double* b, int64_t n, double* d_out2);  // |a-b|^2, |b|^2

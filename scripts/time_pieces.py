@@ -41,6 +41,36 @@ print("kpm orders: total", info.total_order, "max", info.max_order)
 print(f"MTM                : {timeit(lambda: lib.elph_dev_mulMTM(h, v.data_ptr(), y.data_ptr())):8.2f} us")
 print(f"KPM apply (2 FFT + poly): {timeit(lambda: lib.elph_dev_kpm_apply(h, v.data_ptr(), y.data_ptr())):8.2f} us")
 print(f"fourier_accelerate (2 FFT in one kernel): {timeit(lambda: lib.elph_dev_fourier_accelerate(h, v.data_ptr(), y.data_ptr(), 1.0, 0)):8.2f} us")
+import ctypes as C
+import time
+g = rng.normal(size=n)
+bh = np.zeros(n)
+E.mulMT_(bh, em, g)
+b_dev = torch.from_numpy(np.ascontiguousarray(bh.reshape(om.N, om.L).T)).reshape(-1).cuda()
+x_dev = torch.zeros(n, dtype=torch.float64, device="cuda")
+it, eps = C.c_int64(), C.c_double()
+for label, keys in (("persistent", {5: 1}), ("graph", {5: 0, 3: 1}), ("launches", {5: 0, 3: 0})):
+    for k, val in keys.items():
+        lib.elph_set_tuning(h, k, val)
+    for rep in range(3):
+        x_dev.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lib.elph_dev_cg_solve(h, b_dev.data_ptr(), x_dev.data_ptr(), 0, 0.0, 0, C.byref(it), C.byref(eps))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    print(f"CG {label:10s}: {it.value} iters, {dt*1e3:.3f} ms, {dt/it.value*1e6:.2f} us/iter")
+lib.elph_set_tuning(h, 5, 1)
+lib.elph_set_tuning(h, 3, 1)
+for label, usep in (("PCG", 1),):
+    for rep in range(3):
+        x_dev.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lib.elph_dev_cg_solve(h, b_dev.data_ptr(), x_dev.data_ptr(), usep, 0.0, 0, C.byref(it), C.byref(eps))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    print(f"{label}: {it.value} iters, {dt*1e3:.3f} ms, {dt/it.value*1e6:.2f} us/iter")
 for py in (2, 4, 8):
     lib.elph_set_tuning(h, 2, py)
     print(f"KPM apply py={py}: {timeit(lambda: lib.elph_dev_kpm_apply(h, v.data_ptr(), y.data_ptr())):8.2f} us")

@@ -80,6 +80,21 @@ def test_B_cg_iterations_and_residual(config_B):
     true_res = np.linalg.norm(chk - b) / np.linalg.norm(b)
     assert true_res <= np.sqrt(om.tol) and abs(true_res - res_e) <= 1e-8
     assert relerr(xe, xc) <= 1e-3
+    # the three execution strategies of the same algorithm: persistent cooperative kernel (default), CUDA-graph
+    # replay of two-kernel iterations, plain launches -- same iteration count (+-1) and the same solution
+    for persistent, graphs in ((0, 1), (0, 0)):
+        em._call("elph_set_tuning", 5, persistent)
+        em._call("elph_set_tuning", 3, graphs)
+        x2 = np.zeros(om.Ndim)
+        it2, res2, flag2 = E.ldiv_(x2, em, b)
+        assert flag2 == 0 and abs(it2 - it_e) <= 1, (persistent, graphs, it2, it_e)
+        assert relerr(x2, xe) <= 1e-6
+    em._call("elph_set_tuning", 5, 1)
+    em._call("elph_set_tuning", 3, 1)
+    # run-to-run determinism of the persistent kernel (fixed-order reductions)
+    x3 = np.zeros(om.Ndim)
+    E.ldiv_(x3, em, b)
+    assert np.array_equal(x3, xe)
 
 
 def test_B_kpm_pcg_and_force(config_B):
