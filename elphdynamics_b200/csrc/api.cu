@@ -236,7 +236,7 @@ void build(elph_handle* h, const elph_config* c) {
     h->d_p[0] = zeros(h->Ndim);
     h->d_p[1] = zeros(h->Ndim);
     h->d_z = zeros(h->Ndim);
-    h->partial_cap = std::max(4 * h->sm_count, 2 * h->L + 8);
+    h->partial_cap = std::max(std::max(4 * h->sm_count, 2 * h->L + 8), h->N / 4 + 8);
     h->d_partial = zeros(h->partial_cap);
     h->d_ticket = elph_dalloc<unsigned int>(1);
     ELPH_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
@@ -1025,6 +1025,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 3: h->use_graphs = (value != 0); break;
             case 4: h->kpm_split = (value != 0); h->kpm_version++; break;
             case 5: h->use_persistent = (value != 0); break;
+            case 6: h->pcg_fuse = (value != 0); h->kpm_version++; break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }
         return ELPH_OK;

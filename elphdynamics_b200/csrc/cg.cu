@@ -274,6 +274,13 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
             m.cg_S = h->d_cg;
             m.cg_ticket = h->d_ticket;
             elph_launch_matvec(h, MODE_MTM, m);
+            if (precond && h->pcg_fuse) {
+                // 3 more kernels: [x/r update + stop rule + FFT(r)] [Chebyshev recurrences] [iFFT -> z, r.z -> beta]
+                KpmCgFuse f{x_dev, h->d_r, h->d_p[parity], h->d_z};
+                elph_kpm_apply_dev_cg(h, h->d_r, zprec, &f);
+                parity ^= 1;
+                continue;
+            }
             cg_xr_kernel<<<vb, kT, 0, st>>>(x_dev, h->d_r, h->d_p[parity], h->d_z, n, h->d_partial, h->d_cg, h->d_ticket,
                                             precond ? 1 : 0);
             ELPH_CUDA(cudaGetLastError());

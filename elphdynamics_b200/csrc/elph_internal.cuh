@@ -137,6 +137,7 @@ struct elph_handle {
     bool use_graphs = true;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
+    bool pcg_fuse = true;        // preconditioned CG: vector updates fused into the FFT kernels of the KPM apply
     unsigned int* d_bar = nullptr;  // grid-barrier arrival counter of the persistent CG
     bool own_stream = false;
     std::set<const void*> smem_enabled;  // kernels that already have the opt-in shared-memory attribute
@@ -300,6 +301,15 @@ void elph_fourier_accelerate_dev(elph_handle* h, const double* vin, double* vout
 void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2);
 void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info);
 void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout);
+struct KpmCgFuse {   // vectors of the running preconditioned CG iteration (see fft.cu: CgFuse)
+    double* x;
+    double* r;
+    const double* p;
+    const double* ap;
+};
+void elph_kpm_apply_dev_cg(elph_handle* h, const double* vin, double* vout, const KpmCgFuse* cgf);
+void elph_tau_to_omega_dev_cg(elph_handle* h, double* x, double* r, const double* p, const double* ap, cplx* vout);
+void elph_omega_to_tau_dev_cg(elph_handle* h, const cplx* vin, double* z, double* r);
 void elph_kpm_free(elph_handle* h);
 bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, const int* skip);
 void elph_tau_to_omega_dev_skip(elph_handle* h, const double* vin, cplx* vout, const int* skip);

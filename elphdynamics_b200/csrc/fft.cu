@@ -155,13 +155,61 @@ __device__ cplx* fft_smem(cplx* x, cplx* y, const FftPlan& plan, const cplx* __r
 // mode 0: tau_to_omega  (real in, complex out):  out = FFT(theta .* in)
 // mode 1: omega_to_tau  (complex in, real out):  out = Re(conj(theta) .* iFFT(in))
 // mode 2: fourier accelerate (real in, real out): out = Re(iFFT(diag^power .* FFT(in)))
+// CG fusion (preconditioned iteration, cg.cu): with F.S set, mode 0 first performs x += alpha p, r -= alpha Ap on the
+// elements it loads (every element belongs to exactly one thread), transforms the NEW r, and the last CTA applies the
+// stop rule; mode 1 accumulates r.z for the vector z it produces and the last CTA publishes beta.
+struct CgFuse {
+    double* x;
+    double* r;
+    const double* p;
+    const double* ap;
+    double* partial;
+    CgScalars* S;
+    unsigned int* ticket;
+};
+
+__device__ __forceinline__ double fft_block_sum(double x, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = x;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    return t;
+}
+
+// per-CTA partial -> last CTA folds all partials in index order; returns true (+ the sum on thread 0) in the last CTA
+__device__ __forceinline__ bool fft_last_block_sum(double acc, const CgFuse& F, double* red, bool* flag, double* total) {
+    const double t = fft_block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        F.partial[blockIdx.x] = t;
+        __threadfence();
+        const unsigned int n = atomicAdd(F.ticket, 1u);
+        *flag = (n == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*flag) return false;
+    __threadfence();
+    double s = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += ((const volatile double*)F.partial)[k];
+    *total = fft_block_sum(s, red);
+    return true;
+}
+
 template <int SB>
 __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* __restrict__ rin, const cplx* __restrict__ cin,
                                                  double* __restrict__ rout, cplx* __restrict__ cout, FftPlan plan, int N,
                                                  const cplx* __restrict__ tw_g, const cplx* __restrict__ theta,
-                                                 const double* __restrict__ diag, double power, const int* skip) {
+                                                 const double* __restrict__ diag, double power, const int* skip, CgFuse F) {
     extern __shared__ __align__(16) double smem_raw[];
+    __shared__ double red[32];
+    __shared__ bool lastflag;
     if (skip && *skip) return;
+    double fuse_acc = 0.0;
+    const double alpha = (F.S && mode == 0) ? F.S->alpha : 0.0;
     const int L = plan.L;
     cplx* b0 = reinterpret_cast<cplx*>(smem_raw);
     cplx* b1 = b0 + (size_t)L * SB;
@@ -178,7 +226,16 @@ __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* __restr
         cplx v = make_double2(0.0, 0.0);
         if (ok) {
             if (mode == 0) {
-                const double xr = rin[(size_t)t * N + gsite];
+                double xr;
+                if (F.S) {   // fused x += alpha p ; r -= alpha Ap ; |r|^2   (src/IterativeSolvers.jl:205-211)
+                    const size_t e = (size_t)t * N + gsite;
+                    F.x[e] = fma(alpha, F.p[e], F.x[e]);
+                    xr = fma(-alpha, F.ap[e], F.r[e]);
+                    F.r[e] = xr;
+                    fuse_acc = fma(xr, xr, fuse_acc);
+                } else {
+                    xr = rin[(size_t)t * N + gsite];
+                }
                 const cplx th = theta[t];
                 v = make_double2(th.x * xr, th.y * xr);
             } else if (mode == 1) {
@@ -194,6 +251,25 @@ __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* __restr
     if (mode == 0) {
         for (int t = slot; t < L; t += nslots)
             if (ok) cout[(size_t)t * N + gsite] = res[(size_t)t * SB + site];
+        if (F.S) {
+            double rr;
+            if (fft_last_block_sum(fuse_acc, F, red, &lastflag, &rr) && threadIdx.x == 0) {
+                // stop rule, preconditioned variant (src/IterativeSolvers.jl:208-219): beta is set later from r.z
+                CgScalars* S = F.S;
+                const long long j = S->iter + 1;
+                const double eps = sqrt(rr) / S->normb;
+                const double lg = log(2.0 * S->eps0 / eps);
+                const double q = 2.0 * (double)j / lg;
+                const double kap = q * q;
+                double kmin = S->kappa_min;
+                if (kap > kmin) kmin = kap;
+                S->kappa_min = kmin;
+                S->eps = eps;
+                S->iter = j;
+                if (eps < S->tol || kmin > S->kappa_max || j >= S->maxiter) S->done = 1;
+                *F.ticket = 0u;
+            }
+        }
         return;
     }
     if (mode == 1) {
@@ -201,7 +277,19 @@ __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* __restr
             if (ok) {
                 const cplx v = res[(size_t)t * SB + site];
                 const cplx th = theta[t];  // conj(theta) * v, real part
-                rout[(size_t)t * N + gsite] = (th.x * v.x + th.y * v.y) * invL;
+                const double z = (th.x * v.x + th.y * v.y) * invL;
+                rout[(size_t)t * N + gsite] = z;
+                if (F.S) fuse_acc = fma(F.r[(size_t)t * N + gsite], z, fuse_acc);
+            }
+        }
+        if (F.S) {
+            double rz;
+            if (fft_last_block_sum(fuse_acc, F, red, &lastflag, &rz) && threadIdx.x == 0) {
+                // beta = (r.z)_new / (r.z)_old   (src/IterativeSolvers.jl:221-227)
+                CgScalars* S = F.S;
+                S->beta = (S->iter == 0) ? 0.0 : rz / S->rdotz;
+                S->rdotz = rz;
+                *F.ticket = 0u;
             }
         }
         return;
@@ -233,6 +321,9 @@ FftPlan make_plan(const elph_handle* h) {
     return p;
 }
 
+// CG fusion request for the next launch (set and cleared by the *_cg entry points below; one caller thread per handle)
+thread_local CgFuse g_fuse = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
 template <int SB>
 size_t fft_smem_bytes(int L) { return (2ull * L * SB + L) * sizeof(cplx); }
 
@@ -244,7 +335,7 @@ void launch_fft(elph_handle* h, int mode, int ncols, const double* rin, const cp
     elph_enable_smem(h, fft_kernel<SB>);
     const int blocks = (ncols + SB - 1) / SB;
     fft_kernel<SB><<<blocks, kT, smem, h->stream>>>(mode, rin, cin, rout, cout, make_plan(h), ncols, h->d_twiddle, h->d_theta,
-                                                     diag, power, skip);
+                                                     diag, power, skip, g_fuse);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }
@@ -295,6 +386,30 @@ void elph_tau_to_omega_dev_skip(elph_handle* h, const double* vin, cplx* vout, c
 }
 void elph_omega_to_tau_dev_skip(elph_handle* h, const cplx* vin, double* vout, const int* skip) {
     dispatch_fft(h, 1, h->N, nullptr, vin, vout, nullptr, nullptr, 0.0, skip);
+}
+
+// preconditioned CG, fused variants (see CgFuse): forward = x/r update + stop rule + FFT(r); inverse = z + r.z + beta
+void elph_tau_to_omega_dev_cg(elph_handle* h, double* x, double* r, const double* p, const double* ap, cplx* vout) {
+    const int blocks_max = (h->N + 3) / 4;
+    ELPH_REQUIRE(blocks_max <= h->partial_cap, ELPH_ERR_INVALID, "partial buffer too small for the fused FFT");
+    g_fuse = CgFuse{x, r, p, ap, h->d_partial, h->d_cg, h->d_ticket};
+    try {
+        dispatch_fft(h, 0, h->N, r, nullptr, nullptr, vout, nullptr, 0.0, &h->d_cg->done);
+    } catch (...) {
+        g_fuse = CgFuse{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        throw;
+    }
+    g_fuse = CgFuse{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+}
+void elph_omega_to_tau_dev_cg(elph_handle* h, const cplx* vin, double* z, double* r) {
+    g_fuse = CgFuse{nullptr, r, nullptr, nullptr, h->d_partial, h->d_cg, h->d_ticket};
+    try {
+        dispatch_fft(h, 1, h->N, nullptr, vin, z, nullptr, nullptr, 0.0, &h->d_cg->done);
+    } catch (...) {
+        g_fuse = CgFuse{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        throw;
+    }
+    g_fuse = CgFuse{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 }
 
 void elph_tau_to_omega_dev(elph_handle* h, const double* vin, cplx* vout) {

@@ -480,9 +480,15 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
     }
 }
 
-void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) {
+void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) { elph_kpm_apply_dev_cg(h, vin, vout, nullptr); }
+
+// cgf != nullptr (inside the preconditioned CG loop, preconditioner active): the forward FFT kernel first applies
+// x += alpha p, r -= alpha Ap and the stop rule, and the inverse FFT kernel accumulates r.z -> beta (fft.cu);
+// vin must then be the residual vector r.
+void elph_kpm_apply_dev_cg(elph_handle* h, const double* vin, double* vout, const KpmCgFuse* cgf) {
     KpmState& K = h->kpm;
     ELPH_REQUIRE(K.configured && K.ever_setup, ELPH_ERR_STATE, "elph_kpm_apply before elph_kpm_setup");
+    ELPH_REQUIRE(!cgf || K.active, ELPH_ERR_STATE, "fused KPM apply needs an active preconditioner");
     if (!K.active) {  // identity (:475-478)
         if (vout != vin) ELPH_CUDA(cudaMemcpyAsync(vout, vin, h->Ndim * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         return;
@@ -493,7 +499,12 @@ void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) {
     // the recurrence reads nu_in and writes nu_out (the reference's v1 / v2)
     cplx* nu_in = K.d_nu;
     cplx* nu_out = h->d_nu2;
-    elph_tau_to_omega_dev_skip(h, vin, nu_in, skip);
+    auto inverse_fft = [&]() {
+        if (cgf) elph_omega_to_tau_dev_cg(h, nu_out, vout, cgf->r);
+        else elph_omega_to_tau_dev_skip(h, nu_out, vout, skip);
+    };
+    if (cgf) elph_tau_to_omega_dev_cg(h, cgf->x, cgf->r, cgf->p, cgf->ap, nu_in);
+    else elph_tau_to_omega_dev_skip(h, vin, nu_in, skip);
     KpmParams P;
     P.in = nu_in;
     P.out = nu_out;
@@ -512,7 +523,7 @@ void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) {
     P.inv_mag = 1.0 / K.lam_mag;
     P.avg_over_mag = K.lam_avg / K.lam_mag;
     if (elph_launch_kpm_square(h, nu_in, nu_out, skip)) {   // register/shuffle kernel (kpm_square.cu)
-        elph_omega_to_tau_dev_skip(h, nu_out, vout, skip);
+        inverse_fft();
         return;
     }
     int threads = 256;
@@ -524,5 +535,5 @@ void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) {
     else if (spt <= 8) launch_apply<8>(h, P, threads);
     else if (spt <= 16) launch_apply<16>(h, P, threads);
     else ELPH_REQUIRE(false, ELPH_ERR_UNSUPPORTED, "Nsites too large for the KPM kernel");
-    elph_omega_to_tau_dev_skip(h, nu_out, vout, skip);
+    inverse_fft();
 }

@@ -132,6 +132,14 @@ def test_B_kpm_pcg_and_force(config_B):
     it_o, _, fo = ldiv(xo, om, b, cg, Po)
     it_e, res_e, fe = E.ldiv_(xe, em, b, Pe)
     assert fo == fe == 0 and abs(it_o - it_e) <= 2, (it_o, it_e)
+    # same preconditioned solve without the FFT-fused vector updates and without CUDA graphs: identical iteration
+    # count and (to rounding) identical solution
+    for key in (6, 3):
+        em._call("elph_set_tuning", key, 0)
+        x2 = np.zeros(om.Ndim)
+        it2, _, f2 = E.ldiv_(x2, em, b, Pe)
+        em._call("elph_set_tuning", key, 1)
+        assert f2 == 0 and it2 == it_e and relerr(x2, xe) <= 1e-9, key
     # force kernel at full size (no solve involved): <dM/dx> with the oracle's vectors
     do, de = np.zeros(om.Ndof), np.zeros(om.Ndof)
     om.muldMdx(do, g, xo)
@@ -160,6 +168,38 @@ def test_E_products_64x64_L400():
         y2 = np.zeros(om.Ndim)
         E.mulMTM_(y2, em, v)
         assert relerr(y2, yc) <= 1e-12
+    em.close()
+
+
+@pytest.mark.parametrize("geom,Ls,dtau", [("honeycomb", 32, 0.1), ("triangular", 45, 0.05), ("triangular", 46, 0.05)],
+                         ids=["honeycomb32", "triangular45-ragged", "triangular46"])
+def test_D_hmc_lattices_at_2k_sites(geom, Ls, dtau):
+    """Config D: the HMC examples scaled to ~2k sites (honeycomb L=32: 3 colours x 1024; triangular L=45: 8 ragged
+    colours 1012..12; L=46: 6 x 1058), beta = 2 as shipped: products, adjointness, the HMC force pieces."""
+    import elphdynamics_b200 as E
+    from elphdynamics_b200 import hmc as ehmc
+    from oracle import hmc as ohmc
+    om, rng = oracle_holstein(geom, Ls, 2.0, dtau, mu=0.0, seed=3, eps=0.3)
+    em = engine_holstein_like(om)
+    assert em.group_sizes.tolist() == np.diff(om.group_offsets).tolist()
+    u, v = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    yo, ye = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    for fo, fe in ((om.mulM, E.mulM_), (om.mulMT, E.mulMT_), (om.mulMTM, E.mulMTM_)):
+        fo(yo, v)
+        fe(ye, em, v)
+        assert relerr(ye, yo) <= 1e-12, fe.__name__
+    ho = ohmc.HybridMonteCarlo(om, 0.01, 1.0, 0.0, 10)
+    he = ehmc.HybridMonteCarlo(em, 0.01, 1.0, 0.0, 10)
+    Rp, Rm = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    So = ohmc.refresh_phi(ho, om, Rp, Rm)
+    Se = ehmc.refresh_phi_(he, em, Rp, Rm)
+    assert abs(Se - So) <= 1e-12 * abs(So)
+    assert relerr(he.get("phi_plus"), ho.phip) <= 1e-12
+    # force pieces with the oracle's vectors in place of the solves (no CG needed at this size)
+    do, de = np.zeros(om.Ndof), np.zeros(om.Ndof)
+    om.muldMdx(do, u, v)
+    E.muldMdx_(de, u, em, v)
+    assert relerr(de, do) <= 1e-9
     em.close()
 
 
