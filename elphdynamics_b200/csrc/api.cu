@@ -929,6 +929,24 @@ int32_t elph_dev_shard_muldMdx(elph_handle* h, const double* u_own, const double
     ELPH_CATCH(h)
 }
 
+int32_t elph_dev_shard_dSbdx(elph_handle* h, double* dSbdx_own, const double* x_own, int32_t shifted) {
+    ENTER(h) {
+        ELPH_REQUIRE(dSbdx_own && x_own, ELPH_ERR_INVALID, "null device pointer");
+        elph_dSbdx_open_dev(h, dSbdx_own, x_own, shifted != 0);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_fourier_accelerate_cols(elph_handle* h, const double* vin_dev, double* vout_dev, int64_t ncols,
+                                         const double* diag_dev, double power) {
+    ENTER(h) {
+        elph_fourier_accelerate_cols_dev(h, vin_dev, vout_dev, (int)ncols, diag_dev, power);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
 int32_t elph_dev_update_model(elph_handle* h) {
     ENTER(h) {
         elph_launch_update_model(h);

@@ -319,6 +319,8 @@ void elph_omega_to_tau_dev_skip(elph_handle* h, const cplx* vin, double* vout, c
 void elph_muldMdx_dev(elph_handle* h, const double* u, const double* v, double* out, double scale, bool add_dSb,
                       bool shifted);
 void elph_dSbdx_dev(elph_handle* h, double* dSbdx, bool shifted);
+void elph_dSbdx_open_dev(elph_handle* h, double* dSbdx, const double* x_own, bool shifted);
+void elph_fourier_accelerate_cols_dev(elph_handle* h, const double* vin, double* vout, int ncols, const double* diag, double power);
 void elph_Sb_dev(elph_handle* h, bool shifted, double* host_out);
 
 // hmc.cu

@@ -420,6 +420,13 @@ void elph_omega_to_tau_dev(elph_handle* h, const cplx* vin, double* vout) {
     dispatch_fft(h, 1, h->N, nullptr, vin, vout, nullptr, nullptr, 0.0);
 }
 
+// Fourier acceleration of `ncols` columns ([k][col] layout) with an explicit diagonal: used by the tau-sharded driver
+// after the all-to-all transpose, when a rank holds ALL time slices of a subset of the sites.
+void elph_fourier_accelerate_cols_dev(elph_handle* h, const double* vin, double* vout, int ncols, const double* diag, double power) {
+    ELPH_REQUIRE(vin && vout && diag && ncols >= 1, ELPH_ERR_INVALID, "bad arguments");
+    dispatch_fft(h, 2, ncols, vin, nullptr, vout, nullptr, diag, power);
+}
+
 void elph_fourier_accelerate_dev(elph_handle* h, const double* vin, double* vout, double power, bool use_mass) {
     const double* diag = use_mass ? h->d_Mass : h->d_Q;
     ELPH_REQUIRE(use_mass ? h->have_M : h->have_Q, ELPH_ERR_STATE, "fourier acceleration diagonal (fa_Q / fa_M) was not provided");

@@ -103,6 +103,23 @@ __global__ void dSb_kernel(double* __restrict__ dS, const double* __restrict__ x
     }
 }
 
+// tau-sharded slab: x points at the first own slice of a halo'd field ([x(a-1)][own ...][x(b)]); the bosonic action is
+// periodic in tau (no sign), so the ring closure is an ordinary halo
+__global__ void dSb_open_kernel(double* __restrict__ dS, const double* __restrict__ x, const double* __restrict__ omega,
+                                const double* __restrict__ omega4, const double* __restrict__ lam, int ncols, int L, double dtau,
+                                int shifted_holstein) {
+    const long long n = (long long)ncols * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % ncols);
+        const double w = omega[i], w4 = omega4[i];
+        const double xt = x[idx];
+        double d = dtau * w * w * xt - (shifted_holstein ? dtau * lam[i] : 0.0);
+        d += dtau * 4.0 * w4 * xt * xt * xt;
+        d -= (x[idx + ncols] + x[idx - ncols] - 2.0 * xt) / dtau;
+        dS[idx] += d;
+    }
+}
+
 // Sb partial sums (per CTA), folded on the host in index order
 __global__ void __launch_bounds__(kT) Sb_kernel(const double* __restrict__ x, const double* __restrict__ omega,
                                                 const double* __restrict__ omega4, const double* __restrict__ lam,
@@ -285,6 +302,14 @@ void elph_dSbdx_dev(elph_handle* h, double* dSbdx, bool shifted) {
     const int blocks = (int)std::min<int64_t>((h->Ndof + kT - 1) / kT, 8LL * h->sm_count);
     const int sh = (shifted && h->model == ELPH_MODEL_HOLSTEIN) ? 1 : 0;
     dSb_kernel<<<blocks, kT, 0, h->stream>>>(dSbdx, h->d_x, h->d_omega, h->d_omega4, h->d_lam, h->Nph, h->L, h->dtau, sh);
+    ELPH_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+void elph_dSbdx_open_dev(elph_handle* h, double* dSbdx, const double* x_own, bool shifted) {
+    const int blocks = (int)std::min<int64_t>((h->Ndof + kT - 1) / kT, 8LL * h->sm_count);
+    const int sh = (shifted && h->model == ELPH_MODEL_HOLSTEIN) ? 1 : 0;
+    dSb_open_kernel<<<blocks, kT, 0, h->stream>>>(dSbdx, x_own, h->d_omega, h->d_omega4, h->d_lam, h->Nph, h->L, h->dtau, sh);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }

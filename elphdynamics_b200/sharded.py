@@ -67,6 +67,15 @@ class RingComm:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def all_to_all(self, recv, send, recv_counts, send_counts):
+        """All-to-all of 1-D buffers with per-peer element counts (the tau <-> site transposes of the tau-FFT)."""
+        import torch.distributed as dist
+        if self.world == 1:
+            recv.copy_(send)
+            return
+        dist.all_to_all_single(recv, send, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts),
+                               group=self.group)
+
 
 class CudaSlabBackend:
     """Local slab arithmetic on the GPU through libelph_b200.so (device-pointer entry points)."""
@@ -123,6 +132,42 @@ class CudaSlabBackend:
     def dot(self, a, b):
         self._check(self.lib.elph_dev_dot(self.h, self.own_ptr(a), self.own_ptr(b), self.lloc * self.N, self.scal.data_ptr()))
         return self.scal[:1].clone()
+
+    # ---- pieces needed by the sharded Langevin step -------------------------------------------------------------
+    def _wrap(self, ptr, shape):
+        torch = self.torch
+        n = int(np.prod(shape))
+        iface = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        class _W:
+            __cuda_array_interface__ = iface
+        return torch.as_tensor(_W(), device="cuda").view(*shape)
+
+    def x_tensor(self):
+        """The handle's phonon field slab [Lloc][N] wrapped as a CUDA tensor (no copy)."""
+        p = C.c_void_p()
+        self._check(self.lib.elph_dev_ptr_x(self.h, C.byref(p)))
+        return self._wrap(p.value, (self.lloc, self.N))
+
+    def dSbdx(self, dS, xh, shifted=True):
+        self._check(self.lib.elph_dev_shard_dSbdx(self.h, self.own_ptr(dS), self.own_ptr(xh), 1 if shifted else 0))
+
+    def make_fft_plan(self, Lglob: int):
+        """A 1-site handle whose only job is to own the tau-FFT plan of the GLOBAL time extent."""
+        import elphdynamics_b200 as E
+        aux = E.HolsteinModel(E.Lattice(E.UnitCell(1, 1), 1), Lglob * self.model.dtau, self.model.dtau)
+        assert aux.Ltau == Lglob
+        aux.initialize_model_()
+        aux.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self._fft_aux = aux
+
+    def fa_cols(self, vin, vout, diag, power):
+        """fourier_accelerate! on a [L][ncols] block (all time slices of a subset of the sites)."""
+        aux = self._fft_aux
+        st = aux._lib.elph_dev_fourier_accelerate_cols(aux.handle, vin.data_ptr(), vout.data_ptr(), vin.shape[1],
+                                                       diag.data_ptr(), float(power))
+        if st != 0:
+            raise RuntimeError(aux._lib.elph_last_error(aux.handle).decode())
 
 
 class ShardedOperator:
@@ -188,3 +233,105 @@ class ShardedOperator:
             rdotr = nr
             be.lincomb(p, 1.0, r, beta, p)
         return maxiter, eps
+
+
+class ShardedLangevin:
+    """Langevin updates of a tau-sharded Holstein lattice (unpreconditioned CG), reference:
+    src/LangevinDynamics.jl:81-119 (Euler), :162-225 (Runge-Kutta), :334-384 (forces).
+
+    Collectives per force evaluation: one halo exchange per product (CG iterations + M^T g + the force's v(tau-1)),
+    two scalar all-reduces per CG iteration, one x halo for the bosonic gradient; per Fourier acceleration: an
+    all-to-all pair (tau-sharded -> site-sharded, local tau-FFT of all slices of Nsites/P sites, and back).
+    """
+
+    def __init__(self, op: ShardedOperator, N: int, Lglob: int, tau0: int, Q_site_block, dt: float):
+        """``Q_site_block``: the acceleration diagonal of this rank's site block, [k][site_local] (Lglob x Nloc)."""
+        self.op, self.be, self.comm = op, op.be, op.comm
+        self.N, self.L, self.tau0, self.lloc = N, Lglob, tau0, op.lloc
+        self.dt = float(dt)
+        w, r = self.comm.world, self.comm.rank
+        self.site_spans = [slab_bounds(N, w, q) for q in range(w)]
+        self.tau_spans = [slab_bounds(Lglob, w, q) for q in range(w)]
+        self.s0, self.nloc = self.site_spans[r]
+        self.Q = Q_site_block
+        self.xh = self.be.empty()                      # halo'd master copy of the phonon field slab
+        self.last_iters = 0
+
+    # ---- Fourier acceleration through the all-to-all transposes ---------------------------------------------------
+    def fourier_accelerate(self, v, power):
+        """v: halo'd tensor; returns a new halo'd tensor with Re iFFT(Q^power FFT v) on the own slices."""
+        torch = self.be.torch
+        lloc, nloc, L = self.lloc, self.nloc, self.L
+        own = v[1:lloc + 1]
+        send = torch.cat([own[:, s:s + n].reshape(-1) for (s, n) in self.site_spans])
+        send_counts = [lloc * n for (_, n) in self.site_spans]
+        recv_counts = [lt * nloc for (_, lt) in self.tau_spans]
+        recv = torch.empty(L * nloc, dtype=own.dtype, device=own.device)
+        self.comm.all_to_all(recv, send, recv_counts, send_counts)
+        cols = recv.view(L, nloc)                       # chunks arrive in rank = tau order: [tau][site_local]
+        out_cols = torch.empty_like(cols)
+        self.be.fa_cols(cols, out_cols, self.Q, power)
+        back = torch.empty(lloc * self.N, dtype=own.dtype, device=own.device)
+        self.comm.all_to_all(back, out_cols.reshape(-1), send_counts, recv_counts)
+        out = self.be.empty()
+        off = 0
+        for (s, n) in self.site_spans:
+            out[1:lloc + 1, s:s + n] = back[off:off + lloc * n].view(lloc, n)
+            off += lloc * n
+        return out
+
+    # ---- field / forces -------------------------------------------------------------------------------------------
+    def set_x(self, x_slab):
+        """x_slab: (Lloc, N) tensor/array in the engine layout."""
+        self.xh[1:self.lloc + 1] = self.be.torch.as_tensor(x_slab, dtype=self.xh.dtype).to(self.xh.device)
+        self._push_x()
+
+    def _push_x(self):
+        self.be.x_tensor().copy_(self.xh[1:self.lloc + 1])
+        self.op.update_model()
+
+    def calc_dSdx(self, g):
+        """dS/dx = -2 g^T (dM/dx) M^-1 g + dSb/dx (shifted), src/LangevinDynamics.jl:334-384."""
+        be, op = self.be, self.op
+        b, x, dS = be.empty(), be.empty(), be.empty()
+        op.mulMT(b, g)
+        iters, eps = op.solve_cg(x, b)
+        self.last_iters = iters
+        self.comm.exchange(x, self.lloc, lo=True, hi=False)     # the force needs (M^-1 g)(tau-1)
+        be.muldMdx(g, x, dS, -2.0)
+        self.comm.exchange(self.xh, self.lloc)                  # bosonic gradient couples x(tau +- 1), periodic
+        be.dSbdx(dS, self.xh, True)
+        return dS
+
+    def evolve_euler(self, eta, g):
+        """src/LangevinDynamics.jl:81-119; eta, g: halo'd tensors holding this rank's slab of the injected noise."""
+        be = self.be
+        self._push_x()
+        dS = self.calc_dSdx(g)
+        QdS = self.fourier_accelerate(dS, 1.0)
+        sqQeta = self.fourier_accelerate(eta, 0.5)
+        dx = be.empty()
+        be.lincomb(dx, math.sqrt(2.0 * self.dt), sqQeta, -self.dt, QdS)
+        be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
+        self._push_x()
+        return self.last_iters
+
+    def evolve_rk(self, eta, g1, g2):
+        """src/LangevinDynamics.jl:162-225."""
+        be = self.be
+        self._push_x()
+        dS1 = self.calc_dSdx(g1)
+        dx = be.empty()
+        be.lincomb(dx, math.sqrt(2.0 * self.dt), eta, -self.dt, dS1)
+        be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
+        self._push_x()
+        dS2 = self.calc_dSdx(g2)
+        be.lincomb(self.xh, 1.0, self.xh, -1.0, dx)
+        self._push_x()
+        be.lincomb(dS1, 0.5, dS2, 0.5, dS1)
+        QdS = self.fourier_accelerate(dS1, 1.0)
+        sqQeta = self.fourier_accelerate(eta, 0.5)
+        be.lincomb(dx, math.sqrt(2.0 * self.dt), sqQeta, -self.dt, QdS)
+        be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
+        self._push_x()
+        return self.last_iters

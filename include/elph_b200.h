@@ -276,6 +276,13 @@ int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob);
 int32_t elph_dev_shard_matvec(elph_handle* h, int32_t mode, const double* v_own, double* y_own);
 int32_t elph_dev_shard_muldMdx(elph_handle* h, const double* u_own, const double* v_own, double* out, double scale);
 int32_t elph_dev_update_model(elph_handle* h);
+/* calc_dSbdx! on a slab: dSbdx_own += dSb/dx, x_own = first own slice of a halo'd copy of the field (periodic in tau) */
+int32_t elph_dev_shard_dSbdx(elph_handle* h, double* dSbdx_own, const double* x_own, int32_t shifted);
+/* fourier_accelerate! for `ncols` columns in [k][col] layout with an explicit diagonal (same layout): after the
+ * all-to-all transpose of the tau-sharded driver a rank holds all Ltau slices of a subset of the sites.  The handle's
+ * Ltau must be the GLOBAL time extent (the driver keeps a 1-site handle just for this plan). */
+int32_t elph_dev_fourier_accelerate_cols(elph_handle* h, const double* vin_dev, double* vout_dev, int64_t ncols,
+                                         const double* diag_dev, double power);
 /* BLAS-1 on device pointers for the sharded solver: out = a X + b Y + c Z (Y, Z may be NULL); out_dev[0] = a.b */
 int32_t elph_dev_lincomb(elph_handle* h, double* out, double a, const double* X, double b, const double* Y, double c,
                          const double* Z, int64_t n);

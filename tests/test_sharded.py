@@ -43,6 +43,8 @@ class OracleSlabBackend:
         self.D = torch.from_numpy(np.ascontiguousarray(E[idx])).clone()
         self.D[0] = 0.0
         self.D[lloc + 1] = 0.0                      # the halo is filled by the exchange, like on the GPU
+        X = om.x.reshape(om.N, om.L).T
+        self.x = torch.from_numpy(np.ascontiguousarray(X[tau0:tau0 + lloc])).clone()
 
     def empty(self):
         return self.torch.zeros(self.lloc + 2, self.N, dtype=self.torch.float64)
@@ -50,8 +52,38 @@ class OracleSlabBackend:
     def D_tensor(self):
         return self.D
 
+    def x_tensor(self):
+        return self.x
+
     def update_model(self):
+        om, L = self.om, self.lloc
+        X = self.x.numpy()
+        self.D.numpy()[1:L + 1] = np.exp(-om.dtau * (om.lam[None, :] * X + om.lam2[None, :] * X ** 2 + -om.mu[None, :]))
+
+    def dSbdx(self, dS, xh, shifted=True):
+        om, L, dt = self.om, self.lloc, self.om.dtau
+        x = xh.numpy()
+        own, up, dn = x[1:L + 1], x[2:L + 2], x[0:L]
+        d = dt * om.omega[None, :] ** 2 * own - (dt * om.lam[None, :] if shifted else 0.0)
+        d = d + dt * 4 * om.omega4[None, :] * own ** 3
+        d = d - (up + dn - 2.0 * own) / dt
+        dS.numpy()[1:L + 1] += d
+
+    def muldMdx(self, u, v, out, scale=1.0):
+        om, L, dt = self.om, self.lloc, self.om.dtau
+        un, vn, Dn, X = u.numpy(), v.numpy(), self.D.numpy(), self.x.numpy()
+        own = np.arange(1, L + 1)
+        sign = np.where((self.tau0 + own - 1) % self.Lg == 0, -1.0, 1.0)[:, None]
+        d = sign * dt * (om.lam[None, :] + 2 * om.lam2[None, :] * X) * Dn[own] * vn[own - 1]
+        y = self._K(un[own], True)
+        out.numpy()[1:L + 1] = scale * y * d
+
+    def make_fft_plan(self, Lglob):
         pass
+
+    def fa_cols(self, vin, vout, diag, power):
+        a = np.fft.fft(vin.numpy().astype(np.complex128), axis=0) * diag.numpy() ** power
+        vout.numpy()[:] = np.real(np.fft.ifft(a, axis=0))
 
     def _K(self, slices, transpose):
         Y = np.ascontiguousarray(slices.T)           # (N, nsl)
@@ -152,6 +184,75 @@ def _cpu_worker(rank, world, port):
 def test_sharded_host_logic_over_gloo(world):
     import torch.multiprocessing as mp
     mp.spawn(_cpu_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def _langevin_reference(om, method, dt, seed=21):
+    """Global oracle step without preconditioner + the injected noise (engine layout) + Q in [k][site] layout."""
+    from oracle import langevin as olang
+    from oracle.fourier import FourierAccelerator
+    rng = np.random.default_rng(seed)
+    eta, g1, g2 = rng.normal(size=om.Ndof), rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    fa = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
+    fa.update_Q(0.0, 10.0, 1.0)
+    cg = ConjugateGradient(om.Ndim, tol=1e-10, maxiter=20000)
+    x0 = om.x.copy()
+    if method == "euler":
+        it = olang.evolve_euler(om, cg, fa, None, dt, eta, g1)
+    else:
+        it = olang.evolve_rk(om, cg, fa, None, dt, eta, g1, g2)
+    x1 = om.x.copy()
+    om.x[:] = x0
+    om.update_model()
+    eng = lambda a: np.ascontiguousarray(a.reshape(om.N, om.L).T)
+    return eng(eta), eng(g1), eng(g2), eng(fa.Q), eng(x0), eng(x1), it
+
+
+def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4, beta=1.1):
+    import torch
+    from elphdynamics_b200.sharded import ShardedLangevin, ShardedOperator, slab_bounds
+    om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-0.5, seed=7)
+    dt = 1e-3
+    eta, g1, g2, Q, x0, x1, it_ref = _langevin_reference(om, method, dt)
+    tau0, lloc = slab_bounds(om.L, world, rank)
+    s0, nloc = slab_bounds(om.N, world, rank)
+    be = make_backend(om, tau0, lloc)
+    be.make_fft_plan(om.L)
+    op = ShardedOperator(be, comm, tol=1e-10, maxiter=20000)
+    Qb = torch.from_numpy(np.ascontiguousarray(Q[:, s0:s0 + nloc])).to(device)
+    lang = ShardedLangevin(op, om.N, om.L, tau0, Qb, dt)
+    lang.set_x(x0[tau0:tau0 + lloc])
+
+    def slab(a):
+        t = be.empty()
+        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).to(device)
+        return t
+    if method == "euler":
+        it = lang.evolve_euler(slab(eta), slab(g1))
+    else:
+        it = lang.evolve_rk(slab(eta), slab(g1), slab(g2))
+    assert abs(it - it_ref) <= 2, (it, it_ref)
+    got = lang.xh[1:lloc + 1].cpu().numpy()
+    assert relerr(got - x0[tau0:tau0 + lloc], (x1 - x0)[tau0:tau0 + lloc]) <= 1e-7, (method, rank)
+
+
+def _cpu_langevin_worker(rank, world, port, method):
+    import torch.distributed as dist
+    from elphdynamics_b200.sharded import RingComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _check_langevin(lambda om, t0, ll: OracleSlabBackend(om, t0, ll), RingComm(rank, world), rank, world, method)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,method", [(2, "rk"), (3, "euler")])
+def test_sharded_langevin_host_logic_over_gloo(world, method):
+    """Whole tau-sharded Langevin step (halo exchanges, all-reduces, all-to-all transposes around the tau-FFT) over
+    gloo, NumPy slab backend, against the oracle's global step with identical injected noise."""
+    import torch.multiprocessing as mp
+    mp.spawn(_cpu_langevin_worker, args=(world, _free_port(), method), nprocs=world, join=True)
 
 
 def test_slab_bounds_cover_the_time_axis():
@@ -287,6 +388,44 @@ def _gpu_worker(rank, world, port):
         em.close()
     finally:
         dist.destroy_process_group()
+
+
+def _cuda_backend(om, tau0, lloc):
+    from elphdynamics_b200.sharded import CudaSlabBackend
+    return CudaSlabBackend(_engine_slab(om, tau0, lloc), tau0, om.L)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,Ls", [("euler", 4), ("rk", 32)])
+def test_sharded_langevin_single_gpu(method, Ls):
+    """world = 1: the whole sharded driver (open-slab kernels, halo self-exchange, FFT plan handle, column FFT, slab
+    bosonic gradient) on one GPU against the oracle's global step."""
+    from elphdynamics_b200.sharded import RingComm
+    _check_langevin(_cuda_backend, RingComm(0, 1), 0, 1, method, device="cuda", Ls=Ls, beta=1.1 if Ls == 4 else 0.8)
+
+
+def _gpu_langevin_worker(rank, world, port):
+    import torch
+    import torch.distributed as dist
+    from elphdynamics_b200.sharded import RingComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        _check_langevin(_cuda_backend, RingComm(rank, world), rank, world, "rk", device="cuda", Ls=32, beta=0.8)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_langevin_over_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    mp.spawn(_gpu_langevin_worker, args=(world, _free_port()), nprocs=world, join=True)
 
 
 @pytest.mark.gpu
