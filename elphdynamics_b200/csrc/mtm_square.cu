@@ -432,7 +432,10 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
         // machine is covered ~4x, otherwise split finer
         // measured on B200 (32x32xL200, 16..128 replicas): C = 4 is the optimum once the grid covers the
         // machine several times (5.7-6.2 TB/s); longer chunks lose more to the tail than they save in halo
-        C = (latency_regime && Lx == 32) ? 2 : 1;
+        // latency regime: one wave with about one CTA per SM (measured: 32x32xL200 -> C=2: 5.5 us vs 7.4 us at C=1;
+        // 64x64xL400 -> C=3: 12.3 us vs 16.4 us at C=1 and 21.5 us at C=8)
+        C = 1;
+        if (latency_regime) C = (int)std::min<int64_t>(8, (a.nbatch * (int64_t)h->L + h->sm_count - 1) / h->sm_count);
         const int64_t want = 6LL * h->sm_count;
         for (int c : {4, 2}) {
             if (a.nbatch * ((h->L + c - 1) / c) >= want) { C = c; break; }
