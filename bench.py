@@ -98,16 +98,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_models():
-    from helpers import engine_holstein_like, oracle_holstein
-    om, rng = oracle_holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=1234, eps=0.3)  # only to generate inputs
-    em = engine_holstein_like(om)
-    return om, em, rng
+def build_model():
+    """Configuration B through the package's own host API (no oracle on the product arm)."""
+    from elphdynamics_b200 import workloads
+    return workloads.holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=1234, eps=0.3)
 
 
-def cpu_baseline(om, target_seconds=12.0, nthreads=0):
+def oracle_model():
+    """The same configuration and field as an oracle object: ONLY for the cpu_baseline / --impl reference legs."""
+    from helpers import oracle_holstein
+    return oracle_holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=1234, eps=0.3)[0]
+
+
+def cpu_baseline(target_seconds=12.0, nthreads=0):
     """C restatement of the reference loops on the host cores; bounded sample of the same workload."""
     from oracle.cref import CRef
+    om = oracle_model()
     c = CRef(om, native=True)
     ncpu = os.cpu_count() or 1
     nthreads = nthreads or ncpu
@@ -126,8 +132,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from helpers import oracle_holstein
-    om, _ = oracle_holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=1234, eps=0.3)
+    om = oracle_model()
     from oracle.cref import CRef
     c = CRef(om, native=True)
     nthreads = os.cpu_count() or 1
@@ -187,11 +192,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    om, em, rng = build_models()
+    em, rng = build_model()
     lib = em._lib
     stream = torch.cuda.current_stream()
     em.set_stream(stream.cuda_stream)
-    n = om.Ndim
+    n = em.Ndim
+    Nsites, Ltau = em.Nsites, em.Ltau
     R = args.replicas
     hbm_peak, peak_src, _ = peaks()
 
@@ -200,7 +206,7 @@ def main():
     V = torch.randn(R, n, dtype=torch.float64, device="cuda", generator=g)
     Y = torch.empty_like(V)
     # expnV of the synthetic field in the engine layout [tau][site], perturbed per replica (independent chains)
-    base = torch.from_numpy(np.ascontiguousarray(em.expnV.reshape(om.N, om.L).T)).reshape(-1).cuda()
+    base = torch.from_numpy(np.ascontiguousarray(em.expnV.reshape(Nsites, Ltau).T)).reshape(-1).cuda()
     D = base.unsqueeze(0).repeat(R, 1) * (1.0 + 0.01 * torch.rand(R, n, dtype=torch.float64, device="cuda", generator=g))
 
     def step_device():
@@ -309,7 +315,7 @@ def main():
         dt_cg = time.perf_counter() - t0
         extra["cg"] = {"iters": it, "residual": res, "flag": flag, "seconds": dt_cg, "iters_per_s": it / dt_cg}
         P = E.SymmetricKPMPreconditioner(em)
-        kinfo = E.setup_(P, rng.normal(size=2 * om.N))
+        kinfo = E.setup_(P, rng.normal(size=2 * Nsites))
         for _ in range(10):
             lib.elph_dev_kpm_apply(em.handle, v1.data_ptr(), y1.data_ptr())
         torch.cuda.synchronize()
@@ -333,7 +339,7 @@ def main():
         nsteps = 5
         its = []
         noise = [dict(eta=rng.normal(size=n), g1=rng.normal(size=n), g2=rng.normal(size=n),
-                      arnoldi1=rng.normal(size=2 * om.N), arnoldi2=rng.normal(size=2 * om.N)) for _ in range(nsteps + 1)]
+                      arnoldi1=rng.normal(size=2 * Nsites), arnoldi2=rng.normal(size=2 * Nsites)) for _ in range(nsteps + 1)]
         E.evolve_(em, dyn, fa, P, **noise[nsteps])   # warm-up
         t0 = time.perf_counter()
         for k in range(nsteps):
@@ -341,6 +347,54 @@ def main():
         dt_l = time.perf_counter() - t0
         extra["langevin_rk_kpm"] = {"steps_per_s": nsteps / dt_l, "pcg_iters_second_solve": its,
                                     "note": "elph_langevin_step through the C ABI with host noise buffers"}
+
+        # ---- configuration C: SSH 32x32xL200 (per-(tau,bond) cosh/sinh tables, 48 B/pt algorithmic) ----
+        from elphdynamics_b200 import hmc as ehmc
+        from elphdynamics_b200 import workloads
+        mC, rC = workloads.config("C")
+        mC.set_stream(stream.cuda_stream)
+        nC = mC.Ndim
+        vC = torch.randn(nC, dtype=torch.float64, device="cuda")
+        yC = torch.empty_like(vC)
+        for _ in range(10):
+            lib.elph_dev_mulMTM(mC.handle, vC.data_ptr(), yC.data_ptr())
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(100):
+            lib.elph_dev_mulMTM(mC.handle, vC.data_ptr(), yC.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        usC = e0.elapsed_time(e1) * 10.0
+        bC = rC.normal(size=nC)
+        xC = np.zeros(nC)
+        t0 = time.perf_counter()
+        itC, resC, flC = E.ldiv_(xC, mC, bC)
+        dtC = time.perf_counter() - t0
+        extra["ssh_square_32x32_L200"] = {"us_per_matvec": usC, "matvecs_per_s": 1e6 / usC,
+                                          "algorithmic_GBps": 48.0 * nC / usC / 1e3,
+                                          "cg": {"iters": int(itC), "residual": float(resC), "flag": int(flC), "seconds": dtC},
+                                          "note": "single lattice (L2-resident tables); 48 B/pt = v + cosh + sinh tables + y"}
+        mC.close()
+
+        # ---- configuration D: HMC trajectory on the honeycomb lattice L=32 (N=2048, Ltau=20), Nt=10 leapfrog steps ----
+        mD, rD = workloads.config("D_honeycomb")
+        mD.set_stream(stream.cuda_stream)
+        faD = E.FourierAccelerator(mD)
+        E.update_M_(faD, mD, 0.0, 10.0, 1.0, 0.0)
+        hD = ehmc.HybridMonteCarlo(mD, 0.01, 0.1, 0.0, 10)
+        draws = [dict(R_v=rD.normal(size=mD.Ndof), R_plus=rD.normal(size=mD.Ndim), R_minus=rD.normal(size=mD.Ndim),
+                      uniform=float(rD.uniform())) for _ in range(6)]
+        ehmc.update_(mD, hD, faD, None, **draws[0])
+        t0 = time.perf_counter()
+        itsD, accD = [], []
+        for d in draws[1:]:
+            a, it = ehmc.update_(mD, hD, faD, None, **d)
+            itsD.append(float(it)); accD.append(bool(a))
+        dtD = (time.perf_counter() - t0) / (len(draws) - 1)
+        extra["hmc_honeycomb_L32"] = {"trajectories_per_s": 1.0 / dtD, "leapfrog_steps": hD.Nt, "inner_Sb_steps": hD.Nb,
+                                      "solves_per_trajectory": 2 * (hD.Nt + 2), "cg_iters": itsD, "accepted": accD,
+                                      "note": "elph_hmc_update: whole trajectory on the device, noise injected from the host"}
+        mD.close()
 
     # ---------------- tau-sharded single lattice (config E: Holstein 64x64, L=400), strong scaling over ranks -----
     sharded = None
@@ -407,7 +461,7 @@ def main():
         if sharded is not None:
             line["tau_sharded"] = sharded
         if not args.no_cpu:
-            cb, _ = cpu_baseline(om)
+            cb, _ = cpu_baseline()
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     em.close()

@@ -137,3 +137,21 @@ def test_error_reporting_through_the_abi():
     with pytest.raises(ValueError):
         E.mulM_(np.zeros(m.Ndim), m, np.zeros(3))
     m.close()
+
+
+def test_workload_builders_match_the_test_builders():
+    """bench.py builds its models with elphdynamics_b200.workloads (no oracle); same seeds must give the same field
+    and tables as the oracle-side builders the parity tests use."""
+    from helpers import oracle_holstein, relerr
+    from helpers_ssh import oracle_ssh
+    from elphdynamics_b200 import workloads
+    om, _ = oracle_holstein("triangular", 5, 1.0, 0.1, seed=7, eps=0.5)
+    em, _ = workloads.holstein("triangular", 5, 1.0, 0.1, seed=7, eps=0.5)
+    assert np.array_equal(em.x, om.x)
+    assert np.array_equal(em.neighbor_table, om.neighbor_table)
+    assert relerr(em.expnV, om.expnV.reshape(-1)) < 1e-14
+    em.close()
+    os_, _ = oracle_ssh(4, 1.0, 0.05, seed=11)
+    es, _ = workloads.ssh_square(4, 1.0, 0.05, seed=11)
+    assert np.array_equal(es.x, os_.x)
+    es.close()
