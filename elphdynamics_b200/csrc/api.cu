@@ -220,6 +220,7 @@ void build(elph_handle* h, const elph_config* c) {
         up(h->d_grp_members, members);
         h->d_cs = elph_dalloc<double2>((size_t)h->L * h->Nb);
         h->d_tprime = elph_dalloc<double>((size_t)h->L * h->Nb);
+        elph_detect_ssh_square(h);
         h->d_D = zeros(h->N);
         h->d_lam = zeros(h->N);
         h->d_lam2 = zeros(h->N);
@@ -300,7 +301,7 @@ void destroy(elph_handle* h) {
         h->d_D = nullptr;
     }
     void* ptrs[] = {h->d_bonds, h->d_goff, h->d_cs, h->d_lam, h->d_lam2, h->d_mu, h->d_omega, h->d_omega4, h->d_x, h->d_D,
-                    h->d_Q, h->d_Mass, h->d_t, h->d_alpha, h->d_alpha2, h->d_ph_col, h->d_col_ph, h->d_col_bond,
+                    h->d_Q, h->d_Mass, h->d_t, h->d_alpha, h->d_alpha2, h->d_ph_col, h->d_col_ph, h->d_col_bond, h->ssq.d_slot, h->ssq.d_tab,
                     h->d_primary_ph, h->d_grp_start, h->d_grp_members, h->d_tprime, h->d_va, h->d_vb, h->d_vc, h->d_b,
                     h->d_res, h->d_r, h->d_p[0], h->d_p[1], h->d_z, h->d_partial, h->d_ticket, h->d_bar, h->d_cg, h->d_scal,
                     h->d_dSdx, h->d_dSdx2, h->d_eta, h->d_dx, h->d_tmp, h->d_g, h->d_g2, h->d_Minv, h->d_nu2,
@@ -1052,7 +1053,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
 }
 int32_t elph_get_kernel_info(elph_handle* h, int32_t* square_kernel, int32_t* ngroups) {
     ENTER(h) {
-        if (square_kernel) *square_kernel = (h->sq.enabled && !h->sq_disable) ? 1 : 0;
+        if (square_kernel) *square_kernel = ((h->sq.enabled || h->ssq.enabled) && !h->sq_disable) ? 1 : 0;
         if (ngroups) *ngroups = h->ngroups;
         return ELPH_OK;
     }

@@ -233,6 +233,14 @@ struct elph_handle {
         int Lx = 0, Ly = 0;
         double c[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
     } sq;
+    // SSH on the periodic square lattice (ssh_square.cu): second copy of the per-(tau,bond) table in the
+    // register-tile layout [tau][dir][site] (dir 0 = +x bond leaving `site`, 1 = +y bond), written by update_model
+    struct {
+        bool enabled = false;
+        int Lx = 0, Ly = 0;
+        int* d_slot = nullptr;        // [Nb] column -> dir*N + origin site
+        double2* d_tab = nullptr;     // [L][2][N] (cosh, sinh)
+    } ssq;
     // tau-sharding (multi-GPU): this handle owns global slices [shard_tau0, shard_tau0 + L) of shard_Lglob
     bool sharded = false;
     int shard_tau0 = 0, shard_Lglob = 0;
@@ -271,6 +279,9 @@ void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a);
 void elph_launch_update_model(elph_handle* h);
 void elph_detect_square(elph_handle* h, const std::vector<double2>& cs);
 bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a);
+bool elph_match_square(const elph_handle* h, int* Lx, int* Ly, std::vector<int>* slot);
+void elph_detect_ssh_square(elph_handle* h);                          // ssh_square.cu
+bool elph_launch_ssh_square(elph_handle* h, const MatvecArgs& a);     // ssh_square.cu
 void elph_launch_transpose(elph_handle* h, const double* in, double* out, int rows, int cols, int64_t nbatch);
 void elph_launch_transpose_c(elph_handle* h, const cplx* in, cplx* out, int rows, int cols);
 // host layout (ncols rows of length L) -> engine layout [L][ncols]

@@ -245,7 +245,8 @@ __global__ void holstein_update_kernel(const double* __restrict__ x, const doubl
 __global__ void ssh_update_kernel(const double* __restrict__ x, const double* __restrict__ t, const double* __restrict__ alpha,
                                   const double* __restrict__ alpha2, const int* __restrict__ col_ph,
                                   const int* __restrict__ col_bond, double2* __restrict__ cs, double* __restrict__ tprime,
-                                  int Nb, int Nph, long long n, double dtau) {
+                                  const int* __restrict__ sq_slot, double2* __restrict__ sq_tab, int Nb, int Nph, long long n,
+                                  double dtau) {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const int col = (int)(idx % Nb);
         const long long tau = idx / Nb;
@@ -257,7 +258,9 @@ __global__ void ssh_update_kernel(const double* __restrict__ x, const double* __
             tp -= alpha[ph] * xv + sgn * alpha2[ph] * xv * xv;
         }
         tprime[idx] = tp;
-        cs[idx] = make_double2(cosh(dtau * tp), sinh(dtau * tp));
+        const double2 v = make_double2(cosh(dtau * tp), sinh(dtau * tp));
+        cs[idx] = v;
+        if (sq_tab) sq_tab[tau * Nb + sq_slot[col]] = v;   // tile layout [tau][dir][site] of ssh_square.cu
     }
 }
 
@@ -316,7 +319,7 @@ static int pick_chunk(elph_handle* h, MatvecMode mode, int64_t nbatch) {
 }
 
 void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a) {
-    if (mode == MODE_MTM && elph_launch_mtm_square(h, a)) return;
+    if (mode == MODE_MTM && (elph_launch_mtm_square(h, a) || elph_launch_ssh_square(h, a))) return;
     ELPH_REQUIRE(a.v != a.y || a.cg_S, ELPH_ERR_INVALID, "matvec output must not alias its input");
     KParams P;
     P.v = a.v;
@@ -386,7 +389,8 @@ void elph_launch_update_model(elph_handle* h) {
         const long long n = (long long)h->L * h->Nb;
         const int blocks = (int)std::min<long long>((n + T - 1) / T, 8LL * h->sm_count);
         ssh_update_kernel<<<blocks, T, 0, h->stream>>>(h->d_x, h->d_t, h->d_alpha, h->d_alpha2, h->d_col_ph,
-                                                       h->d_col_bond, h->d_cs, h->d_tprime, h->Nb, h->Nph, n, h->dtau);
+                                                       h->d_col_bond, h->d_cs, h->d_tprime, h->ssq.enabled ? h->ssq.d_slot : nullptr,
+                                                       h->ssq.enabled ? h->ssq.d_tab : nullptr, h->Nb, h->Nph, n, h->dtau);
     }
     ELPH_CUDA(cudaGetLastError());
     h->launches++;

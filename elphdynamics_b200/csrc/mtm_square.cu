@@ -24,6 +24,7 @@
 // CG fusion (FUSEP): v := pr + beta*pold is formed on the fly and written to pnew; p.Ap = |M p|^2 is
 // accumulated as sum w^2 (identical in exact arithmetic to dot(p, M^T M p)); the last CTA folds the per-CTA
 // partials in index order and publishes alpha (see cg.cu).
+#include "bulk_copy.cuh"
 #include "elph_internal.cuh"
 
 namespace {
@@ -46,35 +47,7 @@ struct SqParams {
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+using namespace tma;   // mbarrier + cp.async.bulk helpers (bulk_copy.cuh)
 
 template <int NSEG, int PY>
 struct Tile {
@@ -355,26 +328,26 @@ void launch_sq(elph_handle* h, const SqParams& P, dim3 grid, int nwarps) {
 
 }  // namespace
 
-// Recognise the periodic square lattice with the reference's colouring and uniform (cosh, sinh) per colour.
-void elph_detect_square(elph_handle* h, const std::vector<double2>& cs) {
-    h->sq.enabled = false;
-    if (h->model != ELPH_MODEL_HOLSTEIN || h->ngroups != 4) return;
+// Recognise the periodic square lattice with the reference's colouring: 4 groups = (x-bonds, x even), (x-bonds, x odd
+// incl. the wrap), (y-bonds, y even), (y-bonds, y odd incl. the wrap).  slot[b] = dir*N + origin site of column b
+// (origin = the site the bond leaves in +x / +y direction).
+bool elph_match_square(const elph_handle* h, int* Lx_out, int* Ly_out, std::vector<int>* slot) {
+    if (h->ngroups != 4) return false;
     const int N = h->N;
+    if (h->Nb != 2 * N) return false;
     for (int Lx = 32; Lx <= 128; Lx += 32) {
         if (N % Lx) continue;
         const int Ly = N / Lx;
-        if (Ly < 4 || (Ly & 1) || Lx > 128) continue;
-        if (h->Nb != 2 * N) continue;
+        if (Ly < 4 || (Ly & 1)) continue;
         bool ok = true;
+        if (slot) slot->assign(h->Nb, -1);
         for (int g = 0; g < 4 && ok; ++g) {
             const int lo = h->goff_host[g], hi = h->goff_host[g + 1];
             if (hi - lo != N / 2) { ok = false; break; }
             std::vector<char> seen(N, 0);
             for (int b = lo; b < hi && ok; ++b) {
                 int i = h->bonds_host[b].x, j = h->bonds_host[b].y;
-                if (cs[b].x != cs[lo].x || cs[b].y != cs[lo].y) { ok = false; break; }
-                // canonical "first" site of the bond in each group
-                int xi = i % Lx, yi = i / Lx, xj = j % Lx, yj = j / Lx;
+                const int xi = i % Lx, yi = i / Lx, xj = j % Lx, yj = j / Lx;
                 bool match = false;
                 if (g < 2) {   // x-bond: same row, x' = x+1 mod Lx with x parity = g
                     if (yi == yj) {
@@ -389,17 +362,32 @@ void elph_detect_square(elph_handle* h, const std::vector<double2>& cs) {
                 }
                 if (!match || seen[i]) ok = false;
                 seen[i] = 1;
+                if (ok && slot) (*slot)[b] = (g / 2) * N + i;
             }
         }
         if (!ok) continue;
-        h->sq.enabled = true;
-        h->sq.Lx = Lx;
-        h->sq.Ly = Ly;
-        for (int g = 0; g < 4; ++g) {
-            h->sq.c[g] = cs[h->goff_host[g]].x;
-            h->sq.s[g] = cs[h->goff_host[g]].y;
-        }
-        return;
+        *Lx_out = Lx;
+        *Ly_out = Ly;
+        return true;
+    }
+    return false;
+}
+
+// Holstein fast path: additionally the (cosh, sinh) pair must be uniform per colour.
+void elph_detect_square(elph_handle* h, const std::vector<double2>& cs) {
+    h->sq.enabled = false;
+    if (h->model != ELPH_MODEL_HOLSTEIN) return;
+    int Lx, Ly;
+    if (!elph_match_square(h, &Lx, &Ly, nullptr)) return;
+    for (int g = 0; g < 4; ++g)
+        for (int b = h->goff_host[g]; b < h->goff_host[g + 1]; ++b)
+            if (cs[b].x != cs[h->goff_host[g]].x || cs[b].y != cs[h->goff_host[g]].y) return;
+    h->sq.enabled = true;
+    h->sq.Lx = Lx;
+    h->sq.Ly = Ly;
+    for (int g = 0; g < 4; ++g) {
+        h->sq.c[g] = cs[h->goff_host[g]].x;
+        h->sq.s[g] = cs[h->goff_host[g]].y;
     }
 }
 

@@ -14,7 +14,19 @@ CASES = [
     dict(Lside=4, beta=0.5, dtau=0.05, names=["a", "a"]),     # equivalent fields (primary_field folding)
     dict(Lside=4, beta=0.5, dtau=0.05, mixed=True),           # a bond type without phonons
     dict(Lside=8, beta=1.0, dtau=0.05, mu=0.2),
+    # Lx = 32 / 64: served by the register-tile kernel of ssh_square.cu (the cases above use the generic kernel)
+    dict(Lside=32, beta=0.4, dtau=0.05, mu=0.1, alpha2=0.01),
+    dict(Lside=32, beta=0.25, dtau=0.05, mixed=True),
+    dict(Lside=64, beta=0.2, dtau=0.05, mu=-0.1),
 ]
+
+
+def test_kernel_family(pair):
+    import ctypes as C
+    om, em, _ = pair
+    sq = C.c_int32()
+    em._call("elph_get_kernel_info", C.byref(sq), None)
+    assert sq.value == (1 if om.lat.L1 in (32, 64) else 0)
 
 
 @pytest.fixture(scope="module", params=CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
