@@ -20,7 +20,8 @@ namespace {
 using namespace sqt;
 
 struct PcgParams {
-    const double* __restrict__ D;    // expnV [L][N]
+    const double* __restrict__ D;    // Holstein: expnV [L][N]; SSH: exp(dtau mu) [N]
+    const double2* __restrict__ tab; // SSH: (cosh, sinh) [L][2][N] in the tile layout of ssh_square.cu
     double* __restrict__ x;          // [L][N] in: initial guess, out: solution
     double* R;                       // [L][N] residual (in: r0), updated every iteration
     double* P0;                      // [L][N] p buffers (double-buffered); P1 must hold zeros on entry
@@ -72,10 +73,10 @@ __device__ __forceinline__ double tile_block_sum(double v, double* red, int lane
     return t;   // same value on every thread
 }
 
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool SSH>
 __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
     constexpr int LX = 32 * NSEG;
-    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]
+    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; SSH: + the tables of slices tau and tau+1
     __shared__ double red[32];
     __shared__ double bcast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -95,9 +96,24 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
             x.a[rr][q] = P.x[(size_t)tau * N + e];
             r.a[rr][q] = P.R[(size_t)tau * N + e];
             pprev.a[rr][q] = 0.0;
-            Dc.a[rr][q] = P.D[(size_t)tau * N + e];
-            Dn.a[rr][q] = P.D[(size_t)taup * N + e];
+            Dc.a[rr][q] = SSH ? P.D[e] : P.D[(size_t)tau * N + e];
+            Dn.a[rr][q] = SSH ? P.D[e] : P.D[(size_t)taup * N + e];
         }
+    // SSH: K(tau) and K(tau+1) stay in shared memory for the whole solve (the field is fixed during a solve)
+    const double2* txc = nullptr; const double2* tyc = nullptr; const double2* hyc = nullptr;
+    const double2* txn = nullptr; const double2* tyn = nullptr; const double2* hyn = nullptr;
+    if constexpr (SSH) {
+        double2* tabc = reinterpret_cast<double2*>(strips + 2ull * nwarps * 4 * LX);
+        double2* tabn = tabc + 2 * N;
+        for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+            tabc[i] = P.tab[(size_t)tau * 2 * N + i];
+            tabn[i] = P.tab[(size_t)taup * 2 * N + i];
+        }
+        __syncthreads();
+        const size_t halo_off = (size_t)((warp * PY + P.Ly - 1) % P.Ly) * LX;
+        txc = tabc + tile_off; tyc = tabc + N + tile_off; hyc = tabc + N + halo_off;
+        txn = tabn + tile_off; tyn = tabn + N + tile_off; hyn = tabn + N + halo_off;
+    }
     const double normb = P.S->normb, eps0 = P.S->eps0, tol = P.S->tol, kappa_max = P.S->kappa_max;
     const long long maxiter = P.S->maxiter;
     double rdotr = P.S->rdotz, beta = 0.0, kmin = 0.0, eps = eps0;
@@ -125,18 +141,32 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
                 t2.a[rr][q] = Dn.a[rr][q] * pcv;         // D(tau+1) p(tau)
             }
         // ---- K sweep on both tiles (one barrier) ----------------------------------------------------------------
-        g0_x_even(t1, P.c0, P.s0);
-        g0_x_even(t2, P.c0, P.s0);
-        g1_x_odd(t1, P.c1, P.s1, lane);
-        g1_x_odd(t2, P.c1, P.s1, lane);
-        g2_y_even(t1, P.c2, P.s2);
-        g2_y_even(t2, P.c2, P.s2);
+        if constexpr (SSH) {
+            g0_tab(t1, txc, lane);
+            g0_tab(t2, txn, lane);
+            g1_tab(t1, txc, lane);
+            g1_tab(t2, txn, lane);
+            g2_tab(t1, tyc, lane);
+            g2_tab(t2, tyn, lane);
+        } else {
+            g0_x_even(t1, P.c0, P.s0);
+            g0_x_even(t2, P.c0, P.s0);
+            g1_x_odd(t1, P.c1, P.s1, lane);
+            g1_x_odd(t2, P.c1, P.s1, lane);
+            g2_y_even(t1, P.c2, P.s2);
+            g2_y_even(t2, P.c2, P.s2);
+        }
         {
             double a1[NSEG], a2[NSEG], b1[NSEG], b2[NSEG];
             exchange_edges2(t1, t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, a1, a2, b1, b2);
             xbuf ^= 1;
-            g3_y_odd(t1, P.c3, P.s3, a1, b1);
-            g3_y_odd(t2, P.c3, P.s3, a2, b2);
+            if constexpr (SSH) {
+                g3_tab(t1, tyc, hyc, lane, a1, b1);
+                g3_tab(t2, tyn, hyn, lane, a2, b2);
+            } else {
+                g3_y_odd(t1, P.c3, P.s3, a1, b1);
+                g3_y_odd(t2, P.c3, P.s3, a2, b2);
+            }
         }
         // w(tau) -> t1 ; w(tau+1) -> t2 ; partial p.Ap = |w(tau)|^2
         double acc = 0.0;
@@ -157,11 +187,18 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
             double ab[NSEG], be[NSEG];
             exchange_edges1(t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, ab, be);
             xbuf ^= 1;
-            g3_y_odd(t2, P.c3, P.s3, ab, be);
+            if constexpr (SSH) g3_tab(t2, tyn, hyn, lane, ab, be);
+            else g3_y_odd(t2, P.c3, P.s3, ab, be);
         }
-        g2_y_even(t2, P.c2, P.s2);
-        g1_x_odd(t2, P.c1, P.s1, lane);
-        g0_x_even(t2, P.c0, P.s0);
+        if constexpr (SSH) {
+            g2_tab(t2, tyn, lane);
+            g1_tab(t2, txn, lane);
+            g0_tab(t2, txn, lane);
+        } else {
+            g2_y_even(t2, P.c2, P.s2);
+            g1_x_odd(t2, P.c1, P.s1, lane);
+            g0_x_even(t2, P.c0, P.s0);
+        }
         // ---- alpha ------------------------------------------------------------------------------------------------
         const double blockA = tile_block_sum<NSEG, PY>(acc, red, lane, warp, nwarps);
         target += nb;
@@ -210,11 +247,13 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
     }
 }
 
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool SSH>
 bool launch_persistent(elph_handle* h, PcgParams& P, int nwarps) {
     constexpr int LX = 32 * NSEG;
-    const size_t smem = 2ull * nwarps * 4 * LX * sizeof(double);
-    auto kern = cg_persistent_kernel<NSEG, PY, MAXT>;
+    const size_t smem = 2ull * nwarps * 4 * LX * sizeof(double) + (SSH ? 2ull * 2 * h->N * sizeof(double2) : 0);
+    if (smem > h->smem_optin) return false;
+    auto kern = cg_persistent_kernel<NSEG, PY, MAXT, SSH>;
+    elph_enable_smem(h, kern);
     int per_sm = 0;
     ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem));
     if ((long long)per_sm * h->sm_count < h->L) return false;   // all time slices must be co-resident
@@ -230,24 +269,29 @@ bool launch_persistent(elph_handle* h, PcgParams& P, int nwarps) {
 // r0 (in h->d_r), the scalar block (normb, eps0, rdotz = r0.r0, ...) and zeros in h->d_p[1] must be set up by the caller
 // (elph_cg_device does that with the same kernels as the multi-launch path).  Returns false if not applicable.
 bool elph_cg_persistent(elph_handle* h, double* x_dev) {
-    if (!h->sq.enabled || h->sq_disable || !h->use_persistent || h->model != ELPH_MODEL_HOLSTEIN || h->sharded) return false;
+    const bool ssh = (h->model == ELPH_MODEL_SSH);
+    if (!(ssh ? h->ssq.enabled : h->sq.enabled) || h->sq_disable || !h->use_persistent || h->sharded) return false;
     if (h->L < 4) return false;
     int dev_coop = 0;
     cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, h->device);
     if (!dev_coop) return false;
-    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
+    const int Lx = ssh ? h->ssq.Lx : h->sq.Lx, Ly = ssh ? h->ssq.Ly : h->sq.Ly;
     const int PY = (Lx == 32) ? 8 : 4;
     if (Ly % PY) return false;
     const int nwarps = Ly / PY;
     if (nwarps < 2 || nwarps > 32) return false;
     if (h->partial_cap < 2 * h->L) return false;
     PcgParams P;
-    P.D = h->d_D; P.x = x_dev; P.R = h->d_r; P.P0 = h->d_p[0]; P.P1 = h->d_p[1];
+    P.D = h->d_D; P.tab = ssh ? h->ssq.d_tab : nullptr; P.x = x_dev; P.R = h->d_r; P.P0 = h->d_p[0]; P.P1 = h->d_p[1];
     P.partialA = h->d_partial; P.partialB = h->d_partial + h->L; P.bar = h->d_bar; P.S = h->d_cg;
     P.L = h->L; P.Ly = Ly;
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
-    if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256>(h, P, nwarps);
-    if (Lx == 64 && PY == 4 && nwarps * 32 <= 512) return launch_persistent<2, 4, 512>(h, P, nwarps);
+    if (ssh) {
+        if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, true>(h, P, nwarps);
+        return false;
+    }
+    if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, false>(h, P, nwarps);
+    if (Lx == 64 && PY == 4 && nwarps * 32 <= 512) return launch_persistent<2, 4, 512, false>(h, P, nwarps);
     return false;
 }

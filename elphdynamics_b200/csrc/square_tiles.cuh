@@ -121,4 +121,83 @@ __device__ __forceinline__ void exchange_edges2(const Tile<NSEG, PY>& re, const 
     }
 }
 
+// ---- colour groups with per-bond coefficients (SSH): (cosh, sinh) read from shared-memory tables -------------------
+// tx: [PY][LX] double2 of the tile rows, entry (r, x) = bond (x,y)-(x+1,y);  ty: same for the bond (x,y)-(x,y+1);
+// ty_halo: [LX] double2 = the y-table row above the tile (its y-odd bonds enter tile row 0).
+template <int NSEG, int PY>
+__device__ __forceinline__ void g0_tab(Tile<NSEG, PY>& t, const double2* __restrict__ tx, int lane) {
+    constexpr int LX = 32 * NSEG;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double2 cs = tx[r * LX + 32 * q + (lane & ~1)];
+            const double o = __shfl_xor_sync(0xffffffffu, t.a[r][q], 1);
+            t.a[r][q] = cs.x * t.a[r][q] + cs.y * o;
+        }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g1_tab(Tile<NSEG, PY>& t, const double2* __restrict__ tx, int lane) {
+    constexpr int LX = 32 * NSEG;
+    const int partner = (lane & 1) ? ((lane + 1) & 31) : ((lane + 31) & 31);
+#pragma unroll
+    for (int r = 0; r < PY; ++r) {
+        double o[NSEG];
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            double send = t.a[r][q];
+            if (NSEG > 1) {
+                const double nxt = t.a[r][(q + 1) % NSEG], prv = t.a[r][(q + NSEG - 1) % NSEG];
+                send = (lane == 0) ? nxt : ((lane == 31) ? prv : send);
+            }
+            o[q] = __shfl_sync(0xffffffffu, send, partner);
+        }
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            // the bond leaves the odd site: own column for odd lanes, the column to the left (periodic) for even lanes
+            const int x = 32 * q + lane;
+            const int xo = (lane & 1) ? x : ((x + LX - 1) % LX);
+            const double2 cs = tx[r * LX + xo];
+            t.a[r][q] = cs.x * t.a[r][q] + cs.y * o[q];
+        }
+    }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g2_tab(Tile<NSEG, PY>& t, const double2* __restrict__ ty, int lane) {
+    constexpr int LX = 32 * NSEG;
+#pragma unroll
+    for (int r = 0; r < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double2 cs = ty[r * LX + 32 * q + lane];
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = cs.x * t1 + cs.y * t2;
+            t.a[r + 1][q] = cs.x * t2 + cs.y * t1;
+        }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g3_tab(Tile<NSEG, PY>& t, const double2* __restrict__ ty, const double2* __restrict__ ty_halo,
+                                       int lane, const double (&above)[NSEG], const double (&below)[NSEG]) {
+    constexpr int LX = 32 * NSEG;
+#pragma unroll
+    for (int r = 1; r + 1 < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double2 cs = ty[r * LX + 32 * q + lane];
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = cs.x * t1 + cs.y * t2;
+            t.a[r + 1][q] = cs.x * t2 + cs.y * t1;
+        }
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        const double2 ca = ty_halo[32 * q + lane];                 // bond from the row above into tile row 0
+        const double2 cb = ty[(PY - 1) * LX + 32 * q + lane];      // bond from tile row PY-1 into the row below
+        t.a[0][q] = ca.x * t.a[0][q] + ca.y * above[q];
+        t.a[PY - 1][q] = cb.x * t.a[PY - 1][q] + cb.y * below[q];
+    }
+}
+
 }  // namespace sqt

@@ -18,7 +18,7 @@
 namespace {
 
 using namespace tma;
-using sqt::Tile;
+using namespace sqt;
 
 struct SshParams {
     const double* __restrict__ v;
@@ -34,85 +34,6 @@ struct SshParams {
     long long v_stride, y_stride;
     int L, Ly, C;
 };
-
-// ---- colour groups with per-bond coefficients read from the staged tables ---------------------------------------
-// tx: [PY][LX] double2, entry (r, x) = bond (x,y)-(x+1,y);  ty: [PY+1][LX] double2, row 0 = the row above the tile,
-// row r+1 = tile row r, entry (., x) = bond (x,y)-(x,y+1).
-template <int NSEG, int PY>
-__device__ __forceinline__ void g0_tab(Tile<NSEG, PY>& t, const double2* __restrict__ tx, int lane) {
-    constexpr int LX = 32 * NSEG;
-#pragma unroll
-    for (int r = 0; r < PY; ++r)
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            const double2 cs = tx[r * LX + 32 * q + (lane & ~1)];
-            const double o = __shfl_xor_sync(0xffffffffu, t.a[r][q], 1);
-            t.a[r][q] = cs.x * t.a[r][q] + cs.y * o;
-        }
-}
-
-template <int NSEG, int PY>
-__device__ __forceinline__ void g1_tab(Tile<NSEG, PY>& t, const double2* __restrict__ tx, int lane) {
-    constexpr int LX = 32 * NSEG;
-    const int partner = (lane & 1) ? ((lane + 1) & 31) : ((lane + 31) & 31);
-#pragma unroll
-    for (int r = 0; r < PY; ++r) {
-        double o[NSEG];
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            double send = t.a[r][q];
-            if (NSEG > 1) {
-                const double nxt = t.a[r][(q + 1) % NSEG], prv = t.a[r][(q + NSEG - 1) % NSEG];
-                send = (lane == 0) ? nxt : ((lane == 31) ? prv : send);
-            }
-            o[q] = __shfl_sync(0xffffffffu, send, partner);
-        }
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            // the bond leaves the odd site: own column for odd lanes, the column to the left (periodic) for even lanes
-            const int x = 32 * q + lane;
-            const int xo = (lane & 1) ? x : ((x + LX - 1) % LX);
-            const double2 cs = tx[r * LX + xo];
-            t.a[r][q] = cs.x * t.a[r][q] + cs.y * o[q];
-        }
-    }
-}
-
-template <int NSEG, int PY>
-__device__ __forceinline__ void g2_tab(Tile<NSEG, PY>& t, const double2* __restrict__ ty, int lane) {
-    constexpr int LX = 32 * NSEG;
-#pragma unroll
-    for (int r = 0; r < PY; r += 2)
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            const double2 cs = ty[(r + 1) * LX + 32 * q + lane];
-            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
-            t.a[r][q] = cs.x * t1 + cs.y * t2;
-            t.a[r + 1][q] = cs.x * t2 + cs.y * t1;
-        }
-}
-
-template <int NSEG, int PY>
-__device__ __forceinline__ void g3_tab(Tile<NSEG, PY>& t, const double2* __restrict__ ty, int lane, const double (&above)[NSEG],
-                                       const double (&below)[NSEG]) {
-    constexpr int LX = 32 * NSEG;
-#pragma unroll
-    for (int r = 1; r + 1 < PY; r += 2)
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            const double2 cs = ty[(r + 1) * LX + 32 * q + lane];
-            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
-            t.a[r][q] = cs.x * t1 + cs.y * t2;
-            t.a[r + 1][q] = cs.x * t2 + cs.y * t1;
-        }
-#pragma unroll
-    for (int q = 0; q < NSEG; ++q) {
-        const double2 ca = ty[32 * q + lane];              // bond from the row above into tile row 0
-        const double2 cb = ty[PY * LX + 32 * q + lane];    // bond from tile row PY-1 into the row below
-        t.a[0][q] = ca.x * t.a[0][q] + ca.y * above[q];
-        t.a[PY - 1][q] = cb.x * t.a[PY - 1][q] + cb.y * below[q];
-    }
-}
 
 template <int NSEG, int PY, bool FUSEP, int STAGES, int MAXT>
 __global__ void __launch_bounds__(MAXT) ssh_square_kernel(SshParams P) {
@@ -203,7 +124,8 @@ __global__ void __launch_bounds__(MAXT) ssh_square_kernel(SshParams P) {
         const int st = j % STAGES;
         const double* sv = stage_base + (size_t)st * STAGE_DBL;
         const double2* tx = reinterpret_cast<const double2*>(sv + NV * TILE);
-        const double2* ty = tx + TILE;
+        const double2* ty_halo = tx + TILE;            // [1][LX] row above the tile, then the tile rows
+        const double2* ty = ty_halo + LX;
         mbar_wait(&bars[st], (uint32_t)((j / STAGES) & 1));
         // t = exp(dtau mu) .* v(tau-1);  t = K(tau) t
 #pragma unroll
@@ -213,9 +135,9 @@ __global__ void __launch_bounds__(MAXT) ssh_square_kernel(SshParams P) {
         g0_tab(t, tx, lane);
         g1_tab(t, tx, lane);
         g2_tab(t, ty, lane);
-        sqt::exchange_edges1(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+        exchange_edges1(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
         xbuf ^= 1;
-        g3_tab(t, ty, lane, above, below);
+        g3_tab(t, ty, ty_halo, lane, above, below);
         // w(tau) = v(tau) -/+ t
 #pragma unroll
         for (int r = 0; r < PY; ++r)
@@ -235,9 +157,9 @@ __global__ void __launch_bounds__(MAXT) ssh_square_kernel(SshParams P) {
             for (int r = 0; r < PY; ++r)
 #pragma unroll
                 for (int q = 0; q < NSEG; ++q) u.a[r][q] = t.a[r][q];
-            sqt::exchange_edges1(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+            exchange_edges1(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
             xbuf ^= 1;
-            g3_tab(u, ty, lane, above, below);
+            g3_tab(u, ty, ty_halo, lane, above, below);
             g2_tab(u, ty, lane);
             g1_tab(u, tx, lane);
             g0_tab(u, tx, lane);
