@@ -237,7 +237,7 @@ void build(elph_handle* h, const elph_config* c) {
     h->d_p[0] = zeros(h->Ndim);
     h->d_p[1] = zeros(h->Ndim);
     h->d_z = zeros(h->Ndim);
-    h->partial_cap = std::max(std::max(4 * h->sm_count, 2 * h->L + 8), h->N / 4 + 8);
+    h->partial_cap = std::max(std::max(4 * h->sm_count, 4 * h->L + 8), h->N / 4 + 8);
     h->d_partial = zeros(h->partial_cap);
     h->d_ticket = elph_dalloc<unsigned int>(1);
     ELPH_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));

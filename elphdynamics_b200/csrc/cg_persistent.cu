@@ -26,27 +26,33 @@ struct PcgParams {
     double* R;                       // [L][N] residual (in: r0), updated every iteration
     double* P0;                      // [L][N] p buffers (double-buffered); P1 must hold zeros on entry
     double* P1;
-    double* partialA;                // [L]
-    double* partialB;                // [L]
+    double* partialA;                // [L][2] barrier slots (see grid_sum)
+    double* partialB;                // [L][2]
     unsigned int* bar;               // monotonically increasing arrival counter (zero on entry)
     CgScalars* S;                    // in: normb, eps0, rdotz (= r0.r0), tol, kappa_max, maxiter ; out: iter, eps, done
     int L, Ly;
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
 
+// Grid barrier fused with a sum over all CTAs; every CTA returns the same bits (fixed order: lane-strided, then tree).
+// One arrival counter (monotonically increasing, target = seq * nb) polled by one thread per CTA, then the partials are
+// read back.  (Tried and rejected, measured on B200: LL-style flagged slots -- value and sequence number in one 16-byte
+// store, every CTA's warp 0 spinning on all nb slots -- cost 14.3 us/iteration at 200 CTAs against 8.1 us for the
+// counter: O(nb^2) polling traffic in L2.)  The caller must have a __syncthreads between the CTA's global writes and
+// this call.  `seq` numbers the barriers of the launch from 1.
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-// grid barrier fused with a sum over all CTAs; every CTA returns the same bits (fixed order: lane-strided, then tree)
-__device__ __forceinline__ double grid_sum(double block_value, double* partial, unsigned int* bar, unsigned int target, int nb,
+__device__ __forceinline__ double grid_sum(double block_value, double* partial, unsigned int* bar, unsigned int seq, int nb,
                                            double* bcast) {
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = block_value;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        // release-arrive without waiting for the atomic's return value
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        const unsigned int target = seq * (unsigned int)nb;
         while (ld_acquire(bar) < target) {}
     }
     __syncthreads();
@@ -118,7 +124,6 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
     const long long maxiter = P.S->maxiter;
     double rdotr = P.S->rdotz, beta = 0.0, kmin = 0.0, eps = eps0;
     long long j = 0;
-    unsigned int target = 0;
     int xbuf = 0;
     double* Pold = P.P1;   // holds zeros on entry: p_0 = r_0 + 0 * p_{-1}
     double* Pnew = P.P0;
@@ -201,8 +206,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
         }
         // ---- alpha ------------------------------------------------------------------------------------------------
         const double blockA = tile_block_sum<NSEG, PY>(acc, red, lane, warp, nwarps);
-        target += nb;
-        const double pAp = grid_sum(blockA, P.partialA, P.bar, target, nb, &bcast);
+        const double pAp = grid_sum(blockA, P.partialA, P.bar, 2u * (unsigned int)j - 1u, nb, &bcast);
         const double alpha = rdotr / pAp;
         // ---- x += alpha p ; r -= alpha z, z = w(tau) -/+ D(tau+1) u ------------------------------------------------
         double accr = 0.0;
@@ -220,8 +224,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
                 pprev.a[rr][q] = pc.a[rr][q];
             }
         const double blockB = tile_block_sum<NSEG, PY>(accr, red, lane, warp, nwarps);
-        target += nb;
-        const double rrn = grid_sum(blockB, P.partialB, P.bar, target, nb, &bcast);
+        const double rrn = grid_sum(blockB, P.partialB, P.bar, 2u * (unsigned int)j, nb, &bcast);
         // ---- stop rule (src/IterativeSolvers.jl:287-301), identical on every CTA -----------------------------------
         eps = sqrt(rrn) / normb;
         const double lg = log(2.0 * eps0 / eps);
@@ -264,26 +267,228 @@ bool launch_persistent(elph_handle* h, PcgParams& P, int nwarps) {
     return true;
 }
 
+// ---- any lattice (Holstein): one time slice per CTA in shared memory ------------------------------------------------
+// Same iteration as above for arbitrary bond lists (honeycomb, triangular, chains, small test lattices -- config D):
+// the CTA keeps its two working slices D(tau) p(tau-1) and D(tau+1) p(tau) in shared memory together with the whole
+// bond list (sites + cosh/sinh, loaded once per solve), sweeps the colours there (one __syncthreads per colour, both
+// slices per pass), and holds x, r, p, D of its slice in registers (element i = tid + k*T).
+struct GcgParams {
+    const double* __restrict__ D;     // expnV [L][N]
+    double* __restrict__ x;
+    double* R;
+    double* P0;
+    double* P1;
+    double* partialA;
+    double* partialB;
+    unsigned int* bar;
+    CgScalars* S;
+    const int2* __restrict__ bonds;   // [Nb] colour-ordered
+    const double2* __restrict__ cs;   // [Nb]
+    const int* __restrict__ goff;     // [ngroups+1]
+    int N, L, Nb, ngroups;
+};
+
+__device__ __forceinline__ double block_sum_all(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    return t;   // same value on every thread
+}
+
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    __shared__ double red[32];
+    __shared__ double bcast;
+    const int N = P.N, L = P.L, nb = gridDim.x, T = blockDim.x, tid = threadIdx.x;
+    double* A1 = reinterpret_cast<double*>(gsm);
+    double* A2 = A1 + N;
+    double2* scs = reinterpret_cast<double2*>(A2 + N);   // 2N doubles = 16N bytes: 16-byte aligned
+    int2* sb = reinterpret_cast<int2*>(scs + P.Nb);
+    const int tau = blockIdx.x;
+    const int taum = (tau == 0) ? L - 1 : tau - 1;
+    const int taup = (tau == L - 1) ? 0 : tau + 1;
+    for (int b = tid; b < P.Nb; b += T) {
+        sb[b] = P.bonds[b];
+        scs[b] = P.cs[b];
+    }
+    double x[EPT], r[EPT], pprev[EPT], pc[EPT], Dc[EPT], Dn[EPT], pn[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int i = tid + k * T;
+        const bool in = i < N;
+        x[k] = in ? P.x[(size_t)tau * N + i] : 0.0;
+        r[k] = in ? P.R[(size_t)tau * N + i] : 0.0;
+        Dc[k] = in ? P.D[(size_t)tau * N + i] : 0.0;
+        Dn[k] = in ? P.D[(size_t)taup * N + i] : 0.0;
+        pprev[k] = 0.0;
+        pc[k] = 0.0;
+    }
+    const double normb = P.S->normb, eps0 = P.S->eps0, tol = P.S->tol, kappa_max = P.S->kappa_max;
+    const long long maxiter = P.S->maxiter;
+    double rdotr = P.S->rdotz, beta = 0.0, kmin = 0.0, eps = eps0;
+    long long j = 0;
+    double* Pold = P.P1;   // zeros on entry
+    double* Pnew = P.P0;
+    const bool wrap_c = (tau == 0), wrap_n = (taup == 0);
+    __syncthreads();
+
+    while (j < maxiter) {
+        ++j;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                // both neighbour slices are fetched together: one L2 round trip per iteration
+                const double pm = fma(beta, __ldcg(Pold + (size_t)taum * N + i), __ldcg(P.R + (size_t)taum * N + i));
+                pn[k] = fma(beta, __ldcg(Pold + (size_t)taup * N + i), __ldcg(P.R + (size_t)taup * N + i));
+                const double pcv = fma(beta, pprev[k], r[k]);
+                pc[k] = pcv;
+                Pnew[(size_t)tau * N + i] = pcv;
+                A1[i] = Dc[k] * pm;
+                A2[i] = Dn[k] * pcv;
+            }
+        }
+        __syncthreads();
+        for (int g = 0; g < P.ngroups; ++g) {   // K on both slices
+            const int hi = P.goff[g + 1];
+            for (int b = P.goff[g] + tid; b < hi; b += T) {
+                const int2 ij = sb[b];
+                const double2 c = scs[b];
+                const double a1 = A1[ij.x], a2 = A1[ij.y], b1 = A2[ij.x], b2 = A2[ij.y];
+                A1[ij.x] = c.x * a1 + c.y * a2;
+                A1[ij.y] = c.x * a2 + c.y * a1;
+                A2[ij.x] = c.x * b1 + c.y * b2;
+                A2[ij.y] = c.x * b2 + c.y * b1;
+            }
+            __syncthreads();
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                const double wc = wrap_c ? (pc[k] + A1[i]) : (pc[k] - A1[i]);
+                const double wn = wrap_n ? (pn[k] + A2[i]) : (pn[k] - A2[i]);
+                A1[i] = wc;
+                A2[i] = wn;
+                acc = fma(wc, wc, acc);
+            }
+        }
+        __syncthreads();
+        for (int g = P.ngroups - 1; g >= 0; --g) {   // K^T on w(tau+1)
+            const int hi = P.goff[g + 1];
+            for (int b = P.goff[g] + tid; b < hi; b += T) {
+                const int2 ij = sb[b];
+                const double2 c = scs[b];
+                const double b1 = A2[ij.x], b2 = A2[ij.y];
+                A2[ij.x] = c.x * b1 + c.y * b2;
+                A2[ij.y] = c.x * b2 + c.y * b1;
+            }
+            __syncthreads();
+        }
+        const double blockA = block_sum_all(acc, red);
+        const double pAp = grid_sum(blockA, P.partialA, P.bar, 2u * (unsigned int)j - 1u, nb, &bcast);
+        const double alpha = rdotr / pAp;
+        double accr = 0.0;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                const double du = Dn[k] * A2[i];
+                const double z = wrap_n ? (A1[i] + du) : (A1[i] - du);
+                x[k] = fma(alpha, pc[k], x[k]);
+                const double rv = fma(-alpha, z, r[k]);
+                r[k] = rv;
+                P.R[(size_t)tau * N + i] = rv;
+                accr = fma(rv, rv, accr);
+                pprev[k] = pc[k];
+            }
+        }
+        const double blockB = block_sum_all(accr, red);
+        const double rrn = grid_sum(blockB, P.partialB, P.bar, 2u * (unsigned int)j, nb, &bcast);
+        eps = sqrt(rrn) / normb;
+        const double lg = log(2.0 * eps0 / eps);
+        const double qq = 2.0 * (double)j / lg;
+        const double kap = qq * qq;
+        if (kap > kmin) kmin = kap;
+        if (eps < tol || kmin > kappa_max) break;
+        beta = rrn / rdotr;
+        rdotr = rrn;
+        double* tmp = Pold;
+        Pold = Pnew;
+        Pnew = tmp;
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int i = tid + k * T;
+        if (i < N) P.x[(size_t)tau * N + i] = x[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.S->iter = j;
+        P.S->eps = eps;
+        P.S->kappa_min = kmin;
+        P.S->done = 1;
+    }
+}
+
+template <int EPT, int MAXT>
+bool launch_generic(elph_handle* h, GcgParams& P, int threads, size_t smem) {
+    auto kern = cg_persistent_generic_kernel<EPT, MAXT>;
+    elph_enable_smem(h, kern);
+    int per_sm = 0;
+    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if ((long long)per_sm * h->sm_count < h->L) return false;
+    ELPH_CUDA(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned int), h->stream));
+    void* args[] = {&P};
+    ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L), dim3(threads), args, smem, h->stream));
+    h->launches++;
+    return true;
+}
+
+bool cg_persistent_generic(elph_handle* h, double* x_dev) {
+    if (h->model != ELPH_MODEL_HOLSTEIN || h->N > 4096 || h->partial_cap < 4 * h->L) return false;
+    const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2));
+    if (smem > h->smem_optin) return false;
+    GcgParams P;
+    P.D = h->d_D; P.x = x_dev; P.R = h->d_r; P.P0 = h->d_p[0]; P.P1 = h->d_p[1];
+    P.partialA = h->d_partial; P.partialB = h->d_partial + 2 * h->L; P.bar = h->d_bar; P.S = h->d_cg;
+    P.bonds = h->d_bonds; P.cs = h->d_cs; P.goff = h->d_goff;
+    P.N = h->N; P.L = h->L; P.Nb = h->Nb; P.ngroups = h->ngroups;
+    // one bond per thread and colour where possible: short dependent chains between the barriers
+    // measured (honeycomb L=32, N=2048): 512 threads x 4 elements beat 1024 x 2 (cheaper barriers, no spills)
+    const int threads = (h->N <= 64) ? 64 : ((h->N <= 256) ? 256 : 512);
+    const int ept = (h->N + threads - 1) / threads;
+    if (ept <= 1) return launch_generic<1, 512>(h, P, threads, smem);
+    if (ept <= 2) return launch_generic<2, 512>(h, P, threads, smem);
+    if (ept <= 4) return launch_generic<4, 512>(h, P, threads, smem);
+    return launch_generic<8, 512>(h, P, threads, smem);
+}
+
 }  // namespace
 
 // r0 (in h->d_r), the scalar block (normb, eps0, rdotz = r0.r0, ...) and zeros in h->d_p[1] must be set up by the caller
 // (elph_cg_device does that with the same kernels as the multi-launch path).  Returns false if not applicable.
 bool elph_cg_persistent(elph_handle* h, double* x_dev) {
     const bool ssh = (h->model == ELPH_MODEL_SSH);
-    if (!(ssh ? h->ssq.enabled : h->sq.enabled) || h->sq_disable || !h->use_persistent || h->sharded) return false;
-    if (h->L < 4) return false;
+    if (!h->use_persistent || h->sharded) return false;
     int dev_coop = 0;
     cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, h->device);
     if (!dev_coop) return false;
+    if (!(ssh ? h->ssq.enabled : h->sq.enabled) || h->sq_disable || h->L < 4) return cg_persistent_generic(h, x_dev);
     const int Lx = ssh ? h->ssq.Lx : h->sq.Lx, Ly = ssh ? h->ssq.Ly : h->sq.Ly;
     const int PY = (Lx == 32) ? 8 : 4;
     if (Ly % PY) return false;
     const int nwarps = Ly / PY;
     if (nwarps < 2 || nwarps > 32) return false;
-    if (h->partial_cap < 2 * h->L) return false;
+    if (h->partial_cap < 4 * h->L) return false;
     PcgParams P;
     P.D = h->d_D; P.tab = ssh ? h->ssq.d_tab : nullptr; P.x = x_dev; P.R = h->d_r; P.P0 = h->d_p[0]; P.P1 = h->d_p[1];
-    P.partialA = h->d_partial; P.partialB = h->d_partial + h->L; P.bar = h->d_bar; P.S = h->d_cg;
+    P.partialA = h->d_partial; P.partialB = h->d_partial + 2 * h->L; P.bar = h->d_bar; P.S = h->d_cg;
     P.L = h->L; P.Ly = Ly;
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
