@@ -56,15 +56,17 @@ __device__ __forceinline__ double grid_sum(double block_value, double* partial, 
         while (ld_acquire(bar) < target) {}
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        double s = 0.0;
-        for (int k = threadIdx.x; k < nb; k += 32) s += __ldcg(partial + k);
+    // read-back with the whole CTA: one L2 round trip (scripts/micro/barrier_bench.cu: a single warp striding over 200
+    // partials costs 1.35 us, the bare barrier 1.25 us), then a fixed-order tree: thread-strided, shuffle, warps in order
+    double s = 0.0;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s += __ldcg(partial + k);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) *bcast = s;
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) bcast[threadIdx.x >> 5] = s;
     __syncthreads();
-    return *bcast;
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += bcast[k];
+    return t;   // same bits on every thread of every CTA
 }
 
 template <int NSEG, int PY>
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
     constexpr int LX = 32 * NSEG;
     extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; SSH: + the tables of slices tau and tau+1
     __shared__ double red[32];
-    __shared__ double bcast;
+    __shared__ double bcast[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int L = P.L, N = LX * P.Ly, nb = gridDim.x;
     const int tau = blockIdx.x;
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
         }
         // ---- alpha ------------------------------------------------------------------------------------------------
         const double blockA = tile_block_sum<NSEG, PY>(acc, red, lane, warp, nwarps);
-        const double pAp = grid_sum(blockA, P.partialA, P.bar, 2u * (unsigned int)j - 1u, nb, &bcast);
+        const double pAp = grid_sum(blockA, P.partialA, P.bar, 2u * (unsigned int)j - 1u, nb, bcast);
         const double alpha = rdotr / pAp;
         // ---- x += alpha p ; r -= alpha z, z = w(tau) -/+ D(tau+1) u ------------------------------------------------
         double accr = 0.0;
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
                 pprev.a[rr][q] = pc.a[rr][q];
             }
         const double blockB = tile_block_sum<NSEG, PY>(accr, red, lane, warp, nwarps);
-        const double rrn = grid_sum(blockB, P.partialB, P.bar, 2u * (unsigned int)j, nb, &bcast);
+        const double rrn = grid_sum(blockB, P.partialB, P.bar, 2u * (unsigned int)j, nb, bcast);
         // ---- stop rule (src/IterativeSolvers.jl:287-301), identical on every CTA -----------------------------------
         eps = sqrt(rrn) / normb;
         const double lg = log(2.0 * eps0 / eps);
@@ -303,7 +305,7 @@ template <int EPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P) {
     extern __shared__ __align__(16) unsigned char gsm[];
     __shared__ double red[32];
-    __shared__ double bcast;
+    __shared__ double bcast[32];
     const int N = P.N, L = P.L, nb = gridDim.x, T = blockDim.x, tid = threadIdx.x;
     double* A1 = reinterpret_cast<double*>(gsm);
     double* A2 = A1 + N;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
             __syncthreads();
         }
         const double blockA = block_sum_all(acc, red);
-        const double pAp = grid_sum(blockA, P.partialA, P.bar, 2u * (unsigned int)j - 1u, nb, &bcast);
+        const double pAp = grid_sum(blockA, P.partialA, P.bar, 2u * (unsigned int)j - 1u, nb, bcast);
         const double alpha = rdotr / pAp;
         double accr = 0.0;
 #pragma unroll
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
             }
         }
         const double blockB = block_sum_all(accr, red);
-        const double rrn = grid_sum(blockB, P.partialB, P.bar, 2u * (unsigned int)j, nb, &bcast);
+        const double rrn = grid_sum(blockB, P.partialB, P.bar, 2u * (unsigned int)j, nb, bcast);
         eps = sqrt(rrn) / normb;
         const double lg = log(2.0 * eps0 / eps);
         const double qq = 2.0 * (double)j / lg;
