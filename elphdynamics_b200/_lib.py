@@ -110,6 +110,8 @@ def load() -> C.CDLL:
         "elph_kpm_get_coeff": (i32, [H, i64, dp]),
         "elph_cg_solve": (i32, [H, dp, dp, i32, dbl, i64, ip, dp]),
         "elph_solve": (i32, [H, dp, dp, i32, dbl, C.POINTER(SolveInfo)]),
+        "elph_solve_batch": (i32, [H, i64, dp, dp, i32, dbl, C.POINTER(SolveInfo)]),
+        "elph_dev_solve_batch": (i32, [H, i64, C.c_void_p, C.c_void_p, i32, dbl, C.POINTER(SolveInfo)]),
         "elph_tau_to_omega": (i32, [H, dp, dp]),
         "elph_omega_to_tau": (i32, [H, dp, dp]),
         "elph_fourier_accelerate": (i32, [H, dp, dp, dbl, i32]),

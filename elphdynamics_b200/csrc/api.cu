@@ -305,7 +305,8 @@ void destroy(elph_handle* h) {
                     h->d_primary_ph, h->d_grp_start, h->d_grp_members, h->d_tprime, h->d_va, h->d_vb, h->d_vc, h->d_b,
                     h->d_res, h->d_r, h->d_p[0], h->d_p[1], h->d_z, h->d_partial, h->d_ticket, h->d_bar, h->d_cg, h->d_scal,
                     h->d_dSdx, h->d_dSdx2, h->d_eta, h->d_dx, h->d_tmp, h->d_g, h->d_g2, h->d_Minv, h->d_nu2,
-                    h->d_twiddle, h->d_theta, h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stage[3]};
+                    h->d_twiddle, h->d_theta, h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stage[3],
+                    h->batch.x, h->batch.r, h->batch.p0, h->batch.p1, h->batch.partial, h->batch.bar, h->batch.S};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_cg) cudaFreeHost(h->h_cg);
@@ -649,6 +650,41 @@ int32_t elph_solve(elph_handle* h, const double* b, double* x, int32_t use_preco
         upload_vec(h, x, h->d_vb, h->N);
         elph_solve_device(h, h->d_va, h->d_vb, use_precond != 0, tol_power, info);
         download_vec(h, h->d_vb, x, h->N);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// nrhs right-hand sides on the current field (host buffers, nrhs consecutive vectors in host layout); X is output only:
+// the initial guesses are zero, as in update!(Gr, ...) (src/GreensFunctions.jl:219-225) and calc_O⁻¹Λϕ! (src/HMC.jl:855-885)
+int32_t elph_solve_batch(elph_handle* h, int64_t nrhs, const double* B, double* X, int32_t use_precond, double tol_power,
+                         elph_solve_info* infos) {
+    ENTER(h) {
+        ELPH_REQUIRE(nrhs >= 1 && nrhs <= 4096, ELPH_ERR_INVALID, "number of right-hand sides out of range");
+        const size_t n = (size_t)h->Ndim;
+        double* db = stage(h, 2, n * nrhs);
+        double* dx = stage(h, 3, n * nrhs);
+        upload_vec(h, B, db, h->N, nrhs);
+        std::vector<const double*> bl(nrhs);
+        std::vector<double*> xl(nrhs);
+        for (int64_t k = 0; k < nrhs; ++k) { bl[k] = db + k * n; xl[k] = dx + k * n; }
+        elph_solve_batch_device(h, (int)nrhs, bl.data(), xl.data(), use_precond != 0, tol_power, infos);
+        download_vec(h, dx, X, h->N, nrhs);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// same on device buffers in the engine layout: right-hand side k at b_dev + k*Ndim, solution k at x_dev + k*Ndim
+int32_t elph_dev_solve_batch(elph_handle* h, int64_t nrhs, const double* b_dev, double* x_dev, int32_t use_precond,
+                             double tol_power, elph_solve_info* infos) {
+    ENTER(h) {
+        ELPH_REQUIRE(nrhs >= 1 && nrhs <= 4096 && b_dev && x_dev, ELPH_ERR_INVALID, "bad batch arguments");
+        const size_t n = (size_t)h->Ndim;
+        std::vector<const double*> bl(nrhs);
+        std::vector<double*> xl(nrhs);
+        for (int64_t k = 0; k < nrhs; ++k) { bl[k] = b_dev + k * n; xl[k] = x_dev + k * n; }
+        elph_solve_batch_device(h, (int)nrhs, bl.data(), xl.data(), use_precond != 0, tol_power, infos);
         return ELPH_OK;
     }
     ELPH_CATCH(h)

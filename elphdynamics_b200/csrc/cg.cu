@@ -406,3 +406,73 @@ void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool 
     }
     if (info) *info = out;
 }
+
+// ---- batched solves: nrhs right-hand sides on the same field (the n_v measurement vectors of
+// update!(Gr, ...), src/GreensFunctions.jl:201-234, and the two pseudofermion flavours of HMC, src/HMC.jl:820-915) ------
+static void batch_reserve(elph_handle* h, int nrhs) {
+    auto& B = h->batch;
+    if (B.cap >= nrhs) return;
+    for (void* p : {(void*)B.x, (void*)B.r, (void*)B.p0, (void*)B.p1, (void*)B.partial, (void*)B.bar, (void*)B.S})
+        if (p) ELPH_CUDA(cudaFree(p));
+    const size_t n = (size_t)h->Ndim;
+    B.x = elph_dalloc<double>(n * nrhs);
+    B.r = elph_dalloc<double>(n * nrhs);
+    B.p0 = elph_dalloc<double>(n * nrhs);
+    B.p1 = elph_dalloc<double>(n * nrhs);
+    B.partial = elph_dalloc<double>((size_t)2 * h->L * nrhs);
+    B.bar = elph_dalloc<unsigned int>(nrhs);
+    B.S = elph_dalloc<CgScalars>(nrhs);
+    B.hS.resize(nrhs);
+    B.cap = nrhs;
+}
+
+void elph_solve_batch_device(elph_handle* h, int nrhs, const double* const* b_dev, double* const* x_dev, bool use_precond,
+                             double tol_power, elph_solve_info* infos) {
+    ELPH_REQUIRE(nrhs >= 1 && nrhs <= 4096, ELPH_ERR_INVALID, "number of right-hand sides out of range");
+    const double tol = (tol_power == 1.0) ? h->cg_tol : pow(h->cg_tol, tol_power);
+    const int64_t n = h->Ndim;
+    cudaStream_t st = h->stream;
+    bool done = false;
+    if (!(use_precond && h->kpm.configured) && nrhs > 1 && h->use_persistent && !h->sharded) {
+        batch_reserve(h, nrhs);
+        auto& B = h->batch;
+        const int vb = vec_blocks(h, n);
+        ELPH_CUDA(cudaMemsetAsync(B.x, 0, (size_t)n * nrhs * sizeof(double), st));   // x0 = 0 (every caller of ldiv! zeroes x)
+        ELPH_CUDA(cudaMemsetAsync(B.p1, 0, (size_t)n * nrhs * sizeof(double), st));
+        for (int k = 0; k < nrhs; ++k) {
+            // r0 = b - A 0 = b and the scalar block, with the same kernel as the single solve
+            cg_init_kernel<<<vb, kT, 0, st>>>(b_dev[k], B.x + (size_t)k * n, B.r + (size_t)k * n, n, h->d_partial, B.S + k,
+                                              h->d_ticket, tol, h->cg_kappa_max, (long long)h->cg_maxiter, 0);
+            ELPH_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        CgBatchBufs io;
+        io.x = B.x; io.R = B.r; io.P0 = B.p0; io.P1 = B.p1; io.partial = B.partial; io.bar = B.bar; io.S = B.S;
+        io.vstride = n; io.pstride = 2 * h->L;
+        if (elph_cg_persistent_batch(h, nrhs, io)) {
+            ELPH_CUDA(cudaMemcpyAsync(B.hS.data(), B.S, nrhs * sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
+            for (int k = 0; k < nrhs; ++k)
+                ELPH_CUDA(cudaMemcpyAsync(x_dev[k], B.x + (size_t)k * n, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            ELPH_CUDA(cudaStreamSynchronize(st));
+            for (int k = 0; k < nrhs; ++k) {
+                elph_solve_info out = {};
+                double resid = 0.0;
+                residual_check(h, b_dev[k], x_dev[k], &resid);
+                out.iters = out.pcg_iters = B.hS[k].iter;
+                out.residual = resid;
+                if (resid > sqrt(tol)) {
+                    out.flag = (out.iters == h->cg_maxiter) ? 1 : 2;
+                    ELPH_CUDA(cudaMemsetAsync(x_dev[k], 0, n * sizeof(double), st));
+                }
+                if (infos) infos[k] = out;
+            }
+            done = true;
+        }
+    }
+    if (!done) {
+        for (int k = 0; k < nrhs; ++k) {
+            ELPH_CUDA(cudaMemsetAsync(x_dev[k], 0, n * sizeof(double), st));
+            elph_solve_device(h, b_dev[k], x_dev[k], use_precond, tol_power, infos ? infos + k : nullptr);
+        }
+    }
+}

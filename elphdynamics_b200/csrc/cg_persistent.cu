@@ -15,6 +15,8 @@
 // Reductions are index-ordered, so the result is bit-reproducible and independent of CTA scheduling.
 #include "square_tiles.cuh"
 
+#include <algorithm>
+
 namespace {
 
 using namespace sqt;
@@ -31,8 +33,18 @@ struct PcgParams {
     unsigned int* bar;               // monotonically increasing arrival counter (zero on entry)
     CgScalars* S;                    // in: normb, eps0, rdotz (= r0.r0), tol, kappa_max, maxiter ; out: iter, eps, done
     int L, Ly;
+    long long vstride;               // batch: right-hand side k = blockIdx.y lives at x/R/P0/P1 + k*vstride,
+    int pstride;                     //        partialA/B + k*pstride, bar + k, S + k
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
+
+// batch offsets (same field names in both parameter structs)
+template <typename Params>
+__device__ __forceinline__ void select_rhs(Params& P) {
+    const size_t k = blockIdx.y;
+    P.x += k * P.vstride; P.R += k * P.vstride; P.P0 += k * P.vstride; P.P1 += k * P.vstride;
+    P.partialA += k * P.pstride; P.partialB += k * P.pstride; P.bar += k; P.S += k;
+}
 
 // Grid barrier fused with a sum over all CTAs; every CTA returns the same bits (fixed order: lane-strided, then tree).
 // One arrival counter (monotonically increasing, target = seq * nb) polled by one thread per CTA, then the partials are
@@ -81,12 +93,15 @@ __device__ __forceinline__ double tile_block_sum(double v, double* red, int lane
     return t;   // same value on every thread
 }
 
-template <int NSEG, int PY, int MAXT, bool SSH>
-__global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
+// MINB: resident CTAs per SM the register allocation must allow (3 x 128 threads -> 168 registers: 444 CTAs on 148 SMs,
+// i.e. two right-hand sides of config B at once)
+template <int NSEG, int PY, int MAXT, bool SSH, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) cg_persistent_kernel(PcgParams P) {
     constexpr int LX = 32 * NSEG;
     extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; SSH: + the tables of slices tau and tau+1
     __shared__ double red[32];
     __shared__ double bcast[32];
+    select_rhs(P);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int L = P.L, N = LX * P.Ly, nb = gridDim.x;
     const int tau = blockIdx.x;
@@ -252,21 +267,33 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_kernel(PcgParams P) {
     }
 }
 
-template <int NSEG, int PY, int MAXT, bool SSH>
-bool launch_persistent(elph_handle* h, PcgParams& P, int nwarps) {
+// Cooperative launch of nrhs independent solves, grid (L, g): as many right-hand sides at once as stay co-resident.
+template <typename Params, typename Kern>
+bool launch_groups(elph_handle* h, Kern kern, const Params& P, int threads, size_t smem, int nrhs) {
+    elph_enable_smem(h, kern);
+    int per_sm = 0;
+    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    const int cap = (int)std::min<long long>((long long)per_sm * h->sm_count / h->L, 65535);   // all CTAs of a group co-resident
+    if (cap < 1) return false;
+    for (int k0 = 0; k0 < nrhs; k0 += cap) {
+        const int g = std::min(cap, nrhs - k0);
+        Params Q = P;
+        Q.x += k0 * P.vstride; Q.R += k0 * P.vstride; Q.P0 += k0 * P.vstride; Q.P1 += k0 * P.vstride;
+        Q.partialA += (size_t)k0 * P.pstride; Q.partialB += (size_t)k0 * P.pstride; Q.bar += k0; Q.S += k0;
+        ELPH_CUDA(cudaMemsetAsync(Q.bar, 0, g * sizeof(unsigned int), h->stream));
+        void* args[] = {&Q};
+        ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L, g), dim3(threads), args, smem, h->stream));
+        h->launches++;
+    }
+    return true;
+}
+
+template <int NSEG, int PY, int MAXT, bool SSH, int MINB = 1>
+bool launch_persistent(elph_handle* h, const PcgParams& P, int nwarps, int nrhs) {
     constexpr int LX = 32 * NSEG;
     const size_t smem = 2ull * nwarps * 4 * LX * sizeof(double) + (SSH ? 2ull * 2 * h->N * sizeof(double2) : 0);
     if (smem > h->smem_optin) return false;
-    auto kern = cg_persistent_kernel<NSEG, PY, MAXT, SSH>;
-    elph_enable_smem(h, kern);
-    int per_sm = 0;
-    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem));
-    if ((long long)per_sm * h->sm_count < h->L) return false;   // all time slices must be co-resident
-    ELPH_CUDA(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned int), h->stream));
-    void* args[] = {&P};
-    ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L), dim3(nwarps * 32), args, smem, h->stream));
-    h->launches++;
-    return true;
+    return launch_groups(h, cg_persistent_kernel<NSEG, PY, MAXT, SSH, MINB>, P, nwarps * 32, smem, nrhs);
 }
 
 // ---- any lattice (Holstein): one time slice per CTA in shared memory ------------------------------------------------
@@ -288,6 +315,8 @@ struct GcgParams {
     const double2* __restrict__ cs;   // [Nb]
     const int* __restrict__ goff;     // [ngroups+1]
     int N, L, Nb, ngroups;
+    long long vstride;
+    int pstride;
 };
 
 __device__ __forceinline__ double block_sum_all(double v, double* red) {
@@ -306,6 +335,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
     extern __shared__ __align__(16) unsigned char gsm[];
     __shared__ double red[32];
     __shared__ double bcast[32];
+    select_rhs(P);
     const int N = P.N, L = P.L, nb = gridDim.x, T = blockDim.x, tid = threadIdx.x;
     double* A1 = reinterpret_cast<double*>(gsm);
     double* A2 = A1 + N;
@@ -438,67 +468,72 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
     }
 }
 
-template <int EPT, int MAXT>
-bool launch_generic(elph_handle* h, GcgParams& P, int threads, size_t smem) {
-    auto kern = cg_persistent_generic_kernel<EPT, MAXT>;
-    elph_enable_smem(h, kern);
-    int per_sm = 0;
-    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    if ((long long)per_sm * h->sm_count < h->L) return false;
-    ELPH_CUDA(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned int), h->stream));
-    void* args[] = {&P};
-    ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L), dim3(threads), args, smem, h->stream));
-    h->launches++;
-    return true;
+template <typename Params>
+void fill_io(Params& P, const CgBatchBufs& B, int L) {
+    P.x = B.x; P.R = B.R; P.P0 = B.P0; P.P1 = B.P1;
+    P.partialA = B.partial; P.partialB = B.partial + L; P.bar = B.bar; P.S = B.S;
+    P.vstride = B.vstride; P.pstride = B.pstride;
 }
 
-bool cg_persistent_generic(elph_handle* h, double* x_dev) {
-    if (h->model != ELPH_MODEL_HOLSTEIN || h->N > 4096 || h->partial_cap < 4 * h->L) return false;
+bool cg_persistent_generic(elph_handle* h, int nrhs, const CgBatchBufs& B) {
+    if (h->model != ELPH_MODEL_HOLSTEIN || h->N > 4096) return false;
     const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2));
     if (smem > h->smem_optin) return false;
     GcgParams P;
-    P.D = h->d_D; P.x = x_dev; P.R = h->d_r; P.P0 = h->d_p[0]; P.P1 = h->d_p[1];
-    P.partialA = h->d_partial; P.partialB = h->d_partial + 2 * h->L; P.bar = h->d_bar; P.S = h->d_cg;
+    fill_io(P, B, h->L);
+    P.D = h->d_D;
     P.bonds = h->d_bonds; P.cs = h->d_cs; P.goff = h->d_goff;
     P.N = h->N; P.L = h->L; P.Nb = h->Nb; P.ngroups = h->ngroups;
-    // one bond per thread and colour where possible: short dependent chains between the barriers
     // measured (honeycomb L=32, N=2048): 512 threads x 4 elements beat 1024 x 2 (cheaper barriers, no spills)
     const int threads = (h->N <= 64) ? 64 : ((h->N <= 256) ? 256 : 512);
     const int ept = (h->N + threads - 1) / threads;
-    if (ept <= 1) return launch_generic<1, 512>(h, P, threads, smem);
-    if (ept <= 2) return launch_generic<2, 512>(h, P, threads, smem);
-    if (ept <= 4) return launch_generic<4, 512>(h, P, threads, smem);
-    return launch_generic<8, 512>(h, P, threads, smem);
+    if (ept <= 1) return launch_groups(h, cg_persistent_generic_kernel<1, 512>, P, threads, smem, nrhs);
+    if (ept <= 2) return launch_groups(h, cg_persistent_generic_kernel<2, 512>, P, threads, smem, nrhs);
+    if (ept <= 4) return launch_groups(h, cg_persistent_generic_kernel<4, 512>, P, threads, smem, nrhs);
+    return launch_groups(h, cg_persistent_generic_kernel<8, 512>, P, threads, smem, nrhs);
 }
 
 }  // namespace
 
-// r0 (in h->d_r), the scalar block (normb, eps0, rdotz = r0.r0, ...) and zeros in h->d_p[1] must be set up by the caller
-// (elph_cg_device does that with the same kernels as the multi-launch path).  Returns false if not applicable.
-bool elph_cg_persistent(elph_handle* h, double* x_dev) {
+// nrhs independent unpreconditioned solves on the same field.  For right-hand side k the caller has set up r0 in
+// B.R + k*vstride, the initial guess in B.x + k*vstride, zeros in B.P1 + k*vstride and the scalar block B.S[k]
+// (normb, eps0, rdotz = r0.r0, tol, ...) with cg_init_kernel.  B.partial: 2L doubles per right-hand side (pstride),
+// B.bar: one counter per right-hand side.  Returns false if the persistent kernels do not apply to this handle.
+bool elph_cg_persistent_batch(elph_handle* h, int nrhs, const CgBatchBufs& B) {
     const bool ssh = (h->model == ELPH_MODEL_SSH);
-    if (!h->use_persistent || h->sharded) return false;
+    if (!h->use_persistent || h->sharded || nrhs < 1) return false;
     int dev_coop = 0;
     cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, h->device);
     if (!dev_coop) return false;
-    if (!(ssh ? h->ssq.enabled : h->sq.enabled) || h->sq_disable || h->L < 4) return cg_persistent_generic(h, x_dev);
+    if (!(ssh ? h->ssq.enabled : h->sq.enabled) || h->sq_disable || h->L < 4) return cg_persistent_generic(h, nrhs, B);
     const int Lx = ssh ? h->ssq.Lx : h->sq.Lx, Ly = ssh ? h->ssq.Ly : h->sq.Ly;
     const int PY = (Lx == 32) ? 8 : 4;
     if (Ly % PY) return false;
     const int nwarps = Ly / PY;
     if (nwarps < 2 || nwarps > 32) return false;
-    if (h->partial_cap < 4 * h->L) return false;
     PcgParams P;
-    P.D = h->d_D; P.tab = ssh ? h->ssq.d_tab : nullptr; P.x = x_dev; P.R = h->d_r; P.P0 = h->d_p[0]; P.P1 = h->d_p[1];
-    P.partialA = h->d_partial; P.partialB = h->d_partial + 2 * h->L; P.bar = h->d_bar; P.S = h->d_cg;
+    fill_io(P, B, h->L);
+    P.D = h->d_D; P.tab = ssh ? h->ssq.d_tab : nullptr;
     P.L = h->L; P.Ly = Ly;
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
     if (ssh) {
-        if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, true>(h, P, nwarps);
+        if (Lx == 32 && PY == 8 && nwarps * 32 <= 128) return launch_persistent<1, 8, 128, true, 3>(h, P, nwarps, nrhs);
+        if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, true>(h, P, nwarps, nrhs);
         return false;
     }
-    if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, false>(h, P, nwarps);
-    if (Lx == 64 && PY == 4 && nwarps * 32 <= 512) return launch_persistent<2, 4, 512, false>(h, P, nwarps);
+    if (Lx == 32 && PY == 8 && nwarps * 32 <= 128) return launch_persistent<1, 8, 128, false, 3>(h, P, nwarps, nrhs);
+    if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, false>(h, P, nwarps, nrhs);
+    if (Lx == 64 && PY == 4 && nwarps * 32 <= 512) return launch_persistent<2, 4, 512, false>(h, P, nwarps, nrhs);
     return false;
+}
+
+// single solve on the handle's own CG buffers (elph_cg_device)
+bool elph_cg_persistent(elph_handle* h, double* x_dev) {
+    if (h->partial_cap < 2 * h->L) return false;
+    CgBatchBufs B;
+    B.x = x_dev; B.R = h->d_r; B.P0 = h->d_p[0]; B.P1 = h->d_p[1];
+    B.partial = h->d_partial; B.bar = h->d_bar; B.S = h->d_cg;
+    B.vstride = 0; B.pstride = 0;
+    return elph_cg_persistent_batch(h, 1, B);
 }

@@ -241,6 +241,18 @@ struct elph_handle {
         int* d_slot = nullptr;        // [Nb] column -> dir*N + origin site
         double2* d_tab = nullptr;     // [L][2][N] (cosh, sinh)
     } ssq;
+    // batched solves (elph_solve_batch_device): grow-only buffers for `cap` right-hand sides
+    struct {
+        int cap = 0;
+        double* x = nullptr;
+        double* r = nullptr;
+        double* p0 = nullptr;
+        double* p1 = nullptr;
+        double* partial = nullptr;
+        unsigned int* bar = nullptr;
+        CgScalars* S = nullptr;
+        std::vector<CgScalars> hS;
+    } batch;
     // tau-sharding (multi-GPU): this handle owns global slices [shard_tau0, shard_tau0 + L) of shard_Lglob
     bool sharded = false;
     int shard_tau0 = 0, shard_Lglob = 0;
@@ -298,6 +310,23 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
 void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool use_precond, double tol_power,
                        elph_solve_info* info);
 bool elph_cg_persistent(elph_handle* h, double* x_dev);   // cg_persistent.cu
+// buffers of nrhs independent solves for the persistent kernels (right-hand side k at + k*vstride / k*pstride / k)
+struct CgBatchBufs {
+    double* x = nullptr;
+    double* R = nullptr;
+    double* P0 = nullptr;
+    double* P1 = nullptr;
+    double* partial = nullptr;      // 2L doubles per right-hand side
+    unsigned int* bar = nullptr;
+    CgScalars* S = nullptr;
+    long long vstride = 0;
+    int pstride = 0;
+};
+bool elph_cg_persistent_batch(elph_handle* h, int nrhs, const CgBatchBufs& B);
+// nrhs solves A x_k = b_k on the same field with zero initial guesses (device pointers, one per right-hand side);
+// unpreconditioned solves run together in the persistent kernels, everything else falls back to a loop of elph_solve_device
+void elph_solve_batch_device(elph_handle* h, int nrhs, const double* const* b_dev, double* const* x_dev, bool use_precond,
+                             double tol_power, elph_solve_info* infos);
 // reductions: out[0] = sum a*b  (deterministic two-stage); blocking read helpers
 void elph_dot_async(elph_handle* h, const double* a, const double* b, int64_t n, double* d_out);
 void elph_diffnorm2_async(elph_handle* h, const double* a, const double* b, int64_t n, double* d_out2);  // |a-b|^2, |b|^2

@@ -160,6 +160,25 @@ void elph_hmc_calc_Oinv_dev(elph_handle* h, bool use_precond, const double* arno
     update_Lam(h);
     lam_apply(h, S.Lphip, S.phip, 0);
     lam_apply(h, S.Lphim, S.phim, 0);
+    if (!(use_precond && h->kpm.configured) && h->use_persistent && !h->sharded) {
+        // both flavours in one batched launch of the persistent CG (same matrix, independent right-hand sides).  The
+        // reference solves "-" only if "+" succeeded and otherwise leaves O^-1 Lambda phi_- untouched: "-" goes to scratch.
+        const double* bl[2] = {S.Lphip, S.Lphim};
+        double* xl[2] = {S.Op, h->d_vc};
+        elph_solve_info inf[2] = {};
+        elph_solve_batch_device(h, 2, bl, xl, false, power, inf);
+        int64_t tot2 = inf[0].iters;
+        int fl2 = inf[0].flag;
+        if (fl2 == 0) {
+            ELPH_CUDA(cudaMemcpyAsync(S.Om, h->d_vc, h->Ndim * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            tot2 += inf[1].iters;
+            fl2 = inf[1].flag;
+        }
+        if (fl2 == 0) tot2 = (tot2 + 1) / 2;  // cld(iters, 2)
+        *iters = tot2;
+        *flag = fl2;
+        return;
+    }
     elph_solve_info info = {};
     int64_t tot = 0;
     ELPH_CUDA(cudaMemsetAsync(S.Op, 0, h->Ndim * sizeof(double), h->stream));

@@ -256,6 +256,22 @@ def ldiv_(x, model, b, P=None, tol_power: float = 1.0):
     return info.astuple()
 
 
+def ldiv_batch_(X, model, B, P=None, tol_power: float = 1.0):
+    """``fill!(X, 0); ldiv!(X[:,k], model, B[:,k][, P])`` for every column k in one call -- the measurement solves of
+    ``update!(Gr, model, P)`` (src/GreensFunctions.jl:201-234).  ``B``, ``X``: arrays of shape (nrhs, Ndim).
+    Returns a list of ``(iters, residual_error, flag)``."""
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    if B.ndim != 2 or B.shape[1] != model.Ndim:
+        raise ValueError(f"B must have shape (nrhs, {model.Ndim})")
+    if not (isinstance(X, np.ndarray) and X.dtype == np.float64 and X.flags.c_contiguous and X.shape == B.shape):
+        raise ValueError("X must be a C-contiguous float64 array of the same shape as B")
+    nrhs = B.shape[0]
+    infos = (SolveInfo * nrhs)()
+    use_p = 0 if (P is None or getattr(P, "is_identity", False)) else 1
+    model._call("elph_solve_batch", nrhs, ptr(B), ptr(X), use_p, float(tol_power), infos)
+    return [infos[k].astuple() for k in range(nrhs)]
+
+
 def solve_(x, model, b, P=None, tol: float = 0.0, maxiter: int = 0):
     """Raw ``solve!(x, A, b, cg[, P])`` (src/IterativeSolvers.jl:153, :239): returns the iteration count."""
     it = C.c_int64()

@@ -203,6 +203,15 @@ int32_t elph_cg_solve(elph_handle* h, const double* b, double* x, int32_t use_pr
  * src/HMC.jl:838-842); pass 1.0 otherwise. */
 int32_t elph_solve(elph_handle* h, const double* b, double* x, int32_t use_precond, double tol_power,
                    elph_solve_info* info);
+/* nrhs solves on the same field in one call: the n_v measurement vectors of update!(Gr,model,P)
+ * (src/GreensFunctions.jl:201-234: fill!(M^-1 R,0); ldiv! per random vector) and the two pseudofermion flavours of
+ * calc_O^-1Lambda-phi! (src/HMC.jl:855-885).  B, X: nrhs consecutive N*Ltau vectors (host layout).  X is output only --
+ * the initial guesses are zero, as at those call sites.  infos[k] as elph_solve's info for right-hand side k.
+ * Unpreconditioned solves run simultaneously (one persistent cooperative CG kernel, a barrier counter per right-hand
+ * side); with use_precond != 0 the call is a loop of elph_solve.  Iteration counts and results per right-hand side are
+ * those of elph_solve on a zero initial guess. */
+int32_t elph_solve_batch(elph_handle* h, int64_t nrhs, const double* B, double* X, int32_t use_precond, double tol_power,
+                         elph_solve_info* infos);
 
 /* ------------------------------------------------------------------ transforms */
 /* tau_to_omega!(vout,fft,vin) src/TimeFreqFFTs.jl:55; vout complex (re,im interleaved), Ndim entries */
@@ -296,6 +305,9 @@ int32_t elph_dev_ptr_expnV(elph_handle* h, double** expnV_dev);
 /* CG on device pointers; asynchronous until the result scalars are read (blocks). */
 int32_t elph_dev_cg_solve(elph_handle* h, const double* b_dev, double* x_dev, int32_t use_precond, double tol,
                           int64_t maxiter, int64_t* iters, double* eps);
+/* elph_solve_batch on device buffers (engine layout): right-hand side k at b_dev + k*N*Ltau, solution at x_dev + k*N*Ltau */
+int32_t elph_dev_solve_batch(elph_handle* h, int64_t nrhs, const double* b_dev, double* x_dev, int32_t use_precond,
+                             double tol_power, elph_solve_info* infos);
 /* ldiv!(vout,P,vin) and fourier_accelerate! on device pointers (engine layout), asynchronous */
 int32_t elph_dev_kpm_apply(elph_handle* h, const double* vin_dev, double* vout_dev);
 int32_t elph_dev_fourier_accelerate(elph_handle* h, const double* vin_dev, double* vout_dev, double power, int32_t use_mass);

@@ -53,6 +53,19 @@ for label, keys in (("persistent", {5: 1}), ("graph", {5: 0, 3: 1}), ("launches"
     print(f"CG {label:10s}: {it.value} iters, {dt * 1e3:.3f} ms, {dt / max(it.value, 1) * 1e6:.2f} us/iter, eps {eps.value:.2e}")
 lib.elph_set_tuning(h, 5, 1)
 lib.elph_set_tuning(h, 3, 1)
+from elphdynamics_b200._lib import SolveInfo
+for nrhs in (1, 2, 10):
+    Bd = torch.randn(nrhs, n, dtype=torch.float64, device="cuda")
+    Xd = torch.zeros_like(Bd)
+    infos = (SolveInfo * nrhs)()
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lib.elph_dev_solve_batch(h, nrhs, Bd.data_ptr(), Xd.data_ptr(), 0, 1.0, infos)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    its = [infos[k].iters for k in range(nrhs)]
+    print(f"solve_batch nrhs={nrhs:2d}: {dt * 1e3:.3f} ms, {dt / nrhs * 1e3:.3f} ms per solve, iters {its}")
 
 fa = E.FourierAccelerator(m)
 E.update_M_(fa, m, 0.0, 10.0, 1.0, 0.0)
