@@ -314,6 +314,17 @@ def main():
         it, res, flag = E.ldiv_(xs, em, b)
         dt_cg = time.perf_counter() - t0
         extra["cg"] = {"iters": it, "residual": res, "flag": flag, "seconds": dt_cg, "iters_per_s": it / dt_cg}
+        # measurement solves: n_v = 10 right-hand sides on one field in one call (host buffers through the C ABI)
+        Bm = rng.normal(size=(10, n))
+        Xm = np.zeros_like(Bm)
+        E.ldiv_batch_(Xm, em, Bm)
+        t0 = time.perf_counter()
+        infos = E.ldiv_batch_(Xm, em, Bm)
+        dt_b = time.perf_counter() - t0
+        extra["solve_batch_10rhs"] = {"seconds": dt_b, "solves_per_s": 10 / dt_b, "iters": [i[0] for i in infos],
+                                      "cg_iters_per_s": sum(i[0] for i in infos) / dt_b,
+                                      "note": "elph_solve_batch: right-hand sides share one persistent cooperative CG launch "
+                                              "(two at a time fit the machine at 32x32xL200)"}
         P = E.SymmetricKPMPreconditioner(em)
         kinfo = E.setup_(P, rng.normal(size=2 * Nsites))
         for _ in range(10):

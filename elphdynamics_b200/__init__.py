@@ -9,7 +9,7 @@ from . import _lib
 from .lattices import (Lattice, UnitCell, assemble_checkerboard, calc_neighbor_table, checkerboard_groups,
                        checkerboard_order, sorted_neighbor_table_perm)
 from .models import (ConjugateGradient, HolsteinModel, I, Identity, SSHModel, SymmetricKPMPreconditioner, kpm_ldiv_, ldiv_, ldiv_batch_, mul_,
-                     mulM_, mulMT_, mulMTM_, muldMdx_, setup_, solve_, update_model_)
+                     mulM_, mulMT_, mulMTM_, muldMdx_, setup_, solve_, update_Gr_, update_model_)
 from .dynamics import (EulerDynamics, FourierAccelerator, HeunsDynamics, RungeKuttaDynamics, TimeFreqFFT, calc_dSbdx_,
                        calc_dSdx_, calc_Sb, evolve_, fourier_accelerate_, omega_to_tau_, tau_to_omega_, update_M_, update_Q_)
 from . import workloads

@@ -111,6 +111,7 @@ def load() -> C.CDLL:
         "elph_cg_solve": (i32, [H, dp, dp, i32, dbl, i64, ip, dp]),
         "elph_solve": (i32, [H, dp, dp, i32, dbl, C.POINTER(SolveInfo)]),
         "elph_solve_batch": (i32, [H, i64, dp, dp, i32, dbl, C.POINTER(SolveInfo)]),
+        "elph_Minv_batch": (i32, [H, i64, dp, dp, i32, C.POINTER(SolveInfo)]),
         "elph_dev_solve_batch": (i32, [H, i64, C.c_void_p, C.c_void_p, i32, dbl, C.POINTER(SolveInfo)]),
         "elph_tau_to_omega": (i32, [H, dp, dp]),
         "elph_omega_to_tau": (i32, [H, dp, dp]),

@@ -675,6 +675,29 @@ int32_t elph_solve_batch(elph_handle* h, int64_t nrhs, const double* B, double* 
     ELPH_CATCH(h)
 }
 
+// update!(Gr, model, P) (src/GreensFunctions.jl:201-234) for all n_v random vectors at once:
+// MinvR[:,k] = (M^T M)^-1 M^T R[:,k], the random vectors R drawn by the caller.  setup!(P) is the caller's (elph_kpm_setup).
+int32_t elph_Minv_batch(elph_handle* h, int64_t nrhs, const double* R, double* MinvR, int32_t use_precond,
+                        elph_solve_info* infos) {
+    ENTER(h) {
+        ELPH_REQUIRE(nrhs >= 1 && nrhs <= 4096, ELPH_ERR_INVALID, "number of right-hand sides out of range");
+        const size_t n = (size_t)h->Ndim;
+        double* dr = stage(h, 2, n * nrhs);
+        double* dx = stage(h, 3, n * nrhs);
+        upload_vec(h, R, dx, h->N, nrhs);
+        MatvecArgs a;   // b_k = M^T r_k, one batched launch
+        a.v = dx; a.y = dr; a.nbatch = nrhs; a.v_stride = (int64_t)n; a.y_stride = (int64_t)n;
+        elph_launch_matvec(h, MODE_MT, a);
+        std::vector<const double*> bl(nrhs);
+        std::vector<double*> xl(nrhs);
+        for (int64_t k = 0; k < nrhs; ++k) { bl[k] = dr + k * n; xl[k] = dx + k * n; }
+        elph_solve_batch_device(h, (int)nrhs, bl.data(), xl.data(), use_precond != 0, 1.0, infos);
+        download_vec(h, dx, MinvR, h->N, nrhs);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
 // same on device buffers in the engine layout: right-hand side k at b_dev + k*Ndim, solution k at x_dev + k*Ndim
 int32_t elph_dev_solve_batch(elph_handle* h, int64_t nrhs, const double* b_dev, double* x_dev, int32_t use_precond,
                              double tol_power, elph_solve_info* infos) {

@@ -272,6 +272,21 @@ def ldiv_batch_(X, model, B, P=None, tol_power: float = 1.0):
     return [infos[k].astuple() for k in range(nrhs)]
 
 
+def update_Gr_(MinvR, model, R, P=None):
+    """The solves of ``update!(Gr, model, P)`` (src/GreensFunctions.jl:201-234) for all random vectors at once:
+    ``MinvR[k] = (MᵀM)⁻¹ Mᵀ R[k]``.  ``R`` (shape (nv, Ndim)) is drawn by the caller; ``setup_(P)`` is called before."""
+    R = np.ascontiguousarray(R, dtype=np.float64)
+    if R.ndim != 2 or R.shape[1] != model.Ndim:
+        raise ValueError(f"R must have shape (nv, {model.Ndim})")
+    if not (isinstance(MinvR, np.ndarray) and MinvR.dtype == np.float64 and MinvR.flags.c_contiguous and MinvR.shape == R.shape):
+        raise ValueError("MinvR must be a C-contiguous float64 array of the same shape as R")
+    nv = R.shape[0]
+    infos = (SolveInfo * nv)()
+    use_p = 0 if (P is None or getattr(P, "is_identity", False)) else 1
+    model._call("elph_Minv_batch", nv, ptr(R), ptr(MinvR), use_p, infos)
+    return [infos[k].astuple() for k in range(nv)]
+
+
 def solve_(x, model, b, P=None, tol: float = 0.0, maxiter: int = 0):
     """Raw ``solve!(x, A, b, cg[, P])`` (src/IterativeSolvers.jl:153, :239): returns the iteration count."""
     it = C.c_int64()

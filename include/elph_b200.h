@@ -212,6 +212,11 @@ int32_t elph_solve(elph_handle* h, const double* b, double* x, int32_t use_preco
  * those of elph_solve on a zero initial guess. */
 int32_t elph_solve_batch(elph_handle* h, int64_t nrhs, const double* B, double* X, int32_t use_precond, double tol_power,
                          elph_solve_info* infos);
+/* update!(Gr,model,P) src/GreensFunctions.jl:201-234 for all n_v random vectors in one call:
+ * MinvR[:,k] = (M^T M)^-1 M^T R[:,k]  (mulMT! into scratch, fill!(M^-1 r,0), ldiv!).  R is drawn by the caller
+ * (randn!(model.rng, r1), in column order); setup!(P) stays a separate call (elph_kpm_setup) made before this one. */
+int32_t elph_Minv_batch(elph_handle* h, int64_t nrhs, const double* R, double* MinvR, int32_t use_precond,
+                        elph_solve_info* infos);
 
 /* ------------------------------------------------------------------ transforms */
 /* tau_to_omega!(vout,fft,vin) src/TimeFreqFFTs.jl:55; vout complex (re,im interleaved), Ndim entries */

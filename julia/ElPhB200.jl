@@ -101,6 +101,16 @@ function ldiv!(x::Vector{Float64}, g::B200Model, b::Vector{Float64}, P=I; maxite
     info[].iters, info[].residual, Int(info[].flag)
 end
 
+# --- measurement solves: update!(Gr, model, P) src/GreensFunctions.jl:201-234, all n_v vectors in one call -------
+function update!(est::EstimateGreensFunction, g::B200Model, P=I)
+    P isa B200KPM && setup!(P)
+    randn!(g.host.rng, est.R)                          # column k = the k-th randn!(model.rng, r1) of the reference loop
+    infos = Vector{SolveInfo}(undef, est.nᵥ)
+    check(ccall((:elph_Minv_batch, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{SolveInfo}),
+                g.h, est.nᵥ, est.R, est.M⁻¹R, P isa B200KPM ? 1 : 0, infos), g.h)
+    nothing
+end
+
 # --- dynamics: src/LangevinDynamics.jl:81,162,272 ; noise drawn here in the reference's order ---------------------
 method(::EulerDynamics) = Int32(1); method(::RungeKuttaDynamics) = Int32(2); method(::HeunsDynamics) = Int32(3)
 function attach!(g::B200Model, fa::FourierAccelerator)   # after update_Q!/update_M! (ProcessInputFile.jl:516-535)

@@ -82,3 +82,23 @@ def test_batch_argument_checks():
     with pytest.raises(E._lib.ElphError):
         em._call("elph_solve_batch", 0, None, None, 0, 1.0, None)
     em.close()
+
+
+def test_update_Gr_solves(pair):
+    """MinvR[k] = M^-1 R[k] (src/GreensFunctions.jl:201-234): check M MinvR = R and the per-vector oracle solve."""
+    import elphdynamics_b200 as E
+    from oracle.solvers import ConjugateGradient, ldiv
+    om, em, rng = pair
+    R = rng.normal(size=(4, om.Ndim))
+    MinvR = np.empty_like(R)
+    infos = E.update_Gr_(MinvR, em, R)
+    assert all(i[2] == 0 for i in infos)
+    y = np.zeros(om.Ndim)
+    for k in range(4):
+        om.mulM(y, MinvR[k])
+        assert relerr(y, R[k]) <= 50 * np.sqrt(om.tol)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, R[1])
+    xo = np.zeros(om.Ndim)
+    ito, _, flo = ldiv(xo, om, b, ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter))
+    assert flo == 0 and abs(infos[1][0] - ito) <= 2 and relerr(MinvR[1], xo) <= 1e-3
