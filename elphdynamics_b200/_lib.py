@@ -111,6 +111,9 @@ def load() -> C.CDLL:
         "elph_cg_solve": (i32, [H, dp, dp, i32, dbl, i64, ip, dp]),
         "elph_solve": (i32, [H, dp, dp, i32, dbl, C.POINTER(SolveInfo)]),
         "elph_solve_batch": (i32, [H, i64, dp, dp, i32, dbl, C.POINTER(SolveInfo)]),
+        "elph_shard_p2p_export": (i32, [H, i32, i32, C.c_void_p]),
+        "elph_shard_p2p_open": (i32, [H, C.c_void_p, C.c_void_p]),
+        "elph_dev_shard_cg_p2p": (i32, [H, C.c_void_p, C.c_void_p, dbl, i64, ip, dp]),
         "elph_Minv_batch": (i32, [H, i64, dp, dp, i32, C.POINTER(SolveInfo)]),
         "elph_dev_solve_batch": (i32, [H, i64, C.c_void_p, C.c_void_p, i32, dbl, C.POINTER(SolveInfo)]),
         "elph_tau_to_omega": (i32, [H, dp, dp]),

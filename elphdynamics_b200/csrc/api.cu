@@ -296,6 +296,7 @@ void destroy(elph_handle* h) {
         cudaStreamDestroy(h->pipe.s_in);
         cudaStreamDestroy(h->pipe.s_out);
     }
+    elph_shard_p2p_close_impl(h);
     if (h->d_D_alloc) {  // sharded: d_D points one slice into this allocation
         cudaFree(h->d_D_alloc);
         h->d_D = nullptr;
@@ -975,6 +976,35 @@ int32_t elph_dev_shard_matvec(elph_handle* h, int32_t mode, const double* v_own,
         a.y = y_own;
         a.open = true;
         elph_launch_matvec(h, (MatvecMode)mode, a);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// ---- peer-memory CG over NVLink (cg_p2p.cu): one process per GPU, arenas shared through CUDA IPC ------------------
+int32_t elph_shard_p2p_export(elph_handle* h, int32_t rank, int32_t world, unsigned char* ipc_handle_out) {
+    ENTER(h) {
+        ELPH_REQUIRE(ipc_handle_out, ELPH_ERR_INVALID, "null output");
+        elph_shard_p2p_export_impl(h, rank, world, ipc_handle_out);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_shard_p2p_open(elph_handle* h, const unsigned char* ipc_handles, const int64_t* slab_lengths) {
+    ENTER(h) {
+        elph_shard_p2p_open_impl(h, ipc_handles, slab_lengths);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_shard_cg_p2p(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter, int64_t* iters,
+                              double* eps) {
+    ENTER(h) {
+        ELPH_REQUIRE(b_own && x_own, ELPH_ERR_INVALID, "null device pointer");
+        ELPH_REQUIRE(elph_shard_cg_p2p_impl(h, b_own, x_own, tol, maxiter, iters, eps), ELPH_ERR_UNSUPPORTED,
+                     "peer-memory CG: the slab's time slices are not all co-resident on this GPU (or unsupported lattice)");
         return ELPH_OK;
     }
     ELPH_CATCH(h)

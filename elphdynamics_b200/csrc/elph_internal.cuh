@@ -256,6 +256,15 @@ struct elph_handle {
     // tau-sharding (multi-GPU): this handle owns global slices [shard_tau0, shard_tau0 + L) of shard_Lglob
     bool sharded = false;
     int shard_tau0 = 0, shard_Lglob = 0;
+    // peer-memory CG (cg_p2p.cu): arena exported over CUDA IPC, the other ranks' arenas opened in rank order
+    struct {
+        void* arena = nullptr;
+        std::vector<void*> peer;
+        std::vector<int64_t> peer_L;
+        int rank = 0, world = 1, Lmax = 0;
+        unsigned int seq = 0;       // sequence number of the last cross-GPU barrier executed
+        bool opened = false;
+    } p2p;
     double* d_D_alloc = nullptr;   // sharded: d_D points one slice into this allocation (halo slices around it)
     double* d_x_alloc = nullptr;   // sharded: same for the phonon field (the force needs no x halo; kept symmetric)
     bool sq_disable = false;
@@ -310,6 +319,12 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
 void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool use_precond, double tol_power,
                        elph_solve_info* info);
 bool elph_cg_persistent(elph_handle* h, double* x_dev);   // cg_persistent.cu
+// cg_p2p.cu
+void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned char* handle_out);
+void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, const int64_t* slab_lengths);
+void elph_shard_p2p_close_impl(elph_handle* h);
+bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter, int64_t* iters,
+                            double* eps);
 // buffers of nrhs independent solves for the persistent kernels (right-hand side k at + k*vstride / k*pstride / k)
 struct CgBatchBufs {
     double* x = nullptr;

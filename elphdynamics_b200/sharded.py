@@ -133,6 +133,30 @@ class CudaSlabBackend:
         self._check(self.lib.elph_dev_dot(self.h, self.own_ptr(a), self.own_ptr(b), self.lloc * self.N, self.scal.data_ptr()))
         return self.scal[:1].clone()
 
+    # ---- peer-memory CG (csrc/cg_p2p.cu): arenas shared through CUDA IPC, collectives inside the kernel --------------
+    def p2p_setup(self, comm: "RingComm"):
+        """Export this rank's arena, all-gather the IPC handles and slab lengths over torch.distributed, open the peers'."""
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.elph_shard_p2p_export(self.h, comm.rank, comm.world, buf))
+        mine = (bytes(buf), int(self.lloc))
+        if comm.world > 1:
+            gathered = [None] * comm.world
+            dist.all_gather_object(gathered, mine, group=comm.group)
+        else:
+            gathered = [mine]
+        handles = (C.c_ubyte * (64 * comm.world)).from_buffer_copy(b"".join(g[0] for g in gathered))
+        lengths = (C.c_int64 * comm.world)(*[g[1] for g in gathered])
+        self._check(self.lib.elph_shard_p2p_open(self.h, handles, lengths))
+        self._p2p_ready = True
+
+    def cg_p2p(self, x, b, tol: float = 0.0, maxiter: int = 0):
+        """Whole CG solve (x0 = 0) in one persistent kernel per GPU; returns (iters, eps).  x, b: halo'd slab tensors."""
+        it, eps = C.c_int64(), C.c_double()
+        self._check(self.lib.elph_dev_shard_cg_p2p(self.h, self.own_ptr(b), self.own_ptr(x), float(tol), int(maxiter),
+                                                   C.byref(it), C.byref(eps)))
+        return int(it.value), float(eps.value)
+
     # ---- pieces needed by the sharded Langevin step -------------------------------------------------------------
     def _wrap(self, ptr, shape):
         torch = self.torch

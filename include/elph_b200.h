@@ -289,6 +289,18 @@ int32_t elph_dev_mulMTM_replicas(elph_handle* h, int64_t nrep, const double* exp
 int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob);
 int32_t elph_dev_shard_matvec(elph_handle* h, int32_t mode, const double* v_own, double* y_own);
 int32_t elph_dev_shard_muldMdx(elph_handle* h, const double* u_own, const double* v_own, double* out, double scale);
+/* Peer-memory CG of the tau-sharded lattice: solve!(x,A,b,cg) src/IterativeSolvers.jl:239-314 with x0 = 0 as ONE
+ * persistent cooperative kernel per GPU; the halo of p and the two scalar all-reduces of every iteration travel over
+ * NVLink peer memory inside the kernel (no NCCL call, no launch per iteration).  Set-up, once per handle after
+ * elph_set_shard: every rank calls elph_shard_p2p_export (allocates the exchange arena, returns its 64-byte CUDA IPC
+ * handle), the caller all-gathers the handles and the slab lengths in rank order (torch.distributed / MPI / files) and
+ * passes them to elph_shard_p2p_open.  Then every rank of the ring calls elph_dev_shard_cg_p2p with its own slices of
+ * b and x ([Ltau][Nsites], engine layout); all ranks return the same iteration count and eps.  ELPH_ERR_UNSUPPORTED if
+ * the slab's time slices are not all co-resident on the GPU; ELPH_ERR_STATE if a peer never reached a barrier. */
+int32_t elph_shard_p2p_export(elph_handle* h, int32_t rank, int32_t world, unsigned char* ipc_handle_out);
+int32_t elph_shard_p2p_open(elph_handle* h, const unsigned char* ipc_handles, const int64_t* slab_lengths);
+int32_t elph_dev_shard_cg_p2p(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter,
+                              int64_t* iters, double* eps);
 int32_t elph_dev_update_model(elph_handle* h);
 /* calc_dSbdx! on a slab: dSbdx_own += dSb/dx, x_own = first own slice of a halo'd copy of the field (periodic in tau) */
 int32_t elph_dev_shard_dSbdx(elph_handle* h, double* dSbdx_own, const double* x_own, int32_t shifted);

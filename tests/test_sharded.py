@@ -385,9 +385,40 @@ def _gpu_worker(rank, world, port):
         be = CudaSlabBackend(em, tau0, om.L)
         op = ShardedOperator(be, RingComm(rank, world), tol=1e-5, maxiter=5000)
         _check_rank(op, be, rank, tau0, lloc, V, outs, om, b, x_ref, it_ref)
+        _check_p2p_cg(be, op.comm, tau0, lloc, b, x_ref, it_ref)
+        dist.barrier()
         em.close()
     finally:
         dist.destroy_process_group()
+
+
+def _check_p2p_cg(be, comm, tau0, lloc, b_glob, x_ref, it_ref):
+    """Peer-memory CG (csrc/cg_p2p.cu): one persistent kernel per GPU, halo + all-reduce inside the kernel."""
+    import torch
+    be.p2p_setup(comm)
+    b = be.empty()
+    b[1:lloc + 1] = torch.from_numpy(b_glob[tau0:tau0 + lloc]).to(b.device)
+    for rep in range(3):                      # repeated solves: the barrier sequence numbers carry over
+        x = be.empty()
+        x.fill_(3.0)                          # output only (x0 = 0 inside)
+        it, eps = be.cg_p2p(x, b, 1e-5, 5000)
+        assert abs(it - it_ref) <= 2, (it, it_ref)
+        assert eps < 1e-5
+        assert relerr(x[1:lloc + 1].cpu().numpy(), x_ref[tau0:tau0 + lloc]) <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,beta", [(32, 0.9), (32, 4.0), (64, 0.5)])
+def test_p2p_cg_single_gpu(Ls, beta):
+    """world = 1: the ring closes on the GPU itself (the pushes land in its own halo rows, one mailbox slot)."""
+    from elphdynamics_b200.sharded import CudaSlabBackend, RingComm, ShardedOperator
+    om, V, outs, b, x_ref, it_ref = _problem(Ls=Ls, beta=beta)
+    em = _engine_slab(om, 0, om.L)
+    be = CudaSlabBackend(em, 0, om.L)
+    op = ShardedOperator(be, RingComm(0, 1), tol=1e-5, maxiter=5000)
+    op.update_model()
+    _check_p2p_cg(be, op.comm, 0, om.L, b, x_ref, it_ref)
+    em.close()
 
 
 def _cuda_backend(om, tau0, lloc):
