@@ -418,8 +418,11 @@ def main():
         mE.assign_omega(1.0); mE.assign_lambda(1.0); mE.assign_mu(-1.0)
         mE.assign_t(1.0, 0, 0, (1, 0, 0)); mE.assign_t(1.0, 0, 0, (0, 1, 0))
         mE.initialize_model_()
-        rs = np.random.default_rng(99 + rank)
-        mE.x = (rs.integers(-1, 2, size=(mE.Nsites, 1)) + 0.7 * rs.normal(size=(mE.Nsites, 1)) + 0.3 * rs.normal(size=(mE.Nsites, lloc))).reshape(-1)
+        # the same global synthetic field whatever the world size: generated globally, sliced per rank (host layout site-major)
+        rs = np.random.default_rng(99)
+        xgE = rs.integers(-1, 2, size=(mE.Nsites, 1)) + 0.7 * rs.normal(size=(mE.Nsites, 1)) + 0.3 * rs.normal(size=(mE.Nsites, LtauE))
+        bgE = rs.normal(size=(LtauE, mE.Nsites))
+        mE.x = np.ascontiguousarray(xgE[:, tau0:tau0 + lloc]).reshape(-1)
         beE = CudaSlabBackend(mE, tau0, LtauE)
         opE = ShardedOperator(beE, RingComm(rank, world))
         opE.update_model()
@@ -444,6 +447,52 @@ def main():
                    "us_per_matvec": usE, "matvecs_per_s": 1e6 / usE, "slab_slices_per_gpu": lloc,
                    "algorithmic_GBps_per_gpu": BYTES_PER_POINT * mE.Nsites * lloc / usE / 1e3,
                    "collective": "1 halo slice each way per product (NCCL send/recv), antiperiodic sign on global slice 0"}
+        # CG on the sharded lattice: the peer-memory persistent kernel (collectives inside the kernel, csrc/cg_p2p.cu) where
+        # every slab is co-resident, else the single-GPU engine (world = 1) or the NCCL-between-launches loop
+        bE, xE = beE.empty(), beE.empty()
+        bE[1:lloc + 1] = torch.from_numpy(bgE[tau0:tau0 + lloc]).cuda()
+        cgE = {}
+        if opE.enable_p2p():
+            opE.solve(xE, bE)
+            barrier()
+            t0 = time.perf_counter()
+            itE, epsE = opE.solve(xE, bE)
+            torch.cuda.synchronize()
+            dtE = time.perf_counter() - t0
+            cgE = {"path": "peer-memory persistent kernel: halo pushes + scalar all-reduces over NVLink inside the kernel"}
+        elif world == 1:
+            from elphdynamics_b200 import workloads
+            mF, _ = workloads.holstein("square", LE, LtauE * DTAU, DTAU, seed=5)
+            mF.x = xgE.reshape(-1)
+            E.update_model_(mF)
+            mF.set_stream(torch.cuda.current_stream().cuda_stream)
+            bF = torch.from_numpy(np.ascontiguousarray(bgE.T).reshape(-1)).cuda()
+            xF = torch.zeros_like(bF)
+            itc, epc = C.c_int64(), C.c_double()
+            for _ in range(2):
+                xF.zero_()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                mF._lib.elph_dev_cg_solve(mF.handle, bF.data_ptr(), xF.data_ptr(), 0, 0.0, 0, C.byref(itc), C.byref(epc))
+                torch.cuda.synchronize()
+                dtE = time.perf_counter() - t0
+            itE, epsE = itc.value, epc.value
+            cgE = {"path": "single-GPU engine (CUDA-graph CG: 400 slices of 64x64 are not co-resident on one GPU)"}
+            mF.close()
+        else:
+            barrier()
+            t0 = time.perf_counter()
+            itE, epsE = opE.solve_cg(xE, bE, maxiter=40)
+            torch.cuda.synchronize()
+            dtE = time.perf_counter() - t0
+            cgE = {"path": "NCCL send/recv + all-reduce between launches (bounded to 40 iterations)"}
+        if world > 1:
+            t = torch.tensor([dtE], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtE = float(t.item())
+        cgE.update({"iters": int(itE), "eps": float(epsE), "seconds": dtE, "us_per_iter": dtE / max(int(itE), 1) * 1e6,
+                    "algorithmic_GBps_aggregate": 96.0 * mE.Nsites * LtauE * int(itE) / dtE / 1e9})
+        sharded["cg"] = cgE
         mE.close()
 
     if rank == 0:

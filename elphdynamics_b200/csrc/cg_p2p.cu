@@ -6,16 +6,23 @@
 // of cg_persistent.cu, src/IterativeSolvers.jl:239-314) and both collectives happen inside it over NVLink peer memory:
 //
 //   * halo: the CTAs of the first / last slice of a slab PUSH their new r and p tiles straight into the neighbour GPU's
-//     halo rows (posted remote stores); every CTA then reads tau-1 / tau+1 from local memory only;
-//   * all-reduce + barrier: the last CTA to arrive on a GPU folds the GPU's partials in index order and writes
-//     {value, sequence number} into a mailbox slot on EVERY GPU (two 64-bit words, each carrying half of the double and
-//     the sequence number, as one 16-byte store); each CTA polls its own GPU's mailbox until all `world` slots carry
-//     the sequence number and sums them in rank order -- the same bits on every GPU, so all GPUs take the same branch.
+//     halo rows as SELF-VALIDATING words (the "LL" idea of NCCL): every double travels as one 16-byte store of two
+//     64-bit words, each carrying half of the double and a 32-bit tag that names the iteration that produced it.  The
+//     reader spins on the element itself until both tags match -- no flag, no system-scope fence, and the posted stores
+//     overlap the barrier that follows them.  (First version: plain rows + fence.acq_rel.sys + a flag per side; the
+//     fence sat on the critical path of the boundary CTAs: 13.0 us/iteration at config B against 7 us for the
+//     single-GPU persistent kernel.)
+//   * all-reduce + barrier: on each GPU the CTAs arrive on a counter and every CTA reads back the GPU's partials in
+//     index order (the barrier of cg_persistent.cu); CTA 0 then writes {sum, sequence number} into a mailbox slot on
+//     every OTHER GPU (same two-word encoding) and each CTA polls its own GPU's mailbox until the world-1 remote slots
+//     carry the sequence number; the total is summed in rank order -- the same bits on every GPU, so all GPUs take the
+//     same branch.  With world = 1 this is exactly the single-GPU barrier.
 //
 // Memory: each process allocates one arena (cudaMalloc), exports it with cudaIpcGetMemHandle and opens the others'
-// (elph_shard_p2p_*).  Arena = R, P0, P1 as [halo_lo][Lmax slices][halo_hi] plus the mailboxes; Lmax = ceil(Lglob /
-// world), so the layout is the same on every rank.  Sequence numbers increase monotonically over the life of the handle
-// (all ranks execute the same number of barriers), mailbox slots alternate by parity, nothing is ever reset.
+// (elph_shard_p2p_*).  Arena = R, P0, P1 as [Lmax slices] (Lmax = ceil(Lglob / world), same layout on every rank), six
+// tagged halo rows (R, P0, P1 x lo, hi; 16 bytes per site), the mailboxes and the partials.  Sequence numbers / tags
+// increase monotonically over the life of the handle (all ranks execute the same number of barriers), mailbox slots
+// and partials alternate by parity, nothing is ever reset.
 // Holstein on periodic square lattices (the register tiles of mtm_square.cu); the reference has no counterpart.
 #include "square_tiles.cuh"
 
@@ -27,124 +34,131 @@ namespace {
 using namespace sqt;
 
 constexpr int kMaxWorld = 16;
-constexpr unsigned int kSpinLimit = 1u << 27;   // ~ seconds: a dead peer ends the solve with an error instead of a hang
+constexpr unsigned int kSpinLimit = 1u << 25;   // ~ 20 s: a dead peer ends the solve with an error instead of a hang
 
 struct P2pParams {
     const double* __restrict__ D;   // expnV with halos: slice index -1 .. L valid
     const double* __restrict__ b;   // [L][N] right-hand side (initial guess is zero)
     double* __restrict__ x;         // [L][N] out
-    double* R;                      // own slice 0 of the arena's R (rows -1 and L are the halo rows)
-    double* P0;
-    double* P1;
-    double* left_R;                 // left neighbour's halo_hi row of R / P0 / P1 (peer memory)
-    double* left_P0;
-    double* left_P1;
-    double* right_R;                // right neighbour's halo_lo row
-    double* right_P0;
-    double* right_P1;
+    double* R;                      // [L][N] own slices in the arena
+    double* P0;                     // p buffers: P0 and P0 + Lmax * N, alternating by iteration parity
+    // tagged halo rows, [N][2] 64-bit words each, six per arena in the order R lo, R hi, P0 lo, P0 hi, P1 lo, P1 hi:
+    // own arena (written by the neighbours) and the two neighbours' arenas (peer memory, written by this GPU: the hi rows
+    // of the left neighbour, the lo rows of the right neighbour)
+    const unsigned long long* my_halo;
+    unsigned long long* left_halo;
+    unsigned long long* right_halo;
     unsigned long long* mbox[kMaxWorld];   // mailbox base of every rank (own included): [2 parities][world][2 words]
-    unsigned int* left_hi_flag;     // in the left neighbour's arena: "your halo_hi row is complete up to barrier seq"
-    unsigned int* right_lo_flag;    // in the right neighbour's arena: same for its halo_lo row
-    const unsigned int* my_lo_flag; // own arena, written by the left neighbour's last slice
-    const unsigned int* my_hi_flag; // own arena, written by the right neighbour's first slice
-    double* partial;                // [L] per-CTA partials of this GPU
+    double* partial;                // [2 parities][Lmax] per-CTA partials of this GPU
     unsigned int* bar;              // arrival counter of this GPU (monotonic over the launch, zeroed by the host)
     CgScalars* S;                   // in: tol, kappa_max, maxiter; out: iter, eps, normb, done (2 = peer timeout)
     unsigned int seq_base;          // sequence number of the last barrier of the previous solve
-    int L, Ly, rank, world, tau0, Lglob;
+    int L, Lmax, Ly, rank, world, tau0, Lglob;
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
 
-// acq_rel fences (lighter than the sequentially-consistent membar behind __threadfence_system: measured 27.6 -> see
-// DESIGN.md us/iteration at world = 1)
-__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
-__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-
-__device__ __forceinline__ void st_mbox(unsigned long long* p, unsigned long long w0, unsigned long long w1) {
+__device__ __forceinline__ void st_ll(unsigned long long* p, unsigned long long w0, unsigned long long w1) {
     asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ void ld_mbox(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+__device__ __forceinline__ void ld_ll(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-
-__device__ __forceinline__ void st_flag(unsigned int* p, unsigned int v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// one double + tag as two self-validating words (a torn 16-byte store cannot pass for a complete one)
+__device__ __forceinline__ void push_ll(unsigned long long* p, double v, unsigned int tag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_ll(p, (bits & 0xffffffffull) | ((unsigned long long)tag << 32), (bits >> 32) | ((unsigned long long)tag << 32));
 }
-__device__ __forceinline__ unsigned int ld_flag(const unsigned int* p) {
+__device__ __forceinline__ double unpack_ll(unsigned long long a, unsigned long long b) {
+    return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     unsigned int v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-// Barrier over all CTAs of all GPUs fused with the sum of one double per CTA.  `nbar` counts this GPU's barriers of the
-// launch from 1 (local arrival target = nbar * gridDim.x), seq is the global sequence number.  Returns false on a peer
-// timeout.  The all-reduce itself carries no cross-GPU ordering obligation (a mailbox word validates itself through its
-// sequence number): remote data is only ever read through the halo rows, and those are guarded point-to-point -- the
-// CTA of the first / last slice, AFTER arriving (so its system-scope fence overlaps the wait instead of delaying
-// everybody), fences its pushes and stores seq into the neighbour's halo flag.  Measured: with the system fences inside
-// the barrier's critical path an iteration cost 17.2 us (27.6 us with sequentially-consistent membar.sys).
-__device__ __forceinline__ bool global_sum(double block_value, const P2pParams& P, unsigned int nbar, unsigned int seq, bool first,
-                                           bool last, double* red, int* flag, double& out) {
-    const int nb = gridDim.x;
-    if (threadIdx.x == 0) {
-        P.partial[blockIdx.x] = block_value;
-        fence_gpu();
-        const unsigned int prev = atomicAdd(P.bar, 1u);
-        flag[0] = (prev == nbar * (unsigned int)nb - 1u) ? 1 : 0;
-    }
-    __syncthreads();
-    if (flag[0]) {
-        // last CTA of this GPU: fixed-order fold of the GPU's partials, then publish to every GPU's mailbox
-        fence_gpu();
-        double s = 0.0;
-        for (int k = threadIdx.x; k < nb; k += blockDim.x) s += __ldcg(P.partial + k);
+// Read one tagged halo tile (PY x NSEG elements per thread): all loads are issued before any tag is checked, so a tile
+// that has already arrived costs one L2 round trip.  Returns 0 on a timeout.
+template <int NSEG, int PY, typename Idx>
+__device__ __forceinline__ int read_halo(const unsigned long long* row, unsigned int tag, Idx eidx, double (&out)[PY][NSEG]) {
+    unsigned long long wa[PY][NSEG], wb[PY][NSEG];
+    unsigned int spins = 0;
+    bool all;
+    do {
+        all = true;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
-            const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)seq << 32);
-            const unsigned long long w1 = (bits >> 32) | ((unsigned long long)seq << 32);
-            fence_gpu();   // local rows written before the arrivals are ordered before this GPU's own mailbox word
-            const size_t slot = ((size_t)(seq & 1u) * P.world + P.rank) * 2;
-            for (int q = 0; q < P.world; ++q) st_mbox(P.mbox[(P.rank + q) % P.world] + slot, w0, w1);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 32 && (first || last)) {
-        // a thread of ANOTHER warp, after the CTA's publishing duties: the system-scope fence overlaps thread 0's wait on
-        // the mailbox below instead of delaying the barrier (the boundary CTAs do extra work and tend to arrive last).
-        // The caller's __syncthreads ordered the whole CTA's pushes before this fence.
-        fence_sys();   // the tiles pushed so far have reached the neighbour's memory ...
-        if (first) st_flag(P.left_hi_flag, seq);    // ... before it can see its halo flag move
-        if (last) st_flag(P.right_lo_flag, seq);
-    }
-    // every CTA: wait for all GPUs' contributions in the own mailbox, sum in rank order
-    if (threadIdx.x < 32) {
-        double t = 0.0;
+        for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) ld_ll(row + 2 * eidx(rr, q), wa[rr][q], wb[rr][q]);
+#pragma unroll
+        for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q)
+                all = all && ((unsigned int)(wa[rr][q] >> 32) == tag) && ((unsigned int)(wb[rr][q] >> 32) == tag);
+    } while (!all && ++spins < kSpinLimit);
+#pragma unroll
+    for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) out[rr][q] = unpack_ll(wa[rr][q], wb[rr][q]);
+    return all ? 1 : 0;
+}
+
+// Barrier over all CTAs of all GPUs fused with the sum of one double per CTA.  `nbar` counts this GPU's barriers of the
+// launch from 1 (local arrival target = nbar * gridDim.x), seq is the global sequence number.  Returns false on a
+// timeout.  The caller must have a __syncthreads between the CTA's global writes and this call.  The all-reduce carries
+// no cross-GPU ordering obligation: remote data is only ever read through the self-validating halo rows.
+__device__ __forceinline__ bool global_sum(double block_value, const P2pParams& P, unsigned int nbar, unsigned int seq, double* red,
+                                           int* flag, double& out) {
+    const int nb = gridDim.x;
+    double* partial = P.partial + (size_t)(seq & 1u) * P.Lmax;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = block_value;
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.bar), "r"(1u) : "memory");
+        const unsigned int target = nbar * (unsigned int)nb;
+        unsigned int spins = 0;
         int ok = 1;
-        if (threadIdx.x == 0) {
-            const unsigned long long* mine = P.mbox[P.rank] + (size_t)(seq & 1u) * P.world * 2;
-            for (int g = 0; g < P.world && ok; ++g) {
-                unsigned long long a, b;
-                unsigned int spins = 0;
-                do {
-                    ld_mbox(mine + 2 * g, a, b);
-                    if (++spins > kSpinLimit) { ok = 0; break; }
-                } while ((unsigned int)(a >> 32) != seq || (unsigned int)(b >> 32) != seq);
-                t += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
-            }
-            fence_gpu();   // acquire the local rows of the other CTAs of this GPU
-            red[0] = t;
-            flag[1] = ok;
-        }
+        while (ld_acquire_gpu(P.bar) < target)
+            if (++spins > kSpinLimit) { ok = 0; break; }
+        flag[0] = ok;
     }
     __syncthreads();
-    out = red[0];
-    const bool good = (flag[1] != 0);
+    // every CTA folds this GPU's partials in the same fixed order (thread-strided, shuffle tree, warps in order)
+    double s = 0.0;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s += __ldcg(partial + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    bool good = (flag[0] != 0);
+    if (P.world > 1) {
+        __syncthreads();   // red is reused below
+        if (threadIdx.x == 0) {
+            const size_t par = (size_t)(seq & 1u) * P.world * 2;
+            if (blockIdx.x == 0)
+                for (int q = 1; q < P.world; ++q) push_ll(P.mbox[(P.rank + q) % P.world] + par + 2 * P.rank, t, seq);
+            const unsigned long long* mine = P.mbox[P.rank] + par;
+            unsigned long long wa[kMaxWorld], wb[kMaxWorld];
+            unsigned int spins = 0;
+            bool all;
+            do {
+                all = true;
+                for (int g = 0; g < P.world; ++g)
+                    if (g != P.rank) ld_ll(mine + 2 * g, wa[g], wb[g]);
+                for (int g = 0; g < P.world; ++g)
+                    if (g != P.rank) all = all && ((unsigned int)(wa[g] >> 32) == seq) && ((unsigned int)(wb[g] >> 32) == seq);
+            } while (!all && ++spins < kSpinLimit);
+            double tot = 0.0;
+            for (int g = 0; g < P.world; ++g) tot += (g == P.rank) ? t : unpack_ll(wa[g], wb[g]);   // rank order: same bits everywhere
+            red[0] = tot;
+            flag[1] = all ? 1 : 0;
+        }
+        __syncthreads();
+        t = red[0];
+        good = good && (flag[1] != 0);
+    }
+    out = t;
     __syncthreads();   // red / flag are reused by the caller
     return good;
 }
@@ -165,18 +179,34 @@ __device__ __forceinline__ double tile_sum(double v, double* red, int lane, int 
 template <int NSEG, int PY, int MAXT>
 __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
     constexpr int LX = 32 * NSEG;
-    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]
+    // 128-register cap at 512 threads: x, D(tau), D(tau+1) live in shared memory there (one CTA per SM anyway)
+    constexpr bool XS = (MAXT > 256);
+    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; XS: + x, D(tau), D(tau+1) [3][N]
     __shared__ double red[32];
-    __shared__ int flag[2];   // [0] this CTA arrived last on its GPU, [1] barrier completed without a peer timeout
+    __shared__ int flag[2];   // barrier completed without a timeout: [0] local counter, [1] peers' mailbox words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int L = P.L, N = LX * P.Ly;
-    const int tau = blockIdx.x;                      // local slice; rows tau-1 = -1 and tau+1 = L are the halo rows
+    const int tau = blockIdx.x;                      // local slice; tau-1 = -1 and tau+1 = L live in the tagged halo rows
     const bool first = (tau == 0), last = (tau == L - 1);
     const size_t tile_off = (size_t)warp * PY * LX;
     auto eidx = [&](int r, int q) -> size_t { return tile_off + r * LX + 32 * q + lane; };
     const long long row = (long long)tau * N, rowm = row - N, rowp = row + N;
+    // tags: r written in iteration j (0 = the initial residual) carries base + 2j + 1, p written in iteration j >= 1
+    // carries base + 2j; unique over the life of the handle because the host advances base by 2 * iterations + 2
+    const unsigned int base = P.seq_base;
+    const size_t vstride = (size_t)P.Lmax * N, hrow = 2 * (size_t)N;
+    auto halo = [&](const unsigned long long* b, int vec, int side) { return b + (size_t)(2 * vec + side) * hrow; };
+    auto halo_w = [&](unsigned long long* b, int vec, int side) { return b + (size_t)(2 * vec + side) * hrow; };
 
-    Tile<NSEG, PY> x, r, pprev, pc, Dc, Dn, t1, t2;
+    Tile<NSEG, PY> r, pc, t1, t2;   // pc: p_{j-1} on entry to iteration j, p_j after its first loop
+    Tile<NSEG, PY> xr, Dcr, Dnr;   // registers when !XS (dead otherwise)
+    double* xs = strips + 2ull * nwarps * 4 * LX;
+    double* dcs = xs + N;
+    double* dns = dcs + N;
+    auto sidx = [&](int rr, int q) -> int { return (rr * NSEG + q) * (int)blockDim.x + (int)threadIdx.x; };
+    auto X = [&](int rr, int q) -> double& { if constexpr (XS) return xs[sidx(rr, q)]; else return xr.a[rr][q]; };
+    auto DC = [&](int rr, int q) -> double& { if constexpr (XS) return dcs[sidx(rr, q)]; else return Dcr.a[rr][q]; };
+    auto DN = [&](int rr, int q) -> double& { if constexpr (XS) return dns[sidx(rr, q)]; else return Dnr.a[rr][q]; };
     double accb = 0.0;
 #pragma unroll
     for (int rr = 0; rr < PY; ++rr)
@@ -184,64 +214,76 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
         for (int q = 0; q < NSEG; ++q) {
             const size_t e = eidx(rr, q);
             const double bv = P.b[row + e];          // x0 = 0: r0 = b
-            x.a[rr][q] = 0.0;
+            X(rr, q) = 0.0;
             r.a[rr][q] = bv;
-            pprev.a[rr][q] = 0.0;
-            Dc.a[rr][q] = P.D[row + e];
-            Dn.a[rr][q] = P.D[rowp + e];
+            pc.a[rr][q] = 0.0;
+            DC(rr, q) = P.D[row + e];
+            DN(rr, q) = P.D[rowp + e];
             P.R[row + e] = bv;
-            if (first) P.left_R[e] = bv;             // push r0 into the neighbours' halo rows
-            if (last) P.right_R[e] = bv;
+            if (first) push_ll(halo_w(P.left_halo, 0, 1) + 2 * e, bv, base + 1u);   // r0 into the neighbours' halo rows
+            if (last) push_ll(halo_w(P.right_halo, 0, 0) + 2 * e, bv, base + 1u);
             accb = fma(bv, bv, accb);
         }
     const double tol = P.S->tol, kappa_max = P.S->kappa_max;
     const long long maxiter = P.S->maxiter;
-    unsigned int nbar = 0, seq = P.seq_base;
-    const bool boundary = first || last;
+    unsigned int nbar = 0, seq = base;
     double rdotr;
-    bool alive = global_sum(tile_sum<NSEG, PY>(accb, red, lane, warp, nwarps), P, ++nbar, ++seq, first, last, red, flag, rdotr);
+    bool alive = global_sum(tile_sum<NSEG, PY>(accb, red, lane, warp, nwarps), P, ++nbar, ++seq, red, flag, rdotr);
     const double normb = sqrt(rdotr), eps0 = 1.0;
     double beta = 0.0, kmin = 0.0, eps = eps0;
     long long j = 0;
     int xbuf = 0;
-    double* Pold = P.P1;   // zeros on entry (own rows and halo rows)
-    double* Pnew = P.P0;
-    double* left_Pnew = P.left_P0;
-    double* right_Pnew = P.right_P0;
-    double* left_Pother = P.left_P1;
-    double* right_Pother = P.right_P1;
+    int pb = 0;   // p_j goes to buffer pb, p_{j-1} is in buffer pb ^ 1 (never read in the first iteration: beta = 0)
     const int tg = P.tau0 + tau;                       // global slice index
     const bool wrap_c = (tg == 0);
     const bool wrap_n = (tg + 1 == P.Lglob);
 
     while (alive && j < maxiter) {
         ++j;
-        if (boundary) {
-            // the halo rows read below were pushed by the neighbour GPU before its barrier number `seq` (or earlier):
-            // wait for its point-to-point flag (monotonic; the neighbour may already be one barrier ahead)
-            if (threadIdx.x == 0) {
-                unsigned int spins = 0;
-                if (first)
-                    while ((int)(ld_flag(P.my_lo_flag) - seq) < 0 && ++spins < kSpinLimit) {}
-                if (last)
-                    while ((int)(ld_flag(P.my_hi_flag) - seq) < 0 && ++spins < kSpinLimit) {}
-                fence_gpu();   // the tiles are in this GPU's memory, ordered before the flag by the writer's fence.sys
+        const unsigned int tag_r_prev = base + 2u * (unsigned int)(j - 1) + 1u;   // r_{j-1}
+        const unsigned int tag_p_prev = base + 2u * (unsigned int)(j - 1);        // p_{j-1} (j > 1)
+        const unsigned int tag_p = base + 2u * (unsigned int)j;
+        const unsigned int tag_r = tag_p + 1u;
+        int halo_ok = 1;
+        double* Pnew = P.P0 + (pb ? vstride : 0);
+        const double* Pold = P.P0 + (pb ? 0 : vstride);
+        // p_j(tau-1) = r_{j-1}(tau-1) + beta p_{j-1}(tau-1): neighbour rows of this GPU, or the tagged halo row
+        if (first) {
+            double hr[PY][NSEG];
+            halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 0, 0), tag_r_prev, eidx, hr);
+#pragma unroll
+            for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = hr[rr][q];
+            if (j > 1) {
+                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1 + (pb ^ 1), 0), tag_p_prev, eidx, hr);
+#pragma unroll
+                for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = fma(beta, hr[rr][q], t1.a[rr][q]);
             }
-            __syncthreads();
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) {
+                    const size_t e = eidx(rr, q);
+                    const double rm = __ldcg(P.R + rowm + e);
+                    t1.a[rr][q] = (j > 1) ? fma(beta, __ldcg(Pold + rowm + e), rm) : rm;
+                }
         }
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
                 const size_t e = eidx(rr, q);
-                const double pm = fma(beta, __ldcg(Pold + rowm + e), __ldcg(P.R + rowm + e));
-                const double pcv = fma(beta, pprev.a[rr][q], r.a[rr][q]);
+                const double pcv = fma(beta, pc.a[rr][q], r.a[rr][q]);
                 pc.a[rr][q] = pcv;
                 Pnew[row + e] = pcv;
-                if (first) left_Pnew[e] = pcv;
-                if (last) right_Pnew[e] = pcv;
-                t1.a[rr][q] = Dc.a[rr][q] * pm;
-                t2.a[rr][q] = Dn.a[rr][q] * pcv;
+                if (first) push_ll(halo_w(P.left_halo, 1 + pb, 1) + 2 * e, pcv, tag_p);
+                if (last) push_ll(halo_w(P.right_halo, 1 + pb, 0) + 2 * e, pcv, tag_p);
+                t1.a[rr][q] = DC(rr, q) * t1.a[rr][q];
+                t2.a[rr][q] = DN(rr, q) * pcv;
             }
         g0_x_even(t1, P.c0, P.s0);
         g0_x_even(t2, P.c0, P.s0);
@@ -256,15 +298,35 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
             g3_y_odd(t1, P.c3, P.s3, a1, b1);
             g3_y_odd(t2, P.c3, P.s3, a2, b2);
         }
+        // p_j(tau+1), same rule
+        double pn[PY][NSEG];
+        if (last) {
+            halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 0, 1), tag_r_prev, eidx, pn);
+            if (j > 1) {
+                double hp[PY][NSEG];
+                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1 + (pb ^ 1), 1), tag_p_prev, eidx, hp);
+#pragma unroll
+                for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) pn[rr][q] = fma(beta, hp[rr][q], pn[rr][q]);
+            }
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) {
+                    const size_t e = eidx(rr, q);
+                    const double rp = __ldcg(P.R + rowp + e);
+                    pn[rr][q] = (j > 1) ? fma(beta, __ldcg(Pold + rowp + e), rp) : rp;
+                }
+        }
         double acc = 0.0;
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
-                const size_t e = eidx(rr, q);
-                const double pn = fma(beta, __ldcg(Pold + rowp + e), __ldcg(P.R + rowp + e));
                 const double wc = wrap_c ? (pc.a[rr][q] + t1.a[rr][q]) : (pc.a[rr][q] - t1.a[rr][q]);
-                const double wn = wrap_n ? (pn + t2.a[rr][q]) : (pn - t2.a[rr][q]);
+                const double wn = wrap_n ? (pn[rr][q] + t2.a[rr][q]) : (pn[rr][q] - t2.a[rr][q]);
                 t1.a[rr][q] = wc;
                 t2.a[rr][q] = wn;
                 acc = fma(wc, wc, acc);
@@ -278,9 +340,9 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
         g2_y_even(t2, P.c2, P.s2);
         g1_x_odd(t2, P.c1, P.s1, lane);
         g0_x_even(t2, P.c0, P.s0);
+        if (!__syncthreads_and(halo_ok)) { alive = false; break; }   // a neighbour's tile never arrived
         double pAp;
-        // the p pushes of this iteration become visible with this barrier; they are read in the NEXT iteration (as Pold)
-        alive = global_sum(tile_sum<NSEG, PY>(acc, red, lane, warp, nwarps), P, ++nbar, ++seq, first, last, red, flag, pAp);
+        alive = global_sum(tile_sum<NSEG, PY>(acc, red, lane, warp, nwarps), P, ++nbar, ++seq, red, flag, pAp);
         if (!alive) break;
         const double alpha = rdotr / pAp;
         double accr = 0.0;
@@ -289,19 +351,18 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
                 const size_t e = eidx(rr, q);
-                const double du = Dn.a[rr][q] * t2.a[rr][q];
+                const double du = DN(rr, q) * t2.a[rr][q];
                 const double z = wrap_n ? (t1.a[rr][q] + du) : (t1.a[rr][q] - du);
-                x.a[rr][q] = fma(alpha, pc.a[rr][q], x.a[rr][q]);
+                X(rr, q) = fma(alpha, pc.a[rr][q], X(rr, q));
                 const double rv = fma(-alpha, z, r.a[rr][q]);
                 r.a[rr][q] = rv;
                 P.R[row + e] = rv;
-                if (first) P.left_R[e] = rv;
-                if (last) P.right_R[e] = rv;
+                if (first) push_ll(halo_w(P.left_halo, 0, 1) + 2 * e, rv, tag_r);
+                if (last) push_ll(halo_w(P.right_halo, 0, 0) + 2 * e, rv, tag_r);
                 accr = fma(rv, rv, accr);
-                pprev.a[rr][q] = pc.a[rr][q];
             }
         double rrn;
-        alive = global_sum(tile_sum<NSEG, PY>(accr, red, lane, warp, nwarps), P, ++nbar, ++seq, first, last, red, flag, rrn);
+        alive = global_sum(tile_sum<NSEG, PY>(accr, red, lane, warp, nwarps), P, ++nbar, ++seq, red, flag, rrn);
         if (!alive) break;
         eps = sqrt(rrn) / normb;
         const double lg = log(2.0 * eps0 / eps);
@@ -311,55 +372,79 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
         if (eps < tol || kmin > kappa_max) break;
         beta = rrn / rdotr;
         rdotr = rrn;
-        double* tmp = Pold; Pold = Pnew; Pnew = tmp;
-        tmp = left_Pnew; left_Pnew = left_Pother; left_Pother = tmp;
-        tmp = right_Pnew; right_Pnew = right_Pother; right_Pother = tmp;
+        pb ^= 1;
     }
 #pragma unroll
     for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
-        for (int q = 0; q < NSEG; ++q) P.x[row + eidx(rr, q)] = x.a[rr][q];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int q = 0; q < NSEG; ++q) P.x[row + eidx(rr, q)] = X(rr, q);
+    if (!alive && threadIdx.x == 0) P.S->done = 2;   // any CTA that saw a timeout marks the solve as failed
+    if (alive && blockIdx.x == 0 && threadIdx.x == 0) {
         P.S->iter = j;
         P.S->eps = eps;
         P.S->normb = normb;
         P.S->kappa_min = kmin;
-        P.S->done = alive ? 1 : 2;
+        P.S->done = 1;
     }
 }
 
 template <int NSEG, int PY, int MAXT>
-bool launch_p2p(elph_handle* h, P2pParams& P, int nwarps) {
-    constexpr int LX = 32 * NSEG;
-    const size_t smem = 2ull * nwarps * 4 * LX * sizeof(double);
+size_t p2p_smem(const elph_handle* h, int nwarps) {
+    return (2ull * nwarps * 4 * (32 * NSEG) + (MAXT > 256 ? 3ull * h->N : 0)) * sizeof(double);
+}
+
+// all slices of the slab must be co-resident (cooperative launch, one CTA per slice)
+template <int NSEG, int PY, int MAXT>
+bool fits_p2p(elph_handle* h, int nwarps) {
     auto kern = cg_p2p_kernel<NSEG, PY, MAXT>;
     elph_enable_smem(h, kern);
     int per_sm = 0;
-    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem));
-    if ((long long)per_sm * h->sm_count < h->L) return false;   // all slices of the slab must be co-resident
+    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, p2p_smem<NSEG, PY, MAXT>(h, nwarps)));
+    return (long long)per_sm * h->sm_count >= h->L;
+}
+
+template <int NSEG, int PY, int MAXT>
+bool launch_p2p(elph_handle* h, P2pParams& P, int nwarps) {
+    if (!fits_p2p<NSEG, PY, MAXT>(h, nwarps)) return false;
+    auto kern = cg_p2p_kernel<NSEG, PY, MAXT>;
     ELPH_CUDA(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned int), h->stream));
     void* args[] = {&P};
-    ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L), dim3(nwarps * 32), args, smem, h->stream));
+    ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L), dim3(nwarps * 32), args, p2p_smem<NSEG, PY, MAXT>(h, nwarps),
+                                          h->stream));
     h->launches++;
     return true;
 }
 
-size_t arena_vec_doubles(const elph_handle* h) { return (size_t)(h->p2p.Lmax + 2) * h->N; }
+// kernel variant for this handle: 0 = none applies
+int p2p_variant(const elph_handle* h, int& nwarps) {
+    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
+    const int PY = (Lx == 32) ? 8 : 4;
+    if (Ly % PY) return 0;
+    nwarps = Ly / PY;
+    if (nwarps < 2 || nwarps > 32) return 0;
+    if (Lx == 32 && nwarps * 32 <= 256) return 1;
+    if (Lx == 64 && nwarps * 32 <= 512) return 2;
+    return 0;
+}
+
+// ---- arena layout (identical on every rank) ------------------------------------------------------------------------
+size_t arena_vec_doubles(const elph_handle* h) { return (size_t)h->p2p.Lmax * h->N; }
+size_t arena_halo_words(const elph_handle* h) { return 2 * (size_t)h->N; }   // one tagged row
+size_t arena_mbox_words() { return 2ull * kMaxWorld * 2; }
 size_t arena_bytes(const elph_handle* h) {
-    return 3 * arena_vec_doubles(h) * sizeof(double) + 2ull * kMaxWorld * 2 * sizeof(unsigned long long) + 256;
+    return 3 * arena_vec_doubles(h) * sizeof(double) + 6 * arena_halo_words(h) * sizeof(unsigned long long) +
+           arena_mbox_words() * sizeof(unsigned long long) + 2 * (size_t)h->p2p.Lmax * sizeof(double) + 256;
 }
-// halo flags behind the mailboxes, each on its own 128-byte line: which = 0 (halo_lo ready), 1 (halo_hi ready)
-unsigned int* arena_flag(const elph_handle* h, void* base, int which) {
-    unsigned char* p = reinterpret_cast<unsigned char*>(base) + 3 * arena_vec_doubles(h) * sizeof(double) +
-                       2ull * kMaxWorld * 2 * sizeof(unsigned long long);
-    return reinterpret_cast<unsigned int*>(p + 128 * which);
+double* arena_vec(const elph_handle* h, void* base, int which) {   // R (0), P0 (1), P1 (2)
+    return reinterpret_cast<double*>(base) + which * arena_vec_doubles(h);
 }
-double* arena_vec(const elph_handle* h, void* base, int which) {   // own slice 0 of R (0), P0 (1), P1 (2)
-    return reinterpret_cast<double*>(base) + which * arena_vec_doubles(h) + h->N;
+// tagged halo rows: vec = R (0), P0 (1), P1 (2); side = 0 (lo: slice -1), 1 (hi: slice L)
+unsigned long long* arena_halo(const elph_handle* h, void* base, int vec, int side) {
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(base) + 3 * arena_vec_doubles(h)) +
+           (size_t)(2 * vec + side) * arena_halo_words(h);
 }
-unsigned long long* arena_mbox(const elph_handle* h, void* base) {
-    return reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(base) + 3 * arena_vec_doubles(h));
-}
+unsigned long long* arena_mbox(const elph_handle* h, void* base) { return arena_halo(h, base, 3, 0); }
+double* arena_partial(const elph_handle* h, void* base) { return reinterpret_cast<double*>(arena_mbox(h, base) + arena_mbox_words()); }
 
 }  // namespace
 
@@ -403,6 +488,11 @@ void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, cons
         ELPH_CUDA(cudaIpcOpenMemHandle(&A.peer[q], ipc, cudaIpcMemLazyEnablePeerAccess));
     }
     A.opened = true;
+    int nwarps = 0;
+    const int variant = p2p_variant(h, nwarps);
+    const bool fits = (variant == 1) ? fits_p2p<1, 8, 256>(h, nwarps) : (variant == 2) ? fits_p2p<2, 4, 512>(h, nwarps) : false;
+    ELPH_REQUIRE(fits, ELPH_ERR_UNSUPPORTED,
+                 "peer-memory CG: the slab's time slices are not all co-resident on this GPU (or unsupported lattice)");
 }
 
 void elph_shard_p2p_close_impl(elph_handle* h) {
@@ -423,49 +513,36 @@ bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, 
     ELPH_REQUIRE(A.opened, ELPH_ERR_STATE, "elph_shard_p2p_open has not been called");
     if (tol == 0.0) tol = h->cg_tol;
     if (maxiter == 0) maxiter = h->cg_maxiter;
-    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
-    const int PY = (Lx == 32) ? 8 : 4;
-    if (Ly % PY) return false;
-    const int nwarps = Ly / PY;
-    if (nwarps < 2 || nwarps > 32 || h->partial_cap < h->L) return false;
+    int nwarps = 0;
+    const int variant = p2p_variant(h, nwarps);
+    if (!variant) return false;
+    const int Ly = h->sq.Ly;
     cudaStream_t st = h->stream;
     const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
     P2pParams P;
     P.D = h->d_D; P.b = b_own; P.x = x_own;
-    P.R = arena_vec(h, A.arena, 0); P.P0 = arena_vec(h, A.arena, 1); P.P1 = arena_vec(h, A.arena, 2);
-    // left neighbour's halo_hi row sits right after ITS last own slice; right neighbour's halo_lo row is its row -1
-    const int L_left = (int)A.peer_L[left];
-    P.left_R = arena_vec(h, A.peer[left], 0) + (size_t)L_left * h->N;
-    P.left_P0 = arena_vec(h, A.peer[left], 1) + (size_t)L_left * h->N;
-    P.left_P1 = arena_vec(h, A.peer[left], 2) + (size_t)L_left * h->N;
-    P.right_R = arena_vec(h, A.peer[right], 0) - h->N;
-    P.right_P0 = arena_vec(h, A.peer[right], 1) - h->N;
-    P.right_P1 = arena_vec(h, A.peer[right], 2) - h->N;
+    P.R = arena_vec(h, A.arena, 0); P.P0 = arena_vec(h, A.arena, 1);
+    P.my_halo = arena_halo(h, A.arena, 0, 0);
+    P.left_halo = arena_halo(h, A.peer[left], 0, 0);    // this GPU's first slice is the left neighbour's slice L (hi rows)
+    P.right_halo = arena_halo(h, A.peer[right], 0, 0);  // its last slice is the right neighbour's slice -1 (lo rows)
     for (int q = 0; q < kMaxWorld; ++q) P.mbox[q] = (q < A.world) ? arena_mbox(h, A.peer[q]) : nullptr;
-    P.left_hi_flag = arena_flag(h, A.peer[left], 1);
-    P.right_lo_flag = arena_flag(h, A.peer[right], 0);
-    P.my_lo_flag = arena_flag(h, A.arena, 0);
-    P.my_hi_flag = arena_flag(h, A.arena, 1);
-    P.partial = h->d_partial; P.bar = h->d_bar; P.S = h->d_cg;
+    P.partial = arena_partial(h, A.arena); P.bar = h->d_bar; P.S = h->d_cg;
     P.seq_base = A.seq;
-    P.L = h->L; P.Ly = Ly; P.rank = A.rank; P.world = A.world; P.tau0 = h->shard_tau0; P.Lglob = h->shard_Lglob;
+    P.L = h->L; P.Lmax = A.Lmax; P.Ly = Ly; P.rank = A.rank; P.world = A.world; P.tau0 = h->shard_tau0; P.Lglob = h->shard_Lglob;
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
-    // p_old of the first iteration (own rows and halo rows).  Peers push into P halos only after the first barrier of
-    // their kernel, which needs this rank's kernel to be running, i.e. this memset to be complete.
-    ELPH_CUDA(cudaMemsetAsync(P.P1 - h->N, 0, arena_vec_doubles(h) * sizeof(double), st));
     CgScalars init = {};
     init.tol = tol; init.kappa_max = h->cg_kappa_max; init.maxiter = maxiter;
     *h->h_cg = init;
     ELPH_CUDA(cudaMemcpyAsync(h->d_cg, h->h_cg, sizeof(CgScalars), cudaMemcpyHostToDevice, st));
     bool ok = false;
-    if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) ok = launch_p2p<1, 8, 256>(h, P, nwarps);
-    else if (Lx == 64 && PY == 4 && nwarps * 32 <= 512) ok = launch_p2p<2, 4, 512>(h, P, nwarps);
+    if (variant == 1) ok = launch_p2p<1, 8, 256>(h, P, nwarps);
+    else if (variant == 2) ok = launch_p2p<2, 4, 512>(h, P, nwarps);
     if (!ok) return false;
     ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
     ELPH_CUDA(cudaStreamSynchronize(st));
-    ELPH_REQUIRE(h->h_cg->done == 1, ELPH_ERR_STATE, "peer-memory CG: a peer GPU did not reach the barrier (timeout)");
-    A.seq += 1u + 2u * (unsigned int)h->h_cg->iter;   // barriers executed: the initial one + two per iteration
+    ELPH_REQUIRE(h->h_cg->done == 1, ELPH_ERR_STATE, "peer-memory CG: a peer GPU did not reach a barrier or deliver a halo tile (timeout)");
+    A.seq += 2u + 2u * (unsigned int)h->h_cg->iter;   // barriers executed: 1 + 2 per iteration; tags used: up to base + 2 iter + 1
     if (iters) *iters = h->h_cg->iter;
     if (eps) *eps = h->h_cg->eps;
     return true;

@@ -134,21 +134,37 @@ class CudaSlabBackend:
         return self.scal[:1].clone()
 
     # ---- peer-memory CG (csrc/cg_p2p.cu): arenas shared through CUDA IPC, collectives inside the kernel --------------
-    def p2p_setup(self, comm: "RingComm"):
-        """Export this rank's arena, all-gather the IPC handles and slab lengths over torch.distributed, open the peers'."""
+    def p2p_setup(self, comm: "RingComm") -> bool:
+        """Export this rank's arena, all-gather the IPC handles and slab lengths over torch.distributed, open the peers'.
+        Returns True when the peer-memory CG applies on EVERY rank (square lattice, all slices of every slab co-resident)."""
         import torch.distributed as dist
         buf = (C.c_ubyte * 64)()
-        self._check(self.lib.elph_shard_p2p_export(self.h, comm.rank, comm.world, buf))
-        mine = (bytes(buf), int(self.lloc))
+        ok = True
+        try:
+            self._check(self.lib.elph_shard_p2p_export(self.h, comm.rank, comm.world, buf))
+        except RuntimeError:
+            ok = False
+        mine = (bytes(buf), int(self.lloc), ok)
         if comm.world > 1:
             gathered = [None] * comm.world
             dist.all_gather_object(gathered, mine, group=comm.group)
         else:
             gathered = [mine]
-        handles = (C.c_ubyte * (64 * comm.world)).from_buffer_copy(b"".join(g[0] for g in gathered))
-        lengths = (C.c_int64 * comm.world)(*[g[1] for g in gathered])
-        self._check(self.lib.elph_shard_p2p_open(self.h, handles, lengths))
-        self._p2p_ready = True
+        if all(g[2] for g in gathered):
+            handles = (C.c_ubyte * (64 * comm.world)).from_buffer_copy(b"".join(g[0] for g in gathered))
+            lengths = (C.c_int64 * comm.world)(*[g[1] for g in gathered])
+            try:
+                self._check(self.lib.elph_shard_p2p_open(self.h, handles, lengths))
+            except RuntimeError:
+                ok = False
+        else:
+            ok = False
+        if comm.world > 1:                       # every rank must take the same path
+            flags = [None] * comm.world
+            dist.all_gather_object(flags, ok, group=comm.group)
+            ok = all(flags)
+        self._p2p_ready = ok
+        return ok
 
     def cg_p2p(self, x, b, tol: float = 0.0, maxiter: int = 0):
         """Whole CG solve (x0 = 0) in one persistent kernel per GPU; returns (iters, eps).  x, b: halo'd slab tensors."""
@@ -226,6 +242,19 @@ class ShardedOperator:
 
     def gdot(self, a, b) -> float:
         return float(self.comm.allreduce_sum(self.be.dot(a, b)).item())
+
+    def enable_p2p(self) -> bool:
+        """Use the peer-memory CG (one persistent kernel per GPU, collectives inside it) for solve() where it applies."""
+        setup = getattr(self.be, "p2p_setup", None)
+        return bool(setup and setup(self.comm))
+
+    def solve(self, x, b, tol: float = 0.0, maxiter: int = 0):
+        """solve!(x, A, b, cg) with x0 = 0 (what every caller on the hot path does, src/LangevinDynamics.jl:355-360):
+        the peer-memory CG when enable_p2p() succeeded, else the NCCL-between-launches CG."""
+        if getattr(self.be, "_p2p_ready", False):
+            return self.be.cg_p2p(x, b, tol or self.tol, maxiter or self.maxiter)
+        x.zero_()
+        return self.solve_cg(x, b, tol, maxiter)
 
     def solve_cg(self, x, b, tol: float = 0.0, maxiter: int = 0):
         """Plain CG, src/IterativeSolvers.jl:239-314, with the reference stop rule.  Returns (iters, eps)."""
@@ -319,7 +348,7 @@ class ShardedLangevin:
         be, op = self.be, self.op
         b, x, dS = be.empty(), be.empty(), be.empty()
         op.mulMT(b, g)
-        iters, eps = op.solve_cg(x, b)
+        iters, eps = op.solve(x, b)
         self.last_iters = iters
         self.comm.exchange(x, self.lloc, lo=True, hi=False)     # the force needs (M^-1 g)(tau-1)
         be.muldMdx(g, x, dS, -2.0)

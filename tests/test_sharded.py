@@ -207,7 +207,7 @@ def _langevin_reference(om, method, dt, seed=21):
     return eng(eta), eng(g1), eng(g2), eng(fa.Q), eng(x0), eng(x1), it
 
 
-def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4, beta=1.1):
+def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4, beta=1.1, p2p=False):
     import torch
     from elphdynamics_b200.sharded import ShardedLangevin, ShardedOperator, slab_bounds
     om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-0.5, seed=7)
@@ -218,6 +218,8 @@ def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4,
     be = make_backend(om, tau0, lloc)
     be.make_fft_plan(om.L)
     op = ShardedOperator(be, comm, tol=1e-10, maxiter=20000)
+    if p2p:
+        assert op.enable_p2p()      # the solves of the step run in the peer-memory persistent kernel
     Qb = torch.from_numpy(np.ascontiguousarray(Q[:, s0:s0 + nloc])).to(device)
     lang = ShardedLangevin(op, om.N, om.L, tau0, Qb, dt)
     lang.set_x(x0[tau0:tau0 + lloc])
@@ -427,6 +429,13 @@ def _cuda_backend(om, tau0, lloc):
 
 
 @pytest.mark.gpu
+def test_sharded_langevin_p2p_single_gpu():
+    """The sharded Runge-Kutta step with its solves in the peer-memory CG kernel (world = 1: the ring closes on itself)."""
+    from elphdynamics_b200.sharded import RingComm
+    _check_langevin(_cuda_backend, RingComm(0, 1), 0, 1, "rk", device="cuda", Ls=32, beta=0.8, p2p=True)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("method,Ls", [("euler", 4), ("rk", 32)])
 def test_sharded_langevin_single_gpu(method, Ls):
     """world = 1: the whole sharded driver (open-slab kernels, halo self-exchange, FFT plan handle, column FFT, slab
@@ -445,6 +454,9 @@ def _gpu_langevin_worker(rank, world, port):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         _check_langevin(_cuda_backend, RingComm(rank, world), rank, world, "rk", device="cuda", Ls=32, beta=0.8)
+        dist.barrier()
+        _check_langevin(_cuda_backend, RingComm(rank, world), rank, world, "rk", device="cuda", Ls=32, beta=0.8, p2p=True)
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
