@@ -1134,6 +1134,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 4: h->kpm_split = (value != 0); h->kpm_version++; break;
             case 5: h->use_persistent = (value != 0); break;
             case 6: h->pcg_fuse = (value != 0); h->kpm_version++; break;
+            case 7: h->cg_single_reduction = (value < 0) ? -1 : (value != 0); break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }
         return ELPH_OK;

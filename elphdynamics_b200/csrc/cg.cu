@@ -248,7 +248,7 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
     ELPH_CUDA(cudaMemsetAsync(h->d_p[1], 0, n * sizeof(double), st));  // p_old of the first iteration (beta = 0)
     // Unpreconditioned solve on a square lattice whose time slices are all co-resident: the whole loop is ONE cooperative
     // persistent kernel (cg_persistent.cu) -- no launches, two grid barriers per iteration.
-    if (!precond && elph_cg_persistent(h, x_dev)) {
+    if (!precond && ((h->use_persistent && elph_cg_single_reduction(h, x_dev)) || elph_cg_persistent(h, x_dev))) {
         ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
         ELPH_CUDA(cudaStreamSynchronize(st));
         if (iters) *iters = h->h_cg->iter;

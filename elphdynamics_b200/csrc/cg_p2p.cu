@@ -1,28 +1,41 @@
-// Multi-GPU conjugate gradient on A = M^T M for ONE tau-sharded lattice, fused with its collectives over peer memory.
+// Single-reduction conjugate gradient on A = M^T M as ONE persistent cooperative kernel per GPU, for one lattice on one
+// GPU or tau-sharded over several GPUs with the collectives fused into the kernel over NVLink peer memory.
 //
-// rank g owns a contiguous slab of time slices.  A CG iteration needs (1) the neighbouring slices of p
-// across the slab boundary and (2) two scalar all-reduces (p.Ap and |r|^2).  With NCCL calls between kernel launches
-// that is ~77 us per product at config E; here the whole solve is ONE cooperative persistent kernel per GPU (the loop
-// of cg_persistent.cu, src/IterativeSolvers.jl:239-314) and both collectives happen inside it over NVLink peer memory:
+// rank g owns a contiguous slab of time slices.  A CG iteration needs the neighbouring slices across the
+// slab boundary and the all-reduce of its scalars.  With NCCL calls between kernel launches that is ~250 us per
+// iteration at config E; a grid barrier costs ~3 us on one GPU and ~5 us across GPUs while the arithmetic of an
+// iteration is ~1.5 us.  So the loop of src/IterativeSolvers.jl:239-314 is reorganised to need ONE barrier per iteration
+// (Chronopoulos & Gear 1989: the same Krylov iterates, alpha/beta from recurrences):
 //
-//   * halo: the CTAs of the first / last slice of a slab PUSH their new r and p tiles straight into the neighbour GPU's
+//     gamma_k = (r_k, r_k),  delta_k = (r_k, A r_k) = |M r_k|^2        -> one all-reduce of two doubles
+//     beta_k = gamma_k / gamma_{k-1},  alpha_k = gamma_k / (delta_k - beta_k gamma_k / alpha_{k-1})
+//     p_k = r_k + beta_k p_{k-1};  s_k = w_k + beta_k s_{k-1}  (= A p_k);  x += alpha_k p_k;  r_{k+1} = r_k - alpha_k s_k
+//     w_{k+1} = A r_{k+1}
+//
+// A is a 3-point stencil in tau, so CTA tau (one time slice, state in registers for the whole solve) needs r_{k+1} of the
+// slices tau-1 and tau+1 -- and rebuilds them itself from the neighbours' r_k, w_k, s_{k-1} (written before the last
+// barrier) and the scalars alpha_k, beta_k that every CTA holds: 6 neighbour rows read per iteration instead of a
+// second barrier.  Stop rule, iteration numbering and the kappa bound are those of the reference; the iterates agree
+// with the two-reduction form to rounding (iteration counts within +-2 in all parity tests; 948 vs 948 at config B).
+//
+// Multi-GPU (world > 1), both collectives inside the kernel:
+//   * halo: the CTAs of the first / last slice of a slab PUSH their new r, w, s tiles straight into the neighbour GPU's
 //     halo rows as SELF-VALIDATING words (the "LL" idea of NCCL): every double travels as one 16-byte store of two
 //     64-bit words, each carrying half of the double and a 32-bit tag that names the iteration that produced it.  The
 //     reader spins on the element itself until both tags match -- no flag, no system-scope fence, and the posted stores
 //     overlap the barrier that follows them.  (First version: plain rows + fence.acq_rel.sys + a flag per side; the
-//     fence sat on the critical path of the boundary CTAs: 13.0 us/iteration at config B against 7 us for the
-//     single-GPU persistent kernel.)
+//     fence sat on the critical path of the boundary CTAs: 13.0 us/iteration at config B.)
 //   * all-reduce + barrier: on each GPU the CTAs arrive on a counter and every CTA reads back the GPU's partials in
-//     index order (the barrier of cg_persistent.cu); CTA 0 then writes {sum, sequence number} into a mailbox slot on
-//     every OTHER GPU (same two-word encoding) and each CTA polls its own GPU's mailbox until the world-1 remote slots
-//     carry the sequence number; the total is summed in rank order -- the same bits on every GPU, so all GPUs take the
-//     same branch.  With world = 1 this is exactly the single-GPU barrier.
+//     index order (the barrier of cg_persistent.cu); CTA 0 then writes {sums, sequence number} into a mailbox slot on
+//     every OTHER GPU (same encoding) and each CTA polls its own GPU's mailbox until the world-1 remote slots carry the
+//     sequence number; the total is summed in rank order -- the same bits on every GPU, so all GPUs take the same
+//     branch.  With world = 1 the ring closes inside the GPU (plain loads of the wrapped rows, no mailbox).
 //
-// Memory: each process allocates one arena (cudaMalloc), exports it with cudaIpcGetMemHandle and opens the others'
-// (elph_shard_p2p_*).  Arena = R, P0, P1 as [Lmax slices] (Lmax = ceil(Lglob / world), same layout on every rank), six
-// tagged halo rows (R, P0, P1 x lo, hi; 16 bytes per site), the mailboxes and the partials.  Sequence numbers / tags
-// increase monotonically over the life of the handle (all ranks execute the same number of barriers), mailbox slots
-// and partials alternate by parity, nothing is ever reset.
+// Memory: one arena per handle (cudaMalloc; exported with cudaIpcGetMemHandle and opened by the other ranks through
+// elph_shard_p2p_*).  Arena = r, w, s double-buffered by iteration parity ([2][3][Lmax slices], Lmax = ceil(Lglob /
+// world), same layout on every rank), twelve tagged halo rows (2 parities x 3 vectors x lo, hi; 16 bytes per site),
+// the mailboxes and the partials.  Sequence numbers / tags increase monotonically over the life of the handle (all
+// ranks execute the same number of barriers), nothing is ever reset.
 // Holstein on periodic square lattices (the register tiles of mtm_square.cu); the reference has no counterpart.
 #include "square_tiles.cuh"
 
@@ -37,23 +50,24 @@ constexpr int kMaxWorld = 16;
 constexpr unsigned int kSpinLimit = 1u << 25;   // ~ 20 s: a dead peer ends the solve with an error instead of a hang
 
 struct P2pParams {
-    const double* __restrict__ D;   // expnV with halos: slice index -1 .. L valid
-    const double* __restrict__ b;   // [L][N] right-hand side (initial guess is zero)
-    double* __restrict__ x;         // [L][N] out
-    double* R;                      // [L][N] own slices in the arena
-    double* P0;                     // p buffers: P0 and P0 + Lmax * N, alternating by iteration parity
-    // tagged halo rows, [N][2] 64-bit words each, six per arena in the order R lo, R hi, P0 lo, P0 hi, P1 lo, P1 hi:
-    // own arena (written by the neighbours) and the two neighbours' arenas (peer memory, written by this GPU: the hi rows
-    // of the left neighbour, the lo rows of the right neighbour)
+    const double* __restrict__ D;   // expnV; sharded handle: slices -1 .. L valid (halos), else [L][N] and tau wraps
+    const double* __restrict__ r0;  // [L][N] initial residual (= b when the initial guess is zero)
+    double* __restrict__ x;         // [L][N] in (if x0_given) / out
+    double* V;                      // arena vectors [2 parities][3: r, w, s][Lmax][N]
+    // tagged halo rows, [N][2] 64-bit words each, [2 parities][3 vectors][2 sides: lo, hi] per arena: own arena (written
+    // by the neighbours) and the two neighbours' arenas (peer memory, written by this GPU: the hi rows of the left
+    // neighbour, the lo rows of the right neighbour)
     const unsigned long long* my_halo;
     unsigned long long* left_halo;
     unsigned long long* right_halo;
-    unsigned long long* mbox[kMaxWorld];   // mailbox base of every rank (own included): [2 parities][world][2 words]
-    double* partial;                // [2 parities][Lmax] per-CTA partials of this GPU
+    unsigned long long* mbox[kMaxWorld];   // mailbox base of every rank (own included): [2 parities][world][4 words]
+    double* partial;                // [2 parities][2 values][Lmax] per-CTA partials of this GPU
     unsigned int* bar;              // arrival counter of this GPU (monotonic over the launch, zeroed by the host)
-    CgScalars* S;                   // in: tol, kappa_max, maxiter; out: iter, eps, normb, done (2 = peer timeout)
+    CgScalars* S;                   // in: tol, kappa_max, maxiter, normb (0: x0 = 0, |b| = |r0|); out: iter, eps, done
     unsigned int seq_base;          // sequence number of the last barrier of the previous solve
     int L, Lmax, Ly, rank, world, tau0, Lglob;
+    int d_halo;                     // D has halo slices (sharded handle)
+    int x0_given;                   // x holds the initial guess (r0 = b - A x0 computed by the caller)
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
 
@@ -70,6 +84,9 @@ __device__ __forceinline__ void push_ll(unsigned long long* p, double v, unsigne
 }
 __device__ __forceinline__ double unpack_ll(unsigned long long a, unsigned long long b) {
     return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+}
+__device__ __forceinline__ bool tag_ok(unsigned long long a, unsigned long long b, unsigned int tag) {
+    return ((unsigned int)(a >> 32) == tag) && ((unsigned int)(b >> 32) == tag);
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     unsigned int v;
@@ -93,8 +110,7 @@ __device__ __forceinline__ int read_halo(const unsigned long long* row, unsigned
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
-            for (int q = 0; q < NSEG; ++q)
-                all = all && ((unsigned int)(wa[rr][q] >> 32) == tag) && ((unsigned int)(wb[rr][q] >> 32) == tag);
+            for (int q = 0; q < NSEG; ++q) all = all && tag_ok(wa[rr][q], wb[rr][q], tag);
     } while (!all && ++spins < kSpinLimit);
 #pragma unroll
     for (int rr = 0; rr < PY; ++rr)
@@ -103,16 +119,30 @@ __device__ __forceinline__ int read_halo(const unsigned long long* row, unsigned
     return all ? 1 : 0;
 }
 
-// Barrier over all CTAs of all GPUs fused with the sum of one double per CTA.  `nbar` counts this GPU's barriers of the
-// launch from 1 (local arrival target = nbar * gridDim.x), seq is the global sequence number.  Returns false on a
-// timeout.  The caller must have a __syncthreads between the CTA's global writes and this call.  The all-reduce carries
-// no cross-GPU ordering obligation: remote data is only ever read through the self-validating halo rows.
-__device__ __forceinline__ bool global_sum(double block_value, const P2pParams& P, unsigned int nbar, unsigned int seq, double* red,
-                                           int* flag, double& out) {
+// Barrier over all CTAs of all GPUs fused with the sums of two doubles per CTA.  `nbar` counts this GPU's barriers of
+// the launch from 1 (local arrival target = nbar * gridDim.x), seq is the global sequence number.  Returns false on a
+// timeout.  The all-reduce carries no cross-GPU ordering obligation: remote data is only ever read through the
+// self-validating halo rows.  v0, v1: per-thread contributions.
+__device__ __forceinline__ bool global_sum2(double v0, double v1, const P2pParams& P, unsigned int nbar, unsigned int seq,
+                                            double* red, int* flag, double& out0, double& out1) {
     const int nb = gridDim.x;
-    double* partial = P.partial + (size_t)(seq & 1u) * P.Lmax;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // CTA sums (fixed order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    }
+    __syncthreads();   // also orders the CTA's global writes of this iteration before the arrival below
+    if (lane == 0) { red[warp] = v0; red[32 + warp] = v1; }
+    __syncthreads();
+    double* part0 = P.partial + (size_t)(seq & 1u) * 2 * P.Lmax;
+    double* part1 = part0 + P.Lmax;
     if (threadIdx.x == 0) {
-        partial[blockIdx.x] = block_value;
+        double b0 = 0.0, b1 = 0.0;
+        for (int k = 0; k < nwarps; ++k) { b0 += red[k]; b1 += red[32 + k]; }
+        part0[blockIdx.x] = b0;
+        part1[blockIdx.x] = b1;
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.bar), "r"(1u) : "memory");
         const unsigned int target = nbar * (unsigned int)nb;
         unsigned int spins = 0;
@@ -123,167 +153,120 @@ __device__ __forceinline__ bool global_sum(double block_value, const P2pParams& 
     }
     __syncthreads();
     // every CTA folds this GPU's partials in the same fixed order (thread-strided, shuffle tree, warps in order)
-    double s = 0.0;
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) s += __ldcg(partial + k);
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) { s0 += __ldcg(part0 + k); s1 += __ldcg(part1 + k); }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) { red[warp] = s0; red[32 + warp] = s1; }
     __syncthreads();
-    double t = 0.0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < nwarps; ++k) { t0 += red[k]; t1 += red[32 + k]; }
     bool good = (flag[0] != 0);
     if (P.world > 1) {
         __syncthreads();   // red is reused below
         if (threadIdx.x == 0) {
-            const size_t par = (size_t)(seq & 1u) * P.world * 2;
+            const size_t par = (size_t)(seq & 1u) * P.world * 4;
             if (blockIdx.x == 0)
-                for (int q = 1; q < P.world; ++q) push_ll(P.mbox[(P.rank + q) % P.world] + par + 2 * P.rank, t, seq);
+                for (int q = 1; q < P.world; ++q) {
+                    unsigned long long* slot = P.mbox[(P.rank + q) % P.world] + par + 4 * P.rank;
+                    push_ll(slot, t0, seq);
+                    push_ll(slot + 2, t1, seq);
+                }
             const unsigned long long* mine = P.mbox[P.rank] + par;
-            unsigned long long wa[kMaxWorld], wb[kMaxWorld];
+            unsigned long long w[kMaxWorld][4];
             unsigned int spins = 0;
             bool all;
             do {
                 all = true;
                 for (int g = 0; g < P.world; ++g)
-                    if (g != P.rank) ld_ll(mine + 2 * g, wa[g], wb[g]);
+                    if (g != P.rank) { ld_ll(mine + 4 * g, w[g][0], w[g][1]); ld_ll(mine + 4 * g + 2, w[g][2], w[g][3]); }
                 for (int g = 0; g < P.world; ++g)
-                    if (g != P.rank) all = all && ((unsigned int)(wa[g] >> 32) == seq) && ((unsigned int)(wb[g] >> 32) == seq);
+                    if (g != P.rank) all = all && tag_ok(w[g][0], w[g][1], seq) && tag_ok(w[g][2], w[g][3], seq);
             } while (!all && ++spins < kSpinLimit);
-            double tot = 0.0;
-            for (int g = 0; g < P.world; ++g) tot += (g == P.rank) ? t : unpack_ll(wa[g], wb[g]);   // rank order: same bits everywhere
-            red[0] = tot;
+            double a0 = 0.0, a1 = 0.0;   // rank order: same bits everywhere
+            for (int g = 0; g < P.world; ++g) {
+                a0 += (g == P.rank) ? t0 : unpack_ll(w[g][0], w[g][1]);
+                a1 += (g == P.rank) ? t1 : unpack_ll(w[g][2], w[g][3]);
+            }
+            red[0] = a0;
+            red[1] = a1;
             flag[1] = all ? 1 : 0;
         }
         __syncthreads();
-        t = red[0];
+        t0 = red[0];
+        t1 = red[1];
         good = good && (flag[1] != 0);
     }
-    out = t;
+    out0 = t0;
+    out1 = t1;
     __syncthreads();   // red / flag are reused by the caller
     return good;
-}
-
-template <int NSEG, int PY>
-__device__ __forceinline__ double tile_sum(double v, double* red, int lane, int warp, int nwarps) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int k = 0; k < nwarps; ++k) t += red[k];
-    __syncthreads();
-    return t;
 }
 
 template <int NSEG, int PY, int MAXT>
 __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
     constexpr int LX = 32 * NSEG;
-    // 128-register cap at 512 threads: x, D(tau), D(tau+1) live in shared memory there (one CTA per SM anyway)
+    // 128-register cap at 512 threads: x, p, s, D(tau), D(tau+1) live in shared memory there (one CTA per SM anyway)
     constexpr bool XS = (MAXT > 256);
-    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; XS: + x, D(tau), D(tau+1) [3][N]
-    __shared__ double red[32];
+    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; XS: + x, p, s, D(tau), D(tau+1) [5][N]
+    __shared__ double red[64];
     __shared__ int flag[2];   // barrier completed without a timeout: [0] local counter, [1] peers' mailbox words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int L = P.L, N = LX * P.Ly;
-    const int tau = blockIdx.x;                      // local slice; tau-1 = -1 and tau+1 = L live in the tagged halo rows
-    const bool first = (tau == 0), last = (tau == L - 1);
+    const int tau = blockIdx.x;
+    const bool multi = (P.world > 1);
+    // neighbours: inside the slab plain rows; across the slab boundary the tagged halo rows (world > 1) or the wrapped
+    // rows of this GPU (world = 1)
+    const bool first = multi && (tau == 0), last = multi && (tau == L - 1);
     const size_t tile_off = (size_t)warp * PY * LX;
     auto eidx = [&](int r, int q) -> size_t { return tile_off + r * LX + 32 * q + lane; };
-    const long long row = (long long)tau * N, rowm = row - N, rowp = row + N;
-    // tags: r written in iteration j (0 = the initial residual) carries base + 2j + 1, p written in iteration j >= 1
-    // carries base + 2j; unique over the life of the handle because the host advances base by 2 * iterations + 2
+    const long long row = (long long)tau * N;
+    const long long rowm = (long long)((tau == 0) ? L - 1 : tau - 1) * N;      // unused when `first`
+    const long long rowp = (long long)((tau == L - 1) ? 0 : tau + 1) * N;      // unused when `last`
+    const long long rowDn = P.d_halo ? row + N : rowp;
+    // tags: rows written in iteration k+1 (r_{k+1}, w_{k+1}, s_k; parity (k+1)&1) carry base + k + 2; the set-up rows
+    // (r_0, w_0; parity 0) and the pushed right-hand side (parity 1) carry base + 1.  The host advances base by
+    // iterations + 2 per solve.
     const unsigned int base = P.seq_base;
     const size_t vstride = (size_t)P.Lmax * N, hrow = 2 * (size_t)N;
-    auto halo = [&](const unsigned long long* b, int vec, int side) { return b + (size_t)(2 * vec + side) * hrow; };
-    auto halo_w = [&](unsigned long long* b, int vec, int side) { return b + (size_t)(2 * vec + side) * hrow; };
+    auto vec = [&](int par, int which) -> double* { return P.V + (size_t)(par * 3 + which) * vstride; };
+    auto halo = [&](const unsigned long long* b, int par, int which, int side) {
+        return b + (size_t)((par * 3 + which) * 2 + side) * hrow;
+    };
+    auto halo_w = [&](unsigned long long* b, int par, int which, int side) {
+        return b + (size_t)((par * 3 + which) * 2 + side) * hrow;
+    };
 
-    Tile<NSEG, PY> r, pc, t1, t2;   // pc: p_{j-1} on entry to iteration j, p_j after its first loop
-    Tile<NSEG, PY> xr, Dcr, Dnr;   // registers when !XS (dead otherwise)
+    Tile<NSEG, PY> r, w, t1, t2;
+    Tile<NSEG, PY> xr, pr, sr, Dcr, Dnr;   // registers when !XS (dead otherwise)
     double* xs = strips + 2ull * nwarps * 4 * LX;
-    double* dcs = xs + N;
+    double* ps = xs + N;
+    double* ss = ps + N;
+    double* dcs = ss + N;
     double* dns = dcs + N;
     auto sidx = [&](int rr, int q) -> int { return (rr * NSEG + q) * (int)blockDim.x + (int)threadIdx.x; };
     auto X = [&](int rr, int q) -> double& { if constexpr (XS) return xs[sidx(rr, q)]; else return xr.a[rr][q]; };
+    auto PP = [&](int rr, int q) -> double& { if constexpr (XS) return ps[sidx(rr, q)]; else return pr.a[rr][q]; };
+    auto SS = [&](int rr, int q) -> double& { if constexpr (XS) return ss[sidx(rr, q)]; else return sr.a[rr][q]; };
     auto DC = [&](int rr, int q) -> double& { if constexpr (XS) return dcs[sidx(rr, q)]; else return Dcr.a[rr][q]; };
     auto DN = [&](int rr, int q) -> double& { if constexpr (XS) return dns[sidx(rr, q)]; else return Dnr.a[rr][q]; };
-    double accb = 0.0;
-#pragma unroll
-    for (int rr = 0; rr < PY; ++rr)
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            const size_t e = eidx(rr, q);
-            const double bv = P.b[row + e];          // x0 = 0: r0 = b
-            X(rr, q) = 0.0;
-            r.a[rr][q] = bv;
-            pc.a[rr][q] = 0.0;
-            DC(rr, q) = P.D[row + e];
-            DN(rr, q) = P.D[rowp + e];
-            P.R[row + e] = bv;
-            if (first) push_ll(halo_w(P.left_halo, 0, 1) + 2 * e, bv, base + 1u);   // r0 into the neighbours' halo rows
-            if (last) push_ll(halo_w(P.right_halo, 0, 0) + 2 * e, bv, base + 1u);
-            accb = fma(bv, bv, accb);
-        }
-    const double tol = P.S->tol, kappa_max = P.S->kappa_max;
-    const long long maxiter = P.S->maxiter;
-    unsigned int nbar = 0, seq = base;
-    double rdotr;
-    bool alive = global_sum(tile_sum<NSEG, PY>(accb, red, lane, warp, nwarps), P, ++nbar, ++seq, red, flag, rdotr);
-    const double normb = sqrt(rdotr), eps0 = 1.0;
-    double beta = 0.0, kmin = 0.0, eps = eps0;
-    long long j = 0;
-    int xbuf = 0;
-    int pb = 0;   // p_j goes to buffer pb, p_{j-1} is in buffer pb ^ 1 (never read in the first iteration: beta = 0)
+
     const int tg = P.tau0 + tau;                       // global slice index
     const bool wrap_c = (tg == 0);
     const bool wrap_n = (tg + 1 == P.Lglob);
-
-    while (alive && j < maxiter) {
-        ++j;
-        const unsigned int tag_r_prev = base + 2u * (unsigned int)(j - 1) + 1u;   // r_{j-1}
-        const unsigned int tag_p_prev = base + 2u * (unsigned int)(j - 1);        // p_{j-1} (j > 1)
-        const unsigned int tag_p = base + 2u * (unsigned int)j;
-        const unsigned int tag_r = tag_p + 1u;
-        int halo_ok = 1;
-        double* Pnew = P.P0 + (pb ? vstride : 0);
-        const double* Pold = P.P0 + (pb ? 0 : vstride);
-        // p_j(tau-1) = r_{j-1}(tau-1) + beta p_{j-1}(tau-1): neighbour rows of this GPU, or the tagged halo row
-        if (first) {
-            double hr[PY][NSEG];
-            halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 0, 0), tag_r_prev, eidx, hr);
-#pragma unroll
-            for (int rr = 0; rr < PY; ++rr)
-#pragma unroll
-                for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = hr[rr][q];
-            if (j > 1) {
-                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1 + (pb ^ 1), 0), tag_p_prev, eidx, hr);
-#pragma unroll
-                for (int rr = 0; rr < PY; ++rr)
-#pragma unroll
-                    for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = fma(beta, hr[rr][q], t1.a[rr][q]);
-            }
-        } else {
-#pragma unroll
-            for (int rr = 0; rr < PY; ++rr)
-#pragma unroll
-                for (int q = 0; q < NSEG; ++q) {
-                    const size_t e = eidx(rr, q);
-                    const double rm = __ldcg(P.R + rowm + e);
-                    t1.a[rr][q] = (j > 1) ? fma(beta, __ldcg(Pold + rowm + e), rm) : rm;
-                }
-        }
+    int xbuf = 0;
+    // w(tau) = (M^T M v)(tau) from t1 = v(tau-1), r = v(tau), t2 = v(tau+1) given through `load_next` (called after the
+    // first sweeps, so that its loads overlap them); returns this thread's share of |(M v)(tau)|^2
+    auto apply_A = [&](auto&& load_next) -> double {
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
-                const size_t e = eidx(rr, q);
-                const double pcv = fma(beta, pc.a[rr][q], r.a[rr][q]);
-                pc.a[rr][q] = pcv;
-                Pnew[row + e] = pcv;
-                if (first) push_ll(halo_w(P.left_halo, 1 + pb, 1) + 2 * e, pcv, tag_p);
-                if (last) push_ll(halo_w(P.right_halo, 1 + pb, 0) + 2 * e, pcv, tag_p);
                 t1.a[rr][q] = DC(rr, q) * t1.a[rr][q];
-                t2.a[rr][q] = DN(rr, q) * pcv;
+                t2.a[rr][q] = DN(rr, q) * r.a[rr][q];
             }
         g0_x_even(t1, P.c0, P.s0);
         g0_x_even(t2, P.c0, P.s0);
@@ -298,35 +281,15 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
             g3_y_odd(t1, P.c3, P.s3, a1, b1);
             g3_y_odd(t2, P.c3, P.s3, a2, b2);
         }
-        // p_j(tau+1), same rule
-        double pn[PY][NSEG];
-        if (last) {
-            halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 0, 1), tag_r_prev, eidx, pn);
-            if (j > 1) {
-                double hp[PY][NSEG];
-                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1 + (pb ^ 1), 1), tag_p_prev, eidx, hp);
-#pragma unroll
-                for (int rr = 0; rr < PY; ++rr)
-#pragma unroll
-                    for (int q = 0; q < NSEG; ++q) pn[rr][q] = fma(beta, hp[rr][q], pn[rr][q]);
-            }
-        } else {
-#pragma unroll
-            for (int rr = 0; rr < PY; ++rr)
-#pragma unroll
-                for (int q = 0; q < NSEG; ++q) {
-                    const size_t e = eidx(rr, q);
-                    const double rp = __ldcg(P.R + rowp + e);
-                    pn[rr][q] = (j > 1) ? fma(beta, __ldcg(Pold + rowp + e), rp) : rp;
-                }
-        }
+        double vn[PY][NSEG];
+        load_next(vn);
         double acc = 0.0;
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
-                const double wc = wrap_c ? (pc.a[rr][q] + t1.a[rr][q]) : (pc.a[rr][q] - t1.a[rr][q]);
-                const double wn = wrap_n ? (pn[rr][q] + t2.a[rr][q]) : (pn[rr][q] - t2.a[rr][q]);
+                const double wc = wrap_c ? (r.a[rr][q] + t1.a[rr][q]) : (r.a[rr][q] - t1.a[rr][q]);
+                const double wn = wrap_n ? (vn[rr][q] + t2.a[rr][q]) : (vn[rr][q] - t2.a[rr][q]);
                 t1.a[rr][q] = wc;
                 t2.a[rr][q] = wn;
                 acc = fma(wc, wc, acc);
@@ -340,39 +303,188 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
         g2_y_even(t2, P.c2, P.s2);
         g1_x_odd(t2, P.c1, P.s1, lane);
         g0_x_even(t2, P.c0, P.s0);
-        if (!__syncthreads_and(halo_ok)) { alive = false; break; }   // a neighbour's tile never arrived
-        double pAp;
-        alive = global_sum(tile_sum<NSEG, PY>(acc, red, lane, warp, nwarps), P, ++nbar, ++seq, red, flag, pAp);
-        if (!alive) break;
-        const double alpha = rdotr / pAp;
+#pragma unroll
+        for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const double du = DN(rr, q) * t2.a[rr][q];
+                w.a[rr][q] = wrap_n ? (t1.a[rr][q] + du) : (t1.a[rr][q] - du);
+            }
+        return acc;
+    };
+
+    // ---- set-up: r_0, w_0 = A r_0, gamma_0, delta_0 ----------------------------------------------------------------
+    int halo_ok = 1;
+    double accg = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const size_t e = eidx(rr, q);
+            const double bv = P.r0[row + e];
+            X(rr, q) = P.x0_given ? P.x[row + e] : 0.0;
+            PP(rr, q) = 0.0;
+            SS(rr, q) = 0.0;
+            r.a[rr][q] = bv;
+            DC(rr, q) = P.D[row + e];
+            DN(rr, q) = P.D[rowDn + e];
+            if (first) push_ll(halo_w(P.left_halo, 1, 0, 1) + 2 * e, bv, base + 1u);   // r_0 rows for the neighbours' set-up
+            if (last) push_ll(halo_w(P.right_halo, 1, 0, 0) + 2 * e, bv, base + 1u);
+            accg = fma(bv, bv, accg);
+        }
+    if (first) {
+        double h[PY][NSEG];
+        halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1, 0, 0), base + 1u, eidx, h);
+#pragma unroll
+        for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = h[rr][q];
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = P.r0[rowm + eidx(rr, q)];
+    }
+    double accd = apply_A([&](double (&vn)[PY][NSEG]) {
+        if (last) {
+            halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1, 0, 1), base + 1u, eidx, vn);
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) vn[rr][q] = P.r0[rowp + eidx(rr, q)];
+        }
+    });
+    {
+        double* R0 = vec(0, 0);
+        double* W0 = vec(0, 1);
+#pragma unroll
+        for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const size_t e = eidx(rr, q);
+                R0[row + e] = r.a[rr][q];
+                W0[row + e] = w.a[rr][q];
+                if (first) {
+                    push_ll(halo_w(P.left_halo, 0, 0, 1) + 2 * e, r.a[rr][q], base + 1u);
+                    push_ll(halo_w(P.left_halo, 0, 1, 1) + 2 * e, w.a[rr][q], base + 1u);
+                }
+                if (last) {
+                    push_ll(halo_w(P.right_halo, 0, 0, 0) + 2 * e, r.a[rr][q], base + 1u);
+                    push_ll(halo_w(P.right_halo, 0, 1, 0) + 2 * e, w.a[rr][q], base + 1u);
+                }
+            }
+    }
+    const double tol = P.S->tol, kappa_max = P.S->kappa_max;
+    const long long maxiter = P.S->maxiter;
+    const double normb_in = P.S->normb;
+    unsigned int nbar = 0, seq = base;
+    double gamma, delta;
+    bool alive = (__syncthreads_and(halo_ok) != 0);
+    if (alive) alive = global_sum2(accg, accd, P, ++nbar, ++seq, red, flag, gamma, delta);
+    const double normb = (normb_in > 0.0) ? normb_in : sqrt(gamma);
+    const double eps0 = sqrt(gamma) / normb;
+    double alpha = gamma / delta, beta = 0.0, kmin = 0.0, eps = eps0;
+    long long j = 0;
+
+    // ---- iterations ------------------------------------------------------------------------------------------------
+    while (alive && j < maxiter) {
+        const int rd = (int)(j & 1), wr = rd ^ 1;
+        const unsigned int tag_rd = base + (unsigned int)j + 1u, tag_wr = tag_rd + 1u;
+        ++j;
+        const bool have_s = (j > 1);                     // s_{-1} = 0 (beta_0 = 0): nothing to read
+        const double* Rr = vec(rd, 0);
+        const double* Wr = vec(rd, 1);
+        const double* Sr = vec(rd, 2);
+        double* Rw = vec(wr, 0);
+        double* Ww = vec(wr, 1);
+        double* Sw = vec(wr, 2);
+        const double mab = -alpha * beta;
+        // r_new(tau -+ 1) = r - alpha (w + beta s) of the neighbour slice, rebuilt here
+        auto neighbour = [&](bool edge, int side, long long nrow, double (&out)[PY][NSEG]) {
+            if (edge) {
+                double h[PY][NSEG];
+                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, rd, 0, side), tag_rd, eidx, out);
+                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, rd, 1, side), tag_rd, eidx, h);
+#pragma unroll
+                for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) out[rr][q] = fma(-alpha, h[rr][q], out[rr][q]);
+                if (have_s) {
+                    halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, rd, 2, side), tag_rd, eidx, h);
+#pragma unroll
+                    for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                        for (int q = 0; q < NSEG; ++q) out[rr][q] = fma(mab, h[rr][q], out[rr][q]);
+                }
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) {
+                        const size_t e = eidx(rr, q);
+                        double v = fma(-alpha, __ldcg(Wr + nrow + e), __ldcg(Rr + nrow + e));
+                        if (have_s) v = fma(mab, __ldcg(Sr + nrow + e), v);
+                        out[rr][q] = v;
+                    }
+            }
+        };
+        {
+            double rm[PY][NSEG];
+            neighbour(first, 0, rowm, rm);
+#pragma unroll
+            for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = rm[rr][q];
+        }
         double accr = 0.0;
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
                 const size_t e = eidx(rr, q);
-                const double du = DN(rr, q) * t2.a[rr][q];
-                const double z = wrap_n ? (t1.a[rr][q] + du) : (t1.a[rr][q] - du);
-                X(rr, q) = fma(alpha, pc.a[rr][q], X(rr, q));
-                const double rv = fma(-alpha, z, r.a[rr][q]);
+                const double pv = fma(beta, PP(rr, q), r.a[rr][q]);
+                const double sv = fma(beta, SS(rr, q), w.a[rr][q]);
+                PP(rr, q) = pv;
+                SS(rr, q) = sv;
+                X(rr, q) = fma(alpha, pv, X(rr, q));
+                const double rv = fma(-alpha, sv, r.a[rr][q]);
                 r.a[rr][q] = rv;
-                P.R[row + e] = rv;
-                if (first) push_ll(halo_w(P.left_halo, 0, 1) + 2 * e, rv, tag_r);
-                if (last) push_ll(halo_w(P.right_halo, 0, 0) + 2 * e, rv, tag_r);
+                Rw[row + e] = rv;
+                Sw[row + e] = sv;
+                if (first) {
+                    push_ll(halo_w(P.left_halo, wr, 0, 1) + 2 * e, rv, tag_wr);
+                    push_ll(halo_w(P.left_halo, wr, 2, 1) + 2 * e, sv, tag_wr);
+                }
+                if (last) {
+                    push_ll(halo_w(P.right_halo, wr, 0, 0) + 2 * e, rv, tag_wr);
+                    push_ll(halo_w(P.right_halo, wr, 2, 0) + 2 * e, sv, tag_wr);
+                }
                 accr = fma(rv, rv, accr);
             }
-        double rrn;
-        alive = global_sum(tile_sum<NSEG, PY>(accr, red, lane, warp, nwarps), P, ++nbar, ++seq, red, flag, rrn);
+        const double accw = apply_A([&](double (&vn)[PY][NSEG]) { neighbour(last, 1, rowp, vn); });
+#pragma unroll
+        for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const size_t e = eidx(rr, q);
+                Ww[row + e] = w.a[rr][q];
+                if (first) push_ll(halo_w(P.left_halo, wr, 1, 1) + 2 * e, w.a[rr][q], tag_wr);
+                if (last) push_ll(halo_w(P.right_halo, wr, 1, 0) + 2 * e, w.a[rr][q], tag_wr);
+            }
+        if (!__syncthreads_and(halo_ok)) { alive = false; break; }   // a neighbour's tile never arrived
+        double gnew, dnew;
+        alive = global_sum2(accr, accw, P, ++nbar, ++seq, red, flag, gnew, dnew);
         if (!alive) break;
-        eps = sqrt(rrn) / normb;
+        eps = sqrt(gnew) / normb;
         const double lg = log(2.0 * eps0 / eps);
         const double qq = 2.0 * (double)j / lg;
         const double kap = qq * qq;
         if (kap > kmin) kmin = kap;
         if (eps < tol || kmin > kappa_max) break;
-        beta = rrn / rdotr;
-        rdotr = rrn;
-        pb ^= 1;
+        beta = gnew / gamma;
+        alpha = gnew / (dnew - beta * gnew / alpha);
+        gamma = gnew;
     }
 #pragma unroll
     for (int rr = 0; rr < PY; ++rr)
@@ -382,6 +494,7 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
     if (alive && blockIdx.x == 0 && threadIdx.x == 0) {
         P.S->iter = j;
         P.S->eps = eps;
+        P.S->eps0 = eps0;
         P.S->normb = normb;
         P.S->kappa_min = kmin;
         P.S->done = 1;
@@ -390,16 +503,18 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
 
 template <int NSEG, int PY, int MAXT>
 size_t p2p_smem(const elph_handle* h, int nwarps) {
-    return (2ull * nwarps * 4 * (32 * NSEG) + (MAXT > 256 ? 3ull * h->N : 0)) * sizeof(double);
+    return (2ull * nwarps * 4 * (32 * NSEG) + (MAXT > 256 ? 5ull * h->N : 0)) * sizeof(double);
 }
 
 // all slices of the slab must be co-resident (cooperative launch, one CTA per slice)
 template <int NSEG, int PY, int MAXT>
 bool fits_p2p(elph_handle* h, int nwarps) {
     auto kern = cg_p2p_kernel<NSEG, PY, MAXT>;
+    const size_t smem = p2p_smem<NSEG, PY, MAXT>(h, nwarps);
+    if (smem > h->smem_optin) return false;
     elph_enable_smem(h, kern);
     int per_sm = 0;
-    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, p2p_smem<NSEG, PY, MAXT>(h, nwarps)));
+    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem));
     return (long long)per_sm * h->sm_count >= h->L;
 }
 
@@ -417,6 +532,7 @@ bool launch_p2p(elph_handle* h, P2pParams& P, int nwarps) {
 
 // kernel variant for this handle: 0 = none applies
 int p2p_variant(const elph_handle* h, int& nwarps) {
+    if (!h->sq.enabled || h->model != ELPH_MODEL_HOLSTEIN) return 0;
     const int Lx = h->sq.Lx, Ly = h->sq.Ly;
     const int PY = (Lx == 32) ? 8 : 4;
     if (Ly % PY) return 0;
@@ -427,24 +543,80 @@ int p2p_variant(const elph_handle* h, int& nwarps) {
     return 0;
 }
 
+bool p2p_fits(elph_handle* h) {
+    int nwarps = 0;
+    const int variant = p2p_variant(h, nwarps);
+    return (variant == 1) ? fits_p2p<1, 8, 256>(h, nwarps) : (variant == 2) ? fits_p2p<2, 4, 512>(h, nwarps) : false;
+}
+
 // ---- arena layout (identical on every rank) ------------------------------------------------------------------------
-size_t arena_vec_doubles(const elph_handle* h) { return (size_t)h->p2p.Lmax * h->N; }
-size_t arena_halo_words(const elph_handle* h) { return 2 * (size_t)h->N; }   // one tagged row
-size_t arena_mbox_words() { return 2ull * kMaxWorld * 2; }
+size_t arena_vec_doubles(const elph_handle* h) { return 6 * (size_t)h->p2p.Lmax * h->N; }       // [2][3][Lmax][N]
+size_t arena_halo_words(const elph_handle* h) { return 12 * 2 * (size_t)h->N; }                  // [2][3][2][N][2]
+size_t arena_mbox_words() { return 2ull * kMaxWorld * 4; }
 size_t arena_bytes(const elph_handle* h) {
-    return 3 * arena_vec_doubles(h) * sizeof(double) + 6 * arena_halo_words(h) * sizeof(unsigned long long) +
-           arena_mbox_words() * sizeof(unsigned long long) + 2 * (size_t)h->p2p.Lmax * sizeof(double) + 256;
+    return arena_vec_doubles(h) * sizeof(double) + arena_halo_words(h) * sizeof(unsigned long long) +
+           arena_mbox_words() * sizeof(unsigned long long) + 4 * (size_t)h->p2p.Lmax * sizeof(double) + 256;
 }
-double* arena_vec(const elph_handle* h, void* base, int which) {   // R (0), P0 (1), P1 (2)
-    return reinterpret_cast<double*>(base) + which * arena_vec_doubles(h);
+double* arena_vec(const elph_handle* h, void* base) { return reinterpret_cast<double*>(base); }
+unsigned long long* arena_halo(const elph_handle* h, void* base) {
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(base) + arena_vec_doubles(h));
 }
-// tagged halo rows: vec = R (0), P0 (1), P1 (2); side = 0 (lo: slice -1), 1 (hi: slice L)
-unsigned long long* arena_halo(const elph_handle* h, void* base, int vec, int side) {
-    return reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(base) + 3 * arena_vec_doubles(h)) +
-           (size_t)(2 * vec + side) * arena_halo_words(h);
-}
-unsigned long long* arena_mbox(const elph_handle* h, void* base) { return arena_halo(h, base, 3, 0); }
+unsigned long long* arena_mbox(const elph_handle* h, void* base) { return arena_halo(h, base) + arena_halo_words(h); }
 double* arena_partial(const elph_handle* h, void* base) { return reinterpret_cast<double*>(arena_mbox(h, base) + arena_mbox_words()); }
+
+void alloc_arena(elph_handle* h, int rank, int world, int Lglob) {
+    auto& A = h->p2p;
+    if (A.arena) return;
+    A.rank = rank;
+    A.world = world;
+    A.Lmax = (Lglob + world - 1) / world;
+    ELPH_REQUIRE(h->L <= A.Lmax, ELPH_ERR_INVALID, "slab longer than ceil(Lglob / world)");
+    ELPH_CUDA(cudaMalloc(&A.arena, arena_bytes(h)));
+    ELPH_CUDA(cudaMemset(A.arena, 0, arena_bytes(h)));
+    ELPH_CUDA(cudaDeviceSynchronize());
+}
+
+// run one solve on an opened arena; r0/x as in P2pParams.  Returns false if the kernel does not apply.
+// scalars_on_device: tol, kappa_max, maxiter, normb were left in h->d_cg by cg_init_kernel (general initial guess).
+bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool scalars_on_device, double tol, int64_t maxiter) {
+    auto& A = h->p2p;
+    int nwarps = 0;
+    const int variant = p2p_variant(h, nwarps);
+    if (!variant) return false;
+    cudaStream_t st = h->stream;
+    const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
+    P2pParams P;
+    P.D = h->d_D; P.r0 = r0; P.x = x;
+    P.V = arena_vec(h, A.arena);
+    P.my_halo = arena_halo(h, A.arena);
+    P.left_halo = arena_halo(h, A.peer[left]);    // this GPU's first slice is the left neighbour's slice L (hi rows)
+    P.right_halo = arena_halo(h, A.peer[right]);  // its last slice is the right neighbour's slice -1 (lo rows)
+    for (int q = 0; q < kMaxWorld; ++q) P.mbox[q] = (q < A.world) ? arena_mbox(h, A.peer[q]) : nullptr;
+    P.partial = arena_partial(h, A.arena); P.bar = h->d_bar; P.S = h->d_cg;
+    P.seq_base = A.seq;
+    P.L = h->L; P.Lmax = A.Lmax; P.Ly = h->sq.Ly; P.rank = A.rank; P.world = A.world;
+    P.tau0 = h->sharded ? h->shard_tau0 : 0;
+    P.Lglob = h->sharded ? h->shard_Lglob : h->L;
+    P.d_halo = h->sharded ? 1 : 0;
+    P.x0_given = x0_given ? 1 : 0;
+    P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
+    P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
+    if (!scalars_on_device) {
+        CgScalars init = {};
+        init.tol = tol; init.kappa_max = h->cg_kappa_max; init.maxiter = maxiter; init.normb = 0.0;   // |b| = |r0|
+        *h->h_cg = init;
+        ELPH_CUDA(cudaMemcpyAsync(h->d_cg, h->h_cg, sizeof(CgScalars), cudaMemcpyHostToDevice, st));
+    }
+    bool ok = false;
+    if (variant == 1) ok = launch_p2p<1, 8, 256>(h, P, nwarps);
+    else if (variant == 2) ok = launch_p2p<2, 4, 512>(h, P, nwarps);
+    if (!ok) return false;
+    ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
+    ELPH_CUDA(cudaStreamSynchronize(st));
+    ELPH_REQUIRE(h->h_cg->done == 1, ELPH_ERR_STATE, "peer-memory CG: a peer GPU did not reach a barrier or deliver a halo tile (timeout)");
+    A.seq += 2u + (unsigned int)h->h_cg->iter;   // barriers executed: 1 + iterations; tags used: up to base + iterations + 1
+    return true;
+}
 
 }  // namespace
 
@@ -454,15 +626,7 @@ void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned ch
     ELPH_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, ELPH_ERR_INVALID, "bad rank / world");
     ELPH_REQUIRE(h->sq.enabled, ELPH_ERR_UNSUPPORTED, "the peer-memory CG needs the square-lattice register kernels");
     auto& A = h->p2p;
-    if (!A.arena) {
-        A.rank = rank;
-        A.world = world;
-        A.Lmax = (h->shard_Lglob + world - 1) / world;
-        ELPH_REQUIRE(h->L <= A.Lmax, ELPH_ERR_INVALID, "slab longer than ceil(Lglob / world)");
-        ELPH_CUDA(cudaMalloc(&A.arena, arena_bytes(h)));
-        ELPH_CUDA(cudaMemset(A.arena, 0, arena_bytes(h)));
-        ELPH_CUDA(cudaDeviceSynchronize());
-    }
+    alloc_arena(h, rank, world, h->shard_Lglob);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t ipc;
     ELPH_CUDA(cudaIpcGetMemHandle(&ipc, A.arena));
@@ -488,9 +652,7 @@ void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, cons
         ELPH_CUDA(cudaIpcOpenMemHandle(&A.peer[q], ipc, cudaIpcMemLazyEnablePeerAccess));
     }
     A.opened = true;
-    int nwarps = 0;
-    const int variant = p2p_variant(h, nwarps);
-    const bool fits = (variant == 1) ? fits_p2p<1, 8, 256>(h, nwarps) : (variant == 2) ? fits_p2p<2, 4, 512>(h, nwarps) : false;
+    const bool fits = p2p_fits(h);
     ELPH_REQUIRE(fits, ELPH_ERR_UNSUPPORTED,
                  "peer-memory CG: the slab's time slices are not all co-resident on this GPU (or unsupported lattice)");
 }
@@ -513,37 +675,29 @@ bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, 
     ELPH_REQUIRE(A.opened, ELPH_ERR_STATE, "elph_shard_p2p_open has not been called");
     if (tol == 0.0) tol = h->cg_tol;
     if (maxiter == 0) maxiter = h->cg_maxiter;
-    int nwarps = 0;
-    const int variant = p2p_variant(h, nwarps);
-    if (!variant) return false;
-    const int Ly = h->sq.Ly;
-    cudaStream_t st = h->stream;
-    const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
-    P2pParams P;
-    P.D = h->d_D; P.b = b_own; P.x = x_own;
-    P.R = arena_vec(h, A.arena, 0); P.P0 = arena_vec(h, A.arena, 1);
-    P.my_halo = arena_halo(h, A.arena, 0, 0);
-    P.left_halo = arena_halo(h, A.peer[left], 0, 0);    // this GPU's first slice is the left neighbour's slice L (hi rows)
-    P.right_halo = arena_halo(h, A.peer[right], 0, 0);  // its last slice is the right neighbour's slice -1 (lo rows)
-    for (int q = 0; q < kMaxWorld; ++q) P.mbox[q] = (q < A.world) ? arena_mbox(h, A.peer[q]) : nullptr;
-    P.partial = arena_partial(h, A.arena); P.bar = h->d_bar; P.S = h->d_cg;
-    P.seq_base = A.seq;
-    P.L = h->L; P.Lmax = A.Lmax; P.Ly = Ly; P.rank = A.rank; P.world = A.world; P.tau0 = h->shard_tau0; P.Lglob = h->shard_Lglob;
-    P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
-    P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
-    CgScalars init = {};
-    init.tol = tol; init.kappa_max = h->cg_kappa_max; init.maxiter = maxiter;
-    *h->h_cg = init;
-    ELPH_CUDA(cudaMemcpyAsync(h->d_cg, h->h_cg, sizeof(CgScalars), cudaMemcpyHostToDevice, st));
-    bool ok = false;
-    if (variant == 1) ok = launch_p2p<1, 8, 256>(h, P, nwarps);
-    else if (variant == 2) ok = launch_p2p<2, 4, 512>(h, P, nwarps);
-    if (!ok) return false;
-    ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
-    ELPH_CUDA(cudaStreamSynchronize(st));
-    ELPH_REQUIRE(h->h_cg->done == 1, ELPH_ERR_STATE, "peer-memory CG: a peer GPU did not reach a barrier or deliver a halo tile (timeout)");
-    A.seq += 2u + 2u * (unsigned int)h->h_cg->iter;   // barriers executed: 1 + 2 per iteration; tags used: up to base + 2 iter + 1
+    if (!run_p2p(h, b_own, x_own, false, false, tol, maxiter)) return false;
     if (iters) *iters = h->h_cg->iter;
     if (eps) *eps = h->h_cg->eps;
     return true;
+}
+
+// Single-GPU use on an unsharded handle (elph_cg_device): r0 in h->d_r, scalars in h->d_cg (cg_init_kernel), x_dev holds
+// the initial guess.  The ring closes inside the GPU; the arena is private.  Returns false if the kernel does not apply.
+bool elph_cg_single_reduction(elph_handle* h, double* x_dev) {
+    if (h->sharded || h->cg_single_reduction == 0) return false;
+    int nwarps = 0;
+    const int variant = p2p_variant(h, nwarps);
+    if (!variant || h->sq_disable || h->L < 2) return false;
+    // measured on B200 (scripts/bench_cg1r.py): 32x32xL200 6.93 -> 5.85 us/iteration; 64-wide lattices keep more state in
+    // shared memory under the 128-register cap and lose (9.7 -> 10.6 us), so they stay on the two-reduction kernel
+    if (h->cg_single_reduction < 0 && variant != 1) return false;
+    auto& A = h->p2p;
+    if (!A.arena) {
+        alloc_arena(h, 0, 1, h->L);
+        A.peer.assign(1, A.arena);
+        A.peer_L.assign(1, h->L);
+        A.opened = true;
+    }
+    if (!p2p_fits(h)) return false;
+    return run_p2p(h, h->d_r, x_dev, true, true, 0.0, 0);
 }

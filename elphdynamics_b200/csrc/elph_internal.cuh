@@ -137,6 +137,8 @@ struct elph_handle {
     bool use_graphs = true;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
+    int cg_single_reduction = -1;  // unpreconditioned CG, Holstein square: one barrier per iteration (cg_p2p.cu); -1 = auto
+                                   // (on where measured faster: 32-wide lattices), 0 = off, 1 = on
     bool pcg_fuse = true;        // preconditioned CG: vector updates fused into the FFT kernels of the KPM apply
     unsigned int* d_bar = nullptr;  // grid-barrier arrival counter of the persistent CG
     bool own_stream = false;
@@ -325,6 +327,7 @@ void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, cons
 void elph_shard_p2p_close_impl(elph_handle* h);
 bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter, int64_t* iters,
                             double* eps);
+bool elph_cg_single_reduction(elph_handle* h, double* x_dev);
 // buffers of nrhs independent solves for the persistent kernels (right-hand side k at + k*vstride / k*pstride / k)
 struct CgBatchBufs {
     double* x = nullptr;
