@@ -89,6 +89,8 @@ def load() -> C.CDLL:
         "elph_create": (i32, [C.POINTER(Config), C.POINTER(H)]),
         "elph_destroy": (i32, [H]),
         "elph_set_stream": (i32, [H, C.c_void_p]),
+        "elph_host_register": (i32, [H, C.c_void_p, i64]),
+        "elph_host_unregister": (i32, [H, C.c_void_p]),
         "elph_synchronize": (i32, [H]),
         "elph_set_solver": (i32, [H, dbl, i64, dbl]),
         "elph_kpm_configure": (i32, [H, i64, dbl, dbl, dbl]),

@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose and out:
             print(out)
         objs.append(str(obj))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart",
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lpthread",
            "-Xlinker", f"--version-script={CSRC / 'exports.map'}"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

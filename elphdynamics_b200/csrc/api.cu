@@ -4,6 +4,7 @@
 // device path and copy out.  There is no CPU implementation of any operator here.
 #include "elph_internal.cuh"
 
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -237,6 +238,7 @@ void build(elph_handle* h, const elph_config* c) {
     h->d_p[0] = zeros(h->Ndim);
     h->d_p[1] = zeros(h->Ndim);
     h->d_z = zeros(h->Ndim);
+    { const char* tr = getenv("ELPH_TRACE"); h->trace = tr && tr[0] == '1'; }
     h->partial_cap = std::max(std::max(4 * h->sm_count, 4 * h->L + 8), h->N / 4 + 8);
     h->d_partial = zeros(h->partial_cap);
     h->d_ticket = elph_dalloc<unsigned int>(1);
@@ -369,6 +371,24 @@ int32_t elph_set_stream(elph_handle* h, void* cuda_stream) {
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
         h->own_stream = false;
         h->stream = (cudaStream_t)cuda_stream;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_host_register(elph_handle* h, void* host_ptr, int64_t bytes) {
+    ENTER(h) {
+        ELPH_REQUIRE(host_ptr && bytes > 0, ELPH_ERR_INVALID, "null pointer or empty range");
+        ELPH_CUDA(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterDefault));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_host_unregister(elph_handle* h, void* host_ptr) {
+    ENTER(h) {
+        ELPH_REQUIRE(host_ptr, ELPH_ERR_INVALID, "null pointer");
+        ELPH_CUDA(cudaHostUnregister(host_ptr));
         return ELPH_OK;
     }
     ELPH_CATCH(h)
@@ -788,9 +808,11 @@ int32_t elph_langevin_step(elph_handle* h, int32_t method, double dt, const doub
                            elph_solve_info* info1, elph_solve_info* info2) {
     ENTER(h) {
         ELPH_REQUIRE(method == ELPH_LANGEVIN_EULER || g2, ELPH_ERR_INVALID, "g2 is required for the two-stage updates");
+        elph_trace_mark(h, nullptr);
         upload_vec(h, eta, h->d_vc, h->Nph);
         upload_vec(h, g1, h->d_g, h->N);
         if (g2) upload_vec(h, g2, h->d_g2, h->N);
+        elph_trace_mark(h, "upload eta, g1, g2");
         elph_langevin_step_dev(h, method, dt, h->d_vc, h->d_g, h->d_g2, arnoldi1, arnoldi2, use_precond != 0, iters, info1, info2);
         ELPH_CUDA(cudaStreamSynchronize(h->stream));
         return ELPH_OK;

@@ -4,7 +4,9 @@
 // calc_dSdx! :334-345, calc_dSfdx! :350-384.  Noise (eta, g) and the Arnoldi start values are injected.
 #include "elph_internal.cuh"
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 
 namespace {
 
@@ -32,6 +34,14 @@ __global__ void gather_primary_kernel(double* __restrict__ out, const double* __
 
 }  // namespace
 
+void elph_trace_mark(elph_handle* h, const char* label) {
+    if (!h->trace) return;
+    cudaStreamSynchronize(h->stream);
+    const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (label) fprintf(stderr, "[elph trace] %-28s %9.1f us\n", label, (now - h->trace_t0) * 1e6);
+    h->trace_t0 = now;
+}
+
 void elph_lincomb(elph_handle* h, double* out, double a, const double* X, double b, const double* Y, double c, const double* Z,
                   int64_t n) {
     const int blocks = (int)std::min<int64_t>((n + kT - 1) / kT, 8LL * h->sm_count);
@@ -51,15 +61,20 @@ void elph_gather_primary(elph_handle* h, double* out, const double* in) {
 // calc_dSdx!(dSdx, g, M^-1 g, model, P): src/LangevinDynamics.jl:334-384 with g injected
 void elph_calc_dSdx_dev(elph_handle* h, const double* g_dev, const double* arnoldi_host, bool use_precond, double* dSdx_dev,
                         double* Minv_dev, elph_solve_info* info) {
+    elph_trace_mark(h, "(before calc_dSdx)");
     if (use_precond && h->kpm.configured) elph_kpm_setup_impl(h, arnoldi_host, nullptr);  // setup!(P) :364
+    elph_trace_mark(h, "kpm setup");
     ELPH_CUDA(cudaMemsetAsync(Minv_dev, 0, h->Ndim * sizeof(double), h->stream));       // fill!(M^-1 g, 0) :365
     MatvecArgs m;
     m.v = g_dev;
     m.y = h->d_b;
     elph_launch_matvec(h, MODE_MT, m);                                                    // b = M^T g :373
+    elph_trace_mark(h, "b = M^T g");
     elph_solve_device(h, h->d_b, Minv_dev, use_precond, 1.0, info);                       // ldiv! :374
+    elph_trace_mark(h, "solve");
     // dSdx = -2 <dM/dx> + dSb/dx (shifted = true)   :378-381, :341
     elph_muldMdx_dev(h, g_dev, Minv_dev, dSdx_dev, -2.0, true, true);
+    elph_trace_mark(h, "force + dSb/dx");
 }
 
 void elph_langevin_step_dev(elph_handle* h, int method, double dt, const double* eta_dev, const double* g1_dev,
@@ -119,6 +134,7 @@ void elph_langevin_step_dev(elph_handle* h, int method, double dt, const double*
     } else {
         ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown Langevin update method");
     }
+    elph_trace_mark(h, "rest of the step");
     if (info1) *info1 = i1;
     if (info2) *info2 = i2;
 }

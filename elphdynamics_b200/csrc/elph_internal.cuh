@@ -135,6 +135,8 @@ struct elph_handle {
     std::vector<CgGraph> cg_graphs;
     int64_t kpm_version = 0;   // bumped whenever the KPM kernels' launch parameters change
     bool use_graphs = true;
+    bool trace = false;        // ELPH_TRACE=1: phase timings of the dynamics entry points on stderr (synchronises the stream)
+    double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
     int cg_single_reduction = -1;  // unpreconditioned CG, Holstein square: one barrier per iteration (cg_p2p.cu); -1 = auto
@@ -321,6 +323,8 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
 void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool use_precond, double tol_power,
                        elph_solve_info* info);
 bool elph_cg_persistent(elph_handle* h, double* x_dev);   // cg_persistent.cu
+// ELPH_TRACE=1 development aid: wall time since the previous mark, after draining the stream
+void elph_trace_mark(elph_handle* h, const char* label);
 // cg_p2p.cu
 void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned char* handle_out);
 void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, const int64_t* slab_lengths);

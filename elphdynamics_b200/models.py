@@ -99,6 +99,15 @@ class AbstractModel:
     def x(self, value):
         self._call("elph_set_x", ptr(_f64(value, self.Ndof, "x")))
 
+    def pin_host(self, array: np.ndarray):
+        """Page-lock a long-lived host array that is passed to the host-buffer entry points repeatedly (noise vectors,
+        right-hand sides): ``elph_host_register``.  Call ``unpin_host`` before the array goes away."""
+        assert array.flags["C_CONTIGUOUS"]
+        self._call("elph_host_register", C.c_void_p(array.ctypes.data), array.nbytes)
+
+    def unpin_host(self, array: np.ndarray):
+        self._call("elph_host_unregister", C.c_void_p(array.ctypes.data))
+
     def set_mu(self, mu):
         self.mu = _f64(mu, self.Nsites, "mu").copy()
         self._call("elph_set_mu", ptr(self.mu))

@@ -151,6 +151,12 @@ int32_t elph_destroy(elph_handle* h);
 /* launch all work of this handle on `cuda_stream` (a cudaStream_t); NULL = legacy default */
 int32_t elph_set_stream(elph_handle* h, void* cuda_stream);
 int32_t elph_synchronize(elph_handle* h);
+/* Page-lock a long-lived host array of the caller (a preallocated Julia Vector{Float64} that is passed to the host-buffer
+ * entry points again and again: noise vectors, right-hand sides) so that its copies run at full PCIe rate instead of
+ * through the driver's pageable staging path.  The reference has no counterpart (its arrays never leave the host).
+ * Unregister before the array is freed.  Registering the same range twice is an error of the CUDA runtime (status != 0). */
+int32_t elph_host_register(elph_handle* h, void* host_ptr, int64_t bytes);
+int32_t elph_host_unregister(elph_handle* h, void* host_ptr);
 
 /* Objects the reference constructs AFTER the model may also be configured after elph_create:
  *  - ConjugateGradient(tol, maxiter, kappa_max)            src/IterativeSolvers.jl:36-57  (0 keeps the current value)
