@@ -19,8 +19,10 @@
 // with the two-reduction form to rounding (iteration counts within +-2 in all parity tests; 948 vs 948 at config B).
 //
 // Multi-GPU (world > 1), both collectives inside the kernel:
-//   * halo: the CTAs of the first / last slice of a slab PUSH their new r, w, s tiles straight into the neighbour GPU's
-//     halo rows as SELF-VALIDATING words (the "LL" idea of NCCL): every double travels as one 16-byte store of two
+//   * halo: the CTAs of the first / last slice of a slab PUSH their new w tile straight into the neighbour GPU's halo
+//     row (only w crosses NVLink: the receiving CTA keeps its own copies of the neighbour's r and s rows and advances
+//     them with the owner's exact operations -- 3x fewer bytes than pushing r, w, s; measured at 64x64, 2 GPUs:
+//     16.4 -> see DESIGN.md us/iteration) as SELF-VALIDATING words (the "LL" idea of NCCL): every double travels as one 16-byte store of two
 //     64-bit words, each carrying half of the double and a 32-bit tag that names the iteration that produced it.  The
 //     reader spins on the element itself until both tags match -- no flag, no system-scope fence, and the posted stores
 //     overlap the barrier that follows them.  (First version: plain rows + fence.acq_rel.sys + a flag per side; the
@@ -33,7 +35,8 @@
 //
 // Memory: one arena per handle (cudaMalloc; exported with cudaIpcGetMemHandle and opened by the other ranks through
 // elph_shard_p2p_*).  Arena = r, w, s double-buffered by iteration parity ([2][3][Lmax slices], Lmax = ceil(Lglob /
-// world), same layout on every rank), twelve tagged halo rows (2 parities x 3 vectors x lo, hi; 16 bytes per site),
+// world), same layout on every rank), tagged halo rows (2 parities x lo, hi for w, plus the right-hand-side rows of the
+// set-up; 16 bytes per site), the boundary CTAs' private r / s copies of the neighbour rows,
 // the mailboxes and the partials.  Sequence numbers / tags increase monotonically over the life of the handle (all
 // ranks execute the same number of barriers), nothing is ever reset.
 // Holstein on periodic square lattices (the register tiles of mtm_square.cu); the reference has no counterpart.
@@ -62,6 +65,7 @@ struct P2pParams {
     unsigned long long* right_halo;
     unsigned long long* mbox[kMaxWorld];   // mailbox base of every rank (own included): [2 parities][world][4 words]
     double* partial;                // [2 parities][2 values][Lmax] per-CTA partials of this GPU
+    double* ghost;                  // [2 sides][2: r, s][N] the boundary CTAs' own copies of the neighbour GPU's r and s rows
     unsigned int* bar;              // arrival counter of this GPU (monotonic over the launch, zeroed by the host)
     CgScalars* S;                   // in: tol, kappa_max, maxiter, normb (0: x0 = 0, |b| = |r0|); out: iter, eps, done
     unsigned int seq_base;          // sequence number of the last barrier of the previous solve
@@ -332,13 +336,20 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
             if (last) push_ll(halo_w(P.right_halo, 1, 0, 0) + 2 * e, bv, base + 1u);
             accg = fma(bv, bv, accg);
         }
+    double* ghost_r_lo = P.ghost;
+    double* ghost_s_lo = P.ghost + N;
+    double* ghost_r_hi = P.ghost + 2 * (size_t)N;
+    double* ghost_s_hi = P.ghost + 3 * (size_t)N;
     if (first) {
         double h[PY][NSEG];
         halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1, 0, 0), base + 1u, eidx, h);
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
-            for (int q = 0; q < NSEG; ++q) t1.a[rr][q] = h[rr][q];
+            for (int q = 0; q < NSEG; ++q) {
+                t1.a[rr][q] = h[rr][q];
+                ghost_r_lo[eidx(rr, q)] = h[rr][q];
+            }
     } else {
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
@@ -348,6 +359,10 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
     double accd = apply_A([&](double (&vn)[PY][NSEG]) {
         if (last) {
             halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, 1, 0, 1), base + 1u, eidx, vn);
+#pragma unroll
+            for (int rr = 0; rr < PY; ++rr)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) ghost_r_hi[eidx(rr, q)] = vn[rr][q];
         } else {
 #pragma unroll
             for (int rr = 0; rr < PY; ++rr)
@@ -365,14 +380,8 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
                 const size_t e = eidx(rr, q);
                 R0[row + e] = r.a[rr][q];
                 W0[row + e] = w.a[rr][q];
-                if (first) {
-                    push_ll(halo_w(P.left_halo, 0, 0, 1) + 2 * e, r.a[rr][q], base + 1u);
-                    push_ll(halo_w(P.left_halo, 0, 1, 1) + 2 * e, w.a[rr][q], base + 1u);
-                }
-                if (last) {
-                    push_ll(halo_w(P.right_halo, 0, 0, 0) + 2 * e, r.a[rr][q], base + 1u);
-                    push_ll(halo_w(P.right_halo, 0, 1, 0) + 2 * e, w.a[rr][q], base + 1u);
-                }
+                if (first) push_ll(halo_w(P.left_halo, 0, 1, 1) + 2 * e, w.a[rr][q], base + 1u);
+                if (last) push_ll(halo_w(P.right_halo, 0, 1, 0) + 2 * e, w.a[rr][q], base + 1u);
             }
     }
     const double tol = P.S->tol, kappa_max = P.S->kappa_max;
@@ -403,20 +412,22 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
         // r_new(tau -+ 1) = r - alpha (w + beta s) of the neighbour slice, rebuilt here
         auto neighbour = [&](bool edge, int side, long long nrow, double (&out)[PY][NSEG]) {
             if (edge) {
-                double h[PY][NSEG];
-                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, rd, 0, side), tag_rd, eidx, out);
-                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, rd, 1, side), tag_rd, eidx, h);
+                // only w crosses NVLink: this CTA advances its own copies of the neighbour's s and r with the owner's
+                // exact operations (s_k = w_k + beta s_{k-1}, r_{k+1} = r_k - alpha s_k), each thread its own elements
+                double* gr = side ? ghost_r_hi : ghost_r_lo;
+                double* gs = side ? ghost_s_hi : ghost_s_lo;
+                halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, rd, 1, side), tag_rd, eidx, out);
 #pragma unroll
                 for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
-                    for (int q = 0; q < NSEG; ++q) out[rr][q] = fma(-alpha, h[rr][q], out[rr][q]);
-                if (have_s) {
-                    halo_ok &= read_halo<NSEG, PY>(halo(P.my_halo, rd, 2, side), tag_rd, eidx, h);
-#pragma unroll
-                    for (int rr = 0; rr < PY; ++rr)
-#pragma unroll
-                        for (int q = 0; q < NSEG; ++q) out[rr][q] = fma(mab, h[rr][q], out[rr][q]);
-                }
+                    for (int q = 0; q < NSEG; ++q) {
+                        const size_t e = eidx(rr, q);
+                        const double sv = have_s ? fma(beta, gs[e], out[rr][q]) : out[rr][q];
+                        const double rv = fma(-alpha, sv, gr[e]);
+                        gs[e] = sv;
+                        gr[e] = rv;
+                        out[rr][q] = rv;
+                    }
             } else {
 #pragma unroll
                 for (int rr = 0; rr < PY; ++rr)
@@ -452,14 +463,6 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
                 r.a[rr][q] = rv;
                 Rw[row + e] = rv;
                 Sw[row + e] = sv;
-                if (first) {
-                    push_ll(halo_w(P.left_halo, wr, 0, 1) + 2 * e, rv, tag_wr);
-                    push_ll(halo_w(P.left_halo, wr, 2, 1) + 2 * e, sv, tag_wr);
-                }
-                if (last) {
-                    push_ll(halo_w(P.right_halo, wr, 0, 0) + 2 * e, rv, tag_wr);
-                    push_ll(halo_w(P.right_halo, wr, 2, 0) + 2 * e, sv, tag_wr);
-                }
                 accr = fma(rv, rv, accr);
             }
         const double accw = apply_A([&](double (&vn)[PY][NSEG]) { neighbour(last, 1, rowp, vn); });
@@ -555,7 +558,7 @@ size_t arena_halo_words(const elph_handle* h) { return 12 * 2 * (size_t)h->N; } 
 size_t arena_mbox_words() { return 2ull * kMaxWorld * 4; }
 size_t arena_bytes(const elph_handle* h) {
     return arena_vec_doubles(h) * sizeof(double) + arena_halo_words(h) * sizeof(unsigned long long) +
-           arena_mbox_words() * sizeof(unsigned long long) + 4 * (size_t)h->p2p.Lmax * sizeof(double) + 256;
+           arena_mbox_words() * sizeof(unsigned long long) + (4 * (size_t)h->p2p.Lmax + 4 * (size_t)h->N) * sizeof(double) + 256;
 }
 double* arena_vec(const elph_handle* h, void* base) { return reinterpret_cast<double*>(base); }
 unsigned long long* arena_halo(const elph_handle* h, void* base) {
@@ -563,6 +566,7 @@ unsigned long long* arena_halo(const elph_handle* h, void* base) {
 }
 unsigned long long* arena_mbox(const elph_handle* h, void* base) { return arena_halo(h, base) + arena_halo_words(h); }
 double* arena_partial(const elph_handle* h, void* base) { return reinterpret_cast<double*>(arena_mbox(h, base) + arena_mbox_words()); }
+double* arena_ghost(const elph_handle* h, void* base) { return arena_partial(h, base) + 4 * (size_t)h->p2p.Lmax; }
 
 void alloc_arena(elph_handle* h, int rank, int world, int Lglob) {
     auto& A = h->p2p;
@@ -592,7 +596,7 @@ bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool sc
     P.left_halo = arena_halo(h, A.peer[left]);    // this GPU's first slice is the left neighbour's slice L (hi rows)
     P.right_halo = arena_halo(h, A.peer[right]);  // its last slice is the right neighbour's slice -1 (lo rows)
     for (int q = 0; q < kMaxWorld; ++q) P.mbox[q] = (q < A.world) ? arena_mbox(h, A.peer[q]) : nullptr;
-    P.partial = arena_partial(h, A.arena); P.bar = h->d_bar; P.S = h->d_cg;
+    P.partial = arena_partial(h, A.arena); P.ghost = arena_ghost(h, A.arena); P.bar = h->d_bar; P.S = h->d_cg;
     P.seq_base = A.seq;
     P.L = h->L; P.Lmax = A.Lmax; P.Ly = h->sq.Ly; P.rank = A.rank; P.world = A.world;
     P.tau0 = h->sharded ? h->shard_tau0 : 0;
