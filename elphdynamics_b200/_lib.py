@@ -131,6 +131,7 @@ def load() -> C.CDLL:
         "elph_hmc_refresh_phi": (i32, [H, dp, dp, dp]),
         "elph_hmc_calc_Oinv": (i32, [H, i32, dp, dbl, ip, C.POINTER(i32)]),
         "elph_hmc_calc_H": (i32, [H, dp, dp, dp]),
+        "elph_hmc_special_update": (i32, [H, i32, i64, i64, dp, dp, dp, i32, dbl, C.POINTER(i32), dp, dp, ip, C.POINTER(i32)]),
         "elph_hmc_calc_dSdx": (i32, [H, i32, dp]),
         "elph_hmc_update": (i32, [H, dbl, i64, i64, dbl, dp, dp, dp, dp, i32, dbl, C.POINTER(i32), dp, dp, dp, C.POINTER(i32)]),
         "elph_dev_mulMTM": (i32, [H, C.c_void_p, C.c_void_p]),

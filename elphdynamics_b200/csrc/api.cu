@@ -882,6 +882,32 @@ int32_t elph_hmc_calc_Oinv(elph_handle* h, int32_t use_precond, const double* ar
     ELPH_CATCH(h)
 }
 
+int32_t elph_hmc_special_update(elph_handle* h, int32_t kind, int64_t i, int64_t j, const double* R_plus, const double* R_minus,
+                                const double* arnoldi_noise, int32_t use_precond, double uniform, int32_t* accepted, double* S0,
+                                double* S1, int64_t* iters, int32_t* flag) {
+    ENTER(h) {
+        ELPH_REQUIRE(kind == 0 || kind == 1, ELPH_ERR_INVALID, "kind must be 0 (reflection) or 1 (swap)");
+        ELPH_REQUIRE(kind == 1 || h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
+                     "reflection updates exist for the Holstein model only (src/SpecialUpdates.jl:162-165)");
+        ELPH_REQUIRE(i >= 0 && i < h->Nph && (kind == 0 || (j >= 0 && j < h->Nph)), ELPH_ERR_INVALID, "phonon index out of range");
+        elph_hmc_ensure(h);
+        upload_vec(h, R_plus, h->hmc.Rp, h->N);
+        upload_vec(h, R_minus, h->hmc.Rm, h->N);
+        int acc = 0, fl = 0;
+        int64_t it = 0;
+        double s0 = 0.0, s1 = 0.0;
+        elph_hmc_special_update_dev(h, kind, (int)i, (int)j, use_precond != 0, arnoldi_noise, uniform, &acc, &s0, &s1, &it, &fl);
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        if (accepted) *accepted = acc;
+        if (S0) *S0 = s0;
+        if (S1) *S1 = s1;
+        if (iters) *iters = it;
+        if (flag) *flag = fl;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
 int32_t elph_hmc_calc_H(elph_handle* h, double* H, double* S, double* K) {
     ENTER(h) {
         elph_hmc_ensure(h);

@@ -391,6 +391,8 @@ void elph_hmc_free(elph_handle* h);
 void elph_hmc_refresh_v_dev(elph_handle* h, double alpha, const double* R_dev);
 double elph_hmc_refresh_phi_dev(elph_handle* h);
 void elph_hmc_calc_Oinv_dev(elph_handle* h, bool use_precond, const double* arnoldi_host, double power, int64_t* iters, int* flag);
+void elph_hmc_special_update_dev(elph_handle* h, int kind, int i, int j, bool use_precond, const double* arnoldi_host, double uniform,
+                                 int* accepted, double* S0_out, double* S1_out, int64_t* iters, int* flag);
 void elph_hmc_calc_H_dev(elph_handle* h, double* H, double* S, double* K);
 void elph_hmc_calc_dSfdx_dev(elph_handle* h, double* dS);
 void elph_hmc_update_dev(elph_handle* h, double dt, int Nt, int Nb, double alpha, const double* Rv_dev, bool use_precond,

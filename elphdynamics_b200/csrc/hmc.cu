@@ -196,6 +196,53 @@ void elph_hmc_calc_Oinv_dev(elph_handle* h, bool use_precond, const double* arno
     *flag = fl;
 }
 
+double elph_hmc_calc_Sf_dev(elph_handle* h);
+
+// field move of the special updates on the device copy of x ([tau][phonon]): kind 0 negates column i (reflection,
+// src/SpecialUpdates.jl:129), kind 1 exchanges columns i and j (swap, :269 / :335)
+__global__ void field_move_kernel(double* __restrict__ x, int L, int Nph, int kind, int i, int j) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L; t += gridDim.x * blockDim.x) {
+        double* row = x + (size_t)t * Nph;
+        if (kind == 0) {
+            row[i] = -row[i];
+        } else {
+            const double a = row[i];
+            row[i] = row[j];
+            row[j] = a;
+        }
+    }
+}
+
+// One proposal of special_update! (src/SpecialUpdates.jl:97-160 reflection, :233-290 and :296-366 swap): S0 from a
+// phi refresh with the injected R+- (already in S.Rp, S.Rm), the field move, update_model!, the two solves at tol^2,
+// S1 = Sf + Sb, Metropolis test with the injected uniform; the move is undone on rejection (or solver failure).
+void elph_hmc_special_update_dev(elph_handle* h, int kind, int i, int j, bool use_precond, const double* arnoldi_host, double uniform,
+                                 int* accepted, double* S0_out, double* S1_out, int64_t* iters, int* flag) {
+    auto move = [&]() {
+        field_move_kernel<<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->d_x, h->L, h->Nph, kind, i, j);
+        ELPH_CUDA(cudaGetLastError());
+        h->launches++;
+        elph_launch_update_model(h);
+    };
+    elph_launch_update_model(h);
+    const double S0 = elph_hmc_refresh_phi_dev(h);
+    move();
+    int64_t it = 0;
+    int fl = 0;
+    elph_hmc_calc_Oinv_dev(h, use_precond, arnoldi_host, 2.0, &it, &fl);
+    double sb = 0.0;
+    elph_Sb_dev(h, false, &sb);
+    const double S1 = elph_hmc_calc_Sf_dev(h) + sb;
+    const double P = std::min(1.0, std::exp(-(S1 - S0)));
+    const bool ok = (uniform < P) && fl == 0;
+    if (!ok) move();
+    *accepted = ok ? 1 : 0;
+    *S0_out = S0;
+    *S1_out = S1;
+    *iters = it;
+    *flag = fl;
+}
+
 double elph_hmc_calc_Sf_dev(elph_handle* h) {
     HmcState& S = h->hmc;
     return host_dot(h, S.Lphip, S.Op, h->Ndim) / 2 + host_dot(h, S.Lphim, S.Om, h->Ndim) / 2;

@@ -92,3 +92,50 @@ def update_(model, hmc: HybridMonteCarlo, fa, P=None, *, R_v, R_plus, R_minus, a
                 C.byref(acc), C.byref(it), C.byref(H0), C.byref(H1), C.byref(fl))
     hmc.accepted, hmc.H0, hmc.H1, hmc.flag = bool(acc.value), H0.value, H1.value, int(fl.value)
     return hmc.accepted, it.value
+
+
+class ReflectionUpdate:
+    """``ReflectionUpdate(model, freq, nsites)`` (src/SpecialUpdates.jl:40-91): active for Holstein models with phonons."""
+
+    def __init__(self, model, freq: int, nsites: int):
+        from .models import HolsteinModel
+        self.active = isinstance(model, HolsteinModel) and nsites > 0
+        self.freq = int(freq)
+        self.nsites = min(int(nsites), model.Nph) if self.active else 0
+
+
+class SwapUpdate:
+    """``SwapUpdate(model, freq, nbonds)`` (src/SpecialUpdates.jl:169-226)."""
+
+    def __init__(self, model, freq: int, nbonds: int):
+        self.active = not ((model.Nbonds == 0 or model.Nph == 0) and nbonds > 0)
+        self.freq = int(freq)
+        self.nbonds = min(model.Nbonds, int(nbonds))
+
+
+def special_update_(model, hmc: HybridMonteCarlo, upd, P=None, *, targets, R_plus, R_minus, uniforms, arnoldi_noises=None):
+    """``special_update!(model, hmc, update, P)`` (src/SpecialUpdates.jl:97-160, 233-366) with every random draw injected:
+    ``targets`` = the sampled sites (reflection; 0-based phonon columns) or pairs ``(i, j)`` of phonon columns (swap:
+    the two sites of each sampled bond for Holstein, the two sampled phonons for SSH), ``R_plus[k]``, ``R_minus[k]``,
+    ``uniforms[k]`` (and ``arnoldi_noises[k]`` with a preconditioner) the draws of proposal k.  One device call per
+    proposal.  Returns the acceptance ratio; ``hmc.special_log`` holds ``(accepted, S0, S1, iters, flag)`` per proposal."""
+    from .models import HolsteinModel
+    hmc.special_log = []
+    reflect = isinstance(upd, ReflectionUpdate)
+    if not upd.active or (reflect and not isinstance(model, HolsteinModel)):
+        return 0.0
+    n = len(targets)
+    accepted = 0.0
+    for k, tgt in enumerate(targets):
+        i, j = (int(tgt), 0) if reflect else (int(tgt[0]), int(tgt[1]))
+        acc, fl, it = C.c_int32(), C.c_int32(), C.c_int64()
+        S0, S1 = C.c_double(), C.c_double()
+        an = None
+        if _use_p(P):
+            an = ptr(_f64(arnoldi_noises[k], 2 * model.Nsites, "arnoldi_noise"))
+        model._call("elph_hmc_special_update", 0 if reflect else 1, i, j, ptr(_f64(R_plus[k], model.Ndim, "R_plus")),
+                    ptr(_f64(R_minus[k], model.Ndim, "R_minus")), an, _use_p(P), float(uniforms[k]), C.byref(acc), C.byref(S0),
+                    C.byref(S1), C.byref(it), C.byref(fl))
+        hmc.special_log.append((bool(acc.value), S0.value, S1.value, int(it.value), int(fl.value)))
+        accepted += float(acc.value)
+    return accepted / n if n else 0.0

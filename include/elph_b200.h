@@ -264,6 +264,15 @@ int32_t elph_hmc_refresh_phi(elph_handle* h, const double* R_plus, const double*
  * with tol^power; iters = cld(sum,2) when both converge; flag as ldiv! */
 int32_t elph_hmc_calc_Oinv(elph_handle* h, int32_t use_precond, const double* arnoldi_noise, double power, int64_t* iters,
                            int32_t* flag);
+/* One proposal of special_update!(model,hmc,update,P) src/SpecialUpdates.jl:97-160 (ReflectionUpdate, kind 0: x[:,i] = -x[:,i],
+ * Holstein only) and :233-366 (SwapUpdate, kind 1: swap!(x[:,i], x[:,j]); Holstein: the two sites of the sampled bond,
+ * SSH: two sampled phonons), entirely on the device: S0 = refresh_phi! with the injected R_plus / R_minus (Ndim each),
+ * the move, update_model!, calc_O^-1 Lambda phi! at tol^2 (arnoldi_noise: 2*Nsites values or NULL), S1 = calc_S,
+ * accept iff uniform < min(1, exp(-(S1-S0))) and flag == 0, else the move is undone.  i, j: 0-based phonon columns.
+ * The sampling of sites / bonds and the acceptance ratio stay with the caller (the RNG lives in Julia). */
+int32_t elph_hmc_special_update(elph_handle* h, int32_t kind, int64_t i, int64_t j, const double* R_plus, const double* R_minus,
+                                const double* arnoldi_noise, int32_t use_precond, double uniform, int32_t* accepted, double* S0,
+                                double* S1, int64_t* iters, int32_t* flag);
 /* calc_H(hmc,model,fa) src/HMC.jl:698: H = S + K, S = Sf + Sb, K = v.M.v/2 (SSH: primary fields only) */
 int32_t elph_hmc_calc_H(elph_handle* h, double* H, double* S, double* K);
 /* fill!(dSdx,0); calc_dSfdx!(hmc,model) [+ calc_dSbdx!(dSdx,model)] src/HMC.jl:749-814 */

@@ -269,3 +269,38 @@ def update(model, hmc, fa, cg, P, R_v, R_plus, R_minus, arnoldi_noises, uniform)
     if hmc.Nb == 1:
         return standard_update(model, hmc, fa, cg, P, R_v, R_plus, R_minus, arnoldi_noises, uniform)
     return multitimestep_update(model, hmc, fa, cg, P, R_v, R_plus, R_minus, arnoldi_noises, uniform)
+
+
+def special_update(model, hmc, cg, P, kind, targets, R_plus, R_minus, uniforms, arnoldi_noises=None):
+    """``special_update!`` (src/SpecialUpdates.jl:97-160 reflection, :233-290 Holstein swap, :296-366 SSH swap) with
+    the random draws injected: ``targets`` are 0-based phonon columns (reflection) or pairs of columns (swap).
+    Returns (acceptance ratio, log of (accepted, S0, S1, iters, flag))."""
+    L = model.L
+    x = model.x.reshape(-1, L)                 # host layout: column = phonon, tau fastest
+    log = []
+    accepted = 0.0
+    model.update_model()                       # :123 / :259 / :311
+
+    def move(t):
+        if kind == "reflect":
+            x[t] = -x[t]                       # :129
+        else:
+            i, j = t
+            tmp = x[i].copy()                  # swap!(x_i, x_j) :269, :335
+            x[i] = x[j]
+            x[j] = tmp
+        model.update_model()
+
+    for k, t in enumerate(targets):
+        S0 = refresh_phi(hmc, model, R_plus[k], R_minus[k])
+        move(t)
+        iters, flag = calc_Oinv(hmc, model, cg, P, 2.0, None if arnoldi_noises is None else arnoldi_noises[k])
+        S1 = calc_Sf(hmc) + calc_Sb(model)     # calc_S, src/HMC.jl:745-754
+        Pacc = min(1.0, math.exp(-(S1 - S0)))
+        ok = (uniforms[k] < Pacc) and flag == 0
+        if ok:
+            accepted += 1.0
+        else:
+            move(t)
+        log.append((ok, S0, S1, iters, flag))
+    return (accepted / len(targets) if len(targets) else 0.0), log

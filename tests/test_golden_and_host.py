@@ -138,3 +138,35 @@ def test_package_never_imports_the_oracle():
     for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
         if f.is_file():
             assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read_text(errors="ignore"), flags=re.M), f
+
+
+def test_phonon_text_format_host_logic(tmp_path, monkeypatch):
+    """write_phonons! / read_phonons! (src/HolsteinModels.jl:764-853) on a stand-in model without a device: line order
+    (l1 fastest among cells, orbit, tau innermost; 0-based cells, 1-based orbit and tau), '%.6f', partial overwrite."""
+    import elphdynamics_b200 as E
+    import elphdynamics_b200.phonon_io as pio
+    monkeypatch.setattr(pio, "update_model_", lambda m: None)
+
+    class Stub(E.HolsteinModel):
+        def __init__(self, lat, L):
+            self.lattice, self.Ltau = lat, L
+            self._x = np.sin(np.arange(lat.nsites * L, dtype=float))
+        x = property(lambda self: self._x.copy(), lambda self, v: setattr(self, "_x", np.asarray(v, float).copy()))
+
+        def __del__(self):
+            pass
+
+    lat = E.Lattice(E.UnitCell(2, 2), 3, 2)
+    m = Stub(lat, 4)
+    f = tmp_path / "p.out"
+    pio.write_phonons_(m, str(f))
+    lines = f.read_text().splitlines()
+    assert lines[0] == "L3 L2 L1 orbit tau x" and len(lines) == 1 + lat.nsites * 4
+    assert lines[1] == "0 0 0 1 1 0.000000" and lines[5] == "0 0 0 2 1 %.6f" % np.sin(4.0)
+    assert lines[1 + 2 * 4] == "0 0 1 1 1 %.6f" % np.sin(8.0)              # next cell along l1 = site 3 (1-based)
+    assert lines[1 + 6 * 4] == "0 1 0 1 1 %.6f" % np.sin(24.0)             # l2 advances after L1 = 3 cells
+    x0 = m.x
+    m.x = np.zeros_like(x0)
+    pio.read_phonons_(m, str(f))
+    assert np.abs(m.x - x0).max() <= 5e-7
+    assert np.array_equal(m.x, np.array([float("%.6f" % v) for v in x0]))

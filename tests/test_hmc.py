@@ -170,3 +170,86 @@ def test_gpu_hmc_trajectory(kind, Nb):
             assert np.array_equal(em.x, xe0) and np.array_equal(om.x, x0)   # rejected: fields restored bit-exactly
         assert relerr(he.get("v"), ho.v) <= 1e-6
     em.close()
+
+
+# ----------------------------------------------------------------------------- special updates (src/SpecialUpdates.jl)
+def test_oracle_special_updates_restore_on_reject_and_move_on_accept():
+    """Reflection / swap proposals: a rejected proposal restores the field bit for bit, an accepted one leaves exactly the
+    moved columns changed; S0 is the refreshed action (R+^2 + R-^2)/2 + Sb (src/SpecialUpdates.jl:97-160, 233-290)."""
+    from oracle.action import calc_Sb
+    om, rng = oracle_holstein("square", 2, 0.4, 0.1, mu=-0.2, tol=1e-7)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    h = ohmc.HybridMonteCarlo(om, 0.01, 0.05, 0.0, 1)
+    L = om.L
+    for kind, tgt in (("reflect", 1), ("swap", (0, 3))):
+        for uniform in (2.0, -1.0):          # forced reject, forced accept
+            x0 = om.x.copy()
+            Rp, Rm = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+            sb0 = calc_Sb(om)
+            ratio, log = ohmc.special_update(om, h, cg, None, kind, [tgt], [Rp], [Rm], [uniform])
+            ok, S0, S1, iters, flag = log[0]
+            assert flag == 0 and abs(S0 - (Rp @ Rp / 2 + Rm @ Rm / 2 + sb0)) <= 1e-12 * abs(S0)
+            X0, X1 = x0.reshape(-1, L), om.x.reshape(-1, L)
+            if uniform > 1.0:
+                assert not ok and ratio == 0.0 and np.array_equal(om.x, x0)
+            else:
+                assert ok and ratio == 1.0
+                if kind == "reflect":
+                    assert np.array_equal(X1[tgt], -X0[tgt])
+                    rest = [k for k in range(om.Nph) if k != tgt]
+                else:
+                    assert np.array_equal(X1[tgt[0]], X0[tgt[1]]) and np.array_equal(X1[tgt[1]], X0[tgt[0]])
+                    rest = [k for k in range(om.Nph) if k not in tgt]
+                assert np.array_equal(X1[rest], X0[rest])
+    # a reflection of every site of the particle-hole symmetric model (mu = lambda^2/omega^2 ... here: lambda -> -lambda
+    # symmetry) is not assumed; only the bookkeeping above is checked on the CPU.
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["holstein", "holstein-kpm", "ssh"])
+def test_gpu_special_updates(kind):
+    """special_update! proposals on the device against the oracle with identical injected noise: same S0, S1, decisions
+    and final field (moves are exact copies / sign flips, so the fields agree bit for bit)."""
+    import elphdynamics_b200 as E
+    from elphdynamics_b200 import hmc as ehmc
+    if kind.startswith("holstein"):
+        om, rng = oracle_holstein("square", 4, 0.6, 0.1, mu=-0.3, tol=1e-7)
+        em = engine_holstein_like(om)
+    else:
+        om, rng = oracle_ssh(Lside=4, beta=0.4, dtau=0.05, tol=1e-7)
+        em = engine_ssh_like(om)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    ho = ohmc.HybridMonteCarlo(om, 0.01, 0.05, 0.0, 1)
+    he = ehmc.HybridMonteCarlo(em, 0.01, 0.05, 0.0, 1)
+    use_p = kind.endswith("kpm")
+    Po = KPMPreconditioner(om) if use_p else None
+    Pe = E.SymmetricKPMPreconditioner(em) if use_p else None
+    nprop = 4
+    plans = []
+    if kind.startswith("holstein"):
+        sites = rng.integers(0, om.Nph, size=nprop).tolist()                     # sample!(rng, 1:Nph, sites)
+        plans.append(("reflect", ehmc.ReflectionUpdate(em, 1, nprop), sites))
+        bonds = rng.integers(0, om.Nbonds, size=nprop)                            # sample!(rng, 1:Nbonds, bonds)
+        nt = np.asarray(om.neighbor_table)
+        pairs = [(int(nt[0, b]) - (1 if nt.min() == 1 else 0), int(nt[1, b]) - (1 if nt.min() == 1 else 0)) for b in bonds]
+        plans.append(("swap", ehmc.SwapUpdate(em, 1, nprop), pairs))
+    else:
+        pairs = [tuple(int(v) for v in rng.choice(om.Nph, size=2, replace=False)) for _ in range(nprop)]
+        plans.append(("swap", ehmc.SwapUpdate(em, 1, nprop), pairs))
+        assert ehmc.special_update_(em, he, ehmc.ReflectionUpdate(em, 1, 3), None, targets=[0], R_plus=[None], R_minus=[None],
+                                    uniforms=[0.5]) == 0.0                        # no reflection update for SSH (:162-165)
+    for okind, upd, targets in plans:
+        assert upd.active
+        for uniforms in ([0.0] * nprop, [2.0] * nprop, rng.uniform(size=nprop).tolist()):
+            Rps = [rng.normal(size=om.Ndim) for _ in range(nprop)]
+            Rms = [rng.normal(size=om.Ndim) for _ in range(nprop)]
+            noises = [rng.normal(size=2 * om.N) for _ in range(nprop)] if use_p else None
+            r_o, log_o = ohmc.special_update(om, ho, cg, Po, okind, targets, Rps, Rms, uniforms, noises)
+            r_e = ehmc.special_update_(em, he, upd, Pe, targets=targets, R_plus=Rps, R_minus=Rms, uniforms=uniforms,
+                                       arnoldi_noises=noises)
+            assert r_e == r_o
+            for (ok_o, S0o, S1o, it_o, fl_o), (ok_e, S0e, S1e, it_e, fl_e) in zip(log_o, he.special_log):
+                assert ok_o == ok_e and fl_o == fl_e == 0 and abs(it_o - it_e) <= 2
+                assert abs(S0e - S0o) <= 1e-12 * abs(S0o) and abs(S1e - S1o) <= 1e-8 * abs(S1o)
+            assert np.array_equal(em.x, om.x)
+    em.close()
