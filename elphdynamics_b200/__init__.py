@@ -12,6 +12,7 @@ from .models import (ConjugateGradient, HolsteinModel, I, Identity, SSHModel, Sy
                      mulM_, mulMT_, mulMTM_, muldMdx_, setup_, solve_, update_Gr_, update_model_)
 from .dynamics import (EulerDynamics, FourierAccelerator, HeunsDynamics, RungeKuttaDynamics, TimeFreqFFT, calc_dSbdx_,
                        calc_dSdx_, calc_Sb, evolve_, fourier_accelerate_, omega_to_tau_, tau_to_omega_, update_M_, update_Q_)
+from . import greens, hmc
 from .phonon_io import read_phonons_, write_phonons_
 from . import workloads
 

@@ -130,6 +130,8 @@ def load() -> C.CDLL:
         "elph_hmc_refresh_v": (i32, [H, dbl, dp]),
         "elph_hmc_refresh_phi": (i32, [H, dp, dp, dp]),
         "elph_hmc_calc_Oinv": (i32, [H, i32, dp, dbl, ip, C.POINTER(i32)]),
+        "elph_greens_load": (i32, [H, i64, dp, dp]),
+        "elph_greens_setup": (i32, [H, i64, i64, i64, i64, i64, i64, dp, dp, dp, dp]),
         "elph_hmc_calc_H": (i32, [H, dp, dp, dp]),
         "elph_hmc_special_update": (i32, [H, i32, i64, i64, dp, dp, dp, i32, dbl, C.POINTER(i32), dp, dp, ip, C.POINTER(i32)]),
         "elph_hmc_calc_dSdx": (i32, [H, i32, dp]),

@@ -284,6 +284,7 @@ void destroy(elph_handle* h) {
     cudaDeviceSynchronize();
     elph_kpm_free(h);
     elph_hmc_free(h);
+    elph_greens_free(h);
     for (auto& g : h->cg_graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     h->cg_graphs.clear();
@@ -903,6 +904,26 @@ int32_t elph_hmc_special_update(elph_handle* h, int32_t kind, int64_t i, int64_t
         if (S1) *S1 = s1;
         if (iters) *iters = it;
         if (flag) *flag = fl;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// ------------------------------------------------------------ Green's-function estimator (src/GreensFunctions.jl)
+int32_t elph_greens_load(elph_handle* h, int64_t nv, const double* R, const double* MinvR) {
+    ENTER(h) {
+        ELPH_REQUIRE(nv >= 1 && R && MinvR, ELPH_ERR_INVALID, "nv >= 1 and non-null R, MinvR required");
+        elph_greens_load_impl(h, (int)nv, R, MinvR);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_greens_setup(elph_handle* h, int64_t n1, int64_t n2, int64_t L1, int64_t L2, int64_t L3, int64_t norbits, double* G_D0,
+                          double* G_D0_G_D0, double* G_DD_G_00, double* G_D0_G_0D) {
+    ENTER(h) {
+        double* const out[4] = {G_D0, G_D0_G_D0, G_DD_G_00, G_D0_G_0D};
+        elph_greens_setup_impl(h, (int)n1, (int)n2, (int)L1, (int)L2, (int)L3, (int)norbits, out);
         return ELPH_OK;
     }
     ELPH_CATCH(h)

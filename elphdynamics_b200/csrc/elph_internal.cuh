@@ -131,6 +131,7 @@ struct HostPipe {
 struct elph_handle {
     std::string err;
     HmcState hmc;
+    void* greens = nullptr;    // GreensState of greens.cu (Green's-function convolutions), allocated on first use
     HostPipe pipe;
     std::vector<CgGraph> cg_graphs;
     int64_t kpm_version = 0;   // bumped whenever the KPM kernels' launch parameters change
@@ -325,6 +326,10 @@ void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool 
 bool elph_cg_persistent(elph_handle* h, double* x_dev);   // cg_persistent.cu
 // ELPH_TRACE=1 development aid: wall time since the previous mark, after draining the stream
 void elph_trace_mark(elph_handle* h, const char* label);
+// greens.cu
+void elph_greens_free(elph_handle* h);
+void elph_greens_load_impl(elph_handle* h, int nv, const double* R, const double* MinvR);
+void elph_greens_setup_impl(elph_handle* h, int n1, int n2, int L1, int L2, int L3, int ns, double* const out[4]);
 // cg_p2p.cu
 void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned char* handle_out);
 void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, const int64_t* slab_lengths);

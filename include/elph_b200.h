@@ -285,6 +285,19 @@ int32_t elph_hmc_update(elph_handle* h, double dt, int64_t Nt, int64_t Nb, doubl
                         const double* R_minus, const double* arnoldi_noise, int32_t use_precond, double uniform,
                         int32_t* accepted, double* iters, double* H0, double* H1, int32_t* flag);
 
+/* ------------------------------------------------- Green's-function estimator */
+/* EstimateGreensFunction (src/GreensFunctions.jl:23-188).  elph_greens_load keeps the random vectors R and the solutions
+ * M^-1 R of update!(Gr, model, P) (:201-234; computed with elph_Minv_batch) on the device: nv vectors of Ndim doubles
+ * each, host layout, vector k at offset k * Ndim.  elph_greens_setup = setup!(estimator, n1, n2) (:239-296) with 0-based
+ * vector indices: the four convolve! calls (:361-414) -- antiperiodic_copy! / periodic_product! (:420-457), forward
+ * transforms over (omega, k1, k2, k3), a'[w,s2,k] b'[-w,s1,-k] / V, inverse transform -- entirely on the device.  Each
+ * output is a complex array (re, im interleaved) of Julia dimensions (2 Ltau, norbits, norbits, L1, L2, L3) in the
+ * reference's column-major order, i.e. exactly estimator.G... after setup!; NULL skips an output.  FFTW's conventions:
+ * forward unnormalised exp(-2 pi i jk/n), inverse scaled by 1/n.  Any Ltau; lattice extents up to 64 per axis. */
+int32_t elph_greens_load(elph_handle* h, int64_t nv, const double* R, const double* MinvR);
+int32_t elph_greens_setup(elph_handle* h, int64_t n1, int64_t n2, int64_t L1, int64_t L2, int64_t L3, int64_t norbits, double* G_D0,
+                          double* G_D0_G_D0, double* G_DD_G_00, double* G_D0_G_0D);
+
 /* --------------------------------------------------- device-resident (bench) API */
 /* Device pointers, engine layout [tau][site], asynchronous on the handle's stream. */
 int32_t elph_dev_mulMTM(elph_handle* h, const double* v_dev, double* y_dev);

@@ -243,3 +243,30 @@ def test_fourier_acceleration_is_diagonal_in_frequency():
     assert np.abs(a - fa.accelerate(v, 1.0)).max() < 1e-13
     assert np.abs(fa.accelerate(fa.accelerate(v, 1.0), -1.0) - v).max() < 1e-12
     assert fa.Q.reshape(N, L)[0, 0] > fa.Q.reshape(N, L)[0, L // 2] >= 1.0 - 1e-12   # slow modes accelerated most
+
+
+def test_greens_convolution_is_the_antiperiodic_correlation_sum():
+    """convolve! (src/GreensFunctions.jl:361-414) restated with numpy.fft equals the definition it implements,
+    (a * b)[D, s2, s1] = (1/V) sum_i a(i + D, s2) b(i, s1) over the doubled time axis and the cells, V = 2 L N / n_s;
+    with antiperiodic_copy! inputs this is the antiperiodic G(tau + beta) = -G(tau)."""
+    from oracle import greens as og
+    om, rng = oracle_holstein("honeycomb", 3, 0.4, 0.1)
+    Gr = og.EstimateGreensFunction(om, 2)
+    L, ns, L1, L2, L3 = Gr.L, Gr.ns, Gr.L1, Gr.L2, Gr.L3
+    x, y = rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    a = og.antiperiodic_copy(x, L).reshape(L3, L2, L1, ns, 2 * L)
+    b = og.antiperiodic_copy(y, L).reshape(L3, L2, L1, ns, 2 * L)
+    c = og.convolve(a, b, Gr)
+    V = 2 * L * Gr.N / ns
+    for (d3, d2, d1, s1, s2, dt) in ((0, 1, 2, 0, 1, 3), (0, 2, 0, 1, 1, 0), (0, 0, 1, 1, 0, 7)):
+        tot = 0.0
+        for k2 in range(L2):
+            for k1 in range(L1):
+                for t in range(2 * L):
+                    tot += a[0, (k2 + d2) % L2, (k1 + d1) % L1, s2, (t + dt) % (2 * L)] * b[0, k2, k1, s1, t]
+        assert abs(c[d3, d2, d1, s1, s2, dt] - tot / V) <= 1e-13
+        # antiperiodicity in the time displacement
+        assert abs(c[d3, d2, d1, s1, s2, dt] + c[d3, d2, d1, s1, s2, (dt + L) % (2 * L)]) <= 1e-13
+    # periodic_product!: both halves equal
+    z = og.periodic_product(x, y, L)
+    assert np.array_equal(z[:, :L], z[:, L:]) and np.array_equal(z[:, :L], (x * y).reshape(-1, L))
