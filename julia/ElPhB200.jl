@@ -111,6 +111,38 @@ function update!(est::EstimateGreensFunction, g::B200Model, P=I)
     nothing
 end
 
+# --- Green's-function convolutions: setup!(estimator, n1, n2) src/GreensFunctions.jl:239-296 on the device ---------
+# (after update! above: R and M⁻¹R are uploaded once per measurement, the four 6-dimensional arrays come back per pair)
+function load!(est::EstimateGreensFunction, g::B200Model)
+    check(ccall((:elph_greens_load, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), g.h, est.nᵥ, est.R, est.M⁻¹R), g.h)
+end
+function setup!(est::EstimateGreensFunction, g::B200Model, n₁::Int, n₂::Int)
+    est.n₁ = n₁; est.n₂ = n₂
+    check(ccall((:elph_greens_setup, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                g.h, n₁ - 1, n₂ - 1, est.L₁, est.L₂, est.L₃, est.nₛ, est.GΔ0, est.GΔ0_GΔ0, est.GΔΔ_G00, est.GΔ0_G0Δ), g.h)
+    nothing
+end
+
+# --- special updates: src/SpecialUpdates.jl:97-160 (reflection), :233-366 (swap); one device call per proposal ------
+# kind 0: x[:,i] = -x[:,i] (Holstein); kind 1: swap!(x[:,i], x[:,j]).  Sampling and the acceptance ratio stay here.
+function special_proposal!(g::B200Model, kind::Int, i::Int, j::Int, P=I)::Bool
+    m, rng = g.host, g.host.rng
+    R₊ = randn(rng, m.Ndim); R₋ = randn(rng, m.Ndim)    # refresh_ϕ!(hmc, model, sample_R=true)      HMC.jl:674-677
+    a = P isa B200KPM ? randn(rng, 2 * m.Nsites) : Float64[]
+    u = rand(rng)                                      # rand(model.rng) < Pf                      SpecialUpdates.jl:146
+    acc = Ref{Int32}(0); S₀ = Ref{Float64}(0); S₁ = Ref{Float64}(0); it = Ref{Int64}(0); fl = Ref{Int32}(0)
+    check(ccall((:elph_hmc_special_update, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64,
+                 Ref{Int32}, Ref{Float64}, Ref{Float64}, Ref{Int64}, Ref{Int32}),
+                g.h, kind, i - 1, j - 1, R₊, R₋, P isa B200KPM ? a : C_NULL, P isa B200KPM ? 1 : 0, u, acc, S₀, S₁, it, fl), g.h)
+    acc[] == 1
+end
+
+# --- long-lived host arrays (dyn.η, est.R, ...) can be page-locked once so that their copies run at PCIe rate ------
+pin!(g::B200Model, v::Array{Float64}) = check(ccall((:elph_host_register, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), g.h, v, sizeof(v)), g.h)
+unpin!(g::B200Model, v::Array{Float64}) = check(ccall((:elph_host_unregister, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.h, v), g.h)
+
 # --- dynamics: src/LangevinDynamics.jl:81,162,272 ; noise drawn here in the reference's order ---------------------
 method(::EulerDynamics) = Int32(1); method(::RungeKuttaDynamics) = Int32(2); method(::HeunsDynamics) = Int32(3)
 function attach!(g::B200Model, fa::FourierAccelerator)   # after update_Q!/update_M! (ProcessInputFile.jl:516-535)
