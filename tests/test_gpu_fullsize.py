@@ -106,6 +106,32 @@ def test_B_cg_iterations_and_residual(config_B):
     em._call("elph_set_tuning", 7, -1)
 
 
+def test_B_cg_with_initial_guess_and_maxiter(config_B):
+    """Raw solve!(x, A, b, cg) (src/IterativeSolvers.jl:239-314) from a non-zero initial guess, and a solve cut off by
+    maxiter, in both forms of the persistent kernel: iteration counts within +-2 of the C restatement, same iterates."""
+    import elphdynamics_b200 as E
+    from oracle.cref import CRef
+    om, em, rng = config_B
+    b = rng.normal(size=om.Ndim)
+    x0 = 0.05 * rng.normal(size=om.Ndim)
+    xc = x0.copy()
+    it_c, eps_c = CRef(om).cg(xc, b, tol=om.tol, maxiter=om.maxiter)
+    xm = x0.copy()
+    it_m, eps_m = CRef(om).cg(xm, b, tol=om.tol, maxiter=25)
+    assert it_m == 25
+    for key7 in (1, 0):
+        em._call("elph_set_tuning", 7, key7)
+        xe = x0.copy()
+        it_e = E.solve_(xe, em, b)
+        assert abs(it_e - it_c) <= 2, (key7, it_e, it_c)
+        assert em.last_eps < om.tol and relerr(xe, xc) <= 1e-3
+        xe = x0.copy()
+        it_e = E.solve_(xe, em, b, maxiter=25)
+        assert it_e == 25 and abs(em.last_eps - eps_m) <= 1e-6 * eps_m, (key7, em.last_eps, eps_m)
+        assert relerr(xe, xm) <= 1e-8
+    em._call("elph_set_tuning", 7, -1)
+
+
 def test_B_kpm_pcg_and_force(config_B):
     import elphdynamics_b200 as E
     from oracle.kpm import KPMPreconditioner

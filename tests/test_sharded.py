@@ -400,6 +400,9 @@ def _check_p2p_cg(be, comm, tau0, lloc, b_glob, x_ref, it_ref):
     be.p2p_setup(comm)
     b = be.empty()
     b[1:lloc + 1] = torch.from_numpy(b_glob[tau0:tau0 + lloc]).to(b.device)
+    x = be.empty()
+    it, eps = be.cg_p2p(x, b, 1e-5, 7)        # cut off by maxiter: every rank returns the same count and residual
+    assert it == 7 and eps > 1e-5
     for rep in range(3):                      # repeated solves: the barrier sequence numbers carry over
         x = be.empty()
         x.fill_(3.0)                          # output only (x0 = 0 inside)
