@@ -370,6 +370,53 @@ def main():
                                     "note": "elph_langevin_step through the C ABI with host noise buffers (page-locked with "
                                             "elph_host_register); 2 KPM set-ups + 2 KPM-PCG solves + forces + Fourier acceleration"}
 
+        from elphdynamics_b200 import workloads
+        # ---- independent Markov chains on ONE GPU (the reference's own scale-out, ElPhDynamics.jl:90-95: one process per
+        # chain id): a single chain is latency bound and leaves most of the device idle, so K chains, each with its own
+        # handle, stream and host thread (ctypes releases the GIL inside the C ABI), advance concurrently
+        try:
+            import threading as _th
+            K, nst = 8, 6
+            chains = []
+            for c in range(K):
+                mc, rc = workloads.holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=4321 + c, eps=0.3)
+                fc = E.FourierAccelerator(mc)
+                E.update_Q_(fc, mc, 0.0, 10.0, 1.0)
+                Pc = E.SymmetricKPMPreconditioner(mc)
+                dc = E.RungeKuttaDynamics(mc, 1e-3)
+                nz = [dict(eta=rc.normal(size=n), g1=rc.normal(size=n), g2=rc.normal(size=n),
+                           arnoldi1=rc.normal(size=2 * Nsites), arnoldi2=rc.normal(size=2 * Nsites)) for _ in range(nst + 1)]
+                for z in nz:
+                    for key in ("eta", "g1", "g2"):
+                        mc.pin_host(z[key])
+                chains.append((mc, fc, Pc, dc, nz))
+            its_c = [0] * K
+
+            def run_chain(c, first, steps):
+                mc, fc, Pc, dc, nz = chains[c]
+                for k in range(first, first + steps):   # fresh noise every step, as in a real chain
+                    its_c[c] = E.evolve_(mc, dc, fc, Pc, **nz[k])
+
+            for first, steps in ((0, 1), (1, nst)):            # warm-up step, then the timed steps
+                ths = [_th.Thread(target=run_chain, args=(c, first, steps)) for c in range(K)]
+                t0 = time.perf_counter()
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+                dt_c = time.perf_counter() - t0
+            extra["langevin_rk_kpm_chains"] = {"chains": K, "steps_per_s_aggregate": K * nst / dt_c, "steps_per_s_per_chain": nst / dt_c,
+                                               "pcg_iters_last": its_c,
+                                               "note": "K independent 32x32xL200 chains on one GPU, one handle + stream + host thread each "
+                                                       "(elph_langevin_step, page-locked host noise)"}
+            for mc, fc, Pc, dc, nz in chains:
+                for z in nz:
+                    for key in ("eta", "g1", "g2"):
+                        mc.unpin_host(z[key])
+                mc.close()
+        except Exception as exc:   # an extra must not cost the bench line
+            extra["langevin_rk_kpm_chains"] = {"error": str(exc)[:200]}
+
         # ---- measurement side: the four convolutions of setup!(estimator, n1, n2) on the device ----
         from elphdynamics_b200 import greens as eg
         Gr = eg.EstimateGreensFunction(em, 4)
@@ -388,7 +435,6 @@ def main():
 
         # ---- configuration C: SSH 32x32xL200 (per-(tau,bond) cosh/sinh tables, 48 B/pt algorithmic) ----
         from elphdynamics_b200 import hmc as ehmc
-        from elphdynamics_b200 import workloads
         mC, rC = workloads.config("C")
         mC.set_stream(stream.cuda_stream)
         nC = mC.Ndim
