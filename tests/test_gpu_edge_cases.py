@@ -155,3 +155,49 @@ def test_workload_builders_match_the_test_builders():
     es, _ = workloads.ssh_square(4, 1.0, 0.05, seed=11)
     assert np.array_equal(es.x, os_.x)
     es.close()
+
+
+def test_handles_are_independent_across_host_threads():
+    """One handle per caller thread at a time (include/elph_b200.h); different handles may run concurrently from different
+    host threads (independent Markov chains on one GPU): the results equal the sequential ones bit for bit, for the
+    persistent cooperative CG (32-wide lattice) and for a KPM-preconditioned Langevin step."""
+    import threading
+    import elphdynamics_b200 as E
+    from elphdynamics_b200 import workloads
+
+    def make(c):
+        m, rng = workloads.holstein("square", 32, 0.8, 0.1, mu=-0.5, seed=77 + c, eps=0.3)
+        fa = E.FourierAccelerator(m)
+        E.update_Q_(fa, m, 0.0, 10.0, 1.0)
+        P = E.SymmetricKPMPreconditioner(m)
+        nz = dict(eta=rng.normal(size=m.Ndof), g1=rng.normal(size=m.Ndim), g2=rng.normal(size=m.Ndim),
+                  arnoldi1=rng.normal(size=2 * m.Nsites), arnoldi2=rng.normal(size=2 * m.Nsites))
+        return m, fa, P, nz, rng.normal(size=m.Ndim)
+
+    def work(ch, out, c):
+        m, fa, P, nz, b = ch
+        x = np.zeros(m.Ndim)
+        it, res, flag = E.ldiv_(x, m, b)                                        # persistent cooperative CG
+        it2 = E.evolve_(m, E.RungeKuttaDynamics(m, 1e-3), fa, P, **nz)          # graphs, KPM set-up on host threads
+        out[c] = (it, flag, x, it2, m.x)
+
+    K = 4
+    results = []
+    for concurrent in (False, True):
+        chains = [make(c) for c in range(K)]
+        out = [None] * K
+        if concurrent:
+            ths = [threading.Thread(target=work, args=(chains[c], out, c)) for c in range(K)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        else:
+            for c in range(K):
+                work(chains[c], out, c)
+        results.append(out)
+        for ch in chains:
+            ch[0].close()
+    for a, b in zip(*results):
+        assert a[0] == b[0] and a[1] == b[1] == 0 and a[3] == b[3]
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4])
