@@ -142,6 +142,7 @@ struct elph_handle {
     bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
     int cg_single_reduction = -1;  // unpreconditioned CG, Holstein square: one barrier per iteration (cg_p2p.cu); -1 = auto
                                    // (on where measured faster: 32-wide lattices), 0 = off, 1 = on
+    int pipe_chunk = 8;          // replicas per stage of the host-buffer pipeline (elph_mulMTM_batch); 8 measured best
     bool pcg_fuse = true;        // preconditioned CG: vector updates fused into the FFT kernels of the KPM apply
     unsigned int* d_bar = nullptr;  // grid-barrier arrival counter of the persistent CG
     bool own_stream = false;
