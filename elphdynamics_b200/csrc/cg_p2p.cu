@@ -39,7 +39,8 @@
 // set-up; 16 bytes per site), the boundary CTAs' private r / s copies of the neighbour rows,
 // the mailboxes and the partials.  Sequence numbers / tags increase monotonically over the life of the handle (all
 // ranks execute the same number of barriers), nothing is ever reset.
-// Holstein on periodic square lattices (the register tiles of mtm_square.cu); the reference has no counterpart.
+// Holstein on periodic square lattices (the register tiles of mtm_square.cu), any world size; SSH on 32-wide square
+// lattices on one GPU (tables of slices tau, tau+1 resident in shared memory).  The reference has no counterpart.
 #include "square_tiles.cuh"
 
 #include <algorithm>
@@ -53,7 +54,9 @@ constexpr int kMaxWorld = 16;
 constexpr unsigned int kSpinLimit = 1u << 25;   // ~ 20 s: a dead peer ends the solve with an error instead of a hang
 
 struct P2pParams {
-    const double* __restrict__ D;   // expnV; sharded handle: slices -1 .. L valid (halos), else [L][N] and tau wraps
+    const double* __restrict__ D;   // Holstein expnV: sharded handle slices -1 .. L valid (halos), else [L][N] and tau
+                                    // wraps; SSH: exp(dtau mu) [N]
+    const double2* __restrict__ tab; // SSH: (cosh, sinh) [L][2][N] in the tile layout of ssh_square.cu (else unused)
     const double* __restrict__ r0;  // [L][N] initial residual (= b when the initial guess is zero)
     double* __restrict__ x;         // [L][N] in (if x0_given) / out
     double* V;                      // arena vectors [2 parities][3: r, w, s][Lmax][N]
@@ -210,12 +213,13 @@ __device__ __forceinline__ bool global_sum2(double v0, double v1, const P2pParam
     return good;
 }
 
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool SSH>
 __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
     constexpr int LX = 32 * NSEG;
     // 128-register cap at 512 threads: x, p, s, D(tau), D(tau+1) live in shared memory there (one CTA per SM anyway)
     constexpr bool XS = (MAXT > 256);
-    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; XS: + x, p, s, D(tau), D(tau+1) [5][N]
+    extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; XS: + x, p, s, D(tau), D(tau+1) [5][N];
+                                                       // SSH: + the tables of slices tau and tau+1 (fixed during a solve)
     __shared__ double red[64];
     __shared__ int flag[2];   // barrier completed without a timeout: [0] local counter, [1] peers' mailbox words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -258,6 +262,23 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
     auto DC = [&](int rr, int q) -> double& { if constexpr (XS) return dcs[sidx(rr, q)]; else return Dcr.a[rr][q]; };
     auto DN = [&](int rr, int q) -> double& { if constexpr (XS) return dns[sidx(rr, q)]; else return Dnr.a[rr][q]; };
 
+    // SSH: K(tau) and K(tau+1) stay in shared memory for the whole solve (single GPU only: tau wraps)
+    const double2* txc = nullptr; const double2* tyc = nullptr; const double2* hyc = nullptr;
+    const double2* txn = nullptr; const double2* tyn = nullptr; const double2* hyn = nullptr;
+    if constexpr (SSH) {
+        static_assert(!XS || !SSH, "SSH tables and the shared-memory state do not fit together");
+        double2* tabc = reinterpret_cast<double2*>(strips + 2ull * nwarps * 4 * LX);
+        double2* tabn = tabc + 2 * N;
+        const int taup_w = (tau == L - 1) ? 0 : tau + 1;
+        for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+            tabc[i] = P.tab[(size_t)tau * 2 * N + i];
+            tabn[i] = P.tab[(size_t)taup_w * 2 * N + i];
+        }
+        __syncthreads();
+        const size_t halo_off = (size_t)((warp * PY + P.Ly - 1) % P.Ly) * LX;
+        txc = tabc + tile_off; tyc = tabc + N + tile_off; hyc = tabc + N + halo_off;
+        txn = tabn + tile_off; tyn = tabn + N + tile_off; hyn = tabn + N + halo_off;
+    }
     const int tg = P.tau0 + tau;                       // global slice index
     const bool wrap_c = (tg == 0);
     const bool wrap_n = (tg + 1 == P.Lglob);
@@ -272,18 +293,32 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
                 t1.a[rr][q] = DC(rr, q) * t1.a[rr][q];
                 t2.a[rr][q] = DN(rr, q) * r.a[rr][q];
             }
-        g0_x_even(t1, P.c0, P.s0);
-        g0_x_even(t2, P.c0, P.s0);
-        g1_x_odd(t1, P.c1, P.s1, lane);
-        g1_x_odd(t2, P.c1, P.s1, lane);
-        g2_y_even(t1, P.c2, P.s2);
-        g2_y_even(t2, P.c2, P.s2);
+        if constexpr (SSH) {
+            g0_tab(t1, txc, lane);
+            g0_tab(t2, txn, lane);
+            g1_tab(t1, txc, lane);
+            g1_tab(t2, txn, lane);
+            g2_tab(t1, tyc, lane);
+            g2_tab(t2, tyn, lane);
+        } else {
+            g0_x_even(t1, P.c0, P.s0);
+            g0_x_even(t2, P.c0, P.s0);
+            g1_x_odd(t1, P.c1, P.s1, lane);
+            g1_x_odd(t2, P.c1, P.s1, lane);
+            g2_y_even(t1, P.c2, P.s2);
+            g2_y_even(t2, P.c2, P.s2);
+        }
         {
             double a1[NSEG], a2[NSEG], b1[NSEG], b2[NSEG];
             exchange_edges2(t1, t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, a1, a2, b1, b2);
             xbuf ^= 1;
-            g3_y_odd(t1, P.c3, P.s3, a1, b1);
-            g3_y_odd(t2, P.c3, P.s3, a2, b2);
+            if constexpr (SSH) {
+                g3_tab(t1, tyc, hyc, lane, a1, b1);
+                g3_tab(t2, tyn, hyn, lane, a2, b2);
+            } else {
+                g3_y_odd(t1, P.c3, P.s3, a1, b1);
+                g3_y_odd(t2, P.c3, P.s3, a2, b2);
+            }
         }
         double vn[PY][NSEG];
         load_next(vn);
@@ -302,11 +337,18 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
             double ab[NSEG], be[NSEG];
             exchange_edges1(t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, ab, be);
             xbuf ^= 1;
-            g3_y_odd(t2, P.c3, P.s3, ab, be);
+            if constexpr (SSH) g3_tab(t2, tyn, hyn, lane, ab, be);
+            else g3_y_odd(t2, P.c3, P.s3, ab, be);
         }
-        g2_y_even(t2, P.c2, P.s2);
-        g1_x_odd(t2, P.c1, P.s1, lane);
-        g0_x_even(t2, P.c0, P.s0);
+        if constexpr (SSH) {
+            g2_tab(t2, tyn, lane);
+            g1_tab(t2, txn, lane);
+            g0_tab(t2, txn, lane);
+        } else {
+            g2_y_even(t2, P.c2, P.s2);
+            g1_x_odd(t2, P.c1, P.s1, lane);
+            g0_x_even(t2, P.c0, P.s0);
+        }
 #pragma unroll
         for (int rr = 0; rr < PY; ++rr)
 #pragma unroll
@@ -330,8 +372,8 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
             PP(rr, q) = 0.0;
             SS(rr, q) = 0.0;
             r.a[rr][q] = bv;
-            DC(rr, q) = P.D[row + e];
-            DN(rr, q) = P.D[rowDn + e];
+            DC(rr, q) = SSH ? P.D[e] : P.D[row + e];
+            DN(rr, q) = SSH ? P.D[e] : P.D[rowDn + e];
             if (first) push_ll(halo_w(P.left_halo, 1, 0, 1) + 2 * e, bv, base + 1u);   // r_0 rows for the neighbours' set-up
             if (last) push_ll(halo_w(P.right_halo, 1, 0, 0) + 2 * e, bv, base + 1u);
             accg = fma(bv, bv, accg);
@@ -504,16 +546,17 @@ __global__ void __launch_bounds__(MAXT) cg_p2p_kernel(P2pParams P) {
     }
 }
 
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool SSH>
 size_t p2p_smem(const elph_handle* h, int nwarps) {
-    return (2ull * nwarps * 4 * (32 * NSEG) + (MAXT > 256 ? 5ull * h->N : 0)) * sizeof(double);
+    return (2ull * nwarps * 4 * (32 * NSEG) + (MAXT > 256 ? 5ull * h->N : 0)) * sizeof(double) +
+           (SSH ? 2ull * 2 * h->N * sizeof(double2) : 0);
 }
 
 // all slices of the slab must be co-resident (cooperative launch, one CTA per slice)
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool SSH = false>
 bool fits_p2p(elph_handle* h, int nwarps) {
-    auto kern = cg_p2p_kernel<NSEG, PY, MAXT>;
-    const size_t smem = p2p_smem<NSEG, PY, MAXT>(h, nwarps);
+    auto kern = cg_p2p_kernel<NSEG, PY, MAXT, SSH>;
+    const size_t smem = p2p_smem<NSEG, PY, MAXT, SSH>(h, nwarps);
     if (smem > h->smem_optin) return false;
     elph_enable_smem(h, kern);
     int per_sm = 0;
@@ -521,13 +564,13 @@ bool fits_p2p(elph_handle* h, int nwarps) {
     return (long long)per_sm * h->sm_count >= h->L;
 }
 
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool SSH = false>
 bool launch_p2p(elph_handle* h, P2pParams& P, int nwarps) {
-    if (!fits_p2p<NSEG, PY, MAXT>(h, nwarps)) return false;
-    auto kern = cg_p2p_kernel<NSEG, PY, MAXT>;
+    if (!fits_p2p<NSEG, PY, MAXT, SSH>(h, nwarps)) return false;
+    auto kern = cg_p2p_kernel<NSEG, PY, MAXT, SSH>;
     ELPH_CUDA(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned int), h->stream));
     void* args[] = {&P};
-    ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L), dim3(nwarps * 32), args, p2p_smem<NSEG, PY, MAXT>(h, nwarps),
+    ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L), dim3(nwarps * 32), args, p2p_smem<NSEG, PY, MAXT, SSH>(h, nwarps),
                                           h->stream));
     h->launches++;
     return true;
@@ -535,12 +578,14 @@ bool launch_p2p(elph_handle* h, P2pParams& P, int nwarps) {
 
 // kernel variant for this handle: 0 = none applies
 int p2p_variant(const elph_handle* h, int& nwarps) {
-    if (!h->sq.enabled || h->model != ELPH_MODEL_HOLSTEIN) return 0;
-    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
+    const bool ssh = (h->model == ELPH_MODEL_SSH);
+    if (!(ssh ? h->ssq.enabled : h->sq.enabled)) return 0;
+    const int Lx = ssh ? h->ssq.Lx : h->sq.Lx, Ly = ssh ? h->ssq.Ly : h->sq.Ly;
     const int PY = (Lx == 32) ? 8 : 4;
     if (Ly % PY) return 0;
     nwarps = Ly / PY;
     if (nwarps < 2 || nwarps > 32) return 0;
+    if (ssh) return (Lx == 32 && nwarps * 32 <= 256 && !h->sharded) ? 3 : 0;   // single GPU only
     if (Lx == 32 && nwarps * 32 <= 256) return 1;
     if (Lx == 64 && nwarps * 32 <= 512) return 2;
     return 0;
@@ -549,7 +594,8 @@ int p2p_variant(const elph_handle* h, int& nwarps) {
 bool p2p_fits(elph_handle* h) {
     int nwarps = 0;
     const int variant = p2p_variant(h, nwarps);
-    return (variant == 1) ? fits_p2p<1, 8, 256>(h, nwarps) : (variant == 2) ? fits_p2p<2, 4, 512>(h, nwarps) : false;
+    return (variant == 1) ? fits_p2p<1, 8, 256>(h, nwarps) : (variant == 2) ? fits_p2p<2, 4, 512>(h, nwarps)
+         : (variant == 3) ? fits_p2p<1, 8, 256, true>(h, nwarps) : false;
 }
 
 // ---- arena layout (identical on every rank) ------------------------------------------------------------------------
@@ -590,7 +636,7 @@ bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool sc
     cudaStream_t st = h->stream;
     const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
     P2pParams P;
-    P.D = h->d_D; P.r0 = r0; P.x = x;
+    P.D = h->d_D; P.tab = (variant == 3) ? h->ssq.d_tab : nullptr; P.r0 = r0; P.x = x;
     P.V = arena_vec(h, A.arena);
     P.my_halo = arena_halo(h, A.arena);
     P.left_halo = arena_halo(h, A.peer[left]);    // this GPU's first slice is the left neighbour's slice L (hi rows)
@@ -598,7 +644,7 @@ bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool sc
     for (int q = 0; q < kMaxWorld; ++q) P.mbox[q] = (q < A.world) ? arena_mbox(h, A.peer[q]) : nullptr;
     P.partial = arena_partial(h, A.arena); P.ghost = arena_ghost(h, A.arena); P.bar = h->d_bar; P.S = h->d_cg;
     P.seq_base = A.seq;
-    P.L = h->L; P.Lmax = A.Lmax; P.Ly = h->sq.Ly; P.rank = A.rank; P.world = A.world;
+    P.L = h->L; P.Lmax = A.Lmax; P.Ly = (variant == 3) ? h->ssq.Ly : h->sq.Ly; P.rank = A.rank; P.world = A.world;
     P.tau0 = h->sharded ? h->shard_tau0 : 0;
     P.Lglob = h->sharded ? h->shard_Lglob : h->L;
     P.d_halo = h->sharded ? 1 : 0;
@@ -614,6 +660,7 @@ bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool sc
     bool ok = false;
     if (variant == 1) ok = launch_p2p<1, 8, 256>(h, P, nwarps);
     else if (variant == 2) ok = launch_p2p<2, 4, 512>(h, P, nwarps);
+    else if (variant == 3) ok = launch_p2p<1, 8, 256, true>(h, P, nwarps);
     if (!ok) return false;
     ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
     ELPH_CUDA(cudaStreamSynchronize(st));
@@ -628,7 +675,8 @@ bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool sc
 void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned char* handle_out) {
     ELPH_REQUIRE(h->sharded, ELPH_ERR_STATE, "elph_set_shard has not been called");
     ELPH_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, ELPH_ERR_INVALID, "bad rank / world");
-    ELPH_REQUIRE(h->sq.enabled, ELPH_ERR_UNSUPPORTED, "the peer-memory CG needs the square-lattice register kernels");
+    ELPH_REQUIRE(h->sq.enabled && h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
+                 "the peer-memory CG needs the Holstein square-lattice register kernels");
     auto& A = h->p2p;
     alloc_arena(h, rank, world, h->shard_Lglob);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -694,7 +742,7 @@ bool elph_cg_single_reduction(elph_handle* h, double* x_dev) {
     if (!variant || h->sq_disable || h->L < 2) return false;
     // measured on B200 (scripts/bench_cg1r.py): 32x32xL200 6.93 -> 5.85 us/iteration; 64-wide lattices keep more state in
     // shared memory under the 128-register cap and lose (9.7 -> 10.6 us), so they stay on the two-reduction kernel
-    if (h->cg_single_reduction < 0 && variant != 1) return false;
+    if (h->cg_single_reduction < 0 && variant == 2) return false;
     auto& A = h->p2p;
     if (!A.arena) {
         alloc_arena(h, 0, 1, h->L);

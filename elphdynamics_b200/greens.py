@@ -30,6 +30,29 @@ class EstimateGreensFunction:
         self.G_D0_G_D0 = np.zeros(shape, dtype=np.complex128)
         self.G_DD_G_00 = np.zeros(shape, dtype=np.complex128)
         self.G_D0_G_0D = np.zeros(shape, dtype=np.complex128)
+        # the estimator's arrays live as long as the estimator and cross the bus for every pair: page-lock them once
+        self._pinned = []
+        for a in (self.R, self.MinvR, self.G_D0, self.G_D0_G_D0, self.G_DD_G_00, self.G_D0_G_0D):
+            try:
+                model.pin_host(a)
+                self._pinned.append(a)
+            except RuntimeError:
+                break                # pinning is an optimisation only
+
+    def close(self):
+        """Release the page locks (call before the model is closed)."""
+        for a in self._pinned:
+            try:
+                self.model.unpin_host(a)
+            except Exception:
+                pass
+        self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def update_(Gr: EstimateGreensFunction, model, P=None, *, R):

@@ -60,6 +60,9 @@ class AbstractModel:
 
     def close(self):
         if self._lib is not None and self._h:
+            for addr in list(getattr(self, "_pinned", {})):      # page locks taken through this handle
+                self._lib.elph_host_unregister(self._h, C.c_void_p(addr))
+            self._pinned = {}
             self._lib.elph_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -103,10 +106,18 @@ class AbstractModel:
         """Page-lock a long-lived host array that is passed to the host-buffer entry points repeatedly (noise vectors,
         right-hand sides): ``elph_host_register``.  Call ``unpin_host`` before the array goes away."""
         assert array.flags["C_CONTIGUOUS"]
+        if self._h is None or not self._h:
+            raise RuntimeError("model is closed")
         self._call("elph_host_register", C.c_void_p(array.ctypes.data), array.nbytes)
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        self._pinned[array.ctypes.data] = array          # keeps the array alive while it is registered
 
     def unpin_host(self, array: np.ndarray):
+        if self._h is None or not self._h:
+            return                       # the handle is gone; the driver released the registration with the context
         self._call("elph_host_unregister", C.c_void_p(array.ctypes.data))
+        getattr(self, "_pinned", {}).pop(array.ctypes.data, None)
 
     def set_mu(self, mu):
         self.mu = _f64(mu, self.Nsites, "mu").copy()

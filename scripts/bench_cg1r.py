@@ -19,12 +19,16 @@ from elphdynamics_b200 import workloads
 
 torch.cuda.set_device(0)
 torch.cuda.set_stream(torch.cuda.Stream())
-for (Ls, beta, eps_f) in ((32, 20.0, 0.3), (32, 20.0, 1.0), (32, 5.0, 0.3), (64, 10.0, 0.3), (64, 5.0, 0.3)):
-    m, rng = workloads.holstein("square", Ls, beta, 0.1, seed=1234, eps=eps_f)
+for (Ls, beta, eps_f) in ((32, 20.0, 0.3), (32, 20.0, 1.0), (32, 5.0, 0.3), (64, 10.0, 0.3), (64, 5.0, 0.3), ("C", 10.0, 0.3)):
+    if Ls == "C":
+        m, rng = workloads.config("C")          # SSH 32x32, Ltau = 200
+        Ls = 32
+    else:
+        m, rng = workloads.holstein("square", Ls, beta, 0.1, seed=1234, eps=eps_f)
     lib = m._lib
     m.set_stream(torch.cuda.current_stream().cuda_stream)
     b = torch.from_numpy(rng.normal(size=m.Ndim)).cuda()
-    out = {"lattice": f"{Ls}x{Ls}xL{m.Ltau}", "roughness": eps_f}
+    out = {"model": type(m).__name__, "lattice": f"{Ls}x{Ls}xL{m.Ltau}", "roughness": eps_f}
     xs = {}
     for key7 in (0, 1):
         lib.elph_set_tuning(m.handle, 7, key7)
