@@ -1208,6 +1208,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 5: h->use_persistent = (value != 0); break;
             case 6: h->pcg_fuse = (value != 0); h->kpm_version++; break;
             case 7: h->cg_single_reduction = (value < 0) ? -1 : (value != 0); break;
+            case 9: h->hmc_fused_inner = (value != 0); break;
             case 8: ELPH_REQUIRE(value >= 1 && value <= 8, ELPH_ERR_INVALID, "pipeline stage must hold 1..8 replicas"); h->pipe_chunk = value; break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }

@@ -142,6 +142,7 @@ struct elph_handle {
     bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
     int cg_single_reduction = -1;  // unpreconditioned CG, Holstein square: one barrier per iteration (cg_p2p.cu); -1 = auto
                                    // (on where measured faster: 32-wide lattices), 0 = off, 1 = on
+    bool hmc_fused_inner = true; // multi-timestep HMC: the Nb inner steps of an outer step in one kernel (fft.cu)
     int pipe_chunk = 8;          // replicas per stage of the host-buffer pipeline (elph_mulMTM_batch); 8 measured best
     bool pcg_fuse = true;        // preconditioned CG: vector updates fused into the FFT kernels of the KPM apply
     unsigned int* d_bar = nullptr;  // grid-barrier arrival counter of the persistent CG
@@ -325,8 +326,24 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
 void elph_solve_device(elph_handle* h, const double* b_dev, double* x_dev, bool use_precond, double tol_power,
                        elph_solve_info* info);
 bool elph_cg_persistent(elph_handle* h, double* x_dev);   // cg_persistent.cu
+#ifdef __CUDACC__
+// dSb/dx at (tau, i): dtau w^2 x + 4 dtau w4 x^3 - (x(tau+1)+x(tau-1)-2x)/dtau [- dtau lam * shifted]
+// (src/PhononAction.jl:114-233); x: [L][ncols], periodic in tau.  Shared by force.cu and the fused HMC inner loop (fft.cu).
+__device__ __forceinline__ double dSb_term(const double* __restrict__ x, int tau, int i, int ncols, int L, double dtau, double w,
+                                           double w4, double lam_shift) {
+    const int tp = (tau + 1 == L) ? 0 : tau + 1;
+    const int tm = (tau == 0) ? L - 1 : tau - 1;
+    const double xt = x[(size_t)tau * ncols + i];
+    double d = dtau * w * w * xt - lam_shift;
+    d += dtau * 4.0 * w4 * xt * xt * xt;
+    d -= (x[(size_t)tp * ncols + i] + x[(size_t)tm * ncols + i] - 2.0 * xt) / dtau;
+    return d;
+}
+#endif
+
 // ELPH_TRACE=1 development aid: wall time since the previous mark, after draining the stream
 void elph_trace_mark(elph_handle* h, const char* label);
+bool elph_hmc_inner_dev(elph_handle* h, double* x, double* v, double dtp, int Nb);   // fft.cu
 // greens.cu
 void elph_greens_free(elph_handle* h);
 void elph_greens_load_impl(elph_handle* h, int nv, const double* R, const double* MinvR);

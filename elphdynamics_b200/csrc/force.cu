@@ -37,18 +37,6 @@ struct FParams {
     int add_dSb, shifted;
 };
 
-// dSb/dx at (tau, i): dtau w^2 x + 4 dtau w4 x^3 - (x(tau+1)+x(tau-1)-2x)/dtau [- dtau lam * shifted]
-__device__ __forceinline__ double dSb_term(const double* __restrict__ x, int tau, int i, int ncols, int L, double dtau, double w,
-                                           double w4, double lam_shift) {
-    const int tp = (tau + 1 == L) ? 0 : tau + 1;
-    const int tm = (tau == 0) ? L - 1 : tau - 1;
-    const double xt = x[(size_t)tau * ncols + i];
-    double d = dtau * w * w * xt - lam_shift;
-    d += dtau * 4.0 * w4 * xt * xt * xt;
-    d -= (x[(size_t)tp * ncols + i] + x[(size_t)tm * ncols + i] - 2.0 * xt) / dtau;
-    return d;
-}
-
 __global__ void __launch_bounds__(kT) holstein_force_kernel(FParams P) {
     extern __shared__ double smem[];
     const int N = P.N, L = P.L;

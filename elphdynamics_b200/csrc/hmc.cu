@@ -337,6 +337,8 @@ void elph_hmc_update_dev(elph_handle* h, double dt, int Nt, int Nb, double alpha
             elph_lincomb(h, S.v, 1.0, S.v, -dt / 2, S.Q, 0.0, nullptr, nd);
             if (Nb == 1) {
                 elph_lincomb(h, h->d_x, 1.0, h->d_x, dt, S.v, 0.0, nullptr, nd);
+            } else if (h->hmc_fused_inner && elph_hmc_inner_dev(h, h->d_x, S.v, dtp, Nb)) {
+                // the whole inner loop ran in one launch (same operations as the step-by-step kernels below)
             } else {
                 boson_force();
                 for (int tp = 0; tp < Nb; ++tp) {

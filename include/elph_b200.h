@@ -368,7 +368,8 @@ int32_t elph_set_chunk(elph_handle* h, int32_t slices_per_cta);
  * 7 = single-reduction form of the persistent unpreconditioned CG (one grid barrier per iteration; Holstein on square
  *     lattices; same iterates to rounding, iteration counts within +-2 of the two-reduction loop; -1 = auto (default: on for
  *     32-wide lattices, where it is measured faster), 0 = off, 1 = on),
- * 8 = replicas per stage of the H2D | kernels | D2H pipeline behind elph_mulMTM_batch (1..8, default 8) */
+ * 8 = replicas per stage of the H2D | kernels | D2H pipeline behind elph_mulMTM_batch (1..8, default 8),
+ * 9 = multi-timestep HMC: the Nb inner (bosonic) steps of an outer step in one kernel (default 1) */
 int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value);
 /* which kernel family serves the fused M^T M product of this model, and the number of bond colours found */
 int32_t elph_get_kernel_info(elph_handle* h, int32_t* square_kernel, int32_t* ngroups);

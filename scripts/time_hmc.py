@@ -78,3 +78,11 @@ for d in draws:
     acc, its = ehmc.update_(m, hm, fa, None, **d)
     dt = time.perf_counter() - t0
     print(f"trajectory: {dt * 1e3:.2f} ms, launches {m.launch_count() - l0}, iters(avg) {its}, accepted {acc}")
+lib.elph_set_tuning(h, 9, 0)           # inner loop of the multi-timestep integrator step by step (for comparison)
+for d in draws[:2]:
+    l0 = m.launch_count()
+    t0 = time.perf_counter()
+    acc, its = ehmc.update_(m, hm, fa, None, **d)
+    dt = time.perf_counter() - t0
+    print(f"trajectory, unfused inner loop: {dt * 1e3:.2f} ms, launches {m.launch_count() - l0}, iters(avg) {its}, accepted {acc}")
+lib.elph_set_tuning(h, 9, 1)
