@@ -285,6 +285,8 @@ void destroy(elph_handle* h) {
     elph_kpm_free(h);
     elph_hmc_free(h);
     elph_greens_free(h);
+    if (h->g1r.V) cudaFree(h->g1r.V);
+    if (h->g1r.partial) cudaFree(h->g1r.partial);
     for (auto& g : h->cg_graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     h->cg_graphs.clear();
@@ -962,6 +964,7 @@ int32_t elph_hmc_update(elph_handle* h, double dt, int64_t Nt, int64_t Nb, doubl
                         const double* R_minus, const double* arnoldi_noise, int32_t use_precond, double uniform,
                         int32_t* accepted, double* iters, double* H0, double* H1, int32_t* flag) {
     ENTER(h) {
+        elph_trace_mark(h, nullptr);
         ELPH_REQUIRE(Nt >= 0 && Nb >= 1 && dt > 0.0, ELPH_ERR_INVALID, "bad HMC parameters");
         ELPH_REQUIRE(alpha >= 0.0 && alpha < 1.0, ELPH_ERR_INVALID, "alpha must be in [0,1)");
         ELPH_REQUIRE(!use_precond || arnoldi_noise, ELPH_ERR_INVALID, "arnoldi_noise needs (Nt+2)*2*Nsites values");

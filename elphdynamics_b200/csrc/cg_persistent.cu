@@ -475,8 +475,320 @@ void fill_io(Params& P, const CgBatchBufs& B, int L) {
     P.vstride = B.vstride; P.pstride = B.pstride;
 }
 
+
+// ---- any lattice, single-reduction form ------------------------------------------------------------------------------
+// The loop of cg_p2p.cu (one grid barrier per iteration: gamma = (r, r) and delta = (r, A r) reduced together, alpha / beta
+// from the Chronopoulos-Gear recurrences, the neighbour slices' new residuals rebuilt from their r, w, s of the previous
+// iteration) with the body of the generic kernel above: slice pair + bond list in shared memory, x, r, p, s, w, D in
+// registers.  grid.y = independent right-hand sides.  Measured at honeycomb L = 32 (config D, 20 CTAs per right-hand
+// side): the barrier is cheap at this grid size and the shared-memory sweeps dominate, so the gain is small (HMC trajectory
+// 16.1 -> 15.5 ms, ten right-hand sides 2.65 -> 2.56 ms); iteration counts unchanged.
+struct G1Params {
+    const double* __restrict__ D;     // expnV [L][N]
+    double* __restrict__ x;           // in: initial guess, out: solution
+    const double* __restrict__ R0;    // initial residual
+    double* V;                        // [2 parities][3: r, w, s][L][N] per right-hand side
+    double* partial;                  // [2 parities][2 values][L] per right-hand side
+    unsigned int* bar;
+    CgScalars* S;
+    const int2* __restrict__ bonds;
+    const double2* __restrict__ cs;
+    const int* __restrict__ goff;
+    int N, L, Nb, ngroups;
+    long long vstride, v6stride;      // right-hand side k: x, R0 + k*vstride; V + k*v6stride; partial + k*4L; bar + k; S + k
+};
+
+// grid barrier + ordered sums of two doubles per CTA (see grid_sum); part: [2][L] of this barrier's parity
+__device__ __forceinline__ void grid_sum2(double v0, double v1, double* part, unsigned int* bar, unsigned int seq, int nb, int L,
+                                          double* bcast, double& out0, double& out1) {
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = v0;
+        part[L + blockIdx.x] = v1;
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        const unsigned int target = seq * (unsigned int)nb;
+        while (ld_acquire(bar) < target) {}
+    }
+    __syncthreads();
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) { s0 += __ldcg(part + k); s1 += __ldcg(part + L + k); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if ((threadIdx.x & 31) == 0) { bcast[threadIdx.x >> 5] = s0; bcast[32 + (threadIdx.x >> 5)] = s1; }
+    __syncthreads();
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { t0 += bcast[k]; t1 += bcast[32 + k]; }
+    out0 = t0;
+    out1 = t1;
+    __syncthreads();   // bcast is reused by the next call
+}
+
+__device__ __forceinline__ void block_sum_all2(double& v0, double& v1, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = v0; red[32 + (threadIdx.x >> 5)] = v1; }
+    __syncthreads();
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { t0 += red[k]; t1 += red[32 + k]; }
+    v0 = t0;
+    v1 = t1;
+}
+
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) cg1r_generic_kernel(G1Params P) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    __shared__ double red[64];
+    __shared__ double bcast[64];
+    {
+        const size_t k = blockIdx.y;
+        P.x += k * P.vstride; P.R0 += k * P.vstride; P.V += k * P.v6stride;
+        P.partial += k * 4 * (size_t)P.L; P.bar += k; P.S += k;
+    }
+    const int N = P.N, L = P.L, nb = gridDim.x, T = blockDim.x, tid = threadIdx.x;
+    double* A1 = reinterpret_cast<double*>(gsm);
+    double* A2 = A1 + N;
+    double2* scs = reinterpret_cast<double2*>(A2 + N);
+    int2* sb = reinterpret_cast<int2*>(scs + P.Nb);
+    const int tau = blockIdx.x;
+    const int taum = (tau == 0) ? L - 1 : tau - 1;
+    const int taup = (tau == L - 1) ? 0 : tau + 1;
+    for (int b = tid; b < P.Nb; b += T) {
+        sb[b] = P.bonds[b];
+        scs[b] = P.cs[b];
+    }
+    const bool wrap_c = (tau == 0), wrap_n = (taup == 0);
+    const size_t vs = (size_t)L * N;
+    auto vec = [&](int par, int which) -> double* { return P.V + (size_t)(par * 3 + which) * vs; };
+    double x[EPT], r[EPT], p[EPT], s[EPT], w[EPT], Dc[EPT], Dn[EPT], vm[EPT], vp[EPT];
+
+    // w(tau) = (M^T M v)(tau) from vm = v(tau-1), r = v(tau), vp = v(tau+1); returns this thread's share of |(M v)(tau)|^2
+    auto apply_A = [&]() -> double {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                A1[i] = Dc[k] * vm[k];
+                A2[i] = Dn[k] * r[k];
+            }
+        }
+        __syncthreads();
+        for (int g = 0; g < P.ngroups; ++g) {   // K on both slices
+            const int hi = P.goff[g + 1];
+            for (int b = P.goff[g] + tid; b < hi; b += T) {
+                const int2 ij = sb[b];
+                const double2 c = scs[b];
+                const double a1 = A1[ij.x], a2 = A1[ij.y], b1 = A2[ij.x], b2 = A2[ij.y];
+                A1[ij.x] = c.x * a1 + c.y * a2;
+                A1[ij.y] = c.x * a2 + c.y * a1;
+                A2[ij.x] = c.x * b1 + c.y * b2;
+                A2[ij.y] = c.x * b2 + c.y * b1;
+            }
+            __syncthreads();
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                const double wc = wrap_c ? (r[k] + A1[i]) : (r[k] - A1[i]);
+                const double wn = wrap_n ? (vp[k] + A2[i]) : (vp[k] - A2[i]);
+                A1[i] = wc;
+                A2[i] = wn;
+                acc = fma(wc, wc, acc);
+            }
+        }
+        __syncthreads();
+        for (int g = P.ngroups - 1; g >= 0; --g) {   // K^T on (M v)(tau+1)
+            const int hi = P.goff[g + 1];
+            for (int b = P.goff[g] + tid; b < hi; b += T) {
+                const int2 ij = sb[b];
+                const double2 c = scs[b];
+                const double b1 = A2[ij.x], b2 = A2[ij.y];
+                A2[ij.x] = c.x * b1 + c.y * b2;
+                A2[ij.y] = c.x * b2 + c.y * b1;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                const double du = Dn[k] * A2[i];
+                w[k] = wrap_n ? (A1[i] + du) : (A1[i] - du);
+            }
+        }
+        __syncthreads();   // A1 / A2 are rewritten by the next call
+        return acc;
+    };
+
+    // ---- set-up: r_0 (from the caller), w_0 = A r_0, gamma_0, delta_0 ------------------------------------------------
+    double accg = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int i = tid + k * T;
+        const bool in = i < N;
+        x[k] = in ? P.x[(size_t)tau * N + i] : 0.0;
+        r[k] = in ? P.R0[(size_t)tau * N + i] : 0.0;
+        vm[k] = in ? P.R0[(size_t)taum * N + i] : 0.0;
+        vp[k] = in ? P.R0[(size_t)taup * N + i] : 0.0;
+        Dc[k] = in ? P.D[(size_t)tau * N + i] : 0.0;
+        Dn[k] = in ? P.D[(size_t)taup * N + i] : 0.0;
+        p[k] = 0.0;
+        s[k] = 0.0;
+        w[k] = 0.0;
+        accg = fma(r[k], r[k], accg);
+    }
+    __syncthreads();   // bond list staged
+    double accd = apply_A();
+    {
+        double* R0w = vec(0, 0);
+        double* W0w = vec(0, 1);
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                R0w[(size_t)tau * N + i] = r[k];
+                W0w[(size_t)tau * N + i] = w[k];
+            }
+        }
+    }
+    const double normb = P.S->normb, tol = P.S->tol, kappa_max = P.S->kappa_max;
+    const long long maxiter = P.S->maxiter;
+    unsigned int seq = 0;
+    double gamma = accg, delta = accd;
+    block_sum_all2(gamma, delta, red);
+    ++seq;
+    grid_sum2(gamma, delta, P.partial + (size_t)(seq & 1u) * 2 * L, P.bar, seq, nb, L, bcast, gamma, delta);
+    const double eps0 = sqrt(gamma) / normb;
+    double alpha = gamma / delta, beta = 0.0, kmin = 0.0, eps = eps0;
+    long long j = 0;
+
+    while (j < maxiter) {
+        const int rd = (int)(j & 1), wr = rd ^ 1;
+        ++j;
+        const bool have_s = (j > 1);
+        const double* Rr = vec(rd, 0);
+        const double* Wr = vec(rd, 1);
+        const double* Sr = vec(rd, 2);
+        double* Rw = vec(wr, 0);
+        double* Ww = vec(wr, 1);
+        double* Sw = vec(wr, 2);
+        const double mab = -alpha * beta;
+        double accr = 0.0;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) {
+                // r_new of the neighbour slices = r - alpha (w + beta s), rebuilt here; both fetched together
+                const size_t em = (size_t)taum * N + i, ep = (size_t)taup * N + i;
+                double a = fma(-alpha, __ldcg(Wr + em), __ldcg(Rr + em));
+                double b = fma(-alpha, __ldcg(Wr + ep), __ldcg(Rr + ep));
+                if (have_s) {
+                    a = fma(mab, __ldcg(Sr + em), a);
+                    b = fma(mab, __ldcg(Sr + ep), b);
+                }
+                vm[k] = a;
+                vp[k] = b;
+                const double pv = fma(beta, p[k], r[k]);
+                const double sv = fma(beta, s[k], w[k]);
+                p[k] = pv;
+                s[k] = sv;
+                x[k] = fma(alpha, pv, x[k]);
+                const double rv = fma(-alpha, sv, r[k]);
+                r[k] = rv;
+                Rw[(size_t)tau * N + i] = rv;
+                Sw[(size_t)tau * N + i] = sv;
+                accr = fma(rv, rv, accr);
+            }
+        }
+        double accw = apply_A();
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * T;
+            if (i < N) Ww[(size_t)tau * N + i] = w[k];
+        }
+        block_sum_all2(accr, accw, red);
+        ++seq;
+        double gnew, dnew;
+        grid_sum2(accr, accw, P.partial + (size_t)(seq & 1u) * 2 * L, P.bar, seq, nb, L, bcast, gnew, dnew);
+        eps = sqrt(gnew) / normb;
+        const double lg = log(2.0 * eps0 / eps);
+        const double qq = 2.0 * (double)j / lg;
+        const double kap = qq * qq;
+        if (kap > kmin) kmin = kap;
+        if (eps < tol || kmin > kappa_max) break;
+        beta = gnew / gamma;
+        alpha = gnew / (dnew - beta * gnew / alpha);
+        gamma = gnew;
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int i = tid + k * T;
+        if (i < N) P.x[(size_t)tau * N + i] = x[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.S->iter = j;
+        P.S->eps = eps;
+        P.S->kappa_min = kmin;
+        P.S->done = 1;
+    }
+}
+
+template <typename Kern>
+bool launch_g1(elph_handle* h, Kern kern, const G1Params& P, int threads, size_t smem, int nrhs) {
+    elph_enable_smem(h, kern);
+    int per_sm = 0;
+    ELPH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    const int cap = (int)std::min<long long>((long long)per_sm * h->sm_count / h->L, 65535);
+    if (cap < 1) return false;
+    for (int k0 = 0; k0 < nrhs; k0 += cap) {
+        const int g = std::min(cap, nrhs - k0);
+        G1Params Q = P;
+        Q.x += k0 * P.vstride; Q.R0 += k0 * P.vstride; Q.V += k0 * P.v6stride;
+        Q.partial += (size_t)k0 * 4 * h->L; Q.bar += k0; Q.S += k0;
+        ELPH_CUDA(cudaMemsetAsync(Q.bar, 0, g * sizeof(unsigned int), h->stream));
+        void* args[] = {&Q};
+        ELPH_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(h->L, g), dim3(threads), args, smem, h->stream));
+        h->launches++;
+    }
+    return true;
+}
+
+// work space of the single-reduction generic kernel: 6 vectors + 4 L partials per right-hand side, grow-only
+bool cg1r_generic(elph_handle* h, int nrhs, const CgBatchBufs& B) {
+    if (h->model != ELPH_MODEL_HOLSTEIN || h->N > 4096 || h->L < 2) return false;
+    const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2));
+    if (smem > h->smem_optin) return false;
+    auto& W = h->g1r;
+    if (W.cap < nrhs) {
+        if (W.V) cudaFree(W.V);
+        if (W.partial) cudaFree(W.partial);
+        W.V = elph_dalloc<double>((size_t)6 * h->Ndim * nrhs);
+        W.partial = elph_dalloc<double>((size_t)4 * h->L * nrhs);
+        W.cap = nrhs;
+    }
+    G1Params P;
+    P.D = h->d_D; P.x = B.x; P.R0 = B.R; P.V = W.V; P.partial = W.partial; P.bar = B.bar; P.S = B.S;
+    P.bonds = h->d_bonds; P.cs = h->d_cs; P.goff = h->d_goff;
+    P.N = h->N; P.L = h->L; P.Nb = h->Nb; P.ngroups = h->ngroups;
+    P.vstride = B.vstride; P.v6stride = (long long)6 * h->Ndim;
+    const int threads = (h->N <= 64) ? 64 : ((h->N <= 256) ? 256 : 512);
+    const int ept = (h->N + threads - 1) / threads;
+    if (ept <= 1) return launch_g1(h, cg1r_generic_kernel<1, 512>, P, threads, smem, nrhs);
+    if (ept <= 2) return launch_g1(h, cg1r_generic_kernel<2, 512>, P, threads, smem, nrhs);
+    if (ept <= 4) return launch_g1(h, cg1r_generic_kernel<4, 512>, P, threads, smem, nrhs);
+    return launch_g1(h, cg1r_generic_kernel<8, 512>, P, threads, smem, nrhs);
+}
+
 bool cg_persistent_generic(elph_handle* h, int nrhs, const CgBatchBufs& B) {
     if (h->model != ELPH_MODEL_HOLSTEIN || h->N > 4096) return false;
+    if (h->cg_single_reduction != 0 && cg1r_generic(h, nrhs, B)) return true;
     const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2));
     if (smem > h->smem_optin) return false;
     GcgParams P;

@@ -131,6 +131,7 @@ struct HostPipe {
 struct elph_handle {
     std::string err;
     HmcState hmc;
+    struct { int cap = 0; double* V = nullptr; double* partial = nullptr; } g1r;   // cg1r_generic work space (cg_persistent.cu)
     void* greens = nullptr;    // GreensState of greens.cu (Green's-function convolutions), allocated on first use
     HostPipe pipe;
     std::vector<CgGraph> cg_graphs;

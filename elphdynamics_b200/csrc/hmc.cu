@@ -330,9 +330,11 @@ void elph_hmc_update_dev(elph_handle* h, double dt, int Nt, int Nb, double alpha
         elph_dSbdx_dev(h, S.dS, false);
         elph_fourier_accelerate_dev(h, S.dS, S.y, -1.0, true);
     };
+    elph_trace_mark(h, "hmc: refresh + first solves");
     if (flag == 0) {
         elph_hmc_calc_H_dev(h, &H0, &Sx, &Kx);
         force(Nb == 1);
+        elph_trace_mark(h, "hmc: H0 + first force");
         for (int t = 0; t < Nt; ++t) {
             elph_lincomb(h, S.v, 1.0, S.v, -dt / 2, S.Q, 0.0, nullptr, nd);
             if (Nb == 1) {
@@ -348,12 +350,15 @@ void elph_hmc_update_dev(elph_handle* h, double dt, int Nt, int Nb, double alpha
                     elph_lincomb(h, S.v, 1.0, S.v, -dtp / 2, S.y, 0.0, nullptr, nd);
                 }
             }
+            elph_trace_mark(h, "hmc: kick + inner steps");
             elph_launch_update_model(h);
             elph_hmc_calc_Oinv_dev(h, use_precond, next_noise(), 1.0, &it, &flag);
             iters += it;
+            elph_trace_mark(h, "hmc: update_model + solves");
             if (flag > 0) break;
             force(Nb == 1);
             elph_lincomb(h, S.v, 1.0, S.v, -dt / 2, S.Q, 0.0, nullptr, nd);
+            elph_trace_mark(h, "hmc: force + kick");
         }
     }
     double P = 0.0;

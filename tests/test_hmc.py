@@ -285,6 +285,7 @@ def test_gpu_hmc_fused_inner_loop_matches_stepwise_kernels(kind):
         em.close()
     a, b = outs
     assert a[0] == b[0] and a[1] == b[1]
-    assert abs(a[4] - b[4]) <= 1e-13 * abs(b[4]) and abs(a[5] - b[5]) <= 1e-13 * abs(b[5])
-    assert relerr(a[2], b[2]) <= 1e-13 and relerr(a[3], b[3]) <= 1e-12
+    # last-bit differences of the inner loop pass through the two solves of every later outer step (tol^2 = 1e-14)
+    assert abs(a[4] - b[4]) <= 1e-10 * abs(b[4]) and abs(a[5] - b[5]) <= 1e-10 * abs(b[5])
+    assert relerr(a[2], b[2]) <= 1e-9 and relerr(a[3], b[3]) <= 1e-8
     assert a[6] < b[6]                       # fewer launches with the fused inner loop
