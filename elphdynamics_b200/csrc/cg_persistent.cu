@@ -341,6 +341,9 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
     double* A2 = A1 + N;
     double2* scs = reinterpret_cast<double2*>(A2 + N);   // 2N doubles = 16N bytes: 16-byte aligned
     int2* sb = reinterpret_cast<int2*>(scs + P.Nb);
+    // colour offsets in shared memory too: the acquire loads of the grid barrier invalidate L1 (CCTL.IVALL), so a global
+    // goff[g] inside the sweep loops would cost an L2 round trip per colour and iteration
+    int* sgoff = reinterpret_cast<int*>(sb + P.Nb);
     const int tau = blockIdx.x;
     const int taum = (tau == 0) ? L - 1 : tau - 1;
     const int taup = (tau == L - 1) ? 0 : tau + 1;
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
         sb[b] = P.bonds[b];
         scs[b] = P.cs[b];
     }
+    for (int g = tid; g <= P.ngroups; g += T) sgoff[g] = P.goff[g];
     double x[EPT], r[EPT], pprev[EPT], pc[EPT], Dc[EPT], Dn[EPT], pn[EPT];
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
@@ -387,8 +391,8 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
         }
         __syncthreads();
         for (int g = 0; g < P.ngroups; ++g) {   // K on both slices
-            const int hi = P.goff[g + 1];
-            for (int b = P.goff[g] + tid; b < hi; b += T) {
+            const int hi = sgoff[g + 1];
+            for (int b = sgoff[g] + tid; b < hi; b += T) {
                 const int2 ij = sb[b];
                 const double2 c = scs[b];
                 const double a1 = A1[ij.x], a2 = A1[ij.y], b1 = A2[ij.x], b2 = A2[ij.y];
@@ -413,8 +417,8 @@ __global__ void __launch_bounds__(MAXT) cg_persistent_generic_kernel(GcgParams P
         }
         __syncthreads();
         for (int g = P.ngroups - 1; g >= 0; --g) {   // K^T on w(tau+1)
-            const int hi = P.goff[g + 1];
-            for (int b = P.goff[g] + tid; b < hi; b += T) {
+            const int hi = sgoff[g + 1];
+            for (int b = sgoff[g] + tid; b < hi; b += T) {
                 const int2 ij = sb[b];
                 const double2 c = scs[b];
                 const double b1 = A2[ij.x], b2 = A2[ij.y];
@@ -555,6 +559,9 @@ __global__ void __launch_bounds__(MAXT) cg1r_generic_kernel(G1Params P) {
     double* A2 = A1 + N;
     double2* scs = reinterpret_cast<double2*>(A2 + N);
     int2* sb = reinterpret_cast<int2*>(scs + P.Nb);
+    // colour offsets in shared memory too: the acquire loads of the grid barrier invalidate L1 (CCTL.IVALL), so a global
+    // goff[g] inside the sweep loops would cost an L2 round trip per colour and iteration
+    int* sgoff = reinterpret_cast<int*>(sb + P.Nb);
     const int tau = blockIdx.x;
     const int taum = (tau == 0) ? L - 1 : tau - 1;
     const int taup = (tau == L - 1) ? 0 : tau + 1;
@@ -562,6 +569,7 @@ __global__ void __launch_bounds__(MAXT) cg1r_generic_kernel(G1Params P) {
         sb[b] = P.bonds[b];
         scs[b] = P.cs[b];
     }
+    for (int g = tid; g <= P.ngroups; g += T) sgoff[g] = P.goff[g];
     const bool wrap_c = (tau == 0), wrap_n = (taup == 0);
     const size_t vs = (size_t)L * N;
     auto vec = [&](int par, int which) -> double* { return P.V + (size_t)(par * 3 + which) * vs; };
@@ -579,8 +587,8 @@ __global__ void __launch_bounds__(MAXT) cg1r_generic_kernel(G1Params P) {
         }
         __syncthreads();
         for (int g = 0; g < P.ngroups; ++g) {   // K on both slices
-            const int hi = P.goff[g + 1];
-            for (int b = P.goff[g] + tid; b < hi; b += T) {
+            const int hi = sgoff[g + 1];
+            for (int b = sgoff[g] + tid; b < hi; b += T) {
                 const int2 ij = sb[b];
                 const double2 c = scs[b];
                 const double a1 = A1[ij.x], a2 = A1[ij.y], b1 = A2[ij.x], b2 = A2[ij.y];
@@ -605,8 +613,8 @@ __global__ void __launch_bounds__(MAXT) cg1r_generic_kernel(G1Params P) {
         }
         __syncthreads();
         for (int g = P.ngroups - 1; g >= 0; --g) {   // K^T on (M v)(tau+1)
-            const int hi = P.goff[g + 1];
-            for (int b = P.goff[g] + tid; b < hi; b += T) {
+            const int hi = sgoff[g + 1];
+            for (int b = sgoff[g] + tid; b < hi; b += T) {
                 const int2 ij = sb[b];
                 const double2 c = scs[b];
                 const double b1 = A2[ij.x], b2 = A2[ij.y];
@@ -763,7 +771,8 @@ bool launch_g1(elph_handle* h, Kern kern, const G1Params& P, int threads, size_t
 // work space of the single-reduction generic kernel: 6 vectors + 4 L partials per right-hand side, grow-only
 bool cg1r_generic(elph_handle* h, int nrhs, const CgBatchBufs& B) {
     if (h->model != ELPH_MODEL_HOLSTEIN || h->N > 4096 || h->L < 2) return false;
-    const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2));
+    const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2)) +
+                        (size_t)(h->ngroups + 1) * sizeof(int);
     if (smem > h->smem_optin) return false;
     auto& W = h->g1r;
     if (W.cap < nrhs) {
@@ -789,7 +798,8 @@ bool cg1r_generic(elph_handle* h, int nrhs, const CgBatchBufs& B) {
 bool cg_persistent_generic(elph_handle* h, int nrhs, const CgBatchBufs& B) {
     if (h->model != ELPH_MODEL_HOLSTEIN || h->N > 4096) return false;
     if (h->cg_single_reduction != 0 && cg1r_generic(h, nrhs, B)) return true;
-    const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2));
+    const size_t smem = (size_t)(2 * h->N + 2) * sizeof(double) + (size_t)h->Nb * (sizeof(double2) + sizeof(int2)) +
+                        (size_t)(h->ngroups + 1) * sizeof(int);
     if (smem > h->smem_optin) return false;
     GcgParams P;
     fill_io(P, B, h->L);
