@@ -185,6 +185,9 @@ def main():
     # work on a real (non-legacy) stream: CUDA events time it, and the engine can capture CUDA graphs on it
     torch.cuda.set_stream(torch.cuda.Stream())
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in the image) goes to stdout too
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
