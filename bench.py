@@ -171,6 +171,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: NCCL's own messages (the image sets NCCL_DEBUG=VERSION, whose banner goes to
+    # stdout) are sent to stderr, and the bare version banner is dropped; must happen before NCCL is first touched
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
 
     import ctypes as C
     import torch
@@ -185,9 +190,6 @@ def main():
     # work on a real (non-legacy) stream: CUDA events time it, and the engine can capture CUDA graphs on it
     torch.cuda.set_stream(torch.cuda.Stream())
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in the image) goes to stdout too
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
