@@ -616,7 +616,9 @@ double* arena_ghost(const elph_handle* h, void* base) { return arena_partial(h, 
 
 void alloc_arena(elph_handle* h, int rank, int world, int Lglob) {
     auto& A = h->p2p;
-    if (A.arena) return;
+    const int Lmax = (Lglob + world - 1) / world;
+    if (A.arena && A.rank == rank && A.world == world && A.Lmax == Lmax) return;
+    if (A.arena) elph_shard_p2p_close_impl(h);   // geometry changed (e.g. elph_set_shard after a single-GPU solve): start over
     A.rank = rank;
     A.world = world;
     A.Lmax = (Lglob + world - 1) / world;

@@ -108,6 +108,8 @@ class AbstractModel:
         assert array.flags["C_CONTIGUOUS"]
         if self._h is None or not self._h:
             raise RuntimeError("model is closed")
+        if array.ctypes.data in getattr(self, "_pinned", {}):
+            return                       # already page-locked through this handle
         self._call("elph_host_register", C.c_void_p(array.ctypes.data), array.nbytes)
         if not hasattr(self, "_pinned"):
             self._pinned = {}
