@@ -128,6 +128,30 @@ def cpu_baseline(target_seconds=12.0, nthreads=0):
                       f"cannot run here", "seconds": secs}, (nrep, reps, secs, used)
 
 
+def cpu_langevin_baseline(nsteps=2):
+    """The second headline quantity on the host: Langevin Runge-Kutta steps/s of the NumPy restatement at config B with the
+    shipped solver settings (KPM-preconditioned CG) -- one thread, like the reference (src/ElPhDynamics.jl:74-75).  A port:
+    the sweeps are NumPy-vectorised over tau; Julia's compiled loops would be faster by a small factor."""
+    from oracle import langevin as olang
+    from oracle.fourier import FourierAccelerator
+    from oracle.kpm import KPMPreconditioner
+    from oracle.solvers import ConjugateGradient
+    om = oracle_model()
+    rng = np.random.default_rng(4321)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    fo = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
+    fo.update_Q(0.0, 10.0, 1.0)
+    Po = KPMPreconditioner(om)
+    its = []
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        its.append(int(olang.evolve_rk(om, cg, fo, Po, 1e-3, rng.normal(size=om.Ndof), rng.normal(size=om.Ndim),
+                                       rng.normal(size=om.Ndim), rng.normal(size=2 * om.N), rng.normal(size=2 * om.N))))
+    dt = time.perf_counter() - t0
+    return {"steps_per_s": nsteps / dt, "cores": 1, "kind": "port (NumPy restatement)", "pcg_iters_second_solve": its,
+            "sample": f"{nsteps} Runge-Kutta steps of 32x32xL200 with KPM-preconditioned CG, fresh injected noise per step"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -602,6 +626,10 @@ def main():
             line["tau_sharded"] = sharded
         if not args.no_cpu:
             cb, _ = cpu_baseline()
+            try:
+                cb["langevin_rk_kpm"] = cpu_langevin_baseline()
+            except Exception as exc:          # the extra CPU figure must not cost the bench line
+                cb["langevin_rk_kpm"] = {"error": str(exc)[:200]}
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     em.close()
