@@ -150,6 +150,11 @@ def _check_rank(op, be, comm_rank, tau0, lloc, V, outs, om, b_glob, x_ref, it_re
     it, eps = op.solve_cg(x, b)
     assert abs(it - it_ref) <= 2, (it, it_ref)
     assert relerr(x[1:lloc + 1].cpu().numpy(), x_ref[tau0:tau0 + lloc]) <= 1e-3   # both stop at eps < 1e-5
+    # solve(): the x0 = 0 entry the dynamics use; without enable_p2p() it is the loop above and ignores what x held
+    x2 = be.empty()
+    x2.fill_(7.0)
+    it2, eps2 = op.solve(x2, b)
+    assert it2 == it and relerr(x2[1:lloc + 1].cpu().numpy(), x[1:lloc + 1].cpu().numpy()) <= 1e-12
 
 
 def _problem(seed=7, Ls=4, beta=1.1):
@@ -175,6 +180,7 @@ def _cpu_worker(rank, world, port):
         tau0, lloc = slab_bounds(om.L, world, rank)
         be = OracleSlabBackend(om, tau0, lloc)
         op = ShardedOperator(be, RingComm(rank, world), tol=1e-5, maxiter=5000)
+        assert not op.enable_p2p()       # a backend without peer memory keeps the collective-between-launches solver
         _check_rank(op, be, rank, tau0, lloc, V, outs, om, b, x_ref, it_ref)
     finally:
         dist.destroy_process_group()
