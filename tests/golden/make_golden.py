@@ -105,7 +105,38 @@ def float_fixtures():
     np.savez_compressed(OUT / "holstein_square4.npz", **d)
 
 
+def extras_fixtures():
+    """Measurement-side and special-update fixtures: Green's-function convolutions for fixed vectors, the log of
+    three reflection and three swap proposals with injected noise, on a small honeycomb lattice (two orbitals)."""
+    from oracle import greens as og
+    from oracle import hmc as ohmc
+    om, rng = oracle_holstein("honeycomb", 2, 0.4, 0.1, mu=-0.3, seed=20240229, eps=0.3, tol=1e-7)
+    d = {"x": om.x.copy()}
+    Gr = og.EstimateGreensFunction(om, 2)
+    Gr.R[:] = rng.normal(size=Gr.R.shape)
+    Gr.MinvR[:] = rng.normal(size=Gr.R.shape)
+    d["greens_R"], d["greens_MinvR"] = Gr.R.copy(), Gr.MinvR.copy()
+    for name, arr in zip(("G_D0", "G_D0_G_D0", "G_DD_G_00", "G_D0_G_0D"), og.setup(Gr, 0, 1)):
+        d["greens_" + name] = np.asarray(arr)
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    h = ohmc.HybridMonteCarlo(om, 0.01, 0.05, 0.0, 1)
+    logs = []
+    for kind, targets in (("reflect", [1, 5, 2]), ("swap", [(0, 1), (2, 7), (4, 5)])):
+        Rp = [rng.normal(size=om.Ndim) for _ in targets]
+        Rm = [rng.normal(size=om.Ndim) for _ in targets]
+        u = rng.uniform(size=len(targets))
+        ratio, log = ohmc.special_update(om, h, cg, None, kind, targets, Rp, Rm, u.tolist())
+        d[f"special_{kind}_Rp"], d[f"special_{kind}_Rm"], d[f"special_{kind}_u"] = np.array(Rp), np.array(Rm), u
+        d[f"special_{kind}_targets"] = np.array(targets)
+        d[f"special_{kind}_log"] = np.array([[float(a), s0, s1, float(it), float(fl)] for (a, s0, s1, it, fl) in log])
+        logs.append(ratio)
+    d["special_ratios"] = np.array(logs)
+    d["x_after_special"] = om.x.copy()
+    np.savez_compressed(OUT / "honeycomb2_extras.npz", **d)
+
+
 if __name__ == "__main__":
     integer_fixtures()
     float_fixtures()
+    extras_fixtures()
     print("wrote", sorted(p.name for p in OUT.iterdir()))

@@ -170,3 +170,67 @@ def test_phonon_text_format_host_logic(tmp_path, monkeypatch):
     pio.read_phonons_(m, str(f))
     assert np.abs(m.x - x0).max() <= 5e-7
     assert np.array_equal(m.x, np.array([float("%.6f" % v) for v in x0]))
+
+
+def _extras_problem():
+    from helpers import oracle_holstein
+    gold = np.load(GOLD / "honeycomb2_extras.npz")
+    om, _ = oracle_holstein("honeycomb", 2, 0.4, 0.1, mu=-0.3, seed=20240229, eps=0.3, tol=1e-7)
+    assert np.array_equal(om.x, gold["x"])
+    return om, gold
+
+
+def test_oracle_reproduces_greens_and_special_update_fixture():
+    """tests/golden/honeycomb2_extras.npz (made by make_golden.py): Green's-function convolutions for frozen vectors and
+    the log of three reflection + three swap proposals."""
+    from oracle import greens as og
+    from oracle import hmc as ohmc
+    from oracle.solvers import ConjugateGradient
+    om, gold = _extras_problem()
+    Gr = og.EstimateGreensFunction(om, 2)
+    Gr.R[:], Gr.MinvR[:] = gold["greens_R"], gold["greens_MinvR"]
+    for name, arr in zip(("G_D0", "G_D0_G_D0", "G_DD_G_00", "G_D0_G_0D"), og.setup(Gr, 0, 1)):
+        assert np.allclose(arr, gold["greens_" + name], rtol=1e-13, atol=1e-15), name
+    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
+    h = ohmc.HybridMonteCarlo(om, 0.01, 0.05, 0.0, 1)
+    for k, kind in enumerate(("reflect", "swap")):
+        tg = gold[f"special_{kind}_targets"]
+        targets = [int(t) for t in tg] if kind == "reflect" else [tuple(int(v) for v in t) for t in tg]
+        ratio, log = ohmc.special_update(om, h, cg, None, kind, targets, list(gold[f"special_{kind}_Rp"]),
+                                         list(gold[f"special_{kind}_Rm"]), gold[f"special_{kind}_u"].tolist())
+        ref = gold[f"special_{kind}_log"]
+        assert ratio == gold["special_ratios"][k]
+        for (ok, s0, s1, it, fl), row in zip(log, ref):
+            assert float(ok) == row[0] and it == row[3] and fl == row[4]
+            assert abs(s0 - row[1]) <= 1e-12 * abs(row[1]) and abs(s1 - row[2]) <= 1e-10 * abs(row[2])
+    assert np.array_equal(om.x, gold["x_after_special"])
+
+
+@pytest.mark.gpu
+def test_engine_reproduces_greens_and_special_update_fixture():
+    """The same fixture through the C ABI: convolutions to 1e-12, proposals with the same decisions and final field."""
+    from helpers import engine_holstein_like
+    import elphdynamics_b200 as E
+    from elphdynamics_b200 import greens as eg
+    from elphdynamics_b200 import hmc as ehmc
+    om, gold = _extras_problem()
+    em = engine_holstein_like(om)
+    Ge = eg.EstimateGreensFunction(em, 2)
+    Ge.R[:], Ge.MinvR[:] = gold["greens_R"], gold["greens_MinvR"]
+    em._call("elph_greens_load", 2, E._lib.ptr(Ge.R), E._lib.ptr(Ge.MinvR))
+    for name, arr in zip(("G_D0", "G_D0_G_D0", "G_DD_G_00", "G_D0_G_0D"), eg.setup_pair_(Ge, 0, 1)):
+        ref = gold["greens_" + name]
+        assert np.linalg.norm(arr - ref) <= 1e-12 * np.linalg.norm(ref), name
+    he = ehmc.HybridMonteCarlo(em, 0.01, 0.05, 0.0, 1)
+    for k, (kind, upd) in enumerate((("reflect", ehmc.ReflectionUpdate(em, 1, 3)), ("swap", ehmc.SwapUpdate(em, 1, 3)))):
+        tg = gold[f"special_{kind}_targets"]
+        targets = [int(t) for t in tg] if kind == "reflect" else [tuple(int(v) for v in t) for t in tg]
+        ratio = ehmc.special_update_(em, he, upd, None, targets=targets, R_plus=list(gold[f"special_{kind}_Rp"]),
+                                     R_minus=list(gold[f"special_{kind}_Rm"]), uniforms=gold[f"special_{kind}_u"].tolist())
+        assert ratio == gold["special_ratios"][k]
+        for (ok, s0, s1, it, fl), row in zip(he.special_log, gold[f"special_{kind}_log"]):
+            assert float(ok) == row[0] and abs(it - row[3]) <= 2 and fl == row[4]
+            assert abs(s0 - row[1]) <= 1e-12 * abs(row[1]) and abs(s1 - row[2]) <= 1e-8 * abs(row[2])
+    assert np.array_equal(em.x, gold["x_after_special"])
+    Ge.close()
+    em.close()
