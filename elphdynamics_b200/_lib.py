@@ -158,6 +158,7 @@ def load() -> C.CDLL:
         "elph_launch_count": (i64, [H]),
         "elph_set_chunk": (i32, [H, i32]),
         "elph_set_tuning": (i32, [H, i32, i32]),
+        "elph_get_tuning": (i32, [H, i32, C.POINTER(i32)]),
         "elph_get_kernel_info": (i32, [H, C.POINTER(i32), C.POINTER(i32)]),
         "elph_debug_hessenberg_eigvals": (i32, [i32, dp, dp, dp]),
     }

@@ -302,6 +302,7 @@ void destroy(elph_handle* h) {
         cudaStreamDestroy(h->pipe.s_out);
     }
     elph_shard_p2p_close_impl(h);
+    if (h->pipe_prof_buf) cudaFree(h->pipe_prof_buf);
     if (h->d_D_alloc) {  // sharded: d_D points one slice into this allocation
         cudaFree(h->d_D_alloc);
         h->d_D = nullptr;
@@ -1212,7 +1213,35 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 6: h->pcg_fuse = (value != 0); h->kpm_version++; break;
             case 7: h->cg_single_reduction = (value < 0) ? -1 : (value != 0); break;
             case 9: h->hmc_fused_inner = (value != 0); break;
+            case 10: h->cg_pipeline = (value < 0) ? -1 : (value != 0); break;
+            case 13: ELPH_REQUIRE(value >= 0 && value <= 16, ELPH_ERR_INVALID, "variant out of range"); h->pipe_variant = value; break;
+            case 12:
+                h->pipe_prof = (value != 0);
+                if (h->pipe_prof && !h->pipe_prof_buf) {
+                    h->pipe_prof_buf = elph_dalloc<unsigned long long>(8192 * 8);
+                    ELPH_CUDA(cudaMemset(h->pipe_prof_buf, 0, 8192 * 8 * sizeof(unsigned long long)));
+                }
+                break;
+            case 11: ELPH_REQUIRE(value >= 0 && value <= 8, ELPH_ERR_INVALID, "CTAs per slice out of range"); h->pipe_ys = value; break;
             case 8: ELPH_REQUIRE(value >= 1 && value <= 8, ELPH_ERR_INVALID, "pipeline stage must hold 1..8 replicas"); h->pipe_chunk = value; break;
+            default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
+        }
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_get_tuning(elph_handle* h, int32_t key, int32_t* value) {
+    ENTER(h) {
+        ELPH_REQUIRE(value, ELPH_ERR_INVALID, "null output");
+        switch (key) {
+            case 0: *value = h->chunk_override; break;
+            case 1: *value = h->sq_disable ? 1 : 0; break;
+            case 3: *value = h->use_graphs ? 1 : 0; break;
+            case 5: *value = h->use_persistent ? 1 : 0; break;
+            case 7: *value = h->cg_single_reduction; break;
+            case 10: *value = h->cg_pipeline; break;
+            case 11: *value = h->pipe_ys; break;
+            case 100: *value = h->pipe_last_variant; break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }
         return ELPH_OK;
@@ -1223,6 +1252,17 @@ int32_t elph_get_kernel_info(elph_handle* h, int32_t* square_kernel, int32_t* ng
     ENTER(h) {
         if (square_kernel) *square_kernel = ((h->sq.enabled || h->ssq.enabled) && !h->sq_disable) ? 1 : 0;
         if (ngroups) *ngroups = h->ngroups;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// development hook (not in the public header): per-phase cycle counters of the last pipelined CG solve, [ncta][8]
+int32_t elph_debug_pipe_prof(elph_handle* h, int32_t ncta, unsigned long long* out) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->pipe_prof_buf && out && ncta >= 1 && ncta <= 8192, ELPH_ERR_STATE, "profiling not enabled (tuning key 12)");
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        ELPH_CUDA(cudaMemcpy(out, h->pipe_prof_buf, (size_t)ncta * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         return ELPH_OK;
     }
     ELPH_CATCH(h)

@@ -41,6 +41,7 @@
 // ranks execute the same number of barriers), nothing is ever reset.
 // Holstein on periodic square lattices (the register tiles of mtm_square.cu), any world size; SSH on 32-wide square
 // lattices on one GPU (tables of slices tau, tau+1 resident in shared memory).  The reference has no counterpart.
+#include "ll_words.cuh"
 #include "square_tiles.cuh"
 
 #include <algorithm>
@@ -78,23 +79,10 @@ struct P2pParams {
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
 
-__device__ __forceinline__ void st_ll(unsigned long long* p, unsigned long long w0, unsigned long long w1) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
-}
-__device__ __forceinline__ void ld_ll(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-// one double + tag as two self-validating words (a torn 16-byte store cannot pass for a complete one)
-__device__ __forceinline__ void push_ll(unsigned long long* p, double v, unsigned int tag) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    st_ll(p, (bits & 0xffffffffull) | ((unsigned long long)tag << 32), (bits >> 32) | ((unsigned long long)tag << 32));
-}
-__device__ __forceinline__ double unpack_ll(unsigned long long a, unsigned long long b) {
-    return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
-}
-__device__ __forceinline__ bool tag_ok(unsigned long long a, unsigned long long b, unsigned int tag) {
-    return ((unsigned int)(a >> 32) == tag) && ((unsigned int)(b >> 32) == tag);
-}
+__device__ __forceinline__ void ld_ll(const unsigned long long* p, unsigned long long& a, unsigned long long& b) { ll::ld2(p, a, b); }
+__device__ __forceinline__ void push_ll(unsigned long long* p, double v, unsigned int tag) { ll::push(p, v, tag); }
+__device__ __forceinline__ double unpack_ll(unsigned long long a, unsigned long long b) { return ll::unpack(a, b); }
+__device__ __forceinline__ bool tag_ok(unsigned long long a, unsigned long long b, unsigned int tag) { return ll::tag_ok(a, b, tag); }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -602,10 +590,13 @@ bool p2p_fits(elph_handle* h) {
 size_t arena_vec_doubles(const elph_handle* h) { return 6 * (size_t)h->p2p.Lmax * h->N; }       // [2][3][Lmax][N]
 size_t arena_halo_words(const elph_handle* h) { return 12 * 2 * (size_t)h->N; }                  // [2][3][2][N][2]
 size_t arena_mbox_words() { return 2ull * kMaxWorld * 4; }
-size_t arena_bytes(const elph_handle* h) {
-    return arena_vec_doubles(h) * sizeof(double) + arena_halo_words(h) * sizeof(unsigned long long) +
-           arena_mbox_words() * sizeof(unsigned long long) + (4 * (size_t)h->p2p.Lmax + 4 * (size_t)h->N) * sizeof(double) + 256;
+size_t arena_p2p_bytes(const elph_handle* h) {
+    const size_t b = arena_vec_doubles(h) * sizeof(double) + arena_halo_words(h) * sizeof(unsigned long long) +
+                     arena_mbox_words() * sizeof(unsigned long long) + (4 * (size_t)h->p2p.Lmax + 4 * (size_t)h->N) * sizeof(double) + 256;
+    return (b + 255) & ~size_t(255);
 }
+// the region of the pipelined kernel (cg_pipe.cu) follows
+size_t arena_bytes(const elph_handle* h) { return arena_p2p_bytes(h) + elph_pipe_arena_bytes(h->N, h->p2p.Lmax); }
 double* arena_vec(const elph_handle* h, void* base) { return reinterpret_cast<double*>(base); }
 unsigned long long* arena_halo(const elph_handle* h, void* base) {
     return reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(base) + arena_vec_doubles(h));
@@ -626,6 +617,11 @@ void alloc_arena(elph_handle* h, int rank, int world, int Lglob) {
     ELPH_CUDA(cudaMalloc(&A.arena, arena_bytes(h)));
     ELPH_CUDA(cudaMemset(A.arena, 0, arena_bytes(h)));
     ELPH_CUDA(cudaDeviceSynchronize());
+    A.pipe_off = arena_p2p_bytes(h);
+    A.seq = 0;
+    A.pipe_seq = 0;
+    A.failed = false;
+    A.pipe_failed = false;
 }
 
 // run one solve on an opened arena; r0/x as in P2pParams.  Returns false if the kernel does not apply.
@@ -635,6 +631,7 @@ bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool sc
     int nwarps = 0;
     const int variant = p2p_variant(h, nwarps);
     if (!variant) return false;
+    ELPH_REQUIRE(!A.failed, ELPH_ERR_STATE, "peer-memory CG: an earlier solve on this arena timed out; re-open the peer arenas");
     cudaStream_t st = h->stream;
     const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
     P2pParams P;
@@ -666,8 +663,17 @@ bool run_p2p(elph_handle* h, const double* r0, double* x, bool x0_given, bool sc
     if (!ok) return false;
     ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
     ELPH_CUDA(cudaStreamSynchronize(st));
-    ELPH_REQUIRE(h->h_cg->done == 1, ELPH_ERR_STATE, "peer-memory CG: a peer GPU did not reach a barrier or deliver a halo tile (timeout)");
-    A.seq += 2u + (unsigned int)h->h_cg->iter;   // barriers executed: 1 + iterations; tags used: up to base + iterations + 1
+    if (h->h_cg->done != 1) {
+        // tags up to base + j + 1 of an unknown j may sit in the peers' arenas and the ranks may disagree on the count:
+        // the arena is unusable until every rank re-opens it (elph_shard_p2p_export / _open re-zero it and restart the tags)
+        A.failed = true;
+        ELPH_REQUIRE(false, ELPH_ERR_STATE, "peer-memory CG: a peer GPU did not reach a barrier or deliver a halo tile (timeout)");
+    }
+    // barriers executed: 1 + iterations (sequence numbers base + 1 .. base + 1 + iterations); tags used: up to base +
+    // iterations + 1.  Advancing by iterations + 3 puts the first barrier of the next solve on the OTHER mailbox parity than
+    // the last barrier of this one, so a rank that has already relaunched cannot overwrite a slot that a lagging CTA of this
+    // solve is still polling.
+    A.seq += 3u + (unsigned int)h->h_cg->iter;
     return true;
 }
 
@@ -680,7 +686,14 @@ void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned ch
     ELPH_REQUIRE(h->sq.enabled && h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
                  "the peer-memory CG needs the Holstein square-lattice register kernels");
     auto& A = h->p2p;
+    const bool had = (A.arena != nullptr);
     alloc_arena(h, rank, world, h->shard_Lglob);
+    if (had) {   // re-export (every rank does this together, e.g. after a timeout): stale tags must not survive
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        ELPH_CUDA(cudaMemset(A.arena, 0, arena_bytes(h)));
+        ELPH_CUDA(cudaDeviceSynchronize());
+        A.seq = 0; A.pipe_seq = 0; A.failed = false; A.pipe_failed = false;
+    }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t ipc;
     ELPH_CUDA(cudaIpcGetMemHandle(&ipc, A.arena));
@@ -706,7 +719,7 @@ void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, cons
         ELPH_CUDA(cudaIpcOpenMemHandle(&A.peer[q], ipc, cudaIpcMemLazyEnablePeerAccess));
     }
     A.opened = true;
-    const bool fits = p2p_fits(h);
+    const bool fits = p2p_fits(h) || elph_cg_pipe_fits(h);
     ELPH_REQUIRE(fits, ELPH_ERR_UNSUPPORTED,
                  "peer-memory CG: the slab's time slices are not all co-resident on this GPU (or unsupported lattice)");
 }
@@ -721,6 +734,11 @@ void elph_shard_p2p_close_impl(elph_handle* h) {
     A.opened = false;
 }
 
+// the pipelined kernel (cg_pipe.cu) is the default; forcing one of the older forms with tuning key 7 selects that form
+static bool want_pipeline(const elph_handle* h) {
+    return h->cg_pipeline == 1 || (h->cg_pipeline < 0 && h->cg_single_reduction < 0);
+}
+
 // Solve A x = b with x0 = 0 on the slab owned by this rank; every rank of the ring must make the same call.
 // b_own / x_own: [L][N] own slices (engine layout).  Returns false if the kernel does not apply (caller falls back).
 bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter, int64_t* iters,
@@ -729,7 +747,8 @@ bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, 
     ELPH_REQUIRE(A.opened, ELPH_ERR_STATE, "elph_shard_p2p_open has not been called");
     if (tol == 0.0) tol = h->cg_tol;
     if (maxiter == 0) maxiter = h->cg_maxiter;
-    if (!run_p2p(h, b_own, x_own, false, false, tol, maxiter)) return false;
+    const bool piped = want_pipeline(h) && elph_cg_pipe_run(h, b_own, x_own, false, false, tol, maxiter);
+    if (!piped && !run_p2p(h, b_own, x_own, false, false, tol, maxiter)) return false;
     if (iters) *iters = h->h_cg->iter;
     if (eps) *eps = h->h_cg->eps;
     return true;
@@ -738,13 +757,8 @@ bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, 
 // Single-GPU use on an unsharded handle (elph_cg_device): r0 in h->d_r, scalars in h->d_cg (cg_init_kernel), x_dev holds
 // the initial guess.  The ring closes inside the GPU; the arena is private.  Returns false if the kernel does not apply.
 bool elph_cg_single_reduction(elph_handle* h, double* x_dev) {
-    if (h->sharded || h->cg_single_reduction == 0) return false;
-    int nwarps = 0;
-    const int variant = p2p_variant(h, nwarps);
-    if (!variant || h->sq_disable || h->L < 2) return false;
-    // measured on B200 (scripts/bench_cg1r.py): 32x32xL200 6.93 -> 5.85 us/iteration; 64-wide lattices keep more state in
-    // shared memory under the 128-register cap and lose (9.7 -> 10.6 us), so they stay on the two-reduction kernel
-    if (h->cg_single_reduction < 0 && variant == 2) return false;
+    if (h->sharded || h->sq_disable || h->L < 2) return false;
+    if (!((h->model == ELPH_MODEL_SSH) ? h->ssq.enabled : h->sq.enabled)) return false;
     auto& A = h->p2p;
     if (!A.arena) {
         alloc_arena(h, 0, 1, h->L);
@@ -752,6 +766,15 @@ bool elph_cg_single_reduction(elph_handle* h, double* x_dev) {
         A.peer_L.assign(1, h->L);
         A.opened = true;
     }
+    // pipelined kernel: the reduction is off the critical path and a slice may be split over several SMs
+    if (want_pipeline(h) && elph_cg_pipe_run(h, h->d_r, x_dev, true, true, 0.0, 0)) return true;
+    if (h->cg_single_reduction == 0) return false;
+    int nwarps = 0;
+    const int variant = p2p_variant(h, nwarps);
+    if (!variant) return false;
+    // measured on B200 (scripts/bench_cg1r.py): 32x32xL200 6.93 -> 5.85 us/iteration; 64-wide lattices keep more state in
+    // shared memory under the 128-register cap and lose (9.7 -> 10.6 us), so they stay on the two-reduction kernel
+    if (h->cg_single_reduction < 0 && variant == 2) return false;
     if (!p2p_fits(h)) return false;
     return run_p2p(h, h->d_r, x_dev, true, true, 0.0, 0);
 }

@@ -272,7 +272,18 @@ struct elph_handle {
         int rank = 0, world = 1, Lmax = 0;
         unsigned int seq = 0;       // sequence number of the last cross-GPU barrier executed
         bool opened = false;
+        bool failed = false;        // a solve timed out: tags on the peers are undefined until the arenas are re-opened
+        // pipelined CG (cg_pipe.cu): its region of the same arena, own tag counter
+        size_t pipe_off = 0;
+        unsigned int pipe_seq = 0;
+        bool pipe_failed = false;
     } p2p;
+    int cg_pipeline = -1;          // unpreconditioned CG on square lattices: pipelined persistent kernel (cg_pipe.cu); -1 = auto, 0 = off
+    int pipe_ys = 0;               // tuning: CTAs per time slice of the pipelined kernel (0 = automatic)
+    int pipe_variant = 0;          // tuning key 13: force one variant of the pipelined kernel (0 = automatic)
+    bool pipe_prof = false;        // tuning key 12: per-phase cycle counters of the pipelined kernel (development aid)
+    unsigned long long* pipe_prof_buf = nullptr;   // [8192][8]
+    int pipe_last_variant = 0;     // variant * 100 + ys * 10 + warps of the last pipelined solve (diagnostics)
     double* d_D_alloc = nullptr;   // sharded: d_D points one slice into this allocation (halo slices around it)
     double* d_x_alloc = nullptr;   // sharded: same for the phonon field (the force needs no x halo; kept symmetric)
     bool sq_disable = false;
@@ -356,6 +367,10 @@ void elph_shard_p2p_close_impl(elph_handle* h);
 bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter, int64_t* iters,
                             double* eps);
 bool elph_cg_single_reduction(elph_handle* h, double* x_dev);
+// cg_pipe.cu
+size_t elph_pipe_arena_bytes(int N, int Lmax);
+bool elph_cg_pipe_fits(elph_handle* h);
+bool elph_cg_pipe_run(elph_handle* h, const double* r0, double* x, bool x0_given, bool scalars_on_device, double tol, int64_t maxiter);
 // buffers of nrhs independent solves for the persistent kernels (right-hand side k at + k*vstride / k*pstride / k)
 struct CgBatchBufs {
     double* x = nullptr;

@@ -369,8 +369,15 @@ int32_t elph_set_chunk(elph_handle* h, int32_t slices_per_cta);
  *     lattices; same iterates to rounding, iteration counts within +-2 of the two-reduction loop; -1 = auto (default: on for
  *     32-wide lattices, where it is measured faster), 0 = off, 1 = on),
  * 8 = replicas per stage of the H2D | kernels | D2H pipeline behind elph_mulMTM_batch (1..8, default 8),
- * 9 = multi-timestep HMC: the Nb inner (bosonic) steps of an outer step in one kernel (default 1) */
+ * 9 = multi-timestep HMC: the Nb inner (bosonic) steps of an outer step in one kernel (default 1),
+ * 10 = pipelined form of the persistent unpreconditioned CG (csrc/cg_pipe.cu: the all-reduce of an iteration overlaps the
+ *      next product, a time slice may be split over several SMs; periodic square lattices; iteration counts within +-2 of
+ *      the reference loop; -1 = auto (default: on unless key 7 forces one of the older forms), 0 = off, 1 = on),
+ * 11 = CTAs per time slice of the pipelined kernel (0 = auto, else 1, 2, 4, 8) */
 int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value);
+/* read-back of a tuning key; key 100 = which kernel served the last unpreconditioned persistent solve: 0 = none yet /
+ * other kernels, else variant * 100 + CTAs per slice * 10 + warps per CTA of the pipelined kernel */
+int32_t elph_get_tuning(elph_handle* h, int32_t key, int32_t* value);
 /* which kernel family serves the fused M^T M product of this model, and the number of bond colours found */
 int32_t elph_get_kernel_info(elph_handle* h, int32_t* square_kernel, int32_t* ngroups);
 
