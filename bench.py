@@ -530,47 +530,60 @@ def main():
         beE = CudaSlabBackend(mE, tau0, LtauE)
         opE = ShardedOperator(beE, RingComm(rank, world))
         opE.update_model()
+        # products first with the torch.distributed halos (NCCL send/recv), then with the halos pushed through peer memory inside
+        # one kernel (elph_dev_shard_halo): no NCCL call, no host synchronisation per product
         vE, yE = beE.empty(), beE.empty()
         vE[1:lloc + 1].normal_()
-        for _ in range(5):
-            opE.mulMTM(yE, vE)
-        barrier()
-        nrep = 50
-        e0.record()
-        for _ in range(nrep):
-            opE.mulMTM(yE, vE)
-        e1.record()
-        barrier()
-        msE = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([msE], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            msE = float(t.item())
-        usE = msE * 1e3 / nrep
+
+        def time_products(nrep=50):
+            for _ in range(5):
+                opE.mulMTM(yE, vE)
+            barrier()
+            e0.record()
+            for _ in range(nrep):
+                opE.mulMTM(yE, vE)
+            e1.record()
+            barrier()
+            ms_ = e0.elapsed_time(e1)
+            if world > 1:
+                t_ = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                ms_ = float(t_.item())
+            return ms_ * 1e3 / nrep
+
+        us_nccl = time_products()
+        p2p_open = opE.enable_p2p()
+        usE = time_products() if p2p_open else us_nccl
         sharded = {"workload": "holstein_square_64x64_L400, one lattice tau-sharded over the ranks (strong scaling)",
                    "us_per_matvec": usE, "matvecs_per_s": 1e6 / usE, "slab_slices_per_gpu": lloc,
+                   "us_per_matvec_nccl_halo": us_nccl,
                    "algorithmic_GBps_per_gpu": BYTES_PER_POINT * mE.Nsites * lloc / usE / 1e3,
-                   "collective": "1 halo slice each way per product (NCCL send/recv), antiperiodic sign on global slice 0"}
-        # CG on the sharded lattice: the peer-memory persistent kernel (collectives inside the kernel, csrc/cg_p2p.cu) where
-        # every slab is co-resident, else the single-GPU engine (world = 1) or the NCCL-between-launches loop
+                   "collective": ("1 halo slice each way per product pushed through NVLink peer memory inside one kernel "
+                                  "(elph_dev_shard_halo)" if p2p_open else "1 halo slice each way per product (NCCL send/recv)") +
+                                 ", antiperiodic sign on global slice 0"}
+        # CG on the sharded lattice: the pipelined persistent kernel (halo pushes + all-reduce over NVLink inside the kernel,
+        # csrc/cg_pipe.cu) where every slab is co-resident, else the single-GPU engine (world = 1) or the NCCL-between-launches loop
         bE, xE = beE.empty(), beE.empty()
         bE[1:lloc + 1] = torch.from_numpy(bgE[tau0:tau0 + lloc]).cuda()
         cgE = {}
-        if opE.enable_p2p():
+        if getattr(beE, "_p2p_ready", False):
             opE.solve(xE, bE)
             barrier()
             t0 = time.perf_counter()
             itE, epsE = opE.solve(xE, bE)
             torch.cuda.synchronize()
             dtE = time.perf_counter() - t0
-            cgE = {"path": "peer-memory persistent kernel: halo pushes + scalar all-reduces over NVLink inside the kernel"}
+            kv = C.c_int32()
+            lib.elph_get_tuning(mE.handle, 100, C.byref(kv))
+            cgE = {"path": "persistent kernel per GPU: halo pushes + scalar all-reduce over NVLink inside the kernel",
+                   "kernel": f"cgpipe variant*100 + CTAs per slice*10 + warps = {kv.value}" if kv.value else "cg_p2p (single reduction)"}
         elif world == 1:
             from elphdynamics_b200 import workloads
             mF, _ = workloads.holstein("square", LE, LtauE * DTAU, DTAU, seed=5)
             mF.x = xgE.reshape(-1)
             E.update_model_(mF)
             mF.set_stream(torch.cuda.current_stream().cuda_stream)
-            bF = torch.from_numpy(np.ascontiguousarray(bgE.T).reshape(-1)).cuda()
+            bF = torch.from_numpy(np.ascontiguousarray(bgE).reshape(-1)).cuda()     # engine layout [tau][site], as the slabs
             xF = torch.zeros_like(bF)
             itc, epc = C.c_int64(), C.c_double()
             for _ in range(2):
@@ -589,13 +602,26 @@ def main():
             itE, epsE = opE.solve_cg(xE, bE, maxiter=40)
             torch.cuda.synchronize()
             dtE = time.perf_counter() - t0
-            cgE = {"path": "NCCL send/recv + all-reduce between launches (bounded to 40 iterations)"}
+            cgE = {"path": "launch-per-operation CG, halos through peer memory, scalar all-reduces through NCCL (bounded to 40 iterations)"}
         if world > 1:
             t = torch.tensor([dtE], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dtE = float(t.item())
         cgE.update({"iters": int(itE), "eps": float(epsE), "seconds": dtE, "us_per_iter": dtE / max(int(itE), 1) * 1e6,
                     "algorithmic_GBps_aggregate": 96.0 * mE.Nsites * LtauE * int(itE) / dtE / 1e9})
+        # strong-scaling efficiency of this run against the committed 1-GPU figures of the same lattice (this process only knows
+        # its own N; the driver's SCALE record holds all four runs)
+        ref_p = ROOT / "profiles" / "tau_sharded_reference.json"
+        if ref_p.exists():
+            try:
+                ref = json.loads(ref_p.read_text())
+                sharded["efficiency"] = {
+                    "cg_strong": ref["cg_us_per_iter_1gpu"] / (world * cgE["us_per_iter"]),
+                    "matvec_strong": ref["us_per_matvec_1gpu"] / (world * usE),
+                    "reference": {"cg_us_per_iter_1gpu": ref["cg_us_per_iter_1gpu"], "us_per_matvec_1gpu": ref["us_per_matvec_1gpu"],
+                                  "source": ref.get("source", "profiles/tau_sharded_reference.json")}}
+            except Exception:
+                pass
         sharded["cg"] = cgE
         mE.close()
 

@@ -303,6 +303,7 @@ void destroy(elph_handle* h) {
     }
     elph_shard_p2p_close_impl(h);
     if (h->pipe_prof_buf) cudaFree(h->pipe_prof_buf);
+    if (h->h_hx_flag) cudaFreeHost(h->h_hx_flag);
     if (h->d_D_alloc) {  // sharded: d_D points one slice into this allocation
         cudaFree(h->d_D_alloc);
         h->d_D = nullptr;
@@ -1082,6 +1083,24 @@ int32_t elph_dev_shard_cg_p2p(elph_handle* h, const double* b_own, double* x_own
         ELPH_REQUIRE(b_own && x_own, ELPH_ERR_INVALID, "null device pointer");
         ELPH_REQUIRE(elph_shard_cg_p2p_impl(h, b_own, x_own, tol, maxiter, iters, eps), ELPH_ERR_UNSUPPORTED,
                      "peer-memory CG: the slab's time slices are not all co-resident on this GPU (or unsupported lattice)");
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_shard_cg_available(elph_handle* h, int32_t* available) {
+    ENTER(h) {
+        ELPH_REQUIRE(available, ELPH_ERR_INVALID, "null output");
+        *available = elph_shard_cg_available_impl(h) ? 1 : 0;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_shard_halo(elph_handle* h, double* v_own) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->sharded && v_own, ELPH_ERR_INVALID, "elph_set_shard has not been called / null pointer");
+        elph_shard_halo_impl(h, v_own);
         return ELPH_OK;
     }
     ELPH_CATCH(h)

@@ -620,8 +620,11 @@ void alloc_arena(elph_handle* h, int rank, int world, int Lglob) {
     A.pipe_off = arena_p2p_bytes(h);
     A.seq = 0;
     A.pipe_seq = 0;
+    A.hx_seq = 0;
     A.failed = false;
     A.pipe_failed = false;
+    if (!h->h_hx_flag) ELPH_CUDA(cudaMallocHost(&h->h_hx_flag, sizeof(unsigned int)));
+    *h->h_hx_flag = 0u;
 }
 
 // run one solve on an opened arena; r0/x as in P2pParams.  Returns false if the kernel does not apply.
@@ -692,7 +695,8 @@ void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned ch
         ELPH_CUDA(cudaStreamSynchronize(h->stream));
         ELPH_CUDA(cudaMemset(A.arena, 0, arena_bytes(h)));
         ELPH_CUDA(cudaDeviceSynchronize());
-        A.seq = 0; A.pipe_seq = 0; A.failed = false; A.pipe_failed = false;
+        A.seq = 0; A.pipe_seq = 0; A.hx_seq = 0; A.failed = false; A.pipe_failed = false;
+        *h->h_hx_flag = 0u;
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t ipc;
@@ -718,10 +722,7 @@ void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, cons
         memcpy(&ipc, handles + (size_t)q * sizeof(ipc), sizeof(ipc));
         ELPH_CUDA(cudaIpcOpenMemHandle(&A.peer[q], ipc, cudaIpcMemLazyEnablePeerAccess));
     }
-    A.opened = true;
-    const bool fits = p2p_fits(h) || elph_cg_pipe_fits(h);
-    ELPH_REQUIRE(fits, ELPH_ERR_UNSUPPORTED,
-                 "peer-memory CG: the slab's time slices are not all co-resident on this GPU (or unsupported lattice)");
+    A.opened = true;   // the halo exchange of the products works from here on; the persistent CG needs co-resident slabs on top
 }
 
 void elph_shard_p2p_close_impl(elph_handle* h) {
@@ -738,6 +739,8 @@ void elph_shard_p2p_close_impl(elph_handle* h) {
 static bool want_pipeline(const elph_handle* h) {
     return h->cg_pipeline == 1 || (h->cg_pipeline < 0 && h->cg_single_reduction < 0);
 }
+
+bool elph_shard_cg_available_impl(elph_handle* h) { return h->p2p.opened && (p2p_fits(h) || elph_cg_pipe_fits(h)); }
 
 // Solve A x = b with x0 = 0 on the slab owned by this rank; every rank of the ring must make the same call.
 // b_own / x_own: [L][N] own slices (engine layout).  Returns false if the kernel does not apply (caller falls back).

@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 struct PipeLayout {   // offsets (bytes) inside the pipe region of an arena; identical on every rank
-    size_t rows, part, bcast, mbox, abort_word, pg, ghost, total;
+    size_t rows, part, bcast, mbox, abort_word, pg, ghost, hx, hx_flag, total;
 };
 PipeLayout pipe_layout(int N, int Lmax) {
     PipeLayout Y;
@@ -788,6 +788,8 @@ PipeLayout pipe_layout(int N, int Lmax) {
     Y.abort_word = take(sizeof(unsigned int));
     Y.pg = take((size_t)Lmax * N * sizeof(double));
     Y.ghost = take(4ull * Lmax * N * sizeof(double));
+    Y.hx = take(2ull * 2 * N * 2 * sizeof(unsigned long long));      // halo exchange of the products: [2 parities][lo, hi][N][2 words]
+    Y.hx_flag = take(sizeof(unsigned int));
     Y.total = o;
     return Y;
 }
@@ -944,7 +946,9 @@ int pipe_candidates(const elph_handle* h, int (&cand)[32][3]) {
     auto add_ys = [&](int ys) {
         if (ssh) { if (Lx == 32 && !h->sharded && ys == 1) add(6, 1); return; }
         if (Lx == 32) { add(1, ys); add(7, ys); add(2, ys); }
-        else if (Lx == 64) { add(3, ys); add(8, ys); add(4, ys); add(9, ys); add(5, ys); }
+        // (variant 5 -- most of the state in L2 -- is slower than the launch-per-iteration path: 43 against 25 us per iteration
+        // at 64x64xL200; it stays selectable with tuning key 13 only)
+        else if (Lx == 64) { add(3, ys); add(8, ys); add(4, ys); add(9, ys); if (h->pipe_variant == 5) add(5, ys); }
     };
     if (h->pipe_ys > 0) add_ys(h->pipe_ys);    // tuning key 11 first; whatever does not fit falls through to the automatic order
     if (Lx == 32) for (int ys = 1; ys <= kMaxYS; ys *= 2) add_ys(ys);
@@ -966,7 +970,52 @@ bool pipe_select(elph_handle* h, PipeParams& P, PipeConfig& C, bool launch) {
     return false;
 }
 
+// Halo exchange of one halo'd vector ([-1] and [L] around the own slices) through peer memory: every rank pushes its first own
+// slice into the left neighbour's hi row and its last own slice into the right neighbour's lo row as self-validating words,
+// then unpacks its own two rows into the vector.  One launch, no NCCL call, no host synchronisation; the product that
+// follows in the stream finds its halos in place.  Both directions always travel: completing exchange k then implies that
+// both neighbours have consumed exchange k-1, which makes two buffers (tag parity) enough.
+__global__ void __launch_bounds__(256) halo_exchange_kernel(double* v_own, int L, int N, unsigned long long* mine, unsigned long long* left,
+                                                            unsigned long long* right, unsigned int tag, unsigned int* fail_flag) {
+    const size_t side = (size_t)N * 2, par = (size_t)(tag & 1u) * 2 * side;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N; e += gridDim.x * blockDim.x) {
+        ll::push(left + par + side + 2 * (size_t)e, v_own[e], tag);                         // first slice -> left neighbour's hi row
+        ll::push(right + par + 2 * (size_t)e, v_own[(size_t)(L - 1) * N + e], tag);          // last slice -> right neighbour's lo row
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N; e += gridDim.x * blockDim.x) {
+        unsigned long long a0, a1, b0, b1;
+        unsigned int spins = 0;
+        bool ok;
+        do {
+            ll::ld2(mine + par + 2 * (size_t)e, a0, a1);
+            ll::ld2(mine + par + side + 2 * (size_t)e, b0, b1);
+            ok = ll::tag_ok(a0, a1, tag) && ll::tag_ok(b0, b1, tag);
+        } while (!ok && ++spins < kSpinLimit);
+        if (!ok) st_volatile_u32(fail_flag, 1u);
+        v_own[-(ptrdiff_t)N + e] = ll::unpack(a0, a1);
+        v_own[(size_t)L * N + e] = ll::unpack(b0, b1);
+    }
+}
+
 }  // namespace
+
+void elph_shard_halo_impl(elph_handle* h, double* v_own) {
+    auto& A = h->p2p;
+    ELPH_REQUIRE(A.arena && A.opened, ELPH_ERR_STATE, "elph_shard_p2p_open has not been called");
+    const PipeLayout Y = pipe_layout(h->N, A.Lmax);
+    auto at = [&](void* base, size_t off) { return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + A.pipe_off + off); };
+    const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
+    unsigned int* flag = reinterpret_cast<unsigned int*>(at(A.arena, Y.hx_flag));
+    if (A.hx_seq != 0) {     // outcome of the previous exchanges (lags by one call: nothing here waits for the device)
+        ELPH_REQUIRE(*h->h_hx_flag == 0u, ELPH_ERR_STATE, "halo exchange: a neighbour GPU did not deliver its slice in time (timeout)");
+    }
+    const int threads = 256, blocks = std::min(h->sm_count, (h->N + threads - 1) / threads);
+    halo_exchange_kernel<<<blocks, threads, 0, h->stream>>>(v_own, h->L, h->N, at(A.arena, Y.hx), at(A.peer[left], Y.hx), at(A.peer[right], Y.hx),
+                                                            ++A.hx_seq, flag);
+    ELPH_CUDA(cudaGetLastError());
+    ELPH_CUDA(cudaMemcpyAsync(h->h_hx_flag, flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    h->launches++;
+}
 
 size_t elph_pipe_arena_bytes(int N, int Lmax) { return pipe_layout(N, Lmax).total; }
 

@@ -275,9 +275,11 @@ struct elph_handle {
         bool failed = false;        // a solve timed out: tags on the peers are undefined until the arenas are re-opened
         // pipelined CG (cg_pipe.cu): its region of the same arena, own tag counter
         size_t pipe_off = 0;
+        unsigned int hx_seq = 0;    // halo exchanges of the products executed (tag of the last one)
         unsigned int pipe_seq = 0;
         bool pipe_failed = false;
     } p2p;
+    unsigned int* h_hx_flag = nullptr;   // pinned: failure flag of the peer-memory halo exchange
     int cg_pipeline = -1;          // unpreconditioned CG on square lattices: pipelined persistent kernel (cg_pipe.cu); -1 = auto, 0 = off
     int pipe_ys = 0;               // tuning: CTAs per time slice of the pipelined kernel (0 = automatic)
     int pipe_variant = 0;          // tuning key 13: force one variant of the pipelined kernel (0 = automatic)
@@ -364,12 +366,14 @@ void elph_greens_setup_impl(elph_handle* h, int n1, int n2, int L1, int L2, int 
 void elph_shard_p2p_export_impl(elph_handle* h, int rank, int world, unsigned char* handle_out);
 void elph_shard_p2p_open_impl(elph_handle* h, const unsigned char* handles, const int64_t* slab_lengths);
 void elph_shard_p2p_close_impl(elph_handle* h);
+bool elph_shard_cg_available_impl(elph_handle* h);
 bool elph_shard_cg_p2p_impl(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter, int64_t* iters,
                             double* eps);
 bool elph_cg_single_reduction(elph_handle* h, double* x_dev);
 // cg_pipe.cu
 size_t elph_pipe_arena_bytes(int N, int Lmax);
 bool elph_cg_pipe_fits(elph_handle* h);
+void elph_shard_halo_impl(elph_handle* h, double* v_own);
 bool elph_cg_pipe_run(elph_handle* h, const double* r0, double* x, bool x0_given, bool scalars_on_device, double tol, int64_t maxiter);
 // buffers of nrhs independent solves for the persistent kernels (right-hand side k at + k*vstride / k*pstride / k)
 struct CgBatchBufs {

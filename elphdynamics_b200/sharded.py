@@ -37,10 +37,14 @@ class RingComm:
         self.rank, self.world, self.group = rank, world, group
         self.left = (rank - 1) % world
         self.right = (rank + 1) % world
+        self.peer_halo = None        # set by ShardedOperator.enable_p2p(): halo exchange through peer memory instead of NCCL
 
     def exchange(self, v, lloc: int, lo: bool = True, hi: bool = True):
         """Fill v[0] with the left neighbour's last own slice and v[lloc+1] with the right neighbour's first own slice."""
         import torch.distributed as dist
+        if self.peer_halo is not None:       # peer-memory push inside one kernel (csrc/cg_pipe.cu), both directions always
+            self.peer_halo(v)
+            return
         if self.world == 1:
             if lo:
                 v[0].copy_(v[lloc])
@@ -136,7 +140,8 @@ class CudaSlabBackend:
     # ---- peer-memory CG (csrc/cg_p2p.cu): arenas shared through CUDA IPC, collectives inside the kernel --------------
     def p2p_setup(self, comm: "RingComm") -> bool:
         """Export this rank's arena, all-gather the IPC handles and slab lengths over torch.distributed, open the peers'.
-        Returns True when the peer-memory CG applies on EVERY rank (square lattice, all slices of every slab co-resident)."""
+        Returns True when the arenas are open on EVERY rank (halo exchange through peer memory); ``_p2p_ready`` tells
+        whether the persistent CG kernels apply as well (all slices of every slab co-resident)."""
         import torch.distributed as dist
         buf = (C.c_ubyte * 64)()
         ok = True
@@ -159,12 +164,23 @@ class CudaSlabBackend:
                 ok = False
         else:
             ok = False
+        cg_ok = False
+        if ok:
+            avail = C.c_int32()
+            self._check(self.lib.elph_shard_cg_available(self.h, C.byref(avail)))
+            cg_ok = bool(avail.value)
         if comm.world > 1:                       # every rank must take the same path
             flags = [None] * comm.world
-            dist.all_gather_object(flags, ok, group=comm.group)
-            ok = all(flags)
-        self._p2p_ready = ok
+            dist.all_gather_object(flags, (ok, cg_ok), group=comm.group)
+            ok = all(f[0] for f in flags)
+            cg_ok = all(f[1] for f in flags)
+        self._p2p_open = ok                      # arenas mapped: halo exchange through peer memory
+        self._p2p_ready = ok and cg_ok           # ... and every slab is co-resident: the persistent CG kernels apply
         return ok
+
+    def halo_p2p(self, v):
+        """Halo slices of a (Lloc+2, N) slab tensor through peer memory: one kernel, no NCCL call (elph_dev_shard_halo)."""
+        self._check(self.lib.elph_dev_shard_halo(self.h, self.own_ptr(v)))
 
     def cg_p2p(self, x, b, tol: float = 0.0, maxiter: int = 0):
         """Whole CG solve (x0 = 0) in one persistent kernel per GPU; returns (iters, eps).  x, b: halo'd slab tensors."""
@@ -246,7 +262,10 @@ class ShardedOperator:
     def enable_p2p(self) -> bool:
         """Use the peer-memory CG (one persistent kernel per GPU, collectives inside it) for solve() where it applies."""
         setup = getattr(self.be, "p2p_setup", None)
-        return bool(setup and setup(self.comm))
+        ok = bool(setup and setup(self.comm))
+        if ok and hasattr(self.be, "halo_p2p"):
+            self.comm.peer_halo = self.be.halo_p2p
+        return ok
 
     def solve(self, x, b, tol: float = 0.0, maxiter: int = 0):
         """solve!(x, A, b, cg) with x0 = 0 (what every caller on the hot path does, src/LangevinDynamics.jl:355-360):

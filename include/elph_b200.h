@@ -327,11 +327,19 @@ int32_t elph_dev_shard_muldMdx(elph_handle* h, const double* u_own, const double
  * the slab's time slices are not all co-resident on the GPU; ELPH_ERR_STATE if a peer never reached a barrier. */
 int32_t elph_shard_p2p_export(elph_handle* h, int32_t rank, int32_t world, unsigned char* ipc_handle_out);
 int32_t elph_shard_p2p_open(elph_handle* h, const unsigned char* ipc_handles, const int64_t* slab_lengths);
+/* 1 when a persistent CG kernel can serve this rank's slab (every time slice co-resident on the GPU); elph_shard_p2p_open
+ * succeeds either way (the halo exchange elph_dev_shard_halo needs only the arenas) */
+int32_t elph_shard_cg_available(elph_handle* h, int32_t* available);
 int32_t elph_dev_shard_cg_p2p(elph_handle* h, const double* b_own, double* x_own, double tol, int64_t maxiter,
                               int64_t* iters, double* eps);
 int32_t elph_dev_update_model(elph_handle* h);
 /* calc_dSbdx! on a slab: dSbdx_own += dSb/dx, x_own = first own slice of a halo'd copy of the field (periodic in tau) */
 int32_t elph_dev_shard_dSbdx(elph_handle* h, double* dSbdx_own, const double* x_own, int32_t shifted);
+/* Halo exchange of one halo'd slab vector through peer memory (after elph_shard_p2p_open): fills the slice before v_own with the
+ * left neighbour's last own slice and the slice after the own ones with the right neighbour's first own slice -- the exchange
+ * every product of the sharded lattice needs (mulM!: tau-1, src/HolsteinModels.jl:594-601; mulMT!: tau+1, :671-677).  One
+ * kernel launch on the handle's stream, no host synchronisation; every rank of the ring must make the same call. */
+int32_t elph_dev_shard_halo(elph_handle* h, double* v_own);
 /* fourier_accelerate! for `ncols` columns in [k][col] layout with an explicit diagonal (same layout): after the
  * all-to-all transpose of the tau-sharded driver a rank holds all Ltau slices of a subset of the sites.  The handle's
  * Ltau must be the GLOBAL time extent (the driver keeps a 1-site handle just for this plan). */

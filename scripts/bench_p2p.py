@@ -65,7 +65,11 @@ try:
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out["p2p"] = {"iters": it, "eps": eps, "seconds": float(t.item()), "us_per_iter": float(t.item()) / it * 1e6}
+    import ctypes as _C
+    var = _C.c_int32()
+    m._lib.elph_get_tuning(m.handle, 100, _C.byref(var))
+    out["p2p"] = {"iters": it, "eps": eps, "seconds": float(t.item()), "us_per_iter": float(t.item()) / it * 1e6,
+                  "kernel": ("pipelined (cg_pipe.cu) variant*100+ys*10+warps = %d" % var.value) if var.value else "single-reduction (cg_p2p.cu)"}
 except RuntimeError as e:
     out["p2p"] = {"error": str(e)[:200]}
 if baseline:

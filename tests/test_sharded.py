@@ -403,7 +403,16 @@ def _gpu_worker(rank, world, port):
 def _check_p2p_cg(be, comm, tau0, lloc, b_glob, x_ref, it_ref):
     """Peer-memory CG (csrc/cg_p2p.cu): one persistent kernel per GPU, halo + all-reduce inside the kernel."""
     import torch
-    be.p2p_setup(comm)
+    assert be.p2p_setup(comm) and be._p2p_ready
+    # halo exchange through peer memory (elph_dev_shard_halo) against the torch.distributed exchange, repeated (tag parity)
+    for rep in range(3):
+        v = be.empty()
+        v[1:lloc + 1] = torch.from_numpy(b_glob[tau0:tau0 + lloc] + rep).to(v.device)
+        ref = v.clone()
+        comm.exchange(ref, lloc)
+        be.halo_p2p(v)
+        torch.cuda.synchronize()
+        assert torch.equal(v, ref)
     b = be.empty()
     b[1:lloc + 1] = torch.from_numpy(b_glob[tau0:tau0 + lloc]).to(b.device)
     x = be.empty()
