@@ -1234,6 +1234,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 9: h->hmc_fused_inner = (value != 0); break;
             case 10: h->cg_pipeline = (value < 0) ? -1 : (value != 0); break;
             case 13: ELPH_REQUIRE(value >= 0 && value <= 16, ELPH_ERR_INVALID, "variant out of range"); h->pipe_variant = value; break;
+            case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:
                 h->pipe_prof = (value != 0);
                 if (h->pipe_prof && !h->pipe_prof_buf) {
@@ -1261,6 +1262,7 @@ int32_t elph_get_tuning(elph_handle* h, int32_t key, int32_t* value) {
             case 10: *value = h->cg_pipeline; break;
             case 11: *value = h->pipe_ys; break;
             case 100: *value = h->pipe_last_variant; break;
+            case 101: *value = h->pipe_last_spc; break;
             default: ELPH_REQUIRE(false, ELPH_ERR_INVALID, "unknown tuning key");
         }
         return ELPH_OK;

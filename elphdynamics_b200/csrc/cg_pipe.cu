@@ -77,10 +77,11 @@ struct PipeParams {
     unsigned int* abort_word;
     double* pg;                       // [Lmax][N] p when PL_XP_GLOBAL
     double* ghost;                    // [4][Lmax][N] when PL_GHOST_GLOBAL
+    double* state;                    // [6][Lmax][N] r, w, s, z, q, p in multi-slice mode
     CgScalars* S;
     unsigned long long* prof;         // development aid (tuning key 12): [cta][8] cycles per phase, summed over the iterations
     unsigned int base;                // tags of this solve: publication k -> base + 1 + k, reduction n -> base + 1 + n
-    int L, Lmax, Ly, ys, maxcta, rank, world, tau0, Lglob, d_halo, x0_given;
+    int L, Lmax, Ly, ys, spc, maxcta, rank, world, tau0, Lglob, d_halo, x0_given;
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
 
@@ -255,27 +256,35 @@ __device__ void reducer_loop(const PipeParams& P, int ncta, double (*rsum)[8], d
     }
 }
 
-template <int NSEG, int PY, int MAXT, int MINB, int PLACE, bool SSH>
+// MS (multi-slice, "streaming"): a CTA owns P.spc CONSECUTIVE time slices of its rows and keeps all vectors in global memory
+// (L2 resident at the slab sizes this is for: 64x64xL200 per GPU = 46 MB of state); only the two outer neighbours of the
+// chunk need ghosts and rows.  The slab sizes whose state does not fit registers + shared memory run this way.
+template <int NSEG, int PY, int MAXT, int MINB, int PLACE, bool SSH, bool MS = false>
 __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
     constexpr int LX = 32 * NSEG;
     constexpr bool XPS = (PLACE & PL_XP_SMEM) != 0, SZS = (PLACE & PL_SZ_SMEM) != 0, DS = (PLACE & PL_D_SMEM) != 0;
     constexpr bool XPG = (PLACE & PL_XP_GLOBAL) != 0, GG = (PLACE & PL_GHOST_GLOBAL) != 0, RS = (PLACE & PL_R_SMEM) != 0;
     constexpr bool PF = (PLACE & PL_PREFETCH) != 0;
     static_assert(!(XPS && XPG), "x, p: shared memory or global, not both");
+    static_assert(!MS || (GG && !XPS && !SZS && !DS && !RS && !SSH), "multi-slice mode: all state in global memory, Holstein");
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[2][8];
     __shared__ double cf[4];
     const int YS = P.ys;
     const int c = blockIdx.x / YS, yb = blockIdx.x - c * YS;
     const int L = P.L;
-    if (c >= L) {                       // the extra cluster: its first CTA is the reducer of this GPU
-        if (yb == 0) reducer_loop(P, L * YS, red, cf);
+    const int SPC = MS ? P.spc : 1;                       // slices per CTA
+    const int nchunk = (L + SPC - 1) / SPC;
+    if (c >= nchunk) {                  // the extra cluster: its first CTA is the reducer of this GPU
+        if (yb == 0) reducer_loop(P, nchunk * YS, red, cf);
         return;
     }
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
     const int N = LX * P.Ly;
     const int NB = PY * NW * LX;        // sites of this CTA
-    const int tau = c;
+    const int tau = c * SPC;                              // first own slice
+    const int ns = (L - tau < SPC) ? L - tau : SPC;       // own slices: tau .. taul
+    const int taul = tau + ns - 1;
     const bool multi = (P.world > 1);
 
     // ---- shared memory carve-up ------------------------------------------------------------------------------------
@@ -298,10 +307,13 @@ __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
     const long long rowm = (long long)((tau == 0) ? L - 1 : tau - 1) * N;
     const long long rowp = (long long)((tau == L - 1) ? 0 : tau + 1) * N;
     const long long rowDn = P.d_halo ? row + N : rowp;
-    const bool first = multi && (tau == 0), last = multi && (tau == L - 1);
+    const bool first = multi && (tau == 0), last = multi && (taul == L - 1);
     if constexpr (GG) {
+        // ghosts of the slice below the first own one are kept at the first own slice's position, those of the slice above the
+        // last own one at the last own slice's position (indexed by gidx below)
         const size_t gs = (size_t)P.Lmax * N;
-        gwl = P.ghost + row + tile_off - tid; gzl = gwl + gs; gwh = gzl + gs; gzh = gwh + gs;   // indexed by gidx below
+        gwl = P.ghost + row + tile_off - tid; gzl = gwl + gs;
+        gwh = P.ghost + 2 * gs + (long long)taul * N + tile_off - tid; gzh = gwh + gs;
     }
     // ghost element index: shared memory -> sidx, global -> position in the slice
     auto gidx = [&](int rr, int q) -> size_t {
@@ -400,9 +412,9 @@ __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
         txn = t1n + wo; tyn = t1n + RBL + wo; hyn = (warp == 0) ? t1n + 2 * RBL : t1n + RBL + wo - LX;
     }
 
-    const int tg = P.tau0 + tau;                       // global slice index
-    const bool wrap_c = (tg == 0);
-    const bool wrap_n = (tg + 1 == P.Lglob);
+    // antiperiodic wrap: the sign flips on GLOBAL slice 0 (re-set per slice in multi-slice mode)
+    bool wrap_c = (P.tau0 + tau == 0);
+    bool wrap_n = (P.tau0 + tau + 1 == P.Lglob);
     // t1 <- (M^T M v)(tau) from t1 = v(tau-1), vc = v(tau) and v(tau+1) delivered by load_next (after the first sweeps)
     auto apply_A = [&](const Tile<NSEG, PY>& vc, auto&& load_next) {
 #pragma unroll
@@ -459,22 +471,24 @@ __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
     const size_t rstride = (size_t)(P.Lmax + 2) * N * 2;      // words per parity
     auto row_words = [&](unsigned long long* b, unsigned int tag, int r) { return b + (size_t)(tag & 1u) * rstride + (size_t)r * N * 2; };
     const int r_lo = (tau > 0) ? 2 + tau - 1 : (multi ? 0 : 2 + L - 1);
-    const int r_hi = (tau < L - 1) ? 2 + tau + 1 : (multi ? 1 : 2);
+    const int r_hi = (taul < L - 1) ? 2 + taul + 1 : (multi ? 1 : 2);
     bool alive = true;
-    auto publish = [&](const Tile<NSEG, PY>& v, unsigned int tag) {
-        unsigned long long* own = row_words(P.rows, tag, 2 + tau);
-        unsigned long long* pl = first ? row_words(P.left_rows, tag, 1) : nullptr;
-        unsigned long long* pr2 = last ? row_words(P.right_rows, tag, 0) : nullptr;
+    // the row of own slice ts; to_left / to_right: it is also the neighbour GPU's halo row
+    auto publish_slice = [&](const Tile<NSEG, PY>& v, unsigned int tag, int ts, bool to_left, bool to_right) {
+        unsigned long long* own = row_words(P.rows, tag, 2 + ts);
+        unsigned long long* pl = to_left ? row_words(P.left_rows, tag, 1) : nullptr;
+        unsigned long long* pr2 = to_right ? row_words(P.right_rows, tag, 0) : nullptr;
 #pragma unroll
         for (int a = 0; a < PY; ++a)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
                 const size_t e = eidx(a, q);
-                if (first) ll::push(pl + 2 * e, v.a[a][q], tag);      // remote stores first: they travel furthest
-                if (last) ll::push(pr2 + 2 * e, v.a[a][q], tag);
+                if (to_left) ll::push(pl + 2 * e, v.a[a][q], tag);    // remote stores first: they travel furthest
+                if (to_right) ll::push(pr2 + 2 * e, v.a[a][q], tag);
                 ll::push(own + 2 * e, v.a[a][q], tag);
             }
     };
+    auto publish = [&](const Tile<NSEG, PY>& v, unsigned int tag) { publish_slice(v, tag, tau, first, last); };
     auto read_row = [&](int r, unsigned int tag, double (&out)[PY][NSEG]) {
         const unsigned long long* src = row_words(P.rows, tag, r);
         unsigned long long wa[PY][NSEG], wb[PY][NSEG];
@@ -596,6 +610,197 @@ __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
         beta = cf[1];
         return (int)cf[2];
     };
+
+    // ---- multi-slice mode ------------------------------------------------------------------------------------------------
+    if constexpr (MS) {
+        const size_t vs = (size_t)P.Lmax * N;
+        double* Rg = P.state;           // r, w, s, z, q, p of the own slices: touched by their owner thread only
+        double* Wg = Rg + vs;
+        double* Sg = Wg + vs;
+        double* Zg = Sg + vs;
+        double* Qg = Zg + vs;
+        double* Pg = Qg + vs;
+        double* Xg = P.x;
+        const unsigned int base = P.base;
+        auto rowof = [&](int ts) -> long long { return (long long)ts * N; };
+        // D(ts) and D(ts+1) of own slice ts into the register tiles apply_A reads; wrap flags of that slice
+        auto enter_slice = [&](int ts) {
+            const long long rk = rowof(ts);
+            const long long rdn = P.d_halo ? rk + N : rowof((ts == L - 1) ? 0 : ts + 1);
+#pragma unroll
+            for (int a = 0; a < PY; ++a)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) {
+                    Dcr.a[a][q] = P.D[rk + eidx(a, q)];
+                    Dnr.a[a][q] = P.D[rdn + eidx(a, q)];
+                }
+            wrap_c = (P.tau0 + ts == 0);
+            wrap_n = (P.tau0 + ts + 1 == P.Lglob);
+        };
+        auto load_tile = [&](const double* src, long long rk, Tile<NSEG, PY>& t) {
+#pragma unroll
+            for (int a = 0; a < PY; ++a)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) t.a[a][q] = __ldcg(src + rk + eidx(a, q));
+        };
+        // ---- set-up ------------------------------------------------------------------------------------------------------
+        for (int k = 0; k < ns; ++k) {
+            const long long rk = rowof(tau + k);
+#pragma unroll
+            for (int a = 0; a < PY; ++a)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) {
+                    const size_t e = rk + eidx(a, q);
+                    Rg[e] = P.r0[e];
+                    Sg[e] = 0.0; Zg[e] = 0.0; Pg[e] = 0.0;
+                    if (!P.x0_given) Xg[e] = 0.0;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < PY; ++a)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) { gzl[gidx(a, q)] = 0.0; gzh[gidx(a, q)] = 0.0; }
+        if (first) { load_tile(P.r0, rowof(0), w); publish_slice(w, base + 1u, 0, true, false); }          // r_0 for the neighbour GPUs
+        if (last) { load_tile(P.r0, rowof(L - 1), w); publish_slice(w, base + 1u, L - 1, false, true); }
+        double accg = 0.0, accd = 0.0;
+        for (int k = 0; k < ns; ++k) {
+            const int ts = tau + k;
+            enter_slice(ts);
+            Tile<NSEG, PY> vc;
+            load_tile(P.r0, rowof(ts), vc);
+            if (first && ts == 0) {
+                double hrow[PY][NSEG];
+                read_row(0, base + 1u, hrow);
+#pragma unroll
+                for (int a = 0; a < PY; ++a)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) t1.a[a][q] = hrow[a][q];
+            } else {
+                load_tile(P.r0, rowof(ts == 0 ? L - 1 : ts - 1), t1);
+            }
+            apply_A(vc, [&](double (&vn)[PY][NSEG]) {
+                if (last && ts == L - 1) read_row(1, base + 1u, vn);
+                else {
+                    const long long rn = rowof(ts == L - 1 ? 0 : ts + 1);
+#pragma unroll
+                    for (int a = 0; a < PY; ++a)
+#pragma unroll
+                        for (int q = 0; q < NSEG; ++q) vn[a][q] = P.r0[rn + eidx(a, q)];
+                }
+            });
+#pragma unroll
+            for (int a = 0; a < PY; ++a)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) {
+                    Wg[rowof(ts) + eidx(a, q)] = t1.a[a][q];
+                    accg = fma(vc.a[a][q], vc.a[a][q], accg);
+                    accd = fma(t1.a[a][q], vc.a[a][q], accd);
+                }
+            if (k == 0 || k == ns - 1) publish_slice(t1, base + 2u, ts, first && k == 0, last && k == ns - 1);   // w_0 of the edge slices
+        }
+        post(accg, accd, base + 1u);
+        {
+            double lo[PY][NSEG], hi[PY][NSEG];
+            read_row(r_lo, base + 2u, lo);
+            read_row(r_hi, base + 2u, hi);
+#pragma unroll
+            for (int a = 0; a < PY; ++a)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) { gwl[gidx(a, q)] = lo[a][q]; gwh[gidx(a, q)] = hi[a][q]; }
+        }
+        // q = A w for every own slice from the w of its neighbours: own slices from global memory, outer ones from the ghosts
+        auto products = [&](unsigned int tag) {
+            for (int k = 0; k < ns; ++k) {
+                const int ts = tau + k;
+                enter_slice(ts);
+                Tile<NSEG, PY> vc;
+                load_tile(Wg, rowof(ts), vc);
+                if (k == 0) {
+#pragma unroll
+                    for (int a = 0; a < PY; ++a)
+#pragma unroll
+                        for (int q = 0; q < NSEG; ++q) t1.a[a][q] = gwl[gidx(a, q)];
+                } else {
+                    load_tile(Wg, rowof(ts - 1), t1);
+                }
+                apply_A(vc, [&](double (&vn)[PY][NSEG]) {
+#pragma unroll
+                    for (int a = 0; a < PY; ++a)
+#pragma unroll
+                        for (int q = 0; q < NSEG; ++q) vn[a][q] = (k == ns - 1) ? gwh[gidx(a, q)] : __ldcg(Wg + rowof(ts + 1) + eidx(a, q));
+                });
+#pragma unroll
+                for (int a = 0; a < PY; ++a)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) __stcg(Qg + rowof(ts) + eidx(a, q), t1.a[a][q]);
+                if (k == 0 || k == ns - 1) publish_slice(t1, tag, ts, first && k == 0, last && k == ns - 1);
+            }
+        };
+        products(base + 3u);                                                         // q_0
+        // ---- iterations --------------------------------------------------------------------------------------------------
+        double alpha_prev = 0.0;
+        for (unsigned int j = 0;; ++j) {
+            double alpha, beta;
+            const int flags = wait_coeff(base + 1u + j, alpha, beta);
+            if (flags & 1) { alive = false; break; }
+            if (flags & 2) break;
+            prefetch_rows(base + 3u + j);
+            accg = 0.0; accd = 0.0;
+            for (int k = 0; k < ns; ++k) {
+                const long long rk = rowof(tau + k);
+                // all 7 x (PY x NSEG) loads of the slice in flight together: the phase is bound by memory-level parallelism
+                double rj[PY][NSEG], wj[PY][NSEG], sj[PY][NSEG], zj[PY][NSEG], qj[PY][NSEG], pj[PY][NSEG], xj[PY][NSEG];
+#pragma unroll
+                for (int a = 0; a < PY; ++a)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) {
+                        const size_t e = rk + eidx(a, q);
+                        rj[a][q] = __ldcg(Rg + e); wj[a][q] = __ldcg(Wg + e); sj[a][q] = __ldcg(Sg + e); zj[a][q] = __ldcg(Zg + e);
+                        qj[a][q] = __ldcg(Qg + e); pj[a][q] = __ldcg(Pg + e); xj[a][q] = __ldcg(Xg + e);
+                    }
+#pragma unroll
+                for (int a = 0; a < PY; ++a)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) {
+                        const size_t e = rk + eidx(a, q);
+                        if (j > 0) __stcg(Xg + e, fma(alpha_prev, pj[a][q], xj[a][q]));   // commit x_j = x_{j-1} + alpha_{j-1} p_{j-1}
+                        const double zv = fma(beta, zj[a][q], qj[a][q]);
+                        const double sv = fma(beta, sj[a][q], wj[a][q]);
+                        __stcg(Zg + e, zv);
+                        __stcg(Sg + e, sv);
+                        __stcg(Pg + e, fma(beta, pj[a][q], rj[a][q]));
+                        const double rv = fma(-alpha, sv, rj[a][q]);
+                        const double wv = fma(-alpha, zv, wj[a][q]);
+                        __stcg(Rg + e, rv);
+                        __stcg(Wg + e, wv);
+                        accg = fma(rv, rv, accg);
+                        accd = fma(wv, rv, accd);
+                    }
+            }
+            alpha_prev = alpha;
+            post(accg, accd, base + 2u + j);
+            {
+                double lo[PY][NSEG], hi[PY][NSEG];
+                fetch_rows(base + 3u + j, lo, hi);
+#pragma unroll
+                for (int a = 0; a < PY; ++a)
+#pragma unroll
+                    for (int q = 0; q < NSEG; ++q) {
+                        const size_t g = gidx(a, q);
+                        const double zl = fma(beta, gzl[g], lo[a][q]);
+                        const double zh = fma(beta, gzh[g], hi[a][q]);
+                        gzl[g] = zl;
+                        gzh[g] = zh;
+                        gwl[g] = fma(-alpha, zl, gwl[g]);
+                        gwh[g] = fma(-alpha, zh, gwh[g]);
+                    }
+            }
+            products(base + 4u + j);                                                 // q_{j+1}
+        }
+        if (!alive && tid == 0) st_volatile_u32(P.abort_word, 1u);
+        if (YS > 1) cluster.sync();
+        return;
+    }
 
     // ---- set-up: r_0, w_0 = A r_0, q_0 = A w_0 -------------------------------------------------------------------------
     const unsigned int base = P.base;
@@ -775,7 +980,7 @@ __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 struct PipeLayout {   // offsets (bytes) inside the pipe region of an arena; identical on every rank
-    size_t rows, part, bcast, mbox, abort_word, pg, ghost, hx, hx_flag, total;
+    size_t rows, part, bcast, mbox, abort_word, pg, ghost, state, hx, hx_flag, total;
 };
 PipeLayout pipe_layout(int N, int Lmax) {
     PipeLayout Y;
@@ -788,6 +993,7 @@ PipeLayout pipe_layout(int N, int Lmax) {
     Y.abort_word = take(sizeof(unsigned int));
     Y.pg = take((size_t)Lmax * N * sizeof(double));
     Y.ghost = take(4ull * Lmax * N * sizeof(double));
+    Y.state = take(6ull * Lmax * N * sizeof(double));
     Y.hx = take(2ull * 2 * N * 2 * sizeof(unsigned long long));      // halo exchange of the products: [2 parities][lo, hi][N][2 words]
     Y.hx_flag = take(sizeof(unsigned int));
     Y.total = o;
@@ -796,7 +1002,7 @@ PipeLayout pipe_layout(int N, int Lmax) {
 
 struct PipeConfig {
     int variant = 0;     // index into the instantiation table below, 0 = none applies
-    int py = 0, nw = 0, ys = 1;
+    int py = 0, nw = 0, ys = 1, spc = 1;
 };
 
 template <int NSEG, int PY, int MAXT, int MINB, int PLACE, bool SSH>
@@ -883,20 +1089,23 @@ bool pipe_launch(elph_handle* h, K kern, PipeParams& P, int grid, int threads, i
 //   8: Lx 64, 2 rows / warp, 8 warps (<= 128 registers)
 //   5: Lx 64, 4 rows / warp, 256 threads, s, z in shared memory, x, p and the ghosts in L2, 3 CTAs / SM (64x64xL400 on 2 GPUs)
 //   6: Lx 32, 8 rows / warp, SSH (tables of two slices resident in shared memory), single GPU
-#define PIPE_VARIANTS(V)                                         \
-    V(1, 1, 8, 128, 2, PL_PREFETCH, false)                                  \
-    V(2, 1, 4, 128, 3, PL_PREFETCH, false)                                  \
-    V(7, 1, 4, 256, 2, PL_PREFETCH, false)                                  \
-    V(3, 2, 4, 128, 2, PL_PREFETCH, false)                                  \
-    V(4, 2, 4, 128, 3, PL_XP_SMEM | PL_PREFETCH, false)           \
-    V(9, 2, 4, 128, 3, PL_XP_SMEM, false)                         \
-    V(8, 2, 2, 256, 2, PL_PREFETCH, false)                                  \
-    V(5, 2, 4, 256, 3, PL_SZ_SMEM | PL_XP_GLOBAL | PL_GHOST_GLOBAL, false) \
-    V(6, 1, 8, 128, 2, 0, true)
+//  10: Lx 64, multi-slice: 2..8 consecutive slices per CTA, all vectors in L2 (64x64xL400 on 1 or 2 GPUs);  11: the same for Lx 32
+#define PIPE_VARIANTS(V)                                                    \
+    V(1, 1, 8, 128, 2, PL_PREFETCH, false, false)                           \
+    V(2, 1, 4, 128, 3, PL_PREFETCH, false, false)                           \
+    V(7, 1, 4, 256, 2, PL_PREFETCH, false, false)                           \
+    V(3, 2, 4, 128, 2, PL_PREFETCH, false, false)                           \
+    V(4, 2, 4, 128, 3, PL_XP_SMEM | PL_PREFETCH, false, false)              \
+    V(9, 2, 4, 128, 3, PL_XP_SMEM, false, false)                            \
+    V(8, 2, 2, 256, 2, PL_PREFETCH, false, false)                           \
+    V(5, 2, 4, 256, 3, PL_SZ_SMEM | PL_XP_GLOBAL | PL_GHOST_GLOBAL, false, false) \
+    V(6, 1, 8, 128, 2, 0, true, false)                                      \
+    V(10, 2, 4, 128, 2, PL_GHOST_GLOBAL | PL_PREFETCH, false, true)         \
+    V(11, 1, 8, 128, 2, PL_GHOST_GLOBAL | PL_PREFETCH, false, true)
 
 int pipe_variant_py(int variant) {
     switch (variant) {
-#define V(id, nseg, py, maxt, minb, pl, ssh) case id: return py;
+#define V(id, nseg, py, maxt, minb, pl, ssh, ms) case id: return py;
         PIPE_VARIANTS(V)
 #undef V
         default: return 0;
@@ -904,15 +1113,25 @@ int pipe_variant_py(int variant) {
 }
 int pipe_variant_maxw(int variant) {
     switch (variant) {
-#define V(id, nseg, py, maxt, minb, pl, ssh) case id: return maxt / 32;
+#define V(id, nseg, py, maxt, minb, pl, ssh, ms) case id: return maxt / 32;
         PIPE_VARIANTS(V)
 #undef V
         default: return 0;
     }
 }
+bool pipe_variant_ms(int variant) {
+    switch (variant) {
+#define V(id, nseg, py, maxt, minb, pl, ssh, ms) case id: return ms;
+        PIPE_VARIANTS(V)
+#undef V
+        default: return false;
+    }
+}
 
-bool pipe_try(elph_handle* h, PipeParams& P, int variant, int nw, int ys, bool launch) {
-    const int grid = (h->L + 1) * ys, threads = nw * 32;
+// spc: time slices per CTA (1 except in the multi-slice variants)
+bool pipe_try(elph_handle* h, PipeParams& P, int variant, int nw, int ys, int spc, bool launch) {
+    const int nchunk = (h->L + spc - 1) / spc;
+    const int grid = (nchunk + 1) * ys, threads = nw * 32;
     const int Lx = (h->model == ELPH_MODEL_SSH) ? h->ssq.Lx : h->sq.Lx;
     auto go = [&](auto kern, size_t smem) {
         if (!launch) return pipe_fits(h, kern, grid, threads, ys, smem);
@@ -920,52 +1139,63 @@ bool pipe_try(elph_handle* h, PipeParams& P, int variant, int nw, int ys, bool l
     };
     const int nb = pipe_variant_py(variant) * nw * Lx;
     switch (variant) {
-#define V(id, nseg, py, maxt, minb, pl, ssh) \
-        case id: return threads <= maxt && go(cgpipe_kernel<nseg, py, maxt, minb, pl, ssh>, pipe_smem<nseg, py, maxt, minb, pl, ssh>(nb, nw));
+#define V(id, nseg, py, maxt, minb, pl, ssh, ms) \
+        case id: return threads <= maxt && go(cgpipe_kernel<nseg, py, maxt, minb, pl, ssh, ms>, pipe_smem<nseg, py, maxt, minb, pl, ssh>(nb, nw));
         PIPE_VARIANTS(V)
 #undef V
         default: return false;
     }
 }
 
-// candidate (variant, nw, ys) triples for this handle, best first
-int pipe_candidates(const elph_handle* h, int (&cand)[32][3]) {
+// candidate (variant, nw, ys, spc) tuples for this handle, best first
+int pipe_candidates(const elph_handle* h, int (&cand)[64][4]) {
     const bool ssh = (h->model == ELPH_MODEL_SSH);
     if (!(ssh ? h->ssq.enabled : h->sq.enabled) || h->sq_disable) return 0;
     const int Lx = ssh ? h->ssq.Lx : h->sq.Lx, Ly = ssh ? h->ssq.Ly : h->sq.Ly;
     int n = 0;
-    auto add = [&](int variant, int ys) {
+    auto add = [&](int variant, int ys, int spc = 1) {
         const int py = pipe_variant_py(variant);
         if (h->pipe_variant > 0 && variant != h->pipe_variant) return;    // tuning key 13
         if (ys > kMaxYS || Ly % (py * ys)) return;
         const int nw = Ly / (py * ys);
-        if (nw < 1 || nw > pipe_variant_maxw(variant) || (ys == 1 && nw < 2) || n >= 32) return;
-        cand[n][0] = variant; cand[n][1] = nw; cand[n][2] = ys; ++n;
+        if (nw < 1 || nw > pipe_variant_maxw(variant) || (ys == 1 && nw < 2) || n >= 64) return;
+        cand[n][0] = variant; cand[n][1] = nw; cand[n][2] = ys; cand[n][3] = spc; ++n;
     };
     // all placements for one way of cutting a slice, the one with most state in registers first
     auto add_ys = [&](int ys) {
         if (ssh) { if (Lx == 32 && !h->sharded && ys == 1) add(6, 1); return; }
         if (Lx == 32) { add(1, ys); add(7, ys); add(2, ys); }
-        // (variant 5 -- most of the state in L2 -- is slower than the launch-per-iteration path: 43 against 25 us per iteration
-        // at 64x64xL200; it stays selectable with tuning key 13 only)
+        // (variant 5 -- most of the state in L2, one slice per CTA -- is slower than the launch-per-iteration path: 43 against
+        // 25 us per iteration at 64x64xL200; it stays selectable with tuning key 13 only)
         else if (Lx == 64) { add(3, ys); add(8, ys); add(4, ys); add(9, ys); if (h->pipe_variant == 5) add(5, ys); }
     };
     if (h->pipe_ys > 0) add_ys(h->pipe_ys);    // tuning key 11 first; whatever does not fit falls through to the automatic order
     if (Lx == 32) for (int ys = 1; ys <= kMaxYS; ys *= 2) add_ys(ys);
     else { add_ys(4); add_ys(8); add_ys(2); add_ys(1); }
+    // slabs whose state does not fit on chip: several slices per CTA, vectors streamed from L2 / HBM (tuning key 14 = slices per
+    // CTA).  Measured at 64x64: 25 us per iteration for 200 slices, the same as the launch-per-iteration path of one GPU -- so it is
+    // chosen only where that path does not exist (a lattice sharded over several GPUs) or on request (tuning key 13).
+    const bool ms_ok = (h->sharded && h->p2p.world > 1) || h->pipe_variant == 10 || h->pipe_variant == 11;
+    if (!ssh && ms_ok) {
+        const int v = (Lx == 64) ? 10 : ((Lx == 32) ? 11 : 0), ys0 = (Lx == 64) ? 4 : 1;
+        if (v)
+            for (int spc = (h->pipe_spc > 0 ? h->pipe_spc : 2); spc <= (h->pipe_spc > 0 ? h->pipe_spc : 8); ++spc)
+                add(v, (h->pipe_ys > 0) ? h->pipe_ys : ys0, spc);
+    }
     return n;
 }
 
 bool pipe_select(elph_handle* h, PipeParams& P, PipeConfig& C, bool launch) {
-    int cand[32][3];
+    int cand[64][4];
     const int n = pipe_candidates(h, cand);
     for (int k = 0; k < n; ++k)
-        if (pipe_try(h, P, cand[k][0], cand[k][1], cand[k][2], false)) {
-            C.variant = cand[k][0]; C.nw = cand[k][1]; C.ys = cand[k][2];
+        if (pipe_try(h, P, cand[k][0], cand[k][1], cand[k][2], cand[k][3], false)) {
+            C.variant = cand[k][0]; C.nw = cand[k][1]; C.ys = cand[k][2]; C.spc = cand[k][3];
             if (!launch) return true;
             P.ys = C.ys;
+            P.spc = C.spc;
             P.maxcta = h->p2p.Lmax * kMaxYS;
-            return pipe_try(h, P, C.variant, C.nw, C.ys, true);
+            return pipe_try(h, P, C.variant, C.nw, C.ys, C.spc, true);
         }
     return false;
 }
@@ -1046,6 +1276,8 @@ bool elph_cg_pipe_run(elph_handle* h, const double* r0, double* x, bool x0_given
     P.abort_word = reinterpret_cast<unsigned int*>(at(A.arena, Y.abort_word));
     P.pg = reinterpret_cast<double*>(at(A.arena, Y.pg));
     P.ghost = reinterpret_cast<double*>(at(A.arena, Y.ghost));
+    P.state = reinterpret_cast<double*>(at(A.arena, Y.state));
+    P.spc = 1;
     P.S = h->d_cg;
     P.prof = h->pipe_prof ? h->pipe_prof_buf : nullptr;
     P.base = A.pipe_seq;
@@ -1076,5 +1308,6 @@ bool elph_cg_pipe_run(elph_handle* h, const double* r0, double* x, bool x0_given
     // puts the first reduction of the next solve (base' + 1) on the other parity than the last one of this solve.
     A.pipe_seq += 4u + (unsigned int)h->h_cg->iter;
     h->pipe_last_variant = C.variant * 100 + C.ys * 10 + C.nw;
+    h->pipe_last_spc = C.spc;
     return true;
 }

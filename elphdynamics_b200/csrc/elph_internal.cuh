@@ -282,6 +282,8 @@ struct elph_handle {
     unsigned int* h_hx_flag = nullptr;   // pinned: failure flag of the peer-memory halo exchange
     int cg_pipeline = -1;          // unpreconditioned CG on square lattices: pipelined persistent kernel (cg_pipe.cu); -1 = auto, 0 = off
     int pipe_ys = 0;               // tuning: CTAs per time slice of the pipelined kernel (0 = automatic)
+    int pipe_spc = 0;              // tuning key 14: time slices per CTA of the multi-slice variants (0 = smallest that fits)
+    int pipe_last_spc = 1;
     int pipe_variant = 0;          // tuning key 13: force one variant of the pipelined kernel (0 = automatic)
     bool pipe_prof = false;        // tuning key 12: per-phase cycle counters of the pipelined kernel (development aid)
     unsigned long long* pipe_prof_buf = nullptr;   // [8192][8]

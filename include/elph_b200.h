@@ -381,10 +381,12 @@ int32_t elph_set_chunk(elph_handle* h, int32_t slices_per_cta);
  * 10 = pipelined form of the persistent unpreconditioned CG (csrc/cg_pipe.cu: the all-reduce of an iteration overlaps the
  *      next product, a time slice may be split over several SMs; periodic square lattices; iteration counts within +-2 of
  *      the reference loop; -1 = auto (default: on unless key 7 forces one of the older forms), 0 = off, 1 = on),
- * 11 = CTAs per time slice of the pipelined kernel (0 = auto, else 1, 2, 4, 8) */
+ * 11 = CTAs per time slice of the pipelined kernel (0 = auto, else 1, 2, 4, 8),
+ * 12 = per-phase cycle counters of the pipelined kernel (development aid), 13 = force one variant of the pipelined kernel
+ *      (0 = auto), 14 = time slices per CTA of its multi-slice variants (0 = the smallest number that makes the slab co-resident) */
 int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value);
 /* read-back of a tuning key; key 100 = which kernel served the last unpreconditioned persistent solve: 0 = none yet /
- * other kernels, else variant * 100 + CTAs per slice * 10 + warps per CTA of the pipelined kernel */
+ * other kernels, else variant * 100 + CTAs per slice * 10 + warps per CTA of the pipelined kernel; key 101 = its time slices per CTA */
 int32_t elph_get_tuning(elph_handle* h, int32_t key, int32_t* value);
 /* which kernel family serves the fused M^T M product of this model, and the number of bond colours found */
 int32_t elph_get_kernel_info(elph_handle* h, int32_t* square_kernel, int32_t* ngroups);

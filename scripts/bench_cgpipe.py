@@ -21,7 +21,7 @@ torch.cuda.set_device(0)
 torch.cuda.set_stream(torch.cuda.Stream())
 quick = "quick" in sys.argv
 # (lattice side, beta): 64-wide slabs of 50 / 100 slices = the per-GPU share of config E on 8 / 4 GPUs
-cases = [(32, 20.0), ("C", 10.0), (64, 5.0), (64, 10.0), (64, 20.0)] if not quick else [(32, 20.0), (64, 5.0)]
+cases = [(32, 20.0), ("C", 10.0), (64, 5.0), (64, 10.0), (64, 20.0), (64, 40.0)] if not quick else [(64, 20.0), (64, 40.0)]
 for (Ls, beta) in cases:
     if Ls == "C":
         m, rng = workloads.config("C")          # SSH 32x32, Ltau = 200
@@ -34,6 +34,8 @@ for (Ls, beta) in cases:
     out = {"model": type(m).__name__, "lattice": f"{Ls}x{Ls}xL{m.Ltau}"}
     ref = None
     modes = [("two_reductions", 0, 0, 0, 0), ("single_reduction", 1, 0, 0, 0), ("pipelined", -1, 1, 0, 0)]
+    if Ls == 64 and m.Ltau >= 200:
+        modes += [(f"pipe_v10_spc{spc}", -1, 1, 4, 10 + 100 * spc) for spc in ((2, 3, 4) if m.Ltau == 200 else (3, 4, 5, 6))]
     if Ls == 32 and type(m).__name__ == "HolsteinModel":
         modes += [("pipe_v7", -1, 1, 1, 7), ("pipe_v1_ys2", -1, 1, 2, 1), ("pipe_v2_ys2", -1, 1, 2, 2), ("pipe_v7_ys2", -1, 1, 2, 7)]
     elif Ls == 64:
@@ -44,6 +46,8 @@ for (Ls, beta) in cases:
         lib.elph_set_tuning(m.handle, 7, key7)
         lib.elph_set_tuning(m.handle, 10, key10)
         lib.elph_set_tuning(m.handle, 11, ys)
+        lib.elph_set_tuning(m.handle, 14, variant // 100)
+        variant = variant % 100
         lib.elph_set_tuning(m.handle, 13, variant)
         it, ep = C.c_int64(), C.c_double()
         x = torch.zeros_like(b)
@@ -73,7 +77,9 @@ for (Ls, beta) in cases:
             continue
         if ref is None:
             ref = x.clone()
+        spc_ = C.c_int32()
+        lib.elph_get_tuning(m.handle, 101, C.byref(spc_))
         out[name] = {"iters": it.value, "true_residual": res, "us_per_iter": round(best / it.value * 1e6, 3),
-                     "variant": var.value, "rel_diff_x": float(torch.linalg.norm(x - ref) / torch.linalg.norm(ref))}
+                     "variant": var.value, "slices_per_cta": spc_.value, "rel_diff_x": float(torch.linalg.norm(x - ref) / torch.linalg.norm(ref))}
     print(json.dumps(out), flush=True)
     m.close()

@@ -123,3 +123,36 @@ def test_pipelined_cg_ssh_square():
         assert relerr(xe, xo) <= 1e-3
     finally:
         em.close()
+
+
+@pytest.mark.parametrize("Ls,beta,variant,spc", [(64, 0.6, 10, 2), (64, 0.6, 10, 4), (32, 0.8, 11, 3), (32, 0.8, 11, 8), (32, 2.0, 11, 2)])
+def test_multi_slice_variants(Ls, beta, variant, spc):
+    """Several consecutive time slices per CTA with the vectors in L2 (the slabs that are not co-resident otherwise:
+    64x64xL400 on one or two GPUs), ragged last chunk included; maxiter cut-off and initial guess as well."""
+    import elphdynamics_b200 as E
+    om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-1.0)
+    em = engine_holstein_like(om)
+    try:
+        b = rng.normal(size=om.Ndim)
+        x0 = 0.05 * rng.normal(size=om.Ndim)
+        it_o, eps_o, xo = _oracle_cg(om, b)
+        it_g, eps_g, xg = _oracle_cg(om, b, x0)
+        it_m, eps_m, xm = _oracle_cg(om, b, x0, maxiter=5)
+        em._call("elph_set_tuning", 10, 1)
+        em._call("elph_set_tuning", 13, variant)
+        em._call("elph_set_tuning", 14, spc)
+        xe = np.zeros(om.Ndim)
+        it_e = E.solve_(xe, em, b)
+        assert _variant(em) // 100 == variant, _variant(em)
+        got = C.c_int32()
+        em._call("elph_get_tuning", 101, C.byref(got))
+        assert got.value == spc
+        assert abs(it_e - it_o) <= 2 and em.last_eps < om.tol and relerr(xe, xo) <= 1e-3, (it_e, it_o, relerr(xe, xo))
+        xe = x0.copy()
+        it_e = E.solve_(xe, em, b)
+        assert abs(it_e - it_g) <= 2 and relerr(xe, xg) <= 1e-3, (it_e, it_g)
+        xe = x0.copy()
+        it_e = E.solve_(xe, em, b, maxiter=5)
+        assert it_e == 5 and abs(em.last_eps - eps_m) <= 1e-6 * eps_m and relerr(xe, xm) <= 1e-8
+    finally:
+        em.close()
