@@ -143,6 +143,7 @@ def load() -> C.CDLL:
         "elph_set_shard": (i32, [H, i64, i64]),
         "elph_dev_shard_matvec": (i32, [H, i32, C.c_void_p, C.c_void_p]),
         "elph_dev_shard_halo": (i32, [H, C.c_void_p]),
+        "elph_dev_shard_matvec_halo": (i32, [H, i32, C.c_void_p, C.c_void_p]),
         "elph_shard_cg_available": (i32, [H, C.POINTER(i32)]),
         "elph_dev_shard_muldMdx": (i32, [H, C.c_void_p, C.c_void_p, C.c_void_p, dbl]),
         "elph_dev_update_model": (i32, [H]),

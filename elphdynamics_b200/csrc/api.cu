@@ -1088,6 +1088,21 @@ int32_t elph_dev_shard_cg_p2p(elph_handle* h, const double* b_own, double* x_own
     ELPH_CATCH(h)
 }
 
+int32_t elph_dev_shard_matvec_halo(elph_handle* h, int32_t mode, double* v_own, double* y_own) {
+    ENTER(h) {
+        ELPH_REQUIRE(h->sharded, ELPH_ERR_STATE, "elph_set_shard has not been called");
+        ELPH_REQUIRE(mode >= 0 && mode <= 2 && v_own && y_own, ELPH_ERR_INVALID, "bad arguments");
+        elph_shard_halo_impl(h, v_own);
+        MatvecArgs a;
+        a.v = v_own;
+        a.y = y_own;
+        a.open = true;
+        elph_launch_matvec(h, (MatvecMode)mode, a);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
 int32_t elph_shard_cg_available(elph_handle* h, int32_t* available) {
     ENTER(h) {
         ELPH_REQUIRE(available, ELPH_ERR_INVALID, "null output");

@@ -623,7 +623,7 @@ void alloc_arena(elph_handle* h, int rank, int world, int Lglob) {
     A.hx_seq = 0;
     A.failed = false;
     A.pipe_failed = false;
-    if (!h->h_hx_flag) ELPH_CUDA(cudaMallocHost(&h->h_hx_flag, sizeof(unsigned int)));
+    if (!h->h_hx_flag) ELPH_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_hx_flag), sizeof(unsigned int), cudaHostAllocMapped));
     *h->h_hx_flag = 0u;
 }
 

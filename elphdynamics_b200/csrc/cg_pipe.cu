@@ -1235,15 +1235,15 @@ void elph_shard_halo_impl(elph_handle* h, double* v_own) {
     const PipeLayout Y = pipe_layout(h->N, A.Lmax);
     auto at = [&](void* base, size_t off) { return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + A.pipe_off + off); };
     const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
-    unsigned int* flag = reinterpret_cast<unsigned int*>(at(A.arena, Y.hx_flag));
-    if (A.hx_seq != 0) {     // outcome of the previous exchanges (lags by one call: nothing here waits for the device)
-        ELPH_REQUIRE(*h->h_hx_flag == 0u, ELPH_ERR_STATE, "halo exchange: a neighbour GPU did not deliver its slice in time (timeout)");
-    }
+    // the failure flag lives in mapped page-locked host memory: a timed-out kernel writes it directly, the host reads it at the
+    // next call -- no copy, nothing in the stream between the exchange and the product
+    unsigned int* flag = nullptr;
+    ELPH_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&flag), h->h_hx_flag, 0));
+    ELPH_REQUIRE(*h->h_hx_flag == 0u, ELPH_ERR_STATE, "halo exchange: a neighbour GPU did not deliver its slice in time (timeout)");
     const int threads = 256, blocks = std::min(h->sm_count, (h->N + threads - 1) / threads);
     halo_exchange_kernel<<<blocks, threads, 0, h->stream>>>(v_own, h->L, h->N, at(A.arena, Y.hx), at(A.peer[left], Y.hx), at(A.peer[right], Y.hx),
                                                             ++A.hx_seq, flag);
     ELPH_CUDA(cudaGetLastError());
-    ELPH_CUDA(cudaMemcpyAsync(h->h_hx_flag, flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     h->launches++;
 }
 

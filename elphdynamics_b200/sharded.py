@@ -125,6 +125,9 @@ class CudaSlabBackend:
     def matvec(self, mode, v, y):
         self._check(self.lib.elph_dev_shard_matvec(self.h, mode, self.own_ptr(v), self.own_ptr(y)))
 
+    def matvec_halo(self, mode, v, y):
+        self._check(self.lib.elph_dev_shard_matvec_halo(self.h, mode, self.own_ptr(v), self.own_ptr(y)))
+
     def muldMdx(self, u, v, out, scale=1.0):
         self._check(self.lib.elph_dev_shard_muldMdx(self.h, self.own_ptr(u), self.own_ptr(v), self.own_ptr(out), float(scale)))
 
@@ -241,6 +244,10 @@ class ShardedOperator:
         self.comm.exchange(self.be.D_tensor(), self.lloc, lo=False, hi=True)
 
     def _mul(self, mode, y, v):
+        if self.comm.peer_halo is not None and hasattr(self.be, "matvec_halo"):
+            self.halo_exchanges += 1
+            self.be.matvec_halo(mode, v, y)      # halo push through peer memory + product, one call
+            return
         need_lo = mode in (M_MODE, MTM_MODE)
         need_hi = mode in (MT_MODE, MTM_MODE)
         self.comm.exchange(v, self.lloc, lo=need_lo, hi=need_hi)

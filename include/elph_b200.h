@@ -340,6 +340,9 @@ int32_t elph_dev_shard_dSbdx(elph_handle* h, double* dSbdx_own, const double* x_
  * every product of the sharded lattice needs (mulM!: tau-1, src/HolsteinModels.jl:594-601; mulMT!: tau+1, :671-677).  One
  * kernel launch on the handle's stream, no host synchronisation; every rank of the ring must make the same call. */
 int32_t elph_dev_shard_halo(elph_handle* h, double* v_own);
+/* elph_dev_shard_halo on v followed by elph_dev_shard_matvec: one product of the sharded lattice (mode 0 = M, 1 = M^T, 2 = M^T M)
+ * with its halo exchange in ONE call (two launches, nothing returns to the host in between) */
+int32_t elph_dev_shard_matvec_halo(elph_handle* h, int32_t mode, double* v_own, double* y_own);
 /* fourier_accelerate! for `ncols` columns in [k][col] layout with an explicit diagonal (same layout): after the
  * all-to-all transpose of the tau-sharded driver a rank holds all Ltau slices of a subset of the sites.  The handle's
  * Ltau must be the GLOBAL time extent (the driver keeps a 1-site handle just for this plan). */

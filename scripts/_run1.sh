@@ -1,2 +1,6 @@
-timeout 600 python -m pytest tests/test_gpu_cgpipe.py -x -q 2>&1 | tail -15
-timeout 300 python scripts/bench_cgpipe.py quick > gpurun_out/cgpipe_bench.jsonl 2> gpurun_out/cgpipe_bench.err; tail -5 gpurun_out/cgpipe_bench.err; cat gpurun_out/cgpipe_bench.jsonl
+timeout 600 python -m pytest tests/test_sharded.py -m gpu -x -q 2>&1 | tail -4
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -3 gpurun_out/bench_1gpu.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_1gpu.json').read().strip().splitlines()[-1])
+print(json.dumps(d.get('tau_sharded'))[:1500])
+PY
