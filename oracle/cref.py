@@ -45,6 +45,8 @@ def load(native: bool = False) -> C.CDLL:
     lib.ref_mulMTM.argtypes = [dp, mp, dp, dp, dp]
     lib.ref_cg.argtypes = [dp, mp, dp, dp, C.c_double, C.c_int64, C.c_double, dp, dp]
     lib.ref_cg.restype = C.c_int64
+    lib.ref_cg_mt.argtypes = [dp, mp, dp, dp, C.c_double, C.c_int64, C.c_double, dp, dp, C.c_int]
+    lib.ref_cg_mt.restype = C.c_int64
     lib.ref_mulMTM_replicas.argtypes = [mp, C.c_int64, C.c_int64, dp, dp, dp, dp, C.c_int]
     lib.ref_mulMTM_replicas.restype = C.c_int
     return lib
@@ -81,6 +83,14 @@ class CRef:
         eps = C.c_double()
         it = self.lib.ref_cg(_p(x), C.byref(self.m), _p(self.expnV), _p(np.ascontiguousarray(b)), tol, maxiter, kappa_max,
                              _p(work), C.byref(eps))
+        return int(it), eps.value
+
+    def cg_mt(self, x, b, tol=1e-5, maxiter=10000, kappa_max=1e12, nthreads=0):
+        """The same recurrences with the loops of one product threaded along tau (full-size parity tests)."""
+        work = np.zeros(4 * self.n)
+        eps = C.c_double()
+        it = self.lib.ref_cg_mt(_p(x), C.byref(self.m), _p(self.expnV), _p(np.ascontiguousarray(b)), tol, maxiter, kappa_max,
+                                _p(work), C.byref(eps), nthreads)
         return int(it), eps.value
 
     def mulMTM_throughput(self, nrep: int, reps: int, nthreads: int = 0, seed: int = 0):

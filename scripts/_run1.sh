@@ -1,6 +1,1 @@
-timeout 600 python -m pytest tests/test_sharded.py -m gpu -x -q 2>&1 | tail -4
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -3 gpurun_out/bench_1gpu.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_1gpu.json').read().strip().splitlines()[-1])
-print(json.dumps(d.get('tau_sharded'))[:1500])
-PY
+timeout 1500 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_holstein.py -m gpu -x -q --durations=5 -k "not test_B_p and not test_E_p" 2>&1 | tail -25

@@ -258,3 +258,103 @@ def test_C_ssh_32x32_L200_products():
     E.muldMdx_(de, u, em, v)
     assert relerr(de, do) <= 1e-9
     em.close()
+
+
+# ---- iteration counts of the full-size solves against the reference recurrences (src/IterativeSolvers.jl:198-231) -------------
+# north_star: "CG solutions to the reference residual tolerance with iteration counts within +-2".  The persistent kernels do
+# not run the reference's two-reduction loop literally (cg_p2p.cu: Chronopoulos-Gear, cg_pipe.cu: pipelined), so every form is
+# compared with the literal loop at the sizes where rounding has the most room: ~800 (C), ~2000 (E, rough 32x32) iterations.
+
+def _kernel_forms(em):
+    """(label, tuning (key, value) pairs) of the forms of the unpreconditioned solve that apply to this handle."""
+    return [("pipelined", ((10, 1), (7, -1))), ("single-reduction", ((10, 0), (7, 1))), ("two-reduction", ((10, 0), (7, 0))),
+            ("graph replay", ((10, 0), (7, 0), (5, 0))), ("plain launches", ((10, 0), (7, 0), (5, 0), (3, 0)))]
+
+
+def _reset_tuning(em):
+    for key, val in ((10, -1), (7, -1), (5, 1), (3, 1), (13, 0), (14, 0), (11, 0)):
+        em._call("elph_set_tuning", key, val)
+
+
+def _check_forms(em, om, b, it_ref, x_ref, forms=None):
+    import elphdynamics_b200 as E
+    counts = {}
+    for label, keys in (forms or _kernel_forms(em)):
+        _reset_tuning(em)
+        for key, val in keys:
+            em._call("elph_set_tuning", key, val)
+        xe = np.zeros(om.Ndim)
+        it_e = E.solve_(xe, em, b)
+        counts[label] = it_e
+        assert abs(it_e - it_ref) <= 2, (label, it_e, it_ref, counts)
+        assert em.last_eps < om.tol and relerr(xe, x_ref) <= 1e-3, (label, em.last_eps, relerr(xe, x_ref))
+    _reset_tuning(em)
+    return counts
+
+
+def test_E_cg_iterations_64x64_L400():
+    """Config E, ~2000 iterations: the literal loop (C restatement, threaded along tau) against the engine's launch-per-iteration
+    forms (what one GPU runs at this size) and the multi-slice pipelined kernel (what two GPUs run on their slabs)."""
+    from oracle.cref import CRef
+    om, rng = oracle_holstein("square", 64, 40.0, 0.1, mu=-1.0, seed=5, eps=0.3)
+    em = engine_holstein_like(om)
+    try:
+        b = rng.normal(size=om.Ndim)
+        xc = np.zeros(om.Ndim)
+        it_c, eps_c = CRef(om).cg_mt(xc, b, tol=om.tol, maxiter=om.maxiter)
+        assert it_c > 1500
+        forms = [("graph replay", ((10, 0), (7, 0))), ("plain launches", ((10, 0), (7, 0), (3, 0))),
+                 ("pipelined, 6 slices per CTA", ((10, 1), (13, 10)))]
+        _check_forms(em, om, b, it_c, xc, forms)
+    finally:
+        em.close()
+
+
+def test_B_long_solve_all_forms():
+    """32x32xL280 (the longest slab whose slices are all co-resident) with a rough field (eps = 1): a long solve through all five
+    forms, the single-reduction and pipelined recurrences included."""
+    from oracle.cref import CRef
+    om, rng = oracle_holstein("square", 32, 28.0, 0.1, mu=-1.0, seed=1234, eps=1.0)
+    em = engine_holstein_like(om)
+    try:
+        b = rng.normal(size=om.Ndim)
+        xc = np.zeros(om.Ndim)
+        it_c, eps_c = CRef(om).cg(xc, b, tol=om.tol, maxiter=om.maxiter)
+        assert it_c > 1000, it_c
+        counts = _check_forms(em, om, b, it_c, xc)
+        print("iterations: reference", it_c, counts)
+    finally:
+        em.close()
+
+
+def test_C_cg_iterations_ssh_32x32_L200():
+    """Config C (SSH, ~800 iterations): NumPy restatement of the literal loop against the engine's forms."""
+    from helpers_ssh import engine_ssh_like, oracle_ssh
+    from oracle.solvers import ConjugateGradient, solve_cg
+    om, rng = oracle_ssh(Lside=32, beta=10.0, dtau=0.05, seed=11)
+    em = engine_ssh_like(om)
+    try:
+        b = rng.normal(size=om.Ndim)
+        xo = np.zeros(om.Ndim)
+        it_o = solve_cg(xo, om, b, ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter))
+        assert it_o > 500, it_o
+        _check_forms(em, om, b, it_o, xo)
+    finally:
+        em.close()
+
+
+@pytest.mark.parametrize("geom,Ls,dtau", [("honeycomb", 32, 0.1), ("triangular", 45, 0.05)], ids=["honeycomb32", "triangular45"])
+def test_D_cg_iterations(geom, Ls, dtau):
+    """Config D (HMC lattices at ~2k sites): the generic persistent kernels in both forms and the launch-per-iteration forms."""
+    from oracle.cref import CRef
+    om, rng = oracle_holstein(geom, Ls, 2.0, dtau, mu=0.0, seed=3, eps=0.3)
+    em = engine_holstein_like(om)
+    try:
+        b = rng.normal(size=om.Ndim)
+        xc = np.zeros(om.Ndim)
+        it_c, eps_c = CRef(om).cg(xc, b, tol=om.tol, maxiter=om.maxiter)
+        forms = [("single-reduction", ((7, 1),)), ("two-reduction", ((7, 0),)), ("graph replay", ((7, 0), (5, 0))),
+                 ("plain launches", ((7, 0), (5, 0), (3, 0)))]
+        _check_forms(em, om, b, it_c, xc, forms)
+    finally:
+        em.close()

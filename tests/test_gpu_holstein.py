@@ -276,8 +276,10 @@ def test_force_and_langevin(pair):
     from oracle.solvers import ConjugateGradient
     om, em, rng = pair
     x0 = om.x.copy()
-    cg = ConjugateGradient(om.Ndim, tol=1e-10, maxiter=om.maxiter)   # tight solve so the force is comparable at 1e-9
-    em._call("elph_set_solver", 1e-10, 0, 0.0)
+    # the force dS/dx = -2 g^T dM/dx M^-1 g inherits the error of the solve (two different Krylov roundings): both sides solve to
+    # 1e-12 so that the comparison is one of the force arithmetic at north_star's 1e-9, not of the solver tolerance
+    cg = ConjugateGradient(om.Ndim, tol=1e-12, maxiter=om.maxiter)
+    em._call("elph_set_solver", 1e-12, 0, 0.0)
     fo = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
     fo.update_Q(0.0, 10.0, 1.0)
     fe = E.FourierAccelerator(em)
@@ -291,8 +293,15 @@ def test_force_and_langevin(pair):
     me = np.zeros(om.Ndim)
     it_e = E.calc_dSdx_(de, g, me, em)
     assert abs(it_e - it_o) <= 2
-    assert relerr(me, mo) <= 1e-8
-    assert relerr(de, do) <= 1e-8
+    assert relerr(me, mo) <= FORCE_TOL
+    assert relerr(de, do) <= FORCE_TOL
+    # and the force kernel alone on identical inputs (the oracle's M^-1 g)
+    dk_o, dk_e = np.zeros(om.Ndof), np.zeros(om.Ndof)
+    om.muldMdx(dk_o, g, mo)
+    E.muldMdx_(dk_e, g, em, mo)
+    assert relerr(dk_e, dk_o) <= FORCE_TOL
+    cg = ConjugateGradient(om.Ndim, tol=1e-10, maxiter=om.maxiter)
+    em._call("elph_set_solver", 1e-10, 0, 0.0)
     # one step of each update method with identical injected noise, KPM-preconditioned
     for name, dyn_cls, oracle_step in (("euler", E.EulerDynamics, olang.evolve_euler),
                                        ("rk", E.RungeKuttaDynamics, olang.evolve_rk),
