@@ -179,8 +179,22 @@ def ptr(a: np.ndarray | None, dtype=np.float64):
     """Pointer to a C-contiguous numpy array of the given dtype (None -> NULL)."""
     if a is None:
         return None
-    assert a.dtype == dtype and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
+    if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"]):
+        raise TypeError(f"expected a C-contiguous numpy array of dtype {np.dtype(dtype).name}, got "
+                        f"{type(a).__name__}" + (f" of dtype {a.dtype}" if isinstance(a, np.ndarray) else ""))
     return a.ctypes.data_as(C.POINTER(C.c_double if dtype == np.float64 else C.c_int64))
+
+
+def out_ptr(a: np.ndarray, n: int, name: str = "output", dtype=np.float64):
+    """Pointer to an OUTPUT array the library will write ``n`` entries into: the size is checked here because the C side
+    cannot see it (a short buffer would be overrun silently)."""
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{name}: expected a numpy array, got {type(a).__name__}")
+    if a.size != n:
+        raise ValueError(f"{name}: expected {n} entries, got {a.size}")
+    if not a.flags["WRITEABLE"]:
+        raise ValueError(f"{name}: array is read-only")
+    return ptr(a, dtype)
 
 
 def check(status: int, handle=None):

@@ -12,9 +12,10 @@ namespace {
 
 constexpr int kT = 256;
 
-// out = a*X + b*Y + c*Z   (Y, Z optional)
-__global__ void lincomb_kernel(double* __restrict__ out, double a, const double* __restrict__ X, double b,
-                               const double* __restrict__ Y, double c, const double* __restrict__ Z, long long n) {
+// out = a*X + b*Y + c*Z   (Y, Z optional).  out may alias an input (x = x + dx, v = v - dt/2 Q, ...): no __restrict__, every
+// thread reads its own index before it writes it.
+__global__ void lincomb_kernel(double* out, double a, const double* X, double b, const double* Y, double c, const double* Z,
+                               long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double r = a * X[i];
         if (Y) r += b * Y[i];

@@ -200,8 +200,9 @@ __device__ __forceinline__ bool fft_last_block_sum(double acc, const CgFuse& F, 
 }
 
 template <int SB>
-__global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* __restrict__ rin, const cplx* __restrict__ cin,
-                                                 double* __restrict__ rout, cplx* __restrict__ cout, FftPlan plan, int N,
+// rin / rout and cin / cout may alias (fourier_accelerate!(eta, fa, eta, ...) works in place: a column is read completely into
+// shared memory before it is written back): no __restrict__ on them.
+__global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* rin, const cplx* cin, double* rout, cplx* cout, FftPlan plan, int N,
                                                  const cplx* __restrict__ tw_g, const cplx* __restrict__ theta,
                                                  const double* __restrict__ diag, double power, const int* skip, CgFuse F) {
     extern __shared__ __align__(16) double smem_raw[];

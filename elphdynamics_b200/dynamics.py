@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from ._lib import SolveInfo, ptr
+from ._lib import SolveInfo, out_ptr, ptr
 from .models import AbstractModel, _f64
 
 EULER, RUNGE_KUTTA, HEUN = 1, 2, 3
@@ -29,14 +29,17 @@ class TimeFreqFFT:
 
 def tau_to_omega_(vout, op: TimeFreqFFT, vin):
     """``τ_to_ω!(vout::complex, op, vin::real)`` (src/TimeFreqFFTs.jl:55-73)."""
-    assert vout.dtype == np.complex128 and vout.flags["C_CONTIGUOUS"]
+    if not (isinstance(vout, np.ndarray) and vout.dtype == np.complex128 and vout.flags["C_CONTIGUOUS"] and vout.size == op.model.Ndim):
+        raise ValueError(f"vout: expected a C-contiguous complex128 array of {op.model.Ndim} entries")
     op.model._call("elph_tau_to_omega", ptr(_f64(vin, op.model.Ndim, "vin")), vout.ctypes.data_as(C.POINTER(C.c_double)))
 
 
 def omega_to_tau_(vout, op: TimeFreqFFT, vin):
     """``ω_to_τ!(vout::real, op, vin::complex)`` (src/TimeFreqFFTs.jl:112-130)."""
     vin = np.ascontiguousarray(vin, dtype=np.complex128)
-    op.model._call("elph_omega_to_tau", vin.ctypes.data_as(C.POINTER(C.c_double)), ptr(vout))
+    if vin.size != op.model.Ndim:
+        raise ValueError(f"vin: expected {op.model.Ndim} entries, got {vin.size}")
+    op.model._call("elph_omega_to_tau", vin.ctypes.data_as(C.POINTER(C.c_double)), out_ptr(vout, op.model.Ndim, "vout"))
 
 
 # ------------------------------------------------------------------------------ FourierAcceleration
@@ -86,7 +89,7 @@ def update_M_(fa: FourierAccelerator, model, omega_min, omega_max, m0, c=0.0):
 
 def fourier_accelerate_(vout, fa: FourierAccelerator, v, power: float, use_mass: bool = False):
     """``fourier_accelerate!(v', fa, v, power; use_mass)`` real -> real (src/FourierAcceleration.jl:131-137)."""
-    fa.model._call("elph_fourier_accelerate", ptr(_f64(v, fa.N * fa.L, "v")), ptr(vout), float(power), 1 if use_mass else 0)
+    fa.model._call("elph_fourier_accelerate", ptr(_f64(v, fa.N * fa.L, "v")), out_ptr(vout, fa.N * fa.L, "vout"), float(power), 1 if use_mass else 0)
 
 
 # ------------------------------------------------------------------------------ PhononAction
@@ -99,7 +102,7 @@ def calc_Sb(model, shifted: bool = False) -> float:
 
 def calc_dSbdx_(dSbdx, model, shifted: bool = False):
     """``calc_dSbdx!(dSbdx, model, shifted)`` -- accumulates (src/PhononAction.jl:114-233)."""
-    model._call("elph_dSbdx", 1 if shifted else 0, ptr(dSbdx))
+    model._call("elph_dSbdx", 1 if shifted else 0, out_ptr(dSbdx, model.Ndof, "dSbdx"))
 
 
 # ------------------------------------------------------------------------------ LangevinDynamics
@@ -136,8 +139,8 @@ def calc_dSdx_(dSdx, g, Minv_g, model, P=None, arnoldi_noise=None):
     Returns the iteration count."""
     info = SolveInfo()
     an = None if arnoldi_noise is None else ptr(_f64(arnoldi_noise, 2 * model.Nsites, "arnoldi_noise"))
-    model._call("elph_calc_dSdx", ptr(_f64(g, model.Ndim, "g")), an, _use_p(P), ptr(dSdx),
-                None if Minv_g is None else ptr(Minv_g), C.byref(info))
+    model._call("elph_calc_dSdx", ptr(_f64(g, model.Ndim, "g")), an, _use_p(P), out_ptr(dSdx, model.Ndof, "dSdx"),
+                None if Minv_g is None else out_ptr(Minv_g, model.Ndim, "Minv_g"), C.byref(info))
     model.last_solve_info = info
     return int(info.iters)
 

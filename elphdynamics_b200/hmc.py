@@ -99,18 +99,24 @@ class ReflectionUpdate:
 
     def __init__(self, model, freq: int, nsites: int):
         from .models import HolsteinModel
-        self.active = isinstance(model, HolsteinModel) and nsites > 0
+        self.active = isinstance(model, HolsteinModel)        # :79-84 always on for Holstein, :86-90 off for every other model
         self.freq = int(freq)
-        self.nsites = min(int(nsites), model.Nph) if self.active else 0
+        self.nsites = min(model.Nph, int(nsites)) if self.active else 0
 
 
 class SwapUpdate:
     """``SwapUpdate(model, freq, nbonds)`` (src/SpecialUpdates.jl:169-226)."""
 
     def __init__(self, model, freq: int, nbonds: int):
-        self.active = not ((model.Nbonds == 0 or model.Nph == 0) and nbonds > 0)
+        from .models import HolsteinModel, SSHModel
+        if isinstance(model, HolsteinModel):                  # :193-206
+            self.active = not (model.Nbonds == 0 and nbonds > 0)
+        elif isinstance(model, SSHModel):                     # :208-222
+            self.active = not (model.Nph == 0 and nbonds > 0)
+        else:                                                 # :224-229
+            self.active = False
         self.freq = int(freq)
-        self.nbonds = min(model.Nbonds, int(nbonds))
+        self.nbonds = min(model.Nbonds, int(nbonds)) if isinstance(model, (HolsteinModel, SSHModel)) else 0
 
 
 def special_update_(model, hmc: HybridMonteCarlo, upd, P=None, *, targets, R_plus, R_minus, uniforms, arnoldi_noises=None):
@@ -124,7 +130,9 @@ def special_update_(model, hmc: HybridMonteCarlo, upd, P=None, *, targets, R_plu
     reflect = isinstance(upd, ReflectionUpdate)
     if not upd.active or (reflect and not isinstance(model, HolsteinModel)):
         return 0.0
-    n = len(targets)
+    n = upd.nsites if reflect else upd.nbonds      # the reference's bookkeeping: accepted / ru.nsites, accepted / su.nbonds
+    if len(targets) != n:
+        raise ValueError(f"special_update_: {len(targets)} targets for an update configured for {n}")
     accepted = 0.0
     for k, tgt in enumerate(targets):
         i, j = (int(tgt), 0) if reflect else (int(tgt[0]), int(tgt[1]))

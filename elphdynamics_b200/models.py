@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Config, KpmInfo, SolveInfo, check, ptr
+from ._lib import Config, KpmInfo, SolveInfo, check, ptr, out_ptr
 from .lattices import Lattice, assemble_checkerboard, calc_neighbor_table
 
 HOLSTEIN, SSH = 0, 1
@@ -162,6 +162,10 @@ class HolsteinModel(AbstractModel):
     # assign_* (src/HolsteinModels.jl:324-444).  Disorder (stddev) draws come from the caller's RNG
     # in the reference; here a per-site/per-bond array may be passed instead of a scalar.
     def _assign(self, arr, value, orbit):
+        if getattr(self, "_h", None):
+            # the engine copied the parameters at initialize_model_: changing the host copy would silently be ignored
+            raise RuntimeError("assign_* after initialize_model_ does not reach the device: use set_mu (the chemical potential is "
+                               "the only parameter the reference changes during a run, src/MuFinder.jl) or build a new model")
         v = np.asarray(value, dtype=np.float64)
         if orbit is None:
             arr[:] = v
@@ -233,9 +237,7 @@ def update_model_(model: AbstractModel):
 
 def _vec_io(model, name, *vectors_in, out, n_out=None):
     ins = [_f64(v, None) for v in vectors_in]
-    if not (out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]):
-        raise ValueError("output must be a C-contiguous float64 array")
-    model._call(name, *[ptr(v) for v in ins], ptr(out))
+    model._call(name, *[ptr(v) for v in ins], out_ptr(out, model.Ndim if n_out is None else n_out, "output"))
 
 
 def mulM_(y, model, v):
@@ -265,7 +267,7 @@ def mul_(y, model, v):
 
 def muldMdx_(dMdx, u, model, v):
     """``muldMdx!(dMdx, u, model, v)`` (src/HolsteinModels.jl:691, src/SSHModels.jl:707)."""
-    model._call("elph_muldMdx", ptr(_f64(u, model.Ndim, "u")), ptr(_f64(v, model.Ndim, "v")), ptr(dMdx))
+    model._call("elph_muldMdx", ptr(_f64(u, model.Ndim, "u")), ptr(_f64(v, model.Ndim, "v")), out_ptr(dMdx, model.Ndof, "dMdx"))
 
 
 def ldiv_(x, model, b, P=None, tol_power: float = 1.0):
@@ -273,7 +275,7 @@ def ldiv_(x, model, b, P=None, tol_power: float = 1.0):
     ``x`` holds the initial guess on entry (callers zero it) and the solution on exit."""
     info = SolveInfo()
     use_p = 0 if (P is None or getattr(P, "is_identity", False)) else 1
-    model._call("elph_solve", ptr(_f64(b, model.Ndim, "b")), ptr(x), use_p, float(tol_power), C.byref(info))
+    model._call("elph_solve", ptr(_f64(b, model.Ndim, "b")), out_ptr(x, model.Ndim, "x"), use_p, float(tol_power), C.byref(info))
     model.last_solve_info = info
     return info.astuple()
 
@@ -314,7 +316,8 @@ def solve_(x, model, b, P=None, tol: float = 0.0, maxiter: int = 0):
     it = C.c_int64()
     eps = C.c_double()
     use_p = 0 if (P is None or getattr(P, "is_identity", False)) else 1
-    model._call("elph_cg_solve", ptr(_f64(b, model.Ndim, "b")), ptr(x), use_p, float(tol), int(maxiter), C.byref(it), C.byref(eps))
+    model._call("elph_cg_solve", ptr(_f64(b, model.Ndim, "b")), out_ptr(x, model.Ndim, "x"), use_p, float(tol), int(maxiter),
+                C.byref(it), C.byref(eps))
     model.last_eps = eps.value
     return int(it.value)
 
@@ -368,7 +371,7 @@ def kpm_ldiv_(vout, P, vin):
     if getattr(P, "is_identity", False):
         vout[:] = vin
         return
-    P.model._call("elph_kpm_apply", ptr(_f64(vin, P.model.Ndim, "vin")), ptr(vout))
+    P.model._call("elph_kpm_apply", ptr(_f64(vin, P.model.Ndim, "vin")), out_ptr(vout, P.model.Ndim, "vout"))
 
 
 class SSHModel(AbstractModel):
@@ -391,6 +394,8 @@ class SSHModel(AbstractModel):
 
     def assign_mu(self, value, orbit=None):
         """``assign_μ!`` (src/SSHModels.jl:332-343)."""
+        if getattr(self, "_h", None):
+            raise RuntimeError("assign_mu after initialize_model_ does not reach the device: use set_mu")
         v = np.asarray(value, dtype=np.float64)
         sel = slice(None) if orbit is None else (self.lattice.site_to_orbit == orbit)
         self.mu[sel] = v if v.ndim == 0 else v[sel]

@@ -282,6 +282,24 @@ class ShardedOperator:
         x.zero_()
         return self.solve_cg(x, b, tol, maxiter)
 
+    def ldiv(self, x, b, tol: float = 0.0):
+        """``ldiv!(x, model, b)`` without a preconditioner (src/Models.jl:141-186) on the sharded lattice: solve from x0 = 0,
+        then the TRUE relative residual |b - A x| / |b| with one more product.  When it exceeds sqrt(tol): ``flag`` 1 if the solve
+        ran into maxiter, 2 if the solver reported a convergence that the true residual does not confirm -- and ``x`` is zeroed in
+        both cases, as the reference does, so that a failed solve never feeds the force.  Returns ``(iters, residual, flag)``."""
+        tol = tol or self.tol
+        iters, _ = self.solve(x, b, tol)
+        res = self.be.empty()
+        self.mulMTM(res, x)
+        self.be.lincomb(res, 1.0, b, -1.0, res)
+        num, den = self.gdot(res, res), self.gdot(b, b)
+        residual = math.sqrt(num) / math.sqrt(den) if den > 0 else float("nan")
+        flag = 0
+        if residual > math.sqrt(tol):
+            flag = 1 if iters == self.maxiter else 2
+            x.zero_()
+        return iters, residual, flag
+
     def solve_cg(self, x, b, tol: float = 0.0, maxiter: int = 0):
         """Plain CG, src/IterativeSolvers.jl:239-314, with the reference stop rule.  Returns (iters, eps)."""
         be = self.be
@@ -334,7 +352,7 @@ class ShardedLangevin:
         self.s0, self.nloc = self.site_spans[r]
         self.Q = Q_site_block
         self.xh = self.be.empty()                      # halo'd master copy of the phonon field slab
-        self.last_iters = 0
+        self.last_iters, self.last_residual, self.last_flag = 0, 0.0, 0
 
     # ---- Fourier acceleration through the all-to-all transposes ---------------------------------------------------
     def fourier_accelerate(self, v, power):
@@ -374,7 +392,7 @@ class ShardedLangevin:
         be, op = self.be, self.op
         b, x, dS = be.empty(), be.empty(), be.empty()
         op.mulMT(b, g)
-        iters, eps = op.solve(x, b)
+        iters, self.last_residual, self.last_flag = op.ldiv(x, b)
         self.last_iters = iters
         self.comm.exchange(x, self.lloc, lo=True, hi=False)     # the force needs (M^-1 g)(tau-1)
         be.muldMdx(g, x, dS, -2.0)

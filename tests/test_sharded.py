@@ -155,6 +155,16 @@ def _check_rank(op, be, comm_rank, tau0, lloc, V, outs, om, b_glob, x_ref, it_re
     x2.fill_(7.0)
     it2, eps2 = op.solve(x2, b)
     assert it2 == it and relerr(x2[1:lloc + 1].cpu().numpy(), x[1:lloc + 1].cpu().numpy()) <= 1e-12
+    # ldiv!: the solve + true-residual check + flags of src/Models.jl:141-186 (what the sharded force evaluation calls)
+    x3 = be.empty()
+    it3, res3, flag3 = op.ldiv(x3, b)
+    assert it3 == it and flag3 == 0 and res3 <= 2e-5
+    assert relerr(x3[1:lloc + 1].cpu().numpy(), x[1:lloc + 1].cpu().numpy()) <= 1e-12
+    keep = op.maxiter
+    op.maxiter = 3                                   # cut off: residual > sqrt(tol), flag 1, x zeroed on every rank
+    it4, res4, flag4 = op.ldiv(x3, b)
+    op.maxiter = keep
+    assert it4 == 3 and flag4 == 1 and res4 > 1e-5 ** 0.5 and float(x3[1:lloc + 1].abs().max()) == 0.0
 
 
 def _problem(seed=7, Ls=4, beta=1.1):
