@@ -129,27 +129,17 @@ def cpu_baseline(target_seconds=12.0, nthreads=0):
 
 
 def cpu_langevin_baseline(nsteps=2):
-    """The second headline quantity on the host: Langevin Runge-Kutta steps/s of the NumPy restatement at config B with the
-    shipped solver settings (KPM-preconditioned CG) -- one thread, like the reference (src/ElPhDynamics.jl:74-75).  A port:
-    the sweeps are NumPy-vectorised over tau; Julia's compiled loops would be faster by a small factor."""
-    from oracle import langevin as olang
-    from oracle.fourier import FourierAccelerator
-    from oracle.kpm import KPMPreconditioner
-    from oracle.solvers import ConjugateGradient
-    om = oracle_model()
-    rng = np.random.default_rng(4321)
-    cg = ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter)
-    fo = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
-    fo.update_Q(0.0, 10.0, 1.0)
-    Po = KPMPreconditioner(om)
-    its = []
-    t0 = time.perf_counter()
-    for _ in range(nsteps):
-        its.append(int(olang.evolve_rk(om, cg, fo, Po, 1e-3, rng.normal(size=om.Ndof), rng.normal(size=om.Ndim),
-                                       rng.normal(size=om.Ndim), rng.normal(size=2 * om.N), rng.normal(size=2 * om.N))))
-    dt = time.perf_counter() - t0
-    return {"steps_per_s": nsteps / dt, "cores": 1, "kind": "port (NumPy restatement)", "pcg_iters_second_solve": its,
-            "sample": f"{nsteps} Runge-Kutta steps of 32x32xL200 with KPM-preconditioned CG, fresh injected noise per step"}
+    """The second headline quantity on the host: Langevin Runge-Kutta steps/s at config B with the shipped solver settings
+    (KPM-preconditioned CG).  oracle/cfast.py: the reference's loops restated in C (products, force, tau-averaged operator,
+    Chebyshev recurrences), the FFTs through pocketfft and the 20 x 20 eigenvalue problem through LAPACK, as the reference
+    hands them to FFTW and LAPACK.  One chain on one thread (the reference's own setting, src/ElPhDynamics.jl:74-75) and one
+    chain per core (its own scale-out).  Runs in a child process so that the BLAS / OpenMP pools are pinned to one thread."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "oracle.cfast", "--steps", str(nsteps)], cwd=str(ROOT), env=env, capture_output=True,
+                       text=True, timeout=600)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-300:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
 
 
 def run_reference(args):
@@ -178,6 +168,10 @@ def run_reference(args):
             "config": {"workload": "holstein_square_32x32_L200", "replicas_per_step": nrep, "products_per_replica": reps},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:        # the second headline quantity of the same reference arm: Langevin steps/s on the host
+        line["langevin_rk_kpm"] = cpu_langevin_baseline()
+    except Exception as exc:
+        line["langevin_rk_kpm"] = {"error": str(exc)[:200]}
     print(json.dumps(line), flush=True)
 
 

@@ -231,6 +231,155 @@ int64_t ref_cg_mt(double* x, const ref_model* m, const double* expnV, const doub
     return maxiter;
 }
 
+/* ---- the second headline quantity on the host: the loops of a KPM-preconditioned Langevin step ----------------------------
+ *   muldMdx!                         src/HolsteinModels.jl:691-755
+ *   A v, A^T v, A^-1 v (tau-averaged B)  src/KPMPreconditioners.jl:387-420, 758-778
+ *   mul!(::SymmetricKPMPreconditioner) frequency blocks, three-term Chebyshev recurrences  :606-693
+ * The FFTs (FFTW in the reference), the <= 20 x 20 eigenvalue problem (LAPACK) and the coefficient DCT stay with NumPy /
+ * SciPy in oracle/cfast.py, as the reference delegates them to libraries too. */
+void ref_muldMdx(double* dMdx, const ref_model* m, const double* expnV, const double* x, const double* lam, const double* lam2,
+                 double dtau, const double* u, const double* v, double* scratch) {
+    const int64_t N = m->N, L = m->L;
+    memcpy(scratch, u, (size_t)(N * L) * sizeof(double));
+    checkerboard_transpose_mul(scratch, m);
+    for (int64_t i = 0; i < N; ++i) {
+        const double l1 = lam[i], l2 = lam2[i];
+        dMdx[i * L] = scratch[i * L] * (-dtau * (l1 + 2 * l2 * x[i * L]) * expnV[i * L] * v[i * L + L - 1]);
+        for (int64_t t = 1; t < L; ++t)
+            dMdx[i * L + t] = scratch[i * L + t] * (dtau * (l1 + 2 * l2 * x[i * L + t]) * expnV[i * L + t] * v[i * L + t - 1]);
+    }
+}
+
+/* one N-vector (real): y = cb(cbar, sbar) y in bond order / reverse order with +-s */
+static void cb_vec(double* y, const ref_model* m, const double* cbar, const double* sbar, int reverse, double sign) {
+    for (int64_t k = 0; k < m->Nb; ++k) {
+        const int64_t n = reverse ? m->Nb - 1 - k : k;
+        const double c = cbar[n], s = sign * sbar[n];
+        const int64_t i = m->nt[2 * n], j = m->nt[2 * n + 1];
+        const double a = y[i], b = y[j];
+        y[i] = c * a + s * b;
+        y[j] = c * b + s * a;
+    }
+}
+/* mode 0: out = A v = cb diag(eVbar) v; 1: out = A^T v = diag(eVbar) cb^T v; 2: out = A^-1 v = (cb^-1 v) ./ eVbar */
+void ref_mulA(double* out, const ref_model* m, const double* eVbar, const double* cbar, const double* sbar, const double* v, int mode) {
+    const int64_t N = m->N;
+    if (mode == 0) {
+        for (int64_t i = 0; i < N; ++i) out[i] = eVbar[i] * v[i];
+        cb_vec(out, m, cbar, sbar, 0, 1.0);
+    } else if (mode == 1) {
+        memcpy(out, v, (size_t)N * sizeof(double));
+        cb_vec(out, m, cbar, sbar, 1, 1.0);
+        for (int64_t i = 0; i < N; ++i) out[i] *= eVbar[i];
+    } else {
+        memcpy(out, v, (size_t)N * sizeof(double));
+        cb_vec(out, m, cbar, sbar, 1, -1.0);
+        for (int64_t i = 0; i < N; ++i) out[i] /= eVbar[i];
+    }
+}
+
+/* complex N-vector as interleaved (re, im): A' v = (A v) / lam_mag - (lam_avg / lam_mag) v, A real */
+static void mulAprime_c(double* out, const double* v, const ref_model* m, const double* eVbar, const double* cbar, const double* sbar,
+                        double lam_avg, double lam_mag, int transposed) {
+    const int64_t N = m->N;
+    if (!transposed)
+        for (int64_t i = 0; i < N; ++i) { out[2 * i] = eVbar[i] * v[2 * i]; out[2 * i + 1] = eVbar[i] * v[2 * i + 1]; }
+    else
+        memcpy(out, v, (size_t)(2 * N) * sizeof(double));
+    for (int64_t k = 0; k < m->Nb; ++k) {
+        const int64_t n = transposed ? m->Nb - 1 - k : k;
+        const double c = cbar[n], s = sbar[n];
+        const int64_t i = m->nt[2 * n], j = m->nt[2 * n + 1];
+        const double ar = out[2 * i], ai = out[2 * i + 1], br = out[2 * j], bi = out[2 * j + 1];
+        out[2 * i] = c * ar + s * br;
+        out[2 * i + 1] = c * ai + s * bi;
+        out[2 * j] = c * br + s * ar;
+        out[2 * j + 1] = c * bi + s * ai;
+    }
+    const double a = 1.0 / lam_mag, b = lam_avg / lam_mag;
+    if (transposed)
+        for (int64_t i = 0; i < N; ++i) {
+            out[2 * i] = a * (eVbar[i] * out[2 * i]) - b * v[2 * i];
+            out[2 * i + 1] = a * (eVbar[i] * out[2 * i + 1]) - b * v[2 * i + 1];
+        }
+    else
+        for (int64_t i = 0; i < N; ++i) {
+            out[2 * i] = a * out[2 * i] - b * v[2 * i];
+            out[2 * i + 1] = a * out[2 * i + 1] - b * v[2 * i + 1];
+        }
+}
+
+/* out = sum_m c_m T_m(A') v (conj: conjugated coefficients); work: 3 complex N-vectors */
+static void kpm_poly(double* out, const double* v, int64_t order, const double* coeff, int conj, int transposed, const ref_model* m,
+                     const double* eVbar, const double* cbar, const double* sbar, double lam_avg, double lam_mag, double* work) {
+    const int64_t N = m->N;
+    const double sg = conj ? -1.0 : 1.0;
+    double cr = coeff[0], ci = sg * coeff[1];
+    for (int64_t i = 0; i < N; ++i) {
+        out[2 * i] = cr * v[2 * i] - ci * v[2 * i + 1];
+        out[2 * i + 1] = cr * v[2 * i + 1] + ci * v[2 * i];
+    }
+    if (order <= 1) return;
+    double *up = work, *un = work + 2 * N, *ux = work + 4 * N;
+    memcpy(un, v, (size_t)(2 * N) * sizeof(double));
+    mulAprime_c(ux, un, m, eVbar, cbar, sbar, lam_avg, lam_mag, transposed);
+    for (int64_t n = 2;; ++n) {
+        double* t = up; up = un; un = ux; ux = t;              /* (u_prev, u_n) = (u_n, u_next) */
+        cr = coeff[2 * (n - 1)]; ci = sg * coeff[2 * (n - 1) + 1];
+        for (int64_t i = 0; i < N; ++i) {
+            out[2 * i] += cr * un[2 * i] - ci * un[2 * i + 1];
+            out[2 * i + 1] += cr * un[2 * i + 1] + ci * un[2 * i];
+        }
+        if (n == order) break;
+        mulAprime_c(ux, un, m, eVbar, cbar, sbar, lam_avg, lam_mag, transposed);
+        for (int64_t i = 0; i < 2 * N; ++i) ux[i] = 2.0 * ux[i] - up[i];
+    }
+}
+
+/* all frequency blocks of the preconditioner: a2T[w] = M^-1[w,w] M^-T[w,w] a1T[w], w < Lo2; a1T, a2T: [omega][site] complex.
+ * Frequencies are independent: one OpenMP thread per block when nthreads > 1.  Returns the threads used. */
+int ref_kpm_blocks(const ref_model* m, const double* eVbar, const double* cbar, const double* sbar, double lam_avg, double lam_mag,
+                   int64_t Lo2, const int64_t* order, const int64_t* coeff_off, const double* coeff, const double* a1T, double* a2T,
+                   int nthreads) {
+    const int64_t N = m->N;
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+    {
+#pragma omp single
+        used = omp_get_num_threads();
+        double* work = (double*)malloc((size_t)(8 * N) * sizeof(double));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t w = 0; w < Lo2; ++w) {
+            double* tmp = work + 6 * N;
+            kpm_poly(tmp, a1T + 2 * w * N, order[w], coeff + 2 * coeff_off[w], 1, 1, m, eVbar, cbar, sbar, lam_avg, lam_mag, work);
+            kpm_poly(a2T + 2 * w * N, tmp, order[w], coeff + 2 * coeff_off[w], 0, 0, m, eVbar, cbar, sbar, lam_avg, lam_mag, work);
+        }
+        free(work);
+    }
+#else
+    (void)nthreads;
+    double* work = (double*)malloc((size_t)(8 * N) * sizeof(double));
+    for (int64_t w = 0; w < Lo2; ++w) {
+        double* tmp = work + 6 * N;
+        kpm_poly(tmp, a1T + 2 * w * N, order[w], coeff + 2 * coeff_off[w], 1, 1, m, eVbar, cbar, sbar, lam_avg, lam_mag, work);
+        kpm_poly(a2T + 2 * w * N, tmp, order[w], coeff + 2 * coeff_off[w], 0, 0, m, eVbar, cbar, sbar, lam_avg, lam_mag, work);
+    }
+    free(work);
+#endif
+    return used;
+}
+
+void ref_mulMTM_mt(double* y, const ref_model* m, const double* expnV, const double* v, double* scratch, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+    mulMTM_mt(y, m, expnV, v, scratch);
+}
+
 /* Throughput driver: `nrep` independent replicas (the reference's own scale-out: independent runs, one
  * thread each -- BLAS/FFTW are pinned to 1 thread, src/ElPhDynamics.jl:74-75), `reps` M^T M products each.
  * v, y, expnV, scratch: nrep contiguous blocks of N*L doubles.  Returns the number of threads used. */
