@@ -135,8 +135,17 @@ def extras_fixtures():
     np.savez_compressed(OUT / "honeycomb2_extras.npz", **d)
 
 
+def chain_fixture():
+    """Row N1: the measurement series of a short fixed-seed chain of the shipped example (tests/helpers_chain.py)."""
+    from helpers_chain import Noise, OracleChain, run_chain
+    om, _ = oracle_holstein("square", 4, 2.0, 0.1, mu=-1.0, seed=1234, eps=0.3, tol=1e-5)
+    series = run_chain(OracleChain(om, 0.02), Noise(202, om.Ndof, om.Ndim, om.N), burnin=10, nsteps=24, meas_freq=4)
+    np.savez(OUT / "chain_square4.npz", series=series, x_final=om.x.copy())
+
+
 if __name__ == "__main__":
     integer_fixtures()
     float_fixtures()
     extras_fixtures()
+    chain_fixture()
     print("wrote", sorted(p.name for p in OUT.iterdir()))

@@ -9,7 +9,7 @@ import pytest
 
 import elphdynamics_b200 as E
 from elphdynamics_b200 import _lib
-from helpers import GEOMS, oracle_holstein
+from helpers import GEOMS, oracle_holstein, relerr
 from oracle import lattice as olat
 
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -234,3 +234,15 @@ def test_engine_reproduces_greens_and_special_update_fixture():
     assert np.array_equal(em.x, gold["x_after_special"])
     Ge.close()
     em.close()
+
+
+def test_oracle_chain_regression():
+    """Row N1 on the CPU: the oracle's fixed-seed chain of the shipped example (updates + <x>, <x^2>, G(0,0) measurements,
+    tests/helpers_chain.py) reproduces the frozen series of tests/golden/chain_square4.npz."""
+    from helpers_chain import Noise, OracleChain, run_chain
+    gold = np.load(GOLD / "chain_square4.npz")
+    om, _ = oracle_holstein("square", 4, 2.0, 0.1, mu=-1.0, seed=1234, eps=0.3, tol=1e-5)
+    series = run_chain(OracleChain(om, 0.02), Noise(202, om.Ndof, om.Ndim, om.N), burnin=10, nsteps=24, meas_freq=4)
+    assert series.shape == gold["series"].shape
+    assert np.allclose(series, gold["series"], rtol=1e-7, atol=1e-9)
+    assert relerr(om.x, gold["x_final"]) <= 1e-7
