@@ -1249,6 +1249,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 9: h->hmc_fused_inner = (value != 0); break;
             case 10: h->cg_pipeline = (value < 0) ? -1 : (value != 0); break;
             case 13: ELPH_REQUIRE(value >= 0 && value <= 16, ELPH_ERR_INVALID, "variant out of range"); h->pipe_variant = value; break;
+            case 15: h->pipe_sync_mode = value; break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:
                 h->pipe_prof = (value != 0);

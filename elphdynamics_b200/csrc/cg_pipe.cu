@@ -81,6 +81,7 @@ struct PipeParams {
     CgScalars* S;
     unsigned long long* prof;         // development aid (tuning key 12): [cta][8] cycles per phase, summed over the iterations
     unsigned int base;                // tags of this solve: publication k -> base + 1 + k, reduction n -> base + 1 + n
+    int sync_mode;
     int L, Lmax, Ly, ys, spc, maxcta, rank, world, tau0, Lglob, d_halo, x0_given;
     double c0, s0, c1, s1, c2, s2, c3, s3;
 };
@@ -342,7 +343,41 @@ __global__ void __launch_bounds__(MAXT, MINB) cgpipe_kernel(PipeParams P) {
     }
     int xbuf = 0;
     bool dead = false;                     // a row never arrived: stop waiting; the reducer turns the abort word into an abort message
-    auto edge_sync = [&]() { if (YS > 1) cluster.sync(); else __syncthreads(); };
+    // cluster.sync() = MEMBAR.ALL.GPU + barrier: the fence waits for every outstanding global store (the 16-byte row pushes) and
+    // costs more than the barrier.  Only the shared-memory strips have to be ordered here: they live in the owning SM, a
+    // CTA-scope fence completes this CTA's stores to them before it arrives, and the partners read them after the wait.
+    auto edge_sync = [&]() {
+        if (YS > 1) {
+            if (P.sync_mode == 0) cluster.sync();
+            else if (P.sync_mode == 1) {
+                __threadfence_block();
+                asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+            } else if (P.sync_mode == 2) {
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+            } else if (P.sync_mode == 3) {
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            } else if (P.sync_mode == 4) {
+                __threadfence();
+                asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+            } else if (P.sync_mode == 5) {
+                __syncthreads();
+                asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+            } else {
+                __threadfence_block();
+                asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
+    };
     auto exchange2 = [&](const Tile<NSEG, PY>& a, const Tile<NSEG, PY>& b, double (&a_ab)[NSEG], double (&b_ab)[NSEG],
                          double (&a_be)[NSEG], double (&b_be)[NSEG]) {
         const size_t boff = (size_t)xbuf * NW * 4 * LX;
@@ -1278,6 +1313,7 @@ bool elph_cg_pipe_run(elph_handle* h, const double* r0, double* x, bool x0_given
     P.ghost = reinterpret_cast<double*>(at(A.arena, Y.ghost));
     P.state = reinterpret_cast<double*>(at(A.arena, Y.state));
     P.spc = 1;
+    P.sync_mode = h->pipe_sync_mode;
     P.S = h->d_cg;
     P.prof = h->pipe_prof ? h->pipe_prof_buf : nullptr;
     P.base = A.pipe_seq;

@@ -282,6 +282,7 @@ struct elph_handle {
     unsigned int* h_hx_flag = nullptr;   // pinned: failure flag of the peer-memory halo exchange
     int cg_pipeline = -1;          // unpreconditioned CG on square lattices: pipelined persistent kernel (cg_pipe.cu); -1 = auto, 0 = off
     int pipe_ys = 0;               // tuning: CTAs per time slice of the pipelined kernel (0 = automatic)
+    int pipe_sync_mode = 0;        // tuning key 15: how the edge exchange across the CTAs of a slice is synchronised (see cg_pipe.cu)
     int pipe_spc = 0;              // tuning key 14: time slices per CTA of the multi-slice variants (0 = smallest that fits)
     int pipe_last_spc = 1;
     int pipe_variant = 0;          // tuning key 13: force one variant of the pipelined kernel (0 = automatic)

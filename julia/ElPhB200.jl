@@ -60,8 +60,22 @@ function B200Model(m::HolsteinModel)
     push_x!(g); update_model!(g)
     finalizer(x -> ccall((:elph_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), g)
 end
-# B200Model(m::SSHModel): same with model=1 and t, alpha, alpha2, checkerboard_perm, inv_checkerboard_perm,
-# phonon_to_bond, bond_to_phonon, primary_field (src/SSHModels.jl:146-173) -- all 1-based Int64 as stored.
+# SSH: phonons on bonds (src/SSHModels.jl:79-314).  The index maps go over as stored (1-based Int64, index_base = 1):
+# checkerboard_perm / inv_checkerboard_perm (:166-173), phonon_to_bond / bond_to_phonon (0 = no phonon, :155-160),
+# primary_field (:152); t, alpha, alpha2 in the ORIGINAL bond order (:121-133); the engine builds t', cosh, sinh itself.
+function B200Model(m::SSHModel)
+    cfg = ElphConfig(model=1, Ltau=m.Lτ, Nsites=m.Nsites, Nbonds=m.Nbonds, Nph=m.Nph, dtau=m.Δτ,
+        neighbor_table=pointer(m.neighbor_table), mu=pointer(m.μ), omega=pointer(m.ω), omega4=pointer(m.ω₄),
+        t=pointer(m.t), alpha=pointer(m.α), alpha2=pointer(m.α₂),
+        checkerboard_perm=pointer(m.checkerboard_perm), inv_checkerboard_perm=pointer(m.inv_checkerboard_perm),
+        phonon_to_bond=pointer(m.phonon_to_bond), bond_to_phonon=pointer(m.bond_to_phonon), primary_field=pointer(m.primary_field),
+        cg_tol=m.solver.tol, cg_maxiter=m.solver.maxiter, cg_kappa_max=m.solver.κmax)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve m check(ccall((:elph_create, LIB), Int32, (Ref{ElphConfig}, Ref{Ptr{Cvoid}}), cfg, h), C_NULL)
+    g = B200Model{eltype(m.x),eltype(m.v′),typeof(m.solver),typeof(m.rng),typeof(m)}(m, h[])
+    push_x!(g); update_model!(g)
+    finalizer(x -> ccall((:elph_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), g)
+end
 
 Base.getproperty(g::B200Model, s::Symbol) = s in (:host, :h) ? getfield(g, s) : getproperty(getfield(g, :host), s)
 
@@ -167,6 +181,30 @@ function evolve!(g::B200Model, dyn, fa::FourierAccelerator, P=I)::Int
                 g.h, method(dyn), dyn.Δt, η, g1, two ? g2 : C_NULL, usep ? a1 : C_NULL, (usep && two) ? a2 : C_NULL,
                 usep ? 1 : 0, iters, C_NULL, C_NULL), g.h)
     Int(iters[])
+end
+
+# --- HMC: update!(model, hmc, fa, P) src/HMC.jl:310-345 -> one whole trajectory on the device (elph_hmc_update) ---------------
+# The draws are made here in the reference's order: refresh_v! (randn!(R, model), :655), refresh_ϕ! (R₊, R₋, :675-676), the 2N
+# Arnoldi start values of every setup!(P) of the trajectory (Nt + 2 force / action evaluations, call order), and last the
+# Metropolis uniform (:453 / :618).  Nothing else draws in between, so taking them up front leaves model.rng's stream as the
+# reference's.  fa must have been attached (attach!) after update_M!.  On return x lives on the device (pull_x! before measuring).
+import ElPhDynamics.HMC: HybridMonteCarlo, update!
+function update!(g::B200Model, hmc::HybridMonteCarlo, fa::FourierAccelerator, P=I)
+    hmc.Ndof > 0 || return true, 0.0
+    m, rng = g.host, g.host.rng
+    usep = P isa B200KPM
+    hmc.t = 0
+    Rv = randn(rng, m.Ndof)
+    R₊ = randn(rng, m.Ndim); R₋ = randn(rng, m.Ndim)
+    a = usep ? randn(rng, 2 * m.Nsites * (hmc.Nt + 2)) : Float64[]
+    u = rand(rng)
+    acc = Ref{Int32}(0); it = Ref{Float64}(0); H₀ = Ref{Float64}(0); H₁ = Ref{Float64}(0); fl = Ref{Int32}(0)
+    check(ccall((:elph_hmc_update, LIB), Int32,
+                (Ptr{Cvoid}, Float64, Int64, Int64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64,
+                 Ref{Int32}, Ref{Float64}, Ref{Float64}, Ref{Float64}, Ref{Int32}),
+                g.h, hmc.Δt, hmc.Nt, hmc.Nb, hmc.α, Rv, R₊, R₋, usep ? a : C_NULL, usep ? 1 : 0, u, acc, it, H₀, H₁, fl), g.h)
+    hmc.updates += 1
+    acc[] == 1, it[]
 end
 
 end # module
