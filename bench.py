@@ -48,6 +48,30 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this process to the host cores of the NUMA node its GPU hangs off, BEFORE any page-locked staging buffer is
+    allocated (first-touch places the pages on that node): with 8 ranks the host<->device copies of the e2e leg otherwise cross
+    the socket interconnect.  Returns a description for the bench line, or None when the topology cannot be read."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"pci": bus, "numa_node": node, "cores": len(cpus)}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -181,7 +205,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--replicas", type=int, default=256, help="replicas per device-resident step")
+    ap.add_argument("--replicas", type=int, default=256, help="replicas per launch of the device-resident step")
+    ap.add_argument("--launches-per-step", type=int, default=50,
+                    help="a step = this many passes of the fused M^T M kernel over the replica batch (a single 0.22 ms launch per "
+                         "step made the timed window shorter than the power-management time scale)")
     ap.add_argument("--e2e-replicas", type=int, default=64, help="replicas per host-buffer (e2e) step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the CG / Langevin extra measurements")
@@ -205,6 +232,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    all_cores = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     # work on a real (non-legacy) stream: CUDA events time it, and the engine can capture CUDA graphs on it
     torch.cuda.set_stream(torch.cuda.Stream())
     if world > 1:
@@ -232,10 +261,13 @@ def main():
     base = torch.from_numpy(np.ascontiguousarray(em.expnV.reshape(Nsites, Ltau).T)).reshape(-1).cuda()
     D = base.unsqueeze(0).repeat(R, 1) * (1.0 + 0.01 * torch.rand(R, n, dtype=torch.float64, device="cuda", generator=g))
 
+    LPS = max(1, args.launches_per_step)
+
     def step_device():
-        st = lib.elph_dev_mulMTM_replicas(em.handle, R, D.data_ptr(), n, V.data_ptr(), Y.data_ptr(), n)
-        if st != 0:
-            raise RuntimeError(lib.elph_last_error(em.handle))
+        for _ in range(LPS):
+            st = lib.elph_dev_mulMTM_replicas(em.handle, R, D.data_ptr(), n, V.data_ptr(), Y.data_ptr(), n)
+            if st != 0:
+                raise RuntimeError(lib.elph_last_error(em.handle))
 
     for _ in range(args.warmup):
         step_device()
@@ -247,8 +279,7 @@ def main():
     # of the SAME launches (untimed) so that the clock / throttle record is taken under this very load
     t_soak = time.perf_counter()
     while time.perf_counter() - t_soak < 0.4:
-        for _ in range(20):
-            step_device()
+        step_device()
         torch.cuda.synchronize()
     barrier()
     l0 = em.launch_count()
@@ -265,8 +296,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
-    value = world * R * args.steps / (ms * 1e-3)
-    kernel_us = ms * 1e3 / args.steps
+    value = world * R * LPS * args.steps / (ms * 1e-3)
+    kernel_us = ms * 1e3 / (args.steps * LPS)
     achieved = BYTES_PER_POINT * n * R / (kernel_us * 1e-6) / 1e9   # GB/s per GPU
 
     # ---------------- e2e: host buffers through the C ABI ------------------------------------------------------
@@ -483,6 +514,37 @@ def main():
                                           "algorithmic_GBps": 48.0 * nC / usC / 1e3,
                                           "cg": {"iters": int(itC), "residual": float(resC), "flag": int(flC), "seconds": dtC},
                                           "note": "single lattice (L2-resident tables), best of 3 x 200 launches; 48 B/pt = v + cosh + sinh tables + y"}
+        # HBM regime: independent replicas, each with its own phonon field -> own (cosh, sinh) table (6.6 MB) and vector
+        RC = 128
+        LC, NC, NphC = mC.Ltau, mC.Nsites, mC.Nph
+        tab_stride = 4 * LC * NC
+        XC = 0.3 * torch.randn(RC, NphC * LC, dtype=torch.float64, device="cuda")
+        TC = torch.empty(RC * tab_stride, dtype=torch.float64, device="cuda")
+        VC = torch.randn(RC, nC, dtype=torch.float64, device="cuda")
+        YC = torch.empty_like(VC)
+        e0.record()
+        mC._call("elph_dev_ssh_replica_tables", RC, XC.data_ptr(), NphC * LC, TC.data_ptr(), tab_stride)
+        e1.record()
+        torch.cuda.synchronize()
+        us_tab = e0.elapsed_time(e1) * 1e3
+        for _ in range(5):
+            lib.elph_dev_mulMTM_replicas_ssh(mC.handle, RC, TC.data_ptr(), tab_stride, VC.data_ptr(), YC.data_ptr(), nC)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            lib.elph_dev_mulMTM_replicas_ssh(mC.handle, RC, TC.data_ptr(), tab_stride, VC.data_ptr(), YC.data_ptr(), nC)
+        e1.record()
+        torch.cuda.synchronize()
+        us_rep = e0.elapsed_time(e1) * 1e3 / 20
+        extra["ssh_square_32x32_L200"]["replicas"] = {
+            "replicas_per_launch": RC, "us_per_launch": us_rep, "matvecs_per_s": RC * 1e6 / us_rep,
+            "algorithmic_bytes_per_launch": 48.0 * nC * RC, "achieved_GBps": 48.0 * nC * RC / us_rep / 1e3,
+            "frac_of_hbm_peak": 48.0 * nC * RC / us_rep / 1e3 / hbm_peak, "peak": hbm_peak, "peak_source": peak_src,
+            "tables_us": us_tab,
+            "note": "elph_dev_mulMTM_replicas_ssh: every replica streams v + (cosh, sinh) of both bond directions + y = 48 B per "
+                    "lattice point (805 MB per launch vs 126 MB L2); tables_us = update_model! of all replicas in one launch "
+                    "(elph_dev_ssh_replica_tables)"}
+        del XC, TC, VC, YC
         mC.close()
 
         # ---- configuration D: HMC trajectory on the honeycomb lattice L=32 (N=2048, Ltau=20), Nt=10 leapfrog steps ----
@@ -620,31 +682,36 @@ def main():
         mE.close()
 
     if rank == 0:
-        traffic = None
+        traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             try:
                 tj = json.loads(tp.read_text())
                 # captured at tj["replicas"] replicas per launch; the kernel streams, so traffic is linear in replicas
                 traffic = tj["mtm_replicas_dram_bytes_per_launch"] * R / tj.get("replicas", 64)
+                traffic_src = (f"ncu --set full capture of this launch shape at {tj.get('replicas', 64)} replicas "
+                               f"({tj.get('source', 'profiles/traffic.json')}), dram__bytes_read.sum + dram__bytes_write.sum; "
+                               "not re-measured by this run (a profiler cannot run inside the timed region)")
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "holstein_square_32x32_L200", "replicas_per_gpu": R,
-                           "l2_policy": f"inputs larger than L2: {3 * R * n * 8 / 1e6:.0f} MB per step vs 126 MB L2",
+                "config": {"workload": "holstein_square_32x32_L200", "replicas_per_gpu": R, "launches_per_step": LPS,
+                           "matvecs_per_step": world * R * LPS,
+                           "l2_policy": f"inputs larger than L2: {3 * R * n * 8 / 1e6:.0f} MB per launch vs 126 MB L2",
                            "parallelism": f"replicas x{world}" if world > 1 else "single GPU"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "mtm_square_kernel<1,16,0,256> (fused M^T M, register/shuffle, TMA-staged)",
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "mtm_square_kernel<1,16,0,256> (fused M^T M, register/shuffle, TMA-staged)",
                              "algorithmic_bytes_per_launch": BYTES_PER_POINT * n * R, "kernel_us": kernel_us},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Re * n * 8, "d2h_bytes_per_step": Re * n * 8,
-                        "api": "elph_mulMTM_batch (host pointers, pinned)"},
+                        "api": "elph_mulMTM_batch (host pointers, pinned)", "host_numa_binding": numa},
                 "gpu_launches": int(launches), "clocks": clocks}
         line.update(extra)
         if sharded is not None:
             line["tau_sharded"] = sharded
         if not args.no_cpu:
+            os.sched_setaffinity(0, all_cores)     # the CPU baseline uses every host core, not only the GPU's NUMA node
             cb, _ = cpu_baseline()
             try:
                 cb["langevin_rk_kpm"] = cpu_langevin_baseline()

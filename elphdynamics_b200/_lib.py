@@ -140,6 +140,8 @@ def load() -> C.CDLL:
         "elph_dev_mulM": (i32, [H, C.c_void_p, C.c_void_p]),
         "elph_dev_mulMT": (i32, [H, C.c_void_p, C.c_void_p]),
         "elph_dev_mulMTM_replicas": (i32, [H, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64]),
+        "elph_dev_ssh_replica_tables": (i32, [H, i64, C.c_void_p, i64, C.c_void_p, i64]),
+        "elph_dev_mulMTM_replicas_ssh": (i32, [H, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64]),
         "elph_set_shard": (i32, [H, i64, i64]),
         "elph_dev_shard_matvec": (i32, [H, i32, C.c_void_p, C.c_void_p]),
         "elph_dev_shard_halo": (i32, [H, C.c_void_p]),

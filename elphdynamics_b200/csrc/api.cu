@@ -1021,6 +1021,43 @@ int32_t elph_dev_mulMTM_replicas(elph_handle* h, int64_t nrep, const double* exp
     ELPH_CATCH(h)
 }
 
+// SSH: the replicas' tables come from elph_dev_ssh_replica_tables (tile layout of ssh_square.cu), strides in doubles
+int32_t elph_dev_ssh_replica_tables(elph_handle* h, int64_t nrep, const double* x_dev, int64_t x_stride, double* tab_dev,
+                                    int64_t tab_stride) {
+    ENTER(h) {
+        ELPH_REQUIRE(x_dev && tab_dev && nrep >= 1, ELPH_ERR_INVALID, "bad replica arguments");
+        ELPH_REQUIRE(tab_stride % 2 == 0 && tab_stride >= 4LL * h->L * h->N && x_stride >= (int64_t)h->L * h->Nph, ELPH_ERR_INVALID,
+                     "replica strides too small (table: 4*Ltau*Nsites doubles, field: Ltau*Nph doubles)");
+        elph_launch_ssh_replica_tables(h, nrep, x_dev, x_stride, reinterpret_cast<double2*>(tab_dev), tab_stride / 2);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_mulMTM_replicas_ssh(elph_handle* h, int64_t nrep, const double* tab_dev, int64_t tab_stride, const double* v_dev,
+                                     double* y_dev, int64_t vec_stride) {
+    ENTER(h) {
+        ELPH_REQUIRE(v_dev && y_dev && tab_dev && nrep >= 1, ELPH_ERR_INVALID, "bad replica arguments");
+        ELPH_REQUIRE(h->model == ELPH_MODEL_SSH && h->ssq.enabled && !h->sq_disable, ELPH_ERR_UNSUPPORTED,
+                     "SSH replica batches need a periodic square lattice (register-tile kernel)");
+        ELPH_REQUIRE(tab_stride % 2 == 0 && tab_stride >= 4LL * h->L * h->N && vec_stride >= h->Ndim, ELPH_ERR_INVALID,
+                     "replica strides too small");
+        ELPH_REQUIRE((reinterpret_cast<uintptr_t>(tab_dev) % 16) == 0 && (tab_stride * sizeof(double)) % 16 == 0 &&
+                         (reinterpret_cast<uintptr_t>(v_dev) % 16) == 0 && (vec_stride * sizeof(double)) % 16 == 0,
+                     ELPH_ERR_INVALID, "replica tables and vectors must be 16-byte aligned (TMA bulk copies)");
+        MatvecArgs a;
+        a.v = v_dev;
+        a.y = y_dev;
+        a.nbatch = nrep;
+        a.v_stride = vec_stride;
+        a.y_stride = vec_stride;
+        a.ssh_tab = reinterpret_cast<const double2*>(tab_dev);
+        a.ssh_tab_stride = tab_stride / 2;
+        ELPH_REQUIRE(elph_launch_ssh_square(h, a), ELPH_ERR_UNSUPPORTED, "lattice shape not served by the SSH register-tile kernel");
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
 // ---- tau-sharding (multi-GPU): this handle owns global slices [tau0, tau0 + Ltau) of Lglob -------------------
 int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob) {
     ENTER(h) {
@@ -1250,6 +1287,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 10: h->cg_pipeline = (value < 0) ? -1 : (value != 0); break;
             case 13: ELPH_REQUIRE(value >= 0 && value <= 16, ELPH_ERR_INVALID, "variant out of range"); h->pipe_variant = value; break;
             case 15: h->pipe_sync_mode = value; break;
+            case 16: h->kpm_fast = (value != 0); h->kpm_version++; break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:
                 h->pipe_prof = (value != 0);

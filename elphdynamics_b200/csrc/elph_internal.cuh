@@ -140,6 +140,8 @@ struct elph_handle {
     bool trace = false;        // ELPH_TRACE=1: phase timings of the dynamics entry points on stderr (synchronises the stream)
     double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
+    bool kpm_exclusive = true; // KPM apply: one chain CTA per SM (shared-memory request padded)
+    bool kpm_fast = true;      // KPM apply: sweeps in tanh form with folded constants (tuning key 16)
     bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
     int cg_single_reduction = -1;  // unpreconditioned CG, Holstein square: one barrier per iteration (cg_p2p.cu); -1 = auto
                                    // (on where measured faster: 32-wide lattices), 0 = off, 1 = on
@@ -309,6 +311,8 @@ struct MatvecArgs {
     const double* D = nullptr;   // nullptr -> handle's table
     int64_t nbatch = 1;
     int64_t v_stride = 0, y_stride = 0, D_stride = 0;
+    const double2* ssh_tab = nullptr;   // SSH replicas: (cosh, sinh) tables in the tile layout of ssh_square.cu, one per replica
+    int64_t ssh_tab_stride = 0;         // in double2 elements
     bool open = false;              // tau-sharded slab: v (and D) carry one halo slice before and after the own slices
     double* partial_dot = nullptr;  // if set: per-CTA partial sums of dot(v, y); returns count via *npartial
     int* npartial = nullptr;
@@ -322,6 +326,7 @@ struct MatvecArgs {
 
 void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a);
 void elph_launch_update_model(elph_handle* h);
+void elph_launch_ssh_replica_tables(elph_handle* h, int64_t nrep, const double* x_dev, int64_t x_stride, double2* tab_dev, int64_t tab_stride);
 void elph_detect_square(elph_handle* h, const std::vector<double2>& cs);
 bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a);
 bool elph_match_square(const elph_handle* h, int* Lx, int* Ly, std::vector<int>* slot);

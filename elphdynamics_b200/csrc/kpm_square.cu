@@ -26,6 +26,9 @@ struct KsqParams {
     int L, Ly;
     double inv_mag, avg_over_mag;
     double c0, s0, c1, s1, c2, s2, c3, s3;
+    double t0, t1, t2, t3, cprod;   // tanh form (square_tiles.cuh): t_g = s_g / c_g, cprod = c0 c1 c2 c3
+    int fast;
+    unsigned long long* prof;   // development aid (tuning key 12): clock64 stamps of the cluster of the longest polynomial
 };
 
 template <int NSEG, int PY>
@@ -238,6 +241,95 @@ __device__ __forceinline__ void poly_real(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, 
     }
 }
 
+// The same polynomial with the sweep in tanh form and the constants folded (9 / 8 fp64 operations per site and Chebyshev term
+// instead of 15; the chain of the lowest frequency is what an apply waits for):
+//     evs = 2 (c0 c1 c2 c3 / mag) eVbar ;  Kt = prod_g (1 + t_g X_g)
+//     T_1 = (1/2) S v - (avg/mag) v ;  T_n = S T_{n-1} - (2 (avg/mag) T_{n-1} + T_{n-2}) ;  S u = Kt (evs .* u)   [A'^T: evs .* (Kt^T u)]
+// The bracket does not depend on the sweep, so it is off the dependent chain.  Differs from poly_real by rounding only.
+template <int NSEG, int PY, bool TRANSPOSED>
+__device__ __forceinline__ void sweep_t(Tile<NSEG, PY>& s, const KsqParams& P, double* strips, int& xbuf, int warp, int nwarps,
+                                        int lane) {
+    constexpr int LX = 32 * NSEG;
+    double ab[NSEG], be[NSEG];
+    if (!TRANSPOSED) {
+        g0_x_even_t(s, P.t0);
+        g1_x_odd_t(s, P.t1, lane);
+        g2_y_even_t(s, P.t2);
+        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+        xbuf ^= 1;
+        g3_y_odd_t(s, P.t3, ab, be);
+    } else {
+        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+        xbuf ^= 1;
+        g3_y_odd_t(s, P.t3, ab, be);
+        g2_y_even_t(s, P.t2);
+        g1_x_odd_t(s, P.t1, lane);
+        g0_x_even_t(s, P.t0);
+    }
+}
+
+template <int NSEG, int PY, bool TRANSPOSED>
+__device__ __forceinline__ void poly_real_fast(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, const Tile<NSEG, PY>& vin,
+                                               const Tile<NSEG, PY>& evs, const cplx* c_s, int order, const KsqParams& P,
+                                               double* strips, int& xbuf, int warp, int nwarps, int lane) {
+    Tile<NSEG, PY> un, uprev, s, pre;
+    const double sg = TRANSPOSED ? -1.0 : 1.0;
+    const double c0r = c_s[0].x, c0i = sg * c_s[0].y;
+    const double k2 = P.avg_over_mag, k22 = 2.0 * P.avg_over_mag;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double v = vin.a[r][q];
+            A.a[r][q] = c0r * v;
+            B.a[r][q] = c0i * v;
+            un.a[r][q] = v;
+        }
+    if (order < 2) return;
+    {   // n = 1
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                pre.a[r][q] = k2 * un.a[r][q];
+                s.a[r][q] = TRANSPOSED ? un.a[r][q] : (0.5 * evs.a[r][q]) * un.a[r][q];
+            }
+        sweep_t<NSEG, PY, TRANSPOSED>(s, P, strips, xbuf, warp, nwarps, lane);
+        const double cr = c_s[1].x, ci = sg * c_s[1].y;
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const double a = TRANSPOSED ? fma(0.5 * evs.a[r][q], s.a[r][q], -pre.a[r][q]) : (s.a[r][q] - pre.a[r][q]);
+                uprev.a[r][q] = un.a[r][q];
+                un.a[r][q] = a;
+                A.a[r][q] = fma(cr, a, A.a[r][q]);
+                B.a[r][q] = fma(ci, a, B.a[r][q]);
+            }
+    }
+    for (int n = 2; n < order; ++n) {
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                pre.a[r][q] = fma(k22, un.a[r][q], uprev.a[r][q]);
+                s.a[r][q] = TRANSPOSED ? un.a[r][q] : evs.a[r][q] * un.a[r][q];
+            }
+        sweep_t<NSEG, PY, TRANSPOSED>(s, P, strips, xbuf, warp, nwarps, lane);
+        const double cr = c_s[n].x, ci = sg * c_s[n].y;
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const double a = TRANSPOSED ? fma(evs.a[r][q], s.a[r][q], -pre.a[r][q]) : (s.a[r][q] - pre.a[r][q]);
+                uprev.a[r][q] = un.a[r][q];
+                un.a[r][q] = a;
+                A.a[r][q] = fma(cr, a, A.a[r][q]);
+                B.a[r][q] = fma(ci, a, B.a[r][q]);
+            }
+    }
+}
+
 template <int NSEG, int PY, int MAXT>
 __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int max_order) {
     constexpr int LX = 32 * NSEG;
@@ -246,6 +338,10 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
     if (P.skip && *P.skip) return;
     unsigned int crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    unsigned long long* prof = (P.prof && (blockIdx.x >> 1) == 0 && threadIdx.x == 0) ? P.prof + 8 * crank : nullptr;
+    int nstamp = 0;
+    auto stamp = [&]() { if (prof) prof[nstamp++] = (unsigned long long)clock64(); };
+    stamp();
     // both CTAs of the pair must be running before either touches the other's shared memory
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -268,6 +364,7 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
             ev.a[r][q] = P.eVbar[e];
         }
     __syncthreads();
+    stamp();
     // DSMEM address of the partner's exchange buffer
     const uint32_t my_xch = (uint32_t)__cvta_generic_to_shared(xch);
     uint32_t remote_xch;
@@ -296,10 +393,26 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
     };
     int xbuf = 0;
     Tile<NSEG, PY> t1, t2;
-    poly_real<NSEG, PY, true>(A, B, v, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);    // M^-T[w,w]
-    swap_combine(t1);
-    poly_real<NSEG, PY, false>(A, B, t1, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);  // M^-1[w,w]
-    swap_combine(t2);
+    if (P.fast) {
+        const double sc = 2.0 * P.inv_mag * P.cprod;
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) ev.a[r][q] *= sc;
+        poly_real_fast<NSEG, PY, true>(A, B, v, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);    // M^-T[w,w]
+        stamp();
+        swap_combine(t1);
+        stamp();
+        poly_real_fast<NSEG, PY, false>(A, B, t1, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);  // M^-1[w,w]
+        stamp();
+        swap_combine(t2);
+        stamp();
+    } else {
+        poly_real<NSEG, PY, true>(A, B, v, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);    // M^-T[w,w]
+        swap_combine(t1);
+        poly_real<NSEG, PY, false>(A, B, t1, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane);  // M^-1[w,w]
+        swap_combine(t2);
+    }
     const int wm = P.L - 1 - w;
     double* out_comp = reinterpret_cast<double*>(P.out) + crank;
     const double msign = (crank == 0) ? 1.0 : -1.0;   // mirror frequency = complex conjugate
@@ -311,13 +424,16 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
             if (wm != w) out_comp[2 * ((size_t)w * N + e)] = t2.a[r][q];
             out_comp[2 * ((size_t)wm * N + e)] = msign * t2.a[r][q];
         }
+    stamp();
 }
 
 template <int NSEG, int PY, int MAXT>
 void launch_ksq_split(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
     constexpr int LX = 32 * NSEG;
-    const size_t smem = (size_t)max_order * sizeof(cplx) + 2ull * nwarps * 2 * LX * sizeof(double) +
-                        (size_t)LX * P.Ly * sizeof(double);
+    size_t smem = (size_t)max_order * sizeof(cplx) + 2ull * nwarps * 2 * LX * sizeof(double) +
+                  (size_t)LX * P.Ly * sizeof(double);
+    // one CTA per SM: a second cluster on the SM of the longest chain would share its fp64 pipe (the chain is what an apply waits for)
+    if (h->kpm_exclusive) smem = std::max(smem, std::min<size_t>(h->smem_optin, 120 * 1024));
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "KPM split kernel does not fit in shared memory");
     elph_enable_smem(h, kpm_square_split_kernel<NSEG, PY, MAXT>);
     cudaLaunchConfig_t cfg = {};
@@ -371,6 +487,11 @@ bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, con
     P.inv_mag = 1.0 / K.lam_mag; P.avg_over_mag = K.lam_avg / K.lam_mag;
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
+    P.t0 = P.s0 / P.c0; P.t1 = P.s1 / P.c1; P.t2 = P.s2 / P.c2; P.t3 = P.s3 / P.c3;
+    P.cprod = P.c0 * P.c1 * P.c2 * P.c3;
+    P.fast = h->kpm_fast ? 1 : 0;
+    if (const char* e = getenv("ELPH_KPM_EXCL")) h->kpm_exclusive = atoi(e) != 0;
+    P.prof = h->pipe_prof ? h->pipe_prof_buf : nullptr;
 #define KSQ_CASE(NS, PYV, MAXT)                                    \
     if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {       \
         if (h->kpm_split) launch_ksq_split<NS, PYV, MAXT>(h, P, nwarps, max_order); \

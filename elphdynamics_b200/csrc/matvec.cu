@@ -246,7 +246,10 @@ __global__ void ssh_update_kernel(const double* __restrict__ x, const double* __
                                   const double* __restrict__ alpha2, const int* __restrict__ col_ph,
                                   const int* __restrict__ col_bond, double2* __restrict__ cs, double* __restrict__ tprime,
                                   const int* __restrict__ sq_slot, double2* __restrict__ sq_tab, int Nb, int Nph, long long n,
-                                  double dtau) {
+                                  double dtau, long long x_stride = 0, long long tab_stride = 0) {
+    // blockIdx.y = replica (elph_dev_ssh_replica_tables): own phonon field, own tile-layout table, no column-layout copies
+    x += (size_t)blockIdx.y * x_stride;
+    if (sq_tab) sq_tab += (size_t)blockIdx.y * tab_stride;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const int col = (int)(idx % Nb);
         const long long tau = idx / Nb;
@@ -257,9 +260,9 @@ __global__ void ssh_update_kernel(const double* __restrict__ x, const double* __
             const double sgn = (xv > 0.0) ? 1.0 : ((xv < 0.0) ? -1.0 : 0.0);
             tp -= alpha[ph] * xv + sgn * alpha2[ph] * xv * xv;
         }
-        tprime[idx] = tp;
+        if (tprime) tprime[idx] = tp;
         const double2 v = make_double2(cosh(dtau * tp), sinh(dtau * tp));
-        cs[idx] = v;
+        if (cs) cs[idx] = v;
         if (sq_tab) sq_tab[tau * Nb + sq_slot[col]] = v;   // tile layout [tau][dir][site] of ssh_square.cu
     }
 }
@@ -392,6 +395,21 @@ void elph_launch_update_model(elph_handle* h) {
                                                        h->d_col_bond, h->d_cs, h->d_tprime, h->ssq.enabled ? h->ssq.d_slot : nullptr,
                                                        h->ssq.enabled ? h->ssq.d_tab : nullptr, h->Nb, h->Nph, n, h->dtau);
     }
+    ELPH_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+// update_model! (src/SSHModels.jl:510-540) for nrep independent phonon fields at once, written straight into per-replica tables
+// in the tile layout [tau][dir][site] that ssh_square_kernel stages with TMA
+void elph_launch_ssh_replica_tables(elph_handle* h, int64_t nrep, const double* x_dev, int64_t x_stride, double2* tab_dev,
+                                    int64_t tab_stride) {
+    ELPH_REQUIRE(h->model == ELPH_MODEL_SSH && h->ssq.enabled, ELPH_ERR_UNSUPPORTED,
+                 "replica tables need the SSH model on a periodic square lattice (register-tile kernel)");
+    const int T = 256;
+    const long long n = (long long)h->L * h->Nb;
+    dim3 grid((unsigned)std::min<long long>((n + T - 1) / T, 8LL * h->sm_count), (unsigned)nrep);
+    ssh_update_kernel<<<grid, T, 0, h->stream>>>(x_dev, h->d_t, h->d_alpha, h->d_alpha2, h->d_col_ph, h->d_col_bond, nullptr, nullptr,
+                                                 h->ssq.d_slot, tab_dev, h->Nb, h->Nph, n, h->dtau, x_stride, tab_stride);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }

@@ -73,6 +73,71 @@ __device__ __forceinline__ void g3_y_odd(Tile<NSEG, PY>& t, double c, double s, 
     }
 }
 
+// ---- "tanh form" of the same colour groups --------------------------------------------------------------------------------
+// A bond rotation (a, b) -> (c a + s b, s a + c b) equals c * (a + t b, b + t a) with t = s / c.  With one (c, s) per colour
+// the four factors c commute with everything: K = (c0 c1 c2 c3) * prod_g (1 + t_g X_g), X_g = the pair swap of colour g.
+// Latency-bound callers (the Chebyshev chains of the KPM preconditioner) fold the constant into a diagonal they multiply
+// with anyway, and a colour costs ONE fused multiply-add per site instead of a multiply and a multiply-add.
+template <int NSEG, int PY>
+__device__ __forceinline__ void g0_x_even_t(Tile<NSEG, PY>& t, double th) {
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double o = __shfl_xor_sync(0xffffffffu, t.a[r][q], 1);
+            t.a[r][q] = fma(th, o, t.a[r][q]);
+        }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g1_x_odd_t(Tile<NSEG, PY>& t, double th, int lane) {
+    const int partner = (lane & 1) ? ((lane + 1) & 31) : ((lane + 31) & 31);
+#pragma unroll
+    for (int r = 0; r < PY; ++r) {
+        double o[NSEG];
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            double send = t.a[r][q];
+            if (NSEG > 1) {
+                const double nxt = t.a[r][(q + 1) % NSEG], prv = t.a[r][(q + NSEG - 1) % NSEG];
+                send = (lane == 0) ? nxt : ((lane == 31) ? prv : send);
+            }
+            o[q] = __shfl_sync(0xffffffffu, send, partner);
+        }
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) t.a[r][q] = fma(th, o[q], t.a[r][q]);
+    }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g2_y_even_t(Tile<NSEG, PY>& t, double th) {
+#pragma unroll
+    for (int r = 0; r < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = fma(th, t2, t1);
+            t.a[r + 1][q] = fma(th, t1, t2);
+        }
+}
+
+template <int NSEG, int PY>
+__device__ __forceinline__ void g3_y_odd_t(Tile<NSEG, PY>& t, double th, const double (&above)[NSEG], const double (&below)[NSEG]) {
+#pragma unroll
+    for (int r = 1; r + 1 < PY; r += 2)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
+            t.a[r][q] = fma(th, t2, t1);
+            t.a[r + 1][q] = fma(th, t1, t2);
+        }
+#pragma unroll
+    for (int q = 0; q < NSEG; ++q) {
+        t.a[0][q] = fma(th, above[q], t.a[0][q]);
+        t.a[PY - 1][q] = fma(th, below[q], t.a[PY - 1][q]);
+    }
+}
+
 // real tile: publish the edge rows, one barrier, fetch the neighbours' edge rows.  strip: [nwarps][2][LX].
 template <int NSEG, int PY>
 __device__ __forceinline__ void exchange_edges1(const Tile<NSEG, PY>& t, double* strip, int warp, int nwarps, int lane,

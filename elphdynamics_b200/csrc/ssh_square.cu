@@ -31,7 +31,7 @@ struct SshParams {
     double* __restrict__ partial;
     CgScalars* S;
     unsigned int* ticket;
-    long long v_stride, y_stride;
+    long long v_stride, y_stride, tab_stride;   // tab_stride != 0: one table per blockIdx.y (independent replicas)
     int L, Ly, C;
 };
 
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(MAXT) ssh_square_kernel(SshParams P) {
     }
     const double* __restrict__ vin = FUSEP ? P.pr : P.v + (size_t)blockIdx.y * P.v_stride;
     double* __restrict__ y = P.y + (size_t)blockIdx.y * P.y_stride;
+    const double2* __restrict__ tab = P.tab + (size_t)blockIdx.y * P.tab_stride;
 
     double* stage_base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * STAGES * STAGE_DBL;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * STAGES * STAGE_BYTES) + warp * STAGES;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(MAXT) ssh_square_kernel(SshParams P) {
             const size_t g = (size_t)tau * N + tile_off;
             bulk_g2s(dst, vin + g, TILE * sizeof(double), &bars[st]);
             if (FUSEP) bulk_g2s(dst + TILE, P.pold + g, TILE * sizeof(double), &bars[st]);
-            const double2* tx = P.tab + (size_t)tau * 2 * N;
+            const double2* tx = tab + (size_t)tau * 2 * N;
             const double2* ty = tx + N;
             double* dtx = dst + NV * TILE;
             double* dty = dtx + 2 * TILE;
@@ -268,7 +269,8 @@ bool elph_launch_ssh_square(elph_handle* h, const MatvecArgs& a) {
     const int nwarps = Ly / PY;
     if (nwarps > 32 || nwarps < 2) return false;
     SshParams P;
-    P.v = a.v; P.y = a.y; P.Dmu = h->d_D; P.tab = h->ssq.d_tab;
+    P.v = a.v; P.y = a.y; P.Dmu = h->d_D; P.tab = a.ssh_tab ? a.ssh_tab : h->ssq.d_tab;
+    P.tab_stride = a.ssh_tab ? a.ssh_tab_stride : 0;
     P.pr = a.cg_pr; P.pold = a.cg_pold; P.pnew = a.cg_pnew; P.partial = a.partial_dot; P.S = a.cg_S; P.ticket = a.cg_ticket;
     P.v_stride = a.v_stride; P.y_stride = a.y_stride;
     P.L = h->L; P.Ly = Ly;

@@ -307,6 +307,15 @@ int32_t elph_dev_mulMT(elph_handle* h, const double* v_dev, double* y_dev);
  * scale-out is independent runs distinguished by `id` (src/ElPhDynamics.jl:90-95). */
 int32_t elph_dev_mulMTM_replicas(elph_handle* h, int64_t nrep, const double* expnV_dev, int64_t expnV_stride,
                                  const double* v_dev, double* y_dev, int64_t vec_stride);
+/* The same for the SSH model on periodic square lattices (config C).  A replica's operator is its (cosh, sinh)(dtau t') table
+ * (update_model!, src/SSHModels.jl:510-540; sweeps :581-701): elph_dev_ssh_replica_tables evaluates it for nrep phonon
+ * fields x_dev + r*x_stride (engine layout [tau][phonon]) into tab_dev + r*tab_stride, 4*Ltau*Nsites doubles per replica in
+ * the engine's tile layout [tau][direction][site](cosh, sinh); elph_dev_mulMTM_replicas_ssh applies M^T M of every replica to
+ * its own vector (48 B per lattice point of compulsory traffic).  Strides in doubles, pointers 16-byte aligned. */
+int32_t elph_dev_ssh_replica_tables(elph_handle* h, int64_t nrep, const double* x_dev, int64_t x_stride, double* tab_dev,
+                                    int64_t tab_stride);
+int32_t elph_dev_mulMTM_replicas_ssh(elph_handle* h, int64_t nrep, const double* tab_dev, int64_t tab_stride,
+                                     const double* v_dev, double* y_dev, int64_t vec_stride);
 /* ---- tau-sharding across GPUs: one handle per rank, created with Ltau = the rank's slab length.
  * elph_set_shard tells it which global slices it owns (tau0 .. tau0+Ltau-1 of Lglob) so that the antiperiodic sign
  * lands on GLOBAL slice 0; expnV is re-homed with one halo slice on each side ([halo_lo][own...][halo_hi], own start =

@@ -22,6 +22,7 @@ fa = E.FourierAccelerator(em)
 E.update_Q_(fa, em, 0.0, 10.0, 1.0)
 v = torch.randn(n, dtype=torch.float64, device="cuda")
 y = torch.empty_like(v)
+nu = torch.empty(2 * n, dtype=torch.float64, device="cuda")
 
 
 def timeit(fn, iters=200, warm=20):
@@ -75,3 +76,24 @@ for py in (2, 4, 8):
     lib.elph_set_tuning(h, 2, py)
     print(f"KPM apply py={py}: {timeit(lambda: lib.elph_dev_kpm_apply(h, v.data_ptr(), y.data_ptr())):8.2f} us")
 lib.elph_set_tuning(h, 2, 0)
+for fast in (0, 1):
+    lib.elph_set_tuning(h, 16, fast)
+    print(f"KPM apply tanh-form sweeps={fast}: {timeit(lambda: lib.elph_dev_kpm_apply(h, v.data_ptr(), y.data_ptr())):8.2f} us")
+    yy = y.clone()
+    if fast == 0:
+        y0 = yy
+    else:
+        print("   relative difference between the two forms:", float((yy - y0).norm() / y0.norm()))
+
+# where the chain kernel spends its cycles (cluster of the longest polynomial)
+lib.elph_set_tuning(h, 16, 1)
+lib.elph_set_tuning(h, 12, 1)
+lib.elph_dev_kpm_apply(h, v.data_ptr(), y.data_ptr())
+buf = (C.c_ulonglong * 16)()
+lib.elph_debug_pipe_prof.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+lib.elph_debug_pipe_prof(h, 2, buf)
+for cta in range(2):
+    t = [buf[8 * cta + k] for k in range(7)]
+    print("chain CTA", cta, "cycles: load", t[1] - t[0], "poly1", t[2] - t[1], "swap", t[3] - t[2], "poly2", t[4] - t[3], "swap", t[5] - t[4],
+          "store", t[6] - t[5], "| per sweep", (t[2] - t[1]) / (info.max_order - 1), (t[4] - t[3]) / (info.max_order - 1))
+lib.elph_set_tuning(h, 12, 0)
