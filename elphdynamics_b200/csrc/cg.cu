@@ -238,6 +238,16 @@ void elph_cg_device(elph_handle* h, const double* b_dev, double* x_dev, bool use
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
     double* zprec = h->d_res;  // z = P^-1 r lives in the residual scratch during a preconditioned solve
+    // Preconditioned solve on a 32-wide square lattice: the whole loop, preconditioner included, is ONE persistent kernel
+    // (pcg_fused.cu) -- four grid barriers per iteration instead of four launches.
+    if (precond && elph_pcg_fused(h, x_dev, zprec)) {
+        ELPH_CUDA(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
+        ELPH_CUDA(cudaStreamSynchronize(st));
+        ELPH_REQUIRE(h->h_cg->done == 1, ELPH_ERR_STATE, "fused preconditioned CG: a grid barrier timed out");
+        if (iters) *iters = h->h_cg->iter;
+        if (eps) *eps = h->h_cg->eps;
+        return;
+    }
     if (precond) {
         elph_kpm_apply_dev(h, h->d_r, zprec);
         cg_rz_kernel<<<vb, kT, 0, st>>>(h->d_r, zprec, n, h->d_partial, h->d_cg, h->d_ticket);

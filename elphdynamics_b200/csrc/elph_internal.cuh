@@ -141,6 +141,8 @@ struct elph_handle {
     double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool kpm_exclusive = true; // KPM apply: one chain CTA per SM (shared-memory request padded)
+    bool pcg_half_fft = true;   // fused PCG: tau-FFTs at length L/2 for even L (tuning key 18)
+    bool pcg_persistent = true; // KPM-preconditioned CG as one persistent kernel where served (pcg_fused.cu, tuning key 17)
     bool kpm_fast = true;      // KPM apply: sweeps in tanh form with folded constants (tuning key 16)
     bool use_persistent = true;  // unpreconditioned CG as one cooperative persistent kernel (cg_persistent.cu)
     int cg_single_reduction = -1;  // unpreconditioned CG, Holstein square: one barrier per iteration (cg_p2p.cu); -1 = auto
@@ -326,6 +328,7 @@ struct MatvecArgs {
 
 void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a);
 void elph_launch_update_model(elph_handle* h);
+bool elph_pcg_fused(elph_handle* h, double* x_dev, double* z_dev);   // pcg_fused.cu
 void elph_launch_ssh_replica_tables(elph_handle* h, int64_t nrep, const double* x_dev, int64_t x_stride, double2* tab_dev, int64_t tab_stride);
 void elph_detect_square(elph_handle* h, const std::vector<double2>& cs);
 bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a);

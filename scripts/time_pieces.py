@@ -63,7 +63,8 @@ for label, keys in (("persistent", {5: 1}), ("graph", {5: 0, 3: 1}), ("launches"
     print(f"CG {label:10s}: {it.value} iters, {dt*1e3:.3f} ms, {dt/it.value*1e6:.2f} us/iter")
 lib.elph_set_tuning(h, 5, 1)
 lib.elph_set_tuning(h, 3, 1)
-for label, usep in (("PCG", 1),):
+for label, usep in (("PCG launches per phase", 1), ("PCG one persistent kernel", 1)):
+    lib.elph_set_tuning(h, 17, 1 if "persistent" in label else 0)
     for rep in range(3):
         x_dev.zero_()
         torch.cuda.synchronize()
@@ -96,4 +97,19 @@ for cta in range(2):
     t = [buf[8 * cta + k] for k in range(7)]
     print("chain CTA", cta, "cycles: load", t[1] - t[0], "poly1", t[2] - t[1], "swap", t[3] - t[2], "poly2", t[4] - t[3], "swap", t[5] - t[4],
           "store", t[6] - t[5], "| per sweep", (t[2] - t[1]) / (info.max_order - 1), (t[4] - t[3]) / (info.max_order - 1))
+lib.elph_set_tuning(h, 12, 0)
+
+# phases of the fused PCG kernel (CTA 0..3): cycles summed over the iterations
+lib.elph_set_tuning(h, 17, 1)
+lib.elph_set_tuning(h, 12, 1)
+x_dev.zero_()
+lib.elph_dev_cg_solve(h, b_dev.data_ptr(), x_dev.data_ptr(), 1, 0.0, 0, C.byref(it), C.byref(eps))
+torch.cuda.synchronize()
+buf = (C.c_ulonglong * 32)()
+lib.elph_debug_pipe_prof(h, 4, buf)
+names = ["FFT phases", "barriers after FFT phases", "chains", "barrier after chains", "product", "barrier after product"]
+for cta in range(4):
+    print("fused PCG CTA", cta, it.value, "iterations; cycles per iteration:",
+          {nm: round(buf[8 * cta + k] / max(1, it.value)) for k, nm in enumerate(names)},
+          "of which fft_smem fwd/inv", round(buf[8 * cta + 6] / max(1, it.value)), round(buf[8 * cta + 7] / max(1, it.value)))
 lib.elph_set_tuning(h, 12, 0)
