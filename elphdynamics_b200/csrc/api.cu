@@ -1290,6 +1290,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 16: h->kpm_fast = (value != 0); h->kpm_version++; break;
             case 17: h->pcg_persistent = (value != 0); break;
             case 18: h->pcg_half_fft = (value != 0); break;
+            case 19: h->kpm_dev_arnoldi = (value != 0); break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:
                 h->pipe_prof = (value != 0);

@@ -98,6 +98,10 @@ struct KpmState {
     int* d_schedule = nullptr;    // [Lo2]
     size_t d_coeff_cap = 0;
     cplx* d_nu = nullptr;         // [L][N] complex work vector (frequency space)
+    double* d_noise = nullptr;    // [2][N] Arnoldi start vectors (device Arnoldi)
+    double* d_hm = nullptr;       // [2][(n+1) n + 1] Hessenberg matrices + completed steps
+    double* h_hm = nullptr;       // page-locked copy
+    double* d_Q = nullptr;        // Krylov bases when they do not fit in shared memory
 };
 
 // HybridMonteCarlo work vectors (src/HMC.jl:20-279), engine layout, allocated on first use
@@ -141,6 +145,7 @@ struct elph_handle {
     double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool kpm_exclusive = true; // KPM apply: one chain CTA per SM (shared-memory request padded)
+    bool kpm_dev_arnoldi = true; // KPM set-up: Arnoldi eigenvalue bounds on the device (tuning key 19)
     bool pcg_half_fft = true;   // fused PCG: tau-FFTs at length L/2 for even L (tuning key 18)
     bool pcg_persistent = true; // KPM-preconditioned CG as one persistent kernel where served (pcg_fused.cu, tuning key 17)
     bool kpm_fast = true;      // KPM apply: sweeps in tanh form with folded constants (tuning key 16)

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* rin, co
         b0[(size_t)t * SB + site] = v;
     }
     __syncthreads();
-    cplx* res = fft_smem<SB>(b0, b1, plan, tw, mode == 1);
+    cplx* res = fft_smem_auto<SB>(b0, b1, plan, tw, mode == 1);
     if (mode == 0) {
         for (int t = slot; t < L; t += nslots)
             if (ok) cout[(size_t)t * N + gsite] = res[(size_t)t * SB + site];
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kT) fft_kernel(int mode, const double* rin, co
         res[(size_t)t * SB + site] = make_double2(v.x * f, v.y * f);
     }
     __syncthreads();
-    cplx* res2 = fft_smem<SB>(res, other, plan, tw, true);
+    cplx* res2 = fft_smem_auto<SB>(res, other, plan, tw, true);
     for (int t = slot; t < L; t += nslots)
         if (ok) rout[(size_t)t * N + gsite] = res2[(size_t)t * SB + site].x * invL;
 }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kT) hmc_inner_kernel(double* __restrict__ xg, 
             b0[(size_t)t * SB + site] = make_double2(0.0 + d, 0.0);
         }
         __syncthreads();
-        cplx* res = fft_smem<SB>(b0, b1, plan, tw, false);
+        cplx* res = fft_smem_auto<SB>(b0, b1, plan, tw, false);
         cplx* other = (res == b0) ? b1 : b0;
         for (int t = slot; t < L; t += nslots) {
             const double f = fs[(size_t)t * SB + site];
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kT) hmc_inner_kernel(double* __restrict__ xg, 
             res[(size_t)t * SB + site] = make_double2(v.x * f, v.y * f);
         }
         __syncthreads();
-        cplx* res2 = fft_smem<SB>(res, other, plan, tw, true);
+        cplx* res2 = fft_smem_auto<SB>(res, other, plan, tw, true);
         for (int t = slot; t < L; t += nslots) ys[(size_t)t * SB + site] = res2[(size_t)t * SB + site].x * invL;
         // every thread reads back only the ys it wrote; b0 / b1 are rewritten after the next __syncthreads
     };

@@ -15,6 +15,7 @@
 //    polynomial first -> inverse FFT.  In the engine layout the frequency-space vector is [omega][site], so
 //    the reference's two (L,N)<->(N,L) transposes disappear.
 #include "elph_internal.cuh"
+#include "square_tiles.cuh"
 
 #include <future>
 #include <algorithm>
@@ -27,14 +28,36 @@ typedef std::complex<double> zc;
 // host: eigenvalues of a small real upper-Hessenberg matrix (replaces LAPACK eigvals!, :891,:935)
 // Complex single-shift (Wilkinson) QR with Givens rotations and deflation.
 // ------------------------------------------------------------------------------------------------
+// Plain (re, im) arithmetic: std::complex products compile to __muldc3 calls with NaN/Inf recovery, which made the two
+// 20 x 20 problems of a set-up cost 2 x 55 us.  Only eigenvalues are wanted, so every rotation is applied to the active
+// window [lo, hi] alone.
+namespace {
+struct cz {
+    double re, im;
+};
+inline cz operator+(cz a, cz b) { return {a.re + b.re, a.im + b.im}; }
+inline cz operator-(cz a, cz b) { return {a.re - b.re, a.im - b.im}; }
+inline cz operator*(cz a, cz b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+inline cz operator*(double a, cz b) { return {a * b.re, a * b.im}; }
+inline cz conjz(cz a) { return {a.re, -a.im}; }
+inline cz negz(cz a) { return {-a.re, -a.im}; }
+inline double norm2(cz a) { return a.re * a.re + a.im * a.im; }
+inline double absz(cz a) { return std::sqrt(a.re * a.re + a.im * a.im); }   // entries are O(1): no hypot needed
+inline cz sqrtz(cz a) {
+    const zc r = std::sqrt(zc(a.re, a.im));
+    return {r.real(), r.imag()};
+}
+}  // namespace
+
 static std::vector<zc> hessenberg_eigvals(const std::vector<double>& hreal, int n) {
-    std::vector<zc> H((size_t)n * n);
+    std::vector<cz> H((size_t)n * n);
     for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) H[(size_t)i * n + j] = (i <= j + 1) ? zc(hreal[(size_t)i * n + j], 0.0) : zc(0.0, 0.0);
-    auto at = [&](int i, int j) -> zc& { return H[(size_t)i * n + j]; };
+        for (int j = 0; j < n; ++j) H[(size_t)i * n + j] = cz{(i <= j + 1) ? hreal[(size_t)i * n + j] : 0.0, 0.0};
+    auto at = [&](int i, int j) -> cz& { return H[(size_t)i * n + j]; };
     std::vector<zc> ev(n);
+    std::vector<cz> cs(n), sn(n);
     double hnorm = 0.0;
-    for (auto& z : H) hnorm += std::norm(z);
+    for (auto& z : H) hnorm += norm2(z);
     hnorm = std::sqrt(hnorm);
     if (hnorm == 0.0) hnorm = 1.0;
     const double eps = 2.220446049250313e-16;
@@ -42,68 +65,67 @@ static std::vector<zc> hessenberg_eigvals(const std::vector<double>& hreal, int 
     int iter = 0;
     while (hi >= 0) {
         if (hi == 0) {
-            ev[0] = at(0, 0);
+            ev[0] = zc(at(0, 0).re, at(0, 0).im);
             break;
         }
         // look for a negligible sub-diagonal entry
         int lo = hi;
         while (lo > 0) {
-            double s = std::abs(at(lo - 1, lo - 1)) + std::abs(at(lo, lo));
+            double s = absz(at(lo - 1, lo - 1)) + absz(at(lo, lo));
             if (s == 0.0) s = hnorm;
-            if (std::abs(at(lo, lo - 1)) <= eps * s) {
-                at(lo, lo - 1) = 0.0;
+            if (absz(at(lo, lo - 1)) <= eps * s) {
+                at(lo, lo - 1) = cz{0.0, 0.0};
                 break;
             }
             --lo;
         }
         if (lo == hi) {
-            ev[hi] = at(hi, hi);
+            ev[hi] = zc(at(hi, hi).re, at(hi, hi).im);
             --hi;
             iter = 0;
             continue;
         }
         // Wilkinson shift from the trailing 2x2 block
-        zc a = at(hi - 1, hi - 1), b = at(hi - 1, hi), c = at(hi, hi - 1), d = at(hi, hi);
-        zc tr = a + d, det = a * d - b * c;
-        zc disc = std::sqrt(tr * tr - 4.0 * det);
-        zc l1 = 0.5 * (tr + disc), l2 = 0.5 * (tr - disc);
-        zc mu = (std::abs(l1 - d) < std::abs(l2 - d)) ? l1 : l2;
+        const cz a = at(hi - 1, hi - 1), b = at(hi - 1, hi), c = at(hi, hi - 1), d = at(hi, hi);
+        const cz tr = a + d, det = a * d - b * c;
+        const cz disc = sqrtz(tr * tr - 4.0 * det);
+        const cz l1 = 0.5 * (tr + disc), l2 = 0.5 * (tr - disc);
+        cz mu = (absz(l1 - d) < absz(l2 - d)) ? l1 : l2;
         ++iter;
-        if (iter % 11 == 10) mu = zc(std::abs(at(hi, hi - 1)) + std::abs(at(hi - 1, hi - 2 >= lo ? hi - 2 : lo)), 0.0);  // exceptional shift
+        if (iter % 11 == 10) mu = cz{absz(at(hi, hi - 1)) + absz(at(hi - 1, hi - 2 >= lo ? hi - 2 : lo)), 0.0};  // exceptional shift
         if (iter > 30 * n + 300) break;  // give up (values so far are returned; caller treats NaN as inactive)
         // QR step on the active block [lo, hi]
-        std::vector<zc> cs(hi - lo), sn(hi - lo);
-        for (int k = lo; k <= hi; ++k) at(k, k) -= mu;
+        for (int k = lo; k <= hi; ++k) at(k, k) = at(k, k) - mu;
         for (int k = lo; k < hi; ++k) {
-            zc x = at(k, k), y = at(k + 1, k);
-            double r = std::sqrt(std::norm(x) + std::norm(y));
-            zc cc, ss;
+            const cz x = at(k, k), y = at(k + 1, k);
+            const double r = std::sqrt(norm2(x) + norm2(y));
+            cz cc, ss;
             if (r == 0.0) {
-                cc = 1.0;
-                ss = 0.0;
+                cc = cz{1.0, 0.0};
+                ss = cz{0.0, 0.0};
             } else {
-                cc = x / r;
-                ss = y / r;
+                cc = (1.0 / r) * x;
+                ss = (1.0 / r) * y;
             }
             cs[k - lo] = cc;
             sn[k - lo] = ss;
             // rows k, k+1:  [ conj(c) conj(s); -s c ]
-            for (int j = k; j < n; ++j) {
-                zc t1 = at(k, j), t2 = at(k + 1, j);
-                at(k, j) = std::conj(cc) * t1 + std::conj(ss) * t2;
-                at(k + 1, j) = -ss * t1 + cc * t2;
+            for (int j = k; j <= hi; ++j) {
+                const cz t1 = at(k, j), t2 = at(k + 1, j);
+                at(k, j) = conjz(cc) * t1 + conjz(ss) * t2;
+                at(k + 1, j) = cc * t2 - ss * t1;
             }
         }
         for (int k = lo; k < hi; ++k) {
-            zc cc = cs[k - lo], ss = sn[k - lo];
+            const cz cc = cs[k - lo], ss = sn[k - lo];
             const int top = std::min(k + 2, hi);
-            for (int i = 0; i <= top; ++i) {
-                zc t1 = at(i, k), t2 = at(i, k + 1);
+            for (int i = lo; i <= top; ++i) {
+                const cz t1 = at(i, k), t2 = at(i, k + 1);
                 at(i, k) = t1 * cc + t2 * ss;
-                at(i, k + 1) = -t1 * std::conj(ss) + t2 * std::conj(cc);
+                at(i, k + 1) = t2 * conjz(cc) - t1 * conjz(ss);
             }
         }
-        for (int k = lo; k <= hi; ++k) at(k, k) += mu;
+        for (int k = lo; k <= hi; ++k) at(k, k) = at(k, k) + mu;
     }
     return ev;
 }
@@ -195,6 +217,20 @@ static double host_arnoldi(const elph_handle* h, const KpmState& K, const double
     return mx;
 }
 
+// largest real part of the eigenvalues of the leading l x l block of the Arnoldi Hessenberg matrix (leading dimension n)
+static double hessenberg_bound(const double* hm, int n, int l) {
+    std::vector<double> hh((size_t)l * l);
+    for (int i = 0; i < l; ++i)
+        for (int j = 0; j < l; ++j) {
+            hh[(size_t)i * l + j] = hm[(size_t)i * n + j];
+            if (!std::isfinite(hh[(size_t)i * l + j])) return INFINITY;
+        }
+    std::vector<zc> ev = hessenberg_eigvals(hh, l);
+    double mx = -INFINITY;
+    for (auto& e : ev) mx = std::max(mx, e.real());
+    return mx;
+}
+
 // kpm_coefficients! (:789-839): c_0 = S_0/(2M), c_m = 2 S_m/(2M), S_m = sum_n f(x_n) cos(pi m (n+1/2)/(2M))
 static void host_kpm_coefficients(zc* c, int order, double lam_lo, double lam_hi, double phi) {
     const int M = order, NM = 2 * M;
@@ -239,6 +275,237 @@ __global__ void taumean2_kernel(const double2* __restrict__ tab, double2* __rest
         ss += v.y;
     }
     out[i] = make_double2(sc / (double)L, ss / (double)L);
+}
+
+// arnoldi_eigenvalue_bounds! (src/KPMPreconditioners.jl:845-942) on the device: blockIdx.x = 0 runs the Krylov iteration on A
+// (e_max), 1 on A^-1 (1/e_min).  Output per run: the (n+1) x n Hessenberg matrix (row-major, leading dimension n) and the
+// number of completed steps; the 20 x 20 eigenvalue problem stays on the host.
+//
+// Latency is everything here (two CTAs, one dependent chain each).  Measured on B200 with the reference's loop structure
+// (modified Gram-Schmidt: k+1 dependent block reductions in step k; products through the bond list): 1100 cycles per
+// reduction and 5300 per product, 190 us per kernel -- no better than the host loops it replaced.  Hence:
+//   * a thread keeps its EPT elements of the current vector in registers for the whole iteration;
+//   * orthogonalisation = classical Gram-Schmidt, applied twice: all k+1 dots of a pass are formed at once and folded by ONE
+//     block reduction, h(j,k) = the sum of the two passes.  Same Krylov space, same projected matrix in exact arithmetic and
+//     orthogonality at rounding level like the modified form (Giraud et al. 2005, "twice is enough"); the eigenvalue bounds
+//     agree with the sequential form to ~1e-10 and only enter through isapprox(rtol = buf) and floor() of the orders;
+//   * on periodic square lattices the products are register-tile sweeps (square_tiles.cuh), otherwise bond-list sweeps on a
+//     copy in shared memory.
+struct ArnoldiParams {
+    const double* __restrict__ eVbar;
+    const double2* __restrict__ csbar;
+    const int2* __restrict__ bonds;
+    const int* __restrict__ goff;
+    const double* __restrict__ start;   // [2][N]
+    double* Qg;                         // [2][n+1][N] when the basis is kept in global memory
+    double* hm;                         // [2][(n+1) * n + 1]
+    int ngroups, N, n, q_in_smem, Ly;
+    double c[4], s[4];                  // square lattices: (cosh, sinh) per colour
+    unsigned long long* prof;
+};
+
+constexpr int kArnMaxN = 32;            // Krylov steps the kernel is sized for (the reference default is 20)
+constexpr int kArnWarps = 8;            // at most 8 warps per CTA
+constexpr int kArnStride = kArnMaxN + 4;   // partial sums per warp: one per basis vector, padded to whole chunks of four
+
+// fold nval per-thread values over the block: every thread receives the nval sums (same bits everywhere) in out[]
+template <int MAXV>
+__device__ __forceinline__ void arnoldi_block_sums(double (&val)[MAXV], int nval, double* red, int& rbuf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j)
+        if (j < nval) {
+            double x = val[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            val[j] = x;
+        }
+    double* mine = red + (size_t)rbuf * 32 * MAXV;
+    rbuf ^= 1;
+    if (lane == 0)
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j)
+            if (j < nval) mine[warp * MAXV + j] = val[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j)
+        if (j < nval) {
+            double t = 0.0;
+            for (int w = 0; w < nw; ++w) t += mine[w * MAXV + j];
+            val[j] = t;
+        }
+}
+
+// QSMEM: the Krylov basis lives in shared memory (addressed as such: generic loads of it were what the first versions waited for)
+template <int EPT, bool SQUARE, bool QSMEM>
+__global__ void __launch_bounds__(256) arnoldi_kernel(ArnoldiParams P) {
+    extern __shared__ __align__(16) double sm[];
+    const int N = P.N, n = P.n, T = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
+    const bool inverse = (blockIdx.x == 1);
+    // shared memory: [reduction buffers 2 x kArnWarps x kArnStride] [vs: N (bond-list sweeps) or edge strips (tiles)] [Q: n + 4 rows]
+    double* red = sm;
+    double* vs = red + 2 * kArnWarps * kArnStride;
+    double* Qs = vs + (SQUARE ? 2 * nwarps * 2 * 32 : N);
+    double* Q = QSMEM ? Qs : P.Qg + (size_t)blockIdx.x * (n + 4) * N;   // [n+4][N], rows beyond the current basis are zero
+    // two matrices per run: the coefficients of the first and of the second orthogonalisation pass (the host adds them)
+    const size_t hstride = (size_t)(n + 1) * n + 1;
+    double* hm = P.hm + (size_t)blockIdx.x * 2 * hstride;
+    const double* start = P.start + (size_t)blockIdx.x * N;
+    __shared__ double red1[64];
+    int rbuf = 0, rbuf1 = 0, xbuf = 0;
+    for (int i = threadIdx.x; i < 2 * (int)hstride; i += T) hm[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * kArnWarps * kArnStride; i += T) red[i] = 0.0;
+    for (int i = threadIdx.x; i < (n + 4) * N; i += T) Q[i] = 0.0;
+    __syncthreads();
+    // element e of this thread: square lattices: site (EPT * warp + e, lane) -- a register tile; otherwise tid + e * T
+    auto idx = [&](int e) { return SQUARE ? (EPT * warp + e) * 32 + lane : (int)threadIdx.x + e * T; };
+    double v[EPT], ev[EPT];
+    double one[1];
+    one[0] = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = idx(e);
+        v[e] = (i < N) ? start[i] : 0.0;
+        ev[e] = (i < N) ? P.eVbar[i] : 1.0;
+        if (inverse) ev[e] = 1.0 / ev[e];            // A^-1 multiplies by 1/eVbar: one division per element and kernel, not per step
+        one[0] = fma(v[e], v[e], one[0]);
+    }
+    arnoldi_block_sums<1>(one, 1, red1, rbuf1);
+    const double rnb = 1.0 / sqrt(one[0]);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = idx(e);
+        v[e] *= rnb;                                  // v = q_0
+        if (i < N) Q[i] = v[e];
+    }
+    int l = n;
+    long long c_mul = 0, c_gs = 0, c_t = clock64();
+    for (int k = 0; k < n; ++k) {
+        // v holds q_k.  v = A q_k (A = K diag(eVbar)) or A^-1 q_k
+        if (SQUARE) {
+            sqt::Tile<1, EPT> t;
+            double ab[1], be[1];
+            if (!inverse) {   // checkerboard_mul!: colours in order (src/Checkerboard.jl:123-141)
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) t.a[e][0] = ev[e] * v[e];
+                sqt::g0_x_even(t, P.c[0], P.s[0]);
+                sqt::g1_x_odd(t, P.c[1], P.s[1], lane);
+                sqt::g2_y_even(t, P.c[2], P.s[2]);
+                sqt::exchange_edges1(t, vs + (size_t)xbuf * nwarps * 2 * 32, warp, nwarps, lane, ab, be);
+                xbuf ^= 1;
+                sqt::g3_y_odd(t, P.c[3], P.s[3], ab, be);
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) v[e] = t.a[e][0];
+            } else {          // checkerboard_inverse_mul!: reverse order, sinh -> -sinh (src/Checkerboard.jl:298-316), then 1/eVbar
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) t.a[e][0] = v[e];
+                sqt::exchange_edges1(t, vs + (size_t)xbuf * nwarps * 2 * 32, warp, nwarps, lane, ab, be);
+                xbuf ^= 1;
+                sqt::g3_y_odd(t, P.c[3], -P.s[3], ab, be);
+                sqt::g2_y_even(t, P.c[2], -P.s[2]);
+                sqt::g1_x_odd(t, P.c[1], -P.s[1], lane);
+                sqt::g0_x_even(t, P.c[0], -P.s[0]);
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) v[e] = t.a[e][0] * ev[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = idx(e);
+                if (i < N) vs[i] = inverse ? v[e] : ev[e] * v[e];
+            }
+            __syncthreads();
+            for (int gg = 0; gg < P.ngroups; ++gg) {
+                const int g = inverse ? P.ngroups - 1 - gg : gg;
+                for (int b = P.goff[g] + threadIdx.x; b < P.goff[g + 1]; b += T) {
+                    const int2 ij = P.bonds[b];
+                    const double2 cs = P.csbar[b];
+                    const double sn = inverse ? -cs.y : cs.y;
+                    const double t1 = vs[ij.x], t2 = vs[ij.y];
+                    vs[ij.x] = cs.x * t1 + sn * t2;
+                    vs[ij.y] = cs.x * t2 + sn * t1;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = idx(e);
+                v[e] = (i < N) ? (inverse ? vs[i] * ev[e] : vs[i]) : 0.0;
+            }
+        }
+        { const long long t = clock64(); c_mul += t - c_t; c_t = t; }
+        // two passes of classical Gram-Schmidt against q_0 .. q_k
+        // Chunks of four basis vectors, branch-free: the basis has n + 4 rows and the rows that are not written yet are zero, so
+        // a chunk that runs past q_k computes zeros; the partial sums of at most kArnWarps warps are folded with a fixed
+        // trip count (unused slots stay zero).  (A fully unrolled, predicated 33-wide body cost 25 k cycles per step in
+        // instruction issue alone; predicated chunks serialised the four dots.)
+        for (int pass = 0; pass < 2; ++pass) {
+            double* mine = red + (size_t)rbuf * kArnWarps * kArnStride;
+            rbuf ^= 1;
+            for (int j0 = 0; j0 <= k; j0 += 4) {
+                double d[4] = {0.0, 0.0, 0.0, 0.0}, d2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const double* Qj = Q + (size_t)(j0 + jj) * N;
+#pragma unroll
+                    for (int e = 0; e < EPT; e += 2) {
+                        const int i0 = idx(e), i1 = idx(e + 1);
+                        if (SQUARE || i0 < N) d[jj] = fma(Qj[i0], v[e], d[jj]);
+                        if (SQUARE || i1 < N) d2[jj] = fma(Qj[i1], v[e + 1], d2[jj]);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) d[jj] += d2[jj];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) d[jj] += __shfl_xor_sync(0xffffffffu, d[jj], o);
+                if (lane == 0)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) mine[warp * kArnStride + j0 + jj] = d[jj];
+            }
+            __syncthreads();
+            for (int j0 = 0; j0 <= k; j0 += 4) {
+                double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int w = 0; w < kArnWarps; ++w)       // same order in every thread
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) t[jj] += mine[w * kArnStride + j0 + jj];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const double* Qj = Q + (size_t)(j0 + jj) * N;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) {
+                        const int i = idx(e);
+                        if (SQUARE || i < N) v[e] = fma(-t[jj], Qj[i], v[e]);
+                    }
+                    if (threadIdx.x == 0 && j0 + jj <= k) hm[(size_t)pass * hstride + (size_t)(j0 + jj) * n + k] = t[jj];
+                }
+            }
+        }
+        one[0] = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) one[0] = fma(v[e], v[e], one[0]);
+        arnoldi_block_sums<1>(one, 1, red1, rbuf1);
+        const double nv = sqrt(one[0]);
+        if (threadIdx.x == 0) hm[(size_t)(k + 1) * n + k] = nv;
+        if (!(nv > 1e-12)) {
+            l = k + 1;
+            break;
+        }
+        double* Qn = Q + (size_t)(k + 1) * N;
+        const double rnv = 1.0 / nv;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = idx(e);
+            v[e] *= rnv;
+            if (i < N) Qn[i] = v[e];      // read back by the same thread only
+        }
+        { const long long t = clock64(); c_gs += t - c_t; c_t = t; }
+    }
+    if (threadIdx.x == 0) hm[hstride - 1] = (double)l;
+    if (threadIdx.x == 0 && P.prof) { P.prof[2 * blockIdx.x] = c_mul; P.prof[2 * blockIdx.x + 1] = c_gs; }
 }
 
 struct KpmParams {
@@ -398,6 +665,10 @@ void elph_kpm_free(elph_handle* h) {
     cudaFree(K.d_coeff_off);
     cudaFree(K.d_schedule);
     cudaFree(K.d_nu);
+    cudaFree(K.d_noise);
+    cudaFree(K.d_hm);
+    cudaFree(K.d_Q);
+    if (K.h_hm) cudaFreeHost(K.h_hm);
     K = KpmState();
 }
 
@@ -407,6 +678,7 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
     ELPH_REQUIRE(noise != nullptr, ELPH_ERR_INVALID, "arnoldi_noise must provide 2*Nsites values");
     const int N = h->N, L = h->L, Nb = h->Nb, T = 256;
     // update_A!
+    const bool dev = h->kpm_dev_arnoldi && K.n <= 32 && (N <= 8192);
     if (h->model == ELPH_MODEL_HOLSTEIN) {
         taumean_kernel<<<(N + T - 1) / T, T, 0, h->stream>>>(h->d_D, K.d_eVbar, N, L);
         ELPH_CUDA(cudaGetLastError());
@@ -418,8 +690,10 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
             for (int b = 0; b < Nb; ++b) { K.cbar[b] = cs[b].x; K.sbar[b] = cs[b].y; }
             ELPH_CUDA(cudaMemcpyAsync(K.d_csbar, h->d_cs, Nb * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
         }
-        ELPH_CUDA(cudaMemcpyAsync(K.eVbar.data(), K.d_eVbar, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        if (!dev) {
+            ELPH_CUDA(cudaMemcpyAsync(K.eVbar.data(), K.d_eVbar, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        }
     } else {
         if (Nb > 0) {
             taumean2_kernel<<<(Nb + T - 1) / T, T, 0, h->stream>>>(h->d_cs, K.d_csbar, Nb, L);
@@ -427,17 +701,80 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
             h->launches++;
         }
         ELPH_CUDA(cudaMemcpyAsync(K.d_eVbar, h->d_D, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        std::vector<double2> cs(Nb);
-        ELPH_CUDA(cudaMemcpyAsync(cs.data(), K.d_csbar, Nb * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-        ELPH_CUDA(cudaMemcpyAsync(K.eVbar.data(), K.d_eVbar, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        ELPH_CUDA(cudaStreamSynchronize(h->stream));
-        for (int b = 0; b < Nb; ++b) { K.cbar[b] = cs[b].x; K.sbar[b] = cs[b].y; }
+        if (!dev) {
+            std::vector<double2> cs(Nb);
+            ELPH_CUDA(cudaMemcpyAsync(cs.data(), K.d_csbar, Nb * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+            ELPH_CUDA(cudaMemcpyAsync(K.eVbar.data(), K.d_eVbar, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            ELPH_CUDA(cudaStreamSynchronize(h->stream));
+            for (int b = 0; b < Nb; ++b) { K.cbar[b] = cs[b].x; K.sbar[b] = cs[b].y; }
+        }
     }
+    elph_trace_mark(h, "  kpm: tau-mean");
     // Arnoldi bounds
-    // the two Krylov runs (on A for e_max, on A^-1 for e_min) are independent: second host thread for the inverse one
-    auto inv_run = std::async(std::launch::async, [&]() { return host_arnoldi(h, K, noise + N, true); });
-    const double e_max = host_arnoldi(h, K, noise, false);
-    const double inv_max = inv_run.get();
+    double e_max, inv_max;
+    if (dev) {
+        // both Krylov runs in one launch (arnoldi_kernel): only the two small Hessenberg matrices come back
+        const int n = K.n;
+        const size_t hstride = (size_t)(n + 1) * n + 1;
+        if (!K.d_noise) {
+            K.d_noise = elph_dalloc<double>(2 * (size_t)N);
+            K.d_hm = elph_dalloc<double>(4 * hstride);
+            ELPH_CUDA(cudaMallocHost(&K.h_hm, 4 * hstride * sizeof(double)));
+        }
+        ELPH_CUDA(cudaMemcpyAsync(K.d_noise, noise, 2 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ArnoldiParams A;
+        A.eVbar = K.d_eVbar; A.csbar = K.d_csbar; A.bonds = h->d_bonds; A.goff = h->d_goff; A.start = K.d_noise;
+        A.hm = K.d_hm; A.ngroups = h->ngroups; A.N = N; A.n = n;
+        A.prof = h->pipe_prof ? h->pipe_prof_buf : nullptr;
+        // register tiles on periodic square lattices with one (cosh, sinh) per colour: 32 sites wide, 8 rows per warp
+        const bool square = h->model == ELPH_MODEL_HOLSTEIN && h->sq.enabled && !h->sq_disable && h->sq.Lx == 32 &&
+                            h->sq.Ly % 8 == 0 && h->sq.Ly / 8 <= 8;
+        A.Ly = square ? h->sq.Ly : 0;
+        for (int g = 0; g < 4; ++g) { A.c[g] = square ? h->sq.c[g] : 1.0; A.s[g] = square ? h->sq.s[g] : 0.0; }
+        const int ept = square ? 8 : ((N <= 2048) ? 8 : ((N <= 4096) ? 16 : 32));
+        const int threads = square ? 32 * (h->sq.Ly / 8) : ((N + ept - 1) / ept + 31) / 32 * 32;
+        const size_t fixed = (2ull * kArnWarps * kArnStride + (square ? 2ull * (threads / 32) * 2 * 32 : (size_t)N)) * sizeof(double);
+        size_t smem = fixed + (size_t)(n + 4) * N * sizeof(double);
+        A.q_in_smem = smem <= h->smem_optin ? 1 : 0;
+        if (!A.q_in_smem) {
+            smem = fixed;
+            ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Nsites too large for the Arnoldi kernel");
+            if (!K.d_Q) K.d_Q = elph_dalloc<double>(2 * (size_t)(n + 4) * N);
+        }
+        A.Qg = K.d_Q;
+#define ARN_LAUNCH(E, SQ)                                                                      \
+        do {                                                                                   \
+            if (A.q_in_smem) {                                                                 \
+                elph_enable_smem(h, arnoldi_kernel<E, SQ, true>);                              \
+                arnoldi_kernel<E, SQ, true><<<2, threads, smem, h->stream>>>(A);               \
+            } else {                                                                           \
+                elph_enable_smem(h, arnoldi_kernel<E, SQ, false>);                             \
+                arnoldi_kernel<E, SQ, false><<<2, threads, smem, h->stream>>>(A);              \
+            }                                                                                  \
+        } while (0)
+        if (square) ARN_LAUNCH(8, true);
+        else if (ept == 8) ARN_LAUNCH(8, false);
+        else if (ept == 16) ARN_LAUNCH(16, false);
+        else ARN_LAUNCH(32, false);
+#undef ARN_LAUNCH
+        ELPH_CUDA(cudaGetLastError());
+        h->launches++;
+        ELPH_CUDA(cudaMemcpyAsync(K.h_hm, K.d_hm, 4 * hstride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        ELPH_CUDA(cudaStreamSynchronize(h->stream));
+        elph_trace_mark(h, "  kpm: arnoldi kernel");
+        // h = first-pass + second-pass coefficients (the sub-diagonal norms sit in the first matrix only)
+        for (int run = 0; run < 2; ++run)
+            for (size_t i = 0; i + 1 < hstride; ++i) K.h_hm[2 * run * hstride + i] += K.h_hm[(2 * run + 1) * hstride + i];
+        const int l0 = (int)K.h_hm[hstride - 1], l1 = (int)K.h_hm[3 * hstride - 1];
+        e_max = hessenberg_bound(K.h_hm, n, l0);
+        inv_max = hessenberg_bound(K.h_hm + 2 * hstride, n, l1);
+    } else {
+        // the two Krylov runs (on A for e_max, on A^-1 for e_min) are independent: second host thread for the inverse one
+        auto inv_run = std::async(std::launch::async, [&]() { return host_arnoldi(h, K, noise + N, true); });
+        e_max = host_arnoldi(h, K, noise, false);
+        inv_max = inv_run.get();
+    }
+    elph_trace_mark(h, "  kpm: eigenvalues");
     const double e_min = std::isfinite(inv_max) ? 1.0 / inv_max : -INFINITY;
     K.e_min = e_min;
     K.e_max = e_max;

@@ -101,7 +101,7 @@ __device__ __forceinline__ double grid_sum(double thread_value, double* partial,
 // instruction fetches, not in arithmetic)
 template <int SB>
 __device__ __noinline__ cplx* fft_smem_shared(cplx* x, cplx* y, const FftPlan* plan, const cplx* tw, bool inverse) {
-    return fft_smem<SB>(x, y, *plan, tw, inverse);
+    return fft_smem_auto<SB>(x, y, *plan, tw, inverse);
 }
 
 __device__ __forceinline__ void cluster_sync_all() {

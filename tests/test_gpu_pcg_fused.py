@@ -115,3 +115,28 @@ def test_fused_pcg_maxiter_and_initial_guess(setup):
     solve_pcg(xo, om, b, ConjugateGradient(n, tol=om.tol, maxiter=om.maxiter), Po, maxiter=3)
     assert relerr(np.ascontiguousarray(out[1][0].reshape(om.L, om.N).T).reshape(-1), xo) <= 1e-9
 
+
+
+@pytest.mark.parametrize("geom,Lside", [("square", 32), ("square", 4), ("honeycomb", 6), ("triangular", 5), ("square", 64)])
+def test_device_arnoldi_equals_host_arnoldi(geom, Lside):
+    """arnoldi_eigenvalue_bounds! (src/KPMPreconditioners.jl:845-942): the two Krylov runs as one kernel (tuning key 19, default)
+    against the same loops on the host and against the oracle."""
+    import elphdynamics_b200 as E
+    from oracle.kpm import KPMPreconditioner
+    om, rng = oracle_holstein(geom, Lside, 0.8, 0.1, mu=-0.5)
+    em = engine_holstein_like(om)
+    Pe = E.SymmetricKPMPreconditioner(em)
+    Po = KPMPreconditioner(om)
+    noise = rng.normal(size=2 * om.N)
+    Po.setup(noise)
+    em._call("elph_set_tuning", 19, 0)
+    ih = E.setup_(Pe, noise)
+    em._call("elph_set_tuning", 19, 1)
+    idv = E.setup_(Pe, noise)
+    for a, b in ((ih.e_min, idv.e_min), (ih.e_max, idv.e_max)):
+        assert abs(a - b) <= 1e-9 * abs(a), (a, b)
+    assert abs(idv.e_min - Po.e_min) <= 1e-6 * abs(Po.e_min) and abs(idv.e_max - Po.e_max) <= 1e-6 * abs(Po.e_max)
+    assert bool(idv.active) == Po.active
+    if Po.active:
+        assert np.array_equal(Pe.orders(), Po.order)
+    em.close()
