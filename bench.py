@@ -401,7 +401,29 @@ def main():
         t0 = time.perf_counter()
         itp, resp, flagp = E.ldiv_(xs, em, b, P)
         dt_p = time.perf_counter() - t0
-        extra["pcg_kpm"] = {"iters": itp, "residual": resp, "flag": flagp, "seconds": dt_p}
+        # device-side time of the solve alone (device pointers, no copies, no true-residual check)
+        bdev = torch.from_numpy(np.ascontiguousarray(b.reshape(Nsites, Ltau).T)).reshape(-1).cuda()
+        xdev = torch.zeros(n, dtype=torch.float64, device="cuda")
+        itc, epsc = C.c_int64(), C.c_double()
+        pcg = {}
+        for label, fused in (("one_persistent_kernel", 1), ("launch_per_phase", 0)):
+            lib.elph_set_tuning(em.handle, 17, fused)
+            best = float("inf")
+            for _ in range(3):
+                xdev.zero_()
+                torch.cuda.synchronize()
+                l0 = em.launch_count()
+                t0 = time.perf_counter()
+                lib.elph_dev_cg_solve(em.handle, bdev.data_ptr(), xdev.data_ptr(), 1, 0.0, 0, C.byref(itc), C.byref(epsc))
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+                nl = em.launch_count() - l0
+            pcg[label] = {"iters": int(itc.value), "us_per_iteration": best * 1e6 / max(1, itc.value), "launches_per_solve": int(nl)}
+        lib.elph_set_tuning(em.handle, 17, 1)
+        extra["pcg_kpm"] = {"iters": itp, "residual": resp, "flag": flagp, "seconds": dt_p, **pcg,
+                            "note": "KPM-preconditioned CG: ldiv! with host vectors (seconds), and the solve alone on device vectors as "
+                                    "one persistent cooperative kernel (pcg_fused.cu: FFT / Chebyshev chains / inverse FFT / product "
+                                    "between grid barriers) against four launches per iteration"}
         fa = E.FourierAccelerator(em)
         E.update_Q_(fa, em, 0.0, 10.0, 1.0)
         dyn = E.RungeKuttaDynamics(em, 1e-3)
@@ -430,44 +452,55 @@ def main():
         # handle, stream and host thread (ctypes releases the GIL inside the C ABI), advance concurrently
         try:
             import threading as _th
-            K, nst = 8, 6
-            chains = []
-            for c in range(K):
-                mc, rc = workloads.holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=4321 + c, eps=0.3)
-                fc = E.FourierAccelerator(mc)
-                E.update_Q_(fc, mc, 0.0, 10.0, 1.0)
-                Pc = E.SymmetricKPMPreconditioner(mc)
-                dc = E.RungeKuttaDynamics(mc, 1e-3)
-                nz = [dict(eta=rc.normal(size=n), g1=rc.normal(size=n), g2=rc.normal(size=n),
-                           arnoldi1=rc.normal(size=2 * Nsites), arnoldi2=rc.normal(size=2 * Nsites)) for _ in range(nst + 1)]
-                for z in nz:
-                    for key in ("eta", "g1", "g2"):
-                        mc.pin_host(z[key])
-                chains.append((mc, fc, Pc, dc, nz))
-            its_c = [0] * K
+            nsm = torch.cuda.get_device_properties(local).multi_processor_count
+            chain_results = {}
+            # (chains, one-kernel solve?, CTAs per solve): many chains fill the GPU with the launch-per-phase solve; with the
+            # persistent one-kernel solve every chain takes 1/K of the SMs (tuning key 20) and keeps a much shorter step
+            for K, fused, grid in ((8, 0, 0), (4, 1, (nsm // 4) & ~1)):
+                nst = 6
+                chains = []
+                for c in range(K):
+                    mc, rc = workloads.holstein("square", LSIDE, BETA, DTAU, mu=-1.0, seed=4321 + c, eps=0.3)
+                    fc = E.FourierAccelerator(mc)
+                    E.update_Q_(fc, mc, 0.0, 10.0, 1.0)
+                    Pc = E.SymmetricKPMPreconditioner(mc)
+                    mc._call("elph_set_tuning", 17, fused)
+                    mc._call("elph_set_tuning", 20, grid)
+                    dc = E.RungeKuttaDynamics(mc, 1e-3)
+                    nz = [dict(eta=rc.normal(size=n), g1=rc.normal(size=n), g2=rc.normal(size=n),
+                               arnoldi1=rc.normal(size=2 * Nsites), arnoldi2=rc.normal(size=2 * Nsites)) for _ in range(nst + 1)]
+                    for z in nz:
+                        for key in ("eta", "g1", "g2"):
+                            mc.pin_host(z[key])
+                    chains.append((mc, fc, Pc, dc, nz))
+                its_c = [0] * K
 
-            def run_chain(c, first, steps):
-                mc, fc, Pc, dc, nz = chains[c]
-                for k in range(first, first + steps):   # fresh noise every step, as in a real chain
-                    its_c[c] = E.evolve_(mc, dc, fc, Pc, **nz[k])
+                def run_chain(c, first, steps):
+                    mc, fc, Pc, dc, nz = chains[c]
+                    for k in range(first, first + steps):   # fresh noise every step, as in a real chain
+                        its_c[c] = E.evolve_(mc, dc, fc, Pc, **nz[k])
 
-            for first, steps in ((0, 1), (1, nst)):            # warm-up step, then the timed steps
-                ths = [_th.Thread(target=run_chain, args=(c, first, steps)) for c in range(K)]
-                t0 = time.perf_counter()
-                for t in ths:
-                    t.start()
-                for t in ths:
-                    t.join()
-                dt_c = time.perf_counter() - t0
-            extra["langevin_rk_kpm_chains"] = {"chains": K, "steps_per_s_aggregate": K * nst / dt_c, "steps_per_s_per_chain": nst / dt_c,
-                                               "pcg_iters_last": its_c,
+                for first, steps in ((0, 1), (1, nst)):            # warm-up step, then the timed steps
+                    ths = [_th.Thread(target=run_chain, args=(c, first, steps)) for c in range(K)]
+                    t0 = time.perf_counter()
+                    for t in ths:
+                        t.start()
+                    for t in ths:
+                        t.join()
+                    dt_c = time.perf_counter() - t0
+                chain_results[f"{K}_chains_" + ("one_kernel_solve" if fused else "launch_per_phase_solve")] = {
+                    "chains": K, "steps_per_s_aggregate": K * nst / dt_c, "steps_per_s_per_chain": nst / dt_c,
+                    "ctas_per_solve": grid or None, "pcg_iters_last": list(its_c)}
+                for mc, fc, Pc, dc, nz in chains:
+                    for z in nz:
+                        for key in ("eta", "g1", "g2"):
+                            mc.unpin_host(z[key])
+                    mc.close()
+            best = max(chain_results.values(), key=lambda r: r["steps_per_s_aggregate"])
+            extra["langevin_rk_kpm_chains"] = {"chains": best["chains"], "steps_per_s_aggregate": best["steps_per_s_aggregate"],
+                                               "steps_per_s_per_chain": best["steps_per_s_per_chain"], "variants": chain_results,
                                                "note": "K independent 32x32xL200 chains on one GPU, one handle + stream + host thread each "
                                                        "(elph_langevin_step, page-locked host noise)"}
-            for mc, fc, Pc, dc, nz in chains:
-                for z in nz:
-                    for key in ("eta", "g1", "g2"):
-                        mc.unpin_host(z[key])
-                mc.close()
         except Exception as exc:   # an extra must not cost the bench line
             extra["langevin_rk_kpm_chains"] = {"error": str(exc)[:200]}
 

@@ -1291,6 +1291,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 17: h->pcg_persistent = (value != 0); break;
             case 18: h->pcg_half_fft = (value != 0); break;
             case 19: h->kpm_dev_arnoldi = (value != 0); break;
+            case 20: ELPH_REQUIRE(value >= 0 && value <= 4096, ELPH_ERR_INVALID, "CTA count out of range"); h->pcg_grid = value; break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:
                 h->pipe_prof = (value != 0);

@@ -108,8 +108,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// (registers capped below the full register file of an SM -- 512 threads x 128 -- so that the cooperative launch also fits when a
+//  profiler or debugger reserves resources on the SM)
 template <int NSEG, int PY, int SB, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) pcg_fused_kernel(FusedParams P) {
+__global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams P) {
     constexpr int LX = 32 * NSEG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
@@ -603,6 +605,7 @@ bool launch_fused(elph_handle* h, FusedParams& P, int nwarps) {
     const int threads = nwarps * 32;
     // one CTA per SM, an even number of them (2-CTA clusters), all co-resident
     int grid = h->sm_count & ~1;
+    if (h->pcg_grid >= 2) grid = std::min(grid, h->pcg_grid & ~1);   // tuning key 20: leave SMs to other chains on the same GPU
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);
@@ -625,7 +628,10 @@ bool launch_fused(elph_handle* h, FusedParams& P, int nwarps) {
     ELPH_CUDA(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned int), h->stream));
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
-    cfg.numAttrs = 2;
+    // ELPH_PCG_NOCOOP=1 (profiling aid): Nsight Compute refuses launches that are both cooperative and clustered; the occupancy
+    // query above already guarantees that the whole grid is co-resident
+    static const bool nocoop = [] { const char* e = getenv("ELPH_PCG_NOCOOP"); return e && e[0] == '1'; }();
+    cfg.numAttrs = nocoop ? 1 : 2;
     void* args[] = {&P};
     cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
     if (e != cudaSuccess) {
