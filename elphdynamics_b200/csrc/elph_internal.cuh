@@ -92,6 +92,7 @@ struct KpmState {
     // device
     double* d_eVbar = nullptr;    // [N]
     double2* d_csbar = nullptr;   // [Nb] (c,s)
+    double2* d_csbar_tile = nullptr;   // SSH on square lattices: the same in the tile layout [direction][site]
     cplx* d_coeff = nullptr;      // concatenated coefficients
     int* d_order = nullptr;       // [Lo2]
     int* d_coeff_off = nullptr;   // [Lo2]

@@ -265,7 +265,9 @@ __global__ void taumean_kernel(const double* __restrict__ tab, double* __restric
     out[i] = s / (double)L;
 }
 // SSH: (cbar,sbar)[b] = mean_tau (cosh,sinh)[tau][b] (:367-376)
-__global__ void taumean2_kernel(const double2* __restrict__ tab, double2* __restrict__ out, int ncols, int L) {
+// tile_out (optional): second copy in the tile layout [direction][site] of ssh_square.cu (slot = position of the bond there)
+__global__ void taumean2_kernel(const double2* __restrict__ tab, double2* __restrict__ out, int ncols, int L,
+                                const int* __restrict__ slot = nullptr, double2* __restrict__ tile_out = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncols) return;
     double sc = 0.0, ss = 0.0;
@@ -275,6 +277,7 @@ __global__ void taumean2_kernel(const double2* __restrict__ tab, double2* __rest
         ss += v.y;
     }
     out[i] = make_double2(sc / (double)L, ss / (double)L);
+    if (tile_out) tile_out[slot[i]] = out[i];
 }
 
 // arnoldi_eigenvalue_bounds! (src/KPMPreconditioners.jl:845-942) on the device: blockIdx.x = 0 runs the Krylov iteration on A
@@ -666,6 +669,7 @@ void elph_kpm_free(elph_handle* h) {
     cudaFree(K.d_schedule);
     cudaFree(K.d_nu);
     cudaFree(K.d_noise);
+    cudaFree(K.d_csbar_tile);
     cudaFree(K.d_hm);
     cudaFree(K.d_Q);
     if (K.h_hm) cudaFreeHost(K.h_hm);
@@ -696,7 +700,9 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
         }
     } else {
         if (Nb > 0) {
-            taumean2_kernel<<<(Nb + T - 1) / T, T, 0, h->stream>>>(h->d_cs, K.d_csbar, Nb, L);
+            if (h->ssq.enabled && !K.d_csbar_tile) K.d_csbar_tile = elph_dalloc<double2>(Nb);
+            taumean2_kernel<<<(Nb + T - 1) / T, T, 0, h->stream>>>(h->d_cs, K.d_csbar, Nb, L, h->ssq.enabled ? h->ssq.d_slot : nullptr,
+                                                                   h->ssq.enabled ? K.d_csbar_tile : nullptr);
             ELPH_CUDA(cudaGetLastError());
             h->launches++;
         }

@@ -22,6 +22,7 @@ struct KsqParams {
     double c0, s0, c1, s1, c2, s2, c3, s3;
     double t0, t1, t2, t3, cprod;   // tanh form (square_tiles.cuh): t_g = s_g / c_g, cprod = c0 c1 c2 c3
     int fast;
+    const double2* tab;         // SSH: tau-averaged (cosh, sinh) per bond, tile layout [direction][site]
     unsigned long long* prof;   // development aid (tuning key 12): clock64 stamps of the cluster of the longest polynomial
 };
 

@@ -159,11 +159,43 @@ __global__ void __launch_bounds__(MAXT) kpm_square_kernel(KsqParams P, int max_o
 // polynomial (twice per apply).  The work per sweep on the critical chain (the lowest frequency, ~70 terms at
 // config B) is halved.
 // ---------------------------------------------------------------------------------------------------------------
-template <int NSEG, int PY, bool TRANSPOSED>
+// TAB: per-bond (cosh, sinh) from shared-memory tables in the tile layout [direction][site] (SSH: the tau-averaged hoppings of
+// src/KPMPreconditioners.jl:355-381); otherwise one pair per colour (Holstein).
+template <int NSEG, int PY, bool TRANSPOSED, bool TAB = false>
 __device__ __forceinline__ void apply_A_real(Tile<NSEG, PY>& s, const Tile<NSEG, PY>& ev, const KsqParams& P, double* strips,
-                                             int& xbuf, int warp, int nwarps, int lane) {
+                                             int& xbuf, int warp, int nwarps, int lane, const double2* tabs = nullptr) {
     constexpr int LX = 32 * NSEG;
     double ab[NSEG], be[NSEG];
+    if (TAB) {
+        const int N = LX * P.Ly, y0 = warp * PY;
+        const double2* tx = tabs + (size_t)y0 * LX;
+        const double2* ty = tabs + N + (size_t)y0 * LX;
+        const double2* ty_halo = tabs + N + (size_t)((y0 + P.Ly - 1) % P.Ly) * LX;
+        if (!TRANSPOSED) {
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+            g0_tab(s, tx, lane);
+            g1_tab(s, tx, lane);
+            g2_tab(s, ty, lane);
+            exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+            xbuf ^= 1;
+            g3_tab(s, ty, ty_halo, lane, ab, be);
+        } else {
+            exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+            xbuf ^= 1;
+            g3_tab(s, ty, ty_halo, lane, ab, be);
+            g2_tab(s, ty, lane);
+            g1_tab(s, tx, lane);
+            g0_tab(s, tx, lane);
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+        }
+        return;
+    }
     if (!TRANSPOSED) {
 #pragma unroll
         for (int r = 0; r < PY; ++r)
@@ -190,10 +222,10 @@ __device__ __forceinline__ void apply_A_real(Tile<NSEG, PY>& s, const Tile<NSEG,
 }
 
 // A = sum_n cr_n T_n v ,  B = sum_n ci'_n T_n v   (ci' = -ci for the transposed/conjugated pass)
-template <int NSEG, int PY, bool TRANSPOSED>
+template <int NSEG, int PY, bool TRANSPOSED, bool TAB = false>
 __device__ __forceinline__ void poly_real(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, const Tile<NSEG, PY>& vin, const Tile<NSEG, PY>& ev,
                                           const cplx* c_s, int order, const KsqParams& P, double* strips, int& xbuf, int warp,
-                                          int nwarps, int lane) {
+                                          int nwarps, int lane, const double2* tabs = nullptr) {
     Tile<NSEG, PY> un, uprev, s;
     const double sg = TRANSPOSED ? -1.0 : 1.0;
     const double c0r = c_s[0].x, c0i = sg * c_s[0].y;
@@ -210,7 +242,7 @@ __device__ __forceinline__ void poly_real(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, 
     const double k1 = P.inv_mag, k2 = P.avg_over_mag;
     for (int n = 1; n < order; ++n) {
         s = un;
-        apply_A_real<NSEG, PY, TRANSPOSED>(s, ev, P, strips, xbuf, warp, nwarps, lane);
+        apply_A_real<NSEG, PY, TRANSPOSED, TAB>(s, ev, P, strips, xbuf, warp, nwarps, lane, tabs);
         const double cr = c_s[n].x, ci = sg * c_s[n].y;
         const double two = (n > 1) ? 2.0 : 1.0, one = (n > 1) ? 1.0 : 0.0;
 #pragma unroll
@@ -227,7 +259,7 @@ __device__ __forceinline__ void poly_real(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, 
     }
 }
 
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool TAB = false>
 __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int max_order) {
     constexpr int LX = 32 * NSEG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -248,6 +280,9 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
     cplx* c_s = reinterpret_cast<cplx*>(smem_raw);                                            // [max_order]
     double* strips = reinterpret_cast<double*>(smem_raw + (size_t)max_order * sizeof(cplx));  // 2 x [nwarps][2][LX]
     double* xch = strips + 2ull * nwarps * 2 * LX;                                            // [N] written by the partner CTA
+    double2* tabs = reinterpret_cast<double2*>(xch + N);                                      // TAB: [2][N] (cosh, sinh)
+    if (TAB)
+        for (int k = threadIdx.x; k < 2 * N; k += blockDim.x) tabs[k] = P.tab[k];
     for (int k = threadIdx.x; k < order; k += blockDim.x) c_s[k] = P.coeff[P.coeff_off[w] + k];
     const size_t tile_off = (size_t)warp * PY * LX;
     Tile<NSEG, PY> v, A, B, ev;
@@ -290,7 +325,12 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
     };
     int xbuf = 0;
     Tile<NSEG, PY> t1, t2;
-    if (P.fast) {
+    if (TAB) {
+        poly_real<NSEG, PY, true, true>(A, B, v, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane, tabs);    // M^-T[w,w]
+        swap_combine(t1);
+        poly_real<NSEG, PY, false, true>(A, B, t1, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane, tabs);  // M^-1[w,w]
+        swap_combine(t2);
+    } else if (P.fast) {
         const double sc = 2.0 * P.inv_mag * P.cprod;
 #pragma unroll
         for (int r = 0; r < PY; ++r)
@@ -324,15 +364,15 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
     stamp();
 }
 
-template <int NSEG, int PY, int MAXT>
+template <int NSEG, int PY, int MAXT, bool TAB = false>
 void launch_ksq_split(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
     constexpr int LX = 32 * NSEG;
     size_t smem = (size_t)max_order * sizeof(cplx) + 2ull * nwarps * 2 * LX * sizeof(double) +
-                  (size_t)LX * P.Ly * sizeof(double);
+                  (size_t)LX * P.Ly * sizeof(double) + (TAB ? 2ull * LX * P.Ly * sizeof(double2) : 0);
     // one CTA per SM: a second cluster on the SM of the longest chain would share its fp64 pipe (the chain is what an apply waits for)
     if (h->kpm_exclusive) smem = std::max(smem, std::min<size_t>(h->smem_optin, 120 * 1024));
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "KPM split kernel does not fit in shared memory");
-    elph_enable_smem(h, kpm_square_split_kernel<NSEG, PY, MAXT>);
+    elph_enable_smem(h, kpm_square_split_kernel<NSEG, PY, MAXT, TAB>);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * h->kpm.Lo2);
     cfg.blockDim = dim3(nwarps * 32);
@@ -345,7 +385,7 @@ void launch_ksq_split(elph_handle* h, const KsqParams& P, int nwarps, int max_or
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ELPH_CUDA(cudaLaunchKernelEx(&cfg, kpm_square_split_kernel<NSEG, PY, MAXT>, P, max_order));
+    ELPH_CUDA(cudaLaunchKernelEx(&cfg, kpm_square_split_kernel<NSEG, PY, MAXT, TAB>, P, max_order));
     h->launches++;
 }
 
@@ -364,8 +404,27 @@ void launch_ksq(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
 
 // Returns false when the model is not served by the square-lattice kernel (caller falls back to kpm_apply_kernel).
 bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, const int* skip) {
-    if (!h->sq.enabled || h->sq_disable || h->model != ELPH_MODEL_HOLSTEIN) return false;
     const KpmState& K = h->kpm;
+    if (h->model == ELPH_MODEL_SSH) {
+        // SSH on a periodic square lattice 32 sites wide: the same 2-CTA cluster per frequency with the tau-averaged (cosh, sinh)
+        // of every bond in shared memory (tile layout, written by taumean2_kernel next to the bond-order copy)
+        if (!h->ssq.enabled || h->sq_disable || !K.d_csbar_tile || !h->kpm_split) return false;
+        const int Lx = h->ssq.Lx, Ly = h->ssq.Ly;
+        if (Lx != 32 || Ly % 2 || Ly / 2 < 2 || Ly / 2 > 16) return false;
+        int max_order = 1;
+        for (int w = 0; w < K.Lo2; ++w) max_order = std::max(max_order, K.order[w]);
+        KsqParams P;
+        P.in = nu_in; P.out = nu_out; P.eVbar = K.d_eVbar; P.coeff = K.d_coeff; P.order = K.d_order; P.coeff_off = K.d_coeff_off;
+        P.schedule = K.d_schedule; P.skip = skip; P.L = h->L; P.Ly = Ly;
+        P.inv_mag = 1.0 / K.lam_mag; P.avg_over_mag = K.lam_avg / K.lam_mag;
+        P.c0 = P.c1 = P.c2 = P.c3 = 1.0; P.s0 = P.s1 = P.s2 = P.s3 = 0.0;
+        P.t0 = P.t1 = P.t2 = P.t3 = 0.0; P.cprod = 1.0; P.fast = 0;
+        P.prof = nullptr;
+        P.tab = K.d_csbar_tile;
+        launch_ksq_split<1, 2, 512, true>(h, P, Ly / 2, max_order);
+        return true;
+    }
+    if (!h->sq.enabled || h->sq_disable || h->model != ELPH_MODEL_HOLSTEIN) return false;
     const int Lx = h->sq.Lx, Ly = h->sq.Ly;
     // rows per warp: the recurrences are latency bound (one dependent sweep after the other), so on 32-wide lattices the
     // smallest tile wins: 2 rows per warp = 16 warps per CTA at 32x32 (measured 51.2 us per apply against 55.3 with 4)
@@ -389,6 +448,7 @@ bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, con
     P.fast = h->kpm_fast ? 1 : 0;
     if (const char* e = getenv("ELPH_KPM_EXCL")) h->kpm_exclusive = atoi(e) != 0;
     P.prof = h->pipe_prof ? h->pipe_prof_buf : nullptr;
+    P.tab = nullptr;
 #define KSQ_CASE(NS, PYV, MAXT)                                    \
     if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {       \
         if (h->kpm_split) launch_ksq_split<NS, PYV, MAXT>(h, P, nwarps, max_order); \

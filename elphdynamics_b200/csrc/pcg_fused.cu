@@ -691,7 +691,7 @@ bool elph_pcg_fused(elph_handle* h, double* x_dev, double* z_dev) {
     Q.c2 = h->sq.c[2]; Q.s2 = h->sq.s[2]; Q.c3 = h->sq.c[3]; Q.s3 = h->sq.s[3];
     Q.t0 = Q.s0 / Q.c0; Q.t1 = Q.s1 / Q.c1; Q.t2 = Q.s2 / Q.c2; Q.t3 = Q.s3 / Q.c3;
     Q.cprod = Q.c0 * Q.c1 * Q.c2 * Q.c3;
-    Q.fast = 1; Q.prof = nullptr;
+    Q.fast = 1; Q.prof = nullptr; Q.tab = nullptr;
     P.Lo2 = K.Lo2; P.max_order = max_order;
     P.partial = h->d_partial; P.bar = h->d_bar; P.S = h->d_cg;
     P.L = h->L; P.Ly = Ly; P.Cs = 1; P.nchunks = h->L;

@@ -140,3 +140,47 @@ def test_device_arnoldi_equals_host_arnoldi(geom, Lside):
     if Po.active:
         assert np.array_equal(Pe.orders(), Po.order)
     em.close()
+
+
+@pytest.mark.parametrize("beta,dtau", [(0.6, 0.05), (0.35, 0.05)])
+def test_ssh_kpm_apply_register_chains(beta, dtau):
+    """ldiv!(z, P, r) for the SSH model on a 32x32 lattice: the cluster-split chain kernel with the tau-averaged (cosh, sinh) of
+    every bond in shared memory (src/KPMPreconditioners.jl:355-381, 606-679) against the oracle and against the generic
+    shared-memory kernel (tuning key 1)."""
+    import elphdynamics_b200 as E
+    from helpers_ssh import engine_ssh_like, oracle_ssh
+    from oracle.kpm import KPMPreconditioner, kpm_coefficients
+    from oracle.solvers import ConjugateGradient, ldiv
+    om, rng = oracle_ssh(Lside=32, beta=beta, dtau=dtau, mu=0.1)
+    em = engine_ssh_like(om)
+    Po, Pe = KPMPreconditioner(om), E.SymmetricKPMPreconditioner(em)
+    noise = rng.normal(size=2 * om.N)
+    Po.setup(noise)
+    info = E.setup_(Pe, noise)
+    assert bool(info.active) == Po.active
+    if not Po.active:
+        pytest.skip("preconditioner inactive for this field")
+    Po.lam_lo, Po.lam_hi = info.lambda_lo, info.lambda_hi
+    Po.lam_avg, Po.lam_mag = (Po.lam_hi + Po.lam_lo) / 2, (Po.lam_hi - Po.lam_lo) / 2
+    Po.coeff = [kpm_coefficients(int(Po.order[w]), Po.lam_lo, Po.lam_hi, Po.phis[w]) for w in range(Po.Lo2)]
+    r = rng.normal(size=om.Ndim)
+    zo = np.zeros(om.Ndim)
+    Po.ldiv(zo, r)
+    l0 = em.launch_count()
+    ze = np.zeros(om.Ndim)
+    E.kpm_ldiv_(ze, Pe, r)
+    assert relerr(ze, zo) <= 1e-11
+    em._call("elph_set_tuning", 1, 1)       # generic kernels
+    zg = np.zeros(om.Ndim)
+    E.kpm_ldiv_(zg, Pe, r)
+    em._call("elph_set_tuning", 1, 0)
+    assert relerr(zg, zo) <= 1e-11 and relerr(ze, zg) <= 1e-12
+    # and the preconditioned solve through it
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    xo, xe = np.zeros(om.Ndim), np.zeros(om.Ndim)
+    it_o, _, f_o = ldiv(xo, om, b, ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter), Po)
+    it_e, _, f_e = E.ldiv_(xe, em, b, Pe)
+    assert f_o == f_e == 0 and abs(it_o - it_e) <= 2 and relerr(xe, xo) <= 50 * om.tol
+    em.close()
