@@ -598,6 +598,53 @@ def main():
         extra["hmc_honeycomb_L32"] = {"trajectories_per_s": 1.0 / dtD, "leapfrog_steps": hD.Nt, "inner_Sb_steps": hD.Nb,
                                       "solves_per_trajectory": 2 * (hD.Nt + 2), "cg_iters": itsD, "accepted": accD,
                                       "note": "elph_hmc_update: whole trajectory on the device, noise injected from the host"}
+        # the lattice's kernels in isolation: one M^T M, one CG solve (persistent kernel), and the HBM regime with independent
+        # replicas (own expnV table and vector each: 0.98 MB per replica, 1024 replicas = 1 GB per launch)
+        nD = mD.Ndim
+        vD = torch.randn(nD, dtype=torch.float64, device="cuda")
+        yD = torch.empty_like(vD)
+        for _ in range(10):
+            lib.elph_dev_mulMTM(mD.handle, vD.data_ptr(), yD.data_ptr())
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(200):
+            lib.elph_dev_mulMTM(mD.handle, vD.data_ptr(), yD.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        usD = e0.elapsed_time(e1) * 1e3 / 200
+        bD = torch.randn(nD, dtype=torch.float64, device="cuda")
+        xD = torch.zeros_like(bD)
+        itD, epsD = C.c_int64(), C.c_double()
+        bestD = float("inf")
+        for _ in range(3):
+            xD.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lib.elph_dev_cg_solve(mD.handle, bD.data_ptr(), xD.data_ptr(), 0, 0.0, 0, C.byref(itD), C.byref(epsD))
+            torch.cuda.synchronize()
+            bestD = min(bestD, time.perf_counter() - t0)
+        RD = 1024
+        DD = torch.from_numpy(np.ascontiguousarray(mD.expnV.reshape(mD.Nsites, mD.Ltau).T)).reshape(-1).cuda()
+        DD = DD.unsqueeze(0).repeat(RD, 1) * (1.0 + 0.01 * torch.rand(RD, nD, dtype=torch.float64, device="cuda"))
+        VD = torch.randn(RD, nD, dtype=torch.float64, device="cuda")
+        YD = torch.empty_like(VD)
+        for _ in range(3):
+            lib.elph_dev_mulMTM_replicas(mD.handle, RD, DD.data_ptr(), nD, VD.data_ptr(), YD.data_ptr(), nD)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            lib.elph_dev_mulMTM_replicas(mD.handle, RD, DD.data_ptr(), nD, VD.data_ptr(), YD.data_ptr(), nD)
+        e1.record()
+        torch.cuda.synchronize()
+        usRD = e0.elapsed_time(e1) * 1e3 / 20
+        extra["hmc_honeycomb_L32"].update({
+            "us_per_matvec": usD, "cg": {"iters": int(itD.value), "us_per_iteration": bestD * 1e6 / max(1, itD.value)},
+            "replicas": {"replicas_per_launch": RD, "us_per_launch": usRD, "matvecs_per_s": RD * 1e6 / usRD,
+                         "achieved_GBps": BYTES_PER_POINT * nD * RD / usRD / 1e3,
+                         "frac_of_hbm_peak": BYTES_PER_POINT * nD * RD / usRD / 1e3 / hbm_peak,
+                         "note": "register-tile kernels for the honeycomb lattice (cell pair / lane rotation / row pair); 24 B per "
+                                 "lattice point, 1.0 GB per launch"}})
+        del DD, VD, YD
         mD.close()
 
     # ---------------- tau-sharded single lattice (config E: Holstein 64x64, L=400), strong scaling over ranks -----

@@ -161,6 +161,7 @@ void build(elph_handle* h, const elph_config* c) {
         for (int b = 0; b < h->Nb; ++b) cs[b] = make_double2(c->cosht[b], c->sinht[b]);
         up(h->d_cs, cs);
         elph_detect_square(h, cs);
+        elph_detect_honeycomb(h, cs);
         up(h->d_lam, vec(c->lambda, h->N, 0.0));
         up(h->d_lam2, vec(c->lambda2, h->N, 0.0));
         h->d_D = zeros(h->Ndim);
@@ -1291,6 +1292,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 17: h->pcg_persistent = (value != 0); break;
             case 18: h->pcg_half_fft = (value != 0); break;
             case 19: h->kpm_dev_arnoldi = (value != 0); break;
+            case 21: h->hc_tiles = (value != 0); break;
             case 20: ELPH_REQUIRE(value >= 0 && value <= 4096, ELPH_ERR_INVALID, "CTA count out of range"); h->pcg_grid = value; break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:

@@ -95,9 +95,14 @@ __device__ __forceinline__ double tile_block_sum(double v, double* red, int lane
 
 // MINB: resident CTAs per SM the register allocation must allow (3 x 128 threads -> 168 registers: 444 CTAs on 148 SMs,
 // i.e. two right-hand sides of config B at once)
-template <int NSEG, int PY, int MAXT, bool SSH, int MINB = 1>
+// LAT: 0 = square lattice, one (cosh, sinh) per colour; 1 = square lattice, SSH tables; 2 = honeycomb lattice 32 cells wide
+// (NSEG = 2: the two orbitals of a cell, see the hc tiles of square_tiles.cuh)
+template <int NSEG, int PY, int MAXT, int LAT, int MINB = 1>
 __global__ void __launch_bounds__(MAXT, MINB) cg_persistent_kernel(PcgParams P) {
     constexpr int LX = 32 * NSEG;
+    constexpr bool SSH = (LAT == 1);
+    constexpr bool HC = (LAT == 2);
+    static_assert(!HC || NSEG == 2, "honeycomb tiles hold the two orbitals of a cell");
     extern __shared__ __align__(16) double strips[];   // 2 x [nwarps][4][LX]; SSH: + the tables of slices tau and tau+1
     __shared__ double red[32];
     __shared__ double bcast[32];
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(MAXT, MINB) cg_persistent_kernel(PcgParams P) 
     const int taum = (tau == 0) ? L - 1 : tau - 1;
     const int taup = (tau == L - 1) ? 0 : tau + 1;
     const size_t tile_off = (size_t)warp * PY * LX;
-    auto eidx = [&](int r, int q) -> size_t { return tile_off + r * LX + 32 * q + lane; };
+    auto eidx = [&](int r, int q) -> size_t { return HC ? tile_off + r * LX + 2 * lane + q : tile_off + r * LX + 32 * q + lane; };
 
     Tile<NSEG, PY> x, r, pprev, pc, Dc, Dn, t1, t2;
 #pragma unroll
@@ -163,7 +168,17 @@ __global__ void __launch_bounds__(MAXT, MINB) cg_persistent_kernel(PcgParams P) 
                 t2.a[rr][q] = Dn.a[rr][q] * pcv;         // D(tau+1) p(tau)
             }
         // ---- K sweep on both tiles (one barrier) ----------------------------------------------------------------
-        if constexpr (SSH) {
+        if constexpr (HC) {
+            hc0_cell(t1, P.c0, P.s0);
+            hc0_cell(t2, P.c0, P.s0);
+            hc1_lane(t1, P.c1, P.s1, lane);
+            hc1_lane(t2, P.c1, P.s1, lane);
+            double a1, b1, a2, b2;
+            exchange_hc2(t1, t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, a1, b1, a2, b2);
+            xbuf ^= 1;
+            hc2_row(t1, P.c2, P.s2, a1, b1);
+            hc2_row(t2, P.c2, P.s2, a2, b2);
+        } else if constexpr (SSH) {
             g0_tab(t1, txc, lane);
             g0_tab(t2, txn, lane);
             g1_tab(t1, txc, lane);
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(MAXT, MINB) cg_persistent_kernel(PcgParams P) 
             g2_y_even(t1, P.c2, P.s2);
             g2_y_even(t2, P.c2, P.s2);
         }
-        {
+        if constexpr (!HC) {
             double a1[NSEG], a2[NSEG], b1[NSEG], b2[NSEG];
             exchange_edges2(t1, t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, a1, a2, b1, b2);
             xbuf ^= 1;
@@ -205,14 +220,22 @@ __global__ void __launch_bounds__(MAXT, MINB) cg_persistent_kernel(PcgParams P) 
                 acc = fma(wc, wc, acc);
             }
         // ---- u = K^T w(tau+1) (in t2): g3, g2, g1, g0 ----------------------------------------------------------
-        {
+        if constexpr (HC) {
+            double ab, be;
+            exchange_hc1(t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, ab, be);
+            xbuf ^= 1;
+            hc2_row(t2, P.c2, P.s2, ab, be);
+            hc1_lane(t2, P.c1, P.s1, lane);
+            hc0_cell(t2, P.c0, P.s0);
+        } else {
             double ab[NSEG], be[NSEG];
             exchange_edges1(t2, strips + (size_t)xbuf * nwarps * 4 * LX, warp, nwarps, lane, ab, be);
             xbuf ^= 1;
             if constexpr (SSH) g3_tab(t2, tyn, hyn, lane, ab, be);
             else g3_y_odd(t2, P.c3, P.s3, ab, be);
         }
-        if constexpr (SSH) {
+        if constexpr (HC) {
+        } else if constexpr (SSH) {
             g2_tab(t2, tyn, lane);
             g1_tab(t2, txn, lane);
             g0_tab(t2, txn, lane);
@@ -288,12 +311,12 @@ bool launch_groups(elph_handle* h, Kern kern, const Params& P, int threads, size
     return true;
 }
 
-template <int NSEG, int PY, int MAXT, bool SSH, int MINB = 1>
+template <int NSEG, int PY, int MAXT, int LAT, int MINB = 1>
 bool launch_persistent(elph_handle* h, const PcgParams& P, int nwarps, int nrhs) {
     constexpr int LX = 32 * NSEG;
-    const size_t smem = 2ull * nwarps * 4 * LX * sizeof(double) + (SSH ? 2ull * 2 * h->N * sizeof(double2) : 0);
+    const size_t smem = 2ull * nwarps * 4 * LX * sizeof(double) + (LAT == 1 ? 2ull * 2 * h->N * sizeof(double2) : 0);
     if (smem > h->smem_optin) return false;
-    return launch_groups(h, cg_persistent_kernel<NSEG, PY, MAXT, SSH, MINB>, P, nwarps * 32, smem, nrhs);
+    return launch_groups(h, cg_persistent_kernel<NSEG, PY, MAXT, LAT, MINB>, P, nwarps * 32, smem, nrhs);
 }
 
 // ---- any lattice (Holstein): one time slice per CTA in shared memory ------------------------------------------------
@@ -827,6 +850,20 @@ bool elph_cg_persistent_batch(elph_handle* h, int nrhs, const CgBatchBufs& B) {
     int dev_coop = 0;
     cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, h->device);
     if (!dev_coop) return false;
+    if (!ssh && h->hc.enabled && !h->sq_disable && h->hc_tiles && h->L >= 4) {
+        // honeycomb lattice 32 cells wide (config D): register tiles, 4 rows of cells per warp
+        const int nwarps = h->hc.L2 / 4;
+        if (nwarps >= 2 && nwarps <= 16) {
+            PcgParams P;
+            fill_io(P, B, h->L);
+            P.D = h->d_D; P.tab = nullptr;
+            P.L = h->L; P.Ly = h->hc.L2;
+            P.c0 = h->hc.c[0]; P.s0 = h->hc.s[0]; P.c1 = h->hc.c[1]; P.s1 = h->hc.s[1];
+            P.c2 = h->hc.c[2]; P.s2 = h->hc.s[2]; P.c3 = 1.0; P.s3 = 0.0;
+            if (nwarps * 32 <= 256 && launch_persistent<2, 4, 256, 2>(h, P, nwarps, nrhs)) return true;
+            if (nwarps * 32 > 256 && launch_persistent<2, 4, 512, 2>(h, P, nwarps, nrhs)) return true;
+        }
+    }
     if (!(ssh ? h->ssq.enabled : h->sq.enabled) || h->sq_disable || h->L < 4) return cg_persistent_generic(h, nrhs, B);
     const int Lx = ssh ? h->ssq.Lx : h->sq.Lx, Ly = ssh ? h->ssq.Ly : h->sq.Ly;
     const int PY = (Lx == 32) ? 8 : 4;
@@ -840,13 +877,13 @@ bool elph_cg_persistent_batch(elph_handle* h, int nrhs, const CgBatchBufs& B) {
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
     if (ssh) {
-        if (Lx == 32 && PY == 8 && nwarps * 32 <= 128) return launch_persistent<1, 8, 128, true, 3>(h, P, nwarps, nrhs);
-        if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, true>(h, P, nwarps, nrhs);
+        if (Lx == 32 && PY == 8 && nwarps * 32 <= 128) return launch_persistent<1, 8, 128, 1, 3>(h, P, nwarps, nrhs);
+        if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, 1>(h, P, nwarps, nrhs);
         return false;
     }
-    if (Lx == 32 && PY == 8 && nwarps * 32 <= 128) return launch_persistent<1, 8, 128, false, 3>(h, P, nwarps, nrhs);
-    if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, false>(h, P, nwarps, nrhs);
-    if (Lx == 64 && PY == 4 && nwarps * 32 <= 512) return launch_persistent<2, 4, 512, false>(h, P, nwarps, nrhs);
+    if (Lx == 32 && PY == 8 && nwarps * 32 <= 128) return launch_persistent<1, 8, 128, 0, 3>(h, P, nwarps, nrhs);
+    if (Lx == 32 && PY == 8 && nwarps * 32 <= 256) return launch_persistent<1, 8, 256, 0>(h, P, nwarps, nrhs);
+    if (Lx == 64 && PY == 4 && nwarps * 32 <= 512) return launch_persistent<2, 4, 512, 0>(h, P, nwarps, nrhs);
     return false;
 }
 

@@ -146,6 +146,7 @@ struct elph_handle {
     double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool kpm_exclusive = true; // KPM apply: one chain CTA per SM (shared-memory request padded)
+    bool hc_tiles = true;        // honeycomb lattices: register-tile kernels (tuning key 21)
     int pcg_grid = 0;            // fused PCG: CTAs of the persistent kernel (0 = one per SM); tuning key 20
     bool kpm_dev_arnoldi = true; // KPM set-up: Arnoldi eigenvalue bounds on the device (tuning key 19)
     bool pcg_half_fft = true;   // fused PCG: tau-FFTs at length L/2 for even L (tuning key 18)
@@ -252,6 +253,12 @@ struct elph_handle {
         int Lx = 0, Ly = 0;
         double c[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
     } sq;
+    // register/shuffle kernels for the periodic honeycomb lattice 32 cells wide (hc tiles of square_tiles.cuh): config D
+    struct {
+        bool enabled = false;
+        int L1 = 0, L2 = 0;
+        double c[3] = {0, 0, 0}, s[3] = {0, 0, 0};
+    } hc;
     // SSH on the periodic square lattice (ssh_square.cu): second copy of the per-(tau,bond) table in the
     // register-tile layout [tau][dir][site] (dir 0 = +x bond leaving `site`, 1 = +y bond), written by update_model
     struct {
@@ -338,6 +345,7 @@ void elph_launch_update_model(elph_handle* h);
 bool elph_pcg_fused(elph_handle* h, double* x_dev, double* z_dev);   // pcg_fused.cu
 void elph_launch_ssh_replica_tables(elph_handle* h, int64_t nrep, const double* x_dev, int64_t x_stride, double2* tab_dev, int64_t tab_stride);
 void elph_detect_square(elph_handle* h, const std::vector<double2>& cs);
+void elph_detect_honeycomb(elph_handle* h, const std::vector<double2>& cs);
 bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a);
 bool elph_match_square(const elph_handle* h, int* Lx, int* Ly, std::vector<int>* slot);
 void elph_detect_ssh_square(elph_handle* h);                          // ssh_square.cu

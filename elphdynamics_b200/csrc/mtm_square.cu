@@ -26,6 +26,7 @@
 // partials in index order and publishes alpha (see cg.cu).
 #include "bulk_copy.cuh"
 #include "elph_internal.cuh"
+#include "square_tiles.cuh"
 
 namespace {
 
@@ -49,99 +50,22 @@ struct SqParams {
 
 using namespace tma;   // mbarrier + cp.async.bulk helpers (bulk_copy.cuh)
 
-template <int NSEG, int PY>
-struct Tile {
-    double a[PY][NSEG];
-};
+// register tiles and colour groups: square_tiles.cuh (shared with the CG, KPM and SSH kernels)
+using namespace sqt;
 
-// ---- colour groups on a register tile ---------------------------------------------------------------------
-template <int NSEG, int PY>
-__device__ __forceinline__ void g0_x_even(Tile<NSEG, PY>& t, double c, double s) {
-#pragma unroll
-    for (int r = 0; r < PY; ++r)
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            const double o = __shfl_xor_sync(0xffffffffu, t.a[r][q], 1);
-            t.a[r][q] = c * t.a[r][q] + s * o;
-        }
-}
-
-template <int NSEG, int PY>
-__device__ __forceinline__ void g1_x_odd(Tile<NSEG, PY>& t, double c, double s, int lane) {
-    const int partner = (lane & 1) ? ((lane + 1) & 31) : ((lane + 31) & 31);
-#pragma unroll
-    for (int r = 0; r < PY; ++r) {
-        double o[NSEG];
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            // lane 0 is read only by lane 31 (whose partner sits in the NEXT x-segment), lane 31 only by lane 0
-            double send = t.a[r][q];
-            if (NSEG > 1) {
-                const double nxt = t.a[r][(q + 1) % NSEG], prv = t.a[r][(q + NSEG - 1) % NSEG];
-                send = (lane == 0) ? nxt : ((lane == 31) ? prv : send);
-            }
-            o[q] = __shfl_sync(0xffffffffu, send, partner);
-        }
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) t.a[r][q] = c * t.a[r][q] + s * o[q];
-    }
-}
-
-template <int NSEG, int PY>
-__device__ __forceinline__ void g2_y_even(Tile<NSEG, PY>& t, double c, double s) {
-#pragma unroll
-    for (int r = 0; r < PY; r += 2)
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
-            t.a[r][q] = c * t1 + s * t2;
-            t.a[r + 1][q] = c * t2 + s * t1;
-        }
-}
-
-// interior odd pairs (1,2),(3,4),...,(PY-3,PY-2); the edge rows 0 and PY-1 pair with the neighbouring tiles
-template <int NSEG, int PY>
-__device__ __forceinline__ void g3_y_odd(Tile<NSEG, PY>& t, double c, double s, const double (&above)[NSEG],
-                                         const double (&below)[NSEG]) {
-#pragma unroll
-    for (int r = 1; r + 1 < PY; r += 2)
-#pragma unroll
-        for (int q = 0; q < NSEG; ++q) {
-            const double t1 = t.a[r][q], t2 = t.a[r + 1][q];
-            t.a[r][q] = c * t1 + s * t2;
-            t.a[r + 1][q] = c * t2 + s * t1;
-        }
-#pragma unroll
-    for (int q = 0; q < NSEG; ++q) {
-        t.a[0][q] = c * t.a[0][q] + s * above[q];
-        t.a[PY - 1][q] = c * t.a[PY - 1][q] + s * below[q];
-    }
-}
-
-// publish the tile-edge rows, barrier, fetch the neighbours' edge rows
 template <int NSEG, int PY>
 __device__ __forceinline__ void exchange_edges(const Tile<NSEG, PY>& t, double* strip, int warp, int nwarps, int lane,
                                                double (&above)[NSEG], double (&below)[NSEG]) {
-    constexpr int LX = 32 * NSEG;
-    double* mine = strip + (size_t)warp * 2 * LX;
-#pragma unroll
-    for (int q = 0; q < NSEG; ++q) {
-        mine[32 * q + lane] = t.a[0][q];
-        mine[LX + 32 * q + lane] = t.a[PY - 1][q];
-    }
-    __syncthreads();
-    const int up = (warp == 0) ? nwarps - 1 : warp - 1;
-    const int dn = (warp + 1 == nwarps) ? 0 : warp + 1;
-#pragma unroll
-    for (int q = 0; q < NSEG; ++q) {
-        above[q] = strip[(size_t)up * 2 * LX + LX + 32 * q + lane];  // last row of the tile above
-        below[q] = strip[(size_t)dn * 2 * LX + 32 * q + lane];       // first row of the tile below
-    }
+    exchange_edges1(t, strip, warp, nwarps, lane, above, below);
 }
 
-template <int NSEG, int PY, bool FUSEP, int MAXT>
+// HC: honeycomb lattice 32 cells wide (NSEG = 2 = the orbitals of a cell; element (r, q) of lane l sits at r * 64 + 2 l + q of
+// the tile), three colours instead of four (hc tiles of square_tiles.cuh)
+template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false>
 __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     constexpr int LX = 32 * NSEG;
+    static_assert(!HC || NSEG == 2, "honeycomb tiles hold the two orbitals of a cell");
+    auto eoff = [&](int r, int q, int lane_) -> int { return HC ? r * LX + 2 * lane_ + q : r * LX + 32 * q + lane_; };
     constexpr int TILE = PY * LX;                      // doubles per tile
     constexpr int NT = FUSEP ? 3 : 2;                  // tiles per stage: v (or pr, pold) and D
     constexpr uint32_t STAGE_BYTES = NT * TILE * sizeof(double);
@@ -203,7 +127,7 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
         for (int r = 0; r < PY; ++r)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
-                const long long e = g + r * LX + 32 * q + lane;
+                const long long e = g + eoff(r, q, lane);
                 vprev.a[r][q] = FUSEP ? fma(beta, P.pold[e], P.pr[e]) : vin[e];
                 wprev.a[r][q] = 0.0;
             }
@@ -225,20 +149,29 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 #pragma unroll
         for (int r = 0; r < PY; ++r)
 #pragma unroll
-            for (int q = 0; q < NSEG; ++q) t.a[r][q] = sD[r * LX + 32 * q + lane] * vprev.a[r][q];
-        // t = K t : g0, g1, g2, g3
-        g0_x_even(t, P.c0, P.s0);
-        g1_x_odd(t, P.c1, P.s1, lane);
-        g2_y_even(t, P.c2, P.s2);
-        exchange_edges(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
-        xbuf ^= 1;
-        g3_y_odd(t, P.c3, P.s3, above, below);
+            for (int q = 0; q < NSEG; ++q) t.a[r][q] = sD[eoff(r, q, lane)] * vprev.a[r][q];
+        // t = K t : the colour groups in order
+        if constexpr (HC) {
+            hc0_cell(t, P.c0, P.s0);
+            hc1_lane(t, P.c1, P.s1, lane);
+            double aB, bA;
+            exchange_hc1(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, aB, bA);
+            xbuf ^= 1;
+            hc2_row(t, P.c2, P.s2, aB, bA);
+        } else {
+            g0_x_even(t, P.c0, P.s0);
+            g1_x_odd(t, P.c1, P.s1, lane);
+            g2_y_even(t, P.c2, P.s2);
+            exchange_edges(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+            xbuf ^= 1;
+            g3_y_odd(t, P.c3, P.s3, above, below);
+        }
         // w(tau) = v(tau) -/+ t
 #pragma unroll
         for (int r = 0; r < PY; ++r)
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
-                const int e = r * LX + 32 * q + lane;
+                const int e = eoff(r, q, lane);
                 const double vc = FUSEP ? fma(beta, sv[TILE + e], sv[e]) : sv[e];
                 if (FUSEP && j < nout) P.pnew[(size_t)tau * N + tile_off + e] = vc;
                 const double w = wrap ? (vc + t.a[r][q]) : (vc - t.a[r][q]);
@@ -252,12 +185,21 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
             for (int r = 0; r < PY; ++r)
 #pragma unroll
                 for (int q = 0; q < NSEG; ++q) u.a[r][q] = t.a[r][q];
-            exchange_edges(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
-            xbuf ^= 1;
-            g3_y_odd(u, P.c3, P.s3, above, below);
-            g2_y_even(u, P.c2, P.s2);
-            g1_x_odd(u, P.c1, P.s1, lane);
-            g0_x_even(u, P.c0, P.s0);
+            if constexpr (HC) {
+                double aB, bA;
+                exchange_hc1(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, aB, bA);
+                xbuf ^= 1;
+                hc2_row(u, P.c2, P.s2, aB, bA);
+                hc1_lane(u, P.c1, P.s1, lane);
+                hc0_cell(u, P.c0, P.s0);
+            } else {
+                exchange_edges(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+                xbuf ^= 1;
+                g3_y_odd(u, P.c3, P.s3, above, below);
+                g2_y_even(u, P.c2, P.s2);
+                g1_x_odd(u, P.c1, P.s1, lane);
+                g0_x_even(u, P.c0, P.s0);
+            }
             // y(tau-1) = w(tau-1) -/+ D(tau) .* u     ('+' on the antiperiodic wrap tau = 0)
             const int taum = a + j - 1;   // always one of the CTA's own output slices
             const size_t g = (size_t)taum * N + tile_off;
@@ -265,7 +207,7 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
             for (int r = 0; r < PY; ++r)
 #pragma unroll
                 for (int q = 0; q < NSEG; ++q) {
-                    const int e = r * LX + 32 * q + lane;
+                    const int e = eoff(r, q, lane);
                     const double du = sD[e] * u.a[r][q];
                     y[g + e] = wrap ? (wprev.a[r][q] + du) : (wprev.a[r][q] - du);
                 }
@@ -313,15 +255,15 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     }
 }
 
-template <int NSEG, int PY, bool FUSEP, int MAXT>
+template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false>
 void launch_sq(elph_handle* h, const SqParams& P, dim3 grid, int nwarps) {
     constexpr int LX = 32 * NSEG;
     constexpr int NT = FUSEP ? 3 : 2;
     const size_t smem = (size_t)nwarps * kStages * NT * PY * LX * sizeof(double) + (size_t)nwarps * kStages * 8 +
                         2ull * nwarps * 2 * LX * sizeof(double);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "square kernel: tile pipeline does not fit in shared memory");
-    elph_enable_smem(h, mtm_square_kernel<NSEG, PY, FUSEP, MAXT>);
-    mtm_square_kernel<NSEG, PY, FUSEP, MAXT><<<grid, nwarps * 32, smem, h->stream>>>(P);
+    elph_enable_smem(h, mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC>);
+    mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC><<<grid, nwarps * 32, smem, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }
@@ -391,10 +333,48 @@ void elph_detect_square(elph_handle* h, const std::vector<double2>& cs) {
     }
 }
 
+// Honeycomb lattice, 32 unit cells wide, uniform hopping per bond type: the three colour groups must be exactly the three bond
+// types in the order cell / lane / row (this is what the reference's greedy colouring of the sorted neighbour table yields).
+void elph_detect_honeycomb(elph_handle* h, const std::vector<double2>& cs) {
+    h->hc.enabled = false;
+    if (h->model != ELPH_MODEL_HOLSTEIN || h->ngroups != 3) return;
+    const int N = h->N, L1 = 32;
+    if (N % (2 * L1) || 2 * h->Nb != 3 * N) return;
+    const int L2 = N / (2 * L1);
+    if (L2 < 4 || L2 % 4) return;
+    for (int g = 0; g < 3; ++g) {
+        const int lo = h->goff_host[g], hi = h->goff_host[g + 1];
+        if (hi - lo != N / 2) return;
+        std::vector<char> seen(N / 2, 0);
+        for (int b = lo; b < hi; ++b) {
+            int i = h->bonds_host[b].x, j = h->bonds_host[b].y;
+            if (i & 1) std::swap(i, j);           // i = the A site
+            if ((i & 1) || !(j & 1)) return;
+            const int ci = i / 2, cj = j / 2;
+            const int l1 = ci % L1, l2 = ci / L1, m1 = cj % L1, m2 = cj / L1;
+            bool ok;
+            if (g == 0) ok = (ci == cj);
+            else if (g == 1) ok = (m2 == l2 && m1 == (l1 + L1 - 1) % L1);
+            else ok = (m1 == l1 && m2 == (l2 + L2 - 1) % L2);
+            if (!ok || seen[ci]) return;
+            seen[ci] = 1;
+            if (cs[b].x != cs[lo].x || cs[b].y != cs[lo].y) return;
+        }
+    }
+    h->hc.enabled = true;
+    h->hc.L1 = L1;
+    h->hc.L2 = L2;
+    for (int g = 0; g < 3; ++g) {
+        h->hc.c[g] = cs[h->goff_host[g]].x;
+        h->hc.s[g] = cs[h->goff_host[g]].y;
+    }
+}
+
 bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
-    if (!h->sq.enabled || h->sq_disable) return false;
+    const bool hc = h->hc.enabled && h->hc_tiles && !h->sq_disable && !a.open;
+    if (!hc && (!h->sq.enabled || h->sq_disable)) return false;
     if (a.partial_dot && !a.cg_S) return false;
-    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
+    const int Lx = hc ? 64 : h->sq.Lx, Ly = hc ? h->hc.L2 : h->sq.Ly;
     const bool fusep = (a.cg_S != nullptr);
     // tile shape: PY rows per warp
     int PY;
@@ -405,6 +385,7 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
     else if (Lx == 128) PY = 4;
     else PY = 8;
     if (h->sq_py == 4 && Lx == 64) PY = 4;
+    if (hc) PY = (Ly % 8 == 0 && !latency_regime) ? 8 : 4;
     if (Ly % PY) return false;
     const int nwarps = Ly / PY;
     if (nwarps > 32 || nwarps < 2) return false;
@@ -433,6 +414,10 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
     P.C = C;
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
+    if (hc) {
+        P.c0 = h->hc.c[0]; P.s0 = h->hc.s[0]; P.c1 = h->hc.c[1]; P.s1 = h->hc.s[1];
+        P.c2 = h->hc.c[2]; P.s2 = h->hc.s[2]; P.c3 = 1.0; P.s3 = 0.0;
+    }
     const int nchunks = (h->L + C - 1) / C;
     dim3 grid(nchunks, (unsigned)a.nbatch);
     if (fusep) ELPH_REQUIRE(nchunks <= h->partial_cap, ELPH_ERR_INVALID, "partial buffer too small");
@@ -442,6 +427,19 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
         if (fusep) launch_sq<NS, PYV, true, MAXT>(h, P, grid, nwarps);       \
         else launch_sq<NS, PYV, false, MAXT>(h, P, grid, nwarps);            \
         return true;                                                         \
+    }
+    if (hc) {
+        if (PY == 8 && nwarps * 32 <= 256) {
+            if (fusep) launch_sq<2, 8, true, 256, true>(h, P, grid, nwarps);
+            else launch_sq<2, 8, false, 256, true>(h, P, grid, nwarps);
+            return true;
+        }
+        if (PY == 4 && nwarps * 32 <= 512) {
+            if (fusep) launch_sq<2, 4, true, 512, true>(h, P, grid, nwarps);
+            else launch_sq<2, 4, false, 512, true>(h, P, grid, nwarps);
+            return true;
+        }
+        return false;
     }
     SQ_CASE(1, 16, 256)
     SQ_CASE(1, 8, 256)

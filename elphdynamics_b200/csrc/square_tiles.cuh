@@ -186,6 +186,77 @@ __device__ __forceinline__ void exchange_edges2(const Tile<NSEG, PY>& re, const 
     }
 }
 
+// ---- honeycomb lattice, 32 unit cells wide -----------------------------------------------------------------------------------
+// Sites are numbered 2 * (l1 + L1 * l2) + orbit (src/Lattices.jl:52-107), so a row l2 is 64 consecutive values and lane l1 holds
+// the cell (A, B) = a[r][0], a[r][1] of PY rows.  The three checkerboard colours are the three bond types of
+// examples/holstein_hmc_honeycomb.toml:46-64:  A(l1,l2)-B(l1,l2) = register pair;  A(l1,l2)-B(l1-1,l2) = lane rotation;
+// A(l1,l2)-B(l1,l2-1) = row pair (registers inside a warp's rows, shared-memory strip between warps).
+template <int PY>
+__device__ __forceinline__ void hc0_cell(Tile<2, PY>& t, double c, double s) {
+#pragma unroll
+    for (int r = 0; r < PY; ++r) {
+        const double A = t.a[r][0], B = t.a[r][1];
+        t.a[r][0] = c * A + s * B;
+        t.a[r][1] = c * B + s * A;
+    }
+}
+
+template <int PY>
+__device__ __forceinline__ void hc1_lane(Tile<2, PY>& t, double c, double s, int lane) {
+#pragma unroll
+    for (int r = 0; r < PY; ++r) {
+        const double oA = __shfl_sync(0xffffffffu, t.a[r][1], (lane + 31) & 31);   // B of the cell to the left
+        const double oB = __shfl_sync(0xffffffffu, t.a[r][0], (lane + 1) & 31);    // A of the cell to the right
+        t.a[r][0] = c * t.a[r][0] + s * oA;
+        t.a[r][1] = c * t.a[r][1] + s * oB;
+    }
+}
+
+template <int PY>
+__device__ __forceinline__ void hc2_row(Tile<2, PY>& t, double c, double s, double aboveB, double belowA) {
+#pragma unroll
+    for (int r = 1; r < PY; ++r) {
+        const double A = t.a[r][0], B = t.a[r - 1][1];
+        t.a[r][0] = c * A + s * B;
+        t.a[r - 1][1] = c * B + s * A;
+    }
+    t.a[0][0] = c * t.a[0][0] + s * aboveB;
+    t.a[PY - 1][1] = c * t.a[PY - 1][1] + s * belowA;
+}
+
+// publish the first row's A and the last row's B, one barrier, fetch the B of the row above and the A of the row below.
+// strip: [nwarps][2][32]
+template <int PY>
+__device__ __forceinline__ void exchange_hc1(const Tile<2, PY>& t, double* strip, int warp, int nwarps, int lane, double& aboveB,
+                                             double& belowA) {
+    double* mine = strip + (size_t)warp * 64;
+    mine[lane] = t.a[0][0];
+    mine[32 + lane] = t.a[PY - 1][1];
+    __syncthreads();
+    const int up = (warp == 0) ? nwarps - 1 : warp - 1;
+    const int dn = (warp + 1 == nwarps) ? 0 : warp + 1;
+    aboveB = strip[(size_t)up * 64 + 32 + lane];
+    belowA = strip[(size_t)dn * 64 + lane];
+}
+
+// two tiles, one barrier.  strip: [nwarps][4][32]
+template <int PY>
+__device__ __forceinline__ void exchange_hc2(const Tile<2, PY>& t, const Tile<2, PY>& u, double* strip, int warp, int nwarps, int lane,
+                                             double& aboveB_t, double& belowA_t, double& aboveB_u, double& belowA_u) {
+    double* mine = strip + (size_t)warp * 128;
+    mine[lane] = t.a[0][0];
+    mine[32 + lane] = t.a[PY - 1][1];
+    mine[64 + lane] = u.a[0][0];
+    mine[96 + lane] = u.a[PY - 1][1];
+    __syncthreads();
+    const int up = (warp == 0) ? nwarps - 1 : warp - 1;
+    const int dn = (warp + 1 == nwarps) ? 0 : warp + 1;
+    aboveB_t = strip[(size_t)up * 128 + 32 + lane];
+    belowA_t = strip[(size_t)dn * 128 + lane];
+    aboveB_u = strip[(size_t)up * 128 + 96 + lane];
+    belowA_u = strip[(size_t)dn * 128 + 64 + lane];
+}
+
 // ---- colour groups with per-bond coefficients (SSH): (cosh, sinh) read from shared-memory tables -------------------
 // tx: [PY][LX] double2 of the tile rows, entry (r, x) = bond (x,y)-(x+1,y);  ty: same for the bond (x,y)-(x,y+1);
 // ty_halo: [LX] double2 = the y-table row above the tile (its y-odd bonds enter tile row 0).
