@@ -1130,6 +1130,18 @@ int32_t elph_dev_shard_matvec_halo(elph_handle* h, int32_t mode, double* v_own, 
     ENTER(h) {
         ELPH_REQUIRE(h->sharded, ELPH_ERR_STATE, "elph_set_shard has not been called");
         ELPH_REQUIRE(mode >= 0 && mode <= 2 && v_own && y_own, ELPH_ERR_INVALID, "bad arguments");
+        if (mode == MODE_MTM && h->halo_fused && (h->sq.enabled && !h->sq_disable)) {
+            // one launch: the exchange travels inside the product kernel, behind the interior of the slab
+            MatvecArgs f;
+            f.v = v_own;
+            f.y = y_own;
+            f.open = true;
+            f.halo = elph_shard_halo_args(h, v_own, false);
+            if (elph_launch_mtm_square(h, f)) {
+                h->p2p.hx_seq++;
+                return ELPH_OK;
+            }
+        }
         elph_shard_halo_impl(h, v_own);
         MatvecArgs a;
         a.v = v_own;
@@ -1293,6 +1305,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 18: h->pcg_half_fft = (value != 0); break;
             case 19: h->kpm_dev_arnoldi = (value != 0); break;
             case 21: h->hc_tiles = (value != 0); break;
+            case 22: h->halo_fused = (value != 0); break;
             case 20: ELPH_REQUIRE(value >= 0 && value <= 4096, ELPH_ERR_INVALID, "CTA count out of range"); h->pcg_grid = value; break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:

@@ -1282,6 +1282,23 @@ void elph_shard_halo_impl(elph_handle* h, double* v_own) {
     h->launches++;
 }
 
+// the same exchange as arguments for a product kernel that performs it itself (mtm_square.cu, HALO); `advance` consumes a tag
+HaloArgs elph_shard_halo_args(elph_handle* h, double* v_own, bool advance) {
+    auto& A = h->p2p;
+    ELPH_REQUIRE(A.arena && A.opened, ELPH_ERR_STATE, "elph_shard_p2p_open has not been called");
+    const PipeLayout Y = pipe_layout(h->N, A.Lmax);
+    auto at = [&](void* base, size_t off) { return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + A.pipe_off + off); };
+    const int left = (A.rank + A.world - 1) % A.world, right = (A.rank + 1) % A.world;
+    HaloArgs H;
+    ELPH_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&H.fail), h->h_hx_flag, 0));
+    ELPH_REQUIRE(*h->h_hx_flag == 0u, ELPH_ERR_STATE, "halo exchange: a neighbour GPU did not deliver its slice in time (timeout)");
+    H.enabled = true;
+    H.mine = at(A.arena, Y.hx); H.left = at(A.peer[left], Y.hx); H.right = at(A.peer[right], Y.hx);
+    H.v_out = v_own;
+    H.tag = advance ? ++A.hx_seq : A.hx_seq + 1;
+    return H;
+}
+
 size_t elph_pipe_arena_bytes(int N, int Lmax) { return pipe_layout(N, Lmax).total; }
 
 bool elph_cg_pipe_fits(elph_handle* h) {

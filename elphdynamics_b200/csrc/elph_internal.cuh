@@ -146,6 +146,7 @@ struct elph_handle {
     double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool kpm_exclusive = true; // KPM apply: one chain CTA per SM (shared-memory request padded)
+    bool halo_fused = true;      // sharded M^T M: halo exchange inside the product kernel (tuning key 22)
     bool hc_tiles = true;        // honeycomb lattices: register-tile kernels (tuning key 21)
     int pcg_grid = 0;            // fused PCG: CTAs of the persistent kernel (0 = one per SM); tuning key 20
     bool kpm_dev_arnoldi = true; // KPM set-up: Arnoldi eigenvalue bounds on the device (tuning key 19)
@@ -321,7 +322,20 @@ struct elph_handle {
 // ----------------------------------------------------------------------------
 enum MatvecMode { MODE_M = 0, MODE_MT = 1, MODE_MTM = 2 };
 
+// the halo exchange of a sharded product done inside the product kernel (mtm_square.cu, HALO): arena rows of this GPU and of its
+// two neighbours, the tag of this exchange and the failure flag (filled by elph_shard_halo_args, cg_pipe.cu)
+struct HaloArgs {
+    bool enabled = false;
+    unsigned long long* mine = nullptr;
+    unsigned long long* left = nullptr;
+    unsigned long long* right = nullptr;
+    unsigned int* fail = nullptr;
+    double* v_out = nullptr;
+    unsigned int tag = 0;
+};
+
 struct MatvecArgs {
+    HaloArgs halo;
     const double* v = nullptr;
     double* y = nullptr;
     const double* D = nullptr;   // nullptr -> handle's table
@@ -400,6 +414,7 @@ bool elph_cg_single_reduction(elph_handle* h, double* x_dev);
 size_t elph_pipe_arena_bytes(int N, int Lmax);
 bool elph_cg_pipe_fits(elph_handle* h);
 void elph_shard_halo_impl(elph_handle* h, double* v_own);
+HaloArgs elph_shard_halo_args(elph_handle* h, double* v_own, bool advance);
 bool elph_cg_pipe_run(elph_handle* h, const double* r0, double* x, bool x0_given, bool scalars_on_device, double tol, int64_t maxiter);
 // buffers of nrhs independent solves for the persistent kernels (right-hand side k at + k*vstride / k*pstride / k)
 struct CgBatchBufs {

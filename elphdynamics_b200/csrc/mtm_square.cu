@@ -26,6 +26,7 @@
 // partials in index order and publishes alpha (see cg.cu).
 #include "bulk_copy.cuh"
 #include "elph_internal.cuh"
+#include "ll_words.cuh"
 #include "square_tiles.cuh"
 
 namespace {
@@ -46,6 +47,13 @@ struct SqParams {
     int L, Ly, C;
     int open, tau0, Lglob;   // tau-sharded slab: halo slices at index -1 / L instead of the periodic wrap
     double c0, s0, c1, s1, c2, s2, c3, s3;
+    // HALO: the halo exchange of the sharded product inside this kernel (see HaloArgs in elph_internal.cuh)
+    unsigned long long* hx_mine;
+    unsigned long long* hx_left;
+    unsigned long long* hx_right;
+    unsigned int* hx_fail;
+    double* v_halo_out;      // the vector again, writable: the received slices are also stored in its halo rows
+    unsigned int hx_tag;
 };
 
 using namespace tma;   // mbarrier + cp.async.bulk helpers (bulk_copy.cuh)
@@ -61,7 +69,12 @@ __device__ __forceinline__ void exchange_edges(const Tile<NSEG, PY>& t, double* 
 
 // HC: honeycomb lattice 32 cells wide (NSEG = 2 = the orbitals of a cell; element (r, q) of lane l sits at r * 64 + 2 l + q of
 // the tile), three colours instead of four (hc tiles of square_tiles.cuh)
-template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false>
+// HALO (tau-sharded slab): the one-slice halo exchange of the product happens inside the kernel.  CTA 0 pushes
+// the first and the last own slice of v into the neighbour GPUs' arenas as self-validating words (ll_words.cuh) before anything
+// else; only the CTA of the first chunk (left halo, v[-1]) and of the last chunk (right halo, v[L]) wait for their slice, every
+// thread polling the elements of its own tile, while all other chunks stream as usual -- the NVLink round trip hides behind the
+// interior of the slab, and a sharded product is ONE launch instead of exchange kernel + product kernel.
+template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false, bool HALO = false>
 __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     constexpr int LX = 32 * NSEG;
     static_assert(!HC || NSEG == 2, "honeycomb tiles hold the two orbitals of a cell");
@@ -93,6 +106,26 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * kStages * STAGE_BYTES) + warp * kStages;
     double* strips = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * kStages * STAGE_BYTES + (size_t)nwarps * kStages * 8);
     const size_t tile_off = (size_t)warp * TILE;  // offset of this warp's rows inside a slice
+
+    const size_t hx_side = (size_t)N * 2, hx_par = (size_t)(P.hx_tag & 1u) * 2 * hx_side;
+    if (HALO && blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < N; e += blockDim.x) {
+            ll::push(P.hx_left + hx_par + hx_side + 2 * (size_t)e, vin[e], P.hx_tag);                    // first slice -> left GPU's hi row
+            ll::push(P.hx_right + hx_par + 2 * (size_t)e, vin[(size_t)(L - 1) * N + e], P.hx_tag);       // last slice -> right GPU's lo row
+        }
+    }
+    // wait for element e of the lo (side 0) / hi (side 1) halo row of this exchange
+    auto hx_wait = [&](int side, size_t e) -> double {
+        unsigned long long w0, w1;
+        unsigned int spins = 0;
+        bool ok;
+        do {
+            ll::ld2(P.hx_mine + hx_par + (size_t)side * hx_side + 2 * e, w0, w1);
+            ok = ll::tag_ok(w0, w1, P.hx_tag);
+        } while (!ok && ++spins < (1u << 25));
+        if (!ok) *reinterpret_cast<volatile unsigned int*>(P.hx_fail) = 1u;
+        return ll::unpack(w0, w1);
+    };
 
     if (lane == 0) {
 #pragma unroll
@@ -128,7 +161,13 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
                 const long long e = g + eoff(r, q, lane);
-                vprev.a[r][q] = FUSEP ? fma(beta, P.pold[e], P.pr[e]) : vin[e];
+                if (HALO && a == 0) {
+                    const double hv = hx_wait(0, tile_off + eoff(r, q, lane));
+                    vprev.a[r][q] = hv;
+                    P.v_halo_out[e] = hv;
+                } else {
+                    vprev.a[r][q] = FUSEP ? fma(beta, P.pold[e], P.pr[e]) : vin[e];
+                }
                 wprev.a[r][q] = 0.0;
             }
     }
@@ -172,7 +211,11 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
                 const int e = eoff(r, q, lane);
-                const double vc = FUSEP ? fma(beta, sv[TILE + e], sv[e]) : sv[e];
+                double vc = FUSEP ? fma(beta, sv[TILE + e], sv[e]) : sv[e];
+                if (HALO && a + j == L) {          // the right halo slice: from the arena, not from the (stale) halo row of v
+                    vc = hx_wait(1, tile_off + e);
+                    P.v_halo_out[(size_t)L * N + tile_off + e] = vc;
+                }
                 if (FUSEP && j < nout) P.pnew[(size_t)tau * N + tile_off + e] = vc;
                 const double w = wrap ? (vc + t.a[r][q]) : (vc - t.a[r][q]);
                 t.a[r][q] = w;
@@ -255,15 +298,15 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     }
 }
 
-template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false>
+template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false, bool HALO = false>
 void launch_sq(elph_handle* h, const SqParams& P, dim3 grid, int nwarps) {
     constexpr int LX = 32 * NSEG;
     constexpr int NT = FUSEP ? 3 : 2;
     const size_t smem = (size_t)nwarps * kStages * NT * PY * LX * sizeof(double) + (size_t)nwarps * kStages * 8 +
                         2ull * nwarps * 2 * LX * sizeof(double);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "square kernel: tile pipeline does not fit in shared memory");
-    elph_enable_smem(h, mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC>);
-    mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC><<<grid, nwarps * 32, smem, h->stream>>>(P);
+    elph_enable_smem(h, mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC, HALO>);
+    mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC, HALO><<<grid, nwarps * 32, smem, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }
@@ -395,6 +438,10 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
     P.v_stride = a.v_stride; P.y_stride = a.y_stride; P.D_stride = a.D_stride;
     P.L = h->L; P.Ly = Ly;
     P.open = a.open ? 1 : 0; P.tau0 = a.open ? h->shard_tau0 : 0; P.Lglob = a.open ? h->shard_Lglob : h->L;
+    const bool halo = a.halo.enabled && a.open && !fusep && !hc && a.nbatch == 1;
+    if (a.halo.enabled && !halo) return false;     // the caller falls back to exchange kernel + product
+    P.hx_mine = a.halo.mine; P.hx_left = a.halo.left; P.hx_right = a.halo.right; P.hx_fail = a.halo.fail; P.hx_tag = a.halo.tag;
+    P.v_halo_out = a.halo.v_out;
     int C = h->chunk_override;
     if (C <= 0) {
         // halo overhead is one extra K-sweep and one extra v slice per chunk: favour long chunks once the
@@ -422,11 +469,12 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
     dim3 grid(nchunks, (unsigned)a.nbatch);
     if (fusep) ELPH_REQUIRE(nchunks <= h->partial_cap, ELPH_ERR_INVALID, "partial buffer too small");
     if (a.npartial) *a.npartial = nchunks;
-#define SQ_CASE(NS, PYV, MAXT)                                               \
-    if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {                 \
-        if (fusep) launch_sq<NS, PYV, true, MAXT>(h, P, grid, nwarps);       \
-        else launch_sq<NS, PYV, false, MAXT>(h, P, grid, nwarps);            \
-        return true;                                                         \
+#define SQ_CASE(NS, PYV, MAXT)                                                      \
+    if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {                        \
+        if (fusep) launch_sq<NS, PYV, true, MAXT>(h, P, grid, nwarps);              \
+        else if (halo) launch_sq<NS, PYV, false, MAXT, false, true>(h, P, grid, nwarps); \
+        else launch_sq<NS, PYV, false, MAXT>(h, P, grid, nwarps);                   \
+        return true;                                                                \
     }
     if (hc) {
         if (PY == 8 && nwarps * 32 <= 256) {

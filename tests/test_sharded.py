@@ -423,6 +423,23 @@ def _check_p2p_cg(be, comm, tau0, lloc, b_glob, x_ref, it_ref):
         be.halo_p2p(v)
         torch.cuda.synchronize()
         assert torch.equal(v, ref)
+    # M^T M with the exchange INSIDE the product kernel (mtm_square.cu, HALO; tuning key 22) against exchange + product, the two
+    # forms interleaved so that the tag parity of the arena rows is exercised
+    from elphdynamics_b200.sharded import MTM_MODE
+    for rep, fused in enumerate((1, 0, 1, 1, 0, 1)):
+        v = be.empty()
+        v[1:lloc + 1] = torch.from_numpy(b_glob[tau0:tau0 + lloc] * (1.0 + 0.1 * rep)).to(v.device)
+        ref = v.clone()
+        comm.exchange(ref, lloc)
+        y_ref = be.empty()
+        be.matvec(MTM_MODE, ref, y_ref)
+        be.model._call("elph_set_tuning", 22, fused)
+        y = be.empty()
+        be.matvec_halo(MTM_MODE, v, y)
+        torch.cuda.synchronize()
+        assert torch.equal(v, ref), (rep, fused)                       # the halo rows of v are filled either way
+        assert torch.equal(y[1:lloc + 1], y_ref[1:lloc + 1]), (rep, fused)
+    be.model._call("elph_set_tuning", 22, 1)
     b = be.empty()
     b[1:lloc + 1] = torch.from_numpy(b_glob[tau0:tau0 + lloc]).to(b.device)
     x = be.empty()
