@@ -108,23 +108,40 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     const size_t tile_off = (size_t)warp * TILE;  // offset of this warp's rows inside a slice
 
     const size_t hx_side = (size_t)N * 2, hx_par = (size_t)(P.hx_tag & 1u) * 2 * hx_side;
-    if (HALO && blockIdx.x == 0) {
-        for (int e = threadIdx.x; e < N; e += blockDim.x) {
-            ll::push(P.hx_left + hx_par + hx_side + 2 * (size_t)e, vin[e], P.hx_tag);                    // first slice -> left GPU's hi row
-            ll::push(P.hx_right + hx_par + 2 * (size_t)e, vin[(size_t)(L - 1) * N + e], P.hx_tag);       // last slice -> right GPU's lo row
+    if (HALO) {
+        // the first CTAs of the grid (all in the first wave) share the push of the two boundary slices: one element per thread
+        // and slice, so the loads and the posted stores of a slice are all in flight at once
+        const int npush = min((int)gridDim.x, (N + (int)blockDim.x - 1) / (int)blockDim.x);
+        if ((int)blockIdx.x < npush) {
+            for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N; e += npush * blockDim.x) {
+                const double first = vin[e], last = vin[(size_t)(L - 1) * N + e];
+                ll::push(P.hx_left + hx_par + hx_side + 2 * (size_t)e, first, P.hx_tag);     // first slice -> left GPU's hi row
+                ll::push(P.hx_right + hx_par + 2 * (size_t)e, last, P.hx_tag);               // last slice -> right GPU's lo row
+            }
         }
     }
-    // wait for element e of the lo (side 0) / hi (side 1) halo row of this exchange
-    auto hx_wait = [&](int side, size_t e) -> double {
-        unsigned long long w0, w1;
+    // wait for this thread's tile of the lo (side 0) / hi (side 1) halo row of this exchange: all elements are polled together
+    auto hx_wait_tile = [&](int side, Tile<NSEG, PY>& out) {
+        unsigned long long w0[PY][NSEG], w1[PY][NSEG];
+        const unsigned long long* row = P.hx_mine + hx_par + (size_t)side * hx_side + 2 * tile_off;
         unsigned int spins = 0;
         bool ok;
         do {
-            ll::ld2(P.hx_mine + hx_par + (size_t)side * hx_side + 2 * e, w0, w1);
-            ok = ll::tag_ok(w0, w1, P.hx_tag);
-        } while (!ok && ++spins < (1u << 25));
+            ok = true;
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) ll::ld2(row + 2 * (size_t)eoff(r, q, lane), w0[r][q], w1[r][q]);
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) ok = ok && ll::tag_ok(w0[r][q], w1[r][q], P.hx_tag);
+        } while (!ok && ++spins < (1u << 24));
         if (!ok) *reinterpret_cast<volatile unsigned int*>(P.hx_fail) = 1u;
-        return ll::unpack(w0, w1);
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) out.a[r][q] = ll::unpack(w0[r][q], w1[r][q]);
     };
 
     if (lane == 0) {
@@ -161,15 +178,17 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 #pragma unroll
             for (int q = 0; q < NSEG; ++q) {
                 const long long e = g + eoff(r, q, lane);
-                if (HALO && a == 0) {
-                    const double hv = hx_wait(0, tile_off + eoff(r, q, lane));
-                    vprev.a[r][q] = hv;
-                    P.v_halo_out[e] = hv;
-                } else {
-                    vprev.a[r][q] = FUSEP ? fma(beta, P.pold[e], P.pr[e]) : vin[e];
-                }
+                if (!(HALO && a == 0)) vprev.a[r][q] = FUSEP ? fma(beta, P.pold[e], P.pr[e]) : vin[e];
                 wprev.a[r][q] = 0.0;
             }
+    }
+
+    if (HALO && a == 0) {     // left halo slice v[-1]: from the arena (also stored into the halo row of v for later readers)
+        hx_wait_tile(0, vprev);
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) P.v_halo_out[-(long long)N + (long long)tile_off + eoff(r, q, lane)] = vprev.a[r][q];
     }
 
     double acc = 0.0;
@@ -206,6 +225,8 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
             g3_y_odd(t, P.c3, P.s3, above, below);
         }
         // w(tau) = v(tau) -/+ t
+        Tile<NSEG, PY> hright;
+        if (HALO && a + j == L) hx_wait_tile(1, hright);
 #pragma unroll
         for (int r = 0; r < PY; ++r)
 #pragma unroll
@@ -213,7 +234,7 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
                 const int e = eoff(r, q, lane);
                 double vc = FUSEP ? fma(beta, sv[TILE + e], sv[e]) : sv[e];
                 if (HALO && a + j == L) {          // the right halo slice: from the arena, not from the (stale) halo row of v
-                    vc = hx_wait(1, tile_off + e);
+                    vc = hright.a[r][q];
                     P.v_halo_out[(size_t)L * N + tile_off + e] = vc;
                 }
                 if (FUSEP && j < nout) P.pnew[(size_t)tau * N + tile_off + e] = vc;
