@@ -305,6 +305,11 @@ void destroy(elph_handle* h) {
     elph_shard_p2p_close_impl(h);
     if (h->pipe_prof_buf) cudaFree(h->pipe_prof_buf);
     if (h->h_hx_flag) cudaFreeHost(h->h_hx_flag);
+    if (h->upload_stream) {
+        cudaStreamDestroy(h->upload_stream);
+        cudaEventDestroy(h->upload_event);
+        cudaEventDestroy(h->upload_fence);
+    }
     if (h->d_D_alloc) {  // sharded: d_D points one slice into this allocation
         cudaFree(h->d_D_alloc);
         h->d_D = nullptr;
@@ -819,9 +824,41 @@ int32_t elph_langevin_step(elph_handle* h, int32_t method, double dt, const doub
     ENTER(h) {
         ELPH_REQUIRE(method == ELPH_LANGEVIN_EULER || g2, ELPH_ERR_INVALID, "g2 is required for the two-stage updates");
         elph_trace_mark(h, nullptr);
-        upload_vec(h, eta, h->d_vc, h->Nph);
-        upload_vec(h, g1, h->d_g, h->N);
-        if (g2) upload_vec(h, g2, h->d_g2, h->N);
+        upload_vec(h, g1, h->d_g, h->N);          // needed by the first solve
+        if (method == ELPH_LANGEVIN_HEUN || !h->overlap_uploads) {
+            upload_vec(h, eta, h->d_vc, h->Nph);
+            if (g2) upload_vec(h, g2, h->d_g2, h->N);
+        } else {
+            // eta and g2 are first read after the first solve (src/LangevinDynamics.jl:188,198): their host-to-device copies and
+            // layout changes run on a second stream while that solve is under way; elph_langevin_step_dev waits for the event
+            if (!h->upload_stream) {
+                ELPH_CUDA(cudaStreamCreateWithFlags(&h->upload_stream, cudaStreamNonBlocking));
+                ELPH_CUDA(cudaEventCreateWithFlags(&h->upload_event, cudaEventDisableTiming));
+                ELPH_CUDA(cudaEventCreateWithFlags(&h->upload_fence, cudaEventDisableTiming));
+            }
+            // the second stream starts after everything already queued on the main one (the buffers may still be read by it)
+            ELPH_CUDA(cudaEventRecord(h->upload_fence, h->stream));
+            ELPH_CUDA(cudaStreamWaitEvent(h->upload_stream, h->upload_fence, 0));
+            cudaStream_t main = h->stream;
+            h->stream = h->upload_stream;          // upload_vec / the transposes queue on h->stream
+            try {
+                const size_t ne = (size_t)h->Nph * h->L, ng = (size_t)h->N * h->L;
+                double* st2 = stage(h, 2, ne);
+                ELPH_CUDA(cudaMemcpyAsync(st2, eta, ne * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                elph_to_engine(h, st2, h->d_vc, h->Nph, 1);
+                if (g2) {
+                    double* st3 = stage(h, 3, ng);
+                    ELPH_CUDA(cudaMemcpyAsync(st3, g2, ng * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                    elph_to_engine(h, st3, h->d_g2, h->N, 1);
+                }
+                ELPH_CUDA(cudaEventRecord(h->upload_event, h->stream));
+            } catch (...) {
+                h->stream = main;
+                throw;
+            }
+            h->stream = main;
+            h->upload_pending = true;
+        }
         elph_trace_mark(h, "upload eta, g1, g2");
         elph_langevin_step_dev(h, method, dt, h->d_vc, h->d_g, h->d_g2, arnoldi1, arnoldi2, use_precond != 0, iters, info1, info2);
         ELPH_CUDA(cudaStreamSynchronize(h->stream));
@@ -1306,6 +1343,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 19: h->kpm_dev_arnoldi = (value != 0); break;
             case 21: h->hc_tiles = (value != 0); break;
             case 22: h->halo_fused = (value != 0); break;
+            case 23: h->overlap_uploads = (value != 0); break;
             case 20: ELPH_REQUIRE(value >= 0 && value <= 4096, ELPH_ERR_INVALID, "CTA count out of range"); h->pcg_grid = value; break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;
             case 12:

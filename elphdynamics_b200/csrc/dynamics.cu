@@ -85,15 +85,24 @@ void elph_langevin_step_dev(elph_handle* h, int method, double dt, const double*
     const double s2dt = std::sqrt(2.0 * dt);
     double* x = h->d_x;
     double* eta = h->d_eta;
-    if (h->model == ELPH_MODEL_SSH) {
-        elph_gather_primary(h, eta, eta_dev);
-    } else {
-        ELPH_CUDA(cudaMemcpyAsync(eta, eta_dev, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    }
+    // eta (and g2) may still be on their way on the upload stream (elph_langevin_step): wait right before the first use
+    auto fetch_eta = [&]() {
+        if (h->upload_pending) {
+            ELPH_CUDA(cudaStreamWaitEvent(h->stream, h->upload_event, 0));
+            h->upload_pending = false;
+        }
+        if (h->model == ELPH_MODEL_SSH) {
+            elph_gather_primary(h, eta, eta_dev);
+        } else {
+            ELPH_CUDA(cudaMemcpyAsync(eta, eta_dev, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
+    };
+    if (method == ELPH_LANGEVIN_HEUN) fetch_eta();
     elph_solve_info i1 = {}, i2 = {};
     if (method == ELPH_LANGEVIN_EULER) {
         elph_launch_update_model(h);                                                       // :91
         elph_calc_dSdx_dev(h, g1_dev, arn1, use_precond, h->d_dSdx, h->d_Minv, &i1);       // :101
+        fetch_eta();
         elph_fourier_accelerate_dev(h, h->d_dSdx, h->d_dSdx, 1.0, false);                  // :104
         elph_fourier_accelerate_dev(h, eta, eta, 0.5, false);                              // :107
         elph_lincomb(h, h->d_dx, s2dt, eta, -dt, h->d_dSdx, 0.0, nullptr, nd);             // :110
@@ -103,6 +112,7 @@ void elph_langevin_step_dev(elph_handle* h, int method, double dt, const double*
     } else if (method == ELPH_LANGEVIN_RK) {
         elph_launch_update_model(h);                                                       // :178
         elph_calc_dSdx_dev(h, g1_dev, arn1, use_precond, h->d_dSdx, h->d_Minv, &i1);       // :185
+        fetch_eta();
         elph_lincomb(h, h->d_dx, s2dt, eta, -dt, h->d_dSdx, 0.0, nullptr, nd);             // :188
         elph_lincomb(h, x, 1.0, x, 1.0, h->d_dx, 0.0, nullptr, nd);                        // :191
         elph_launch_update_model(h);                                                       // :194

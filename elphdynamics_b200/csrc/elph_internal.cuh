@@ -146,6 +146,10 @@ struct elph_handle {
     double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool kpm_exclusive = true; // KPM apply: one chain CTA per SM (shared-memory request padded)
+    bool overlap_uploads = true; // elph_langevin_step: eta and g2 travel on a second stream during the first solve (tuning key 23)
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t upload_event = nullptr, upload_fence = nullptr;
+    bool upload_pending = false;
     bool halo_fused = true;      // sharded M^T M: halo exchange inside the product kernel (tuning key 22)
     bool hc_tiles = true;        // honeycomb lattices: register-tile kernels (tuning key 21)
     int pcg_grid = 0;            // fused PCG: CTAs of the persistent kernel (0 = one per SM); tuning key 20
