@@ -146,6 +146,7 @@ struct elph_handle {
     double trace_t0 = 0.0;
     bool kpm_split = true;     // KPM apply: one 2-CTA cluster per frequency (re / im chains), see kpm_square.cu
     bool kpm_exclusive = true; // KPM apply: one chain CTA per SM (shared-memory request padded)
+    bool mtm_tanh = true;        // fused M^T M on square lattices: sweeps in tanh form (tuning key 24)
     bool overlap_uploads = true; // elph_langevin_step: eta and g2 travel on a second stream during the first solve (tuning key 23)
     cudaStream_t upload_stream = nullptr;
     cudaEvent_t upload_event = nullptr, upload_fence = nullptr;

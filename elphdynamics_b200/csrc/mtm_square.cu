@@ -47,6 +47,7 @@ struct SqParams {
     int L, Ly, C;
     int open, tau0, Lglob;   // tau-sharded slab: halo slices at index -1 / L instead of the periodic wrap
     double c0, s0, c1, s1, c2, s2, c3, s3;
+    double t0, t1, t2, t3, cprod;   // tanh form: t_g = s_g / c_g, cprod = c0 c1 c2 c3
     // HALO: the halo exchange of the sharded product inside this kernel (see HaloArgs in elph_internal.cuh)
     unsigned long long* hx_mine;
     unsigned long long* hx_left;
@@ -74,7 +75,10 @@ __device__ __forceinline__ void exchange_edges(const Tile<NSEG, PY>& t, double* 
 // else; only the CTA of the first chunk (left halo, v[-1]) and of the last chunk (right halo, v[L]) wait for their slice, every
 // thread polling the elements of its own tile, while all other chunks stream as usual -- the NVLink round trip hides behind the
 // interior of the slab, and a sharded product is ONE launch instead of exchange kernel + product kernel.
-template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false, bool HALO = false>
+// TANH (square lattices): the sweeps in tanh form (square_tiles.cuh) -- K = (c0 c1 c2 c3) prod_g (1 + t_g X_g), the constant folded
+// into D: 12 fp64 operations per lattice point and product instead of 20.  The kernel is HBM bound at full clocks but loses ~13 %
+// when the SM clock drops under the power cap, i.e. it is then limited by instruction issue; the result differs by rounding only.
+template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false, bool HALO = false, bool TANH = false>
 __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     constexpr int LX = 32 * NSEG;
     static_assert(!HC || NSEG == 2, "honeycomb tiles hold the two orbitals of a cell");
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     for (int j = 0; j < kStages; ++j)
         if (j < nsteps) issue(j);
 
-    Tile<NSEG, PY> vprev, wprev, t, u;
+    Tile<NSEG, PY> vprev, wprev, t, u, dsc;
     {   // v(a-1), straight from global (coalesced, once per chunk)
         const int taum = (a == 0) ? (P.open ? -1 : L - 1) : a - 1;   // open slab: index -1 is the left halo slice
         const long long g = (long long)taum * N + (long long)tile_off;
@@ -207,9 +211,23 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 #pragma unroll
         for (int r = 0; r < PY; ++r)
 #pragma unroll
-            for (int q = 0; q < NSEG; ++q) t.a[r][q] = sD[eoff(r, q, lane)] * vprev.a[r][q];
+            for (int q = 0; q < NSEG; ++q) {
+                if constexpr (TANH) {
+                    dsc.a[r][q] = P.cprod * sD[eoff(r, q, lane)];
+                    t.a[r][q] = dsc.a[r][q] * vprev.a[r][q];
+                } else {
+                    t.a[r][q] = sD[eoff(r, q, lane)] * vprev.a[r][q];
+                }
+            }
         // t = K t : the colour groups in order
-        if constexpr (HC) {
+        if constexpr (TANH) {
+            g0_x_even_t(t, P.t0);
+            g1_x_odd_t(t, P.t1, lane);
+            g2_y_even_t(t, P.t2);
+            exchange_edges(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+            xbuf ^= 1;
+            g3_y_odd_t(t, P.t3, above, below);
+        } else if constexpr (HC) {
             hc0_cell(t, P.c0, P.s0);
             hc1_lane(t, P.c1, P.s1, lane);
             double aB, bA;
@@ -249,7 +267,14 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
             for (int r = 0; r < PY; ++r)
 #pragma unroll
                 for (int q = 0; q < NSEG; ++q) u.a[r][q] = t.a[r][q];
-            if constexpr (HC) {
+            if constexpr (TANH) {
+                exchange_edges(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
+                xbuf ^= 1;
+                g3_y_odd_t(u, P.t3, above, below);
+                g2_y_even_t(u, P.t2);
+                g1_x_odd_t(u, P.t1, lane);
+                g0_x_even_t(u, P.t0);
+            } else if constexpr (HC) {
                 double aB, bA;
                 exchange_hc1(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, aB, bA);
                 xbuf ^= 1;
@@ -272,8 +297,12 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
 #pragma unroll
                 for (int q = 0; q < NSEG; ++q) {
                     const int e = eoff(r, q, lane);
-                    const double du = sD[e] * u.a[r][q];
-                    y[g + e] = wrap ? (wprev.a[r][q] + du) : (wprev.a[r][q] - du);
+                    if constexpr (TANH) {
+                        y[g + e] = wrap ? fma(dsc.a[r][q], u.a[r][q], wprev.a[r][q]) : fma(-dsc.a[r][q], u.a[r][q], wprev.a[r][q]);
+                    } else {
+                        const double du = sD[e] * u.a[r][q];
+                        y[g + e] = wrap ? (wprev.a[r][q] + du) : (wprev.a[r][q] - du);
+                    }
                 }
         }
 #pragma unroll
@@ -319,15 +348,15 @@ __global__ void __launch_bounds__(MAXT) mtm_square_kernel(SqParams P) {
     }
 }
 
-template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false, bool HALO = false>
+template <int NSEG, int PY, bool FUSEP, int MAXT, bool HC = false, bool HALO = false, bool TANH = false>
 void launch_sq(elph_handle* h, const SqParams& P, dim3 grid, int nwarps) {
     constexpr int LX = 32 * NSEG;
     constexpr int NT = FUSEP ? 3 : 2;
     const size_t smem = (size_t)nwarps * kStages * NT * PY * LX * sizeof(double) + (size_t)nwarps * kStages * 8 +
                         2ull * nwarps * 2 * LX * sizeof(double);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "square kernel: tile pipeline does not fit in shared memory");
-    elph_enable_smem(h, mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC, HALO>);
-    mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC, HALO><<<grid, nwarps * 32, smem, h->stream>>>(P);
+    elph_enable_smem(h, mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC, HALO, TANH>);
+    mtm_square_kernel<NSEG, PY, FUSEP, MAXT, HC, HALO, TANH><<<grid, nwarps * 32, smem, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }
@@ -482,6 +511,9 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
     P.C = C;
     P.c0 = h->sq.c[0]; P.s0 = h->sq.s[0]; P.c1 = h->sq.c[1]; P.s1 = h->sq.s[1];
     P.c2 = h->sq.c[2]; P.s2 = h->sq.s[2]; P.c3 = h->sq.c[3]; P.s3 = h->sq.s[3];
+    P.t0 = P.s0 / P.c0; P.t1 = P.s1 / P.c1; P.t2 = P.s2 / P.c2; P.t3 = P.s3 / P.c3;
+    P.cprod = P.c0 * P.c1 * P.c2 * P.c3;
+    const bool tanh_form = h->mtm_tanh && !hc;
     if (hc) {
         P.c0 = h->hc.c[0]; P.s0 = h->hc.s[0]; P.c1 = h->hc.c[1]; P.s1 = h->hc.s[1];
         P.c2 = h->hc.c[2]; P.s2 = h->hc.s[2]; P.c3 = 1.0; P.s3 = 0.0;
@@ -493,7 +525,9 @@ bool elph_launch_mtm_square(elph_handle* h, const MatvecArgs& a) {
 #define SQ_CASE(NS, PYV, MAXT)                                                      \
     if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {                        \
         if (fusep) launch_sq<NS, PYV, true, MAXT>(h, P, grid, nwarps);              \
+        else if (halo && tanh_form) launch_sq<NS, PYV, false, MAXT, false, true, true>(h, P, grid, nwarps); \
         else if (halo) launch_sq<NS, PYV, false, MAXT, false, true>(h, P, grid, nwarps); \
+        else if (tanh_form) launch_sq<NS, PYV, false, MAXT, false, false, true>(h, P, grid, nwarps); \
         else launch_sq<NS, PYV, false, MAXT>(h, P, grid, nwarps);                   \
         return true;                                                                \
     }
