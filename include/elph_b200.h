@@ -395,7 +395,17 @@ int32_t elph_set_chunk(elph_handle* h, int32_t slices_per_cta);
  *      the reference loop; -1 = auto (default: on unless key 7 forces one of the older forms), 0 = off, 1 = on),
  * 11 = CTAs per time slice of the pipelined kernel (0 = auto, else 1, 2, 4, 8),
  * 12 = per-phase cycle counters of the pipelined kernel (development aid), 13 = force one variant of the pipelined kernel
- *      (0 = auto), 14 = time slices per CTA of its multi-slice variants (0 = the smallest number that makes the slab co-resident) */
+ *      (0 = auto), 14 = time slices per CTA of its multi-slice variants (0 = the smallest number that makes the slab co-resident),
+ * 15 = cluster barrier flavour of the pipelined kernel (development aid; default = full cluster barrier),
+ * 16 = KPM chains with the sweeps in tanh form and the constants folded (default 1; differs from the plain form by rounding),
+ * 17 = the KPM-preconditioned solve (solve!(x,A,b,cg,P), src/IterativeSolvers.jl:153-234) as ONE persistent cooperative kernel
+ *      where served (csrc/pcg_fused.cu: Holstein on 32-wide square lattices; default 1), 18 = its tau-FFTs at half length for
+ *      even Ltau (default 1), 20 = its CTA count (0 = one per SM; SMs / K when K chains share one GPU),
+ * 19 = Arnoldi eigenvalue bounds of setup!(P) (src/KPMPreconditioners.jl:845-942) on the device (default 1; 0 = host loops),
+ * 21 = register-tile kernels for the honeycomb lattice 32 cells wide (default 1),
+ * 22 = tau-sharded M^T M with the halo exchange inside the product kernel (default 1; 0 = exchange kernel + product kernel),
+ * 23 = elph_langevin_step: eta and g2 travel host-to-device on a second stream during the first solve (default 1),
+ * 24 = fused M^T M on square lattices with the sweeps in tanh form (default 1) */
 int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value);
 /* read-back of a tuning key; key 100 = which kernel served the last unpreconditioned persistent solve: 0 = none yet /
  * other kernels, else variant * 100 + CTAs per slice * 10 + warps per CTA of the pipelined kernel; key 101 = its time slices per CTA */
