@@ -578,6 +578,31 @@ def main():
                     "lattice point (805 MB per launch vs 126 MB L2); tables_us = update_model! of all replicas in one launch "
                     "(elph_dev_ssh_replica_tables)"}
         del XC, TC, VC, YC
+        # the second Langevin configuration of BASELINE.json (examples/ssh_langevin_square.toml scaled to 32x32, L = 200):
+        # Runge-Kutta steps with Fourier acceleration (mass 0.1) and the KPM-preconditioned solve as one persistent kernel
+        try:
+            PC = E.SymmetricKPMPreconditioner(mC)
+            faC = E.FourierAccelerator(mC)
+            E.update_Q_(faC, mC, 0.0, 10.0, 0.1)
+            dynC = E.RungeKuttaDynamics(mC, 1e-3)
+            nzC = [dict(eta=rC.normal(size=mC.Ndof), g1=rC.normal(size=nC), g2=rC.normal(size=nC),
+                        arnoldi1=rC.normal(size=2 * NC), arnoldi2=rC.normal(size=2 * NC)) for _ in range(6)]
+            for z in nzC:
+                for key in ("eta", "g1", "g2"):
+                    mC.pin_host(z[key])
+            E.evolve_(mC, dynC, faC, PC, **nzC[0])
+            t0 = time.perf_counter()
+            itsC = [int(E.evolve_(mC, dynC, faC, PC, **z)) for z in nzC[1:]]
+            dtC = (time.perf_counter() - t0) / 5
+            for z in nzC:
+                for key in ("eta", "g1", "g2"):
+                    mC.unpin_host(z[key])
+            extra["ssh_square_32x32_L200"]["langevin_rk_kpm"] = {
+                "steps_per_s": 1.0 / dtC, "pcg_iters_second_solve": itsC,
+                "note": "elph_langevin_step, SSH model: 2 KPM set-ups + 2 KPM-PCG solves (one persistent kernel each, per-slice "
+                        "(cosh, sinh) tables resident in shared memory) + forces + Fourier acceleration"}
+        except Exception as exc:
+            extra["ssh_square_32x32_L200"]["langevin_rk_kpm"] = {"error": str(exc)[:200]}
         mC.close()
 
         # ---- configuration D: HMC trajectory on the honeycomb lattice L=32 (N=2048, Ltau=20), Nt=10 leapfrog steps ----

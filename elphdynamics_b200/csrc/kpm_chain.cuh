@@ -26,6 +26,108 @@ struct KsqParams {
     unsigned long long* prof;   // development aid (tuning key 12): clock64 stamps of the cluster of the longest polynomial
 };
 
+// ---- plain form (any coefficients per colour, or per-bond tables) -------------------------------------------------------
+// TAB: per-bond (cosh, sinh) from shared-memory tables in the tile layout [direction][site] (SSH: the tau-averaged hoppings of
+// src/KPMPreconditioners.jl:355-381); otherwise one pair per colour (Holstein).
+template <int NSEG, int PY, bool TRANSPOSED, bool TAB = false>
+__device__ __forceinline__ void apply_A_real(Tile<NSEG, PY>& s, const Tile<NSEG, PY>& ev, const KsqParams& P, double* strips,
+                                             int& xbuf, int warp, int nwarps, int lane, const double2* tabs = nullptr) {
+    constexpr int LX = 32 * NSEG;
+    double ab[NSEG], be[NSEG];
+    if (TAB) {
+        const int N = LX * P.Ly, y0 = warp * PY;
+        const double2* tx = tabs + (size_t)y0 * LX;
+        const double2* ty = tabs + N + (size_t)y0 * LX;
+        const double2* ty_halo = tabs + N + (size_t)((y0 + P.Ly - 1) % P.Ly) * LX;
+        if (!TRANSPOSED) {
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+            g0_tab(s, tx, lane);
+            g1_tab(s, tx, lane);
+            g2_tab(s, ty, lane);
+            exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+            xbuf ^= 1;
+            g3_tab(s, ty, ty_halo, lane, ab, be);
+        } else {
+            exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+            xbuf ^= 1;
+            g3_tab(s, ty, ty_halo, lane, ab, be);
+            g2_tab(s, ty, lane);
+            g1_tab(s, tx, lane);
+            g0_tab(s, tx, lane);
+#pragma unroll
+            for (int r = 0; r < PY; ++r)
+#pragma unroll
+                for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+        }
+        return;
+    }
+    if (!TRANSPOSED) {
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+        g0_x_even(s, P.c0, P.s0);
+        g1_x_odd(s, P.c1, P.s1, lane);
+        g2_y_even(s, P.c2, P.s2);
+        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+        xbuf ^= 1;
+        g3_y_odd(s, P.c3, P.s3, ab, be);
+    } else {
+        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+        xbuf ^= 1;
+        g3_y_odd(s, P.c3, P.s3, ab, be);
+        g2_y_even(s, P.c2, P.s2);
+        g1_x_odd(s, P.c1, P.s1, lane);
+        g0_x_even(s, P.c0, P.s0);
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) s.a[r][q] *= ev.a[r][q];
+    }
+}
+
+// A = sum_n cr_n T_n v ,  B = sum_n ci'_n T_n v   (ci' = -ci for the transposed/conjugated pass)
+template <int NSEG, int PY, bool TRANSPOSED, bool TAB = false>
+__device__ __forceinline__ void poly_real(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, const Tile<NSEG, PY>& vin, const Tile<NSEG, PY>& ev,
+                                          const cplx* c_s, int order, const KsqParams& P, double* strips, int& xbuf, int warp,
+                                          int nwarps, int lane, const double2* tabs = nullptr) {
+    Tile<NSEG, PY> un, uprev, s;
+    const double sg = TRANSPOSED ? -1.0 : 1.0;
+    const double c0r = c_s[0].x, c0i = sg * c_s[0].y;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const double v = vin.a[r][q];
+            A.a[r][q] = c0r * v;
+            B.a[r][q] = c0i * v;
+            un.a[r][q] = v;
+            uprev.a[r][q] = 0.0;
+        }
+    const double k1 = P.inv_mag, k2 = P.avg_over_mag;
+    for (int n = 1; n < order; ++n) {
+        s = un;
+        apply_A_real<NSEG, PY, TRANSPOSED, TAB>(s, ev, P, strips, xbuf, warp, nwarps, lane, tabs);
+        const double cr = c_s[n].x, ci = sg * c_s[n].y;
+        const double two = (n > 1) ? 2.0 : 1.0, one = (n > 1) ? 1.0 : 0.0;
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                double a = k1 * s.a[r][q] - k2 * un.a[r][q];
+                a = two * a - one * uprev.a[r][q];
+                uprev.a[r][q] = un.a[r][q];
+                un.a[r][q] = a;
+                A.a[r][q] += cr * a;
+                B.a[r][q] += ci * a;
+            }
+    }
+}
+
+
 // The same polynomial with the sweep in tanh form and the constants folded (9 / 8 fp64 operations per site and Chebyshev term
 // instead of 15; the chain of the lowest frequency is what an apply waits for):
 //     evs = 2 (c0 c1 c2 c3 / mag) eVbar ;  Kt = prod_g (1 + t_g X_g)

@@ -41,7 +41,8 @@ struct FusedParams {
     double* z;
     cplx* nu_in;
     cplx* nu_out;
-    const double* D;        // expnV [L][N]
+    const double* D;        // Holstein: expnV [L][N]; SSH: exp(dtau mu) [N]
+    const double2* ssh_tab; // SSH: (cosh, sinh)(dtau t') per time slice in the tile layout [L][2][N] (ssh_square.cu)
     FftPlan plan;
     FftPlan plan_half;      // L even: the transforms run at length L/2 (see phase F)
     const cplx* tw;
@@ -110,7 +111,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // (registers capped below the full register file of an SM -- 512 threads x 128 -- so that the cooperative launch also fits when a
 //  profiler or debugger reserves resources on the SM)
-template <int NSEG, int PY, int SB, int MAXT>
+// SSH: per-bond hoppings.  The chains read the tau-averaged tables of the preconditioner and the product phase the tables of the
+// CTA's own time slices (chunk + halo slice); both sets stay in shared memory for the whole solve (the field is fixed during a
+// solve and the chunk of a CTA never changes).
+template <int NSEG, int PY, int SB, int MAXT, bool SSH = false>
 __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams P) {
     constexpr int LX = 32 * NSEG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,6 +139,11 @@ __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams
     cplx* c_s = reinterpret_cast<cplx*>(region);                                  // [max_order]
     double* strips = reinterpret_cast<double*>(c_s + P.max_order);                // 2 x [nwarps][2][LX]
     double* xch = strips + 2ull * nwarps * 2 * LX;                                // 2 x [N], written by the partner CTA
+    // SSH tables behind the region shared by the phases
+    const size_t region_bytes = max(2ull * L * SB * sizeof(cplx),
+                                    (size_t)P.max_order * sizeof(cplx) + (2ull * nwarps * 2 * LX + 2ull * N) * sizeof(double));
+    double2* tabbar = reinterpret_cast<double2*>(region + ((region_bytes + 15) & ~size_t(15)));   // [2][N] tau-averaged
+    double2* tabA = tabbar + 2 * N;                                                               // [Cs + 1][2][N]
 
     const bool half = (L % 2 == 0) && P.plan_half.L == L / 2;
     const int Lh = L / 2;
@@ -147,6 +156,17 @@ __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams
         failed = 0;
         plans[0] = P.plan;
         plans[1] = P.plan_half;
+    }
+    if constexpr (SSH) {
+        for (int k = threadIdx.x; k < 2 * N; k += blockDim.x) tabbar[k] = P.K.tab[k];
+        if (cta < P.nchunks) {
+            const int a0 = cta * P.Cs, ns = min(P.Cs, L - a0) + 1;
+            for (int j = 0; j < ns; ++j) {
+                int tau = a0 + j;
+                if (tau >= L) tau -= L;
+                for (int k = threadIdx.x; k < 2 * N; k += blockDim.x) tabA[(size_t)j * 2 * N + k] = P.ssh_tab[(size_t)tau * 2 * N + k];
+            }
+        }
     }
     __syncthreads();
     cluster_sync_all();   // the partner CTA is running before its shared memory is addressed
@@ -322,7 +342,7 @@ __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams
                     for (int q = 0; q < NSEG; ++q) {
                         const size_t e = tile_off + r * LX + 32 * q + lane;
                         v.a[r][q] = __ldcg(in_comp + 2 * ((size_t)w * N + e));
-                        evs.a[r][q] = sc * P.K.eVbar[e];
+                        evs.a[r][q] = (SSH ? 1.0 : sc) * P.K.eVbar[e];
                     }
                 __syncthreads();
                 // the two exchange buffers alternate: the partner writes buffer b again only after it has passed the cluster
@@ -347,10 +367,17 @@ __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams
                     ++nswap;
                 };
                 int xbuf = 0;
-                poly_real_fast<NSEG, PY, true>(A, B, v, evs, c_s, order, P.K, strips, xbuf, warp, nwarps, lane);
-                swap_combine(t1);
-                poly_real_fast<NSEG, PY, false>(A, B, t1, evs, c_s, order, P.K, strips, xbuf, warp, nwarps, lane);
-                swap_combine(v);
+                if constexpr (SSH) {
+                    poly_real<NSEG, PY, true, true>(A, B, v, evs, c_s, order, P.K, strips, xbuf, warp, nwarps, lane, tabbar);
+                    swap_combine(t1);
+                    poly_real<NSEG, PY, false, true>(A, B, t1, evs, c_s, order, P.K, strips, xbuf, warp, nwarps, lane, tabbar);
+                    swap_combine(v);
+                } else {
+                    poly_real_fast<NSEG, PY, true>(A, B, v, evs, c_s, order, P.K, strips, xbuf, warp, nwarps, lane);
+                    swap_combine(t1);
+                    poly_real_fast<NSEG, PY, false>(A, B, t1, evs, c_s, order, P.K, strips, xbuf, warp, nwarps, lane);
+                    swap_combine(v);
+                }
 #pragma unroll
                 for (int r = 0; r < PY; ++r)
 #pragma unroll
@@ -514,15 +541,27 @@ __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams
                         for (int q = 0; q < NSEG; ++q) {
                             const size_t e = g + r * LX + 32 * q + lane;
                             vc.a[r][q] = fma(beta, __ldcg(pold + e), __ldcg(P.z + e));
-                            dt.a[r][q] = P.D[e];
+                            dt.a[r][q] = SSH ? P.D[tile_off + r * LX + 32 * q + lane] : P.D[e];
                             t.a[r][q] = dt.a[r][q] * vprev.a[r][q];
                         }
-                    g0_x_even(t, P.K.c0, P.K.s0);
-                    g1_x_odd(t, P.K.c1, P.K.s1, lane);
-                    g2_y_even(t, P.K.c2, P.K.s2);
+                    // SSH: K(tau) from the CTA's resident tables (x bonds, y bonds, the y row above the tile)
+                    const int y0 = warp * PY;
+                    const double2* txs = tabA + (size_t)j * 2 * N + (size_t)y0 * LX;
+                    const double2* tys = tabA + (size_t)j * 2 * N + N + (size_t)y0 * LX;
+                    const double2* hys = tabA + (size_t)j * 2 * N + N + (size_t)((y0 + P.Ly - 1) % P.Ly) * LX;
+                    if constexpr (SSH) {
+                        g0_tab(t, txs, lane);
+                        g1_tab(t, txs, lane);
+                        g2_tab(t, tys, lane);
+                    } else {
+                        g0_x_even(t, P.K.c0, P.K.s0);
+                        g1_x_odd(t, P.K.c1, P.K.s1, lane);
+                        g2_y_even(t, P.K.c2, P.K.s2);
+                    }
                     exchange_edges1(t, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
                     xbuf ^= 1;
-                    g3_y_odd(t, P.K.c3, P.K.s3, above, below);
+                    if constexpr (SSH) g3_tab(t, tys, hys, lane, above, below);
+                    else g3_y_odd(t, P.K.c3, P.K.s3, above, below);
 #pragma unroll
                     for (int r = 0; r < PY; ++r)
 #pragma unroll
@@ -541,10 +580,17 @@ __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams
                             for (int q = 0; q < NSEG; ++q) u.a[r][q] = t.a[r][q];
                         exchange_edges1(u, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, above, below);
                         xbuf ^= 1;
-                        g3_y_odd(u, P.K.c3, P.K.s3, above, below);
-                        g2_y_even(u, P.K.c2, P.K.s2);
-                        g1_x_odd(u, P.K.c1, P.K.s1, lane);
-                        g0_x_even(u, P.K.c0, P.K.s0);
+                        if constexpr (SSH) {
+                            g3_tab(u, tys, hys, lane, above, below);
+                            g2_tab(u, tys, lane);
+                            g1_tab(u, txs, lane);
+                            g0_tab(u, txs, lane);
+                        } else {
+                            g3_y_odd(u, P.K.c3, P.K.s3, above, below);
+                            g2_y_even(u, P.K.c2, P.K.s2);
+                            g1_x_odd(u, P.K.c1, P.K.s1, lane);
+                            g0_x_even(u, P.K.c0, P.K.s0);
+                        }
                         const size_t gm = (size_t)(a + j - 1) * N + tile_off;
 #pragma unroll
                         for (int r = 0; r < PY; ++r)
@@ -589,17 +635,24 @@ __global__ void __maxnreg__(MAXT == 512 ? 120 : 56) pcg_fused_kernel(FusedParams
 }
 
 template <int NSEG, int PY, int SB>
-size_t fused_smem(int L, int Ly, int nwarps, int max_order) {
+size_t fused_smem(int L, int Ly, int nwarps, int max_order, int ssh_slices) {
     constexpr int LX = 32 * NSEG;
     const size_t fft = 2ull * L * SB * sizeof(cplx);
     const size_t chain = (size_t)max_order * sizeof(cplx) + (2ull * nwarps * 2 * LX + 2ull * LX * Ly) * sizeof(double);
-    return (2ull * L + (L + 1) / 2) * sizeof(cplx) + std::max(fft, chain);
+    const size_t region = (std::max(fft, chain) + 15) & ~size_t(15);
+    // SSH: the tau-averaged tables + the tables of the CTA's slices (chunk + halo), 2 N (cosh, sinh) pairs each
+    const size_t tabs = ssh_slices ? (size_t)(1 + ssh_slices) * 2 * LX * Ly * sizeof(double2) : 0;
+    return (2ull * L + (L + 1) / 2) * sizeof(cplx) + region + tabs;
 }
 
-template <int NSEG, int PY, int SB, int MAXT>
+template <int NSEG, int PY, int SB, int MAXT, bool SSH = false>
 bool launch_fused(elph_handle* h, FusedParams& P, int nwarps) {
-    auto kern = pcg_fused_kernel<NSEG, PY, SB, MAXT>;
-    const size_t smem = fused_smem<NSEG, PY, SB>(h->L, P.Ly, nwarps, P.max_order);
+    auto kern = pcg_fused_kernel<NSEG, PY, SB, MAXT, SSH>;
+    // SSH keeps the tables of a CTA's slices resident: the chunk length is fixed by the full grid (one CTA per SM)
+    int full = h->sm_count & ~1;
+    if (h->pcg_grid >= 2) full = std::min(full, h->pcg_grid & ~1);
+    const int cs_full = (h->L + full - 1) / full;
+    const size_t smem = fused_smem<NSEG, PY, SB>(h->L, P.Ly, nwarps, P.max_order, SSH ? cs_full + 1 : 0);
     if (smem > h->smem_optin) return false;
     elph_enable_smem(h, kern);
     const int threads = nwarps * 32;
@@ -620,6 +673,7 @@ bool launch_fused(elph_handle* h, FusedParams& P, int nwarps) {
     if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
     if (nclusters < 1) return false;
     grid = std::min(grid, 2 * nclusters);
+    if (SSH && (h->L + grid - 1) / grid != cs_full) return false;   // fewer co-resident CTAs than assumed: tables would not fit
     cfg.gridDim = dim3(grid);
     // slices per chunk of the product phase: every CTA at most one chunk
     P.Cs = (h->L + grid - 1) / grid;
@@ -658,10 +712,13 @@ FftPlan elph_fft_plan(const elph_handle* h) {
 // The whole preconditioned solve after cg_init_kernel (r = b - A x0, the norms and the stop-rule constants in h->d_cg) in one
 // launch.  Returns false when the configuration is not served (the caller runs the launch-per-phase loop).
 bool elph_pcg_fused(elph_handle* h, double* x_dev, double* z_dev) {
-    if (!h->pcg_persistent || h->model != ELPH_MODEL_HOLSTEIN || !h->sq.enabled || h->sq_disable || h->sharded) return false;
+    const bool ssh = (h->model == ELPH_MODEL_SSH);
+    if (!h->pcg_persistent || h->sq_disable || h->sharded) return false;
+    if (ssh ? !h->ssq.enabled : !h->sq.enabled) return false;
     const KpmState& K = h->kpm;
     if (!K.active || !K.d_coeff) return false;
-    const int Lx = h->sq.Lx, Ly = h->sq.Ly;
+    if (ssh && !K.d_csbar_tile) return false;
+    const int Lx = ssh ? h->ssq.Lx : h->sq.Lx, Ly = ssh ? h->ssq.Ly : h->sq.Ly;
     if (Lx != 32 || Ly % 2 || Ly / 2 < 2 || Ly / 2 > 32 || h->L < 4) return false;
     const int nwarps = Ly / 2;
     int max_order = 1;
@@ -687,16 +744,22 @@ bool elph_pcg_fused(elph_handle* h, double* x_dev, double* z_dev) {
     Q.in = nullptr; Q.out = nullptr; Q.eVbar = K.d_eVbar; Q.coeff = K.d_coeff; Q.order = K.d_order; Q.coeff_off = K.d_coeff_off;
     Q.schedule = K.d_schedule; Q.skip = nullptr; Q.L = h->L; Q.Ly = Ly;
     Q.inv_mag = 1.0 / K.lam_mag; Q.avg_over_mag = K.lam_avg / K.lam_mag;
-    Q.c0 = h->sq.c[0]; Q.s0 = h->sq.s[0]; Q.c1 = h->sq.c[1]; Q.s1 = h->sq.s[1];
-    Q.c2 = h->sq.c[2]; Q.s2 = h->sq.s[2]; Q.c3 = h->sq.c[3]; Q.s3 = h->sq.s[3];
+    if (ssh) {
+        Q.c0 = Q.c1 = Q.c2 = Q.c3 = 1.0; Q.s0 = Q.s1 = Q.s2 = Q.s3 = 0.0;
+    } else {
+        Q.c0 = h->sq.c[0]; Q.s0 = h->sq.s[0]; Q.c1 = h->sq.c[1]; Q.s1 = h->sq.s[1];
+        Q.c2 = h->sq.c[2]; Q.s2 = h->sq.s[2]; Q.c3 = h->sq.c[3]; Q.s3 = h->sq.s[3];
+    }
     Q.t0 = Q.s0 / Q.c0; Q.t1 = Q.s1 / Q.c1; Q.t2 = Q.s2 / Q.c2; Q.t3 = Q.s3 / Q.c3;
     Q.cprod = Q.c0 * Q.c1 * Q.c2 * Q.c3;
-    Q.fast = 1; Q.prof = nullptr; Q.tab = nullptr;
+    Q.fast = ssh ? 0 : 1; Q.prof = nullptr; Q.tab = ssh ? K.d_csbar_tile : nullptr;
+    P.ssh_tab = ssh ? h->ssq.d_tab : nullptr;
     P.Lo2 = K.Lo2; P.max_order = max_order;
     P.partial = h->d_partial; P.bar = h->d_bar; P.S = h->d_cg;
     P.L = h->L; P.Ly = Ly; P.Cs = 1; P.nchunks = h->L;
     P.prof = h->pipe_prof ? h->pipe_prof_buf : nullptr;
     ELPH_CUDA(cudaMemsetAsync(h->d_p[1], 0, h->Ndim * sizeof(double), h->stream));   // p_old of the first product (beta = 0)
+    if (ssh) return (nwarps * 32 <= 512) ? launch_fused<1, 2, 8, 512, true>(h, P, nwarps) : false;
     if (nwarps * 32 <= 512) return launch_fused<1, 2, 8, 512>(h, P, nwarps);
     return launch_fused<1, 2, 8, 1024>(h, P, nwarps);
 }

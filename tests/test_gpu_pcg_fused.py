@@ -181,6 +181,17 @@ def test_ssh_kpm_apply_register_chains(beta, dtau):
     om.mulMT(b, g)
     xo, xe = np.zeros(om.Ndim), np.zeros(om.Ndim)
     it_o, _, f_o = ldiv(xo, om, b, ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter), Po)
+    l0 = em.launch_count()
     it_e, _, f_e = E.ldiv_(xe, em, b, Pe)
+    n_fused = em.launch_count() - l0
     assert f_o == f_e == 0 and abs(it_o - it_e) <= 2 and relerr(xe, xo) <= 50 * om.tol
+    # the SSH solve is one persistent kernel as well (per-slice tables resident in shared memory); launch-per-phase form for comparison
+    em._call("elph_set_tuning", 17, 0)
+    x2 = np.zeros(om.Ndim)
+    l0 = em.launch_count()
+    it2, _, f2 = E.ldiv_(x2, em, b, Pe)
+    n_unfused = em.launch_count() - l0
+    em._call("elph_set_tuning", 17, 1)
+    assert f2 == 0 and abs(it2 - it_e) <= 1 and relerr(x2, xe) <= 1e-6
+    assert n_fused <= 8 and n_unfused >= n_fused + 3 * it2, (n_fused, n_unfused)
     em.close()
