@@ -151,6 +151,11 @@ def load() -> C.CDLL:
         "elph_dev_update_model": (i32, [H]),
         "elph_dev_shard_dSbdx": (i32, [H, C.c_void_p, C.c_void_p, i32]),
         "elph_dev_fourier_accelerate_cols": (i32, [H, C.c_void_p, C.c_void_p, i64, C.c_void_p, dbl]),
+        "elph_dev_tau_to_omega_cols": (i32, [H, C.c_void_p, C.c_void_p, i64]),
+        "elph_dev_omega_to_tau_cols": (i32, [H, C.c_void_p, C.c_void_p, i64]),
+        "elph_dev_kpm_setup_bar": (i32, [H, C.c_void_p, dp, C.POINTER(KpmInfo)]),
+        "elph_kpm_set_omega_subset": (i32, [H, i64, i64]),
+        "elph_dev_kpm_chains": (i32, [H, C.c_void_p, C.c_void_p]),
         "elph_dev_lincomb": (i32, [H, C.c_void_p, dbl, C.c_void_p, dbl, C.c_void_p, dbl, C.c_void_p, i64]),
         "elph_dev_dot": (i32, [H, C.c_void_p, C.c_void_p, i64, C.c_void_p]),
         "elph_dev_to_engine_layout": (i32, [H, C.c_void_p, C.c_void_p, i64]),

@@ -1235,6 +1235,48 @@ int32_t elph_dev_fourier_accelerate_cols(elph_handle* h, const double* vin_dev, 
     ELPH_CATCH(h)
 }
 
+// ---- tau-sharded KPM preconditioner (sharded.py: ShardedKPM): site-sharded FFT stage and omega-sharded chain stage ----
+int32_t elph_dev_tau_to_omega_cols(elph_handle* h, const double* vin_dev, double* nu_dev, int64_t ncols) {
+    ENTER(h) {
+        elph_tau_to_omega_cols_dev(h, vin_dev, reinterpret_cast<cplx*>(nu_dev), (int)ncols);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_omega_to_tau_cols(elph_handle* h, const double* nu_dev, double* vout_dev, int64_t ncols) {
+    ENTER(h) {
+        elph_omega_to_tau_cols_dev(h, reinterpret_cast<const cplx*>(nu_dev), vout_dev, (int)ncols);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_kpm_setup_bar(elph_handle* h, const double* eVbar_dev, const double* arnoldi_noise, elph_kpm_info* info) {
+    ENTER(h) {
+        ELPH_REQUIRE(eVbar_dev, ELPH_ERR_INVALID, "null tau-mean");
+        elph_kpm_setup_impl(h, arnoldi_noise, info, eVbar_dev);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_set_omega_subset(elph_handle* h, int64_t first, int64_t stride) {
+    ENTER(h) {
+        elph_kpm_set_omega_subset(h, (int)first, (int)stride);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_kpm_chains(elph_handle* h, const double* nu_in_dev, double* nu_out_dev) {
+    ENTER(h) {
+        elph_kpm_chains_dev(h, reinterpret_cast<const cplx*>(nu_in_dev), reinterpret_cast<cplx*>(nu_out_dev));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
 int32_t elph_dev_update_model(elph_handle* h) {
     ENTER(h) {
         elph_launch_update_model(h);

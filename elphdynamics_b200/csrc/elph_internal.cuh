@@ -87,6 +87,8 @@ struct KpmState {
     std::vector<int> coeff_off;             // prefix offsets into coeff
     std::vector<std::complex<double>> coeff;  // concatenated c_m per omega
     std::vector<int> schedule;              // omegas sorted by order, longest first
+    int nsched = 0;                         // frequencies the chain kernels run (= Lo2 unless an omega subset is set)
+    int sub_first = 0, sub_stride = 1;      // omega-sharded apply (sharded.py): this handle runs w = first, first+stride, ...
     // host copies of the tau-averaged operator (for the Arnoldi iteration)
     std::vector<double> eVbar, cbar, sbar;
     // device
@@ -450,7 +452,9 @@ void elph_fourier_accelerate_dev(elph_handle* h, const double* vin, double* vout
 
 // kpm.cu
 void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2);
-void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info);
+void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info, const double* ext_eVbar_dev = nullptr);
+void elph_kpm_set_omega_subset(elph_handle* h, int first, int stride);
+void elph_kpm_chains_dev(elph_handle* h, const cplx* nu_in, cplx* nu_out);
 void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout);
 struct KpmCgFuse {   // vectors of the running preconditioned CG iteration (see fft.cu: CgFuse)
     double* x;
@@ -459,6 +463,8 @@ struct KpmCgFuse {   // vectors of the running preconditioned CG iteration (see 
     const double* ap;
 };
 void elph_kpm_apply_dev_cg(elph_handle* h, const double* vin, double* vout, const KpmCgFuse* cgf);
+void elph_tau_to_omega_cols_dev(elph_handle* h, const double* vin, cplx* vout, int ncols);
+void elph_omega_to_tau_cols_dev(elph_handle* h, const cplx* vin, double* vout, int ncols);
 void elph_tau_to_omega_dev_cg(elph_handle* h, double* x, double* r, const double* p, const double* ap, cplx* vout);
 void elph_omega_to_tau_dev_cg(elph_handle* h, const cplx* vin, double* z, double* r);
 void elph_kpm_free(elph_handle* h);

@@ -384,6 +384,17 @@ void elph_omega_to_tau_dev(elph_handle* h, const cplx* vin, double* vout) {
     dispatch_fft(h, 1, h->N, nullptr, vin, vout, nullptr, nullptr, 0.0);
 }
 
+// tau_to_omega! / omega_to_tau! of `ncols` columns ([tau][col] <-> [omega][col]): the site-sharded stage of the tau-sharded
+// preconditioner (after the first all-to-all a rank holds ALL time slices of a subset of the sites)
+void elph_tau_to_omega_cols_dev(elph_handle* h, const double* vin, cplx* vout, int ncols) {
+    ELPH_REQUIRE(vin && vout && ncols >= 1, ELPH_ERR_INVALID, "bad arguments");
+    dispatch_fft(h, 0, ncols, vin, nullptr, nullptr, vout, nullptr, 0.0);
+}
+void elph_omega_to_tau_cols_dev(elph_handle* h, const cplx* vin, double* vout, int ncols) {
+    ELPH_REQUIRE(vin && vout && ncols >= 1, ELPH_ERR_INVALID, "bad arguments");
+    dispatch_fft(h, 1, ncols, nullptr, vin, vout, nullptr, nullptr, 0.0);
+}
+
 // Fourier acceleration of `ncols` columns ([k][col] layout) with an explicit diagonal: used by the tau-sharded driver
 // after the all-to-all transpose, when a rank holds ALL time slices of a subset of the sites.
 void elph_fourier_accelerate_cols_dev(elph_handle* h, const double* vin, double* vout, int ncols, const double* diag, double power) {

@@ -621,7 +621,7 @@ void launch_apply(elph_handle* h, const KpmParams& P, int threads) {
     const size_t smem = (size_t)h->N * sizeof(cplx);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Nsites too large for the KPM shared-memory kernel");
     elph_enable_smem(h, kpm_apply_kernel<SPT>);
-    kpm_apply_kernel<SPT><<<h->kpm.Lo2, threads, smem, h->stream>>>(P);
+    kpm_apply_kernel<SPT><<<h->kpm.nsched, threads, smem, h->stream>>>(P);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }
@@ -645,6 +645,7 @@ void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2) {
     K.coeff.assign(K.Lo2, zc(0.0, 0.0));
     K.schedule.resize(K.Lo2);
     std::iota(K.schedule.begin(), K.schedule.end(), 0);
+    K.nsched = K.Lo2;
     K.eVbar.assign(h->N, 0.0);
     K.cbar.assign(h->Nb, 0.0);
     K.sbar.assign(h->Nb, 0.0);
@@ -676,17 +677,46 @@ void elph_kpm_free(elph_handle* h) {
     K = KpmState();
 }
 
-void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* info) {
+// frequencies the chain kernels run, longest polynomial first; with an omega subset (omega-sharded apply of the tau-sharded
+// lattice) only w = first, first + stride, ... of them
+static void kpm_build_schedule(elph_handle* h) {
+    KpmState& K = h->kpm;
+    K.schedule.clear();
+    for (int w = K.sub_first; w < K.Lo2; w += K.sub_stride) K.schedule.push_back(w);
+    std::stable_sort(K.schedule.begin(), K.schedule.end(), [&](int a, int b) { return K.order[a] > K.order[b]; });
+    K.nsched = (int)K.schedule.size();
+    if (K.nsched)
+        ELPH_CUDA(cudaMemcpyAsync(K.d_schedule, K.schedule.data(), K.nsched * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    ELPH_CUDA(cudaStreamSynchronize(h->stream));   // the host vector may be rebuilt by the next call
+    h->kpm_version++;
+}
+
+void elph_kpm_set_omega_subset(elph_handle* h, int first, int stride) {
+    KpmState& K = h->kpm;
+    ELPH_REQUIRE(K.configured, ELPH_ERR_STATE, "KPM preconditioner not configured (kpm_n == 0 at elph_create)");
+    ELPH_REQUIRE(stride >= 1 && first >= 0 && first < stride, ELPH_ERR_INVALID, "omega subset: need 0 <= first < stride");
+    K.sub_first = first;
+    K.sub_stride = stride;
+    kpm_build_schedule(h);
+}
+
+void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* info, const double* ext_eVbar) {
     KpmState& K = h->kpm;
     ELPH_REQUIRE(K.configured, ELPH_ERR_STATE, "KPM preconditioner not configured (kpm_n == 0 at elph_create)");
     ELPH_REQUIRE(noise != nullptr, ELPH_ERR_INVALID, "arnoldi_noise must provide 2*Nsites values");
     const int N = h->N, L = h->L, Nb = h->Nb, T = 256;
     // update_A!
     const bool dev = h->kpm_dev_arnoldi && K.n <= 32 && (N <= 8192);
+    ELPH_REQUIRE(!ext_eVbar || h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
+                 "KPM set-up from an external tau-mean is implemented for the Holstein model");
     if (h->model == ELPH_MODEL_HOLSTEIN) {
-        taumean_kernel<<<(N + T - 1) / T, T, 0, h->stream>>>(h->d_D, K.d_eVbar, N, L);
-        ELPH_CUDA(cudaGetLastError());
-        h->launches++;
+        if (ext_eVbar) {   // tau-sharded lattice: the mean over ALL slices was summed across the ranks by the caller
+            ELPH_CUDA(cudaMemcpyAsync(K.d_eVbar, ext_eVbar, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            taumean_kernel<<<(N + T - 1) / T, T, 0, h->stream>>>(h->d_D, K.d_eVbar, N, L);
+            ELPH_CUDA(cudaGetLastError());
+            h->launches++;
+        }
         if (!K.ever_setup) {  // static hoppings: cbar = cosht, sbar = sinht (:128-130)
             std::vector<double2> cs(Nb);
             ELPH_CUDA(cudaMemcpyAsync(cs.data(), h->d_cs, Nb * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
@@ -803,8 +833,6 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
             }
             K.coeff.assign(total, zc(0.0, 0.0));
             for (int w = 0; w < K.Lo2; ++w) host_kpm_coefficients(&K.coeff[K.coeff_off[w]], K.order[w], lam_lo, lam_hi, K.phis[w]);
-            std::iota(K.schedule.begin(), K.schedule.end(), 0);
-            std::stable_sort(K.schedule.begin(), K.schedule.end(), [&](int a, int b) { return K.order[a] > K.order[b]; });
             if ((size_t)total > K.d_coeff_cap) {
                 cudaFree(K.d_coeff);
                 K.d_coeff_cap = (size_t)total * 2;
@@ -814,10 +842,8 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
             ELPH_CUDA(cudaMemcpyAsync(K.d_coeff, K.coeff.data(), total * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
             ELPH_CUDA(cudaMemcpyAsync(K.d_order, K.order.data(), K.Lo2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
             ELPH_CUDA(cudaMemcpyAsync(K.d_coeff_off, K.coeff_off.data(), K.Lo2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-            ELPH_CUDA(cudaMemcpyAsync(K.d_schedule, K.schedule.data(), K.Lo2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-            ELPH_CUDA(cudaStreamSynchronize(h->stream));  // host vectors may be reallocated by the next setup
-            recomputed = true;
-            h->kpm_version++;   // captured CG graphs carry the old polynomial orders / window
+            kpm_build_schedule(h);   // synchronises: host vectors may be reallocated by the next setup; bumps kpm_version
+            recomputed = true;     // (captured CG graphs carry the old polynomial orders / window)
         }
         K.active = true;
     } else {
@@ -838,31 +864,10 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
     }
 }
 
-void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) { elph_kpm_apply_dev_cg(h, vin, vout, nullptr); }
-
-// cgf != nullptr (inside the preconditioned CG loop, preconditioner active): the forward FFT kernel first applies
-// x += alpha p, r -= alpha Ap and the stop rule, and the inverse FFT kernel accumulates r.z -> beta (fft.cu);
-// vin must then be the residual vector r.
-void elph_kpm_apply_dev_cg(elph_handle* h, const double* vin, double* vout, const KpmCgFuse* cgf) {
+// the Chebyshev chains of every scheduled frequency: nu_out[w], nu_out[L-1-w] from nu_in[w]  (:606-679, :464-466)
+static void kpm_launch_chains(elph_handle* h, const cplx* nu_in, cplx* nu_out, const int* skip) {
     KpmState& K = h->kpm;
-    ELPH_REQUIRE(K.configured && K.ever_setup, ELPH_ERR_STATE, "elph_kpm_apply before elph_kpm_setup");
-    ELPH_REQUIRE(!cgf || K.active, ELPH_ERR_STATE, "fused KPM apply needs an active preconditioner");
-    if (!K.active) {  // identity (:475-478)
-        if (vout != vin) ELPH_CUDA(cudaMemcpyAsync(vout, vin, h->Ndim * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        return;
-    }
-    ELPH_REQUIRE(K.d_coeff != nullptr, ELPH_ERR_STATE, "KPM coefficients missing");
-    const int* skip = &h->d_cg->done;
-    if (!h->kpm_skip_enabled) skip = nullptr;
-    // the recurrence reads nu_in and writes nu_out (the reference's v1 / v2)
-    cplx* nu_in = K.d_nu;
-    cplx* nu_out = h->d_nu2;
-    auto inverse_fft = [&]() {
-        if (cgf) elph_omega_to_tau_dev_cg(h, nu_out, vout, cgf->r);
-        else elph_omega_to_tau_dev_skip(h, nu_out, vout, skip);
-    };
-    if (cgf) elph_tau_to_omega_dev_cg(h, cgf->x, cgf->r, cgf->p, cgf->ap, nu_in);
-    else elph_tau_to_omega_dev_skip(h, vin, nu_in, skip);
+    if (K.nsched == 0) return;
     KpmParams P;
     P.in = nu_in;
     P.out = nu_out;
@@ -880,10 +885,7 @@ void elph_kpm_apply_dev_cg(elph_handle* h, const double* vin, double* vout, cons
     P.L = h->L;
     P.inv_mag = 1.0 / K.lam_mag;
     P.avg_over_mag = K.lam_avg / K.lam_mag;
-    if (elph_launch_kpm_square(h, nu_in, nu_out, skip)) {   // register/shuffle kernel (kpm_square.cu)
-        inverse_fft();
-        return;
-    }
+    if (elph_launch_kpm_square(h, nu_in, nu_out, skip)) return;   // register/shuffle kernel (kpm_square.cu)
     int threads = 256;
     while (threads < 512 && threads * 4 < h->N) threads *= 2;   // <= 512 threads: __launch_bounds__(512) on the kernel
     const int spt = (h->N + threads - 1) / threads;
@@ -893,5 +895,43 @@ void elph_kpm_apply_dev_cg(elph_handle* h, const double* vin, double* vout, cons
     else if (spt <= 8) launch_apply<8>(h, P, threads);
     else if (spt <= 16) launch_apply<16>(h, P, threads);
     else ELPH_REQUIRE(false, ELPH_ERR_UNSUPPORTED, "Nsites too large for the KPM kernel");
+}
+
+// omega-sharded apply: only the chain phase, on frequency-space vectors [L][N] indexed by the GLOBAL frequency (the caller
+// moved its frequencies' rows in through the all-to-all; rows of other frequencies are not touched)
+void elph_kpm_chains_dev(elph_handle* h, const cplx* nu_in, cplx* nu_out) {
+    KpmState& K = h->kpm;
+    ELPH_REQUIRE(K.configured && K.ever_setup && K.active && K.d_coeff, ELPH_ERR_STATE, "elph_dev_kpm_chains needs an active preconditioner");
+    ELPH_REQUIRE(nu_in && nu_out && nu_in != nu_out, ELPH_ERR_INVALID, "bad frequency-space buffers");
+    kpm_launch_chains(h, nu_in, nu_out, nullptr);
+}
+
+void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout) { elph_kpm_apply_dev_cg(h, vin, vout, nullptr); }
+
+// cgf != nullptr (inside the preconditioned CG loop, preconditioner active): the forward FFT kernel first applies
+// x += alpha p, r -= alpha Ap and the stop rule, and the inverse FFT kernel accumulates r.z -> beta (fft.cu);
+// vin must then be the residual vector r.
+void elph_kpm_apply_dev_cg(elph_handle* h, const double* vin, double* vout, const KpmCgFuse* cgf) {
+    KpmState& K = h->kpm;
+    ELPH_REQUIRE(K.configured && K.ever_setup, ELPH_ERR_STATE, "elph_kpm_apply before elph_kpm_setup");
+    ELPH_REQUIRE(!cgf || K.active, ELPH_ERR_STATE, "fused KPM apply needs an active preconditioner");
+    if (!K.active) {  // identity (:475-478)
+        if (vout != vin) ELPH_CUDA(cudaMemcpyAsync(vout, vin, h->Ndim * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        return;
+    }
+    ELPH_REQUIRE(K.d_coeff != nullptr, ELPH_ERR_STATE, "KPM coefficients missing");
+    ELPH_REQUIRE(K.sub_stride == 1, ELPH_ERR_STATE, "this handle runs an omega subset (elph_kpm_set_omega_subset): use elph_dev_kpm_chains");
+    const int* skip = &h->d_cg->done;
+    if (!h->kpm_skip_enabled) skip = nullptr;
+    // the recurrence reads nu_in and writes nu_out (the reference's v1 / v2)
+    cplx* nu_in = K.d_nu;
+    cplx* nu_out = h->d_nu2;
+    auto inverse_fft = [&]() {
+        if (cgf) elph_omega_to_tau_dev_cg(h, nu_out, vout, cgf->r);
+        else elph_omega_to_tau_dev_skip(h, nu_out, vout, skip);
+    };
+    if (cgf) elph_tau_to_omega_dev_cg(h, cgf->x, cgf->r, cgf->p, cgf->ap, nu_in);
+    else elph_tau_to_omega_dev_skip(h, vin, nu_in, skip);
+    kpm_launch_chains(h, nu_in, nu_out, skip);
     inverse_fft();
 }

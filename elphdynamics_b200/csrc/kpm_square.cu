@@ -274,7 +274,7 @@ void launch_ksq_split(elph_handle* h, const KsqParams& P, int nwarps, int max_or
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "KPM split kernel does not fit in shared memory");
     elph_enable_smem(h, kpm_square_split_kernel<NSEG, PY, MAXT, TAB>);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * h->kpm.Lo2);
+    cfg.gridDim = dim3(2 * h->kpm.nsched);
     cfg.blockDim = dim3(nwarps * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
@@ -295,7 +295,7 @@ void launch_ksq(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
     const size_t smem = (size_t)max_order * sizeof(cplx) + 2ull * nwarps * 4 * LX * sizeof(double);
     ELPH_REQUIRE(smem <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "KPM square kernel: polynomial order too large for shared memory");
     elph_enable_smem(h, kpm_square_kernel<NSEG, PY, MAXT>);
-    kpm_square_kernel<NSEG, PY, MAXT><<<h->kpm.Lo2, nwarps * 32, smem, h->stream>>>(P, max_order);
+    kpm_square_kernel<NSEG, PY, MAXT><<<h->kpm.nsched, nwarps * 32, smem, h->stream>>>(P, max_order);
     ELPH_CUDA(cudaGetLastError());
     h->launches++;
 }

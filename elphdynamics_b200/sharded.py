@@ -229,8 +229,178 @@ class CudaSlabBackend:
             raise RuntimeError(aux._lib.elph_last_error(aux.handle).decode())
 
 
+    # ---- KPM preconditioner of the sharded lattice (ShardedKPM): site-sharded FFT stage, omega-sharded chain stage ------
+    def kpm_init(self, aux_model, n: int = 20, buf: float = 0.05, c1: float = 1.0, c2: float = 1.0):
+        """``aux_model``: a HolsteinModel of the GLOBAL lattice (all sites, global Ltau, same hoppings) -- it owns the FFT plan
+        of the global time extent, the polynomial coefficients and the chain kernels; its own field is never used."""
+        from .models import SymmetricKPMPreconditioner
+        assert aux_model.Nsites == self.N
+        aux_model.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self._kpm_aux = aux_model
+        self._kpm_P = SymmetricKPMPreconditioner(aux_model, n, buf, c1, c2)
+        self.kpm_L = aux_model.Ltau
+
+    def kpm_set_subset(self, first: int, stride: int):
+        self._kpm_aux._call("elph_kpm_set_omega_subset", int(first), int(stride))
+
+    def kpm_setup_bar(self, eVbar, noise):
+        """setup!(P) (src/KPMPreconditioners.jl:269-321) from the all-reduced tau-mean; returns (active, recomputed)."""
+        P = self._kpm_P
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        if noise.size != 2 * self.N:
+            raise ValueError("arnoldi_noise must hold 2*Nsites values")
+        self._kpm_aux._call("elph_dev_kpm_setup_bar", eVbar.data_ptr(), noise.ctypes.data_as(C.POINTER(C.c_double)),
+                            C.byref(P.info))
+        return bool(P.info.active), bool(P.info.recomputed)
+
+    def kpm_orders(self):
+        return self._kpm_P.orders()
+
+    def kpm_window(self):
+        """(lambda_lo, lambda_hi, e_min, e_max) of the last set-up."""
+        i = self._kpm_P.info
+        return i.lambda_lo, i.lambda_hi, i.e_min, i.e_max
+
+    def tau_to_omega_cols(self, cols):
+        """[tau][col] real -> [omega][col] complex (tau_to_omega!, src/TimeFreqFFTs.jl:31-75)."""
+        nu = self.torch.empty(cols.shape, dtype=self.torch.complex128, device=cols.device)
+        self._kpm_aux._call("elph_dev_tau_to_omega_cols", cols.data_ptr(), nu.data_ptr(), cols.shape[1])
+        return nu
+
+    def omega_to_tau_cols(self, nu):
+        """[omega][col] complex -> [tau][col] real (omega_to_tau!, :78-122)."""
+        out = self.torch.empty(nu.shape, dtype=self.torch.float64, device=nu.device)
+        self._kpm_aux._call("elph_dev_omega_to_tau_cols", nu.data_ptr(), out.data_ptr(), nu.shape[1])
+        return out
+
+    def kpm_chains(self, nu_in, nu_out):
+        """The Chebyshev recurrences of this rank's frequencies on [L][N] complex buffers indexed by the global frequency."""
+        self._kpm_aux._call("elph_dev_kpm_chains", nu_in.data_ptr(), nu_out.data_ptr())
+
+
+class TauSiteTranspose:
+    """The all-to-all pair around every tau-FFT: tau-sharded [Lloc][N] <-> site-sharded [L][Nloc]."""
+
+    def __init__(self, comm: RingComm, N: int, Lglob: int, lloc: int):
+        w, r = comm.world, comm.rank
+        self.comm, self.N, self.L, self.lloc = comm, N, Lglob, lloc
+        self.site_spans = [slab_bounds(N, w, q) for q in range(w)]
+        self.tau_spans = [slab_bounds(Lglob, w, q) for q in range(w)]
+        self.s0, self.nloc = self.site_spans[r]
+        self.to_cols_counts = ([lloc * n for (_, n) in self.site_spans], [lt * self.nloc for (_, lt) in self.tau_spans])
+
+    def to_cols(self, own):
+        """own: [Lloc][N] (the own slices of a slab vector) -> [L][Nloc]: all time slices of this rank's site block."""
+        import torch
+        send = torch.cat([own[:, s:s + n].reshape(-1) for (s, n) in self.site_spans])
+        send_counts, recv_counts = self.to_cols_counts
+        recv = torch.empty(self.L * self.nloc, dtype=own.dtype, device=own.device)
+        self.comm.all_to_all(recv, send, recv_counts, send_counts)
+        return recv.view(self.L, self.nloc)             # chunks arrive in rank = tau order: [tau][site_local]
+
+    def to_slab(self, cols, out_own):
+        """cols: [L][Nloc] -> out_own [Lloc][N] (written in place)."""
+        import torch
+        send_counts, recv_counts = self.to_cols_counts
+        back = torch.empty(self.lloc * self.N, dtype=cols.dtype, device=cols.device)
+        self.comm.all_to_all(back, cols.contiguous().reshape(-1), send_counts, recv_counts)
+        off = 0
+        for (s, n) in self.site_spans:
+            out_own[:, s:s + n] = back[off:off + self.lloc * n].view(self.lloc, n)
+            off += self.lloc * n
+
+
+class ShardedKPM:
+    """``SymmetricKPMPreconditioner`` (src/KPMPreconditioners.jl:219-481) of a tau-sharded Holstein lattice.
+
+    setup!: the tau-mean of expnV (update_A!, :332-350) is a local sum over the slab + one all-reduce of Nsites doubles; the
+    Arnoldi bounds, the hysteresis and the coefficients (:269-321, :781-942) act on Nsites-vectors and are replicated on every
+    rank from the same injected start vectors, so every rank holds identical polynomials.
+    ldiv! (:426-481) runs on three shardings with an all-to-all between them:
+        tau-sharded r  --all-to-all-->  site-sharded: twisted tau-FFT of all slices of Nsites/P sites
+                       --all-to-all-->  omega-sharded: the Chebyshev recurrences (:606-679) of the frequencies w = rank, rank + P,
+                                        ... (the polynomial order falls monotonically with w, so dealing the frequencies round
+                                        robin is the longest-first assignment) on ALL sites
+                       --all-to-all-->  site-sharded: mirror frequencies L-1-w = conj (:464-466), inverse FFT
+                       --all-to-all-->  tau-sharded z.
+    Only the cld(L,2) independent frequencies travel; the receiver rebuilds the mirrors.
+    """
+    is_identity = False
+
+    def __init__(self, op: "ShardedOperator", N: int, Lglob: int, transpose: TauSiteTranspose | None = None):
+        import torch
+        self.op, self.be, self.comm = op, op.be, op.comm
+        self.N, self.L, self.lloc = N, Lglob, op.lloc
+        self.Lo2 = (Lglob + 1) // 2
+        self.tr = transpose or TauSiteTranspose(self.comm, N, Lglob, self.lloc)
+        w, r = self.comm.world, self.comm.rank
+        self.my_w = list(range(r, self.Lo2, w))
+        self.nw = [len(range(q, self.Lo2, w)) for q in range(w)]
+        self.be.kpm_set_subset(r, w)
+        self.active = False
+        self.recomputed = False
+        dev = self.be.empty().device
+        self.nu_in = torch.zeros(Lglob, N, dtype=torch.complex128, device=dev)
+        self.nu_out = torch.zeros(Lglob, N, dtype=torch.complex128, device=dev)
+        self.applies = 0
+
+    def setup(self, arnoldi_noise):
+        """setup!(P) with the 2*Nsites Arnoldi start values injected (the same array on every rank)."""
+        D = self.be.D_tensor()[1:self.lloc + 1]
+        acc = D.sum(dim=0)
+        self.comm.allreduce_sum(acc)
+        acc /= float(self.L)
+        self.active, self.recomputed = self.be.kpm_setup_bar(acc, arnoldi_noise)
+
+    def ldiv(self, z, r):
+        """z = P^-1 r on halo'd slab tensors (own slices only)."""
+        import torch
+        lloc, Lo2, L = self.lloc, self.Lo2, self.L
+        self.applies += 1
+        if not self.active:                      # identity (:475-478)
+            z[1:lloc + 1] = r[1:lloc + 1]
+            return
+        tr, comm = self.tr, self.comm
+        w, me = comm.world, comm.rank
+        nloc = tr.nloc
+        cols = tr.to_cols(r[1:lloc + 1])
+        nu = self.be.tau_to_omega_cols(cols)                         # [L][nloc]; rows < Lo2 are the independent frequencies
+        # site-sharded -> omega-sharded
+        send = torch.cat([torch.view_as_real(nu[q:Lo2:w]).reshape(-1) for q in range(w)])
+        send_counts = [2 * self.nw[q] * nloc for q in range(w)]
+        recv_counts = [2 * self.nw[me] * n for (_, n) in tr.site_spans]
+        recv = torch.empty(sum(recv_counts), dtype=torch.float64, device=send.device)
+        comm.all_to_all(recv, send, recv_counts, send_counts)
+        nmine = self.nw[me]
+        off = 0
+        for (s, n) in tr.site_spans:
+            blk = torch.view_as_complex(recv[off:off + 2 * nmine * n].view(nmine, n, 2))
+            self.nu_in[me:Lo2:w, s:s + n] = blk
+            off += 2 * nmine * n
+        self.be.kpm_chains(self.nu_in, self.nu_out)
+        # omega-sharded -> site-sharded (independent frequencies only)
+        own_rows = self.nu_out[me:Lo2:w]
+        send2 = torch.cat([torch.view_as_real(own_rows[:, s:s + n].contiguous()).reshape(-1) for (s, n) in tr.site_spans])
+        recv2 = torch.empty(sum(send_counts), dtype=torch.float64, device=send.device)
+        comm.all_to_all(recv2, send2, send_counts, recv_counts)
+        nu2 = torch.empty(L, nloc, dtype=torch.complex128, device=send.device)
+        off = 0
+        blocks = []
+        for q in range(w):
+            blk = torch.view_as_complex(recv2[off:off + 2 * self.nw[q] * nloc].view(self.nw[q], nloc, 2))
+            nu2[q:Lo2:w] = blk
+            blocks.append(blk)
+            off += 2 * self.nw[q] * nloc
+        for q in range(w):                                           # mirrors after ALL direct rows: for odd L the middle
+            if self.nw[q]:                                           # frequency ends up conjugated in place, as in :464-466
+                idx = torch.arange(q, Lo2, w, device=send.device)
+                nu2[L - 1 - idx] = torch.conj(blocks[q])
+        zc = self.be.omega_to_tau_cols(nu2)
+        tr.to_slab(zc, z[1:lloc + 1])
+
+
 class ShardedOperator:
-    """The fermion matrix of one tau-sharded lattice: products and plain CG on M^T M."""
+    """The fermion matrix of one tau-sharded lattice: products, plain and preconditioned CG on M^T M."""
 
     def __init__(self, backend, comm: RingComm, tol: float = 1e-5, maxiter: int = 10000, kappa_max: float = 1e12):
         self.be, self.comm = backend, comm
@@ -282,23 +452,75 @@ class ShardedOperator:
         x.zero_()
         return self.solve_cg(x, b, tol, maxiter)
 
-    def ldiv(self, x, b, tol: float = 0.0):
-        """``ldiv!(x, model, b)`` without a preconditioner (src/Models.jl:141-186) on the sharded lattice: solve from x0 = 0,
-        then the TRUE relative residual |b - A x| / |b| with one more product.  When it exceeds sqrt(tol): ``flag`` 1 if the solve
-        ran into maxiter, 2 if the solver reported a convergence that the true residual does not confirm -- and ``x`` is zeroed in
-        both cases, as the reference does, so that a failed solve never feeds the force.  Returns ``(iters, residual, flag)``."""
-        tol = tol or self.tol
-        iters, _ = self.solve(x, b, tol)
+    def _true_residual(self, x, b):
         res = self.be.empty()
         self.mulMTM(res, x)
         self.be.lincomb(res, 1.0, b, -1.0, res)
         num, den = self.gdot(res, res), self.gdot(b, b)
-        residual = math.sqrt(num) / math.sqrt(den) if den > 0 else float("nan")
+        return math.sqrt(num) / math.sqrt(den) if den > 0 else float("nan")
+
+    def ldiv(self, x, b, tol: float = 0.0, P=None):
+        """``ldiv!(x, model, b)`` without a preconditioner (src/Models.jl:141-186) on the sharded lattice: solve from x0 = 0,
+        then the TRUE relative residual |b - A x| / |b| with one more product.  When it exceeds sqrt(tol): ``flag`` 1 if the solve
+        ran into maxiter, 2 if the solver reported a convergence that the true residual does not confirm -- and ``x`` is zeroed in
+        both cases, as the reference does, so that a failed solve never feeds the force.  Returns ``(iters, residual, flag)``.
+        With a preconditioner ``P`` (ShardedKPM): ``ldiv!(x, model, b, P)`` (:74-137) -- preconditioned CG, the same check, and on
+        failure the unpreconditioned solve with 10 x maxiter as the fallback."""
+        tol = tol or self.tol
+        if P is not None and not getattr(P, "is_identity", False):
+            x.zero_()
+            iters, _ = self.solve_pcg(x, b, P, tol)
+            residual = self._true_residual(x, b)
+            if residual <= math.sqrt(tol):
+                return iters, residual, 0
+            iters, _ = self.solve(x, b, tol, maxiter=10 * self.maxiter)
+            residual = self._true_residual(x, b)
+            flag = 0
+            if residual > math.sqrt(tol):
+                flag = 1 if iters == self.maxiter else 2      # src/Models.jl:160 compares with solver.maxiter
+                x.zero_()
+            return iters, residual, flag
+        iters, _ = self.solve(x, b, tol)
+        residual = self._true_residual(x, b)
         flag = 0
         if residual > math.sqrt(tol):
             flag = 1 if iters == self.maxiter else 2
             x.zero_()
         return iters, residual, flag
+
+    def solve_pcg(self, x, b, P, tol: float = 0.0, maxiter: int = 0):
+        """Preconditioned CG, src/IterativeSolvers.jl:153-234, on the sharded lattice: per iteration one product (one halo
+        exchange), one preconditioner application (four all-to-alls) and three scalar all-reduces.  Returns (iters, eps)."""
+        be = self.be
+        tol = tol or self.tol
+        maxiter = maxiter or self.maxiter
+        r, p, z = be.empty(), be.empty(), be.empty()
+        normb = math.sqrt(self.gdot(b, b))
+        self.mulMTM(r, x)
+        be.lincomb(r, 1.0, b, -1.0, r)
+        P.ldiv(z, r)
+        be.lincomb(p, 1.0, z)
+        rdotz = self.gdot(r, z)
+        eps0 = math.sqrt(self.gdot(r, r)) / normb
+        eps, kmin = eps0, 0.0
+        for j in range(1, maxiter + 1):
+            self.mulMTM(z, p)
+            alpha = rdotz / self.gdot(p, z)
+            be.lincomb(x, 1.0, x, alpha, p)
+            be.lincomb(r, 1.0, r, -alpha, z)
+            eps = math.sqrt(self.gdot(r, r)) / normb
+            with np.errstate(all="ignore"):
+                k = float((2.0 * j / np.log(2.0 * eps0 / eps)) ** 2)
+            if k > kmin:
+                kmin = k
+            if eps < tol or kmin > self.kappa_max:
+                return j, eps
+            P.ldiv(z, r)
+            new_rdotz = self.gdot(r, z)
+            beta = new_rdotz / rdotz
+            rdotz = new_rdotz
+            be.lincomb(p, 1.0, z, beta, p)
+        return maxiter, eps
 
     def solve_cg(self, x, b, tol: float = 0.0, maxiter: int = 0):
         """Plain CG, src/IterativeSolvers.jl:239-314, with the reference stop rule.  Returns (iters, eps)."""
@@ -333,7 +555,7 @@ class ShardedOperator:
 
 
 class ShardedLangevin:
-    """Langevin updates of a tau-sharded Holstein lattice (unpreconditioned CG), reference:
+    """Langevin updates of a tau-sharded Holstein lattice (plain CG, or KPM-preconditioned CG with a ShardedKPM), reference:
     src/LangevinDynamics.jl:81-119 (Euler), :162-225 (Runge-Kutta), :334-384 (forces).
 
     Collectives per force evaluation: one halo exchange per product (CG iterations + M^T g + the force's v(tau-1)),
@@ -341,15 +563,16 @@ class ShardedLangevin:
     all-to-all pair (tau-sharded -> site-sharded, local tau-FFT of all slices of Nsites/P sites, and back).
     """
 
-    def __init__(self, op: ShardedOperator, N: int, Lglob: int, tau0: int, Q_site_block, dt: float):
-        """``Q_site_block``: the acceleration diagonal of this rank's site block, [k][site_local] (Lglob x Nloc)."""
+    def __init__(self, op: ShardedOperator, N: int, Lglob: int, tau0: int, Q_site_block, dt: float, P=None):
+        """``Q_site_block``: the acceleration diagonal of this rank's site block, [k][site_local] (Lglob x Nloc).
+        ``P``: a ShardedKPM (the solves of the force become ``ldiv!(x, model, b, P)``) or None."""
         self.op, self.be, self.comm = op, op.be, op.comm
         self.N, self.L, self.tau0, self.lloc = N, Lglob, tau0, op.lloc
         self.dt = float(dt)
-        w, r = self.comm.world, self.comm.rank
-        self.site_spans = [slab_bounds(N, w, q) for q in range(w)]
-        self.tau_spans = [slab_bounds(Lglob, w, q) for q in range(w)]
-        self.s0, self.nloc = self.site_spans[r]
+        self.tr = P.tr if P is not None else TauSiteTranspose(self.comm, N, Lglob, self.lloc)
+        self.site_spans, self.tau_spans = self.tr.site_spans, self.tr.tau_spans
+        self.s0, self.nloc = self.tr.s0, self.tr.nloc
+        self.P = P
         self.Q = Q_site_block
         self.xh = self.be.empty()                      # halo'd master copy of the phonon field slab
         self.last_iters, self.last_residual, self.last_flag = 0, 0.0, 0
@@ -358,23 +581,11 @@ class ShardedLangevin:
     def fourier_accelerate(self, v, power):
         """v: halo'd tensor; returns a new halo'd tensor with Re iFFT(Q^power FFT v) on the own slices."""
         torch = self.be.torch
-        lloc, nloc, L = self.lloc, self.nloc, self.L
-        own = v[1:lloc + 1]
-        send = torch.cat([own[:, s:s + n].reshape(-1) for (s, n) in self.site_spans])
-        send_counts = [lloc * n for (_, n) in self.site_spans]
-        recv_counts = [lt * nloc for (_, lt) in self.tau_spans]
-        recv = torch.empty(L * nloc, dtype=own.dtype, device=own.device)
-        self.comm.all_to_all(recv, send, recv_counts, send_counts)
-        cols = recv.view(L, nloc)                       # chunks arrive in rank = tau order: [tau][site_local]
+        cols = self.tr.to_cols(v[1:self.lloc + 1])
         out_cols = torch.empty_like(cols)
         self.be.fa_cols(cols, out_cols, self.Q, power)
-        back = torch.empty(lloc * self.N, dtype=own.dtype, device=own.device)
-        self.comm.all_to_all(back, out_cols.reshape(-1), send_counts, recv_counts)
         out = self.be.empty()
-        off = 0
-        for (s, n) in self.site_spans:
-            out[1:lloc + 1, s:s + n] = back[off:off + lloc * n].view(lloc, n)
-            off += lloc * n
+        self.tr.to_slab(out_cols, out[1:self.lloc + 1])
         return out
 
     # ---- field / forces -------------------------------------------------------------------------------------------
@@ -387,12 +598,15 @@ class ShardedLangevin:
         self.be.x_tensor().copy_(self.xh[1:self.lloc + 1])
         self.op.update_model()
 
-    def calc_dSdx(self, g):
-        """dS/dx = -2 g^T (dM/dx) M^-1 g + dSb/dx (shifted), src/LangevinDynamics.jl:334-384."""
+    def calc_dSdx(self, g, arnoldi_noise=None):
+        """dS/dx = -2 g^T (dM/dx) M^-1 g + dSb/dx (shifted), src/LangevinDynamics.jl:334-384; with a preconditioner, setup!(P)
+        first (:353) from the injected Arnoldi start values."""
         be, op = self.be, self.op
         b, x, dS = be.empty(), be.empty(), be.empty()
+        if self.P is not None:
+            self.P.setup(arnoldi_noise)
         op.mulMT(b, g)
-        iters, self.last_residual, self.last_flag = op.ldiv(x, b)
+        iters, self.last_residual, self.last_flag = op.ldiv(x, b, P=self.P)
         self.last_iters = iters
         self.comm.exchange(x, self.lloc, lo=True, hi=False)     # the force needs (M^-1 g)(tau-1)
         be.muldMdx(g, x, dS, -2.0)
@@ -400,11 +614,11 @@ class ShardedLangevin:
         be.dSbdx(dS, self.xh, True)
         return dS
 
-    def evolve_euler(self, eta, g):
+    def evolve_euler(self, eta, g, arnoldi_noise=None):
         """src/LangevinDynamics.jl:81-119; eta, g: halo'd tensors holding this rank's slab of the injected noise."""
         be = self.be
         self._push_x()
-        dS = self.calc_dSdx(g)
+        dS = self.calc_dSdx(g, arnoldi_noise)
         QdS = self.fourier_accelerate(dS, 1.0)
         sqQeta = self.fourier_accelerate(eta, 0.5)
         dx = be.empty()
@@ -413,16 +627,16 @@ class ShardedLangevin:
         self._push_x()
         return self.last_iters
 
-    def evolve_rk(self, eta, g1, g2):
+    def evolve_rk(self, eta, g1, g2, arnoldi_noise1=None, arnoldi_noise2=None):
         """src/LangevinDynamics.jl:162-225."""
         be = self.be
         self._push_x()
-        dS1 = self.calc_dSdx(g1)
+        dS1 = self.calc_dSdx(g1, arnoldi_noise1)
         dx = be.empty()
         be.lincomb(dx, math.sqrt(2.0 * self.dt), eta, -self.dt, dS1)
         be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
         self._push_x()
-        dS2 = self.calc_dSdx(g2)
+        dS2 = self.calc_dSdx(g2, arnoldi_noise2)
         be.lincomb(self.xh, 1.0, self.xh, -1.0, dx)
         self._push_x()
         be.lincomb(dS1, 0.5, dS2, 0.5, dS1)

@@ -357,6 +357,22 @@ int32_t elph_dev_shard_matvec_halo(elph_handle* h, int32_t mode, double* v_own, 
  * Ltau must be the GLOBAL time extent (the driver keeps a 1-site handle just for this plan). */
 int32_t elph_dev_fourier_accelerate_cols(elph_handle* h, const double* vin_dev, double* vout_dev, int64_t ncols,
                                          const double* diag_dev, double power);
+/* ---- KPM preconditioner of a tau-sharded lattice (reference: ldiv!(v', P, v), src/KPMPreconditioners.jl:426-481, on one
+ * process).  The apply is three stages on three shardings with an all-to-all between them: tau-sharded ->
+ * site-sharded (tau_to_omega! on all slices of a subset of the sites, src/TimeFreqFFTs.jl:31-75) -> omega-sharded (the
+ * Chebyshev recurrences of this rank's frequencies on ALL sites, :606-679) -> back.  These entries act on an auxiliary handle
+ * created for the GLOBAL lattice (Nsites, global Ltau, kpm_n > 0): it owns the FFT plan, the coefficients and the chain kernels.
+ *   elph_dev_tau_to_omega_cols / elph_dev_omega_to_tau_cols: [tau][col] real <-> [omega][col] complex (interleaved re, im)
+ *   elph_dev_kpm_setup_bar: setup!(P) (:269-321) with the tau-mean of expnV supplied by the caller (local sums + all-reduce
+ *     replace update_A!, :332-350); Arnoldi bounds, hysteresis and coefficients as elph_kpm_setup.  Holstein model.
+ *   elph_kpm_set_omega_subset: this handle's chain kernels run the frequencies w = first, first + stride, ... < cld(Ltau, 2)
+ *   elph_dev_kpm_chains: nu_out[w], nu_out[Ltau-1-w] = conj for every frequency of the subset from nu_in[w]; both buffers are
+ *     [Ltau][Nsites] complex indexed by the GLOBAL frequency, rows of other frequencies are left untouched. */
+int32_t elph_dev_tau_to_omega_cols(elph_handle* h, const double* vin_dev, double* nu_dev, int64_t ncols);
+int32_t elph_dev_omega_to_tau_cols(elph_handle* h, const double* nu_dev, double* vout_dev, int64_t ncols);
+int32_t elph_dev_kpm_setup_bar(elph_handle* h, const double* eVbar_dev, const double* arnoldi_noise, elph_kpm_info* info);
+int32_t elph_kpm_set_omega_subset(elph_handle* h, int64_t first, int64_t stride);
+int32_t elph_dev_kpm_chains(elph_handle* h, const double* nu_in_dev, double* nu_out_dev);
 /* BLAS-1 on device pointers for the sharded solver: out = a X + b Y + c Z (Y, Z may be NULL); out_dev[0] = a.b */
 int32_t elph_dev_lincomb(elph_handle* h, double* out, double a, const double* X, double b, const double* Y, double c,
                          const double* Z, int64_t n);

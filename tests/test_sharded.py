@@ -85,6 +85,44 @@ class OracleSlabBackend:
         a = np.fft.fft(vin.numpy().astype(np.complex128), axis=0) * diag.numpy() ** power
         vout.numpy()[:] = np.real(np.fft.ifft(a, axis=0))
 
+    # ---- KPM pieces (oracle/kpm.py per frequency, numpy.fft per column) -----------------------------------------------
+    def kpm_init(self, aux_model=None, n=20, buf=0.05, c1=1.0, c2=1.0):
+        from oracle.kpm import KPMPreconditioner
+        P = KPMPreconditioner(self.om, n, buf, c1, c2)
+        P.update_A = lambda: None                    # the tau-mean comes from the sharded driver (local sums + all-reduce)
+        self._P, self.kpm_L, self._sub = P, self.om.L, (0, 1)
+
+    def kpm_set_subset(self, first, stride):
+        self._sub = (first, stride)
+
+    def kpm_setup_bar(self, eVbar, noise):
+        self._P.expnVbar[:] = eVbar.numpy()
+        self._P.setup(noise)
+        return self._P.active, self._P.recomputed
+
+    def kpm_orders(self):
+        return self._P.order.copy()
+
+    def kpm_window(self):
+        return self._P.lam_lo, self._P.lam_hi, self._P.e_min, self._P.e_max
+
+    def tau_to_omega_cols(self, cols):
+        L = self.Lg
+        theta = np.exp(-1j * np.pi * np.arange(L) / L)
+        return self.torch.from_numpy(np.fft.fft(theta[:, None] * cols.numpy(), axis=0))
+
+    def omega_to_tau_cols(self, nu):
+        L = self.Lg
+        theta = np.exp(-1j * np.pi * np.arange(L) / L)
+        return self.torch.from_numpy(np.real(np.conj(theta)[:, None] * np.fft.ifft(nu.numpy(), axis=0)))
+
+    def kpm_chains(self, nu_in, nu_out):
+        L, (first, stride) = self.Lg, self._sub
+        a, o = nu_in.numpy(), nu_out.numpy()
+        for w in range(first, self._P.Lo2, stride):
+            o[w] = self._P.mul_block(w, a[w])
+            o[L - 1 - w] = np.conj(o[w])
+
     def _K(self, slices, transpose):
         Y = np.ascontiguousarray(slices.T)           # (N, nsl)
         f = cb.checkerboard_transpose_mul if transpose else cb.checkerboard_mul
@@ -202,20 +240,124 @@ def test_sharded_host_logic_over_gloo(world):
     mp.spawn(_cpu_worker, args=(world, _free_port()), nprocs=world, join=True)
 
 
-def _langevin_reference(om, method, dt, seed=21):
-    """Global oracle step without preconditioner + the injected noise (engine layout) + Q in [k][site] layout."""
+# ---------------------------------------------------------------- KPM-preconditioned solve of the sharded lattice
+def _pcg_problem(Ls=4, beta=2.1, seed=7):
+    """Global oracle: setup!(P), one application z = P^-1 r, and ldiv!(x, model, b, P) (src/Models.jl:74-137)."""
+    from oracle.kpm import KPMPreconditioner
+    from oracle.solvers import ldiv
+    om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-0.5, seed=seed)
+    noise = rng.normal(size=2 * om.N)
+    P = KPMPreconditioner(om, n=min(20, om.N))
+    P.setup(noise)
+    assert P.active
+    r = rng.normal(size=om.Ndim)
+    z = np.zeros(om.Ndim)
+    P.ldiv(z, r)
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    x = np.zeros(om.Ndim)
+    cg = ConjugateGradient(om.Ndim, tol=1e-8, maxiter=5000)
+    it, res, flag = ldiv(x, om, b, cg, P)
+    assert flag == 0
+    eng = lambda a: np.ascontiguousarray(a.reshape(om.N, om.L).T)
+    return om, noise, P, eng(r), eng(z), eng(b), eng(x), it
+
+
+def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, aux=None, p2p=False):
+    import torch
+    from elphdynamics_b200.sharded import ShardedKPM, ShardedOperator, slab_bounds
+    om, noise, Pref, r, z_ref, b, x_ref, it_ref = _pcg_problem(Ls, beta)
+    tau0, lloc = slab_bounds(om.L, world, rank)
+    be = make_backend(om, tau0, lloc)
+    be.kpm_init(aux(om) if aux else None, n=min(20, om.N))
+    op = ShardedOperator(be, comm, tol=1e-8, maxiter=5000)
+    if p2p:
+        assert op.enable_p2p()
+    op.update_model()
+    P = ShardedKPM(op, om.N, om.L)
+    P.setup(noise)
+    assert P.active and P.recomputed
+    assert np.array_equal(np.asarray(be.kpm_orders()), Pref.order)
+    # 20 Arnoldi steps amplify last-bit differences of the Gram-Schmidt sums (1e-9 in the bounds): compare the bounds at 1e-6 as
+    # the single-GPU tests do, then evaluate the oracle's polynomials on the engine's window for the 1e-11 comparison
+    lo, hi, e_min, e_max = be.kpm_window()
+    assert abs(e_min - Pref.e_min) <= 1e-6 * Pref.e_min and abs(e_max - Pref.e_max) <= 1e-6 * Pref.e_max
+    assert abs(lo - Pref.lam_lo) <= 1e-6 * Pref.lam_lo and abs(hi - Pref.lam_hi) <= 1e-6 * Pref.lam_hi
+    if (lo, hi) != (Pref.lam_lo, Pref.lam_hi):
+        from oracle.kpm import kpm_coefficients
+        Pref.lam_lo, Pref.lam_hi = lo, hi
+        Pref.lam_avg, Pref.lam_mag = (hi + lo) / 2, (hi - lo) / 2
+        Pref.coeff = [kpm_coefficients(int(Pref.order[w]), lo, hi, Pref.phis[w]) for w in range(Pref.Lo2)]
+        zz = np.zeros(om.Ndim)
+        Pref.ldiv(zz, np.ascontiguousarray(r.T).reshape(-1))
+        z_ref = np.ascontiguousarray(zz.reshape(om.N, om.L).T)
+
+    def slab(a):
+        t = be.empty()
+        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).to(device)
+        return t
+    z = be.empty()
+    P.ldiv(z, slab(r))
+    assert relerr(z[1:lloc + 1].cpu().numpy(), z_ref[tau0:tau0 + lloc]) <= 1e-11, rank
+    x = be.empty()
+    x.fill_(5.0)                                   # output only
+    it, res, flag = op.ldiv(x, slab(b), P=P)
+    assert flag == 0 and abs(it - it_ref) <= 2, (it, it_ref)
+    assert res <= 1e-4
+    assert relerr(x[1:lloc + 1].cpu().numpy(), x_ref[tau0:tau0 + lloc]) <= 1e-6
+    # second set-up on the same field: inside the hysteresis window, polynomials kept (:296-309)
+    P.setup(noise)
+    assert P.active and not P.recomputed
+    # cut-off preconditioned solve: the fallback of ldiv! runs the plain CG with 10 x maxiter and converges
+    keep = op.maxiter
+    op.maxiter = 3
+    it2, res2, flag2 = op.ldiv(x, slab(b), P=P)
+    op.maxiter = keep
+    assert flag2 in (0, 2) and it2 > 3
+    return be
+
+
+def _cpu_pcg_worker(rank, world, port, Ls, beta):
+    import torch.distributed as dist
+    from elphdynamics_b200.sharded import RingComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _check_pcg(lambda om, t0, ll: OracleSlabBackend(om, t0, ll), RingComm(rank, world), rank, world, Ls=Ls, beta=beta)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,Ls,beta", [(2, 4, 2.1), (3, 4, 2.1), (3, 4, 0.4)])
+def test_sharded_kpm_pcg_host_logic_over_gloo(world, Ls, beta):
+    """ShardedKPM (tau-mean all-reduce, the four all-to-alls of an application, round-robin frequencies, mirror rebuild incl.
+    the odd-Ltau middle frequency at beta = 2.1 and fewer frequencies than ranks at beta = 0.4) and the preconditioned CG with
+    its ldiv! wrapper over gloo, NumPy slab backend, against the oracle's global preconditioner and solve."""
+    import torch.multiprocessing as mp
+    mp.spawn(_cpu_pcg_worker, args=(world, _free_port(), Ls, beta), nprocs=world, join=True)
+
+
+def _langevin_reference(om, method, dt, seed=21, precond=False):
+    """Global oracle step (plain CG, or KPM-preconditioned with injected Arnoldi start vectors) + the injected noise (engine
+    layout) + Q in [k][site] layout."""
     from oracle import langevin as olang
     from oracle.fourier import FourierAccelerator
+    from oracle.kpm import KPMPreconditioner
     rng = np.random.default_rng(seed)
     eta, g1, g2 = rng.normal(size=om.Ndof), rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    an1, an2 = rng.normal(size=2 * om.N), rng.normal(size=2 * om.N)
+    _langevin_reference.arnoldi = (an1, an2)
+    P = KPMPreconditioner(om, n=min(20, om.N)) if precond else None
     fa = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
     fa.update_Q(0.0, 10.0, 1.0)
     cg = ConjugateGradient(om.Ndim, tol=1e-10, maxiter=20000)
     x0 = om.x.copy()
     if method == "euler":
-        it = olang.evolve_euler(om, cg, fa, None, dt, eta, g1)
+        it = olang.evolve_euler(om, cg, fa, P, dt, eta, g1, an1)
     else:
-        it = olang.evolve_rk(om, cg, fa, None, dt, eta, g1, g2)
+        it = olang.evolve_rk(om, cg, fa, P, dt, eta, g1, g2, an1, an2)
     x1 = om.x.copy()
     om.x[:] = x0
     om.update_model()
@@ -223,12 +365,13 @@ def _langevin_reference(om, method, dt, seed=21):
     return eng(eta), eng(g1), eng(g2), eng(fa.Q), eng(x0), eng(x1), it
 
 
-def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4, beta=1.1, p2p=False):
+def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4, beta=1.1, p2p=False, precond=False, aux=None):
     import torch
-    from elphdynamics_b200.sharded import ShardedLangevin, ShardedOperator, slab_bounds
+    from elphdynamics_b200.sharded import ShardedKPM, ShardedLangevin, ShardedOperator, slab_bounds
     om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-0.5, seed=7)
     dt = 1e-3
-    eta, g1, g2, Q, x0, x1, it_ref = _langevin_reference(om, method, dt)
+    eta, g1, g2, Q, x0, x1, it_ref = _langevin_reference(om, method, dt, precond=precond)
+    an1, an2 = _langevin_reference.arnoldi
     tau0, lloc = slab_bounds(om.L, world, rank)
     s0, nloc = slab_bounds(om.N, world, rank)
     be = make_backend(om, tau0, lloc)
@@ -237,7 +380,11 @@ def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4,
     if p2p:
         assert op.enable_p2p()      # the solves of the step run in the peer-memory persistent kernel
     Qb = torch.from_numpy(np.ascontiguousarray(Q[:, s0:s0 + nloc])).to(device)
-    lang = ShardedLangevin(op, om.N, om.L, tau0, Qb, dt)
+    P = None
+    if precond:
+        be.kpm_init(aux(om) if aux else None, n=min(20, om.N))
+        P = ShardedKPM(op, om.N, om.L)
+    lang = ShardedLangevin(op, om.N, om.L, tau0, Qb, dt, P=P)
     lang.set_x(x0[tau0:tau0 + lloc])
 
     def slab(a):
@@ -245,32 +392,35 @@ def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4,
         t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).to(device)
         return t
     if method == "euler":
-        it = lang.evolve_euler(slab(eta), slab(g1))
+        it = lang.evolve_euler(slab(eta), slab(g1), an1)
     else:
-        it = lang.evolve_rk(slab(eta), slab(g1), slab(g2))
+        it = lang.evolve_rk(slab(eta), slab(g1), slab(g2), an1, an2)
     assert abs(it - it_ref) <= 2, (it, it_ref)
+    assert lang.last_flag == 0 and (P is None or P.active)
     got = lang.xh[1:lloc + 1].cpu().numpy()
     assert relerr(got - x0[tau0:tau0 + lloc], (x1 - x0)[tau0:tau0 + lloc]) <= 1e-7, (method, rank)
 
 
-def _cpu_langevin_worker(rank, world, port, method):
+def _cpu_langevin_worker(rank, world, port, method, precond):
     import torch.distributed as dist
     from elphdynamics_b200.sharded import RingComm
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        _check_langevin(lambda om, t0, ll: OracleSlabBackend(om, t0, ll), RingComm(rank, world), rank, world, method)
+        _check_langevin(lambda om, t0, ll: OracleSlabBackend(om, t0, ll), RingComm(rank, world), rank, world, method,
+                        precond=precond, beta=2.0 if precond else 1.1)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,method", [(2, "rk"), (3, "euler")])
-def test_sharded_langevin_host_logic_over_gloo(world, method):
-    """Whole tau-sharded Langevin step (halo exchanges, all-reduces, all-to-all transposes around the tau-FFT) over
-    gloo, NumPy slab backend, against the oracle's global step with identical injected noise."""
+@pytest.mark.parametrize("world,method,precond", [(2, "rk", False), (3, "euler", False), (2, "rk", True)])
+def test_sharded_langevin_host_logic_over_gloo(world, method, precond):
+    """Whole tau-sharded Langevin step (halo exchanges, all-reduces, all-to-all transposes around the tau-FFT; with
+    ``precond`` the KPM set-ups and preconditioned solves of ShardedKPM) over gloo, NumPy slab backend, against the oracle's
+    global step with identical injected noise."""
     import torch.multiprocessing as mp
-    mp.spawn(_cpu_langevin_worker, args=(world, _free_port(), method), nprocs=world, join=True)
+    mp.spawn(_cpu_langevin_worker, args=(world, _free_port(), method, precond), nprocs=world, join=True)
 
 
 def test_slab_bounds_cover_the_time_axis():
@@ -406,6 +556,12 @@ def _gpu_worker(rank, world, port):
         _check_p2p_cg(be, op.comm, tau0, lloc, b, x_ref, it_ref)
         dist.barrier()
         em.close()
+        # KPM-preconditioned solve: omega-sharded application through NCCL all-to-alls, products with the halo through NCCL and
+        # (second pass) through peer memory inside the product kernel
+        for p2p in (False, True):
+            _check_pcg(_cuda_backend, RingComm(rank, world), rank, world, device="cuda", Ls=32, beta=2.0, aux=_engine_global,
+                       p2p=p2p)
+            dist.barrier()
     finally:
         dist.destroy_process_group()
 
@@ -473,6 +629,28 @@ def _cuda_backend(om, tau0, lloc):
     return CudaSlabBackend(_engine_slab(om, tau0, lloc), tau0, om.L)
 
 
+def _engine_global(om):
+    """The auxiliary engine model of the GLOBAL lattice that owns the FFT plan, the polynomials and the chain kernels."""
+    return _engine_slab(om, 0, om.L)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,beta", [(4, 2.1), (32, 2.0), (32, 3.1)])
+def test_sharded_kpm_pcg_single_gpu(Ls, beta):
+    """world = 1: ShardedKPM on the CUDA backend (column FFTs, set-up from the supplied tau-mean, chain kernels on the frequency
+    subset -- generic at 4x4, register tiles at 32x32; odd Ltau at beta = 2.1 / 3.1) and the preconditioned solve against the
+    oracle's global preconditioner and ldiv!."""
+    from elphdynamics_b200.sharded import RingComm
+    _check_pcg(_cuda_backend, RingComm(0, 1), 0, 1, device="cuda", Ls=Ls, beta=beta, aux=_engine_global)
+
+
+@pytest.mark.gpu
+def test_sharded_langevin_kpm_single_gpu():
+    """The sharded Runge-Kutta step with KPM-preconditioned solves (two set-ups from injected Arnoldi vectors), world = 1."""
+    from elphdynamics_b200.sharded import RingComm
+    _check_langevin(_cuda_backend, RingComm(0, 1), 0, 1, "rk", device="cuda", Ls=32, beta=2.0, precond=True, aux=_engine_global)
+
+
 @pytest.mark.gpu
 def test_sharded_langevin_p2p_single_gpu():
     """The sharded Runge-Kutta step with its solves in the peer-memory CG kernel (world = 1: the ring closes on itself)."""
@@ -501,6 +679,9 @@ def _gpu_langevin_worker(rank, world, port):
         _check_langevin(_cuda_backend, RingComm(rank, world), rank, world, "rk", device="cuda", Ls=32, beta=0.8)
         dist.barrier()
         _check_langevin(_cuda_backend, RingComm(rank, world), rank, world, "rk", device="cuda", Ls=32, beta=0.8, p2p=True)
+        dist.barrier()
+        _check_langevin(_cuda_backend, RingComm(rank, world), rank, world, "rk", device="cuda", Ls=32, beta=2.0, precond=True,
+                        aux=_engine_global)
         dist.barrier()
     finally:
         dist.destroy_process_group()
