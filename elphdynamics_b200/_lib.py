@@ -156,6 +156,10 @@ def load() -> C.CDLL:
         "elph_dev_kpm_setup_bar": (i32, [H, C.c_void_p, dp, C.POINTER(KpmInfo)]),
         "elph_kpm_set_omega_subset": (i32, [H, i64, i64]),
         "elph_dev_kpm_chains": (i32, [H, C.c_void_p, C.c_void_p]),
+        "elph_kpm_shard_export": (i32, [H, i32, i32, i64, i64, C.c_void_p]),
+        "elph_kpm_shard_open": (i32, [H, C.c_void_p, C.c_void_p]),
+        "elph_dev_kpm_shard_apply": (i32, [H, C.c_void_p, C.c_void_p]),
+        "elph_kpm_shard_check": (i32, [H]),
         "elph_dev_lincomb": (i32, [H, C.c_void_p, dbl, C.c_void_p, dbl, C.c_void_p, dbl, C.c_void_p, i64]),
         "elph_dev_dot": (i32, [H, C.c_void_p, C.c_void_p, i64, C.c_void_p]),
         "elph_dev_to_engine_layout": (i32, [H, C.c_void_p, C.c_void_p, i64]),

@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libelph_b200.so"
-SOURCES = ["api.cu", "matvec.cu", "mtm_square.cu", "ssh_square.cu","cg.cu", "cg_persistent.cu", "cg_p2p.cu", "cg_pipe.cu", "pcg_fused.cu","fft.cu", "kpm.cu", "kpm_square.cu", "force.cu", "dynamics.cu", "hmc.cu", "greens.cu"]
+SOURCES = ["api.cu", "matvec.cu", "mtm_square.cu", "ssh_square.cu","cg.cu", "cg_persistent.cu", "cg_p2p.cu", "cg_pipe.cu", "pcg_fused.cu","fft.cu", "kpm.cu", "kpm_square.cu", "kpm_shard.cu", "force.cu", "dynamics.cu", "hmc.cu", "greens.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -303,6 +303,7 @@ void destroy(elph_handle* h) {
         cudaStreamDestroy(h->pipe.s_out);
     }
     elph_shard_p2p_close_impl(h);
+    elph_kpm_shard_free(h);
     if (h->pipe_prof_buf) cudaFree(h->pipe_prof_buf);
     if (h->h_hx_flag) cudaFreeHost(h->h_hx_flag);
     if (h->upload_stream) {
@@ -1272,6 +1273,40 @@ int32_t elph_kpm_set_omega_subset(elph_handle* h, int64_t first, int64_t stride)
 int32_t elph_dev_kpm_chains(elph_handle* h, const double* nu_in_dev, double* nu_out_dev) {
     ENTER(h) {
         elph_kpm_chains_dev(h, reinterpret_cast<const cplx*>(nu_in_dev), reinterpret_cast<cplx*>(nu_out_dev));
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+// the same application with the three transposes through peer memory (kpm_shard.cu): no NCCL call per application
+int32_t elph_kpm_shard_export(elph_handle* h, int32_t rank, int32_t world, int64_t tau0, int64_t lloc, unsigned char* ipc_handle_out) {
+    ENTER(h) {
+        ELPH_REQUIRE(ipc_handle_out, ELPH_ERR_INVALID, "null output");
+        elph_kpm_shard_export_impl(h, rank, world, (int)tau0, (int)lloc, ipc_handle_out);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_shard_open(elph_handle* h, const unsigned char* ipc_handles, const int64_t* slab_starts) {
+    ENTER(h) {
+        elph_kpm_shard_open_impl(h, ipc_handles, slab_starts);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_dev_kpm_shard_apply(elph_handle* h, const double* r_own_dev, double* z_own_dev) {
+    ENTER(h) {
+        elph_kpm_shard_apply_impl(h, r_own_dev, z_own_dev);
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+
+int32_t elph_kpm_shard_check(elph_handle* h) {
+    ENTER(h) {
+        ELPH_REQUIRE(elph_kpm_shard_ok(h), ELPH_ERR_STATE, "sharded KPM apply: a peer GPU did not reach a barrier (timeout)");
         return ELPH_OK;
     }
     ELPH_CATCH(h)

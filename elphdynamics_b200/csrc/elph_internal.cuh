@@ -305,6 +305,20 @@ struct elph_handle {
         unsigned int pipe_seq = 0;
         bool pipe_failed = false;
     } p2p;
+    // KPM preconditioner of a tau-sharded lattice with the transposes through peer memory (kpm_shard.cu); lives on the auxiliary
+    // handle of the GLOBAL lattice
+    struct {
+        void* arena = nullptr;
+        size_t bytes = 0, offA = 0, offB = 0, offC = 0, offD = 0;
+        std::vector<void*> peer;
+        std::vector<int> tau0s, s0s;     // [world + 1] first slice / first site of every rank
+        int rank = 0, world = 1, tau0 = 0, lloc = 0;
+        unsigned long long seq = 0;      // number of the last cross-GPU barrier issued
+        bool opened = false;
+        cplx* nu_in = nullptr;           // [L][N] gathered input rows of this rank's frequencies
+        unsigned int* h_fail = nullptr;  // pinned + mapped: a barrier timed out
+        unsigned int* d_fail = nullptr;
+    } kshard;
     unsigned int* h_hx_flag = nullptr;   // pinned: failure flag of the peer-memory halo exchange
     int cg_pipeline = -1;          // unpreconditioned CG on square lattices: pipelined persistent kernel (cg_pipe.cu); -1 = auto, 0 = off
     int pipe_ys = 0;               // tuning: CTAs per time slice of the pipelined kernel (0 = automatic)
@@ -455,6 +469,13 @@ void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2);
 void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info, const double* ext_eVbar_dev = nullptr);
 void elph_kpm_set_omega_subset(elph_handle* h, int first, int stride);
 void elph_kpm_chains_dev(elph_handle* h, const cplx* nu_in, cplx* nu_out);
+// kpm_shard.cu
+void elph_kpm_shard_export_impl(elph_handle* h, int rank, int world, int tau0, int lloc, unsigned char* handle_out);
+void elph_kpm_shard_open_impl(elph_handle* h, const unsigned char* handles, const int64_t* tau0s);
+void elph_kpm_shard_close_impl(elph_handle* h);
+void elph_kpm_shard_free(elph_handle* h);
+void elph_kpm_shard_apply_impl(elph_handle* h, const double* r_own, double* z_own);
+bool elph_kpm_shard_ok(elph_handle* h);
 void elph_kpm_apply_dev(elph_handle* h, const double* vin, double* vout);
 struct KpmCgFuse {   // vectors of the running preconditioned CG iteration (see fft.cu: CgFuse)
     double* x;

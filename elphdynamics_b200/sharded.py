@@ -278,6 +278,45 @@ class CudaSlabBackend:
         self._kpm_aux._call("elph_dev_kpm_chains", nu_in.data_ptr(), nu_out.data_ptr())
 
 
+    def kpm_shard_setup(self, comm: "RingComm", tau0: int) -> bool:
+        """Arenas of the fused application (csrc/kpm_shard.cu): export this rank's, all-gather the IPC handles and the slab
+        starts over torch.distributed, open the peers'.  True when every rank succeeded."""
+        import torch.distributed as dist
+        aux = self._kpm_aux
+        buf = (C.c_ubyte * 64)()
+        ok = True
+        try:
+            aux._call("elph_kpm_shard_export", comm.rank, comm.world, int(tau0), int(self.lloc), buf)
+        except Exception:
+            ok = False
+        mine = (bytes(buf), int(tau0), ok)
+        if comm.world > 1:
+            gathered = [None] * comm.world
+            dist.all_gather_object(gathered, mine, group=comm.group)
+        else:
+            gathered = [mine]
+        if all(g[2] for g in gathered):
+            handles = (C.c_ubyte * (64 * comm.world)).from_buffer_copy(b"".join(g[0] for g in gathered))
+            starts = (C.c_int64 * comm.world)(*[g[1] for g in gathered])
+            try:
+                aux._call("elph_kpm_shard_open", handles, starts)
+            except Exception:
+                ok = False
+        else:
+            ok = False
+        if comm.world > 1:                       # every rank must take the same path
+            flags = [None] * comm.world
+            dist.all_gather_object(flags, ok, group=comm.group)
+            ok = all(flags)
+        return ok
+
+    def kpm_shard_apply(self, r, z):
+        self._kpm_aux._call("elph_dev_kpm_shard_apply", self.own_ptr(r), self.own_ptr(z))
+
+    def kpm_shard_check(self):
+        self._kpm_aux._call("elph_kpm_shard_check")
+
+
 class TauSiteTranspose:
     """The all-to-all pair around every tau-FFT: tau-sharded [Lloc][N] <-> site-sharded [L][Nloc]."""
 
@@ -343,6 +382,14 @@ class ShardedKPM:
         self.nu_in = torch.zeros(Lglob, N, dtype=torch.complex128, device=dev)
         self.nu_out = torch.zeros(Lglob, N, dtype=torch.complex128, device=dev)
         self.applies = 0
+        self.fused = False
+
+    def enable_fused(self, tau0: int) -> bool:
+        """Use the one-call application with the transposes through peer memory (csrc/kpm_shard.cu) where the backend has it and
+        every rank could open every arena; otherwise the all-to-all form stays.  ``tau0``: first global slice of this slab."""
+        setup = getattr(self.be, "kpm_shard_setup", None)
+        self.fused = bool(setup and setup(self.comm, tau0))
+        return self.fused
 
     def setup(self, arnoldi_noise):
         """setup!(P) with the 2*Nsites Arnoldi start values injected (the same array on every rank)."""
@@ -359,6 +406,9 @@ class ShardedKPM:
         self.applies += 1
         if not self.active:                      # identity (:475-478)
             z[1:lloc + 1] = r[1:lloc + 1]
+            return
+        if self.fused:
+            self.be.kpm_shard_apply(r, z)
             return
         tr, comm = self.tr, self.comm
         w, me = comm.world, comm.rank

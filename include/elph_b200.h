@@ -373,6 +373,19 @@ int32_t elph_dev_omega_to_tau_cols(elph_handle* h, const double* nu_dev, double*
 int32_t elph_dev_kpm_setup_bar(elph_handle* h, const double* eVbar_dev, const double* arnoldi_noise, elph_kpm_info* info);
 int32_t elph_kpm_set_omega_subset(elph_handle* h, int64_t first, int64_t stride);
 int32_t elph_dev_kpm_chains(elph_handle* h, const double* nu_in_dev, double* nu_out_dev);
+/* The same application as ONE call per rank with the transposes through peer memory instead of all-to-alls (csrc/kpm_shard.cu):
+ * every rank exports an arena holding the output of each of its stages (CUDA IPC handle, 64 bytes), all ranks open all arenas
+ * (handles in rank order; slab_starts[q] = first global slice of rank q's slab, near-equal contiguous slabs; the site blocks are
+ * the near-equal contiguous split of Nsites), and elph_dev_kpm_shard_apply runs  copy-in | forward FFT | gather + chains | inverse
+ * FFT | gather  with the loads of each stage pulling from the producers' arenas over NVLink and one 32-thread cross-GPU barrier
+ * kernel between stages.  r_own / z_own: [Lloc][Nsites] device vectors of this rank's slab; every rank must make the same calls
+ * in the same order.  Requires elph_kpm_set_omega_subset(rank, world) and an active preconditioner (the caller copies r to z
+ * otherwise, src/KPMPreconditioners.jl:475-478).  A barrier that is not reached within 2 s raises a failure flag, reported by
+ * the next call and by elph_kpm_shard_check (which synchronises the stream). */
+int32_t elph_kpm_shard_export(elph_handle* h, int32_t rank, int32_t world, int64_t tau0, int64_t lloc, unsigned char* ipc_handle_out);
+int32_t elph_kpm_shard_open(elph_handle* h, const unsigned char* ipc_handles, const int64_t* slab_starts);
+int32_t elph_dev_kpm_shard_apply(elph_handle* h, const double* r_own_dev, double* z_own_dev);
+int32_t elph_kpm_shard_check(elph_handle* h);
 /* BLAS-1 on device pointers for the sharded solver: out = a X + b Y + c Z (Y, Z may be NULL); out_dev[0] = a.b */
 int32_t elph_dev_lincomb(elph_handle* h, double* out, double a, const double* X, double b, const double* Y, double c,
                          const double* Z, int64_t n);

@@ -58,10 +58,13 @@ if "--p2p" in sys.argv:
 op.update_model()
 be.kpm_init(aux)
 P = ShardedKPM(op, N, Lglob)
+if "--fused" in sys.argv:
+    assert P.enable_fused(tau0)
 b = be.empty()
 b[1:lloc + 1] = torch.from_numpy(bg[tau0:tau0 + lloc]).cuda()
 x = be.empty()
-out = {"lattice": f"{Ls}x{Ls}xL{Lglob}", "n_gpus": world, "slab_slices": lloc, "halo": "peer memory" if comm.peer_halo else "nccl"}
+out = {"lattice": f"{Ls}x{Ls}xL{Lglob}", "n_gpus": world, "slab_slices": lloc, "halo": "peer memory" if comm.peer_halo else "nccl",
+       "kpm_transposes": "peer memory (kpm_shard.cu)" if P.fused else "nccl all-to-all"}
 
 
 def sync():

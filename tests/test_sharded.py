@@ -264,7 +264,7 @@ def _pcg_problem(Ls=4, beta=2.1, seed=7):
     return om, noise, P, eng(r), eng(z), eng(b), eng(x), it
 
 
-def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, aux=None, p2p=False):
+def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, aux=None, p2p=False, fused=False):
     import torch
     from elphdynamics_b200.sharded import ShardedKPM, ShardedOperator, slab_bounds
     om, noise, Pref, r, z_ref, b, x_ref, it_ref = _pcg_problem(Ls, beta)
@@ -276,6 +276,10 @@ def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, au
         assert op.enable_p2p()
     op.update_model()
     P = ShardedKPM(op, om.N, om.L)
+    if fused:
+        assert P.enable_fused(tau0)                # transposes through peer memory, one call per application
+    else:
+        assert not hasattr(be, "kpm_shard_setup") or not P.fused
     P.setup(noise)
     assert P.active and P.recomputed
     assert np.array_equal(np.asarray(be.kpm_orders()), Pref.order)
@@ -315,6 +319,8 @@ def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, au
     it2, res2, flag2 = op.ldiv(x, slab(b), P=P)
     op.maxiter = keep
     assert flag2 in (0, 2) and it2 > 3
+    if fused:
+        be.kpm_shard_check()                       # no barrier of the fused applications timed out
     return be
 
 
@@ -558,9 +564,9 @@ def _gpu_worker(rank, world, port):
         em.close()
         # KPM-preconditioned solve: omega-sharded application through NCCL all-to-alls, products with the halo through NCCL and
         # (second pass) through peer memory inside the product kernel
-        for p2p in (False, True):
-            _check_pcg(_cuda_backend, RingComm(rank, world), rank, world, device="cuda", Ls=32, beta=2.0, aux=_engine_global,
-                       p2p=p2p)
+        for p2p, fused, beta in ((False, False, 2.0), (True, False, 2.0), (True, True, 2.0), (True, True, 2.1), (False, True, 0.5)):
+            _check_pcg(_cuda_backend, RingComm(rank, world), rank, world, device="cuda", Ls=32, beta=beta, aux=_engine_global,
+                       p2p=p2p, fused=fused)
             dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -642,6 +648,15 @@ def test_sharded_kpm_pcg_single_gpu(Ls, beta):
     oracle's global preconditioner and ldiv!."""
     from elphdynamics_b200.sharded import RingComm
     _check_pcg(_cuda_backend, RingComm(0, 1), 0, 1, device="cuda", Ls=Ls, beta=beta, aux=_engine_global)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,beta", [(4, 2.1), (32, 2.0), (32, 3.1), (64, 1.2)])
+def test_sharded_kpm_fused_single_gpu(Ls, beta):
+    """world = 1: the application with the transposes through the arenas (csrc/kpm_shard.cu; the ring closes on the GPU itself:
+    copy-in, pulling forward FFT, gather, chains, pulling inverse FFT, gather, four barrier kernels) against the oracle."""
+    from elphdynamics_b200.sharded import RingComm
+    _check_pcg(_cuda_backend, RingComm(0, 1), 0, 1, device="cuda", Ls=Ls, beta=beta, aux=_engine_global, fused=True)
 
 
 @pytest.mark.gpu
