@@ -166,6 +166,7 @@ def load() -> C.CDLL:
         "elph_dev_from_engine_layout": (i32, [H, C.c_void_p, C.c_void_p, i64]),
         "elph_dev_ptr_x": (i32, [H, C.POINTER(C.c_void_p)]),
         "elph_dev_ptr_expnV": (i32, [H, C.POINTER(C.c_void_p)]),
+        "elph_dev_ptr_cosh_sinh": (i32, [H, C.POINTER(C.c_void_p)]),
         "elph_dev_cg_solve": (i32, [H, C.c_void_p, C.c_void_p, i32, dbl, i64, ip, dp]),
         "elph_dev_kpm_apply": (i32, [H, C.c_void_p, C.c_void_p]),
         "elph_dev_fourier_accelerate": (i32, [H, C.c_void_p, C.c_void_p, dbl, i32]),

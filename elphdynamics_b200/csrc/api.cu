@@ -315,6 +315,10 @@ void destroy(elph_handle* h) {
         cudaFree(h->d_D_alloc);
         h->d_D = nullptr;
     }
+    if (h->d_cs_alloc) {
+        cudaFree(h->d_cs_alloc);
+        h->d_cs = nullptr;
+    }
     void* ptrs[] = {h->d_bonds, h->d_goff, h->d_cs, h->d_lam, h->d_lam2, h->d_mu, h->d_omega, h->d_omega4, h->d_x, h->d_D,
                     h->d_Q, h->d_Mass, h->d_t, h->d_alpha, h->d_alpha2, h->d_ph_col, h->d_col_ph, h->d_col_bond, h->ssq.d_slot, h->ssq.d_tab,
                     h->d_primary_ph, h->d_grp_start, h->d_grp_members, h->d_tprime, h->d_va, h->d_vb, h->d_vc, h->d_b,
@@ -1100,10 +1104,18 @@ int32_t elph_dev_mulMTM_replicas_ssh(elph_handle* h, int64_t nrep, const double*
 // ---- tau-sharding (multi-GPU): this handle owns global slices [tau0, tau0 + Ltau) of Lglob -------------------
 int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob) {
     ENTER(h) {
-        ELPH_REQUIRE(h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED, "tau-sharding is implemented for the Holstein model");
         ELPH_REQUIRE(Lglob >= h->L && tau0 >= 0 && tau0 + h->L <= Lglob, ELPH_ERR_INVALID, "bad shard bounds");
         ELPH_CUDA(cudaStreamSynchronize(h->stream));
-        if (!h->sharded) {
+        if (!h->sharded && h->model == ELPH_MODEL_SSH) {
+            // SSH: the per-tau (cosh, sinh) table is what couples to the neighbour slab (K(b) of the right neighbour's first slice
+            // is needed to recompute (M v)(b), src/SSHModels.jl:581-701); expmu has no time index.  Same re-homing, rows of Nb.
+            double2* alloc = elph_dalloc<double2>((size_t)(h->L + 2) * h->Nb);
+            ELPH_CUDA(cudaMemset(alloc, 0, (size_t)(h->L + 2) * h->Nb * sizeof(double2)));
+            ELPH_CUDA(cudaMemcpy(alloc + h->Nb, h->d_cs, (size_t)h->L * h->Nb * sizeof(double2), cudaMemcpyDeviceToDevice));
+            ELPH_CUDA(cudaFree(h->d_cs));
+            h->d_cs_alloc = alloc;
+            h->d_cs = alloc + h->Nb;
+        } else if (!h->sharded) {
             // re-home expnV with one halo slice on each side: [halo_lo][own ...][halo_hi]
             double* alloc = elph_dalloc<double>((size_t)(h->L + 2) * h->N);
             ELPH_CUDA(cudaMemset(alloc, 0, (size_t)(h->L + 2) * h->N * sizeof(double)));
@@ -1363,6 +1375,13 @@ int32_t elph_dev_ptr_x(elph_handle* h, double** x_dev) {
 int32_t elph_dev_ptr_expnV(elph_handle* h, double** p) {
     ENTER(h) {
         *p = h->d_D;
+        return ELPH_OK;
+    }
+    ELPH_CATCH(h)
+}
+int32_t elph_dev_ptr_cosh_sinh(elph_handle* h, double** p) {
+    ENTER(h) {
+        *p = reinterpret_cast<double*>(h->d_cs);
         return ELPH_OK;
     }
     ELPH_CATCH(h)

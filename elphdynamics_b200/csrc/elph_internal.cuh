@@ -330,6 +330,7 @@ struct elph_handle {
     unsigned long long* pipe_prof_buf = nullptr;   // [8192][8]
     int pipe_last_variant = 0;     // variant * 100 + ys * 10 + warps of the last pipelined solve (diagnostics)
     double* d_D_alloc = nullptr;   // sharded: d_D points one slice into this allocation (halo slices around it)
+    double2* d_cs_alloc = nullptr; // sharded SSH: d_cs points one slice into this allocation ([halo][own ...][halo] rows of Nb)
     double* d_x_alloc = nullptr;   // sharded: same for the phonon field (the force needs no x halo; kept symmetric)
     bool sq_disable = false;
     int sq_py = 0;

@@ -159,6 +159,7 @@ struct SParams {
     const double2* __restrict__ cs;  // [L][Nb]
     const int* __restrict__ col_ph;  // column -> phonon or -1
     int ngroups, N, L, Nb, Nph, C;
+    int open, tau0, Lglob;           // tau-sharded slab: v(tau-1) of the first own slice is the left halo, sign on GLOBAL slice 0
     double dtau;
 };
 
@@ -171,9 +172,9 @@ __global__ void __launch_bounds__(kT) ssh_force_kernel(SParams P) {
     double* Cc = smem + (size_t)P.C * N;       // c(tau) = K^T(tau) u(tau)
     for (int k = 0; k < nout; ++k) {
         const int tau = a + k;
-        const int taum = (tau == 0) ? L - 1 : tau - 1;
+        const long long taum = (tau == 0) ? (P.open ? -1 : L - 1) : tau - 1;
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
-            B[(size_t)k * N + i] = P.expmu[i] * P.v[(size_t)taum * N + i];
+            B[(size_t)k * N + i] = P.expmu[i] * P.v[taum * N + i];
             Cc[(size_t)k * N + i] = P.u[(size_t)tau * N + i];
         }
     }
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kT) ssh_force_kernel(SParams P) {
                     const double xn = P.x[(size_t)tau * P.Nph + ph];
                     const double dK = P.alpha[ph] + 2.0 * P.alpha2[ph] * xn;
                     double dm = ncj * P.dtau * dK * nbi + (nci * P.dtau * dK) * nbj;
-                    if (tau == 0) dm = -dm;
+                    if (((P.tau0 + tau) % P.Lglob) == 0) dm = -dm;
                     P.raw[(size_t)tau * P.Nph + ph] = dm;
                 }
             }
@@ -273,6 +274,8 @@ void elph_muldMdx_dev(elph_handle* h, const double* u, const double* v, double* 
     P.u = u; P.v = v; P.raw = h->d_tmp; P.x = h->d_x; P.expmu = h->d_D; P.alpha = h->d_alpha; P.alpha2 = h->d_alpha2;
     P.bonds = h->d_bonds; P.goff = h->d_goff; P.cs = h->d_cs; P.col_ph = h->d_col_ph;
     P.ngroups = h->ngroups; P.N = h->N; P.L = h->L; P.Nb = h->Nb; P.Nph = h->Nph; P.C = 1; P.dtau = h->dtau;
+    P.open = h->sharded ? 1 : 0; P.tau0 = h->sharded ? h->shard_tau0 : 0; P.Lglob = h->sharded ? h->shard_Lglob : h->L;
+    ELPH_REQUIRE(!(h->sharded && add_dSb), ELPH_ERR_UNSUPPORTED, "tau-sharded force: add the bosonic gradient separately (it needs x halos)");
     ELPH_REQUIRE(2 * slice <= h->smem_optin, ELPH_ERR_UNSUPPORTED, "Nsites too large for the shared-memory force kernel");
     ELPH_CUDA(cudaMemsetAsync(h->d_tmp, 0, h->Ndof * sizeof(double), h->stream));
     elph_enable_smem(h, ssh_force_kernel);

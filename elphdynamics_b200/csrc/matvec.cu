@@ -66,7 +66,7 @@ __device__ __forceinline__ void sweep_smem(double* __restrict__ buf, int nsl, in
             } else {
                 for (int k = 0; k < nsl; ++k) {
                     int tau = tau0 + k;
-                    if (tau >= P.L) tau -= P.L;
+                    if (tau >= P.L && !P.open) tau -= P.L;   // open slab: row L of the table is the right neighbour's first slice
                     const double2 cs = P.cs[(size_t)tau * P.Nb + b];
                     rotate(buf + (size_t)k * N, ij.x, ij.y, cs.x, cs.y);
                 }
@@ -344,8 +344,6 @@ void elph_launch_matvec(elph_handle* h, MatvecMode mode, const MatvecArgs& a) {
     P.open = a.open ? 1 : 0;
     P.tau0 = a.open ? h->shard_tau0 : 0;
     P.Lglob = a.open ? h->shard_Lglob : h->L;
-    ELPH_REQUIRE(!a.open || h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
-                 "tau-sharded slabs are implemented for the Holstein model");
     P.N = h->N;
     P.L = h->L;
     P.Nb = h->Nb;

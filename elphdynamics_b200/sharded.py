@@ -39,10 +39,11 @@ class RingComm:
         self.right = (rank + 1) % world
         self.peer_halo = None        # set by ShardedOperator.enable_p2p(): halo exchange through peer memory instead of NCCL
 
-    def exchange(self, v, lloc: int, lo: bool = True, hi: bool = True):
-        """Fill v[0] with the left neighbour's last own slice and v[lloc+1] with the right neighbour's first own slice."""
+    def exchange(self, v, lloc: int, lo: bool = True, hi: bool = True, rows_of_sites: bool = True):
+        """Fill v[0] with the left neighbour's last own slice and v[lloc+1] with the right neighbour's first own slice.
+        ``rows_of_sites`` = False for tables whose rows are not Nsites doubles (they do not fit the peer-memory halo rows)."""
         import torch.distributed as dist
-        if self.peer_halo is not None:       # peer-memory push inside one kernel (csrc/cg_pipe.cu), both directions always
+        if self.peer_halo is not None and rows_of_sites:   # peer-memory push inside one kernel (csrc/cg_pipe.cu), both directions
             self.peer_halo(v)
             return
         if self.world == 1:
@@ -87,17 +88,26 @@ class CudaSlabBackend:
     def __init__(self, model, tau0: int, Lglob: int):
         import torch
         self.torch = torch
-        self.model = model                     # HolsteinModel created with Ltau = Lloc
+        self.model = model                     # HolsteinModel / SSHModel created with Ltau = Lloc
         self.lib = model._lib
         self.h = model.handle
         self.N, self.lloc = model.Nsites, model.Ltau
+        self.is_ssh = getattr(model, "kind", 0) == 1
+        self.Nph = model.Nph if self.is_ssh else self.N     # phonon fields per time slice
         self._check(self.lib.elph_set_shard(self.h, tau0, Lglob))
         model.set_stream(torch.cuda.current_stream().cuda_stream)
         self.scal = torch.zeros(2, dtype=torch.float64, device="cuda")
         p = C.c_void_p()
-        self._check(self.lib.elph_dev_ptr_expnV(self.h, C.byref(p)))
-        # view of the handle's halo'd expnV allocation as a (Lloc+2, N) tensor for the halo exchange
-        self._D_ptr = p.value - self.N * 8
+        if self.is_ssh:
+            # the table that couples to the neighbour slab is (cosh, sinh)[tau][column]: (Lloc+2) rows of 2*Ncolumns doubles
+            self._check(self.lib.elph_dev_ptr_cosh_sinh(self.h, C.byref(p)))
+            self.ncs = 2 * model.Nbonds
+            self._D_ptr = p.value - self.ncs * 8
+        else:
+            self._check(self.lib.elph_dev_ptr_expnV(self.h, C.byref(p)))
+            # view of the handle's halo'd expnV allocation as a (Lloc+2, N) tensor for the halo exchange
+            self.ncs = self.N
+            self._D_ptr = p.value - self.N * 8
 
     def _check(self, st):
         if st != 0:
@@ -106,18 +116,23 @@ class CudaSlabBackend:
     def empty(self):
         return self.torch.zeros(self.lloc + 2, self.N, dtype=self.torch.float64, device="cuda")
 
+    def empty_field(self):
+        """A halo'd slab of phonon-field shape (Lloc + 2, Nph): forces, noise, the field itself (Nph = Nsites for Holstein)."""
+        return self.torch.zeros(self.lloc + 2, self.Nph, dtype=self.torch.float64, device="cuda")
+
     def own_ptr(self, v):
-        return v.data_ptr() + self.N * 8
+        return v.data_ptr() + v.shape[1] * 8
 
     def D_tensor(self):
-        """The handle's expnV with halos, wrapped as a CUDA tensor (no copy)."""
+        """The handle's time-dependent table with halos -- expnV (Holstein, rows of Nsites) or (cosh, sinh) (SSH, rows of
+        2*Ncolumns) -- wrapped as a CUDA tensor (no copy)."""
         torch = self.torch
-        n = (self.lloc + 2) * self.N
+        n = (self.lloc + 2) * self.ncs
         iface = {"shape": (n,), "typestr": "<f8", "data": (self._D_ptr, False), "version": 3}
 
         class _W:
             __cuda_array_interface__ = iface
-        return torch.as_tensor(_W(), device="cuda").view(self.lloc + 2, self.N)
+        return torch.as_tensor(_W(), device="cuda").view(self.lloc + 2, self.ncs)
 
     def update_model(self):
         self._check(self.lib.elph_dev_update_model(self.h))
@@ -461,7 +476,8 @@ class ShardedOperator:
     def update_model(self):
         """update_model! on the slab, then refresh the right expnV halo (D(b) is needed to recompute (M v)(b))."""
         self.be.update_model()
-        self.comm.exchange(self.be.D_tensor(), self.lloc, lo=False, hi=True)
+        D = self.be.D_tensor()
+        self.comm.exchange(D, self.lloc, lo=False, hi=True, rows_of_sites=(D.shape[1] == getattr(self.be, "N", D.shape[1])))
 
     def _mul(self, mode, y, v):
         if self.comm.peer_halo is not None and hasattr(self.be, "matvec_halo"):

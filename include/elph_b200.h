@@ -322,7 +322,11 @@ int32_t elph_dev_mulMTM_replicas_ssh(elph_handle* h, int64_t nrep, const double*
  * elph_dev_ptr_expnV).  The shard entry points take pointers to the FIRST OWN slice of vectors laid out the same way:
  * the caller (one process per GPU, torch.distributed/NCCL) fills v[-1] with the left neighbour's last slice and v[Ltau]
  * (and expnV[Ltau]) with the right neighbour's first slice before the call -- one halo exchange per product.
- * mode: 0 = M v, 1 = M^T v, 2 = M^T M v.  No reference counterpart (the reference is single-process). */
+ * mode: 0 = M v, 1 = M^T v, 2 = M^T M v.  No reference counterpart (the reference is single-process).
+ * SSH model (src/SSHModels.jl:581-701): expmu has no time index; what couples to the neighbour slab is the per-slice
+ * (cosh, sinh) table, which is re-homed the same way in rows of 2*Ncolumns doubles (own start = elph_dev_ptr_cosh_sinh); the
+ * caller fills row Ltau with the right neighbour's first row after every update_model!.  Products, the force (elph_dev_shard_
+ * muldMdx, src/SSHModels.jl:745-830) and the bosonic gradient work on SSH slabs; the peer-memory kernels are Holstein-only. */
 int32_t elph_set_shard(elph_handle* h, int64_t tau0, int64_t Lglob);
 int32_t elph_dev_shard_matvec(elph_handle* h, int32_t mode, const double* v_own, double* y_own);
 int32_t elph_dev_shard_muldMdx(elph_handle* h, const double* u_own, const double* v_own, double* out, double scale);
@@ -396,6 +400,7 @@ int32_t elph_dev_from_engine_layout(elph_handle* h, const double* engine_dev, do
 /* device pointers to resident state (engine layout) */
 int32_t elph_dev_ptr_x(elph_handle* h, double** x_dev);
 int32_t elph_dev_ptr_expnV(elph_handle* h, double** expnV_dev);
+int32_t elph_dev_ptr_cosh_sinh(elph_handle* h, double** cosh_sinh_dev);   /* Holstein [Ncolumns][2]; SSH [Ltau][Ncolumns][2] */
 /* CG on device pointers; asynchronous until the result scalars are read (blocks). */
 int32_t elph_dev_cg_solve(elph_handle* h, const double* b_dev, double* x_dev, int32_t use_precond, double tol,
                           int64_t maxiter, int64_t* iters, double* eps);

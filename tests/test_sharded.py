@@ -544,6 +544,120 @@ def test_open_slab_kernels_single_gpu(Ls, world):
         em.close()
 
 
+# ------------------------------------------------------------------------------------------- SSH slabs
+def _engine_ssh_slab(om, tau0, lloc):
+    """Engine SSH model for one slab: Ltau = lloc, field = the slab of the global field."""
+    import elphdynamics_b200 as E
+    lat = om.lat
+    elat = E.Lattice(E.UnitCell(lat.ndim, lat.norbits), lat.L1, lat.L2, lat.L3)
+    em = E.SSHModel(elat, lloc * om.dtau, om.dtau, tol=om.tol, maxiter=om.maxiter)
+    assert em.Ltau == lloc
+    em.assign_mu(om.mu)
+    for bd in om.bond_defs:
+        em.assign_hopping(bd.t, bd.omega, bd.omega4, bd.alpha, bd.alpha2, bd.o1, bd.o2, bd.d, bd.name)
+    em.initialize_model_()
+    em.x = np.ascontiguousarray(om.x.reshape(om.Nph, om.L)[:, tau0:tau0 + lloc]).reshape(-1)
+    return em
+
+
+def _ssh_problem(Ls=4, beta=1.0):
+    from helpers_ssh import oracle_ssh
+    om, rng = oracle_ssh(Lside=Ls, beta=beta, dtau=0.05, seed=11)
+    V, outs = _global_reference(om, rng)
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    x = np.zeros(om.Ndim)
+    it = solve_cg(x, om, b, ConjugateGradient(om.Ndim, tol=1e-5, maxiter=5000))
+    u = rng.normal(size=om.Ndim)
+    d = np.zeros(om.Ndof)
+    om.muldMdx(d, u, np.ascontiguousarray(V.T).reshape(-1))
+    eng = lambda a: np.ascontiguousarray(a.reshape(om.N, om.L).T)
+    return om, V, outs, eng(b), eng(x), it, eng(u), np.ascontiguousarray(d.reshape(om.Nph, om.L).T)
+
+
+def _check_ssh_rank(comm, rank, world, Ls=4, beta=1.0):
+    """Products, plain CG and the force <dM/dx> of a tau-sharded SSH lattice (open-slab generic kernels with the per-slice
+    (cosh, sinh) table halo) against the oracle's global operator (src/SSHModels.jl:581-701, :745-830)."""
+    import torch
+    from elphdynamics_b200.sharded import CudaSlabBackend, ShardedOperator, slab_bounds
+    om, V, outs, b, x_ref, it_ref, U, d_ref = _ssh_problem(Ls, beta)
+    tau0, lloc = slab_bounds(om.L, world, rank)
+    em = _engine_ssh_slab(om, tau0, lloc)
+    be = CudaSlabBackend(em, tau0, om.L)
+    assert be.is_ssh and be.Nph == om.Nph
+    op = ShardedOperator(be, comm, tol=1e-5, maxiter=5000)
+    op.update_model()
+
+    def slab(a):
+        t = be.empty()
+        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).cuda()
+        return t
+    v, y = slab(V), be.empty()
+    for name, fn in (("M", op.mulM), ("MT", op.mulMT), ("MTM", op.mulMTM)):
+        fn(y, v)
+        assert relerr(y[1:lloc + 1].cpu().numpy(), outs[name][tau0:tau0 + lloc]) <= 1e-12, (name, rank)
+    x = be.empty()
+    it, eps = op.solve_cg(x, slab(b))
+    assert abs(it - it_ref) <= 2, (it, it_ref)
+    assert relerr(x[1:lloc + 1].cpu().numpy(), x_ref[tau0:tau0 + lloc]) <= 1e-3
+    comm.exchange(v, lloc, lo=True, hi=False)
+    out = be.empty_field()
+    be.muldMdx(slab(U), v, out, 1.0)
+    assert relerr(out[1:lloc + 1].cpu().numpy(), d_ref[tau0:tau0 + lloc]) <= 1e-9, rank
+    em.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,beta", [(4, 1.0), (32, 0.5)])
+def test_sharded_ssh_single_gpu(Ls, beta):
+    """world = 1: the SSH open-slab path (table halo = the slab's own first row, self-exchanged) against the oracle."""
+    from elphdynamics_b200.sharded import RingComm
+    _check_ssh_rank(RingComm(0, 1), 0, 1, Ls=Ls, beta=beta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,world", [(4, 3), (32, 2)])
+def test_open_slab_ssh_kernels_single_gpu(Ls, world):
+    """Several SSH slabs on ONE GPU, halos copied in-process: the (cosh, sinh) row of the right neighbour's first slice, the
+    global-tau sign and uneven slab lengths against the oracle's global products and force."""
+    import torch
+    from elphdynamics_b200.sharded import CudaSlabBackend, slab_bounds
+    om, V, outs, b, x_ref, it_ref, U, d_ref = _ssh_problem(Ls, 1.0 if Ls == 4 else 0.5)
+    ring = _InProcessRing(world)
+    slabs = []
+    for r in range(world):
+        tau0, lloc = slab_bounds(om.L, world, r)
+        em = _engine_ssh_slab(om, tau0, lloc)
+        be = CudaSlabBackend(em, tau0, om.L)
+        be.update_model()
+        slabs.append((em, be, tau0, lloc))
+    Ds = [be.D_tensor() for (_, be, _, _) in slabs]
+    for r, (em, be, tau0, lloc) in enumerate(slabs):
+        Ds[r][lloc + 1].copy_(Ds[(r + 1) % world][1])
+    vs, ys = [], []
+    for (em, be, tau0, lloc) in slabs:
+        v = be.empty()
+        v[1:lloc + 1] = torch.from_numpy(V[tau0:tau0 + lloc]).cuda()
+        vs.append(v)
+        ys.append(be.empty())
+    for r in range(world):
+        ring.registry[id(vs[r])] = vs
+    for mode, name in ((0, "M"), (1, "MT"), (2, "MTM")):
+        for r, (em, be, tau0, lloc) in enumerate(slabs):
+            ring.comm(r).exchange(vs[r], lloc)
+            be.matvec(mode, vs[r], ys[r])
+            assert relerr(ys[r][1:lloc + 1].cpu().numpy(), outs[name][tau0:tau0 + lloc]) <= 1e-12, (name, r)
+    for r, (em, be, tau0, lloc) in enumerate(slabs):
+        u = be.empty()
+        u[1:lloc + 1] = torch.from_numpy(U[tau0:tau0 + lloc]).cuda()
+        out = be.empty_field()
+        be.muldMdx(u, vs[r], out, 1.0)
+        assert relerr(out[1:lloc + 1].cpu().numpy(), d_ref[tau0:tau0 + lloc]) <= 1e-9, r
+    for em, *_ in slabs:
+        em.close()
+
+
 def _gpu_worker(rank, world, port):
     import torch
     import torch.distributed as dist
@@ -562,6 +676,8 @@ def _gpu_worker(rank, world, port):
         _check_p2p_cg(be, op.comm, tau0, lloc, b, x_ref, it_ref)
         dist.barrier()
         em.close()
+        _check_ssh_rank(RingComm(rank, world), rank, world, Ls=32, beta=0.5)     # SSH slabs: table halo through NCCL
+        dist.barrier()
         # KPM-preconditioned solve: omega-sharded application through NCCL all-to-alls, products with the halo through NCCL and
         # (second pass) through peer memory inside the product kernel
         for p2p, fused, beta in ((False, False, 2.0), (True, False, 2.0), (True, True, 2.0), (True, True, 2.1), (False, True, 0.5)):
