@@ -147,7 +147,7 @@ class CudaSlabBackend:
         self._check(self.lib.elph_dev_shard_muldMdx(self.h, self.own_ptr(u), self.own_ptr(v), self.own_ptr(out), float(scale)))
 
     def lincomb(self, out, a, X, b=0.0, Y=None):
-        n = self.lloc * self.N
+        n = self.lloc * out.shape[1]              # site vectors (Nsites per slice) and phonon fields (Nph per slice) alike
         self._check(self.lib.elph_dev_lincomb(self.h, self.own_ptr(out), float(a), self.own_ptr(X), float(b),
                                               None if Y is None else self.own_ptr(Y), 0.0, None, n))
 
@@ -221,7 +221,7 @@ class CudaSlabBackend:
         """The handle's phonon field slab [Lloc][N] wrapped as a CUDA tensor (no copy)."""
         p = C.c_void_p()
         self._check(self.lib.elph_dev_ptr_x(self.h, C.byref(p)))
-        return self._wrap(p.value, (self.lloc, self.N))
+        return self._wrap(p.value, (self.lloc, self.Nph))
 
     def dSbdx(self, dS, xh, shifted=True):
         self._check(self.lib.elph_dev_shard_dSbdx(self.h, self.own_ptr(dS), self.own_ptr(xh), 1 if shifted else 0))
@@ -621,7 +621,8 @@ class ShardedOperator:
 
 
 class ShardedLangevin:
-    """Langevin updates of a tau-sharded Holstein lattice (plain CG, or KPM-preconditioned CG with a ShardedKPM), reference:
+    """Langevin updates of a tau-sharded lattice -- Holstein (plain CG, or KPM-preconditioned CG with a ShardedKPM) or SSH (plain
+    CG; phonon fields on the bonds, every field its own primary field: src/SSHModels.jl:567-576 is then the identity) --, reference:
     src/LangevinDynamics.jl:81-119 (Euler), :162-225 (Runge-Kutta), :334-384 (forces).
 
     Collectives per force evaluation: one halo exchange per product (CG iterations + M^T g + the force's v(tau-1)),
@@ -635,12 +636,15 @@ class ShardedLangevin:
         self.op, self.be, self.comm = op, op.be, op.comm
         self.N, self.L, self.tau0, self.lloc = N, Lglob, tau0, op.lloc
         self.dt = float(dt)
-        self.tr = P.tr if P is not None else TauSiteTranspose(self.comm, N, Lglob, self.lloc)
+        # the Fourier acceleration acts on phonon fields: Nph columns per time slice (= Nsites for Holstein, the bonds for SSH)
+        self.Nph = int(getattr(self.be, "Nph", N))
+        self.empty_field = getattr(self.be, "empty_field", self.be.empty)
+        self.tr = P.tr if (P is not None and self.Nph == N) else TauSiteTranspose(self.comm, self.Nph, Lglob, self.lloc)
         self.site_spans, self.tau_spans = self.tr.site_spans, self.tr.tau_spans
         self.s0, self.nloc = self.tr.s0, self.tr.nloc
         self.P = P
         self.Q = Q_site_block
-        self.xh = self.be.empty()                      # halo'd master copy of the phonon field slab
+        self.xh = self.empty_field()                   # halo'd master copy of the phonon field slab
         self.last_iters, self.last_residual, self.last_flag = 0, 0.0, 0
 
     # ---- Fourier acceleration through the all-to-all transposes ---------------------------------------------------
@@ -650,7 +654,7 @@ class ShardedLangevin:
         cols = self.tr.to_cols(v[1:self.lloc + 1])
         out_cols = torch.empty_like(cols)
         self.be.fa_cols(cols, out_cols, self.Q, power)
-        out = self.be.empty()
+        out = self.empty_field()
         self.tr.to_slab(out_cols, out[1:self.lloc + 1])
         return out
 
@@ -668,7 +672,7 @@ class ShardedLangevin:
         """dS/dx = -2 g^T (dM/dx) M^-1 g + dSb/dx (shifted), src/LangevinDynamics.jl:334-384; with a preconditioner, setup!(P)
         first (:353) from the injected Arnoldi start values."""
         be, op = self.be, self.op
-        b, x, dS = be.empty(), be.empty(), be.empty()
+        b, x, dS = be.empty(), be.empty(), self.empty_field()
         if self.P is not None:
             self.P.setup(arnoldi_noise)
         op.mulMT(b, g)
@@ -687,7 +691,7 @@ class ShardedLangevin:
         dS = self.calc_dSdx(g, arnoldi_noise)
         QdS = self.fourier_accelerate(dS, 1.0)
         sqQeta = self.fourier_accelerate(eta, 0.5)
-        dx = be.empty()
+        dx = self.empty_field()
         be.lincomb(dx, math.sqrt(2.0 * self.dt), sqQeta, -self.dt, QdS)
         be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
         self._push_x()
@@ -698,7 +702,7 @@ class ShardedLangevin:
         be = self.be
         self._push_x()
         dS1 = self.calc_dSdx(g1, arnoldi_noise1)
-        dx = be.empty()
+        dx = self.empty_field()
         be.lincomb(dx, math.sqrt(2.0 * self.dt), eta, -self.dt, dS1)
         be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
         self._push_x()

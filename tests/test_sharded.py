@@ -608,6 +608,60 @@ def _check_ssh_rank(comm, rank, world, Ls=4, beta=1.0):
     em.close()
 
 
+def _check_ssh_langevin(comm, rank, world, method="rk", Ls=4, beta=1.0):
+    """One Langevin step of a tau-sharded SSH lattice (fields on the bonds: Nph columns in the Fourier acceleration and the
+    bosonic gradient, Nsites columns in the solves) against the oracle's global step with identical injected noise."""
+    import torch
+    from helpers_ssh import oracle_ssh
+    from oracle import langevin as olang
+    from oracle.fourier import FourierAccelerator
+    from elphdynamics_b200.sharded import CudaSlabBackend, ShardedLangevin, ShardedOperator, slab_bounds
+    om, rng = oracle_ssh(Lside=Ls, beta=beta, dtau=0.05, seed=11)
+    assert np.array_equal(om.primary_field, np.arange(om.Ndof))
+    dt = 1e-3
+    eta, g1, g2 = rng.normal(size=om.Ndof), rng.normal(size=om.Ndim), rng.normal(size=om.Ndim)
+    fa = FourierAccelerator(om.Nph, om.L, om.dtau, om.omega)
+    fa.update_Q(0.0, 10.0, 0.1)
+    cg = ConjugateGradient(om.Ndim, tol=1e-10, maxiter=20000)
+    x0 = om.x.copy()
+    it_ref = olang.evolve_euler(om, cg, fa, None, dt, eta, g1) if method == "euler" else olang.evolve_rk(om, cg, fa, None, dt, eta, g1, g2)
+    x1 = om.x.copy()
+    om.x[:] = x0
+    om.update_model()
+    engf = lambda a: np.ascontiguousarray(a.reshape(om.Nph, om.L).T)     # fields: [tau][phonon]
+    engv = lambda a: np.ascontiguousarray(a.reshape(om.N, om.L).T)       # site vectors: [tau][site]
+    tau0, lloc = slab_bounds(om.L, world, rank)
+    s0, nloc = slab_bounds(om.Nph, world, rank)
+    em = _engine_ssh_slab(om, tau0, lloc)
+    be = CudaSlabBackend(em, tau0, om.L)
+    be.make_fft_plan(om.L)
+    op = ShardedOperator(be, comm, tol=1e-10, maxiter=20000)
+    Qb = torch.from_numpy(np.ascontiguousarray(engf(fa.Q)[:, s0:s0 + nloc])).cuda()
+    lang = ShardedLangevin(op, om.N, om.L, tau0, Qb, dt)
+    lang.set_x(engf(x0)[tau0:tau0 + lloc])
+
+    def slab(a, field):
+        t = be.empty_field() if field else be.empty()
+        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).cuda()
+        return t
+    if method == "euler":
+        it = lang.evolve_euler(slab(engf(eta), True), slab(engv(g1), False))
+    else:
+        it = lang.evolve_rk(slab(engf(eta), True), slab(engv(g1), False), slab(engv(g2), False))
+    assert abs(it - it_ref) <= 2, (it, it_ref)
+    assert lang.last_flag == 0
+    got = lang.xh[1:lloc + 1].cpu().numpy()
+    assert relerr(got - engf(x0)[tau0:tau0 + lloc], engf(x1 - x0)[tau0:tau0 + lloc]) <= 1e-7, (method, rank)
+    em.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,Ls", [("euler", 4), ("rk", 32)])
+def test_sharded_ssh_langevin_single_gpu(method, Ls):
+    from elphdynamics_b200.sharded import RingComm
+    _check_ssh_langevin(RingComm(0, 1), 0, 1, method, Ls=Ls, beta=1.0 if Ls == 4 else 0.5)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("Ls,beta", [(4, 1.0), (32, 0.5)])
 def test_sharded_ssh_single_gpu(Ls, beta):
@@ -677,6 +731,8 @@ def _gpu_worker(rank, world, port):
         dist.barrier()
         em.close()
         _check_ssh_rank(RingComm(rank, world), rank, world, Ls=32, beta=0.5)     # SSH slabs: table halo through NCCL
+        dist.barrier()
+        _check_ssh_langevin(RingComm(rank, world), rank, world, "rk", Ls=32, beta=0.5)
         dist.barrier()
         # KPM-preconditioned solve: omega-sharded application through NCCL all-to-alls, products with the halo through NCCL and
         # (second pass) through peer memory inside the product kernel
