@@ -63,7 +63,19 @@ void elph_gather_primary(elph_handle* h, double* out, const double* in) {
 void elph_calc_dSdx_dev(elph_handle* h, const double* g_dev, const double* arnoldi_host, bool use_precond, double* dSdx_dev,
                         double* Minv_dev, elph_solve_info* info) {
     elph_trace_mark(h, "(before calc_dSdx)");
-    if (use_precond && h->kpm.configured) elph_kpm_setup_impl(h, arnoldi_host, nullptr);  // setup!(P) :364
+    // setup!(P) :364.  The polynomials survive a set-up unless the spectral window moved by more than the hysteresis buffer, so the
+    // solve starts right behind update_A! with the polynomials it would almost always end up with, while the Arnoldi kernel runs
+    // beside it (two SMs are left free) and a host thread reduces its result; if the set-up does change them, the solve is repeated.
+    bool speculative = false;
+    if (use_precond && h->kpm.configured) {
+        if (elph_kpm_can_speculate(h)) {
+            elph_kpm_setup_begin(h, arnoldi_host);
+            speculative = true;
+            h->spec_running = true;
+        } else {
+            elph_kpm_setup_impl(h, arnoldi_host, nullptr);
+        }
+    }
     elph_trace_mark(h, "kpm setup");
     ELPH_CUDA(cudaMemsetAsync(Minv_dev, 0, h->Ndim * sizeof(double), h->stream));       // fill!(M^-1 g, 0) :365
     MatvecArgs m;
@@ -71,7 +83,24 @@ void elph_calc_dSdx_dev(elph_handle* h, const double* g_dev, const double* arnol
     m.y = h->d_b;
     elph_launch_matvec(h, MODE_MT, m);                                                    // b = M^T g :373
     elph_trace_mark(h, "b = M^T g");
-    elph_solve_device(h, h->d_b, Minv_dev, use_precond, 1.0, info);                       // ldiv! :374
+    if (speculative) {
+        bool stale = true;
+        try {
+            elph_solve_device(h, h->d_b, Minv_dev, use_precond, 1.0, info);
+        } catch (...) {
+            h->spec_running = false;
+            try { elph_kpm_setup_finish(h, nullptr); } catch (...) {}
+            throw;
+        }
+        h->spec_running = false;
+        stale = elph_kpm_setup_finish(h, nullptr);
+        if (stale) {   // the window moved: repeat with the new polynomials (or without, if the preconditioner switched itself off)
+            ELPH_CUDA(cudaMemsetAsync(Minv_dev, 0, h->Ndim * sizeof(double), h->stream));
+            elph_solve_device(h, h->d_b, Minv_dev, use_precond, 1.0, info);
+        }
+    } else {
+        elph_solve_device(h, h->d_b, Minv_dev, use_precond, 1.0, info);                   // ldiv! :374
+    }
     elph_trace_mark(h, "solve");
     // dSdx = -2 <dM/dx> + dSb/dx (shifted = true)   :378-381, :341
     elph_muldMdx_dev(h, g_dev, Minv_dev, dSdx_dev, -2.0, true, true);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <complex>
+#include <future>
 #include <set>
 #include <string>
 #include <vector>
@@ -87,6 +88,10 @@ struct KpmState {
     std::vector<int> coeff_off;             // prefix offsets into coeff
     std::vector<std::complex<double>> coeff;  // concatenated c_m per omega
     std::vector<int> schedule;              // omegas sorted by order, longest first
+    cudaStream_t spec_stream = nullptr;     // speculative set-up: Arnoldi kernel + read-back beside the solve
+    cudaEvent_t spec_fork = nullptr, spec_done = nullptr;
+    bool spec_stale = false;                // the last set-up changed the polynomials / the active flag
+    std::future<std::pair<double, double>> spec_future;   // (e_max, 1/e_min) of the set-up in flight
     int nsched = 0;                         // frequencies the chain kernels run (= Lo2 unless an omega subset is set)
     int sub_first = 0, sub_stride = 1;      // omega-sharded apply (sharded.py): this handle runs w = first, first+stride, ...
     // host copies of the tau-averaged operator (for the Arnoldi iteration)
@@ -157,6 +162,8 @@ struct elph_handle {
     bool hc_tiles = true;        // honeycomb lattices: register-tile kernels (tuning key 21)
     int pcg_grid = 0;            // fused PCG: CTAs of the persistent kernel (0 = one per SM); tuning key 20
     bool kpm_dev_arnoldi = true; // KPM set-up: Arnoldi eigenvalue bounds on the device (tuning key 19)
+    bool kpm_speculate = true;   // force evaluation: solve with the previous polynomials while the Arnoldi bounds are computed (key 25)
+    bool spec_running = false;   // a speculative set-up is in flight: the one-kernel PCG leaves two SMs to the Arnoldi kernel
     bool pcg_half_fft = true;   // fused PCG: tau-FFTs at length L/2 for even L (tuning key 18)
     bool pcg_persistent = true; // KPM-preconditioned CG as one persistent kernel where served (pcg_fused.cu, tuning key 17)
     bool kpm_fast = true;      // KPM apply: sweeps in tanh form with folded constants (tuning key 16)
@@ -467,7 +474,11 @@ void elph_fourier_accelerate_dev(elph_handle* h, const double* vin, double* vout
 
 // kpm.cu
 void elph_kpm_init(elph_handle* h, int n, double buf, double c1, double c2);
-void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info, const double* ext_eVbar_dev = nullptr);
+void elph_kpm_setup_impl(elph_handle* h, const double* arnoldi_noise_host, elph_kpm_info* info, const double* ext_eVbar_dev = nullptr,
+                         int phase = 0);
+bool elph_kpm_can_speculate(const elph_handle* h);
+void elph_kpm_setup_begin(elph_handle* h, const double* arnoldi_noise_host);
+bool elph_kpm_setup_finish(elph_handle* h, elph_kpm_info* info);
 void elph_kpm_set_omega_subset(elph_handle* h, int first, int stride);
 void elph_kpm_chains_dev(elph_handle* h, const cplx* nu_in, cplx* nu_out);
 // kpm_shard.cu

@@ -673,6 +673,11 @@ void elph_kpm_free(elph_handle* h) {
     cudaFree(K.d_csbar_tile);
     cudaFree(K.d_hm);
     cudaFree(K.d_Q);
+    if (K.spec_stream) {
+        cudaStreamDestroy(K.spec_stream);
+        cudaEventDestroy(K.spec_fork);
+        cudaEventDestroy(K.spec_done);
+    }
     if (K.h_hm) cudaFreeHost(K.h_hm);
     K = KpmState();
 }
@@ -691,6 +696,21 @@ static void kpm_build_schedule(elph_handle* h) {
     h->kpm_version++;
 }
 
+// Speculative set-up (dynamics.cu): the hysteresis keeps the polynomials of the previous set-up unless the spectral window moved
+// by more than `buf` (src/KPMPreconditioners.jl:296-309), so the solve that follows setup!(P) can start as soon as update_A! is
+// queued, while the Arnoldi kernel runs beside it on two SMs and the host reduces the two Hessenberg matrices.
+bool elph_kpm_can_speculate(const elph_handle* h) {
+    const KpmState& K = h->kpm;
+    return h->kpm_speculate && K.configured && K.ever_setup && K.active && K.d_coeff && h->kpm_dev_arnoldi && K.n <= 32 && h->N <= 8192 &&
+           !h->trace;
+}
+void elph_kpm_setup_begin(elph_handle* h, const double* noise) { elph_kpm_setup_impl(h, noise, nullptr, nullptr, 1); }
+// true when the speculative solve has to be repeated (polynomials recomputed or the preconditioner switched itself off)
+bool elph_kpm_setup_finish(elph_handle* h, elph_kpm_info* info) {
+    elph_kpm_setup_impl(h, nullptr, info, nullptr, 2);
+    return h->kpm.spec_stale;
+}
+
 void elph_kpm_set_omega_subset(elph_handle* h, int first, int stride) {
     KpmState& K = h->kpm;
     ELPH_REQUIRE(K.configured, ELPH_ERR_STATE, "KPM preconditioner not configured (kpm_n == 0 at elph_create)");
@@ -700,13 +720,28 @@ void elph_kpm_set_omega_subset(elph_handle* h, int first, int stride) {
     kpm_build_schedule(h);
 }
 
-void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* info, const double* ext_eVbar) {
+// phase 0: the whole of setup!(P).  Phases 1 / 2 split it for the speculative solve of the force evaluation (dynamics.cu): phase 1
+// queues update_A! on the handle's stream and the Arnoldi kernel + read-back on the side stream and returns without waiting;
+// phase 2 waits for the read-back, finishes (bounds, hysteresis, coefficients) and tells through info->recomputed / the return
+// of elph_kpm_setup_finish whether the polynomials the speculative solve used are still the right ones.
+void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* info, const double* ext_eVbar, int phase) {
     KpmState& K = h->kpm;
     ELPH_REQUIRE(K.configured, ELPH_ERR_STATE, "KPM preconditioner not configured (kpm_n == 0 at elph_create)");
-    ELPH_REQUIRE(noise != nullptr, ELPH_ERR_INVALID, "arnoldi_noise must provide 2*Nsites values");
+    ELPH_REQUIRE(noise != nullptr || phase == 2, ELPH_ERR_INVALID, "arnoldi_noise must provide 2*Nsites values");
     const int N = h->N, L = h->L, Nb = h->Nb, T = 256;
     // update_A!
     const bool dev = h->kpm_dev_arnoldi && K.n <= 32 && (N <= 8192);
+    ELPH_REQUIRE(phase == 0 || (dev && K.ever_setup), ELPH_ERR_STATE, "split KPM set-up needs the device Arnoldi path and a previous set-up");
+    cudaStream_t arn_stream = h->stream;
+    if (phase == 1) {
+        if (!K.spec_stream) {
+            ELPH_CUDA(cudaStreamCreateWithFlags(&K.spec_stream, cudaStreamNonBlocking));
+            ELPH_CUDA(cudaEventCreateWithFlags(&K.spec_fork, cudaEventDisableTiming));
+            ELPH_CUDA(cudaEventCreateWithFlags(&K.spec_done, cudaEventDisableTiming));
+        }
+        arn_stream = K.spec_stream;
+    }
+    if (phase != 2) {
     ELPH_REQUIRE(!ext_eVbar || h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
                  "KPM set-up from an external tau-mean is implemented for the Holstein model");
     if (h->model == ELPH_MODEL_HOLSTEIN) {
@@ -746,18 +781,24 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
         }
     }
     elph_trace_mark(h, "  kpm: tau-mean");
+    }   // phase != 2
     // Arnoldi bounds
     double e_max, inv_max;
     if (dev) {
         // both Krylov runs in one launch (arnoldi_kernel): only the two small Hessenberg matrices come back
         const int n = K.n;
         const size_t hstride = (size_t)(n + 1) * n + 1;
+        if (phase != 2) {
+        if (phase == 1) {   // the side stream starts where update_A! ends on the handle's stream
+            ELPH_CUDA(cudaEventRecord(K.spec_fork, h->stream));
+            ELPH_CUDA(cudaStreamWaitEvent(arn_stream, K.spec_fork, 0));
+        }
         if (!K.d_noise) {
             K.d_noise = elph_dalloc<double>(2 * (size_t)N);
             K.d_hm = elph_dalloc<double>(4 * hstride);
             ELPH_CUDA(cudaMallocHost(&K.h_hm, 4 * hstride * sizeof(double)));
         }
-        ELPH_CUDA(cudaMemcpyAsync(K.d_noise, noise, 2 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ELPH_CUDA(cudaMemcpyAsync(K.d_noise, noise, 2 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, arn_stream));
         ArnoldiParams A;
         A.eVbar = K.d_eVbar; A.csbar = K.d_csbar; A.bonds = h->d_bonds; A.goff = h->d_goff; A.start = K.d_noise;
         A.hm = K.d_hm; A.ngroups = h->ngroups; A.N = N; A.n = n;
@@ -782,10 +823,10 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
         do {                                                                                   \
             if (A.q_in_smem) {                                                                 \
                 elph_enable_smem(h, arnoldi_kernel<E, SQ, true>);                              \
-                arnoldi_kernel<E, SQ, true><<<2, threads, smem, h->stream>>>(A);               \
+                arnoldi_kernel<E, SQ, true><<<2, threads, smem, arn_stream>>>(A);              \
             } else {                                                                           \
                 elph_enable_smem(h, arnoldi_kernel<E, SQ, false>);                             \
-                arnoldi_kernel<E, SQ, false><<<2, threads, smem, h->stream>>>(A);              \
+                arnoldi_kernel<E, SQ, false><<<2, threads, smem, arn_stream>>>(A);             \
             }                                                                                  \
         } while (0)
         if (square) ARN_LAUNCH(8, true);
@@ -795,15 +836,37 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
 #undef ARN_LAUNCH
         ELPH_CUDA(cudaGetLastError());
         h->launches++;
-        ELPH_CUDA(cudaMemcpyAsync(K.h_hm, K.d_hm, 4 * hstride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        ELPH_CUDA(cudaStreamSynchronize(h->stream));
-        elph_trace_mark(h, "  kpm: arnoldi kernel");
-        // h = first-pass + second-pass coefficients (the sub-diagonal norms sit in the first matrix only)
-        for (int run = 0; run < 2; ++run)
-            for (size_t i = 0; i + 1 < hstride; ++i) K.h_hm[2 * run * hstride + i] += K.h_hm[(2 * run + 1) * hstride + i];
-        const int l0 = (int)K.h_hm[hstride - 1], l1 = (int)K.h_hm[3 * hstride - 1];
-        e_max = hessenberg_bound(K.h_hm, n, l0);
-        inv_max = hessenberg_bound(K.h_hm + 2 * hstride, n, l1);
+        ELPH_CUDA(cudaMemcpyAsync(K.h_hm, K.d_hm, 4 * hstride * sizeof(double), cudaMemcpyDeviceToHost, arn_stream));
+        }   // phase != 2
+        // h = first-pass + second-pass coefficients (the sub-diagonal norms sit in the first matrix only), then the two bounds
+        auto reduce_bounds = [hm = K.h_hm, hstride, n]() {
+            for (int run = 0; run < 2; ++run)
+                for (size_t i = 0; i + 1 < hstride; ++i) hm[2 * run * hstride + i] += hm[(2 * run + 1) * hstride + i];
+            const int l0 = (int)hm[hstride - 1], l1 = (int)hm[3 * hstride - 1];
+            return std::make_pair(hessenberg_bound(hm, n, l0), hessenberg_bound(hm + 2 * hstride, n, l1));
+        };
+        if (phase == 1) {
+            // a host thread waits for the read-back and reduces the Hessenberg matrices while the caller queues and waits for the solve
+            ELPH_CUDA(cudaEventRecord(K.spec_done, arn_stream));
+            K.spec_future = std::async(std::launch::async, [done = K.spec_done, dev_id = h->device, reduce_bounds]() {
+                cudaSetDevice(dev_id);
+                const cudaError_t e = cudaEventSynchronize(done);
+                if (e != cudaSuccess) return std::make_pair((double)NAN, (double)NAN);
+                return reduce_bounds();
+            });
+            return;
+        }
+        std::pair<double, double> eb;
+        if (phase == 2) {
+            eb = K.spec_future.get();
+            ELPH_REQUIRE(eb.first == eb.first, ELPH_ERR_CUDA, "speculative KPM set-up: the Arnoldi read-back failed");
+        } else {
+            ELPH_CUDA(cudaStreamSynchronize(h->stream));
+            elph_trace_mark(h, "  kpm: arnoldi kernel");
+            eb = reduce_bounds();
+        }
+        e_max = eb.first;
+        inv_max = eb.second;
     } else {
         // the two Krylov runs (on A for e_max, on A^-1 for e_min) are independent: second host thread for the inverse one
         auto inv_run = std::async(std::launch::async, [&]() { return host_arnoldi(h, K, noise + N, true); });
@@ -812,6 +875,7 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
     }
     elph_trace_mark(h, "  kpm: eigenvalues");
     const double e_min = std::isfinite(inv_max) ? 1.0 / inv_max : -INFINITY;
+    const bool was_active = K.active;
     K.e_min = e_min;
     K.e_max = e_max;
     bool recomputed = false;
@@ -850,6 +914,7 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
         K.active = false;
     }
     K.ever_setup = true;
+    K.spec_stale = recomputed || (K.active != was_active);
     if (info) {
         info->active = K.active ? 1 : 0;
         info->recomputed = recomputed ? 1 : 0;

@@ -649,7 +649,7 @@ template <int NSEG, int PY, int SB, int MAXT, bool SSH = false>
 bool launch_fused(elph_handle* h, FusedParams& P, int nwarps) {
     auto kern = pcg_fused_kernel<NSEG, PY, SB, MAXT, SSH>;
     // SSH keeps the tables of a CTA's slices resident: the chunk length is fixed by the full grid (one CTA per SM)
-    int full = h->sm_count & ~1;
+    int full = (h->spec_running ? h->sm_count - 2 : h->sm_count) & ~1;   // a speculative set-up runs its Arnoldi kernel on two SMs
     if (h->pcg_grid >= 2) full = std::min(full, h->pcg_grid & ~1);
     const int cs_full = (h->L + full - 1) / full;
     const size_t smem = fused_smem<NSEG, PY, SB>(h->L, P.Ly, nwarps, P.max_order, SSH ? cs_full + 1 : 0);
@@ -657,7 +657,7 @@ bool launch_fused(elph_handle* h, FusedParams& P, int nwarps) {
     elph_enable_smem(h, kern);
     const int threads = nwarps * 32;
     // one CTA per SM, an even number of them (2-CTA clusters), all co-resident
-    int grid = h->sm_count & ~1;
+    int grid = (h->spec_running ? h->sm_count - 2 : h->sm_count) & ~1;
     if (h->pcg_grid >= 2) grid = std::min(grid, h->pcg_grid & ~1);   // tuning key 20: leave SMs to other chains on the same GPU
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
