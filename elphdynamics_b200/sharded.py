@@ -556,7 +556,8 @@ class ShardedOperator:
 
     def solve_pcg(self, x, b, P, tol: float = 0.0, maxiter: int = 0):
         """Preconditioned CG, src/IterativeSolvers.jl:153-234, on the sharded lattice: per iteration one product (one halo
-        exchange), one preconditioner application (four all-to-alls) and three scalar all-reduces.  Returns (iters, eps)."""
+        exchange), one preconditioner application (ShardedKPM.ldiv) and two scalar round trips (p.Ap; |r|^2 and r.z together).
+        Returns (iters, eps)."""
         be = self.be
         tol = tol or self.tol
         maxiter = maxiter or self.maxiter
@@ -569,20 +570,29 @@ class ShardedOperator:
         rdotz = self.gdot(r, z)
         eps0 = math.sqrt(self.gdot(r, r)) / normb
         eps, kmin = eps0, 0.0
+        import torch
         for j in range(1, maxiter + 1):
             self.mulMTM(z, p)
             alpha = rdotz / self.gdot(p, z)
             be.lincomb(x, 1.0, x, alpha, p)
             be.lincomb(r, 1.0, r, -alpha, z)
-            eps = math.sqrt(self.gdot(r, r)) / normb
+            # |r|^2 decides the stop rule and r.z the next direction.  The application of the preconditioner is queued BEFORE |r|^2
+            # is read back, so the round trip of the scalars (all-reduce + device-to-host) hides behind it and both travel together:
+            # two host synchronisations per iteration instead of three.  Same values, same decisions as :205-227; the one
+            # application after the last iteration is computed and dropped.
+            rr_t = be.dot(r, r)
+            P.ldiv(z, r)
+            rz_t = be.dot(r, z)
+            both = torch.cat([rr_t.reshape(1), rz_t.reshape(1)])
+            self.comm.allreduce_sum(both)
+            rr, new_rdotz = (float(v) for v in both.tolist())
+            eps = math.sqrt(rr) / normb
             with np.errstate(all="ignore"):
                 k = float((2.0 * j / np.log(2.0 * eps0 / eps)) ** 2)
             if k > kmin:
                 kmin = k
             if eps < tol or kmin > self.kappa_max:
                 return j, eps
-            P.ldiv(z, r)
-            new_rdotz = self.gdot(r, z)
             beta = new_rdotz / rdotz
             rdotz = new_rdotz
             be.lincomb(p, 1.0, z, beta, p)
