@@ -866,7 +866,7 @@ def main():
                 "transposes": "pulled through peer memory inside the FFT / gather kernels, 4 barrier kernels per application "
                               "(csrc/kpm_shard.cu)" if fusedE else "4 NCCL all-to-alls per application",
                 "note": "ShardedOperator.solve_pcg: host-driven loop (product with the halo inside the kernel, preconditioner "
-                        "application, 3 all-reduced scalars per iteration); the application is bounded by the Chebyshev chain of the "
+                        "application queued before |r|^2 is read back: 2 scalar round trips per iteration); the application is bounded by the Chebyshev chain of the "
                         "lowest frequency (2 x max_order dependent sweeps of one 64x64 slice), which omega-sharding does not shorten"}
             auxE.close()
         except Exception as exc:              # an extra figure must not cost the bench line

@@ -80,7 +80,44 @@ def sharded_p2p():
     m.close()
 
 
-for name, fn in (("holstein", holstein_square), ("generic", generic_and_hmc), ("ssh", ssh_square), ("p2p", sharded_p2p)):
+def sharded_kpm_and_ssh():
+    """Round 2: the sharded KPM application through the arenas (kpm_shard.cu), the all-to-all form's column FFTs and chain subset,
+    the speculative set-up, and the SSH open-slab kernels (world 1: the ring closes on the GPU itself)."""
+    import torch
+    from elphdynamics_b200.sharded import CudaSlabBackend, RingComm, ShardedKPM, ShardedOperator
+    m, rng = workloads.holstein("square", 32, 0.8, 0.1, mu=-0.5)
+    aux, _ = workloads.holstein("square", 32, 0.8, 0.1, mu=-0.5)
+    be = CudaSlabBackend(m, 0, m.Ltau)
+    op = ShardedOperator(be, RingComm(0, 1), tol=1e-6)
+    op.update_model()
+    be.kpm_init(aux)
+    P = ShardedKPM(op, m.Nsites, m.Ltau)
+    noise = rng.normal(size=2 * m.Nsites)
+    P.setup(noise)
+    b, x = be.empty(), be.empty()
+    b[1:m.Ltau + 1].normal_()
+    print("sharded PCG, all-to-all form", op.ldiv(x, b, P=P))
+    assert P.enable_fused(0)
+    print("sharded PCG, arena form", op.ldiv(x, b, P=P))
+    be.kpm_shard_check()
+    m.close()
+    aux.close()
+    ms, rs = workloads.ssh_square(Lside=32, beta=0.2, dtau=0.05)
+    bs = CudaSlabBackend(ms, 0, ms.Ltau)
+    ops = ShardedOperator(bs, RingComm(0, 1), tol=1e-6)
+    ops.update_model()
+    v, y = bs.empty(), bs.empty()
+    v[1:ms.Ltau + 1].normal_()
+    for f in (ops.mulM, ops.mulMT, ops.mulMTM):
+        f(y, v)
+    out = bs.empty_field()
+    bs.muldMdx(y, v, out, 1.0)
+    print("ssh slab", float(y.abs().max()), float(out.abs().max()))
+    ms.close()
+
+
+for name, fn in (("holstein", holstein_square), ("generic", generic_and_hmc), ("ssh", ssh_square), ("p2p", sharded_p2p),
+                 ("shardkpm", sharded_kpm_and_ssh)):
     if which in ("all", name):
         fn()
 print("sanitize targets done")
