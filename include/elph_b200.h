@@ -439,7 +439,12 @@ int32_t elph_set_chunk(elph_handle* h, int32_t slices_per_cta);
  * 21 = register-tile kernels for the honeycomb lattice 32 cells wide (default 1),
  * 22 = tau-sharded M^T M with the halo exchange inside the product kernel (default 1; 0 = exchange kernel + product kernel),
  * 23 = elph_langevin_step: eta and g2 travel host-to-device on a second stream during the first solve (default 1),
- * 24 = fused M^T M on square lattices with the sweeps in tanh form (default 1) */
+ * 24 = fused M^T M on square lattices with the sweeps in tanh form (default 1),
+ * 25 = speculative setup!(P) in the force evaluation (calc_dSfdx!, src/LangevinDynamics.jl:350-384; default 1): the solve is queued
+ *      right behind update_A! with the polynomials of the previous set-up -- which the hysteresis of setup! keeps unless the
+ *      spectral window moved by more than `buf` (src/KPMPreconditioners.jl:296-309) -- while the Arnoldi kernel runs beside it and a
+ *      host thread reduces its result; the solve is repeated when the set-up does change the polynomials or the active flag, so
+ *      the results are those of the reference order (0 = set-up strictly before the solve) */
 int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value);
 /* read-back of a tuning key; key 100 = which kernel served the last unpreconditioned persistent solve: 0 = none yet /
  * other kernels, else variant * 100 + CTAs per slice * 10 + warps per CTA of the pipelined kernel; key 101 = its time slices per CTA */

@@ -364,3 +364,49 @@ def test_D_cg_iterations(geom, Ls, dtau):
         _check_forms(em, om, b, it_c, xc, forms)
     finally:
         em.close()
+
+
+def test_B_sharded_kpm_pcg_against_oracle_and_engine(config_B):
+    """Config B through the tau-sharded driver at world 1 (the slab = the whole lattice, the ring closes on the GPU): the
+    omega-sharded application of the preconditioner in both forms (all-to-all path degenerate to copies, arena path of
+    csrc/kpm_shard.cu) and ``ldiv!(x, model, b, P)`` against the oracle's iteration count (+-2) and the single-GPU engine's solution."""
+    import torch
+    import elphdynamics_b200 as E
+    from oracle.kpm import KPMPreconditioner
+    from oracle.solvers import ConjugateGradient, ldiv
+    from elphdynamics_b200.sharded import CudaSlabBackend, RingComm, ShardedKPM, ShardedOperator
+    om, em, rng = config_B
+    noise = rng.normal(size=2 * om.N)
+    g = rng.normal(size=om.Ndim)
+    b = np.zeros(om.Ndim)
+    om.mulMT(b, g)
+    Po = KPMPreconditioner(om)
+    Po.setup(noise)
+    xo = np.zeros(om.Ndim)
+    it_o, _, fo = ldiv(xo, om, b, ConjugateGradient(om.Ndim, tol=om.tol, maxiter=om.maxiter), Po)
+    Pe = E.SymmetricKPMPreconditioner(em)
+    E.setup_(Pe, noise)
+    xe = np.zeros(om.Ndim)
+    it_e, _, fe = E.ldiv_(xe, em, b, Pe)
+    assert fo == fe == 0
+    slab, aux = engine_holstein_like(om), engine_holstein_like(om)
+    be = CudaSlabBackend(slab, 0, om.L)
+    op = ShardedOperator(be, RingComm(0, 1), tol=om.tol, maxiter=om.maxiter)
+    op.update_model()
+    be.kpm_init(aux)
+    P = ShardedKPM(op, om.N, om.L)
+    eng = lambda a: np.ascontiguousarray(a.reshape(om.N, om.L).T)
+    bt = be.empty()
+    bt[1:om.L + 1] = torch.from_numpy(eng(b)).cuda()
+    for fused in (False, True):
+        if fused:
+            assert P.enable_fused(0)
+        P.setup(noise)
+        assert P.active and np.array_equal(be.kpm_orders(), Po.order)
+        x = be.empty()
+        it_s, res_s, fs = op.ldiv(x, bt, P=P)
+        assert fs == 0 and abs(it_s - it_o) <= 2 and abs(it_s - it_e) <= 1, (fused, it_s, it_o, it_e)
+        assert relerr(x[1:om.L + 1].cpu().numpy(), eng(xe)) <= 1e-6, fused
+    be.kpm_shard_check()
+    slab.close()
+    aux.close()
