@@ -156,7 +156,18 @@ double elph_hmc_refresh_phi_dev(elph_handle* h) {
 // calc_O^-1 Lambda phi!  (:820-915)
 void elph_hmc_calc_Oinv_dev(elph_handle* h, bool use_precond, const double* arnoldi_host, double power, int64_t* iters, int* flag) {
     HmcState& S = h->hmc;
-    if (use_precond && h->kpm.configured) elph_kpm_setup_impl(h, arnoldi_host, nullptr);
+    // setup!(P) :829; speculative as in the Langevin force (dynamics.cu): the two solves start with the previous polynomials while
+    // the Arnoldi bounds are computed beside them, and are repeated if the set-up changes the polynomials
+    bool speculative = false;
+    if (use_precond && h->kpm.configured) {
+        if (elph_kpm_can_speculate(h)) {
+            elph_kpm_setup_begin(h, arnoldi_host);
+            speculative = true;
+            h->spec_running = true;
+        } else {
+            elph_kpm_setup_impl(h, arnoldi_host, nullptr);
+        }
+    }
     update_Lam(h);
     lam_apply(h, S.Lphip, S.phip, 0);
     lam_apply(h, S.Lphim, S.phim, 0);
@@ -179,21 +190,42 @@ void elph_hmc_calc_Oinv_dev(elph_handle* h, bool use_precond, const double* arno
         *flag = fl2;
         return;
     }
-    elph_solve_info info = {};
-    int64_t tot = 0;
-    ELPH_CUDA(cudaMemsetAsync(S.Op, 0, h->Ndim * sizeof(double), h->stream));
-    elph_solve_device(h, S.Lphip, S.Op, use_precond, power, &info);
-    tot += info.iters;
-    int fl = info.flag;
-    if (fl == 0) {
-        ELPH_CUDA(cudaMemsetAsync(S.Om, 0, h->Ndim * sizeof(double), h->stream));
-        elph_solve_device(h, S.Lphim, S.Om, use_precond, power, &info);
+    // a rejected speculation must leave O^-1 Lambda phi_- as the reference would: keep what it held before the first attempt
+    if (speculative)
+        ELPH_CUDA(cudaMemcpyAsync(h->d_vc, S.Om, h->Ndim * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    auto solve_pair = [&]() {
+        elph_solve_info info = {};
+        int64_t tot = 0;
+        ELPH_CUDA(cudaMemsetAsync(S.Op, 0, h->Ndim * sizeof(double), h->stream));
+        elph_solve_device(h, S.Lphip, S.Op, use_precond, power, &info);
         tot += info.iters;
-        fl = info.flag;
+        int fl = info.flag;
+        if (fl == 0) {
+            ELPH_CUDA(cudaMemsetAsync(S.Om, 0, h->Ndim * sizeof(double), h->stream));
+            elph_solve_device(h, S.Lphim, S.Om, use_precond, power, &info);
+            tot += info.iters;
+            fl = info.flag;
+        }
+        if (fl == 0) tot = (tot + 1) / 2;  // cld(iters, 2)
+        *iters = tot;
+        *flag = fl;
+    };
+    if (speculative) {
+        try {
+            solve_pair();
+        } catch (...) {
+            h->spec_running = false;
+            try { elph_kpm_setup_finish(h, nullptr); } catch (...) {}
+            throw;
+        }
+        h->spec_running = false;
+        if (elph_kpm_setup_finish(h, nullptr)) {
+            ELPH_CUDA(cudaMemcpyAsync(S.Om, h->d_vc, h->Ndim * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            solve_pair();
+        }
+    } else {
+        solve_pair();
     }
-    if (fl == 0) tot = (tot + 1) / 2;  // cld(iters, 2)
-    *iters = tot;
-    *flag = fl;
 }
 
 double elph_hmc_calc_Sf_dev(elph_handle* h);
