@@ -1441,6 +1441,7 @@ int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value) {
             case 22: h->halo_fused = (value != 0); break;
             case 23: h->overlap_uploads = (value != 0); break;
             case 25: h->kpm_speculate = (value != 0); break;
+            case 26: h->kpm_wide = (value != 0); h->kpm_version++; break;
             case 24: h->mtm_tanh = (value != 0); break;
             case 20: ELPH_REQUIRE(value >= 0 && value <= 4096, ELPH_ERR_INVALID, "CTA count out of range"); h->pcg_grid = value; break;
             case 14: ELPH_REQUIRE(value >= 0 && value <= 64, ELPH_ERR_INVALID, "slices per CTA out of range"); h->pipe_spc = value; break;

@@ -162,6 +162,8 @@ struct elph_handle {
     bool hc_tiles = true;        // honeycomb lattices: register-tile kernels (tuning key 21)
     int pcg_grid = 0;            // fused PCG: CTAs of the persistent kernel (0 = one per SM); tuning key 20
     bool kpm_dev_arnoldi = true; // KPM set-up: Arnoldi eigenvalue bounds on the device (tuning key 19)
+    bool kpm_wide = false;       // KPM apply on 64-wide lattices: 8-CTA clusters, (re | im) x 4 row strips per frequency (key 26;
+                                 // measured no faster than the 2-CTA kernel: the strip-edge round trip through DSMEM costs what it saves)
     bool kpm_speculate = true;   // force evaluation: solve with the previous polynomials while the Arnoldi bounds are computed (key 25)
     bool spec_running = false;   // a speculative set-up is in flight: the one-kernel PCG leaves two SMs to the Arnoldi kernel
     bool pcg_half_fft = true;   // fused PCG: tau-FFTs at length L/2 for even L (tuning key 18)

@@ -133,21 +133,25 @@ __device__ __forceinline__ void poly_real(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, 
 //     evs = 2 (c0 c1 c2 c3 / mag) eVbar ;  Kt = prod_g (1 + t_g X_g)
 //     T_1 = (1/2) S v - (avg/mag) v ;  T_n = S T_{n-1} - (2 (avg/mag) T_{n-1} + T_{n-2}) ;  S u = Kt (evs .* u)   [A'^T: evs .* (Kt^T u)]
 // The bracket does not depend on the sweep, so it is off the dependent chain.  Differs from poly_real by rounding only.
-template <int NSEG, int PY, bool TRANSPOSED>
+// WIDE: the slice is split into row strips over the CTAs of a cluster (exchange_edges1_wide; wc = the neighbours' cluster ranks)
+template <int NSEG, int PY, bool TRANSPOSED, bool WIDE = false>
 __device__ __forceinline__ void sweep_t(Tile<NSEG, PY>& s, const KsqParams& P, double* strips, int& xbuf, int warp, int nwarps,
-                                        int lane) {
+                                        int lane, WideCtx* wc = nullptr) {
     constexpr int LX = 32 * NSEG;
     double ab[NSEG], be[NSEG];
+    auto exchange = [&]() {
+        if (WIDE) exchange_edges1_wide(s, strips + (size_t)xbuf * nwarps * 2 * LX, xbuf, warp, nwarps, lane, ab, be, *wc);
+        else exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
+        xbuf ^= 1;
+    };
     if (!TRANSPOSED) {
         g0_x_even_t(s, P.t0);
         g1_x_odd_t(s, P.t1, lane);
         g2_y_even_t(s, P.t2);
-        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
-        xbuf ^= 1;
+        exchange();
         g3_y_odd_t(s, P.t3, ab, be);
     } else {
-        exchange_edges1(s, strips + (size_t)xbuf * nwarps * 2 * LX, warp, nwarps, lane, ab, be);
-        xbuf ^= 1;
+        exchange();
         g3_y_odd_t(s, P.t3, ab, be);
         g2_y_even_t(s, P.t2);
         g1_x_odd_t(s, P.t1, lane);
@@ -155,10 +159,11 @@ __device__ __forceinline__ void sweep_t(Tile<NSEG, PY>& s, const KsqParams& P, d
     }
 }
 
-template <int NSEG, int PY, bool TRANSPOSED>
+template <int NSEG, int PY, bool TRANSPOSED, bool WIDE = false>
 __device__ __forceinline__ void poly_real_fast(Tile<NSEG, PY>& A, Tile<NSEG, PY>& B, const Tile<NSEG, PY>& vin,
                                                const Tile<NSEG, PY>& evs, const cplx* c_s, int order, const KsqParams& P,
-                                               double* strips, int& xbuf, int warp, int nwarps, int lane) {
+                                               double* strips, int& xbuf, int warp, int nwarps, int lane,
+                                               WideCtx* wc = nullptr) {
     Tile<NSEG, PY> un, uprev, s, pre;
     const double sg = TRANSPOSED ? -1.0 : 1.0;
     const double c0r = c_s[0].x, c0i = sg * c_s[0].y;
@@ -181,7 +186,7 @@ __device__ __forceinline__ void poly_real_fast(Tile<NSEG, PY>& A, Tile<NSEG, PY>
                 pre.a[r][q] = k2 * un.a[r][q];
                 s.a[r][q] = TRANSPOSED ? un.a[r][q] : (0.5 * evs.a[r][q]) * un.a[r][q];
             }
-        sweep_t<NSEG, PY, TRANSPOSED>(s, P, strips, xbuf, warp, nwarps, lane);
+        sweep_t<NSEG, PY, TRANSPOSED, WIDE>(s, P, strips, xbuf, warp, nwarps, lane, wc);
         const double cr = c_s[1].x, ci = sg * c_s[1].y;
 #pragma unroll
         for (int r = 0; r < PY; ++r)
@@ -202,7 +207,7 @@ __device__ __forceinline__ void poly_real_fast(Tile<NSEG, PY>& A, Tile<NSEG, PY>
                 pre.a[r][q] = fma(k22, un.a[r][q], uprev.a[r][q]);
                 s.a[r][q] = TRANSPOSED ? un.a[r][q] : evs.a[r][q] * un.a[r][q];
             }
-        sweep_t<NSEG, PY, TRANSPOSED>(s, P, strips, xbuf, warp, nwarps, lane);
+        sweep_t<NSEG, PY, TRANSPOSED, WIDE>(s, P, strips, xbuf, warp, nwarps, lane, wc);
         const double cr = c_s[n].x, ci = sg * c_s[n].y;
 #pragma unroll
         for (int r = 0; r < PY; ++r)

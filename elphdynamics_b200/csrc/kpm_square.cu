@@ -264,6 +264,141 @@ __global__ void __launch_bounds__(MAXT) kpm_square_split_kernel(KsqParams P, int
     stamp();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide variant for 64-wide lattices: the polynomial order falls as 1/(w + 1/2), so one apply waits for the chain of the lowest
+// frequency (2 x 143 dependent sweeps at 64x64xL400) while most SMs idle; a sweep of a 64x64 slice on ONE CTA is bound by that
+// SM's fp64 pipe and shuffle unit (~1700 cycles).  Here a frequency takes a cluster of 2 x STRIPS CTAs: (re | im) x STRIPS row strips
+// of Ly / STRIPS rows.  Per sweep the first / last rows of a strip travel to the neighbouring strips through distributed shared
+// memory and the barrier of the edge exchange becomes the cluster barrier; the B tiles of the (re, im) pair are swapped as in
+// the 2-CTA kernel.  Tanh-form sweeps only (Holstein, uniform hopping per colour).
+// MEASURED (profiles/r2_kpm_wide_summary.md): 175 us against 178 us for the chain of w = 0 at 64x64xL400 -- no gain.  The arithmetic
+// per CTA drops fourfold, but every sweep now waits for a strip-edge round trip through distributed shared memory (~700 cycles
+// whether it is a cluster barrier or tagged words polled by the receiver), and with 2 warps per scheduler the dependent
+// instruction chain of a sweep is not hidden.  Kept behind tuning key 26 (default off) with its parity test; what would help is
+// exchanging k edge rows every k sweeps (redundant halo sweeps), not more CTAs per slice.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NSEG, int PY, int MAXT, int STRIPS>
+__global__ void __launch_bounds__(MAXT) kpm_square_wide_kernel(KsqParams P, int max_order) {
+    constexpr int LX = 32 * NSEG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (P.skip && *P.skip) return;   // all CTAs of a cluster take the same exit (the flag is written before this kernel starts)
+    unsigned int crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const unsigned int part = crank & 1u, strip = crank >> 1;
+    auto cluster_sync = []() {
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int N = LX * P.Ly, rows = P.Ly / STRIPS, Nloc = LX * rows;
+    const int w = P.schedule[blockIdx.x / (2 * STRIPS)];
+    const int order = P.order[w];
+    cplx* c_s = reinterpret_cast<cplx*>(smem_raw);                                            // [max_order]
+    // (the cluster barrier at the top comes after the zeroing of the halo words below in every CTA: moved there)
+    const size_t c_bytes = ((size_t)max_order * sizeof(cplx) + 15) & ~size_t(15);
+    ulonglong2* halo = reinterpret_cast<ulonglong2*>(smem_raw + c_bytes);                     // 2 x [2][LX] tagged words
+    double* strips = reinterpret_cast<double*>(halo + 4 * LX);                                // 2 x [nwarps][2][LX]
+    double* xch = strips + 2ull * nwarps * 2 * LX;                                            // [Nloc] written by the partner CTA
+    for (int k = threadIdx.x; k < 4 * LX; k += blockDim.x) halo[k] = make_ulonglong2(0ull, 0ull);
+    for (int k = threadIdx.x; k < order; k += blockDim.x) c_s[k] = P.coeff[P.coeff_off[w] + k];
+    __syncthreads();
+    cluster_sync();   // halo words are zero and every CTA of the cluster is running before anyone writes into another one's memory
+    const size_t tile_off = (size_t)warp * PY * LX;                  // within the strip
+    const size_t strip_off = (size_t)strip * Nloc;                   // of the strip within the slice
+    Tile<NSEG, PY> v, A, B, ev;
+    const double* in_comp = reinterpret_cast<const double*>(P.in) + part;   // re (even ranks) or im (odd ranks)
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const size_t e = strip_off + tile_off + r * LX + 32 * q + lane;
+            v.a[r][q] = in_comp[2 * ((size_t)w * N + e)];
+            ev.a[r][q] = P.eVbar[e];
+        }
+    __syncthreads();
+    WideCtx wc;
+    wc.up_rank = (((strip + STRIPS - 1) % STRIPS) << 1) | part;
+    wc.dn_rank = (((strip + 1) % STRIPS) << 1) | part;
+    wc.seq = 0ull;
+    wc.halo = halo;
+    const uint32_t my_xch = (uint32_t)__cvta_generic_to_shared(xch);
+    uint32_t remote_xch;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_xch) : "r"(my_xch), "r"(crank ^ 1u));
+    // swap B tiles with the (re | im) partner and combine:  re: A - B_partner ;  im: A + B_partner
+    auto swap_combine = [&](Tile<NSEG, PY>& out) {
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const uint32_t addr = remote_xch + (uint32_t)((tile_off + r * LX + 32 * q + lane) * sizeof(double));
+                asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(B.a[r][q]) : "memory");
+            }
+        cluster_sync();
+#pragma unroll
+        for (int r = 0; r < PY; ++r)
+#pragma unroll
+            for (int q = 0; q < NSEG; ++q) {
+                const double bp = xch[tile_off + r * LX + 32 * q + lane];
+                out.a[r][q] = (part == 0) ? (A.a[r][q] - bp) : (A.a[r][q] + bp);
+            }
+        cluster_sync();   // the partner may overwrite xch again only after both have read
+    };
+    int xbuf = 0;
+    Tile<NSEG, PY> t1, t2;
+    const double sc = 2.0 * P.inv_mag * P.cprod;
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) ev.a[r][q] *= sc;
+    poly_real_fast<NSEG, PY, true, true>(A, B, v, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane, &wc);    // M^-T[w,w]
+    swap_combine(t1);
+    poly_real_fast<NSEG, PY, false, true>(A, B, t1, ev, c_s, order, P, strips, xbuf, warp, nwarps, lane, &wc);  // M^-1[w,w]
+    swap_combine(t2);
+    const int wm = P.L - 1 - w;
+    double* out_comp = reinterpret_cast<double*>(P.out) + part;
+    const double msign = (part == 0) ? 1.0 : -1.0;   // mirror frequency = complex conjugate
+#pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int q = 0; q < NSEG; ++q) {
+            const size_t e = strip_off + tile_off + r * LX + 32 * q + lane;
+            if (wm != w) out_comp[2 * ((size_t)w * N + e)] = t2.a[r][q];
+            out_comp[2 * ((size_t)wm * N + e)] = msign * t2.a[r][q];
+        }
+}
+
+template <int NSEG, int PY, int MAXT, int STRIPS>
+bool launch_ksq_wide(elph_handle* h, const KsqParams& P, int max_order) {
+    constexpr int LX = 32 * NSEG;
+    const int rows = P.Ly / STRIPS, nwarps = rows / PY;
+    if (P.Ly % STRIPS || rows % PY || nwarps < 1 || nwarps * 32 > MAXT) return false;
+    size_t smem = (((size_t)max_order * sizeof(cplx) + 15) & ~size_t(15)) + 4ull * LX * sizeof(ulonglong2) +
+                  2ull * nwarps * 2 * LX * sizeof(double) + (size_t)LX * rows * sizeof(double);
+    if (h->kpm_exclusive) smem = std::max(smem, std::min<size_t>(h->smem_optin, 120 * 1024));   // one chain CTA per SM
+    if (smem > h->smem_optin) return false;
+    auto kern = kpm_square_wide_kernel<NSEG, PY, MAXT, STRIPS>;
+    elph_enable_smem(h, kern);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * STRIPS * h->kpm.nsched);
+    cfg.blockDim = dim3(nwarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * STRIPS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    ELPH_CUDA(cudaLaunchKernelEx(&cfg, kern, P, max_order));
+    h->launches++;
+    return true;
+}
+
 template <int NSEG, int PY, int MAXT, bool TAB = false>
 void launch_ksq_split(elph_handle* h, const KsqParams& P, int nwarps, int max_order) {
     constexpr int LX = 32 * NSEG;
@@ -349,6 +484,8 @@ bool elph_launch_kpm_square(elph_handle* h, const cplx* nu_in, cplx* nu_out, con
     if (const char* e = getenv("ELPH_KPM_EXCL")) h->kpm_exclusive = atoi(e) != 0;
     P.prof = h->pipe_prof ? h->pipe_prof_buf : nullptr;
     P.tab = nullptr;
+    // 64-wide lattices: every frequency on an 8-CTA cluster, (re | im) x 4 row strips (tuning key 26; default off, see below)
+    if (Lx == 64 && h->kpm_split && h->kpm_fast && h->kpm_wide && launch_ksq_wide<2, 2, 512, 4>(h, P, max_order)) return true;
 #define KSQ_CASE(NS, PYV, MAXT)                                    \
     if (Lx == 32 * NS && PY == PYV && nwarps * 32 <= MAXT) {       \
         if (h->kpm_split) launch_ksq_split<NS, PYV, MAXT>(h, P, nwarps, max_order); \

@@ -444,7 +444,9 @@ int32_t elph_set_chunk(elph_handle* h, int32_t slices_per_cta);
  *      right behind update_A! with the polynomials of the previous set-up -- which the hysteresis of setup! keeps unless the
  *      spectral window moved by more than `buf` (src/KPMPreconditioners.jl:296-309) -- while the Arnoldi kernel runs beside it and a
  *      host thread reduces its result; the solve is repeated when the set-up does change the polynomials or the active flag, so
- *      the results are those of the reference order (0 = set-up strictly before the solve) */
+ *      the results are those of the reference order (0 = set-up strictly before the solve),
+ * 26 = KPM chains on 64-wide lattices with every frequency on an 8-CTA cluster, (re | im) x 4 row strips with the strip edges through
+ *      distributed shared memory (default 0: measured no faster than the 2-CTA clusters, see csrc/kpm_square.cu) */
 int32_t elph_set_tuning(elph_handle* h, int32_t key, int32_t value);
 /* read-back of a tuning key; key 100 = which kernel served the last unpreconditioned persistent solve: 0 = none yet /
  * other kernels, else variant * 100 + CTAs per slice * 10 + warps per CTA of the pipelined kernel; key 101 = its time slices per CTA */
