@@ -726,3 +726,29 @@ class ShardedLangevin:
         be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
         self._push_x()
         return self.last_iters
+
+    def evolve_heun(self, eta, g1, g2, arnoldi_noise1=None, arnoldi_noise2=None):
+        """src/LangevinDynamics.jl:272-324 (Heun): xi = sqrt(Q) eta once, both force evaluations Fourier accelerated; returns
+        div(iters1 + iters2, 2) as the reference does (:324)."""
+        be = self.be
+        s2dt = math.sqrt(2.0 * self.dt)
+        xi = self.fourier_accelerate(eta, 0.5)                    # :293
+        self._push_x()                                            # :296
+        dS1 = self.calc_dSdx(g1, arnoldi_noise1)                  # :298
+        it1 = self.last_iters
+        dG1 = self.fourier_accelerate(dS1, 1.0)                   # :301
+        dx = self.empty_field()
+        be.lincomb(dx, s2dt, xi, -self.dt, dG1)                   # :304
+        be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)                # :307
+        self._push_x()                                            # :308
+        dS2 = self.calc_dSdx(g2, arnoldi_noise2)                  # :312
+        it2 = self.last_iters
+        dG2 = self.fourier_accelerate(dS2, 1.0)                   # :315
+        be.lincomb(self.xh, 1.0, self.xh, -1.0, dx)               # :318
+        # x'' = x + sqrt(2 dt) xi - dt (dG + dG') / 2             # :321
+        be.lincomb(dx, 0.5, dG1, 0.5, dG2)
+        be.lincomb(dx, s2dt, xi, -self.dt, dx)
+        be.lincomb(self.xh, 1.0, self.xh, 1.0, dx)
+        self._push_x()                                            # :322
+        return (it1 + it2) // 2
+

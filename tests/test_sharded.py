@@ -162,6 +162,132 @@ class OracleSlabBackend:
         return (a[1:L + 1] * b[1:L + 1]).sum().reshape(1)
 
 
+class OracleSSHSlabBackend:
+    """NumPy slab arithmetic for the SSH model from the oracle's sweeps with per-slice (cosh, sinh) tables (TEST ONLY): what the
+    open-slab SSH kernels compute, for the gloo tests of the host logic (table halo with rows of 2*Ncolumns doubles, field-shaped
+    slabs of Nph columns next to site vectors of Nsites columns)."""
+    is_ssh = True
+
+    def __init__(self, om, tau0, lloc):
+        import torch
+        self.torch = torch
+        self.om, self.tau0, self.lloc, self.N, self.Lg, self.Nph, self.Nb = om, tau0, lloc, om.N, om.L, om.Nph, om.Nbonds
+        self.CS = torch.zeros(lloc + 2, 2 * om.Nbonds, dtype=torch.float64)      # rows of (cosh, sinh) per column, interleaved
+        X = om.x.reshape(om.Nph, om.L).T
+        self.x = torch.from_numpy(np.ascontiguousarray(X[tau0:tau0 + lloc])).clone()
+        self.update_model()
+
+    def empty(self):
+        return self.torch.zeros(self.lloc + 2, self.N, dtype=self.torch.float64)
+
+    def empty_field(self):
+        return self.torch.zeros(self.lloc + 2, self.Nph, dtype=self.torch.float64)
+
+    def D_tensor(self):
+        return self.CS
+
+    def x_tensor(self):
+        return self.x
+
+    def update_model(self):
+        """src/SSHModels.jl:510-540 on the slab's own rows; the halo rows belong to the exchange."""
+        om, L = self.om, self.lloc
+        X = self.x.numpy()                                   # (lloc, Nph)
+        tp = np.repeat(om.t[None, :], L, axis=0)             # (lloc, bond) in the original bond order
+        for ph in range(om.Nph):
+            xt = X[:, ph]
+            tp[:, om.phonon_to_bond[ph]] = om.t[om.phonon_to_bond[ph]] - (om.alpha[ph] * xt + np.sign(xt) * om.alpha2[ph] * xt ** 2)
+        cs = self.CS.numpy()
+        cols = om.checkerboard_perm                          # bond -> column
+        c = np.zeros((L, om.Nbonds))
+        sh = np.zeros((L, om.Nbonds))
+        c[:, cols] = np.cosh(om.dtau * tp)
+        sh[:, cols] = np.sinh(om.dtau * tp)
+        cs[1:L + 1, 0::2] = c
+        cs[1:L + 1, 1::2] = sh
+
+    def _K(self, slices, rows, transpose):
+        """K(t) or K^T(t) applied to slices[k] with the table of halo'd row rows[k]."""
+        cs = self.CS.numpy()
+        Y = np.ascontiguousarray(slices.T)                   # (N, nsl)
+        c = np.ascontiguousarray(cs[rows, 0::2].T)           # (Nb, nsl)
+        sh = np.ascontiguousarray(cs[rows, 1::2].T)
+        f = cb.checkerboard_transpose_mul if transpose else cb.checkerboard_mul
+        f(Y, self.om.neighbor_table, c, sh, self.om.group_offsets)
+        return Y.T
+
+    def _w(self, v, ts):
+        ts = np.asarray(ts)
+        Bv = self._K(self.om.expmu[None, :] * v[ts - 1], ts, False)
+        sign = np.where((self.tau0 + ts - 1) % self.Lg == 0, 1.0, -1.0)[:, None]
+        return v[ts] + sign * Bv
+
+    def matvec(self, mode, v, y):
+        vn, L = v.numpy(), self.lloc
+        own = np.arange(1, L + 1)
+        if mode == 0:
+            out = self._w(vn, own)
+        else:
+            w = vn if mode == 1 else np.zeros_like(vn)
+            if mode == 2:
+                w[1:L + 2] = self._w(vn, np.arange(1, L + 2))
+            u = self._K(w[own + 1], own + 1, True)
+            sign = np.where((self.tau0 + own) % self.Lg == 0, 1.0, -1.0)[:, None]
+            out = w[own] + sign * self.om.expmu[None, :] * u
+        y.numpy()[1:L + 1] = out
+
+    def muldMdx(self, u, v, out, scale=1.0):
+        """src/SSHModels.jl:707-829 on the slab: bond-sequential recurrence, vectorised over the own slices."""
+        om, L, dt = self.om, self.lloc, self.om.dtau
+        un, vn, cs, X = u.numpy(), v.numpy(), self.CS.numpy(), self.x.numpy()
+        own = np.arange(1, L + 1)
+        b = (om.expmu[None, :] * vn[own - 1]).T.copy()       # (N, lloc)
+        c = self._K(un[own], own, True).T.copy()
+        acc = np.zeros((L, om.Nph))
+        flip = ((self.tau0 + own - 1) % self.Lg == 0)
+        for n in range(om.Nbonds):
+            bond = om.inv_checkerboard_perm[n]
+            ph = om.bond_to_phonon[bond]
+            i, j = om.neighbor_table[0, n], om.neighbor_table[1, n]
+            ch, sh = cs[own, 2 * n], cs[own, 2 * n + 1]
+            bi, bj = b[i].copy(), b[j].copy()
+            b[i] = ch * bi + sh * bj
+            b[j] = ch * bj + sh * bi
+            ci, cj = c[i].copy(), c[j].copy()
+            c[i] = ch * ci - sh * cj
+            c[j] = ch * cj - sh * ci
+            if ph >= 0:
+                dK = om.alpha[ph] + 2 * om.alpha2[ph] * X[:, ph]
+                dm = c[j] * dt * dK * b[i] + (c[i] * dt * dK) * b[j]
+                acc[:, ph] += np.where(flip, -dm, dm)
+        out.numpy()[1:L + 1] = scale * acc
+
+    def dSbdx(self, dS, xh, shifted=True):
+        om, L, dt = self.om, self.lloc, self.om.dtau
+        x = xh.numpy()
+        own, up, dn = x[1:L + 1], x[2:L + 2], x[0:L]
+        d = dt * om.omega[None, :] ** 2 * own + dt * 4 * om.omega4[None, :] * own ** 3 - (up + dn - 2.0 * own) / dt
+        dS.numpy()[1:L + 1] += d
+
+    def make_fft_plan(self, Lglob):
+        pass
+
+    def fa_cols(self, vin, vout, diag, power):
+        a = np.fft.fft(vin.numpy().astype(np.complex128), axis=0) * diag.numpy() ** power
+        vout.numpy()[:] = np.real(np.fft.ifft(a, axis=0))
+
+    def lincomb(self, out, a, X, b=0.0, Y=None):
+        L = self.lloc
+        r = a * X[1:L + 1]
+        if Y is not None:
+            r = r + b * Y[1:L + 1]
+        out[1:L + 1] = r
+
+    def dot(self, a, b):
+        L = self.lloc
+        return (a[1:L + 1] * b[1:L + 1]).sum().reshape(1)
+
+
 def _global_reference(om, rng):
     v = rng.normal(size=om.Ndim)
     outs = {}
@@ -362,6 +488,8 @@ def _langevin_reference(om, method, dt, seed=21, precond=False):
     x0 = om.x.copy()
     if method == "euler":
         it = olang.evolve_euler(om, cg, fa, P, dt, eta, g1, an1)
+    elif method == "heun":
+        it = olang.evolve_heun(om, cg, fa, P, dt, eta, g1, g2, an1, an2)
     else:
         it = olang.evolve_rk(om, cg, fa, P, dt, eta, g1, g2, an1, an2)
     x1 = om.x.copy()
@@ -399,6 +527,8 @@ def _check_langevin(make_backend, comm, rank, world, method, device="cpu", Ls=4,
         return t
     if method == "euler":
         it = lang.evolve_euler(slab(eta), slab(g1), an1)
+    elif method == "heun":
+        it = lang.evolve_heun(slab(eta), slab(g1), slab(g2), an1, an2)
     else:
         it = lang.evolve_rk(slab(eta), slab(g1), slab(g2), an1, an2)
     assert abs(it - it_ref) <= 2, (it, it_ref)
@@ -420,7 +550,7 @@ def _cpu_langevin_worker(rank, world, port, method, precond):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,method,precond", [(2, "rk", False), (3, "euler", False), (2, "rk", True)])
+@pytest.mark.parametrize("world,method,precond", [(2, "rk", False), (3, "euler", False), (2, "rk", True), (3, "heun", False)])
 def test_sharded_langevin_host_logic_over_gloo(world, method, precond):
     """Whole tau-sharded Langevin step (halo exchanges, all-reduces, all-to-all transposes around the tau-FFT; with
     ``precond`` the KPM set-ups and preconditioned solves of ShardedKPM) over gloo, NumPy slab backend, against the oracle's
@@ -576,22 +706,26 @@ def _ssh_problem(Ls=4, beta=1.0):
     return om, V, outs, eng(b), eng(x), it, eng(u), np.ascontiguousarray(d.reshape(om.Nph, om.L).T)
 
 
-def _check_ssh_rank(comm, rank, world, Ls=4, beta=1.0):
+def _cuda_ssh_backend(om, tau0, lloc):
+    from elphdynamics_b200.sharded import CudaSlabBackend
+    return CudaSlabBackend(_engine_ssh_slab(om, tau0, lloc), tau0, om.L)
+
+
+def _check_ssh_rank(comm, rank, world, Ls=4, beta=1.0, make_backend=_cuda_ssh_backend, device="cuda"):
     """Products, plain CG and the force <dM/dx> of a tau-sharded SSH lattice (open-slab generic kernels with the per-slice
     (cosh, sinh) table halo) against the oracle's global operator (src/SSHModels.jl:581-701, :745-830)."""
     import torch
-    from elphdynamics_b200.sharded import CudaSlabBackend, ShardedOperator, slab_bounds
+    from elphdynamics_b200.sharded import ShardedOperator, slab_bounds
     om, V, outs, b, x_ref, it_ref, U, d_ref = _ssh_problem(Ls, beta)
     tau0, lloc = slab_bounds(om.L, world, rank)
-    em = _engine_ssh_slab(om, tau0, lloc)
-    be = CudaSlabBackend(em, tau0, om.L)
+    be = make_backend(om, tau0, lloc)
     assert be.is_ssh and be.Nph == om.Nph
     op = ShardedOperator(be, comm, tol=1e-5, maxiter=5000)
     op.update_model()
 
     def slab(a):
         t = be.empty()
-        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).cuda()
+        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).to(device)
         return t
     v, y = slab(V), be.empty()
     for name, fn in (("M", op.mulM), ("MT", op.mulMT), ("MTM", op.mulMTM)):
@@ -605,17 +739,18 @@ def _check_ssh_rank(comm, rank, world, Ls=4, beta=1.0):
     out = be.empty_field()
     be.muldMdx(slab(U), v, out, 1.0)
     assert relerr(out[1:lloc + 1].cpu().numpy(), d_ref[tau0:tau0 + lloc]) <= 1e-9, rank
-    em.close()
+    if hasattr(be, "model"):
+        be.model.close()
 
 
-def _check_ssh_langevin(comm, rank, world, method="rk", Ls=4, beta=1.0):
+def _check_ssh_langevin(comm, rank, world, method="rk", Ls=4, beta=1.0, make_backend=_cuda_ssh_backend, device="cuda"):
     """One Langevin step of a tau-sharded SSH lattice (fields on the bonds: Nph columns in the Fourier acceleration and the
     bosonic gradient, Nsites columns in the solves) against the oracle's global step with identical injected noise."""
     import torch
     from helpers_ssh import oracle_ssh
     from oracle import langevin as olang
     from oracle.fourier import FourierAccelerator
-    from elphdynamics_b200.sharded import CudaSlabBackend, ShardedLangevin, ShardedOperator, slab_bounds
+    from elphdynamics_b200.sharded import ShardedLangevin, ShardedOperator, slab_bounds
     om, rng = oracle_ssh(Lside=Ls, beta=beta, dtau=0.05, seed=11)
     assert np.array_equal(om.primary_field, np.arange(om.Ndof))
     dt = 1e-3
@@ -632,17 +767,16 @@ def _check_ssh_langevin(comm, rank, world, method="rk", Ls=4, beta=1.0):
     engv = lambda a: np.ascontiguousarray(a.reshape(om.N, om.L).T)       # site vectors: [tau][site]
     tau0, lloc = slab_bounds(om.L, world, rank)
     s0, nloc = slab_bounds(om.Nph, world, rank)
-    em = _engine_ssh_slab(om, tau0, lloc)
-    be = CudaSlabBackend(em, tau0, om.L)
+    be = make_backend(om, tau0, lloc)
     be.make_fft_plan(om.L)
     op = ShardedOperator(be, comm, tol=1e-10, maxiter=20000)
-    Qb = torch.from_numpy(np.ascontiguousarray(engf(fa.Q)[:, s0:s0 + nloc])).cuda()
+    Qb = torch.from_numpy(np.ascontiguousarray(engf(fa.Q)[:, s0:s0 + nloc])).to(device)
     lang = ShardedLangevin(op, om.N, om.L, tau0, Qb, dt)
     lang.set_x(engf(x0)[tau0:tau0 + lloc])
 
     def slab(a, field):
         t = be.empty_field() if field else be.empty()
-        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).cuda()
+        t[1:lloc + 1] = torch.from_numpy(a[tau0:tau0 + lloc]).to(device)
         return t
     if method == "euler":
         it = lang.evolve_euler(slab(engf(eta), True), slab(engv(g1), False))
@@ -652,7 +786,33 @@ def _check_ssh_langevin(comm, rank, world, method="rk", Ls=4, beta=1.0):
     assert lang.last_flag == 0
     got = lang.xh[1:lloc + 1].cpu().numpy()
     assert relerr(got - engf(x0)[tau0:tau0 + lloc], engf(x1 - x0)[tau0:tau0 + lloc]) <= 1e-7, (method, rank)
-    em.close()
+    if hasattr(be, "model"):
+        be.model.close()
+
+
+def _cpu_ssh_worker(rank, world, port, what):
+    import torch.distributed as dist
+    from elphdynamics_b200.sharded import RingComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mk = lambda om, t0, ll: OracleSSHSlabBackend(om, t0, ll)
+        if what == "operator":
+            _check_ssh_rank(RingComm(rank, world), rank, world, Ls=4, beta=1.0, make_backend=mk, device="cpu")
+        else:
+            _check_ssh_langevin(RingComm(rank, world), rank, world, what, Ls=4, beta=1.0, make_backend=mk, device="cpu")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,what", [(2, "operator"), (3, "operator"), (2, "rk"), (3, "euler")])
+def test_sharded_ssh_host_logic_over_gloo(world, what):
+    """tau-sharded SSH lattice over gloo with a NumPy slab backend: the (cosh, sinh) table halo (rows of 2*Ncolumns doubles, refreshed
+    after every update_model!), products, CG and force against the oracle's global operator, and a whole Langevin step with
+    field-shaped slabs (Nph columns) next to site vectors."""
+    import torch.multiprocessing as mp
+    mp.spawn(_cpu_ssh_worker, args=(world, _free_port(), what), nprocs=world, join=True)
 
 
 @pytest.mark.gpu
@@ -846,7 +1006,7 @@ def test_sharded_langevin_p2p_single_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,Ls", [("euler", 4), ("rk", 32)])
+@pytest.mark.parametrize("method,Ls", [("euler", 4), ("rk", 32), ("heun", 32)])
 def test_sharded_langevin_single_gpu(method, Ls):
     """world = 1: the whole sharded driver (open-slab kernels, halo self-exchange, FFT plan handle, column FFT, slab
     bosonic gradient) on one GPU against the oracle's global step."""
