@@ -473,17 +473,25 @@ def main():
         for nz in noise:                             # the driver's preallocated noise vectors, page-locked once
             for key in ("eta", "g1", "g2"):
                 em.pin_host(nz[key])
-        E.evolve_(em, dyn, fa, P, **noise[nsteps])   # warm-up
-        t0 = time.perf_counter()
-        for k in range(nsteps):
-            its.append(E.evolve_(em, dyn, fa, P, **noise[k]))   # noise drawn outside the timed region (stays in the driver)
-        dt_l = time.perf_counter() - t0
+        # the timed window is short (5 steps = 16 ms): three repetitions of the SAME five steps (field reset to the start, warm-up
+        # step, then the timed steps), best and all reported -- one host hiccup must not decide the figure
+        x_start = em.x.copy()
+        reps_l = []
+        for rep in range(3):
+            em.x = x_start
+            E.update_model_(em)
+            E.evolve_(em, dyn, fa, P, **noise[nsteps])   # warm-up
+            t0 = time.perf_counter()
+            its = [E.evolve_(em, dyn, fa, P, **noise[k]) for k in range(nsteps)]   # noise drawn outside the timed region
+            reps_l.append(nsteps / (time.perf_counter() - t0))
         for nz in noise:
             for key in ("eta", "g1", "g2"):
                 em.unpin_host(nz[key])
-        extra["langevin_rk_kpm"] = {"steps_per_s": nsteps / dt_l, "pcg_iters_second_solve": its,
+        extra["langevin_rk_kpm"] = {"steps_per_s": max(reps_l), "steps_per_s_repetitions": reps_l, "pcg_iters_second_solve": its,
                                     "note": "elph_langevin_step through the C ABI with host noise buffers (page-locked with "
-                                            "elph_host_register); 2 KPM set-ups + 2 KPM-PCG solves + forces + Fourier acceleration"}
+                                            "elph_host_register); 2 KPM set-ups (speculative: the Arnoldi bounds are computed beside "
+                                            "the solve) + 2 KPM-PCG solves + forces + Fourier acceleration; best of three repetitions "
+                                            "of the same five steps"}
 
         from elphdynamics_b200 import workloads
         # ---- independent Markov chains on ONE GPU (the reference's own scale-out, ElPhDynamics.jl:90-95: one process per
