@@ -280,6 +280,12 @@ __global__ void taumean2_kernel(const double2* __restrict__ tab, double2* __rest
     if (tile_out) tile_out[slot[i]] = out[i];
 }
 
+// SSH set-up from an external tau-mean (tau-sharded lattice): copy of the (cbar, sbar) pairs in the tile layout of ssh_square.cu
+__global__ void csbar_tile_kernel(const double2* __restrict__ in, const int* __restrict__ slot, double2* __restrict__ tile_out, int ncols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncols) tile_out[slot[i]] = in[i];
+}
+
 // arnoldi_eigenvalue_bounds! (src/KPMPreconditioners.jl:845-942) on the device: blockIdx.x = 0 runs the Krylov iteration on A
 // (e_max), 1 on A^-1 (1/e_min).  Output per run: the (n+1) x n Hessenberg matrix (row-major, leading dimension n) and the
 // number of completed steps; the 20 x 20 eigenvalue problem stays on the host.
@@ -742,8 +748,6 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
         arn_stream = K.spec_stream;
     }
     if (phase != 2) {
-    ELPH_REQUIRE(!ext_eVbar || h->model == ELPH_MODEL_HOLSTEIN, ELPH_ERR_UNSUPPORTED,
-                 "KPM set-up from an external tau-mean is implemented for the Holstein model");
     if (h->model == ELPH_MODEL_HOLSTEIN) {
         if (ext_eVbar) {   // tau-sharded lattice: the mean over ALL slices was summed across the ranks by the caller
             ELPH_CUDA(cudaMemcpyAsync(K.d_eVbar, ext_eVbar, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -766,8 +770,14 @@ void elph_kpm_setup_impl(elph_handle* h, const double* noise, elph_kpm_info* inf
     } else {
         if (Nb > 0) {
             if (h->ssq.enabled && !K.d_csbar_tile) K.d_csbar_tile = elph_dalloc<double2>(Nb);
-            taumean2_kernel<<<(Nb + T - 1) / T, T, 0, h->stream>>>(h->d_cs, K.d_csbar, Nb, L, h->ssq.enabled ? h->ssq.d_slot : nullptr,
-                                                                   h->ssq.enabled ? K.d_csbar_tile : nullptr);
+            if (ext_eVbar) {   // tau-sharded SSH lattice: ext = the all-reduced mean of the (cosh, sinh) pairs, [Ncolumns][2]
+                ELPH_CUDA(cudaMemcpyAsync(K.d_csbar, ext_eVbar, Nb * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+                if (h->ssq.enabled)
+                    csbar_tile_kernel<<<(Nb + T - 1) / T, T, 0, h->stream>>>(K.d_csbar, h->ssq.d_slot, K.d_csbar_tile, Nb);
+            } else {
+                taumean2_kernel<<<(Nb + T - 1) / T, T, 0, h->stream>>>(h->d_cs, K.d_csbar, Nb, L, h->ssq.enabled ? h->ssq.d_slot : nullptr,
+                                                                       h->ssq.enabled ? K.d_csbar_tile : nullptr);
+            }
             ELPH_CUDA(cudaGetLastError());
             h->launches++;
         }

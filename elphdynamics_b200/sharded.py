@@ -246,11 +246,13 @@ class CudaSlabBackend:
 
     # ---- KPM preconditioner of the sharded lattice (ShardedKPM): site-sharded FFT stage, omega-sharded chain stage ------
     def kpm_init(self, aux_model, n: int = 20, buf: float = 0.05, c1: float = 1.0, c2: float = 1.0):
-        """``aux_model``: a HolsteinModel of the GLOBAL lattice (all sites, global Ltau, same hoppings) -- it owns the FFT plan
-        of the global time extent, the polynomial coefficients and the chain kernels; its own field is never used."""
-        from .models import SymmetricKPMPreconditioner
+        """``aux_model``: a model of the same kind for the GLOBAL lattice (all sites, global Ltau, same hoppings / couplings) -- it
+        owns the FFT plan of the global time extent, the polynomial coefficients and the chain kernels; its own field is never
+        used."""
+        from .models import SymmetricKPMPreconditioner, update_model_
         assert aux_model.Nsites == self.N
         aux_model.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        update_model_(aux_model)               # SSH: expmu of the handle is what the set-up copies (it has no time index)
         self._kpm_aux = aux_model
         self._kpm_P = SymmetricKPMPreconditioner(aux_model, n, buf, c1, c2)
         self.kpm_L = aux_model.Ltau
@@ -365,9 +367,10 @@ class TauSiteTranspose:
 
 
 class ShardedKPM:
-    """``SymmetricKPMPreconditioner`` (src/KPMPreconditioners.jl:219-481) of a tau-sharded Holstein lattice.
+    """``SymmetricKPMPreconditioner`` (src/KPMPreconditioners.jl:219-481) of a tau-sharded lattice (Holstein or SSH).
 
-    setup!: the tau-mean of expnV (update_A!, :332-350) is a local sum over the slab + one all-reduce of Nsites doubles; the
+    setup!: the tau-mean of expnV (update_A!, :332-350; SSH: of the per-bond (cosh, sinh) pairs, :355-381) is a local sum over the
+    slab's rows of the time-dependent table + one all-reduce; the
     Arnoldi bounds, the hysteresis and the coefficients (:269-321, :781-942) act on Nsites-vectors and are replicated on every
     rank from the same injected start vectors, so every rank holds identical polynomials.
     ldiv! (:426-481) runs on three shardings with an all-to-all between them:

@@ -367,14 +367,15 @@ int32_t elph_dev_fourier_accelerate_cols(elph_handle* h, const double* vin_dev, 
  * Chebyshev recurrences of this rank's frequencies on ALL sites, :606-679) -> back.  These entries act on an auxiliary handle
  * created for the GLOBAL lattice (Nsites, global Ltau, kpm_n > 0): it owns the FFT plan, the coefficients and the chain kernels.
  *   elph_dev_tau_to_omega_cols / elph_dev_omega_to_tau_cols: [tau][col] real <-> [omega][col] complex (interleaved re, im)
- *   elph_dev_kpm_setup_bar: setup!(P) (:269-321) with the tau-mean of expnV supplied by the caller (local sums + all-reduce
- *     replace update_A!, :332-350); Arnoldi bounds, hysteresis and coefficients as elph_kpm_setup.  Holstein model.
+ *   elph_dev_kpm_setup_bar: setup!(P) (:269-321) with the tau-mean supplied by the caller (local sums + all-reduce replace
+ *     update_A!): Holstein: the mean of expnV, [Nsites] (:332-350); SSH: the mean of the (cosh, sinh) pairs, [Ncolumns][2] in the
+ *     order of elph_dev_ptr_cosh_sinh (:355-381).  Arnoldi bounds, hysteresis and coefficients as elph_kpm_setup.
  *   elph_kpm_set_omega_subset: this handle's chain kernels run the frequencies w = first, first + stride, ... < cld(Ltau, 2)
  *   elph_dev_kpm_chains: nu_out[w], nu_out[Ltau-1-w] = conj for every frequency of the subset from nu_in[w]; both buffers are
  *     [Ltau][Nsites] complex indexed by the GLOBAL frequency, rows of other frequencies are left untouched. */
 int32_t elph_dev_tau_to_omega_cols(elph_handle* h, const double* vin_dev, double* nu_dev, int64_t ncols);
 int32_t elph_dev_omega_to_tau_cols(elph_handle* h, const double* nu_dev, double* vout_dev, int64_t ncols);
-int32_t elph_dev_kpm_setup_bar(elph_handle* h, const double* eVbar_dev, const double* arnoldi_noise, elph_kpm_info* info);
+int32_t elph_dev_kpm_setup_bar(elph_handle* h, const double* bar_dev, const double* arnoldi_noise, elph_kpm_info* info);
 int32_t elph_kpm_set_omega_subset(elph_handle* h, int64_t first, int64_t stride);
 int32_t elph_dev_kpm_chains(elph_handle* h, const double* nu_in_dev, double* nu_out_dev);
 /* The same application as ONE call per rank with the transposes through peer memory instead of all-to-alls (csrc/kpm_shard.cu):

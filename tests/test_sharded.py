@@ -31,7 +31,53 @@ def _free_port():
     return port
 
 
-class OracleSlabBackend:
+class _OracleKpmMixin:
+    """KPM pieces of the NumPy slab backends (oracle/kpm.py per frequency, numpy.fft per column)."""
+
+    def kpm_init(self, aux_model=None, n=20, buf=0.05, c1=1.0, c2=1.0):
+        from oracle.kpm import KPMPreconditioner
+        P = KPMPreconditioner(self.om, n, buf, c1, c2)
+        P.update_A = lambda: None                    # the tau-mean comes from the sharded driver (local sums + all-reduce)
+        self._P, self.kpm_L, self._sub = P, self.om.L, (0, 1)
+
+    def kpm_set_subset(self, first, stride):
+        self._sub = (first, stride)
+
+    def kpm_setup_bar(self, bar, noise):
+        if self.om.kind == "ssh":                    # tau-mean of the (cosh, sinh) pairs, [Ncolumns][2]
+            self._P.coshbar[:] = bar.numpy()[0::2]
+            self._P.sinhbar[:] = bar.numpy()[1::2]
+            self._P.expnVbar[:] = self.om.expmu
+        else:
+            self._P.expnVbar[:] = bar.numpy()
+        self._P.setup(noise)
+        return self._P.active, self._P.recomputed
+
+    def kpm_orders(self):
+        return self._P.order.copy()
+
+    def kpm_window(self):
+        return self._P.lam_lo, self._P.lam_hi, self._P.e_min, self._P.e_max
+
+    def tau_to_omega_cols(self, cols):
+        L = self.Lg
+        theta = np.exp(-1j * np.pi * np.arange(L) / L)
+        return self.torch.from_numpy(np.fft.fft(theta[:, None] * cols.numpy(), axis=0))
+
+    def omega_to_tau_cols(self, nu):
+        L = self.Lg
+        theta = np.exp(-1j * np.pi * np.arange(L) / L)
+        return self.torch.from_numpy(np.real(np.conj(theta)[:, None] * np.fft.ifft(nu.numpy(), axis=0)))
+
+    def kpm_chains(self, nu_in, nu_out):
+        L, (first, stride) = self.Lg, self._sub
+        a, o = nu_in.numpy(), nu_out.numpy()
+        for w in range(first, self._P.Lo2, stride):
+            o[w] = self._P.mul_block(w, a[w])
+            o[L - 1 - w] = np.conj(o[w])
+
+
+class OracleSlabBackend(_OracleKpmMixin):
     """NumPy slab arithmetic from the oracle's checkerboard sweeps (TEST ONLY; the package has no CPU backend)."""
 
     def __init__(self, om, tau0, lloc):
@@ -85,44 +131,6 @@ class OracleSlabBackend:
         a = np.fft.fft(vin.numpy().astype(np.complex128), axis=0) * diag.numpy() ** power
         vout.numpy()[:] = np.real(np.fft.ifft(a, axis=0))
 
-    # ---- KPM pieces (oracle/kpm.py per frequency, numpy.fft per column) -----------------------------------------------
-    def kpm_init(self, aux_model=None, n=20, buf=0.05, c1=1.0, c2=1.0):
-        from oracle.kpm import KPMPreconditioner
-        P = KPMPreconditioner(self.om, n, buf, c1, c2)
-        P.update_A = lambda: None                    # the tau-mean comes from the sharded driver (local sums + all-reduce)
-        self._P, self.kpm_L, self._sub = P, self.om.L, (0, 1)
-
-    def kpm_set_subset(self, first, stride):
-        self._sub = (first, stride)
-
-    def kpm_setup_bar(self, eVbar, noise):
-        self._P.expnVbar[:] = eVbar.numpy()
-        self._P.setup(noise)
-        return self._P.active, self._P.recomputed
-
-    def kpm_orders(self):
-        return self._P.order.copy()
-
-    def kpm_window(self):
-        return self._P.lam_lo, self._P.lam_hi, self._P.e_min, self._P.e_max
-
-    def tau_to_omega_cols(self, cols):
-        L = self.Lg
-        theta = np.exp(-1j * np.pi * np.arange(L) / L)
-        return self.torch.from_numpy(np.fft.fft(theta[:, None] * cols.numpy(), axis=0))
-
-    def omega_to_tau_cols(self, nu):
-        L = self.Lg
-        theta = np.exp(-1j * np.pi * np.arange(L) / L)
-        return self.torch.from_numpy(np.real(np.conj(theta)[:, None] * np.fft.ifft(nu.numpy(), axis=0)))
-
-    def kpm_chains(self, nu_in, nu_out):
-        L, (first, stride) = self.Lg, self._sub
-        a, o = nu_in.numpy(), nu_out.numpy()
-        for w in range(first, self._P.Lo2, stride):
-            o[w] = self._P.mul_block(w, a[w])
-            o[L - 1 - w] = np.conj(o[w])
-
     def _K(self, slices, transpose):
         Y = np.ascontiguousarray(slices.T)           # (N, nsl)
         f = cb.checkerboard_transpose_mul if transpose else cb.checkerboard_mul
@@ -162,7 +170,7 @@ class OracleSlabBackend:
         return (a[1:L + 1] * b[1:L + 1]).sum().reshape(1)
 
 
-class OracleSSHSlabBackend:
+class OracleSSHSlabBackend(_OracleKpmMixin):
     """NumPy slab arithmetic for the SSH model from the oracle's sweeps with per-slice (cosh, sinh) tables (TEST ONLY): what the
     open-slab SSH kernels compute, for the gloo tests of the host logic (table halo with rows of 2*Ncolumns doubles, field-shaped
     slabs of Nph columns next to site vectors of Nsites columns)."""
@@ -367,11 +375,15 @@ def test_sharded_host_logic_over_gloo(world):
 
 
 # ---------------------------------------------------------------- KPM-preconditioned solve of the sharded lattice
-def _pcg_problem(Ls=4, beta=2.1, seed=7):
+def _pcg_problem(Ls=4, beta=2.1, seed=7, kind="holstein"):
     """Global oracle: setup!(P), one application z = P^-1 r, and ldiv!(x, model, b, P) (src/Models.jl:74-137)."""
     from oracle.kpm import KPMPreconditioner
     from oracle.solvers import ldiv
-    om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-0.5, seed=seed)
+    if kind == "ssh":
+        from helpers_ssh import oracle_ssh
+        om, rng = oracle_ssh(Lside=Ls, beta=beta, dtau=0.05, seed=seed)
+    else:
+        om, rng = oracle_holstein("square", Ls, beta, 0.1, mu=-0.5, seed=seed)
     noise = rng.normal(size=2 * om.N)
     P = KPMPreconditioner(om, n=min(20, om.N))
     P.setup(noise)
@@ -390,10 +402,10 @@ def _pcg_problem(Ls=4, beta=2.1, seed=7):
     return om, noise, P, eng(r), eng(z), eng(b), eng(x), it
 
 
-def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, aux=None, p2p=False, fused=False):
+def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, aux=None, p2p=False, fused=False, kind="holstein"):
     import torch
     from elphdynamics_b200.sharded import ShardedKPM, ShardedOperator, slab_bounds
-    om, noise, Pref, r, z_ref, b, x_ref, it_ref = _pcg_problem(Ls, beta)
+    om, noise, Pref, r, z_ref, b, x_ref, it_ref = _pcg_problem(Ls, beta, kind=kind)
     tau0, lloc = slab_bounds(om.L, world, rank)
     be = make_backend(om, tau0, lloc)
     be.kpm_init(aux(om) if aux else None, n=min(20, om.N))
@@ -450,16 +462,25 @@ def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, au
     return be
 
 
-def _cpu_pcg_worker(rank, world, port, Ls, beta):
+def _cpu_pcg_worker(rank, world, port, Ls, beta, kind="holstein"):
     import torch.distributed as dist
     from elphdynamics_b200.sharded import RingComm
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        _check_pcg(lambda om, t0, ll: OracleSlabBackend(om, t0, ll), RingComm(rank, world), rank, world, Ls=Ls, beta=beta)
+        cls = OracleSSHSlabBackend if kind == "ssh" else OracleSlabBackend
+        _check_pcg(lambda om, t0, ll: cls(om, t0, ll), RingComm(rank, world), rank, world, Ls=Ls, beta=beta, kind=kind)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ssh_kpm_pcg_host_logic_over_gloo(world):
+    """ShardedKPM on a tau-sharded SSH lattice over gloo: the tau-mean of the (cosh, sinh) table by local sums + all-reduce
+    (update_A!, src/KPMPreconditioners.jl:355-381), the omega-sharded application and the preconditioned solve against the oracle."""
+    import torch.multiprocessing as mp
+    mp.spawn(_cpu_pcg_worker, args=(world, _free_port(), 4, 1.05, "ssh"), nprocs=world, join=True)
 
 
 @pytest.mark.parametrize("world,Ls,beta", [(2, 4, 2.1), (3, 4, 2.1), (3, 4, 0.4)])
@@ -894,6 +915,9 @@ def _gpu_worker(rank, world, port):
         dist.barrier()
         _check_ssh_langevin(RingComm(rank, world), rank, world, "rk", Ls=32, beta=0.5)
         dist.barrier()
+        _check_pcg(_cuda_ssh_backend, RingComm(rank, world), rank, world, device="cuda", Ls=32, beta=1.05, aux=_engine_ssh_global,
+                   fused=True, kind="ssh")
+        dist.barrier()
         # KPM-preconditioned solve: omega-sharded application through NCCL all-to-alls, products with the halo through NCCL and
         # (second pass) through peer memory inside the product kernel
         for p2p, fused, beta in ((False, False, 2.0), (True, False, 2.0), (True, True, 2.0), (True, True, 2.1), (False, True, 0.5)):
@@ -989,6 +1013,20 @@ def test_sharded_kpm_fused_single_gpu(Ls, beta):
     copy-in, pulling forward FFT, gather, chains, pulling inverse FFT, gather, four barrier kernels) against the oracle."""
     from elphdynamics_b200.sharded import RingComm
     _check_pcg(_cuda_backend, RingComm(0, 1), 0, 1, device="cuda", Ls=Ls, beta=beta, aux=_engine_global, fused=True)
+
+
+def _engine_ssh_global(om):
+    return _engine_ssh_slab(om, 0, om.L)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,beta,fused", [(4, 1.05, False), (32, 1.0, False), (32, 1.05, True)])
+def test_sharded_ssh_kpm_pcg_single_gpu(Ls, beta, fused):
+    """world = 1: ShardedKPM on SSH slabs (set-up from the supplied mean of the (cosh, sinh) table, chain kernels with per-bond
+    tables -- generic at 4x4, register tiles at 32x32; odd Ltau at beta = 1.05) and the preconditioned solve against the oracle."""
+    from elphdynamics_b200.sharded import RingComm
+    _check_pcg(_cuda_ssh_backend, RingComm(0, 1), 0, 1, device="cuda", Ls=Ls, beta=beta, aux=_engine_ssh_global, fused=fused,
+               kind="ssh")
 
 
 @pytest.mark.gpu
