@@ -424,8 +424,11 @@ def _check_pcg(make_backend, comm, rank, world, device="cpu", Ls=4, beta=2.1, au
     # 20 Arnoldi steps amplify last-bit differences of the Gram-Schmidt sums (1e-9 in the bounds): compare the bounds at 1e-6 as
     # the single-GPU tests do, then evaluate the oracle's polynomials on the engine's window for the 1e-11 comparison
     lo, hi, e_min, e_max = be.kpm_window()
-    # (SSH: 20 Krylov steps leave the extreme Ritz values of the narrow, nearly degenerate spectrum unconverged, and they move with
-    # the summation order of the tau-mean; the single-GPU SSH tests compare orders and iteration counts only)
+    # (SSH at weak coupling: A is close to translation invariant, the spectrum is nearly degenerate and 20 Krylov steps run into
+    # the noise floor of the orthogonalisation, so the extreme Ritz values depend on its rounding: measured 1e-4 .. 5e-4 between
+    # the engine's two-pass classical Gram-Schmidt and the oracle's modified Gram-Schmidt at 32x32 -- identical to 13 digits between
+    # the sharded set-up and the single-GPU engine.  The bounds only enter through a 5 % buffer, a hysteresis and floor() of the
+    # orders, which are compared exactly above.)
     btol = 1e-6 if kind == "holstein" else 1e-3
     assert abs(e_min - Pref.e_min) <= btol * Pref.e_min and abs(e_max - Pref.e_max) <= btol * Pref.e_max, (e_min, Pref.e_min, e_max, Pref.e_max)
     assert abs(lo - Pref.lam_lo) <= btol * Pref.lam_lo and abs(hi - Pref.lam_hi) <= btol * Pref.lam_hi
